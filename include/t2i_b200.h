@@ -1,0 +1,203 @@
+/* t2i_b200 -- C ABI of the B200-native wgancls hot path.
+ *
+ * The reference (crisbodnar/text-to-image) has no FFI: its hot path is Python calling
+ * TensorFlow-1.4 library ops.  Each entry point below replaces the TF op(s) behind one reference
+ * call site (cited per function, paths relative to the reference root).  The binding a
+ * maintainer adds is a ctypes stub; text-to-image_b200/_lib.py is that stub.
+ *
+ * Conventions
+ *  - Every pointer is a DEVICE pointer owned by the caller (PyTorch tensors in our host code);
+ *    the library never allocates or frees user-visible memory.
+ *  - All work is enqueued on the caller's `stream` (a cudaStream_t passed as void*); no internal
+ *    synchronisation, CUDA-graph capturable.
+ *  - Return 0 on success, a negative t2i_status otherwise; t2i_last_error() gives the text.
+ *    Nothing throws or aborts across the ABI.  There is no CPU fallback.
+ *  - Activations are NHWC "bf16 planes": np = 1 -> one bf16 tensor (throughput mode);
+ *    np = 2 -> value = hi + lo, two bf16 tensors plane_stride elements apart (parity mode: every
+ *    tensor-core product is expanded into hi*hi + lo*hi + hi*lo, ~2^-17 relative error).
+ */
+#ifndef T2I_B200_H
+#define T2I_B200_H
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef enum {
+    T2I_OK = 0,
+    T2I_ERR_BAD_ARG = -1,     /* shape / alignment / unsupported configuration */
+    T2I_ERR_CUDA = -2,        /* a CUDA runtime or driver call failed          */
+    T2I_ERR_UNSUPPORTED = -3  /* device is not sm_100                          */
+} t2i_status;
+
+enum { T2I_CONV_S1 = 0, T2I_CONV_K4S2 = 1, T2I_DECONV_K4S2 = 2 };
+enum { T2I_ACT_NONE = 0, T2I_ACT_LRELU = 1, T2I_ACT_RELU = 2 };
+enum { T2I_MASK_NONE = 0, T2I_MASK_LRELU = 1, T2I_MASK_RELU = 2 };
+
+/* View of an NHWC activation tensor stored as bf16 planes. */
+typedef struct {
+    void* ptr;              /* plane 0, element (n=0,h=0,w=0,channel 0 of the buffer)            */
+    long long plane_stride; /* elements between plane 0 and plane 1 (ignored when np == 1)      */
+    int n, h, w, c;         /* logical extent of the view; c = channels in the window           */
+    int pitch;              /* channels per pixel in memory (>= coff + c, multiple of 8)        */
+    int coff;               /* first channel of the window inside the pixel (multiple of 8)     */
+} t2i_act;
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, accumulators in TMEM):
+ *   y = act( conv(x, w) + bias + add ) * mask'(mask)
+ * mode T2I_CONV_S1   : k x k (k = 1 or 3) stride 1, SAME.  flip = 1 correlates with the taps
+ *                      mirrored (input-gradient of a k3 conv).  A dense layer is k = 1, h = w = 1.
+ * mode T2I_CONV_K4S2 : 4x4 stride 2 SAME (y is h/2 x w/2); also the input-gradient of a deconv.
+ * mode T2I_DECONV_K4S2: 4x4 stride 2 SAME transposed conv as four 2x2 sub-pixel phases
+ *                      (y is 2h x 2w); also the input-gradient of a 4x4/s2 conv.
+ * w: packed bf16 planes [np][taps][w_cout][w_cin], contraction (w_cin) contiguous, tap = kh*k+kw.
+ * Replaces Conv2D/Conv2DBackpropInput/MatMul + BiasAdd + LeakyRelu behind utils/ops.py:61,69,87
+ * (called from models/wgancls/model.py:135-160,174-219) and their tf.gradients counterparts.
+ */
+typedef struct {
+    int mode, k, flip, np;
+    t2i_act x;
+    const void* w;
+    long long w_plane_stride;
+    int w_cout, w_cin;
+    t2i_act y;
+    const float* bias; /* [y.c] or NULL */
+    t2i_act add;       /* ptr NULL = none; same pixel grid as y */
+    t2i_act mask;      /* ptr NULL = none; same pixel grid as y */
+    int act, mask_kind;
+} t2i_conv_gemm_desc;
+int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
+
+/* Weight gradient of the same three conv forms on tcgen05 (both operands MN-major, contraction
+ * over pixels, split-K with fp32 atomic accumulation into dw, which the caller zeroes):
+ *   dw[tap][co][ci] += sum_pixels dy[pixel][co] * x[pixel shifted by tap][ci]
+ * x: the layer's forward input (or its tangent for the gradient-penalty second-order term),
+ * dy: gradient at the layer's output.  Replaces Conv2DBackpropFilter / MatMul(grad) reached
+ * through tf.train.AdamOptimizer.minimize at models/wgancls/model.py:94-106.
+ */
+typedef struct {
+    int mode, k, np;
+    t2i_act x, dy;
+    float* dw; /* fp32 [taps][cout][cin] */
+    int cout, cin;
+    int split_k; /* 0 = choose */
+} t2i_wgrad_desc;
+int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream);
+
+/* ---- HBM-bound kernels (elementwise.cu); see each definition for the reference lines ---- */
+
+/* fp32 -> bf16 planes, optional per-row scale (rows x cols, row-major). */
+int t2i_to_planes(const float* src, void* dst, long long plane_stride, int np, long long rows, int cols,
+                  const float* row_scale, void* stream);
+/* bf16 planes -> fp32 */
+int t2i_from_planes(const void* src, long long plane_stride, int np, float* dst, long long n, void* stream);
+
+/* 3-channel image <-> 4x4/s2 patch matrix [n*(h/2)*(w/2), 64] (col = (kh*4+kw)*3 + c, 48 used).
+ * im2col feeds d_net's first conv (model.py:135) and the input-gradient of g_net's last deconv
+ * (model.py:218); col2im is their transpose. */
+int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sample_scale, void* col,
+                       long long plane_stride, int np, void* stream);
+int t2i_col2im_k4s2_c3(const void* col, long long plane_stride, int np, int n, int h, int w,
+                       const float* bias3, float* img, void* stream);
+
+/* g_net's last conv 3->3 k3 s1 + tanh (model.py:219-221), direct; and its backward
+ * (dw, db, dx_sum are accumulated: dx_sum[c] += sum of dx over pixels = bias gradient of the
+ * preceding transposed conv; may be NULL). */
+int t2i_conv3x3_c3_tanh_fwd(const float* x, const float* w, const float* b, float* y, int n, int h, int wd,
+                            void* stream);
+int t2i_conv3x3_c3_tanh_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
+                            float* dw, float* db, float* dx_sum, int n, int h, int wd, void* stream);
+
+/* per-channel sum over rows [row_begin,row_end) of a [rows, pitch] planes tensor -> out[c] (+=) */
+int t2i_colsum(const void* src, long long plane_stride, int np, long long rows, int c, int pitch, int coff,
+               float* out, void* stream);
+
+/* Training-mode batch norm (utils/ops.py:7-29 via model.py:176-216): statistics, apply, backward. */
+int t2i_bn_stats(const void* x, long long plane_stride, int np, long long rows, int c, float* mean,
+                 float* rstd, float* var, float eps, void* stream);
+int t2i_bn_apply(const void* x, long long x_ps, const float* mean, const float* rstd, const float* gamma,
+                 const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
+                 long long rows, int c, int relu, void* stream);
+int t2i_bn_bwd_reduce(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
+                      const float* rstd, int np, long long rows, int c, float* dgamma, float* dbeta,
+                      void* stream);
+int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
+                     const float* rstd, const float* gamma, const float* dgamma, const float* dbeta, void* dx,
+                     long long dx_ps, int np, long long rows, int c, void* stream);
+int t2i_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var,
+                         long long rows, int c, float decay, void* stream);
+/* dst = dy * act'(y)  (relu / lrelu masks on post-activation values) */
+int t2i_act_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, void* dst, long long dst_ps,
+                int np, long long n, int mask_kind, void* stream);
+
+/* d_net embedding path (model.py:150-155): tile [s,c] -> channels [coff,coff+c) of [s,4,4,pitch];
+ * reduce sums the 16 positions back. */
+int t2i_embed_tile(const void* e, long long e_ps, void* cat, long long cat_ps, int np, int s, int c, int pitch,
+                   int coff, int hw, void* stream);
+int t2i_embed_reduce(const void* dcat, long long dcat_ps, void* de, long long de_ps, int np, int s, int c,
+                     int pitch, int coff, int hw, void* stream);
+
+/* d_net output conv 4x4/s4 VALID 1024->1 (model.py:160) as a per-sample dot product. */
+int t2i_dout_fwd(const void* a, long long a_ps, int np, const float* w, const float* b, float* logit, int s,
+                 int k, void* stream);
+/* da = seed[s] * w * lrelu'(a);  dw += sum_s seed[s] * a_or_tangent[s];  db += sum seed[0..s_bias) */
+int t2i_dout_bwd_data(const void* a, long long a_ps, int np, const float* w, const float* seed, void* da,
+                      long long da_ps, int s, int k, void* stream);
+int t2i_dout_bwd_weight(const void* a, long long a_ps, int np, const float* seed, float* dw, float* db,
+                        int s, int s_bias, int k, void* stream);
+
+/* x_hat = eps*G + (1-eps)*x (model.py:53) */
+int t2i_gp_interp(const float* g, const float* x, const float* eps, float* xhat, int n, int per_sample,
+                  void* stream);
+/* slopes / one-sided penalty / second-order seed coefficient (model.py:62-70,88-91):
+ *   slope[b] = ||grad[b,:]||_2 ; *pen_sum += sum_b max(0,slope-1)^2 ;
+ *   coef[b] = weight * 2 * max(0,slope-1) / slope * inv_global_batch     (0 when slope <= 1) */
+int t2i_gp_penalty(const float* grad, int n, int per_sample, float weight, float inv_global_batch,
+                   float* slope, float* coef, float* pen_sum, void* stream);
+
+/* conditioning augmentation (model.py:108-127): ms = [mean | log_sigma] (post-LeakyReLU) [b,2*ce].
+ * fwd: zc[b, z_dim + j] = mean + exp(log_sigma) * tn_eps ; zc[b, :z_dim] = z ; *kl_sum += KL terms.
+ * bwd: dms = lrelu'(ms) * ( [dc | dc*eps*exp(ls)] + kl_scale * [mean | exp(2 ls) - 1] ),
+ *      kl_scale = kl_coeff / (global_batch * ce). */
+int t2i_ca_fwd(const void* ms, long long ms_ps, const float* z, const float* tn_eps, void* zc, long long zc_ps,
+               int np, int b, int z_dim, int ce, float* kl_sum, void* stream);
+int t2i_ca_bwd(const void* ms, long long ms_ps, const void* dzc, long long dzc_ps, const float* tn_eps,
+               void* dms, long long dms_ps, int np, int b, int z_dim, int ce, float kl_scale, void* stream);
+
+/* Scalars of the two runs (model.py:79-92,100).  The per-rank sums live at the tail of the flat
+ * gradient buffer so that the single NCCL allreduce of the step also reduces them.
+ *   d sums: [0] sum Dg, [1] sum Dx, [2] sum Dxmi, [3] sum Dxmi^2, [4] sum pen(x_hat), [5] sum pen(cond)
+ *   g sums: [0] sum Dg, [1] sum KL terms
+ * t2i_d_seeds writes the per-sample backward seeds of the 4 segments [fake|real|mismatch|x_hat]:
+ *   1/B, -(1+kt)/B, kt/B, 1  (B = global batch).  t2i_d_scalars also applies kt -= kt_lr * dkt. */
+enum {
+    T2I_S_D_LOSS = 0, T2I_S_D_LOSS_REAL, T2I_S_D_LOSS_FAKE, T2I_S_D_LOSS_MISMATCH, T2I_S_WDIST, T2I_S_WDIST2,
+    T2I_S_REG_LOSS, T2I_S_BALANCE_LOSS, T2I_S_REAL_GP, T2I_S_REAL_GP2, T2I_S_KT, T2I_S_KT_GRAD,
+    T2I_S_G_LOSS, T2I_S_G_KL_LOSS, T2I_S_COUNT = 16
+};
+int t2i_d_seeds(const float* kt, float* seed, int b, float inv_global_batch, void* stream);
+int t2i_d_sums(const float* logit, int b, float* sums, void* stream);
+int t2i_d_scalars(const float* sums, float* kt, float* scalars, int global_batch, float gp_weight, float kt_lr,
+                  void* stream);
+int t2i_g_sums(const float* logit_fake, int b, float* sums, void* stream);
+int t2i_g_scalars(const float* sums, float* scalars, int global_batch, int ce, float kl_coeff, void* stream);
+
+/* weights: fp32 master [taps][cout][cin] -> bf16 planes in both contraction orders
+ * (fwd [taps][cout][cin], bwd [taps][cin][cout]); either destination may be NULL. */
+int t2i_pack_weight(const float* w, int taps, int cout, int cin, void* fwd, long long fwd_ps, void* bwd,
+                    long long bwd_ps, int np, void* stream);
+
+/* TF-form Adam on a flat fp32 buffer (tf.train.AdamOptimizer at model.py:94-96,103-105):
+ * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; theta -= lr_t m / (sqrt(v) + eps),
+ * lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller.  grad_scale multiplies g first. */
+int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, float lr_t, float beta1,
+                float beta2, float eps, float grad_scale, void* stream);
+
+const char* t2i_last_error(void);
+int t2i_version(void);
+/* number of kernels this library has launched in this process (bench.py's gpu_launches) */
+long long t2i_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,924 @@
+// HBM-bound kernels of the wgancls step: coalesced 16-byte vector loads/stores, warp-shuffle and
+// shared-memory reductions, fp32 arithmetic on bf16-plane storage.  Each C entry point cites the
+// reference lines (relative to the reference root) whose TF ops it replaces.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace t2i {
+
+typedef __nv_bfloat16 bf16;
+
+// ---- bf16 planes: 8 consecutive values (16 bytes per plane) --------------------------------
+__device__ __forceinline__ void unpack8(const uint4 u, float* v) {
+    v[0] = bf16_lo(u.x); v[1] = bf16_hi(u.x); v[2] = bf16_lo(u.y); v[3] = bf16_hi(u.y);
+    v[4] = bf16_lo(u.z); v[5] = bf16_hi(u.z); v[6] = bf16_lo(u.w); v[7] = bf16_hi(u.w);
+}
+__device__ __forceinline__ void load8(const bf16* p, long long ps, int np, float* v) {
+    unpack8(*reinterpret_cast<const uint4*>(p), v);
+    if (np == 2) {
+        float l[8];
+        unpack8(*reinterpret_cast<const uint4*>(p + ps), l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += l[j];
+    }
+}
+__device__ __forceinline__ void store8(bf16* p, long long ps, int np, const float* v) {
+    uint4 hi;
+    hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+    hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+    *reinterpret_cast<uint4*>(p) = hi;
+    if (np == 2) {
+        float h[8];
+        unpack8(hi, h);
+        uint4 lo;
+        lo.x = pack_bf16x2(v[0] - h[0], v[1] - h[1]); lo.y = pack_bf16x2(v[2] - h[2], v[3] - h[3]);
+        lo.z = pack_bf16x2(v[4] - h[4], v[5] - h[5]); lo.w = pack_bf16x2(v[6] - h[6], v[7] - h[7]);
+        *reinterpret_cast<uint4*>(p + ps) = lo;
+    }
+}
+__device__ __forceinline__ float load1(const bf16* p, long long ps, int np) {
+    float v = __bfloat162float(p[0]);
+    if (np == 2) v += __bfloat162float(p[ps]);
+    return v;
+}
+__device__ __forceinline__ void store1(bf16* p, long long ps, int np, float v) {
+    const bf16 h = __float2bfloat16_rn(v);
+    p[0] = h;
+    if (np == 2) p[ps] = __float2bfloat16_rn(v - __bfloat162float(h));
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+// block-wide sum of one float per thread; result valid in thread 0
+__device__ __forceinline__ float block_sum(float v, float* sh) {
+    v = warp_sum(v);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    __syncthreads();
+    if (lane == 0) sh[warp] = v;
+    __syncthreads();
+    float r = 0.f;
+    if (warp == 0) {
+        r = (lane < (int)(blockDim.x >> 5)) ? sh[lane] : 0.f;
+        r = warp_sum(r);
+    }
+    return r;
+}
+
+static inline int grid_for(long long work_items, int threads, int max_blocks_per_sm = 8) {
+    long long b = (work_items + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * max_blocks_per_sm;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+// ------------------------------------------------------------------------------------------
+// fp32 <-> planes
+__global__ void to_planes_kernel(const float* __restrict__ src, bf16* dst, long long ps, int np, long long rows,
+                                 int cols, const float* __restrict__ row_scale) {
+    const long long n8 = rows * cols / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        const long long e = i * 8;
+        const float4 a = *reinterpret_cast<const float4*>(src + e);
+        const float4 b = *reinterpret_cast<const float4*>(src + e + 4);
+        float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+        if (row_scale != nullptr) {
+            const float s = row_scale[e / cols];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] *= s;
+        }
+        store8(dst + e, ps, np, v);
+    }
+}
+__global__ void from_planes_kernel(const bf16* __restrict__ src, long long ps, int np, float* dst, long long n) {
+    const long long n8 = n / 8;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        load8(src + i * 8, ps, np, v);
+        *reinterpret_cast<float4*>(dst + i * 8) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4*>(dst + i * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// 3-channel 4x4/s2 patch matrix.  Row r = (n, p, q) of the (h/2 x w/2) grid, column
+// (kh*4 + kw)*3 + c holds img[n, 2p-1+kh, 2q-1+kw, c] (zero outside); columns 48..63 are zero.
+__global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, int n, int h, int w,
+                                      const float* __restrict__ sample_scale, bf16* col, long long ps, int np) {
+    const int hp = h / 2, wq = w / 2;
+    const long long rows = (long long)n * hp * wq;
+    // one thread per (row, kh): 12 values = columns [kh*12, kh*12+12); kh == 4 -> zero tail
+    const long long items = rows * 5;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i / 5;
+        const int kh = (int)(i % 5);
+        bf16* dst = col + r * 64;
+        if (kh == 4) {
+            for (int j = 48; j < 64; ++j) store1(dst + j, ps, np, 0.f);
+            continue;
+        }
+        const int q = (int)(r % wq);
+        const int p = (int)((r / wq) % hp);
+        const int b = (int)(r / ((long long)wq * hp));
+        const float s = sample_scale ? sample_scale[b] : 1.f;
+        const int ih = 2 * p - 1 + kh;
+        for (int kw = 0; kw < 4; ++kw) {
+            const int iw = 2 * q - 1 + kw;
+            const bool in = (ih >= 0 && ih < h && iw >= 0 && iw < w);
+            const float* src = img + (((long long)b * h + ih) * w + iw) * 3;
+            for (int c = 0; c < 3; ++c) store1(dst + (kh * 4 + kw) * 3 + c, ps, np, in ? src[c] * s : 0.f);
+        }
+    }
+}
+// transpose of the above: img[n, oh, ow, c] = bias[c] + sum over (kh,kw) col[(n,p,q), (kh*4+kw)*3+c]
+// with oh = 2p-1+kh, ow = 2q-1+kw.
+__global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps, int np, int n, int h, int w,
+                                      const float* __restrict__ bias3, float* img) {
+    const int hp = h / 2, wq = w / 2;
+    const long long pixels = (long long)n * h * w;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(i % w);
+        const int oh = (int)((i / w) % h);
+        const int b = (int)(i / ((long long)w * h));
+        float acc[3] = {0.f, 0.f, 0.f};
+        if (bias3) { acc[0] = bias3[0]; acc[1] = bias3[1]; acc[2] = bias3[2]; }
+        for (int kh = (oh + 1) & 1; kh < 4; kh += 2) {
+            const int p = (oh + 1 - kh) / 2;
+            if (p < 0 || p >= hp) continue;
+            for (int kw = (ow + 1) & 1; kw < 4; kw += 2) {
+                const int q = (ow + 1 - kw) / 2;
+                if (q < 0 || q >= wq) continue;
+                const bf16* src = col + (((long long)b * hp + p) * wq + q) * 64 + (kh * 4 + kw) * 3;
+                for (int c = 0; c < 3; ++c) acc[c] += load1(src + c, ps, np);
+            }
+        }
+        float* dst = img + i * 3;
+        dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2];
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// g_net's last conv: 3 -> 3 channels, 3x3 stride 1 SAME, then tanh.  w is TF HWIO [3][3][3][3].
+__global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                           const float* __restrict__ b, float* y, int n, int h, int wd) {
+    __shared__ float sw[81 + 3];
+    if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
+    if (threadIdx.x < 3) sw[81 + threadIdx.x] = b[threadIdx.x];
+    __syncthreads();
+    const long long pixels = (long long)n * h * wd;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(i % wd);
+        const int oh = (int)((i / wd) % h);
+        const long long base = i - (long long)oh * wd - ow;  // pixel index of (b, 0, 0)
+        float acc[3] = {sw[81], sw[82], sw[83]};
+        for (int kh = 0; kh < 3; ++kh) {
+            const int ih = oh + kh - 1;
+            if (ih < 0 || ih >= h) continue;
+            for (int kw = 0; kw < 3; ++kw) {
+                const int iw = ow + kw - 1;
+                if (iw < 0 || iw >= wd) continue;
+                const float* xp = x + (base + (long long)ih * wd + iw) * 3;
+                const float* wp = sw + (kh * 3 + kw) * 9;
+#pragma unroll
+                for (int ci = 0; ci < 3; ++ci) {
+                    const float xv = xp[ci];
+                    acc[0] += xv * wp[ci * 3 + 0];
+                    acc[1] += xv * wp[ci * 3 + 1];
+                    acc[2] += xv * wp[ci * 3 + 2];
+                }
+            }
+        }
+        y[i * 3 + 0] = tanhf(acc[0]);
+        y[i * 3 + 1] = tanhf(acc[1]);
+        y[i * 3 + 2] = tanhf(acc[2]);
+    }
+}
+// backward: dl = dy * (1 - y^2); dx = conv^T(dl); dw[kh,kw,ci,co] += sum x[.+k-1, ci] dl[., co]; db += sum dl
+__global__ void conv3x3_c3_tanh_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                           const float* __restrict__ y, const float* __restrict__ dy, float* dx,
+                                           float* dw, float* db, float* dx_sum, int n, int h, int wd) {
+    __shared__ float sw[81];
+    __shared__ float sred[87];
+    if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
+    if (threadIdx.x < 87) sred[threadIdx.x] = 0.f;
+    __syncthreads();
+    float gw[81];
+    float gb[3] = {0.f, 0.f, 0.f};
+    float gs[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+    for (int j = 0; j < 81; ++j) gw[j] = 0.f;
+    const long long pixels = (long long)n * h * wd;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+        const int ow = (int)(i % wd);
+        const int oh = (int)((i / wd) % h);
+        const long long base = i - (long long)oh * wd - ow;
+        // this pixel as an OUTPUT position: weight/bias gradient contributions
+        float dl[3];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float yv = y[i * 3 + c];
+            dl[c] = dy[i * 3 + c] * (1.f - yv * yv);
+            gb[c] += dl[c];
+        }
+        // this pixel as an INPUT position: dx[i, ci] = sum_k dl[i - (k-1), co] w[k, ci, co]
+        float gx[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+        for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+            for (int kw = 0; kw < 3; ++kw) {
+                const int ih = oh + kh - 1, iw = ow + kw - 1;   // input read by output i through tap (kh,kw)
+                if (ih >= 0 && ih < h && iw >= 0 && iw < wd) {
+                    const float* xp = x + (base + (long long)ih * wd + iw) * 3;
+#pragma unroll
+                    for (int ci = 0; ci < 3; ++ci) {
+                        const float xv = xp[ci];
+#pragma unroll
+                        for (int co = 0; co < 3; ++co) gw[(kh * 3 + kw) * 9 + ci * 3 + co] += xv * dl[co];
+                    }
+                }
+                const int oh2 = oh - kh + 1, ow2 = ow - kw + 1;  // output that reads input i through (kh,kw)
+                if (oh2 >= 0 && oh2 < h && ow2 >= 0 && ow2 < wd) {
+                    const long long o = base + (long long)oh2 * wd + ow2;
+                    const float* wp = sw + (kh * 3 + kw) * 9;
+#pragma unroll
+                    for (int co = 0; co < 3; ++co) {
+                        const float yv = y[o * 3 + co];
+                        const float d = dy[o * 3 + co] * (1.f - yv * yv);
+#pragma unroll
+                        for (int ci = 0; ci < 3; ++ci) gx[ci] += d * wp[ci * 3 + co];
+                    }
+                }
+            }
+        }
+        dx[i * 3 + 0] = gx[0]; dx[i * 3 + 1] = gx[1]; dx[i * 3 + 2] = gx[2];
+        gs[0] += gx[0]; gs[1] += gx[1]; gs[2] += gx[2];
+    }
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int j = 0; j < 81; ++j) {
+        const float s = warp_sum(gw[j]);
+        if (lane == 0) atomicAdd(&sred[j], s);
+    }
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+        const float s = warp_sum(gb[c]);
+        if (lane == 0) atomicAdd(&sred[81 + c], s);
+        const float s2 = warp_sum(gs[c]);
+        if (lane == 0) atomicAdd(&sred[84 + c], s2);
+    }
+    __syncthreads();
+    if (threadIdx.x < 81) atomicAdd(&dw[threadIdx.x], sred[threadIdx.x]);
+    else if (threadIdx.x < 84) atomicAdd(&db[threadIdx.x - 81], sred[threadIdx.x]);
+    else if (threadIdx.x < 87 && dx_sum != nullptr) atomicAdd(&dx_sum[threadIdx.x - 84], sred[threadIdx.x]);
+}
+
+// ------------------------------------------------------------------------------------------
+// Per-channel reductions over the rows of a [rows, pitch] planes tensor.  A block covers CG column
+// groups (8 channels each) x RY row lanes; partial sums go through shared memory, then one fp32
+// atomic per channel per block.
+enum { RED_SUM = 0, RED_STATS = 1, RED_BN_BWD = 2 };
+
+template <int MODE>
+__global__ void col_reduce_kernel(const bf16* __restrict__ a, long long a_ps, const bf16* __restrict__ x, long long x_ps,
+                                  const float* __restrict__ mean, const float* __restrict__ rstd, int np,
+                                  long long rows, int c, int pitch, int coff, int CG, float* out0, float* out1) {
+    extern __shared__ float sh[];  // [2][RY][CG*8]
+    const int RY = blockDim.x / CG;
+    const int cgl = threadIdx.x % CG, ry = threadIdx.x / CG;
+    const int cg = blockIdx.x * CG + cgl;
+    const int ch = cg * 8;
+    float s0[8], s1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) s0[j] = s1[j] = 0.f;
+    if (ch < c && ry < RY) {
+        float mu[8], rs[8];
+        if (MODE == RED_BN_BWD) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { mu[j] = mean[ch + j]; rs[j] = rstd[ch + j]; }
+        }
+        for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
+            float v[8];
+            load8(a + r * pitch + coff + ch, a_ps, np, v);
+            if (MODE == RED_SUM) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s0[j] += v[j];
+            } else if (MODE == RED_STATS) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s0[j] += v[j]; s1[j] += v[j] * v[j]; }
+            } else {
+                float xv[8];
+                load8(x + r * pitch + coff + ch, x_ps, np, xv);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { s0[j] += v[j]; s1[j] += v[j] * (xv[j] - mu[j]) * rs[j]; }
+            }
+        }
+    }
+    const int W = CG * 8;
+    if (ry < RY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sh[(0 * RY + ry) * W + cgl * 8 + j] = s0[j];
+            sh[(1 * RY + ry) * W + cgl * 8 + j] = s1[j];
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * W; i += blockDim.x) {
+        const int which = i / W, col = i % W;
+        if (which == 1 && MODE == RED_SUM) continue;
+        const int chn = blockIdx.x * W + col;
+        if (chn >= c) continue;
+        float t = 0.f;
+        for (int k = 0; k < RY; ++k) t += sh[(which * RY + k) * W + col];
+        atomicAdd((which == 0 ? out0 : out1) + chn, t);
+    }
+}
+
+template <int MODE>
+static int launch_col_reduce(const void* a, long long a_ps, const void* x, long long x_ps, const float* mean,
+                             const float* rstd, int np, long long rows, int c, int pitch, int coff, float* out0,
+                             float* out1, cudaStream_t stream) {
+    if (c % 8 || pitch % 8 || coff % 8) return fail(T2I_ERR_BAD_ARG, "col_reduce: channels must be multiples of 8");
+    const int threads = 256;
+    int CG = c / 8;
+    if (CG > 32) CG = 32;
+    // CG must divide the block: round down to a power of two
+    CG = floor_pow2(CG);
+    const int RY = threads / CG;
+    const int gx = ceil_div(c / 8, CG);
+    long long gy = (rows + RY - 1) / RY;
+    const long long cap = ((long long)num_sms() * 8 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    const size_t shm = (size_t)2 * RY * CG * 8 * sizeof(float);
+    col_reduce_kernel<MODE><<<dim3(gx, (unsigned)gy), threads, shm, stream>>>(
+        static_cast<const bf16*>(a), a_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, np, rows, c, pitch, coff, CG,
+        out0, out1);
+    return check_launch("col_reduce_kernel");
+}
+
+// (sum, sumsq) -> (mean, biased var, rstd), in place on the accumulators
+__global__ void bn_finalize_kernel(float* mean, float* var, float* rstd, int c, float inv_rows, float eps) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    const float m = mean[i] * inv_rows;
+    float v = var[i] * inv_rows - m * m;
+    v = fmaxf(v, 0.f);
+    mean[i] = m;
+    var[i] = v;
+    rstd[i] = rsqrtf(v + eps);
+}
+
+__global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, const float* __restrict__ mean,
+                                const float* __restrict__ rstd, const float* __restrict__ gamma,
+                                const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps, bf16* y,
+                                long long y_ps, int np, long long rows, int c, int relu) {
+    const int cg = c / 8;
+    const long long items = rows * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cg) * 8;
+        const long long e = i * 8;
+        float v[8];
+        load8(x + e, x_ps, np, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean[ch + j]) * rstd[ch + j] * gamma[ch + j] + beta[ch + j];
+        if (res != nullptr) {
+            float r[8];
+            load8(res + e, r_ps, np, r);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += r[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store8(y + e, y_ps, np, v);
+    }
+}
+
+// dx = gamma * rstd * (dy - dbeta/R - xhat * dgamma/R)
+__global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ x,
+                                    long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ dgamma,
+                                    const float* __restrict__ dbeta, bf16* dx, long long dx_ps, int np, long long rows,
+                                    int c, float inv_rows) {
+    const int cg = c / 8;
+    const long long items = rows * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int ch = (int)(i % cg) * 8;
+        const long long e = i * 8;
+        float g[8], xv[8];
+        load8(dy + e, dy_ps, np, g);
+        load8(x + e, x_ps, np, xv);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float xh = (xv[j] - mean[ch + j]) * rstd[ch + j];
+            g[j] = gamma[ch + j] * rstd[ch + j] * (g[j] - dbeta[ch + j] * inv_rows - xh * dgamma[ch + j] * inv_rows);
+        }
+        store8(dx + e, dx_ps, np, g);
+    }
+}
+
+__global__ void bn_update_moving_kernel(float* mm, float* mv, const float* mean, const float* var, int c, float decay,
+                                        float bessel) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= c) return;
+    mm[i] = decay * mm[i] + (1.f - decay) * mean[i];
+    mv[i] = decay * mv[i] + (1.f - decay) * var[i] * bessel;
+}
+
+__global__ void act_bwd_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ y, long long y_ps,
+                               bf16* dst, long long dst_ps, int np, long long n8, float neg) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float g[8], a[8];
+        load8(dy + i * 8, dy_ps, np, g);
+        load8(y + i * 8, y_ps, np, a);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g[j] *= (a[j] > 0.f) ? 1.f : neg;
+        store8(dst + i * 8, dst_ps, np, g);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// d_net embedding replicate / reduce
+__global__ void embed_tile_kernel(const bf16* __restrict__ e, long long e_ps, bf16* cat, long long cat_ps, int np, int s,
+                                  int c, int pitch, int coff, int hw) {
+    const int cg = c / 8;
+    const long long items = (long long)s * hw * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const long long pix = i / cg;  // sample * hw + pos
+        const long long smp = pix / hw;
+        float v[8];
+        load8(e + smp * c + g * 8, e_ps, np, v);
+        store8(cat + pix * pitch + coff + g * 8, cat_ps, np, v);
+    }
+}
+__global__ void embed_reduce_kernel(const bf16* __restrict__ dcat, long long dcat_ps, bf16* de, long long de_ps, int np,
+                                    int s, int c, int pitch, int coff, int hw) {
+    const int cg = c / 8;
+    const long long items = (long long)s * cg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % cg);
+        const long long smp = i / cg;
+        float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        for (int pos = 0; pos < hw; ++pos) {
+            float v[8];
+            load8(dcat + (smp * hw + pos) * pitch + coff + g * 8, dcat_ps, np, v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) acc[j] += v[j];
+        }
+        store8(de + smp * c + g * 8, de_ps, np, acc);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// d_net output layer: per-sample dot product over k = 4*4*C values (NHWC order == TF HWIO order)
+__global__ void dout_fwd_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ w,
+                                const float* __restrict__ b, float* logit, int k) {
+    __shared__ float sh[32];
+    const long long s = blockIdx.x;
+    float acc = 0.f;
+    for (int i = threadIdx.x * 8; i < k; i += blockDim.x * 8) {
+        float v[8];
+        load8(a + s * k + i, a_ps, np, v);
+        const float4 w0 = *reinterpret_cast<const float4*>(w + i);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + i + 4);
+        acc += v[0] * w0.x + v[1] * w0.y + v[2] * w0.z + v[3] * w0.w + v[4] * w1.x + v[5] * w1.y + v[6] * w1.z + v[7] * w1.w;
+    }
+    const float t = block_sum(acc, sh);
+    if (threadIdx.x == 0) logit[s] = t + b[0];
+}
+__global__ void dout_bwd_data_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ w,
+                                     const float* __restrict__ seed, bf16* da, long long da_ps, int s, int k) {
+    const int kg = k / 8;
+    const long long items = (long long)s * kg;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const int g = (int)(i % kg);
+        const long long smp = i / kg;
+        const float sd = seed[smp];
+        float v[8];
+        load8(a + i * 8, a_ps, np, v);
+        const float4 w0 = *reinterpret_cast<const float4*>(w + g * 8);
+        const float4 w1 = *reinterpret_cast<const float4*>(w + g * 8 + 4);
+        const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = sd * ww[j] * ((v[j] > 0.f) ? 1.f : 0.2f);
+        store8(da + i * 8, da_ps, np, v);
+    }
+}
+// dw[k] += sum_s seed[s] * a[s, k]; blockIdx.y strides over samples
+__global__ void dout_bwd_weight_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ seed,
+                                       float* dw, int s, int k) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g * 8 >= k) return;
+    float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    for (int smp = blockIdx.y; smp < s; smp += gridDim.y) {
+        float v[8];
+        load8(a + (long long)smp * k + g * 8, a_ps, np, v);
+        const float sd = seed[smp];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] += sd * v[j];
+    }
+#pragma unroll
+    for (int j = 0; j < 8; ++j) atomicAdd(dw + g * 8 + j, acc[j]);
+}
+__global__ void seed_sum_kernel(const float* __restrict__ seed, int n, float* out) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) acc += seed[i];
+    const float t = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(out, t);
+}
+
+// ------------------------------------------------------------------------------------------
+// gradient penalty path
+__global__ void gp_interp_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ eps,
+                                 float* xhat, long long n4, int per_sample4) {
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float e = eps[i / per_sample4];
+        const float4 a = reinterpret_cast<const float4*>(g)[i];
+        const float4 b = reinterpret_cast<const float4*>(x)[i];
+        float4 o;
+        o.x = e * a.x + (1.f - e) * b.x; o.y = e * a.y + (1.f - e) * b.y;
+        o.z = e * a.z + (1.f - e) * b.z; o.w = e * a.w + (1.f - e) * b.w;
+        reinterpret_cast<float4*>(xhat)[i] = o;
+    }
+}
+__global__ void gp_penalty_kernel(const float* __restrict__ grad, int per_sample, float weight, float inv_batch,
+                                  float* slope, float* coef, float* pen_sum) {
+    __shared__ float sh[32];
+    const long long b = blockIdx.x;
+    const float* gp = grad + b * per_sample;
+    float acc = 0.f;
+    for (int i = threadIdx.x * 4; i < per_sample; i += blockDim.x * 4) {
+        const float4 v = *reinterpret_cast<const float4*>(gp + i);
+        acc += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+    }
+    const float t = block_sum(acc, sh);
+    if (threadIdx.x == 0) {
+        const float s = sqrtf(t);
+        const float ex = fmaxf(s - 1.f, 0.f);
+        slope[b] = s;
+        coef[b] = (ex > 0.f) ? weight * 2.f * ex / s * inv_batch : 0.f;
+        atomicAdd(pen_sum, ex * ex);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// conditioning augmentation
+__global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, const float* __restrict__ z,
+                              const float* __restrict__ tn, bf16* zc, long long zc_ps, int np, int b, int z_dim, int ce,
+                              float* kl_sum) {
+    __shared__ float sh[32];
+    const int width = z_dim + ce;
+    float kl = 0.f;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)b * width;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(i % width);
+        const long long row = i / width;
+        float v;
+        if (col < z_dim) {
+            v = z[row * z_dim + col];
+        } else {
+            const int j = col - z_dim;
+            const float mean = load1(ms + row * 2 * ce + j, ms_ps, np);
+            const float ls = load1(ms + row * 2 * ce + ce + j, ms_ps, np);
+            v = mean + expf(ls) * tn[row * ce + j];
+            kl += -ls + 0.5f * (-1.f + expf(2.f * ls) + mean * mean);
+        }
+        store1(zc + i, zc_ps, np, v);
+    }
+    const float t = block_sum(kl, sh);
+    if (threadIdx.x == 0 && kl_sum != nullptr) atomicAdd(kl_sum, t);
+}
+__global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, const bf16* __restrict__ dzc, long long dzc_ps,
+                              const float* __restrict__ tn, bf16* dms, long long dms_ps, int np, int b, int z_dim, int ce,
+                              float kl_scale) {
+    const int width = z_dim + ce;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)b * ce;
+         i += (long long)gridDim.x * blockDim.x) {
+        const int j = (int)(i % ce);
+        const long long row = i / ce;
+        const float mean = load1(ms + row * 2 * ce + j, ms_ps, np);
+        const float ls = load1(ms + row * 2 * ce + ce + j, ms_ps, np);
+        const float dc = load1(dzc + row * width + z_dim + j, dzc_ps, np);
+        float dmean = dc + kl_scale * mean;
+        float dls = dc * tn[row * ce + j] * expf(ls) + kl_scale * (expf(2.f * ls) - 1.f);
+        dmean *= (mean > 0.f) ? 1.f : 0.2f;  // LeakyReLU on both heads (model.py:113-114)
+        dls *= (ls > 0.f) ? 1.f : 0.2f;
+        store1(dms + row * 2 * ce + j, dms_ps, np, dmean);
+        store1(dms + row * 2 * ce + ce + j, dms_ps, np, dls);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// scalars
+__global__ void d_seeds_kernel(const float* kt, float* seed, int b, float inv_gb) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 4 * b) return;
+    const float k = kt[0];
+    const int seg = i / b;
+    // D_loss = -(real - fake) - kt (real - mismatch) + gp terms   (model.py:82-91)
+    seed[i] = (seg == 0) ? inv_gb : (seg == 1) ? -(1.f + k) * inv_gb : (seg == 2) ? k * inv_gb : 1.f;
+}
+__global__ void d_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
+    __shared__ float sh[32];
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int i = threadIdx.x; i < b; i += blockDim.x) {
+        acc[0] += logit[i];
+        acc[1] += logit[b + i];
+        const float m = logit[2 * b + i];
+        acc[2] += m;
+        acc[3] += m * m;
+    }
+    for (int j = 0; j < 4; ++j) {
+        const float t = block_sum(acc[j], sh);
+        if (threadIdx.x == 0) atomicAdd(&sums[j], t);
+    }
+}
+__global__ void d_scalars_kernel(const float* sums, float* kt, float* sc, float inv_gb, float gp_weight, float kt_lr) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float fake = sums[0] * inv_gb, real = sums[1] * inv_gb, mis = sums[2] * inv_gb;
+    const float reg = sums[3] * inv_gb, gp = sums[4] * inv_gb, gp2 = sums[5] * inv_gb;
+    const float k = kt[0];
+    const float wdist = real - fake, wdist2 = real - mis;
+    const float bal = k * wdist2 - wdist;
+    sc[T2I_S_D_LOSS_REAL] = real;
+    sc[T2I_S_D_LOSS_FAKE] = fake;
+    sc[T2I_S_D_LOSS_MISMATCH] = mis;
+    sc[T2I_S_WDIST] = wdist;
+    sc[T2I_S_WDIST2] = wdist2;
+    sc[T2I_S_REG_LOSS] = reg;
+    sc[T2I_S_BALANCE_LOSS] = bal * bal;
+    sc[T2I_S_REAL_GP] = gp;
+    sc[T2I_S_REAL_GP2] = gp2;
+    sc[T2I_S_D_LOSS] = -wdist - k * wdist2 + gp_weight * (gp + gp2);
+    const float kt_grad = 2.f * bal * wdist2;   // d balance_loss / d kt   (model.py:85,100)
+    sc[T2I_S_KT_GRAD] = kt_grad;
+    const float nk = k - kt_lr * kt_grad;
+    kt[0] = nk;
+    sc[T2I_S_KT] = nk;
+}
+__global__ void g_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < b; i += blockDim.x) acc += logit[i];
+    const float t = block_sum(acc, sh);
+    if (threadIdx.x == 0) atomicAdd(&sums[0], t);
+}
+__global__ void g_scalars_kernel(const float* sums, float* sc, float inv_gb, float inv_gb_ce, float kl_coeff) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const float fake = sums[0] * inv_gb;
+    const float kl = sums[1] * inv_gb_ce;
+    sc[T2I_S_G_KL_LOSS] = kl;
+    sc[T2I_S_G_LOSS] = -fake + kl_coeff * kl;   // model.py:92
+}
+
+// ------------------------------------------------------------------------------------------
+// weights: fp32 [taps][cout][cin] -> planes fwd (same layout) and bwd ([taps][cin][cout]); 32x32 tiles
+__global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, bf16* fwd, long long fwd_ps, bf16* bwd,
+                                   long long bwd_ps, int np) {
+    __shared__ float tile[32][33];
+    const int tap = blockIdx.z;
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const float* src = w + (long long)tap * cout * cin;
+    for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+        const int co = co0 + r, ci = ci0 + threadIdx.x;
+        float v = 0.f;
+        if (co < cout && ci < cin) {
+            v = src[(long long)co * cin + ci];
+            if (fwd != nullptr) store1(fwd + ((long long)tap * cout + co) * cin + ci, fwd_ps, np, v);
+        }
+        tile[r][threadIdx.x] = v;
+    }
+    __syncthreads();
+    if (bwd != nullptr) {
+        for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+            const int ci = ci0 + r, co = co0 + threadIdx.x;
+            if (co < cout && ci < cin) store1(bwd + ((long long)tap * cin + ci) * cout + co, bwd_ps, np, tile[threadIdx.x][r]);
+        }
+    }
+}
+
+__global__ void adam_tf_kernel(float* theta, const float* __restrict__ grad, float* m, float* v, long long n, float lr_t,
+                               float b1, float b2, float eps, float gs) {
+    const long long n4 = n / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        float4 g = reinterpret_cast<const float4*>(grad)[i];
+        float4 mm = reinterpret_cast<float4*>(m)[i];
+        float4 vv = reinterpret_cast<float4*>(v)[i];
+        float4 th = reinterpret_cast<float4*>(theta)[i];
+        float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x; float* tp = &th.x;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float gj = gp[j] * gs;
+            mp[j] = b1 * mp[j] + (1.f - b1) * gj;
+            vp[j] = b2 * vp[j] + (1.f - b2) * gj * gj;
+            tp[j] -= lr_t * mp[j] / (sqrtf(vp[j]) + eps);
+        }
+        reinterpret_cast<float4*>(m)[i] = mm;
+        reinterpret_cast<float4*>(v)[i] = vv;
+        reinterpret_cast<float4*>(theta)[i] = th;
+    }
+    // tail
+    for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const float gj = grad[i] * gs;
+        m[i] = b1 * m[i] + (1.f - b1) * gj;
+        v[i] = b2 * v[i] + (1.f - b2) * gj * gj;
+        theta[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+    }
+}
+
+}  // namespace t2i
+
+using namespace t2i;
+#define STREAM static_cast<cudaStream_t>(stream)
+
+extern "C" int t2i_to_planes(const float* src, void* dst, long long ps, int np, long long rows, int cols,
+                             const float* row_scale, void* stream) {
+    if ((rows * cols) % 8 != 0 || cols % 8 != 0) return fail(T2I_ERR_BAD_ARG, "to_planes: cols must be a multiple of 8");
+    to_planes_kernel<<<grid_for(rows * cols / 8, 256), 256, 0, STREAM>>>(src, static_cast<bf16*>(dst), ps, np, rows, cols, row_scale);
+    return check_launch("to_planes");
+}
+extern "C" int t2i_from_planes(const void* src, long long ps, int np, float* dst, long long n, void* stream) {
+    if (n % 8 != 0) return fail(T2I_ERR_BAD_ARG, "from_planes: n must be a multiple of 8");
+    from_planes_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(static_cast<const bf16*>(src), ps, np, dst, n);
+    return check_launch("from_planes");
+}
+extern "C" int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sample_scale, void* col,
+                                  long long ps, int np, void* stream) {
+    if ((h & 1) || (w & 1)) return fail(T2I_ERR_BAD_ARG, "im2col: odd extent");
+    const long long items = (long long)n * (h / 2) * (w / 2) * 5;
+    im2col_k4s2_c3_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(img, n, h, w, sample_scale, static_cast<bf16*>(col), ps, np);
+    return check_launch("im2col_k4s2_c3");
+}
+extern "C" int t2i_col2im_k4s2_c3(const void* col, long long ps, int np, int n, int h, int w, const float* bias3,
+                                  float* img, void* stream) {
+    if ((h & 1) || (w & 1)) return fail(T2I_ERR_BAD_ARG, "col2im: odd extent");
+    col2im_k4s2_c3_kernel<<<grid_for((long long)n * h * w, 256, 16), 256, 0, STREAM>>>(static_cast<const bf16*>(col), ps, np, n, h, w, bias3, img);
+    return check_launch("col2im_k4s2_c3");
+}
+extern "C" int t2i_conv3x3_c3_tanh_fwd(const float* x, const float* w, const float* b, float* y, int n, int h, int wd,
+                                       void* stream) {
+    conv3x3_c3_tanh_fwd_kernel<<<grid_for((long long)n * h * wd, 256, 16), 256, 0, STREAM>>>(x, w, b, y, n, h, wd);
+    return check_launch("conv3x3_c3_tanh_fwd");
+}
+extern "C" int t2i_conv3x3_c3_tanh_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
+                                       float* dw, float* db, float* dx_sum, int n, int h, int wd, void* stream) {
+    conv3x3_c3_tanh_bwd_kernel<<<grid_for((long long)n * h * wd, 128, 4), 128, 0, STREAM>>>(x, w, y, dy, dx, dw, db, dx_sum, n, h, wd);
+    return check_launch("conv3x3_c3_tanh_bwd");
+}
+extern "C" int t2i_colsum(const void* src, long long ps, int np, long long rows, int c, int pitch, int coff, float* out,
+                          void* stream) {
+    return launch_col_reduce<RED_SUM>(src, ps, nullptr, 0, nullptr, nullptr, np, rows, c, pitch, coff, out, nullptr, STREAM);
+}
+extern "C" int t2i_bn_stats(const void* x, long long ps, int np, long long rows, int c, float* mean, float* rstd,
+                            float* var, float eps, void* stream) {
+    cudaMemsetAsync(mean, 0, sizeof(float) * c, STREAM);
+    cudaMemsetAsync(var, 0, sizeof(float) * c, STREAM);
+    int rc = launch_col_reduce<RED_STATS>(x, ps, nullptr, 0, nullptr, nullptr, np, rows, c, c, 0, mean, var, STREAM);
+    if (rc != T2I_OK) return rc;
+    bn_finalize_kernel<<<ceil_div(c, 256), 256, 0, STREAM>>>(mean, var, rstd, c, 1.f / (float)rows, eps);
+    return check_launch("bn_finalize");
+}
+extern "C" int t2i_bn_apply(const void* x, long long x_ps, const float* mean, const float* rstd, const float* gamma,
+                            const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
+                            long long rows, int c, int relu, void* stream) {
+    if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply: c must be a multiple of 8");
+    bn_apply_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, STREAM>>>(
+        static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, beta, static_cast<const bf16*>(residual), r_ps,
+        static_cast<bf16*>(y), y_ps, np, rows, c, relu);
+    return check_launch("bn_apply");
+}
+extern "C" int t2i_bn_bwd_reduce(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
+                                 const float* rstd, int np, long long rows, int c, float* dgamma, float* dbeta,
+                                 void* stream) {
+    return launch_col_reduce<RED_BN_BWD>(dy, dy_ps, x, x_ps, mean, rstd, np, rows, c, c, 0, dbeta, dgamma, STREAM);
+}
+extern "C" int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
+                                const float* rstd, const float* gamma, const float* dgamma, const float* dbeta, void* dx,
+                                long long dx_ps, int np, long long rows, int c, void* stream) {
+    if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_apply: c must be a multiple of 8");
+    bn_bwd_apply_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, STREAM>>>(
+        static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dgamma, dbeta,
+        static_cast<bf16*>(dx), dx_ps, np, rows, c, 1.f / (float)rows);
+    return check_launch("bn_bwd_apply");
+}
+extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,
+                                    float decay, void* stream) {
+    const float bessel = rows > 1 ? (float)rows / (float)(rows - 1) : 1.f;
+    bn_update_moving_kernel<<<ceil_div(c, 256), 256, 0, STREAM>>>(mm, mv, mean, var, c, decay, bessel);
+    return check_launch("bn_update_moving");
+}
+extern "C" int t2i_act_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, void* dst, long long dst_ps,
+                           int np, long long n, int mask_kind, void* stream) {
+    if (n % 8) return fail(T2I_ERR_BAD_ARG, "act_bwd: n must be a multiple of 8");
+    const float neg = (mask_kind == T2I_MASK_LRELU) ? 0.2f : 0.f;
+    act_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(y),
+                                                            y_ps, static_cast<bf16*>(dst), dst_ps, np, n / 8, neg);
+    return check_launch("act_bwd");
+}
+extern "C" int t2i_embed_tile(const void* e, long long e_ps, void* cat, long long cat_ps, int np, int s, int c, int pitch,
+                              int coff, int hw, void* stream) {
+    if (c % 8 || pitch % 8 || coff % 8) return fail(T2I_ERR_BAD_ARG, "embed_tile: channels must be multiples of 8");
+    embed_tile_kernel<<<grid_for((long long)s * hw * (c / 8), 256), 256, 0, STREAM>>>(
+        static_cast<const bf16*>(e), e_ps, static_cast<bf16*>(cat), cat_ps, np, s, c, pitch, coff, hw);
+    return check_launch("embed_tile");
+}
+extern "C" int t2i_embed_reduce(const void* dcat, long long dcat_ps, void* de, long long de_ps, int np, int s, int c,
+                                int pitch, int coff, int hw, void* stream) {
+    if (c % 8 || pitch % 8 || coff % 8) return fail(T2I_ERR_BAD_ARG, "embed_reduce: channels must be multiples of 8");
+    embed_reduce_kernel<<<grid_for((long long)s * (c / 8), 128), 128, 0, STREAM>>>(
+        static_cast<const bf16*>(dcat), dcat_ps, static_cast<bf16*>(de), de_ps, np, s, c, pitch, coff, hw);
+    return check_launch("embed_reduce");
+}
+extern "C" int t2i_dout_fwd(const void* a, long long a_ps, int np, const float* w, const float* b, float* logit, int s,
+                            int k, void* stream) {
+    if (k % 8) return fail(T2I_ERR_BAD_ARG, "dout_fwd: k must be a multiple of 8");
+    dout_fwd_kernel<<<s, 256, 0, STREAM>>>(static_cast<const bf16*>(a), a_ps, np, w, b, logit, k);
+    return check_launch("dout_fwd");
+}
+extern "C" int t2i_dout_bwd_data(const void* a, long long a_ps, int np, const float* w, const float* seed, void* da,
+                                 long long da_ps, int s, int k, void* stream) {
+    if (k % 8) return fail(T2I_ERR_BAD_ARG, "dout_bwd_data: k must be a multiple of 8");
+    dout_bwd_data_kernel<<<grid_for((long long)s * (k / 8), 256), 256, 0, STREAM>>>(
+        static_cast<const bf16*>(a), a_ps, np, w, seed, static_cast<bf16*>(da), da_ps, s, k);
+    return check_launch("dout_bwd_data");
+}
+extern "C" int t2i_dout_bwd_weight(const void* a, long long a_ps, int np, const float* seed, float* dw, float* db, int s,
+                                   int s_bias, int k, void* stream) {
+    if (k % 8) return fail(T2I_ERR_BAD_ARG, "dout_bwd_weight: k must be a multiple of 8");
+    const int gx = ceil_div(k / 8, 128);
+    int gy = s < 32 ? s : 32;
+    dout_bwd_weight_kernel<<<dim3(gx, gy), 128, 0, STREAM>>>(static_cast<const bf16*>(a), a_ps, np, seed, dw, s, k);
+    int rc = check_launch("dout_bwd_weight");
+    if (rc != T2I_OK) return rc;
+    if (db != nullptr && s_bias > 0) {
+        seed_sum_kernel<<<1, 256, 0, STREAM>>>(seed, s_bias, db);
+        rc = check_launch("seed_sum");
+    }
+    return rc;
+}
+extern "C" int t2i_gp_interp(const float* g, const float* x, const float* eps, float* xhat, int n, int per_sample,
+                             void* stream) {
+    if (per_sample % 4) return fail(T2I_ERR_BAD_ARG, "gp_interp: per_sample must be a multiple of 4");
+    const long long n4 = (long long)n * per_sample / 4;
+    gp_interp_kernel<<<grid_for(n4, 256), 256, 0, STREAM>>>(g, x, eps, xhat, n4, per_sample / 4);
+    return check_launch("gp_interp");
+}
+extern "C" int t2i_gp_penalty(const float* grad, int n, int per_sample, float weight, float inv_global_batch,
+                              float* slope, float* coef, float* pen_sum, void* stream) {
+    if (per_sample % 4) return fail(T2I_ERR_BAD_ARG, "gp_penalty: per_sample must be a multiple of 4");
+    gp_penalty_kernel<<<n, 256, 0, STREAM>>>(grad, per_sample, weight, inv_global_batch, slope, coef, pen_sum);
+    return check_launch("gp_penalty");
+}
+extern "C" int t2i_ca_fwd(const void* ms, long long ms_ps, const float* z, const float* tn_eps, void* zc, long long zc_ps,
+                          int np, int b, int z_dim, int ce, float* kl_sum, void* stream) {
+    ca_fwd_kernel<<<grid_for((long long)b * (z_dim + ce), 256, 1), 256, 0, STREAM>>>(
+        static_cast<const bf16*>(ms), ms_ps, z, tn_eps, static_cast<bf16*>(zc), zc_ps, np, b, z_dim, ce, kl_sum);
+    return check_launch("ca_fwd");
+}
+extern "C" int t2i_ca_bwd(const void* ms, long long ms_ps, const void* dzc, long long dzc_ps, const float* tn_eps,
+                          void* dms, long long dms_ps, int np, int b, int z_dim, int ce, float kl_scale, void* stream) {
+    ca_bwd_kernel<<<grid_for((long long)b * ce, 256, 1), 256, 0, STREAM>>>(
+        static_cast<const bf16*>(ms), ms_ps, static_cast<const bf16*>(dzc), dzc_ps, tn_eps, static_cast<bf16*>(dms), dms_ps,
+        np, b, z_dim, ce, kl_scale);
+    return check_launch("ca_bwd");
+}
+extern "C" int t2i_d_seeds(const float* kt, float* seed, int b, float inv_global_batch, void* stream) {
+    d_seeds_kernel<<<ceil_div(4 * b, 256), 256, 0, STREAM>>>(kt, seed, b, inv_global_batch);
+    return check_launch("d_seeds");
+}
+extern "C" int t2i_d_sums(const float* logit, int b, float* sums, void* stream) {
+    d_sums_kernel<<<1, 256, 0, STREAM>>>(logit, b, sums);
+    return check_launch("d_sums");
+}
+extern "C" int t2i_d_scalars(const float* sums, float* kt, float* scalars, int global_batch, float gp_weight, float kt_lr,
+                             void* stream) {
+    d_scalars_kernel<<<1, 32, 0, STREAM>>>(sums, kt, scalars, 1.f / (float)global_batch, gp_weight, kt_lr);
+    return check_launch("d_scalars");
+}
+extern "C" int t2i_g_sums(const float* logit_fake, int b, float* sums, void* stream) {
+    g_sums_kernel<<<1, 256, 0, STREAM>>>(logit_fake, b, sums);
+    return check_launch("g_sums");
+}
+extern "C" int t2i_g_scalars(const float* sums, float* scalars, int global_batch, int ce, float kl_coeff, void* stream) {
+    g_scalars_kernel<<<1, 32, 0, STREAM>>>(sums, scalars, 1.f / (float)global_batch,
+                                           1.f / ((float)global_batch * (float)ce), kl_coeff);
+    return check_launch("g_scalars");
+}
+extern "C" int t2i_pack_weight(const float* w, int taps, int cout, int cin, void* fwd, long long fwd_ps, void* bwd,
+                               long long bwd_ps, int np, void* stream) {
+    dim3 grid(ceil_div(cin, 32), ceil_div(cout, 32), taps);
+    pack_weight_kernel<<<grid, dim3(32, 8), 0, STREAM>>>(w, cout, cin, static_cast<bf16*>(fwd), fwd_ps,
+                                                        static_cast<bf16*>(bwd), bwd_ps, np);
+    return check_launch("pack_weight");
+}
+extern "C" int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, float lr_t, float beta1,
+                           float beta2, float eps, float grad_scale, void* stream) {
+    adam_tf_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, STREAM>>>(theta, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+    return check_launch("adam_tf");
+}

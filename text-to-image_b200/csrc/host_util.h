@@ -1,0 +1,45 @@
+// Host-side helpers shared by the C-ABI translation units: error reporting, launch counting,
+// TMA tensor-map encoding through the driver entry point (no link-time libcuda dependency).
+#pragma once
+#include <cuda.h>
+#include <cuda_runtime.h>
+#include <stdarg.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/t2i_b200.h"
+
+namespace t2i {
+
+void set_error(const char* fmt, ...);
+int fail(int status, const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError after a launch -> status
+int num_sms();
+
+// Encode a bf16 tiled tensor map with 128-byte swizzle and zero OOB fill.
+// dims/strides are innermost first; strides_bytes[i] is the stride of dim i+1.
+int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims,
+                     const uint64_t* strides_bytes, const uint32_t* box);
+
+struct Tap {
+    int8_t dp, dq;  // shift of the input box on the virtual pixel grid
+    int8_t map;     // which input tensor map (stride-2 parity view) the tap reads
+    int8_t wtap;    // tap index into the packed weights (kh*k + kw)
+};
+struct TapTable {
+    int n_phases, taps_per_phase, n_maps;
+    Tap taps[16];
+    int8_t ph_op[4], ph_oq[4];  // DECONV: output sub-pixel offsets per phase
+};
+// Tap tables for the three conv forms (see include/t2i_b200.h); returns 0 or sets the error.
+int build_taps(int mode, int k, int flip, TapTable* t);
+
+inline int floor_pow2(int v) {
+    int p = 1;
+    while (p * 2 <= v) p *= 2;
+    return p;
+}
+inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
+
+}  // namespace t2i

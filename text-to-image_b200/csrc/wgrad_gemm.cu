@@ -1,0 +1,275 @@
+// Weight-gradient GEMM for sm_100a.  dw[tap][co][ci] += sum_pixels dy[pixel][co] * x[pixel+tap][ci].
+// The contraction runs over pixels, which is the slow (row) index of NHWC tensors, so both
+// operands are MN-major: TMA loads [64 pixels x 64 channels] boxes (128B swizzle) and the UMMA
+// descriptors walk 16 pixel rows per instruction (LBO = distance between 64-channel atoms,
+// SBO = 8 pixel rows).  One CTA per (tap, co tile, ci tile, K split); split-K partial sums are
+// combined with vectorised fp32 reductions (red.global.add.v4.f32) into dw.
+//
+// Replaces Conv2DBackpropFilter / MatMul-grad reached via AdamOptimizer.minimize at
+// models/wgancls/model.py:94-106 of the reference; also forms the second-order term of the
+// gradient penalty (model.py:62-70,88-91) when x holds the tangent activations.
+#include "host_util.h"
+#include "ptx.cuh"
+
+namespace t2i {
+
+constexpr int kWM = 128;       // co per tile
+constexpr int kWN = 128;       // ci per tile
+constexpr int kWK = 64;        // pixels per K block
+constexpr int kWStages = 6;
+constexpr int kWAtomBytes = kWK * 128;                  // 64 pixels x 64 channels bf16 = 8 KB
+constexpr int kWABytes = (kWM / 64) * kWAtomBytes;      // 16 KB
+constexpr int kWBBytes = (kWN / 64) * kWAtomBytes;      // 16 KB
+constexpr int kWStageBytes = kWABytes + kWBBytes;
+constexpr int kWBarOffset = kWStages * kWStageBytes;
+constexpr int kWSmemBytes = kWBarOffset + 256 + 1024;
+constexpr int kWThreads = 192;
+
+struct alignas(64) WgradParams {
+    CUtensorMap x_maps[4];
+    CUtensorMap dy_maps[4];
+    TapTable tt;
+    int N, P, Q;
+    int bn, bp, bq;        // K box, bn*bp*bq == 64
+    int tiles_p, tiles_q, k_blocks;  // k_blocks = pixel boxes covering the virtual grid
+    int tiles_co, tiles_ci, jobs;    // jobs = n_phases * taps_per_phase
+    int splits, kb_per_split;
+    int n_pass;
+    int cout, cin;
+    float* dw;
+};
+
+__global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams prm) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWBarOffset);
+    uint64_t* empty_bar = full_bar + kWStages;
+    uint64_t* tmem_full = empty_bar + kWStages;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    // work decode: split fastest so the CTAs of one output tile run together
+    int w = blockIdx.x;
+    const int split = w % prm.splits; w /= prm.splits;
+    const int cit = w % prm.tiles_ci; w /= prm.tiles_ci;
+    const int cot = w % prm.tiles_co; w /= prm.tiles_co;
+    const int job = w;  // phase * taps_per_phase + t
+    const int phase_idx = job / prm.tt.taps_per_phase;
+    const Tap tap = prm.tt.taps[job];
+    const int kb_begin = split * prm.kb_per_split;
+    int kb_end = kb_begin + prm.kb_per_split;
+    if (kb_end > prm.k_blocks) kb_end = prm.k_blocks;
+    const int n_kb = (kb_end > kb_begin) ? (kb_end - kb_begin) * prm.n_pass : 0;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&prm.x_maps[tap.map]);
+        tma_prefetch_desc(&prm.dy_maps[prm.tt.n_phases > 1 ? phase_idx : 0]);
+        for (int i = 0; i < kWStages; ++i) {
+            mbar_init(&full_bar[i], 1);
+            mbar_init(&empty_bar[i], 1);
+        }
+        mbar_init(tmem_full, 1);
+        fence_barrier_init();
+    }
+    if (warp == 1) {
+        tmem_alloc(tmem_slot, kWN);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (n_kb > 0) {
+        if (warp == 0) {
+            if (elect_one()) {
+                const CUtensorMap* dy_map = &prm.dy_maps[prm.tt.n_phases > 1 ? phase_idx : 0];
+                const CUtensorMap* x_map = &prm.x_maps[tap.map];
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int pass = 0; pass < prm.n_pass; ++pass) {
+                    const int pa = (pass == 1) ? 1 : 0;  // dy plane: hi, lo, hi
+                    const int pb = (pass == 2) ? 1 : 0;  // x  plane: hi, hi, lo
+                    for (int kb = kb_begin; kb < kb_end; ++kb) {
+                        const int tq = kb % prm.tiles_q;
+                        const int tp = (kb / prm.tiles_q) % prm.tiles_p;
+                        const int tn = kb / (prm.tiles_q * prm.tiles_p);
+                        const int q0 = tq * prm.bq, p0 = tp * prm.bp, n0 = tn * prm.bn;
+                        mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
+                        mbar_arrive_expect_tx(&full_bar[stage], kWStageBytes);
+                        uint8_t* sa = smem + stage * kWStageBytes;
+#pragma unroll
+                        for (int a = 0; a < kWM / 64; ++a)
+                            tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, cot * kWM + a * 64, q0, p0, n0, pa);
+#pragma unroll
+                        for (int b = 0; b < kWN / 64; ++b)
+                            tma_load_5d(x_map, &full_bar[stage], sa + kWABytes + b * kWAtomBytes, cit * kWN + b * 64,
+                                        q0 + tap.dq, p0 + tap.dp, n0, pb);
+                        if (++stage == kWStages) {
+                            stage = 0;
+                            phase ^= 1;
+                        }
+                    }
+                }
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                constexpr uint32_t idesc = make_idesc_bf16(kWM, kWN, 1, 1);
+                int stage = 0;
+                uint32_t phase = 0;
+                for (int kb = 0; kb < n_kb; ++kb) {
+                    mbar_wait(&full_bar[stage], phase, 200 + stage);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(smem + stage * kWStageBytes);
+#pragma unroll
+                    for (int k = 0; k < kWK / 16; ++k) {
+                        // 16 pixel rows of 128 B per instruction
+                        const uint64_t da = make_sw128_desc(sa + k * 2048, kWAtomBytes, 1024);
+                        const uint64_t db = make_sw128_desc(sa + kWABytes + k * 2048, kWAtomBytes, 1024);
+                        umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+                    }
+                    umma_commit(&empty_bar[stage]);
+                    if (kb == n_kb - 1) umma_commit(tmem_full);
+                    if (++stage == kWStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        } else {
+            const int quarter = warp & 3;
+            const int co = cot * kWM + quarter * 32 + lane;
+            mbar_wait(tmem_full, 0, 400);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
+            float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
+#pragma unroll 1
+            for (int c0 = 0; c0 < kWN; c0 += 32) {
+                const int ci0 = cit * kWN + c0;
+                if (ci0 >= prm.cin) break;
+                __syncwarp();
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+                if (co < prm.cout) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int ci = ci0 + g * 4;
+                        if (ci < prm.cin)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci),
+                                         "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
+                                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                                         : "memory");
+                    }
+                }
+            }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        __syncwarp();
+        tc_fence_after();
+        tmem_dealloc(tmem_base, kWN);
+    }
+}
+
+static int make_maps(const t2i_act& t, bool parity, int np, int bq, int bp, int bn, CUtensorMap* maps) {
+    if (t.pitch % 8 != 0 || t.coff % 8 != 0 || t.c % 8 != 0)
+        return fail(T2I_ERR_BAD_ARG, "activation channels must be multiples of 8 (c=%d pitch=%d coff=%d)", t.c, t.pitch,
+                    t.coff);
+    const uint64_t e = 2;
+    const uint64_t plane_bytes = (np == 2) ? (uint64_t)t.plane_stride * e : (uint64_t)t.n * t.h * t.w * t.pitch * e;
+    const uint32_t box[5] = {64, (uint32_t)bq, (uint32_t)bp, (uint32_t)bn, 1};
+    const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(t.ptr) + t.coff;
+    if (!parity) {
+        const uint64_t dims[5] = {(uint64_t)t.c, (uint64_t)t.w, (uint64_t)t.h, (uint64_t)t.n, (uint64_t)np};
+        const uint64_t str[4] = {(uint64_t)t.pitch * e, (uint64_t)t.w * t.pitch * e, (uint64_t)t.h * t.w * t.pitch * e,
+                                 plane_bytes};
+        return encode_tmap_bf16(&maps[0], base, 5, dims, str, box);
+    }
+    if ((t.h & 1) || (t.w & 1)) return fail(T2I_ERR_BAD_ARG, "stride-2 views need even h, w (got %d x %d)", t.h, t.w);
+    for (int rh = 0; rh < 2; ++rh)
+        for (int rw = 0; rw < 2; ++rw) {
+            const uint64_t dims[5] = {(uint64_t)t.c, (uint64_t)t.w / 2, (uint64_t)t.h / 2, (uint64_t)t.n, (uint64_t)np};
+            const uint64_t str[4] = {2 * (uint64_t)t.pitch * e, 2 * (uint64_t)t.w * t.pitch * e,
+                                     (uint64_t)t.h * t.w * t.pitch * e, plane_bytes};
+            int rc = encode_tmap_bf16(&maps[rh * 2 + rw], base + ((long long)rh * t.w + rw) * t.pitch, 5, dims, str, box);
+            if (rc != T2I_OK) return rc;
+        }
+    return T2I_OK;
+}
+
+}  // namespace t2i
+
+using namespace t2i;
+
+extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
+    if (d == nullptr) return fail(T2I_ERR_BAD_ARG, "null descriptor");
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WgradParams prm;
+    memset(&prm, 0, sizeof(prm));
+    int rc = build_taps(d->mode, d->k, 0, &prm.tt);
+    if (rc != T2I_OK) return rc;
+    if (d->np != 1 && d->np != 2) return fail(T2I_ERR_BAD_ARG, "np must be 1 or 2");
+    const t2i_act& x = d->x;
+    const t2i_act& dy = d->dy;
+    if (x.ptr == nullptr || dy.ptr == nullptr || d->dw == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
+    if (d->cin % 4 != 0 || x.c > d->cin || dy.c > d->cout)
+        return fail(T2I_ERR_BAD_ARG, "bad channels x.c=%d cin=%d dy.c=%d cout=%d", x.c, d->cin, dy.c, d->cout);
+    int eh, ew;  // expected dy extent
+    if (d->mode == T2I_CONV_S1) {
+        prm.P = x.h; prm.Q = x.w; eh = x.h; ew = x.w;
+    } else if (d->mode == T2I_CONV_K4S2) {
+        prm.P = x.h / 2; prm.Q = x.w / 2; eh = x.h / 2; ew = x.w / 2;
+    } else {
+        prm.P = x.h; prm.Q = x.w; eh = 2 * x.h; ew = 2 * x.w;
+    }
+    prm.N = x.n;
+    if (dy.n != x.n || dy.h != eh || dy.w != ew)
+        return fail(T2I_ERR_BAD_ARG, "dy shape [%d,%d,%d] does not match expected [%d,%d,%d]", dy.n, dy.h, dy.w, x.n, eh, ew);
+    {
+        int q = floor_pow2(prm.Q); if (q > kWK) q = kWK;
+        int p = floor_pow2(prm.P); if (p > kWK / q) p = kWK / q;
+        prm.bq = q; prm.bp = p; prm.bn = kWK / (q * p);
+    }
+    prm.tiles_q = ceil_div(prm.Q, prm.bq);
+    prm.tiles_p = ceil_div(prm.P, prm.bp);
+    prm.k_blocks = ceil_div(prm.N, prm.bn) * prm.tiles_p * prm.tiles_q;
+    prm.cout = d->cout;
+    prm.cin = d->cin;
+    prm.tiles_co = ceil_div(dy.c, kWM);
+    prm.tiles_ci = ceil_div(x.c, kWN);
+    prm.jobs = prm.tt.n_phases * prm.tt.taps_per_phase;
+    prm.n_pass = (d->np == 2) ? 3 : 1;
+    const int tiles = prm.jobs * prm.tiles_co * prm.tiles_ci;
+    int splits = d->split_k;
+    if (splits <= 0) {
+        splits = ceil_div(2 * num_sms(), tiles);
+        const int max_splits = prm.k_blocks / 8 > 0 ? prm.k_blocks / 8 : 1;  // >= 8 K blocks per CTA
+        if (splits > max_splits) splits = max_splits;
+        if (splits < 1) splits = 1;
+    }
+    if (splits > prm.k_blocks) splits = prm.k_blocks;
+    prm.kb_per_split = ceil_div(prm.k_blocks, splits);
+    prm.splits = ceil_div(prm.k_blocks, prm.kb_per_split);
+    prm.dw = d->dw;
+
+    rc = make_maps(x, d->mode == T2I_CONV_K4S2, d->np, prm.bq, prm.bp, prm.bn, prm.x_maps);
+    if (rc != T2I_OK) return rc;
+    rc = make_maps(dy, d->mode == T2I_DECONV_K4S2, d->np, prm.bq, prm.bp, prm.bn, prm.dy_maps);
+    if (rc != T2I_OK) return rc;
+
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
+        if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    const int grid = tiles * prm.splits;
+    wgrad_gemm_kernel<<<grid, kWThreads, kWSmemBytes, stream>>>(prm);
+    return check_launch("wgrad_gemm_kernel");
+}

@@ -1,0 +1,618 @@
+"""Host orchestration of one wgancls iteration on the CUDA kernels (no arithmetic happens here).
+
+What the reference expresses as a TF-1.4 graph plus tf.gradients / AdamOptimizer.minimize
+(models/wgancls/model.py:34-106) is scheduled explicitly:
+
+  D run (trainer.py:97):  G forward -> D forward on the 4B batch [fake | real | mismatch | x_hat]
+      -> seeded D backward (input gradients at every layer; x_hat's goes down to the image and to
+      cond) -> slopes / one-sided penalties / tangent seeds -> tangent forward of the x_hat segment
+      IN PLACE over its activations (d_net is piecewise linear: d/dtheta of the penalty is the
+      weight gradient of the JVP) -> ONE merged weight-gradient pass over the 4B
+      batch -> [allreduce] -> kt SGD, Adam.
+  G run (trainer.py:101): G forward (fresh noise) -> D forward -> D input-gradient -> G backward
+      (BatchNorm backward included) -> [allreduce] -> Adam, BN moving statistics.
+
+Parameters live in kernel layout in two flat fp32 buffers (d / g) with flat gradient and Adam
+buffers beside them; conversion to/from the reference's TF variable layout happens only in
+``set_params_tf`` / ``get_params_tf`` (checkpoint boundary).  ``K`` is the kernel module
+(text-to-image_b200/kernels.py); tests inject their CPU restatement to check this file on CPU.
+"""
+import math
+from collections import OrderedDict
+
+import torch
+
+GP_WEIGHT = 150.0   # models/wgancls/model.py:91
+KT_LR = 0.001       # models/wgancls/model.py:100
+KT_INIT = 0.7       # models/wgancls/model.py:77
+BN_EPS = 1e-5       # utils/ops.py:7
+BN_DECAY = 0.9
+ADAM_EPS = 1e-8
+SUMS = 8            # per-net tail of the flat gradient buffer holding the scalar sums
+IMG = 64            # the path is only valid for 64x64 (model.py:154 hard-codes the 4x4 tile)
+
+
+def _align(n, a=64):
+    return (n + a - 1) // a * a
+
+
+class Layer:
+    """One contraction layer: kernel-layout master weight/bias views, gradient views, packed copies."""
+
+    def __init__(self, name, kind, tf_w, tf_b, mode, k, taps, cout, cin, need_bwd=True):
+        self.name, self.kind, self.tf_w, self.tf_b = name, kind, tf_w, tf_b
+        self.mode, self.k, self.taps, self.cout, self.cin = mode, k, taps, cout, cin
+        self.need_bwd = need_bwd
+        self.w = self.b = self.gw = self.gb = self.Wf = self.Wb = None
+
+
+class Engine:
+    def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
+                 beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None):
+        self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
+        self.Z, self.E, self.ce, self.gf, self.df = z_dim, embed_dim, ce, gf, df
+        self.beta1, self.beta2, self.kl_coeff = beta1, beta2, kl_coeff
+        self.world, self.allreduce = world, allreduce
+        self.GB = batch * world
+        for v in (z_dim, embed_dim, ce, gf, df):
+            assert v % 8 == 0, "channel counts must be multiples of 8"
+        self.d_t = 0
+        self.g_t = 0
+        self._build_params()
+        self._build_buffers()
+
+    # ------------------------------------------------------------------ parameters
+    def _build_params(self):
+        K = self.K
+        gf, df, ce, E, Z = self.gf, self.df, self.ce, self.E, self.Z
+        C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
+        S1, K4, DC = K.CONV_S1, K.CONV_K4S2, K.DECONV_K4S2
+        d, g = "d_net/", "g_net/"
+        L = Layer
+        self.dl = OrderedDict((l.name, l) for l in [
+            L("h0", "col_in", d + "Conv", d + "Conv", S1, 1, 1, df, 64),
+            L("h1", "conv", d + "Conv_1", d + "Conv_1", K4, 4, 16, 2 * df, df),
+            L("h2", "conv", d + "Conv_2", d + "Conv_2", K4, 4, 16, 4 * df, 2 * df),
+            L("h3", "conv", d + "Conv_3", d + "Conv_3", K4, 4, 16, 8 * df, 4 * df),
+            L("r1", "conv", d + "Conv_4", d + "Conv_4", S1, 1, 1, 2 * df, 8 * df),
+            L("r2", "conv", d + "Conv_5", d + "Conv_5", S1, 3, 9, 4 * df, 2 * df),
+            L("r3", "conv", d + "Conv_6", d + "Conv_6", S1, 3, 9, 8 * df, 4 * df),
+            L("efc", "dense", d + "dense", d + "dense", S1, 1, 1, ce, E),
+            L("h5", "conv", d + "Conv_7", d + "Conv_7", S1, 3, 9, 8 * df, 8 * df + ce),
+            L("h6", "conv", d + "Conv_8", d + "Conv_8", S1, 1, 1, 8 * df, 8 * df),
+            L("out", "dout", d + "Conv_9", d + "Conv_9", None, 4, 1, 1, 16 * 8 * df, need_bwd=False),
+        ])
+        self.gl = OrderedDict((l.name, l) for l in [
+            L("ms", "ms", (g + "dense", g + "dense_1"), (g + "dense", g + "dense_1"), S1, 1, 1, 2 * ce, E,
+              need_bwd=False),
+            L("fc0", "fc0", g + "dense_2", g + "dense_2", S1, 1, 1, 16 * C8, Z + ce),
+            L("c0", "conv", g + "Conv", g + "Conv", S1, 1, 1, C2, C8),
+            L("c1", "conv", g + "Conv_1", g + "Conv_1", S1, 3, 9, C2, C2),
+            L("c2", "conv", g + "Conv_2", g + "Conv_2", S1, 3, 9, C8, C2),
+            L("t0", "deconv", g + "Conv2d_transpose", g + "Conv2d_transpose", DC, 4, 16, C4, C8),
+            L("c3", "conv", g + "Conv_3", g + "Conv_3", S1, 3, 9, C4, C4),
+            L("c4", "conv", g + "Conv_4", g + "Conv_4", S1, 1, 1, C1, C4),
+            L("c5", "conv", g + "Conv_5", g + "Conv_5", S1, 3, 9, C1, C1),
+            L("c6", "conv", g + "Conv_6", g + "Conv_6", S1, 3, 9, C4, C1),
+            L("t1", "deconv", g + "Conv2d_transpose_1", g + "Conv2d_transpose_1", DC, 4, 16, C2, C4),
+            L("c7", "conv", g + "Conv_7", g + "Conv_7", S1, 3, 9, C2, C2),
+            L("t2", "deconv", g + "Conv2d_transpose_2", g + "Conv2d_transpose_2", DC, 4, 16, C1, C2),
+            L("c8", "conv", g + "Conv_8", g + "Conv_8", S1, 3, 9, C1, C1),
+            L("t3", "col_out", g + "Conv2d_transpose_3", g + "Conv2d_transpose_3", S1, 1, 1, 64, C1),
+            L("c9", "c9", g + "Conv_9", g + "Conv_9", None, 3, 9, 3, 3, need_bwd=False),
+        ])
+        # BatchNorm layers of g_net in creation order (model.py:176-216): (tf scope, channels)
+        self.bn_ch = [16 * C8, C2, C2, C8, C4, C1, C1, C4, C2, C1]
+        self.bn_tf = [g + "BatchNorm" + ("" if i == 0 else "_%d" % i) for i in range(10)]
+
+        def bias_len(l):
+            return {"dout": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)
+
+        def layout(layers, with_bn):
+            off, table = 0, OrderedDict()
+            for l in layers.values():
+                wn = l.taps * l.cout * l.cin if l.kind not in ("dout", "c9") else (l.cin if l.kind == "dout" else 81)
+                table[l.name + ".w"] = (off, wn); off = _align(off + wn)
+                table[l.name + ".b"] = (off, bias_len(l)); off = _align(off + bias_len(l))
+            if with_bn:
+                for i, c in enumerate(self.bn_ch):
+                    table["bn%d.gamma" % i] = (off, c); off = _align(off + c)
+                    table["bn%d.beta" % i] = (off, c); off = _align(off + c)
+            return off, table
+
+        self.d_n, self.d_table = layout(self.dl, False)
+        self.g_n, self.g_table = layout(self.gl, True)
+        f32 = dict(device=self.dev, dtype=torch.float32)
+        self.flat = {"d": torch.zeros(self.d_n, **f32), "g": torch.zeros(self.g_n, **f32)}
+        self.grad = {"d": torch.zeros(self.d_n + SUMS, **f32), "g": torch.zeros(self.g_n + SUMS, **f32)}
+        self.adam_m = {k: torch.zeros_like(v) for k, v in self.flat.items()}
+        self.adam_v = {k: torch.zeros_like(v) for k, v in self.flat.items()}
+        self.sums = {"d": self.grad["d"][self.d_n:], "g": self.grad["g"][self.g_n:]}
+        self.P, self.G = {}, {}
+        for net, table in (("d", self.d_table), ("g", self.g_table)):
+            for name, (off, n) in table.items():
+                self.P[net + "." + name] = self.flat[net][off:off + n]
+                self.G[net + "." + name] = self.grad[net][off:off + n]
+        bf = dict(device=self.dev, dtype=torch.bfloat16)
+        for net, layers in (("d", self.dl), ("g", self.gl)):
+            for l in layers.values():
+                l.w, l.b = self.P["%s.%s.w" % (net, l.name)], self.P["%s.%s.b" % (net, l.name)]
+                l.gw, l.gb = self.G["%s.%s.w" % (net, l.name)], self.G["%s.%s.b" % (net, l.name)]
+                if l.kind in ("dout", "c9"):
+                    continue
+                l.w = l.w.view(l.taps, l.cout, l.cin)
+                l.gw = l.gw.view(l.taps, l.cout, l.cin)
+                l.Wf = torch.zeros(self.np, l.taps, l.cout, l.cin, **bf)
+                l.Wb = torch.zeros(self.np, l.taps, l.cin, l.cout, **bf) if l.need_bwd else None
+        self.bn_gamma = [self.P["g.bn%d.gamma" % i] for i in range(10)]
+        self.bn_beta = [self.P["g.bn%d.beta" % i] for i in range(10)]
+        self.bn_dgamma = [self.G["g.bn%d.gamma" % i] for i in range(10)]
+        self.bn_dbeta = [self.G["g.bn%d.beta" % i] for i in range(10)]
+        self.bn_mm = [torch.zeros(c, **f32) for c in self.bn_ch]
+        self.bn_mv = [torch.ones(c, **f32) for c in self.bn_ch]
+        self.bn_mean = [torch.zeros(c, **f32) for c in self.bn_ch]
+        self.bn_var = [torch.zeros(c, **f32) for c in self.bn_ch]
+        self.bn_rstd = [torch.zeros(c, **f32) for c in self.bn_ch]
+        for gmm in self.bn_gamma:
+            gmm.fill_(1.0)
+        self.kt = torch.full((1,), KT_INIT, **f32)
+        self.scalars = torch.zeros(16, **f32)
+
+    # -- layout conversion between the reference's TF variables and the kernel layout ---------
+    def _perm_fc0(self, v_tf, inverse=False):
+        """feature order: TF c*16 + hw (NCHW reshape, model.py:179)  <->  kernel hw*C8 + c (NHWC)."""
+        C8 = 8 * self.gf
+        lead = v_tf.shape[:-1]
+        if not inverse:
+            return v_tf.reshape(*lead, C8, 16).transpose(-1, -2).reshape(*lead, 16 * C8)
+        return v_tf.reshape(*lead, 16, C8).transpose(-1, -2).reshape(*lead, 16 * C8)
+
+    def _w_to_kernel(self, l, p):
+        if l.kind == "conv":
+            w = p[l.tf_w + "/weights"]
+            return w.permute(0, 1, 3, 2).reshape(l.taps, l.cout, l.cin)
+        if l.kind == "deconv":
+            return p[l.tf_w + "/weights"].reshape(l.taps, l.cout, l.cin)
+        if l.kind == "dense":
+            return p[l.tf_w + "/kernel"].t().reshape(1, l.cout, l.cin)
+        if l.kind == "ms":
+            return torch.cat([p[l.tf_w[0] + "/kernel"].t(), p[l.tf_w[1] + "/kernel"].t()], 0).reshape(1, l.cout, l.cin)
+        if l.kind == "fc0":
+            return self._perm_fc0(p[l.tf_w + "/kernel"]).t().reshape(1, l.cout, l.cin)
+        if l.kind == "col_in":   # [4,4,3,co] -> [co, (kh*4+kw)*3+c], zero padded to 64 columns
+            w = p[l.tf_w + "/weights"]
+            out = torch.zeros(1, l.cout, 64, dtype=w.dtype)
+            out[0, :, :48] = w.reshape(48, l.cout).t()
+            return out
+        if l.kind == "col_out":  # deconv [4,4,co=3,ci] -> [(kh*4+kw)*3+co, ci], zero padded to 64 rows
+            w = p[l.tf_w + "/weights"]
+            out = torch.zeros(1, 64, l.cin, dtype=w.dtype)
+            out[0, :48] = w.reshape(48, l.cin)
+            return out
+        if l.kind == "dout":     # [4,4,C,1] -> (kh,kw,c) flat == NHWC order of the 4x4xC activation
+            return p[l.tf_w + "/weights"].reshape(-1)
+        if l.kind == "c9":
+            return p[l.tf_w + "/weights"].reshape(-1)
+        raise ValueError(l.kind)
+
+    def _w_to_tf(self, l, w, out):
+        if l.kind == "conv":
+            out[l.tf_w + "/weights"] = w.reshape(l.k, l.k, l.cout, l.cin).permute(0, 1, 3, 2).contiguous()
+        elif l.kind == "deconv":
+            out[l.tf_w + "/weights"] = w.reshape(4, 4, l.cout, l.cin).clone()
+        elif l.kind == "dense":
+            out[l.tf_w + "/kernel"] = w.reshape(l.cout, l.cin).t().contiguous()
+        elif l.kind == "ms":
+            w2 = w.reshape(l.cout, l.cin)
+            out[l.tf_w[0] + "/kernel"] = w2[:self.ce].t().contiguous()
+            out[l.tf_w[1] + "/kernel"] = w2[self.ce:].t().contiguous()
+        elif l.kind == "fc0":
+            out[l.tf_w + "/kernel"] = self._perm_fc0(w.reshape(l.cout, l.cin).t(), inverse=True).contiguous()
+        elif l.kind == "col_in":
+            out[l.tf_w + "/weights"] = w.reshape(l.cout, 64)[:, :48].t().reshape(4, 4, 3, l.cout).contiguous()
+        elif l.kind == "col_out":
+            out[l.tf_w + "/weights"] = w.reshape(64, l.cin)[:48].reshape(4, 4, 3, l.cin).clone()
+        elif l.kind == "dout":
+            out[l.tf_w + "/weights"] = w.reshape(4, 4, -1, 1).clone()
+        elif l.kind == "c9":
+            out[l.tf_w + "/weights"] = w.reshape(3, 3, 3, 3).clone()
+
+    def _b_names(self, l):
+        leaf = "/bias" if l.kind in ("dense", "ms", "fc0") else "/biases"
+        return [n + leaf for n in (l.tf_b if isinstance(l.tf_b, tuple) else (l.tf_b,))]
+
+    def set_params_tf(self, p):
+        """Load parameters given in the reference's TF variable layout (oracle / checkpoint names)."""
+        p = {k: torch.as_tensor(v).detach().to("cpu", torch.float32) for k, v in p.items()}
+        for net, layers in (("d", self.dl), ("g", self.gl)):
+            for l in layers.values():
+                self.P["%s.%s.w" % (net, l.name)].copy_(self._w_to_kernel(l, p).reshape(-1))
+                b = torch.cat([p[n] for n in self._b_names(l)])
+                if l.kind == "fc0":
+                    b = self._perm_fc0(b)
+                self.P["%s.%s.b" % (net, l.name)].copy_(b)
+        for i, scope in enumerate(self.bn_tf):
+            perm = (lambda v: self._perm_fc0(v)) if i == 0 else (lambda v: v)
+            self.bn_gamma[i].copy_(perm(p[scope + "/gamma"]))
+            self.bn_beta[i].copy_(perm(p[scope + "/beta"]))
+            self.bn_mm[i].copy_(perm(p[scope + "/moving_mean"]))
+            self.bn_mv[i].copy_(perm(p[scope + "/moving_variance"]))
+        self.repack("d")
+        self.repack("g")
+
+    def _export(self, flat_views, include_moving):
+        out = OrderedDict()
+        for net, layers in (("d", self.dl), ("g", self.gl)):
+            for l in layers.values():
+                self._w_to_tf(l, flat_views["%s.%s.w" % (net, l.name)].detach().cpu(), out)
+                b = flat_views["%s.%s.b" % (net, l.name)].detach().cpu()
+                if l.kind == "fc0":
+                    b = self._perm_fc0(b, inverse=True)
+                names = self._b_names(l)
+                for j, n in enumerate(names):
+                    out[n] = b.reshape(len(names), -1)[j].clone()
+        for i, scope in enumerate(self.bn_tf):
+            perm = (lambda v: self._perm_fc0(v, inverse=True)) if i == 0 else (lambda v: v)
+            out[scope + "/gamma"] = perm(flat_views["g.bn%d.gamma" % i].detach().cpu()).clone()
+            out[scope + "/beta"] = perm(flat_views["g.bn%d.beta" % i].detach().cpu()).clone()
+            if include_moving:
+                out[scope + "/moving_mean"] = perm(self.bn_mm[i].detach().cpu()).clone()
+                out[scope + "/moving_variance"] = perm(self.bn_mv[i].detach().cpu()).clone()
+        return out
+
+    def get_params_tf(self):
+        return self._export(self.P, True)
+
+    def get_grads_tf(self):
+        """Gradients of the last d_step / g_step in TF layout (the other net's entries are stale)."""
+        return self._export(self.G, False)
+
+    def repack(self, net):
+        """fp32 master -> bf16 planes in both contraction orders (after every optimizer step)."""
+        for l in (self.dl if net == "d" else self.gl).values():
+            if l.Wf is not None:
+                self.K.pack_weight(l.w, l.Wf, l.Wb)
+
+    # ------------------------------------------------------------------ buffers
+    def _build_buffers(self):
+        B, S, np_ = self.B, 4 * self.B, self.np
+        df, gf, ce, E, Z = self.df, self.gf, self.ce, self.E, self.Z
+        C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
+        bf = dict(device=self.dev, dtype=torch.bfloat16)
+        f32 = dict(device=self.dev, dtype=torch.float32)
+
+        def planes(*shape):
+            return torch.zeros(np_, *shape, **bf)
+
+        d = self.d = {}
+        d["img"] = torch.zeros(S, IMG, IMG, 3, **f32)     # [fake | real | mismatch | x_hat]
+        d["col0"] = planes(S * 1024, 64)
+        dshapes = {"a0": (S, 32, 32, df), "a1": (S, 16, 16, 2 * df), "a2": (S, 8, 8, 4 * df), "a3": (S, 4, 4, 8 * df),
+                   "r1": (S, 4, 4, 2 * df), "r2": (S, 4, 4, 4 * df), "cat": (S, 4, 4, 8 * df + ce),
+                   "a5": (S, 4, 4, 8 * df), "a6": (S, 4, 4, 8 * df)}
+        for n, sh in dshapes.items():
+            d[n] = planes(*sh)
+            d["d_" + n] = planes(*sh)
+        d["cond"] = planes(S, E)
+        d["e"] = planes(S, ce)
+        d["d_e"] = planes(S, ce)
+        d["logit"] = torch.zeros(S, **f32)
+        d["seed"] = torch.zeros(S, **f32)
+        d["gseed"] = torch.full((B,), -1.0 / self.GB, **f32)    # G_loss = -mean D(G) + ...  (model.py:92)
+        d["d_col0"] = planes(B * 1024, 64)
+        d["gx"] = torch.zeros(B, IMG, IMG, 3, **f32)       # dD/d image
+        d["d_cond"] = planes(B, E)
+        d["g2"] = torch.zeros(B, E, **f32)                  # dD/d cond
+        for n in ("slope", "coef", "slope2", "coef2"):
+            d[n] = torch.zeros(B, **f32)
+
+        g = self.g = {}
+        gshapes = {"f0": (B, 4, 4, C8), "h0": (B, 4, 4, C8), "t1": (B, 4, 4, C2), "u1": (B, 4, 4, C2),
+                   "t2": (B, 4, 4, C2), "u2": (B, 4, 4, C2), "t3": (B, 4, 4, C8), "h1": (B, 4, 4, C8),
+                   "d1": (B, 8, 8, C4), "t4": (B, 8, 8, C4), "h2": (B, 8, 8, C4), "t5": (B, 8, 8, C1),
+                   "u5": (B, 8, 8, C1), "t6": (B, 8, 8, C1), "u6": (B, 8, 8, C1), "t7": (B, 8, 8, C4),
+                   "h3": (B, 8, 8, C4), "d2": (B, 16, 16, C2), "t8": (B, 16, 16, C2), "h4": (B, 16, 16, C2),
+                   "d3": (B, 32, 32, C1), "t9": (B, 32, 32, C1), "h5": (B, 32, 32, C1)}
+        for n, sh in gshapes.items():
+            g[n] = planes(*sh)
+            g["d_" + n] = planes(*sh)
+        for n, sh in {"cond": (B, E), "ms": (B, 2 * ce), "zc": (B, Z + ce), "colg": (B * 1024, 64)}.items():
+            g[n] = planes(*sh)
+            g["d_" + n] = planes(*sh)
+        g["ds"] = {"h1": planes(B, 4, 4, C8), "h3": planes(B, 8, 8, C4)}   # gradient at the residual sums
+        g["u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
+        g["d_u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
+        g["tn"] = torch.zeros(B, ce, **f32)
+        g["z"] = torch.zeros(B, Z, **f32)
+        g["kl_scratch"] = torch.zeros(1, **f32)
+        self.feed = {"cond": torch.zeros(B, E, **f32), "epsilon": torch.zeros(B, **f32)}
+
+    @staticmethod
+    def _rows(t):
+        """[np, n, h, w, c] planes -> [np, n*h*w, c] alias (rows = pixels)."""
+        return t.view(t.shape[0], -1, t.shape[-1])
+
+    # ------------------------------------------------------------------ generator
+    def _bn(self, i, x, y, residual=None, relu=False, train=True):
+        K = self.K
+        if train:
+            K.bn_stats(x, self.bn_mean[i], self.bn_rstd[i], self.bn_var[i], BN_EPS)
+            mean, rstd = self.bn_mean[i], self.bn_rstd[i]
+        else:   # inference: moving statistics (sampler, model.py:57) -- not on the training path
+            mean, rstd = self.bn_mm[i], torch.rsqrt(self.bn_mv[i] + BN_EPS)
+        K.bn_apply(x, mean, rstd, self.bn_gamma[i], self.bn_beta[i], y, residual, relu)
+
+    def g_forward(self, z, cond, tn_eps, img_out, kl_sum, train=True, cond_noise=True):
+        """models/wgancls/model.py:163-225.  z, cond, tn_eps: fp32 device tensors; image -> img_out."""
+        K, g, gl, V = self.K, self.g, self.gl, self.K.View
+        S1, DC = K.CONV_S1, K.DECONV_K4S2
+        K.to_planes(cond, g["cond"])
+        K.conv_gemm(S1, 1, 0, V(g["cond"]), gl["ms"].Wf, V(g["ms"]), bias=gl["ms"].b, act=K.ACT_LRELU)   # :113-114
+        if not cond_noise:
+            tn_eps = torch.zeros_like(tn_eps)
+        K.ca_fwd(g["ms"], z, tn_eps, g["zc"], kl_sum)                                                   # :117-122,174
+        f0r = g["f0"].view(self.np, self.B, -1)
+        K.conv_gemm(S1, 1, 0, V(g["zc"]), gl["fc0"].Wf, V(f0r), bias=gl["fc0"].b)                        # :175
+        self._bn(0, f0r, g["h0"].view(self.np, self.B, -1), train=train)                                 # :176
+
+        def conv(l, x, y):
+            K.conv_gemm(gl[l].mode, gl[l].k, 0, V(g[x]), gl[l].Wf, V(g[y]), bias=gl[l].b)
+
+        def res(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out):
+            conv(c_a, x, t_a); self._bn(bn_a, g[t_a], g[u_a], relu=True, train=train)
+            conv(c_b, u_a, t_b); self._bn(bn_b, g[t_b], g[u_b], relu=True, train=train)
+            conv(c_c, u_b, t_c); self._bn(bn_c, g[t_c], g[out], residual=g[x], relu=True, train=train)
+
+        res("h0", "c0", "t1", 1, "u1", "c1", "t2", 2, "u2", "c2", "t3", 3, "h1")                        # :184-191
+        conv("t0", "h1", "d1"); conv("c3", "d1", "t4"); self._bn(4, g["t4"], g["h2"], train=train)      # :194-196
+        res("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3")                        # :200-207
+        conv("t1", "h3", "d2"); conv("c7", "d2", "t8"); self._bn(8, g["t8"], g["h4"], relu=True, train=train)  # :210-212
+        conv("t2", "h4", "d3"); conv("c8", "d3", "t9"); self._bn(9, g["t9"], g["h5"], relu=True, train=train)  # :214-216
+        K.conv_gemm(S1, 1, 0, V(self._rows(g["h5"])), gl["t3"].Wf, V(g["colg"]))                        # :218 as patches
+        K.col2im_k4s2_c3(g["colg"], g["u4"], gl["t3"].b)
+        K.conv3x3_c3_tanh_fwd(g["u4"], gl["c9"].w, gl["c9"].b, img_out)                                  # :219-221
+
+    def g_backward(self, d_img):
+        """Backward of g_forward given dLoss/d image (fp32 [B,64,64,3]); fills the g gradient buffer."""
+        K, g, gl, V = self.K, self.g, self.gl, self.K.View
+        S1, K4, DC = K.CONV_S1, K.CONV_K4S2, K.DECONV_K4S2
+        B, np_ = self.B, self.np
+        rows = self._rows
+        img = self.d["img"][:B]
+        K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
+        K.im2col_k4s2_c3(g["d_u4"], g["d_colg"])
+        K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw)
+        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wb, V(rows(g["d_h5"])))
+
+        def bn_bwd(i, dy, y_post, x_pre, dx, relu):
+            """dy: gradient w.r.t. the BN(+ReLU) output; writes the gradient w.r.t. its input."""
+            if relu:
+                K.act_bwd(dy, y_post, dy, K.MASK_RELU)
+            K.bn_bwd_reduce(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_dgamma[i], self.bn_dbeta[i])
+            K.bn_bwd_apply(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_gamma[i], self.bn_dgamma[i],
+                           self.bn_dbeta[i], dx)
+
+        def conv_bwd(l, x, dy, dx, add=None):
+            """weight/bias gradient of layer l (input x, output gradient dy) and input gradient -> dx."""
+            L = gl[l]
+            K.colsum(V(g[dy]), L.gb)
+            K.wgrad_gemm(L.mode, L.k, V(g[x]), V(g[dy]), L.gw)
+            if dx is not None:
+                mode = {S1: S1, DC: K4, K4: DC}[L.mode]
+                K.conv_gemm(mode, L.k, 1 if L.k == 3 else 0, V(g[dy]), L.Wb, V(g[dx]),
+                            add=None if add is None else V(add))
+
+        def res_bwd(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out):
+            ds = g["ds"][out]
+            K.act_bwd(g["d_" + out], g[out], ds, K.MASK_RELU)          # gradient at (x + bn(t_c))
+            bn_bwd(bn_c, ds, None, g[t_c], g["d_" + t_c], relu=False)
+            conv_bwd(c_c, u_b, "d_" + t_c, "d_" + u_b)
+            bn_bwd(bn_b, g["d_" + u_b], g[u_b], g[t_b], g["d_" + t_b], relu=True)
+            conv_bwd(c_b, u_a, "d_" + t_b, "d_" + u_a)
+            bn_bwd(bn_a, g["d_" + u_a], g[u_a], g[t_a], g["d_" + t_a], relu=True)
+            conv_bwd(c_a, x, "d_" + t_a, "d_" + x, add=ds)            # skip connection joins here
+
+        bn_bwd(9, g["d_h5"], g["h5"], g["t9"], g["d_t9"], relu=True)
+        conv_bwd("c8", "d3", "d_t9", "d_d3"); conv_bwd("t2", "h4", "d_d3", "d_h4")
+        bn_bwd(8, g["d_h4"], g["h4"], g["t8"], g["d_t8"], relu=True)
+        conv_bwd("c7", "d2", "d_t8", "d_d2"); conv_bwd("t1", "h3", "d_d2", "d_h3")
+        res_bwd("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3")
+        bn_bwd(4, g["d_h2"], None, g["t4"], g["d_t4"], relu=False)
+        conv_bwd("c3", "d1", "d_t4", "d_d1"); conv_bwd("t0", "h1", "d_d1", "d_h1")
+        res_bwd("h0", "c0", "t1", 1, "u1", "c1", "t2", 2, "u2", "c2", "t3", 3, "h1")
+        flat = lambda t: t.view(np_, B, -1)
+        bn_bwd(0, flat(g["d_h0"]), None, flat(g["f0"]), flat(g["d_f0"]), relu=False)
+        L = gl["fc0"]
+        K.colsum(V(flat(g["d_f0"])), L.gb)
+        K.wgrad_gemm(S1, 1, V(g["zc"]), V(flat(g["d_f0"])), L.gw)
+        K.conv_gemm(S1, 1, 0, V(flat(g["d_f0"])), L.Wb, V(g["d_zc"]))
+        K.ca_bwd(g["ms"], g["d_zc"], g["tn"], g["d_ms"], self.Z, self.kl_coeff / (self.GB * self.ce))
+        L = gl["ms"]
+        K.colsum(V(g["d_ms"]), L.gb)
+        K.wgrad_gemm(S1, 1, V(g["cond"]), V(g["d_ms"]), L.gw)
+
+    # ------------------------------------------------------------------ discriminator
+    def d_forward(self, s0, n, tangent=False):
+        """models/wgancls/model.py:129-161 on samples [s0, s0+n) of the D buffers.  tangent=True
+        propagates a tangent instead: no biases, LeakyReLU replaced by its saved derivative mask,
+        written in place over the forward activations of those samples (no logit)."""
+        K, d, dl = self.K, self.d, self.dl
+        S1, K4 = K.CONV_S1, K.CONV_K4S2
+        rows = self._rows
+        df8 = 8 * self.df
+
+        def V(t, **kw):
+            return K.View(t, s0, n, **kw)
+
+        def R(t):   # per-pixel rows of a 32x32 tensor
+            return K.View(t, s0 * 1024, n * 1024)
+
+        def cg(l, x, y, act=True, add=None):
+            L = dl[l]
+            kw = {}
+            if tangent:
+                if act:
+                    kw = dict(mask=y, mask_kind=K.MASK_LRELU)
+            else:
+                kw = dict(bias=L.b, act=K.ACT_LRELU if act else K.ACT_NONE)
+            K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, **kw)
+
+        if not tangent:
+            K.im2col_k4s2_c3(d["img"][s0:s0 + n], d["col0"][:, s0 * 1024:(s0 + n) * 1024])
+        cg("h0", R(d["col0"]), R(rows(d["a0"])))                                   # :135
+        cg("h1", V(d["a0"]), V(d["a1"]))                                            # :136
+        cg("h2", V(d["a1"]), V(d["a2"]))                                            # :137
+        cg("h3", V(d["a2"]), V(d["a3"]), act=False)                                 # :138
+        cg("r1", V(d["a3"]), V(d["r1"]))                                            # :142
+        cg("r2", V(d["r1"]), V(d["r2"]))                                            # :143
+        cg("r3", V(d["r2"]), V(d["cat"], coff=0, c=df8), add=V(d["a3"]))            # :144-146
+        cg("efc", V(d["cond"]), V(d["e"]))                                          # :150
+        K.embed_tile(d["e"][:, s0:s0 + n], d["cat"][:, s0:s0 + n], df8)             # :153-155
+        cg("h5", V(d["cat"]), V(d["a5"]))                                           # :157
+        cg("h6", V(d["a5"]), V(d["a6"]))                                            # :158
+        if not tangent:
+            K.dout_fwd(d["a6"][:, s0:s0 + n], dl["out"].w, dl["out"].b, d["logit"][s0:s0 + n])   # :160
+
+    def d_backward(self, s0, n, seed, g0, gn, want_cond_grad):
+        """Seeded backward of d_forward through the inputs of every layer (no weight gradients).
+        Samples [g0, g0+gn) additionally get dD/d image -> d['gx'] (and dD/d cond -> d['g2'])."""
+        K, d, dl = self.K, self.d, self.dl
+        S1, DC = K.CONV_S1, K.DECONV_K4S2
+        rows = self._rows
+        df8 = 8 * self.df
+        LR = K.MASK_LRELU
+
+        def V(t, **kw):
+            return K.View(t, s0, n, **kw)
+
+        K.dout_bwd_data(d["a6"][:, s0:s0 + n], dl["out"].w, seed[s0:s0 + n], d["d_a6"][:, s0:s0 + n])
+        K.conv_gemm(S1, 1, 0, V(d["d_a6"]), dl["h6"].Wb, V(d["d_a5"]), mask=V(d["a5"]), mask_kind=LR)
+        K.conv_gemm(S1, 3, 1, V(d["d_a5"]), dl["h5"].Wb, V(d["d_cat"]), mask=V(d["cat"]), mask_kind=LR)
+        K.embed_reduce(d["d_cat"][:, s0:s0 + n], d["d_e"][:, s0:s0 + n], df8)
+        K.conv_gemm(S1, 3, 1, V(d["d_cat"], coff=0, c=df8), dl["r3"].Wb, V(d["d_r2"]), mask=V(d["r2"]), mask_kind=LR)
+        K.conv_gemm(S1, 3, 1, V(d["d_r2"]), dl["r2"].Wb, V(d["d_r1"]), mask=V(d["r1"]), mask_kind=LR)
+        K.conv_gemm(S1, 1, 0, V(d["d_r1"]), dl["r1"].Wb, V(d["d_a3"]), add=V(d["d_cat"], coff=0, c=df8))
+        K.conv_gemm(DC, 4, 0, V(d["d_a3"]), dl["h3"].Wb, V(d["d_a2"]), mask=V(d["a2"]), mask_kind=LR)
+        K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wb, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR)
+        K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wb, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR)
+        if gn > 0:
+            K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wb, K.View(d["d_col0"], 0, gn * 1024))
+            K.col2im_k4s2_c3(d["d_col0"], d["gx"], None)
+            if want_cond_grad:
+                K.conv_gemm(S1, 1, 0, K.View(d["d_e"], g0, gn), dl["efc"].Wb, K.View(d["d_cond"], 0, gn))
+                K.from_planes(d["d_cond"], d["g2"])
+
+    def d_wgrad(self, n, n_bias):
+        """Weight gradients over samples [0, n) (activations x input gradients), biases over [0, n_bias)."""
+        K, d, dl = self.K, self.d, self.dl
+        rows = self._rows
+        df8 = 8 * self.df
+
+        def V(t, **kw):
+            return K.View(t, 0, n, **kw)
+
+        def Vb(t, **kw):
+            return K.View(t, 0, n_bias, **kw)
+
+        pairs = [("h1", "a0", "d_a1", {}), ("h2", "a1", "d_a2", {}), ("h3", "a2", "d_a3", {}),
+                 ("r1", "a3", "d_r1", {}), ("r2", "r1", "d_r2", {}), ("r3", "r2", "d_cat", dict(coff=0, c=df8)),
+                 ("efc", "cond", "d_e", {}), ("h5", "cat", "d_a5", {}), ("h6", "a5", "d_a6", {})]
+        K.wgrad_gemm(K.CONV_S1, 1, K.View(d["col0"], 0, n * 1024), K.View(rows(d["d_a0"]), 0, n * 1024), dl["h0"].gw)
+        K.colsum(K.View(rows(d["d_a0"]), 0, n_bias * 1024), dl["h0"].gb)
+        for l, x, dy, kw in pairs:
+            L = dl[l]
+            K.wgrad_gemm(L.mode, L.k, V(d[x]), V(d[dy], **kw), L.gw)
+            K.colsum(Vb(d[dy], **kw), L.gb)
+        K.dout_bwd_weight(d["a6"][:, :n], d["seed"][:n], dl["out"].gw, dl["out"].gb, n_bias)
+
+    # ------------------------------------------------------------------ optimizer plumbing
+    def _adam(self, net, lr, t):
+        lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        n = self.d_n if net == "d" else self.g_n
+        self.K.adam_tf(self.flat[net], self.grad[net][:n], self.adam_m[net], self.adam_v[net], lr_t, self.beta1,
+                       self.beta2, ADAM_EPS, 1.0)
+        self.repack(net)
+
+    def _reduce(self, net):
+        if self.world > 1:
+            self.allreduce(self.grad[net])
+
+    # ------------------------------------------------------------------ the two runs of an iteration
+    def load_feed(self, x=None, x_mismatch=None, cond=None, z=None, epsilon=None, tn_eps=None):
+        """Stage inputs (fp32 host or device tensors) into the engine's device buffers."""
+        B, d, g = self.B, self.d, self.g
+        if x is not None:
+            d["img"][B:2 * B].copy_(x, non_blocking=True)
+        if x_mismatch is not None:
+            d["img"][2 * B:3 * B].copy_(x_mismatch, non_blocking=True)
+        if cond is not None:
+            self.feed["cond"].copy_(cond, non_blocking=True)
+        if z is not None:
+            g["z"].copy_(z, non_blocking=True)
+        if epsilon is not None:
+            self.feed["epsilon"].copy_(epsilon.reshape(-1), non_blocking=True)
+        if tn_eps is not None:
+            g["tn"].copy_(tn_eps, non_blocking=True)
+
+    def d_step(self, lr_d):
+        """sess.run([D_optim, kt_optim, D_loss]) -- models/wgancls/trainer.py:97."""
+        K, d, g, B = self.K, self.d, self.g, self.B
+        S = 4 * B
+        cond = self.feed["cond"]
+        self.grad["d"].zero_()
+        g["kl_scratch"].zero_()
+        self.g_forward(g["z"], cond, g["tn"], d["img"][:B], g["kl_scratch"])              # model.py:48
+        K.gp_interp(d["img"][:B], d["img"][B:2 * B], self.feed["epsilon"], d["img"][3 * B:])   # model.py:53
+        for seg in range(4):
+            K.to_planes(cond, d["cond"][:, seg * B:(seg + 1) * B])                        # cond_inp = cond (:54)
+        self.d_forward(0, S)                                                             # model.py:49-55
+        K.d_seeds(self.kt, d["seed"], B, 1.0 / self.GB)
+        K.d_sums(d["logit"], B, self.sums["d"])
+        self.d_backward(0, S, d["seed"], 3 * B, B, True)                                 # tf.gradients, :63,68
+        inv = 1.0 / self.GB
+        K.gp_penalty(d["gx"], GP_WEIGHT, inv, d["slope"], d["coef"], self.sums["d"][4:5])       # :62-65
+        K.gp_penalty(d["g2"], GP_WEIGHT, inv, d["slope2"], d["coef2"], self.sums["d"][5:6])     # :67-70
+        # second-order term: tangent (coef * g) through d_net, in place over the x_hat segment
+        K.im2col_k4s2_c3(d["gx"], d["col0"][:, 3 * B * 1024:], d["coef"])
+        K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])
+        self.d_forward(3 * B, B, tangent=True)
+        self.d_wgrad(S, 3 * B)
+        self._reduce("d")
+        K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, KT_LR)     # :79-91,100
+        self.d_t += 1
+        self._adam("d", lr_d, self.d_t)                                                  # :94-97
+
+    def g_step(self, lr_g):
+        """sess.run([G_optim, G_loss]) -- models/wgancls/trainer.py:101."""
+        K, d, g, B = self.K, self.d, self.g, self.B
+        cond = self.feed["cond"]
+        self.grad["g"].zero_()
+        self.g_forward(g["z"], cond, g["tn"], d["img"][:B], self.sums["g"][1:2])
+        K.to_planes(cond, d["cond"][:, :B])
+        self.d_forward(0, B)
+        K.g_sums(d["logit"], B, self.sums["g"])
+        self.d_backward(0, B, d["gseed"], 0, B, False)
+        self.g_backward(d["gx"])
+        self._reduce("g")
+        K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)        # model.py:92
+        for i, c in enumerate(self.bn_ch):                                               # UPDATE_OPS, :98,102
+            rows = g_rows(self, i)
+            K.bn_update_moving(self.bn_mm[i], self.bn_mv[i], self.bn_mean[i], self.bn_var[i], rows, BN_DECAY)
+        self.g_t += 1
+        self._adam("g", lr_g, self.g_t)                                                  # :103-106
+
+    def sample(self, z, cond, tn_eps, out, cond_noise=True):
+        """generator(z, cond, is_training=False) -- the sampler of model.py:57 (batch = engine batch)."""
+        self.g["kl_scratch"].zero_()
+        self.g_forward(z, cond, tn_eps, out, self.g["kl_scratch"], train=False, cond_noise=cond_noise)
+
+    def scalars_dict(self):
+        from ._lib import SCALARS
+        vals = self.scalars.detach().cpu().tolist()
+        return {n: vals[i] for i, n in enumerate(SCALARS)}
+
+
+def g_rows(eng, i):
+    """number of values per channel the i-th BatchNorm of g_net normalises over"""
+    B = eng.B
+    return [B, 16 * B, 16 * B, 16 * B, 64 * B, 64 * B, 64 * B, 64 * B, 256 * B, 1024 * B][i]

@@ -1,0 +1,266 @@
+"""Tensor-level wrappers over the C ABI: every function takes torch CUDA tensors (used purely as
+device-memory containers), builds the C descriptors and enqueues the kernel on torch's current
+stream.  ``tests/fake_kernels.py`` restates each function's contract on the CPU so that the host
+orchestration can be tested without a GPU; the product never imports it.
+
+Storage convention ("bf16 planes"): a tensor of logical shape S is a torch.bfloat16 tensor of shape
+[np, *S]; its value is the sum over the first axis (np = 1: plain bf16; np = 2: hi + lo).
+"""
+import ctypes as C
+
+import torch
+
+from . import _lib
+from ._lib import (ACT_LRELU, ACT_NONE, ACT_RELU, CONV_K4S2, CONV_S1, DECONV_K4S2, MASK_LRELU, MASK_NONE,
+                   MASK_RELU)
+
+__all__ = ["View", "CONV_S1", "CONV_K4S2", "DECONV_K4S2", "ACT_NONE", "ACT_LRELU", "ACT_RELU", "MASK_NONE",
+           "MASK_LRELU", "MASK_RELU"]
+
+
+class View:
+    """A window of a planes tensor [np, N, H, W, pitch] (a [np, rows, pitch] tensor has H = W = 1):
+    samples [n0, n0 + n) and channels [coff, coff + c)."""
+
+    def __init__(self, t, n0=0, n=None, coff=0, c=None):
+        assert t.dtype == torch.bfloat16 and t.is_contiguous()
+        if t.dim() == 3:
+            self.N, self.H, self.W, self.pitch = t.shape[1], 1, 1, t.shape[2]
+        else:
+            assert t.dim() == 5, t.shape
+            self.N, self.H, self.W, self.pitch = t.shape[1:]
+        self.t = t
+        self.np = t.shape[0]
+        self.n0 = n0
+        self.n = self.N - n0 if n is None else n
+        self.coff = coff
+        self.c = self.pitch - coff if c is None else c
+        assert 0 <= self.n0 and self.n0 + self.n <= self.N and self.coff + self.c <= self.pitch
+
+    def values(self):
+        """fp32 value of the window (test helper; works on any device)."""
+        t = self.t.reshape(self.np, self.N, self.H, self.W, self.pitch)
+        return t[:, self.n0:self.n0 + self.n, :, :, self.coff:self.coff + self.c].float().sum(0)
+
+    def _act(self):
+        a = _lib.Act()
+        esz = 2
+        a.ptr = self.t.data_ptr() + self.n0 * self.H * self.W * self.pitch * esz
+        a.plane_stride = self.t.stride(0)
+        a.n, a.h, a.w, a.c = self.n, self.H, self.W, self.c
+        a.pitch, a.coff = self.pitch, self.coff
+        return a
+
+
+def _null_act():
+    return _lib.Act()
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def _f32(t):
+    assert t.dtype == torch.float32 and t.is_contiguous()
+    return C.c_void_p(t.data_ptr())
+
+
+def _ps(t):
+    return t.stride(0)
+
+
+def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE):
+    """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, w_cout, w_cin]."""
+    d = _lib.ConvGemmDesc()
+    d.mode, d.k, d.flip, d.np = mode, k, flip, x.np
+    d.x = x._act()
+    assert w.dtype == torch.bfloat16 and w.dim() == 4 and w.is_contiguous() and w.shape[0] == x.np
+    d.w = w.data_ptr()
+    d.w_plane_stride = w.stride(0)
+    d.w_cout, d.w_cin = w.shape[2], w.shape[3]
+    d.y = y._act()
+    d.bias = None if bias is None else bias.data_ptr()
+    d.add = add._act() if add is not None else _null_act()
+    d.mask = mask._act() if mask is not None else _null_act()
+    d.act, d.mask_kind = act, mask_kind
+    _lib.call("t2i_conv_gemm", C.byref(d), _stream())
+
+
+def wgrad_gemm(mode, k, x, dy, dw, split_k=0):
+    """dw[tap, co, ci] += sum_pixels dy[pixel, co] * x[pixel + tap, ci]; dw fp32 [taps, cout, cin]."""
+    d = _lib.WgradDesc()
+    d.mode, d.k, d.np = mode, k, x.np
+    d.x, d.dy = x._act(), dy._act()
+    assert dw.dtype == torch.float32 and dw.dim() == 3 and dw.is_contiguous()
+    d.dw = dw.data_ptr()
+    d.cout, d.cin = dw.shape[1], dw.shape[2]
+    d.split_k = split_k
+    _lib.call("t2i_wgrad_gemm", C.byref(d), _stream())
+
+
+def to_planes(src, dst, row_scale=None):
+    rows = src.shape[0]
+    cols = src.numel() // rows
+    _lib.call("t2i_to_planes", _f32(src), _p(dst), _ps(dst), dst.shape[0], rows, cols, _p(row_scale), _stream())
+
+
+def from_planes(src, dst):
+    _lib.call("t2i_from_planes", _p(src), _ps(src), src.shape[0], _f32(dst), dst.numel(), _stream())
+
+
+def im2col_k4s2_c3(img, col, sample_scale=None):
+    n, h, w, _ = img.shape
+    _lib.call("t2i_im2col_k4s2_c3", _f32(img), n, h, w, _p(sample_scale), _p(col), _ps(col), col.shape[0], _stream())
+
+
+def col2im_k4s2_c3(col, img, bias3=None):
+    n, h, w, _ = img.shape
+    _lib.call("t2i_col2im_k4s2_c3", _p(col), _ps(col), col.shape[0], n, h, w, _p(bias3), _f32(img), _stream())
+
+
+def conv3x3_c3_tanh_fwd(x, w, b, y):
+    n, h, wd, _ = x.shape
+    _lib.call("t2i_conv3x3_c3_tanh_fwd", _f32(x), _f32(w), _f32(b), _f32(y), n, h, wd, _stream())
+
+
+def conv3x3_c3_tanh_bwd(x, w, y, dy, dx, dw, db, dx_sum=None):
+    n, h, wd, _ = x.shape
+    _lib.call("t2i_conv3x3_c3_tanh_bwd", _f32(x), _f32(w), _f32(y), _f32(dy), _f32(dx), _f32(dw), _f32(db),
+              _p(dx_sum), n, h, wd, _stream())
+
+
+def colsum(src, out):
+    """out[c] += sum over all pixels of the view (bias gradients)."""
+    a = src._act()
+    rows = src.n * src.H * src.W
+    _lib.call("t2i_colsum", C.c_void_p(a.ptr), a.plane_stride, src.np, rows, src.c, src.pitch, src.coff, _f32(out),
+              _stream())
+
+
+def _rows_c(t):
+    c = t.shape[-1]
+    return t[0].numel() // c, c
+
+
+def bn_stats(x, mean, rstd, var, eps):
+    rows, c = _rows_c(x)
+    _lib.call("t2i_bn_stats", _p(x), _ps(x), x.shape[0], rows, c, _f32(mean), _f32(rstd), _f32(var), eps, _stream())
+
+
+def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
+    rows, c = _rows_c(x)
+    _lib.call("t2i_bn_apply", _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(beta), _p(residual),
+              0 if residual is None else _ps(residual), _p(y), _ps(y), x.shape[0], rows, c, int(relu), _stream())
+
+
+def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta):
+    rows, c = _rows_c(x)
+    _lib.call("t2i_bn_bwd_reduce", _p(dy), _ps(dy), _p(x), _ps(x), _f32(mean), _f32(rstd), x.shape[0], rows, c,
+              _f32(dgamma), _f32(dbeta), _stream())
+
+
+def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta, dx):
+    rows, c = _rows_c(x)
+    _lib.call("t2i_bn_bwd_apply", _p(dy), _ps(dy), _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(dgamma),
+              _f32(dbeta), _p(dx), _ps(dx), x.shape[0], rows, c, _stream())
+
+
+def bn_update_moving(mm, mv, mean, var, rows, decay):
+    _lib.call("t2i_bn_update_moving", _f32(mm), _f32(mv), _f32(mean), _f32(var), rows, mm.numel(), decay, _stream())
+
+
+def act_bwd(dy, y, dst, mask_kind):
+    _lib.call("t2i_act_bwd", _p(dy), _ps(dy), _p(y), _ps(y), _p(dst), _ps(dst), dy.shape[0], dy[0].numel(), mask_kind,
+              _stream())
+
+
+def embed_tile(e, cat, coff):
+    """e planes [np, s, c] -> channels [coff, coff + c) of cat planes [np, s, h, w, pitch]."""
+    s, c = e.shape[1], e.shape[2]
+    hw = cat.shape[2] * cat.shape[3]
+    _lib.call("t2i_embed_tile", _p(e), _ps(e), _p(cat), _ps(cat), e.shape[0], s, c, cat.shape[4], coff, hw, _stream())
+
+
+def embed_reduce(dcat, de, coff):
+    s, c = de.shape[1], de.shape[2]
+    hw = dcat.shape[2] * dcat.shape[3]
+    _lib.call("t2i_embed_reduce", _p(dcat), _ps(dcat), _p(de), _ps(de), de.shape[0], s, c, dcat.shape[4], coff, hw,
+              _stream())
+
+
+def dout_fwd(a, w, b, logit):
+    s = a.shape[1]
+    _lib.call("t2i_dout_fwd", _p(a), _ps(a), a.shape[0], _f32(w), _f32(b), _f32(logit), s, a[0, 0].numel(), _stream())
+
+
+def dout_bwd_data(a, w, seed, da):
+    s = a.shape[1]
+    _lib.call("t2i_dout_bwd_data", _p(a), _ps(a), a.shape[0], _f32(w), _f32(seed), _p(da), _ps(da), s,
+              a[0, 0].numel(), _stream())
+
+
+def dout_bwd_weight(a, seed, dw, db, s_bias):
+    s = a.shape[1]
+    _lib.call("t2i_dout_bwd_weight", _p(a), _ps(a), a.shape[0], _f32(seed), _f32(dw), _p(db), s, s_bias,
+              a[0, 0].numel(), _stream())
+
+
+def gp_interp(g, x, eps, xhat):
+    n = g.shape[0]
+    _lib.call("t2i_gp_interp", _f32(g), _f32(x), _f32(eps), _f32(xhat), n, g[0].numel(), _stream())
+
+
+def gp_penalty(grad, weight, inv_global_batch, slope, coef, pen_sum):
+    n = grad.shape[0]
+    _lib.call("t2i_gp_penalty", _f32(grad), n, grad[0].numel(), weight, inv_global_batch, _f32(slope), _f32(coef),
+              _f32(pen_sum), _stream())
+
+
+def ca_fwd(ms, z, tn_eps, zc, kl_sum):
+    b, z_dim = z.shape
+    ce = tn_eps.shape[1]
+    _lib.call("t2i_ca_fwd", _p(ms), _ps(ms), _f32(z), _f32(tn_eps), _p(zc), _ps(zc), ms.shape[0], b, z_dim, ce,
+              _p(kl_sum), _stream())
+
+
+def ca_bwd(ms, dzc, tn_eps, dms, z_dim, kl_scale):
+    b, ce = tn_eps.shape
+    _lib.call("t2i_ca_bwd", _p(ms), _ps(ms), _p(dzc), _ps(dzc), _f32(tn_eps), _p(dms), _ps(dms), ms.shape[0], b, z_dim,
+              ce, kl_scale, _stream())
+
+
+def d_seeds(kt, seed, b, inv_global_batch):
+    _lib.call("t2i_d_seeds", _f32(kt), _f32(seed), b, inv_global_batch, _stream())
+
+
+def d_sums(logit, b, sums):
+    _lib.call("t2i_d_sums", _f32(logit), b, _f32(sums), _stream())
+
+
+def d_scalars(sums, kt, scalars, global_batch, gp_weight, kt_lr):
+    _lib.call("t2i_d_scalars", _f32(sums), _f32(kt), _f32(scalars), global_batch, gp_weight, kt_lr, _stream())
+
+
+def g_sums(logit_fake, b, sums):
+    _lib.call("t2i_g_sums", _f32(logit_fake), b, _f32(sums), _stream())
+
+
+def g_scalars(sums, scalars, global_batch, ce, kl_coeff):
+    _lib.call("t2i_g_scalars", _f32(sums), _f32(scalars), global_batch, ce, kl_coeff, _stream())
+
+
+def pack_weight(w, fwd=None, bwd=None):
+    """fp32 master [taps, cout, cin] -> planes fwd [np, taps, cout, cin] and bwd [np, taps, cin, cout]."""
+    taps, cout, cin = w.shape
+    ref = fwd if fwd is not None else bwd
+    _lib.call("t2i_pack_weight", _f32(w), taps, cout, cin, _p(fwd), 0 if fwd is None else _ps(fwd), _p(bwd),
+              0 if bwd is None else _ps(bwd), ref.shape[0], _stream())
+
+
+def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
+    _lib.call("t2i_adam_tf", _f32(theta), _f32(grad), _f32(m), _f32(v), theta.numel(), lr_t, beta1, beta2, eps,
+              grad_scale, _stream())
