@@ -24,7 +24,11 @@ def val(t):
 
 
 def put(t, v):
-    """round v into the planes tensor t ([np, ...])"""
+    """round v into the planes tensor t ([np, ...]); float64 "planes" store the value exactly"""
+    if t.dtype == torch.float64:
+        t.zero_()
+        t[0].copy_(v.reshape(t.shape[1:]))
+        return
     v = v.to(torch.float32).reshape(t.shape[1:])
     hi = v.to(torch.bfloat16)
     t[0].copy_(hi)
@@ -34,7 +38,6 @@ def put(t, v):
 
 class View:
     def __init__(self, t, n0=0, n=None, coff=0, c=None):
-        assert t.dtype == torch.bfloat16
         if t.dim() == 3:
             self.N, self.H, self.W, self.pitch = t.shape[1], 1, 1, t.shape[2]
         else:
@@ -53,6 +56,10 @@ class View:
 
     def put(self, v):
         w = self._win()
+        if self.t.dtype == torch.float64:
+            w.zero_()
+            w[0].copy_(v)
+            return
         v = v.to(torch.float32)
         hi = v.to(torch.bfloat16)
         w[0].copy_(hi)
@@ -104,7 +111,7 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0):
     w = torch.zeros(taps, dyv.shape[-1], xv.shape[-1], dtype=torch.float64, requires_grad=True)
     y = _conv_core(mode, k, 0, xv, w)
     (g,) = torch.autograd.grad((y * dyv).sum(), [w])
-    dw[:, :g.shape[1], :g.shape[2]] += g.float()
+    dw[:, :g.shape[1], :g.shape[2]] += g
 
 
 def to_planes(src, dst, row_scale=None):
@@ -115,7 +122,7 @@ def to_planes(src, dst, row_scale=None):
 
 
 def from_planes(src, dst):
-    dst.copy_(val(src).float().reshape(dst.shape))
+    dst.copy_(val(src).reshape(dst.shape))
 
 
 def im2col_k4s2_c3(img, col, sample_scale=None):
@@ -141,13 +148,13 @@ def col2im_k4s2_c3(col, img, bias3=None):
     out = acc[:, 1:h + 1, 1:w + 1, :]
     if bias3 is not None:
         out = out + bias3.double()
-    img.copy_(out.float())
+    img.copy_(out)
 
 
 def conv3x3_c3_tanh_fwd(x, w, b, y):
     wk = w.double().view(3, 3, 3, 3).permute(3, 2, 0, 1)
     v = F.conv2d(x.double().permute(0, 3, 1, 2), wk, b.double(), padding=1)
-    y.copy_(torch.tanh(v).permute(0, 2, 3, 1).float())
+    y.copy_(torch.tanh(v).permute(0, 2, 3, 1))
 
 
 def conv3x3_c3_tanh_bwd(x, w, y, dy, dx, dw, db, dx_sum=None):
@@ -157,22 +164,22 @@ def conv3x3_c3_tanh_bwd(x, w, y, dy, dx, dw, db, dx_sum=None):
     v = F.conv2d(xd.permute(0, 3, 1, 2), wd.permute(3, 2, 0, 1), bd, padding=1).permute(0, 2, 3, 1)
     dl = dy.double() * (1 - y.double() ** 2)
     gx, gw, gb = torch.autograd.grad((v * dl).sum(), [xd, wd, bd])
-    dx.copy_(gx.float())
-    dw += gw.float().reshape(dw.shape)
-    db += gb.float()
+    dx.copy_(gx)
+    dw += gw.reshape(dw.shape)
+    db += gb
     if dx_sum is not None:
-        dx_sum += gx.sum((0, 1, 2)).float()
+        dx_sum += gx.sum((0, 1, 2))
 
 
 def colsum(src, out):
-    out[:src.c] += src.values().reshape(-1, src.c).sum(0).float()
+    out[:src.c] += src.values().reshape(-1, src.c).sum(0)
 
 
 def bn_stats(x, mean, rstd, var, eps):
     v = val(x).reshape(-1, x.shape[-1])
     m = v.mean(0)
     s = v.var(0, unbiased=False)
-    mean.copy_(m.float()); var.copy_(s.float()); rstd.copy_(torch.rsqrt(s + eps).float())
+    mean.copy_(m); var.copy_(s); rstd.copy_(torch.rsqrt(s + eps))
 
 
 def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
@@ -187,8 +194,8 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta):
     g = val(dy).reshape(-1, x.shape[-1])
     xh = (val(x).reshape(-1, x.shape[-1]) - mean.double()) * rstd.double()
-    dbeta += g.sum(0).float()
-    dgamma += (g * xh).sum(0).float()
+    dbeta += g.sum(0)
+    dgamma += (g * xh).sum(0)
 
 
 def bn_bwd_apply(dy, x, mean, rstd, gamma, dgamma, dbeta, dx):
@@ -222,7 +229,7 @@ def embed_reduce(dcat, de, coff):
 
 def dout_fwd(a, w, b, logit):
     s = a.shape[1]
-    logit[:s] = (val(a).reshape(s, -1) @ w.double().reshape(-1) + b.double()[0]).float()
+    logit[:s] = (val(a).reshape(s, -1) @ w.double().reshape(-1) + b.double()[0])
 
 
 def dout_bwd_data(a, w, seed, da):
@@ -234,9 +241,9 @@ def dout_bwd_data(a, w, seed, da):
 
 def dout_bwd_weight(a, seed, dw, db, s_bias):
     s = a.shape[1]
-    dw += (seed.double()[:s, None] * val(a).reshape(s, -1)).sum(0).float().reshape(dw.shape)
+    dw += (seed.double()[:s, None] * val(a).reshape(s, -1)).sum(0).reshape(dw.shape)
     if db is not None and s_bias > 0:
-        db += seed[:s_bias].double().sum().float()
+        db += seed[:s_bias].double().sum()
 
 
 def gp_interp(g, x, eps, xhat):
@@ -248,9 +255,9 @@ def gp_penalty(grad, weight, inv_global_batch, slope, coef, pen_sum):
     n = grad.shape[0]
     s = grad.double().reshape(n, -1).pow(2).sum(1).sqrt()
     ex = torch.clamp(s - 1, min=0)
-    slope[:n] = s.float()
-    coef[:n] = torch.where(ex > 0, weight * 2 * ex / s * inv_global_batch, torch.zeros_like(s)).float()
-    pen_sum += (ex * ex).sum().float()
+    slope[:n] = s
+    coef[:n] = torch.where(ex > 0, weight * 2 * ex / s * inv_global_batch, torch.zeros_like(s))
+    pen_sum += (ex * ex).sum()
 
 
 def ca_fwd(ms, z, tn_eps, zc, kl_sum):
@@ -260,7 +267,7 @@ def ca_fwd(ms, z, tn_eps, zc, kl_sum):
     c = mean + torch.exp(ls) * tn_eps.double()
     put(zc, torch.cat([z.double(), c], 1))
     if kl_sum is not None:
-        kl_sum += (-ls + 0.5 * (-1 + torch.exp(2 * ls) + mean * mean)).sum().float()
+        kl_sum += (-ls + 0.5 * (-1 + torch.exp(2 * ls) + mean * mean)).sum()
 
 
 def ca_bwd(ms, dzc, tn_eps, dms, z_dim, kl_scale):

@@ -48,8 +48,12 @@ class Layer:
 
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
-                 beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None):
+                 beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
+                 f32_dtype=torch.float32):
+        # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
+        # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
+        self.act_dtype, self.f32_dtype = act_dtype, f32_dtype
         self.Z, self.E, self.ce, self.gf, self.df = z_dim, embed_dim, ce, gf, df
         self.beta1, self.beta2, self.kl_coeff = beta1, beta2, kl_coeff
         self.world, self.allreduce = world, allreduce
@@ -122,7 +126,7 @@ class Engine:
 
         self.d_n, self.d_table = layout(self.dl, False)
         self.g_n, self.g_table = layout(self.gl, True)
-        f32 = dict(device=self.dev, dtype=torch.float32)
+        f32 = dict(device=self.dev, dtype=self.f32_dtype)
         self.flat = {"d": torch.zeros(self.d_n, **f32), "g": torch.zeros(self.g_n, **f32)}
         self.grad = {"d": torch.zeros(self.d_n + SUMS, **f32), "g": torch.zeros(self.g_n + SUMS, **f32)}
         self.adam_m = {k: torch.zeros_like(v) for k, v in self.flat.items()}
@@ -133,7 +137,7 @@ class Engine:
             for name, (off, n) in table.items():
                 self.P[net + "." + name] = self.flat[net][off:off + n]
                 self.G[net + "." + name] = self.grad[net][off:off + n]
-        bf = dict(device=self.dev, dtype=torch.bfloat16)
+        bf = dict(device=self.dev, dtype=self.act_dtype)
         for net, layers in (("d", self.dl), ("g", self.gl)):
             for l in layers.values():
                 l.w, l.b = self.P["%s.%s.w" % (net, l.name)], self.P["%s.%s.b" % (net, l.name)]
@@ -223,7 +227,7 @@ class Engine:
 
     def set_params_tf(self, p):
         """Load parameters given in the reference's TF variable layout (oracle / checkpoint names)."""
-        p = {k: torch.as_tensor(v).detach().to("cpu", torch.float32) for k, v in p.items()}
+        p = {k: torch.as_tensor(v).detach().to("cpu", self.f32_dtype) for k, v in p.items()}
         for net, layers in (("d", self.dl), ("g", self.gl)):
             for l in layers.values():
                 self.P["%s.%s.w" % (net, l.name)].copy_(self._w_to_kernel(l, p).reshape(-1))
@@ -278,8 +282,8 @@ class Engine:
         B, S, np_ = self.B, 4 * self.B, self.np
         df, gf, ce, E, Z = self.df, self.gf, self.ce, self.E, self.Z
         C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
-        bf = dict(device=self.dev, dtype=torch.bfloat16)
-        f32 = dict(device=self.dev, dtype=torch.float32)
+        bf = dict(device=self.dev, dtype=self.act_dtype)
+        f32 = dict(device=self.dev, dtype=self.f32_dtype)
 
         def planes(*shape):
             return torch.zeros(np_, *shape, **bf)
