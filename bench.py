@@ -1,0 +1,292 @@
+#!/usr/bin/env python
+"""bench.py -- images/sec of one wgancls iteration (D+GP run, then G run) at 64x64, per BASELINE.json.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch 256] [--impl ours|reference]
+    python -m torch.distributed.run --nproc-per-node N ... bench.py --gpus N ...     (N > 1)
+
+A step is one trainer iteration (models/wgancls/trainer.py:97-102 of the reference) on one
+synthetic batch of 256 images per GPU (BASELINE config 2; config 3 = 8 x 256, weak scaling), bf16
+throughput mode.  `value`: inputs already resident in HBM.  `e2e`: the same iteration through the
+reference-facing API (WGanCls.run with host feed dicts): pinned-host -> device copies of the feeds
+and a device -> host read of D_loss / G_loss inside the timed region.  `roofline`: the dominant
+kernel (conv_gemm_kernel, all of its launches in a step) timed with CUDA events on the launch stream.
+`cpu_baseline` / `--impl reference`: the reference's TF-1.4 graph cannot run, so the
+CPU arm is the oracle port (oracle/wgancls_oracle.py, PyTorch-CPU fp32, all host threads) on
+BASELINE config 1 (batch 16).  One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "images/sec (G+D+GP step) 64x64 wgancls"
+GFLOP_PER_IMAGE = 28.585          # 2 * (4 G_f + 15 D_f) MACs per image per iteration
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            p = json.load(f)
+        return {"bf16_burst": p["bf16_tflops"], "bf16_sustained": p["bf16_tflops_sustained"], "hbm": p["hbm_gbs"],
+                "source": "measured (MEASURED_PEAKS.json)"}
+    return {"bf16_burst": 1590.0, "bf16_sustained": 1400.0, "hbm": 6650.0, "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """samples nvidia-smi clocks / throttle reasons during the timed region"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for n, v in zip(names, r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        mx = [int(float(r[1])) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def oracle_cpu_throughput(batch, steps, warmup):
+    """images/s of the oracle port (one D run + one G run per step) on the host cores."""
+    import torch
+    from oracle import wgancls_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cfg = O.OracleCfg(batch_size=batch)
+    p = O.init_params(cfg, 0, torch.float32)
+    st = O.new_state(p)
+    feed = O.make_feed(cfg, 1234, torch.float32)
+    for _ in range(warmup):
+        O.iteration(p, st, feed, cfg)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        O.iteration(p, st, feed, cfg)
+    dt = time.perf_counter() - t0
+    return batch * steps / dt, dt / steps
+
+
+def model_cfg(batch):
+    from t2i_b200.utils.config import config_from_yaml
+    cfg = config_from_yaml(os.path.join(ROOT, "text-to-image_b200", "models", "wgancls", "cfg", "flowers.yml"))
+    cfg.TRAIN.BATCH_SIZE = batch
+    return cfg
+
+
+def run_reference(args, rank):
+    """--impl reference: the CPU arm.  Rank 0 alone works; other ranks exit 0."""
+    if rank != 0:
+        return
+    batch = 16
+    ips, spi = oracle_cpu_throughput(batch, args.steps, max(args.warmup, 1))
+    line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": spi * 1e3, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "wgancls 64x64, batch=16 per step (BASELINE config 1), 1024-d random text embeds, "
+                                   "CPU restatement of the reference's TF-1.4 graph (TF 1.4 not installable)"},
+            "cpu_baseline": {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+                             "sample": "%d full iterations (D run + G run) at batch 16, fp32, PyTorch-CPU, all host threads"
+                                       % args.steps},
+            "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-out", default=None, help="write the per-launch GEMM table (JSON) here")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from t2i_b200 import _lib, kernels
+    from t2i_b200.models.wgancls.model import WGanCls
+
+    B = args.batch
+    model = WGanCls(model_cfg(B), precision=args.precision, device=dev, distributed=True if world > 1 else None)
+    model.initialize(0)                       # reference init, identical on all ranks
+    eng = model._train_engine()
+    gen = torch.Generator().manual_seed(1234 + rank)
+    host = {
+        "x": (torch.rand(B, 64, 64, 3, generator=gen) * 2 - 1).pin_memory(),
+        "x_mismatch": (torch.rand(B, 64, 64, 3, generator=gen) * 2 - 1).pin_memory(),
+        "cond": torch.randn(B, 1024, generator=gen).pin_memory(),
+        "z": torch.randn(B, 128, generator=gen).pin_memory(),
+        "epsilon": torch.rand(B, 1, 1, 1, generator=gen).pin_memory(),
+    }
+    model.seed_noise(99 + rank)
+    lr = 1e-4
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ------------------------------------------------------------ device-resident timing (`value`)
+    eng.load_feed(x=host["x"], x_mismatch=host["x_mismatch"], cond=host["cond"], z=host["z"], epsilon=host["epsilon"])
+    tn = [torch.empty(B, 128, device=dev).normal_().clamp_(-2, 2) for _ in range(2)]
+
+    def resident_step():
+        eng.g["tn"].copy_(tn[0])
+        eng.d_step(lr)
+        eng.g["tn"].copy_(tn[1])
+        eng.g_step(lr)
+
+    for _ in range(args.warmup):
+        resident_step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        resident_step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() - l0
+    clocks = sampler.finish()
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+    finite = all(v == v for v in eng.scalars_dict().values())
+
+    # ------------------------------------------------------------ end-to-end through the public API
+    def e2e_step():
+        fd = {model.x: host["x"], model.x_mismatch: host["x_mismatch"], model.cond: host["cond"], model.z: host["z"],
+              model.epsilon: host["epsilon"], model.learning_rate_d: lr, model.learning_rate_g: lr}
+        d_loss = model.run([model.D_optim, model.kt_optim, model.D_loss], fd)[2]
+        g_loss = model.run([model.G_optim, model.G_loss], fd)[1]
+        return d_loss, g_loss
+
+    for _ in range(3):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * args.steps / float(dt.item())
+    h2d = sum(host[k].numel() * 4 for k in ("x", "x_mismatch", "cond", "z", "epsilon")) + \
+        sum(host[k].numel() * 4 for k in ("cond", "z"))       # the G run re-feeds cond and z
+    d2h = 2 * 16 * 4                                           # the scalars vector, read once per run
+
+    # ------------------------------------------------------------ per-launch GEMM timing (roofline)
+    pk = peaks()
+    roofline = None
+    if rank == 0:
+        kernels.PROFILE = []
+        psteps = 2
+        for _ in range(psteps):
+            resident_step()
+        torch.cuda.synchronize()
+        rows = [(k, tag, fl, nb, a.elapsed_time(b)) for k, tag, fl, nb, a, b in kernels.PROFILE]
+        kernels.PROFILE = None
+        agg = {}
+        for k, tag, fl, nb, t in rows:
+            a = agg.setdefault(k, [0.0, 0.0, 0.0, 0])
+            a[0] += fl; a[1] += nb; a[2] += t; a[3] += 1
+        top = max(agg, key=lambda k: agg[k][2])
+        fl, nb, t, n = agg[top]
+        achieved = fl / (t * 1e-3) / 1e12
+        roofline = {"kernel": top + "_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                    "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
+                    "launches_per_step": n // psteps, "ms_per_step_in_kernel": t / psteps,
+                    "share_of_step": (t / psteps) / ms_per_step,
+                    "whole_step_tflops": GFLOP_PER_IMAGE * 1e9 * value / world / 1e12,
+                    "whole_step_frac_of_sustained": GFLOP_PER_IMAGE * 1e9 * value / world / 1e12 / pk["bf16_sustained"],
+                    "other_kernels": {k: {"ms_per_step": v[2] / psteps, "tflops": v[0] / (v[2] * 1e-3) / 1e12}
+                                      for k, v in agg.items() if k != top}}
+        if args.profile_out:
+            per = {}
+            for k, tag, fl, nb, t in rows:
+                a = per.setdefault(k + " " + tag, [0.0, 0.0, 0.0, 0])
+                a[0] += fl; a[1] += nb; a[2] += t; a[3] += 1
+            table = [{"launch": k, "calls_per_step": v[3] / psteps, "ms_per_step": v[2] / psteps,
+                      "tflops": v[0] / (v[2] * 1e-3) / 1e12, "algo_gbytes_per_s": v[1] / (v[2] * 1e-3) / 1e9}
+                     for k, v in sorted(per.items(), key=lambda kv: -kv[1][2])]
+            with open(args.profile_out, "w") as f:
+                json.dump({"ms_per_step": ms_per_step, "table": table}, f, indent=1)
+
+    # ------------------------------------------------------------ CPU baseline (rank 0, N = 1)
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        ips, spi = oracle_cpu_throughput(16, 3, 1)
+        cpu = {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
+               "sample": "3 full iterations (D run + G run) at batch 16 (BASELINE config 1), fp32, PyTorch-CPU oracle port, "
+                         "all host threads; %.2f s per iteration" % spi}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16 (split x3, parity mode)",
+                "data": "synthetic",
+                "config": {"workload": "wgancls 64x64, batch=%d per GPU (BASELINE config %s), 1024-d random text embeds, "
+                                       "GF=DF=128, one D+GP run then one G run per step (N_CRITIC=1), TF-form Adam, "
+                                       "reference init" % (B, "2" if world == 1 else "3-style weak scaling"),
+                           "global_batch": B * world, "parallelism": "dp%d (batch shards, one NCCL allreduce per optimizer step)" % world,
+                           "l2": "per-step working set (activations + gradients > 2 GB) exceeds the 126 MB L2; no explicit flush",
+                           "bn": "per-replica batch statistics" if world > 1 else "single replica"},
+                "roofline": roofline, "cpu_baseline": cpu,
+                "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
+                "gpu_launches": int(launches), "clocks": clocks, "finite": bool(finite)}
+        print(json.dumps(line))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

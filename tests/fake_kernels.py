@@ -85,7 +85,8 @@ def _conv_core(mode, k, flip, x, w):
     return y.permute(0, 2, 3, 1)
 
 
-def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE):
+def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
+              algo_scale=1.0):
     xv = x.values()
     wv = val(w)[:, :y.c, :xv.shape[-1]]
     v = _conv_core(mode, k, flip, xv, wv)
@@ -104,7 +105,7 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     y.put(v)
 
 
-def wgrad_gemm(mode, k, x, dy, dw, split_k=0):
+def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
     xv = x.values().requires_grad_(False)
     dyv = dy.values()
     taps, co, ci = dw.shape

@@ -164,3 +164,222 @@ def test_wgrad_gemm(K, case, np_):
     K.wgrad_gemm(mode, k, K.View(x.cuda()), K.View(dy.cuda()), dwg, split_k=3)
     torch.cuda.synchronize()
     check_close(name + "_acc", dwg.cpu(), 2 * dw, 2e-5 if np_ == 2 else 1e-4, 10.0)
+
+
+# ------------------------------------------------------------------------------------------
+# HBM-bound kernels
+def both(np_, shape, gen, scale=1.0):
+    t = rand_planes(np_, shape, gen, scale)
+    return t, t.cuda()
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_planes_im2col_col2im(K, np_):
+    gen = torch.Generator().manual_seed(1)
+    src = torch.randn(6, 40, generator=gen)
+    rs = torch.rand(6, generator=gen)
+    dst = torch.zeros(np_, 6, 40, dtype=torch.bfloat16)
+    fk.to_planes(src, dst, rs)
+    dg = torch.zeros_like(dst).cuda()
+    K.to_planes(src.cuda(), dg, rs.cuda())
+    assert torch.equal(dg.cpu(), dst)
+    back = torch.zeros(6, 40, device="cuda")
+    K.from_planes(dg, back)
+    np.testing.assert_allclose(back.cpu().numpy(), fk.val(dst).float().numpy(), rtol=1e-6)
+    img = torch.rand(3, 16, 16, 3, generator=gen) * 2 - 1
+    sc = torch.rand(3, generator=gen) + 0.5
+    col = torch.zeros(np_, 3 * 64, 64, dtype=torch.bfloat16)
+    fk.im2col_k4s2_c3(img, col, sc)
+    cg = torch.full_like(col, 3.0).cuda()
+    K.im2col_k4s2_c3(img.cuda(), cg, sc.cuda())
+    check_close("im2col", fk.val(cg.cpu()), fk.val(col), 2.0 ** -8 if np_ == 1 else 1e-5, 1e-3)
+    c2, c2g = both(np_, (3 * 64, 64), gen)
+    bias = torch.randn(3, generator=gen)
+    out = torch.zeros(3, 16, 16, 3)
+    fk.col2im_k4s2_c3(c2, out, bias)
+    og = torch.zeros(3, 16, 16, 3, device="cuda")
+    K.col2im_k4s2_c3(c2g, og, bias.cuda())
+    check_close("col2im", og.cpu(), out, 1e-5, 1.0)
+
+
+def test_conv3x3_c3_tanh(K):
+    gen = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 16, 16, 3, generator=gen)
+    w = torch.randn(3, 3, 3, 3, generator=gen) * 0.3
+    b = torch.randn(3, generator=gen) * 0.1
+    y = torch.zeros_like(x)
+    fk.conv3x3_c3_tanh_fwd(x, w, b, y)
+    yg = torch.zeros_like(x).cuda()
+    K.conv3x3_c3_tanh_fwd(x.cuda(), w.cuda(), b.cuda(), yg)
+    check_close("c9 fwd", yg.cpu(), y, 1e-5, 1.0)
+    dy = torch.randn(3, 16, 16, 3, generator=gen)
+    dx, dw, db, dxs = torch.zeros_like(x), torch.zeros(81), torch.zeros(3), torch.zeros(3)
+    fk.conv3x3_c3_tanh_bwd(x, w, y, dy, dx, dw, db, dxs)
+    dxg, dwg, dbg, dxsg = [torch.zeros_like(t).cuda() for t in (dx, dw, db, dxs)]
+    K.conv3x3_c3_tanh_bwd(x.cuda(), w.cuda(), yg, dy.cuda(), dxg, dwg, dbg, dxsg)
+    check_close("c9 dx", dxg.cpu(), dx, 1e-4, 1.0)
+    check_close("c9 dw", dwg.cpu(), dw, 1e-4, 1.0)
+    check_close("c9 db", dbg.cpu(), db, 1e-4, 1.0)
+    check_close("c9 dxsum", dxsg.cpu(), dxs, 1e-4, 1.0)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("rows,c", [(64, 16384), (4096, 256), (2048, 24), (70000, 128)])
+def test_batch_norm_kernels(K, np_, rows, c):
+    gen = torch.Generator().manual_seed(3)
+    x, xg = both(np_, (rows, c), gen, 2.0)
+    dy, dyg = both(np_, (rows, c), gen)
+    res, resg = both(np_, (rows, c), gen)
+    gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    mean, rstd, var = torch.zeros(c), torch.zeros(c), torch.zeros(c)
+    fk.bn_stats(x, mean, rstd, var, 1e-5)
+    mg, rg, vg = [torch.zeros(c, device="cuda") for _ in range(3)]
+    K.bn_stats(xg, mg, rg, vg, 1e-5)
+    check_close("bn mean", mg.cpu(), mean, 1e-4, 1.0)
+    check_close("bn var", vg.cpu(), var, 1e-4, 1.0)
+    check_close("bn rstd", rg.cpu(), rstd, 1e-4, 1.0)
+    y = torch.zeros_like(x)
+    fk.bn_apply(x, mean, rstd, gamma, beta, y, res, True)
+    yg = torch.zeros_like(x).cuda()
+    K.bn_apply(xg, mean.cuda(), rstd.cuda(), gamma.cuda(), beta.cuda(), yg, resg, True)
+    check_close("bn apply", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    dga, dbe = torch.zeros(c), torch.zeros(c)
+    fk.bn_bwd_reduce(dy, x, mean, rstd, dga, dbe)
+    dgag, dbeg = torch.zeros(c, device="cuda"), torch.zeros(c, device="cuda")
+    K.bn_bwd_reduce(dyg, xg, mean.cuda(), rstd.cuda(), dgag, dbeg)
+    check_close("bn dgamma", dgag.cpu(), dga, 2e-4, 5.0)
+    check_close("bn dbeta", dbeg.cpu(), dbe, 2e-4, 5.0)
+    dx = torch.zeros_like(x)
+    fk.bn_bwd_apply(dy, x, mean, rstd, gamma, dga, dbe, dx)
+    dxg = torch.zeros_like(x).cuda()
+    K.bn_bwd_apply(dyg, xg, mean.cuda(), rstd.cuda(), gamma.cuda(), dga.cuda(), dbe.cuda(), dxg)
+    check_close("bn dx", fk.val(dxg.cpu()), fk.val(dx), *tol(np_))
+    mm, mv = torch.randn(c, generator=gen), torch.rand(c, generator=gen)
+    mmg, mvg = mm.cuda(), mv.cuda()
+    fk.bn_update_moving(mm, mv, mean, var, rows, 0.9)
+    K.bn_update_moving(mmg, mvg, mean.cuda(), var.cuda(), rows, 0.9)
+    check_close("bn mm", mmg.cpu(), mm, 1e-5, 1.0)
+    check_close("bn mv", mvg.cpu(), mv, 1e-5, 1.0)
+    a = torch.zeros_like(x)
+    fk.act_bwd(dy, res, a, fk.MASK_LRELU)
+    ag = torch.zeros_like(x).cuda()
+    K.act_bwd(dyg, resg, ag, K.MASK_LRELU)
+    check_close("act_bwd", fk.val(ag.cpu()), fk.val(a), *tol(np_))
+    s = torch.zeros(c)
+    fk.colsum(fk.View(x), s)
+    sg = torch.zeros(c, device="cuda")
+    K.colsum(K.View(xg), sg)
+    check_close("colsum", sg.cpu(), s, 2e-4, 5.0)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_discriminator_side_kernels(K, np_):
+    gen = torch.Generator().manual_seed(4)
+    S, ce, C = 12, 16, 64
+    e, eg = both(np_, (S, ce), gen)
+    cat, catg = both(np_, (S, 4, 4, C + ce), gen)
+    fk.embed_tile(e, cat, C)
+    K.embed_tile(eg, catg, C)
+    assert torch.equal(catg.cpu(), cat)
+    de = torch.zeros_like(e)
+    fk.embed_reduce(cat, de, C)
+    deg = torch.zeros_like(e).cuda()
+    K.embed_reduce(catg, deg, C)
+    check_close("embed_reduce", fk.val(deg.cpu()), fk.val(de), *tol(np_))
+    a, ag = both(np_, (S, 4, 4, C), gen)
+    w = torch.randn(16 * C, generator=gen) * 0.05
+    b = torch.randn(1, generator=gen)
+    seed = torch.randn(S, generator=gen)
+    logit = torch.zeros(S)
+    fk.dout_fwd(a, w, b, logit)
+    lg = torch.zeros(S, device="cuda")
+    K.dout_fwd(ag, w.cuda(), b.cuda(), lg)
+    check_close("dout_fwd", lg.cpu(), logit, 1e-5, 1.0)
+    da = torch.zeros_like(a)
+    fk.dout_bwd_data(a, w, seed, da)
+    dag = torch.zeros_like(a).cuda()
+    K.dout_bwd_data(ag, w.cuda(), seed.cuda(), dag)
+    check_close("dout_bwd_data", fk.val(dag.cpu()), fk.val(da), *tol(np_))
+    dw, db = torch.zeros(16 * C), torch.zeros(1)
+    fk.dout_bwd_weight(a, seed, dw, db, 9)
+    dwg, dbg = torch.zeros(16 * C, device="cuda"), torch.zeros(1, device="cuda")
+    K.dout_bwd_weight(ag, seed.cuda(), dwg, dbg, 9)
+    check_close("dout dw", dwg.cpu(), dw, 1e-4, 1.0)
+    check_close("dout db", dbg.cpu(), db, 1e-4, 1.0)
+
+
+def test_gp_ca_scalar_adam_pack_kernels(K):
+    gen = torch.Generator().manual_seed(5)
+    B = 8
+    g, x = torch.rand(B, 64, 64, 3, generator=gen), torch.rand(B, 64, 64, 3, generator=gen)
+    eps = torch.rand(B, generator=gen)
+    xh = torch.zeros_like(g)
+    fk.gp_interp(g, x, eps, xh)
+    xhg = torch.zeros_like(g).cuda()
+    K.gp_interp(g.cuda(), x.cuda(), eps.cuda(), xhg)
+    check_close("gp_interp", xhg.cpu(), xh, 1e-6, 1.0)
+    grad = torch.randn(B, 64, 64, 3, generator=gen) * 0.012
+    grad[0] *= 0.1      # slope < 1: coefficient must be exactly 0
+    sl, co, pen = torch.zeros(B), torch.zeros(B), torch.zeros(1)
+    fk.gp_penalty(grad, 150.0, 1.0 / 16, sl, co, pen)
+    slg, cog, peng = [torch.zeros_like(t).cuda() for t in (sl, co, pen)]
+    K.gp_penalty(grad.cuda(), 150.0, 1.0 / 16, slg, cog, peng)
+    check_close("slope", slg.cpu(), sl, 1e-5, 1.0)
+    check_close("coef", cog.cpu(), co, 1e-4, 1.0)
+    check_close("pen", peng.cpu(), pen, 1e-4, 1.0)
+    assert float(co[0]) == 0.0 and float(cog[0]) == 0.0 and float(co[1]) > 0
+    for np_ in (1, 2):
+        ce, zd = 16, 24
+        ms, msg_ = both(np_, (B, 2 * ce), gen, 0.5)
+        z, tn = torch.randn(B, zd, generator=gen), torch.randn(B, ce, generator=gen)
+        zc, kl = torch.zeros(np_, B, zd + ce, dtype=torch.bfloat16), torch.zeros(1)
+        fk.ca_fwd(ms, z, tn, zc, kl)
+        zcg, klg = torch.zeros_like(zc).cuda(), torch.zeros(1, device="cuda")
+        K.ca_fwd(msg_, z.cuda(), tn.cuda(), zcg, klg)
+        check_close("ca_fwd", fk.val(zcg.cpu()), fk.val(zc), *tol(np_))
+        check_close("kl", klg.cpu(), kl, 1e-4, 1.0)
+        dzc, dzcg = both(np_, (B, zd + ce), gen)
+        dms = torch.zeros_like(ms)
+        fk.ca_bwd(ms, dzc, tn, dms, zd, 0.01)
+        dmsg = torch.zeros_like(ms).cuda()
+        K.ca_bwd(msg_, dzcg, tn.cuda(), dmsg, zd, 0.01)
+        check_close("ca_bwd", fk.val(dmsg.cpu()), fk.val(dms), *tol(np_))
+        w = torch.randn(9, 40, 24, generator=gen)
+        f, bwd = torch.zeros(np_, 9, 40, 24, dtype=torch.bfloat16), torch.zeros(np_, 9, 24, 40, dtype=torch.bfloat16)
+        fk.pack_weight(w, f, bwd)
+        fg, bg = torch.zeros_like(f).cuda(), torch.zeros_like(bwd).cuda()
+        K.pack_weight(w.cuda(), fg, bg)
+        assert torch.equal(fg.cpu(), f) and torch.equal(bg.cpu(), bwd)
+    # scalars
+    kt = torch.tensor([0.7])
+    logit = torch.randn(4 * B, generator=gen)
+    seed, sums, sc = torch.zeros(4 * B), torch.zeros(8), torch.zeros(16)
+    sums[4], sums[5] = 0.3, 0.2
+    fk.d_seeds(kt, seed, B, 1.0 / 16)
+    fk.d_sums(logit, B, sums)
+    ktg, seedg, sumsg, scg = kt.cuda(), torch.zeros(4 * B, device="cuda"), torch.zeros(8, device="cuda"), torch.zeros(16, device="cuda")
+    sumsg[4], sumsg[5] = 0.3, 0.2
+    K.d_seeds(ktg, seedg, B, 1.0 / 16)
+    K.d_sums(logit.cuda(), B, sumsg)
+    check_close("seeds", seedg.cpu(), seed, 1e-6, 1.0)
+    check_close("sums", sumsg.cpu(), sums, 1e-5, 1.0)
+    fk.d_scalars(sums, kt, sc, 16, 150.0, 1e-3)
+    K.d_scalars(sumsg, ktg, scg, 16, 150.0, 1e-3)
+    check_close("d_scalars", scg.cpu()[:12], sc[:12], 1e-5, 1.0)
+    check_close("kt", ktg.cpu(), kt, 1e-6, 1.0)
+    gs, gsg = torch.tensor([1.5, 40.0] + [0.0] * 6), torch.tensor([1.5, 40.0] + [0.0] * 6).cuda()
+    fk.g_sums(logit, B, gs)
+    K.g_sums(logit.cuda(), B, gsg)
+    fk.g_scalars(gs, sc, 16, 8, 1.0)
+    K.g_scalars(gsg, scg, 16, 8, 1.0)
+    check_close("g_scalars", scg.cpu()[12:14], sc[12:14], 1e-5, 1.0)
+    # Adam (TF form), odd length exercises the tail
+    n = 1003
+    th, gr = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
+    m, v = torch.rand(n, generator=gen), torch.rand(n, generator=gen)
+    thg, mg_, vg_ = th.cuda(), m.cuda(), v.cuda()
+    fk.adam_tf(th, gr, m, v, 3e-5, 0.5, 0.9)
+    K.adam_tf(thg, gr.cuda(), mg_, vg_, 3e-5, 0.5, 0.9)
+    check_close("adam theta", thg.cpu(), th, 1e-6, 1.0)
+    check_close("adam m", mg_.cpu(), m, 1e-6, 1.0)
+    check_close("adam v", vg_.cpu(), v, 1e-6, 1.0)

@@ -1,0 +1,206 @@
+"""-m gpu: the CUDA path, driven through the reference-facing API (WGanCls) and the C ABI, against
+(a) the committed golden fixtures and (b) the CPU oracle run live on the same seeded inputs.
+
+Stated tolerances (relative L2 unless noted):
+  precision "bf16x3" (parity mode):  G / D forward <= 1e-3 (north-star bar; measured ~1e-5),
+      losses 1e-3, parameter gradients 5e-2 worst case (ReLU/LeakyReLU sign flips at |x| ~ 1e-6
+      move single elements), gradient norms 2e-2.
+  precision "bf16" (throughput mode): forward <= 3e-2, reported alongside; gradients sanity only.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import wgancls_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+TINY = dict(batch_size=4, z_dim=8, embed_dim=32, compressed_embed_dim=8, gf_dim=8, df_dim=8)
+
+
+def cfg_for(o):
+    from t2i_b200.utils.config import AttrDict
+    return AttrDict({"MODEL": {"Z_DIM": o.z_dim, "OUTPUT_SIZE": 64, "EMBED_DIM": o.embed_dim,
+                               "COMPRESSED_EMBED_DIM": o.compressed_embed_dim, "GF_DIM": o.gf_dim, "DF_DIM": o.df_dim,
+                               "IMAGE_SHAPE": {"W": 64, "H": 64, "D": 3}},
+                     "TRAIN": {"BATCH_SIZE": o.batch_size, "SAMPLE_NUM": 4, "D_LR": o.d_lr, "G_LR": o.g_lr,
+                               "BETA1": o.beta1, "BETA2": o.beta2, "N_CRITIC": 1,
+                               "COEFF": {"KL": o.kl_coeff, "LAMBDA": 100.0}}})
+
+
+def rel(a, b):
+    a = torch.as_tensor(np.asarray(a) if not torch.is_tensor(a) else a).double().cpu().reshape(-1)
+    b = torch.as_tensor(np.asarray(b) if not torch.is_tensor(b) else b).double().cpu().reshape(-1)
+    return float((a - b).norm() / (b.norm() + 1e-30))
+
+
+def feed_dict(m, f, which):
+    return {m.x: f["x"], m.x_mismatch: f["x_mismatch"], m.cond: f["cond"], m.z: f["z"], m.epsilon: f["epsilon"],
+            m.cond_noise: f[which], m.learning_rate_d: 1e-4, m.learning_rate_g: 1e-4}
+
+
+def build(ocfg, precision, params):
+    from t2i_b200.models.wgancls.model import WGanCls
+    m = WGanCls(cfg_for(ocfg), precision=precision)
+    m.set_variables({k: v for k, v in params.items()})
+    return m
+
+
+@pytest.mark.parametrize("precision", ["bf16x3", "bf16"])
+def test_tiny_iteration_against_golden(precision):
+    z = np.load(os.path.join(GOLD, "wgancls_tiny.npz"))
+    ocfg = O.OracleCfg(**TINY)
+    p = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("p/")}
+    f = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("f/")}
+    m = build(ocfg, precision, p)
+    tight = precision == "bf16x3"
+    d_loss = m.run([m.D_optim, m.kt_optim, m.D_loss], feed_dict(m, f, "tn_eps"))[2]
+    eng = m._train_engine()
+    ftol, stol = (1e-3, 1e-3) if tight else (6e-2, 0.25)
+    assert rel(eng.d["img"][:4], z["o/G"]) < ftol
+    lg = eng.d["logit"].cpu()
+    # segment 3 was overwritten by the tangent pass only in its activations, not in the logits
+    for i, k in enumerate(["Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit"]):
+        assert rel(lg[4 * i:4 * i + 4], z["o/" + k]) < ftol * 5, k
+    gtol = 1e-3 if tight else 0.5
+    assert rel(eng.d["gx"], z["o/grad_x_hat"]) < gtol
+    assert rel(eng.d["g2"], z["o/grad_cond"]) < gtol
+    sc = eng.scalars_dict()
+    assert abs(d_loss - sc["D_loss"]) == 0
+    for k in ["D_loss", "D_loss_real", "D_loss_fake", "D_loss_mismatch", "wdist", "wdist2", "reg_loss", "balance_loss",
+              "real_gp", "real_gp2"]:
+        assert abs(sc[k] - float(z["o/" + k])) < stol * max(1.0, abs(float(z["o/" + k]))), (k, sc[k], float(z["o/" + k]))
+    if tight:
+        assert abs(sc["kt"] - float(z["o/kt"])) < 1e-6
+        grads = eng.get_grads_tf()
+        for n in m.d_vars:
+            ref = float(z["gn/" + n])
+            if ref > 1e-12:
+                got = float(grads[n].double().norm())
+                assert abs(got - ref) < 2e-2 * ref, (n, got, ref)
+    g_loss = m.run([m.G_optim, m.G_loss], feed_dict(m, f, "tn_eps_g"))[1]
+    assert abs(g_loss - float(z["o/G_loss"])) < stol * abs(float(z["o/G_loss"]))
+    assert rel(eng.d["img"][:4], z["o/G_run_G"]) < ftol
+    if tight:
+        grads = eng.get_grads_tf()
+        for n in m.g_vars:
+            ref = float(z["gn/" + n])
+            if ref > 1e-9:
+                got = float(grads[n].double().norm())
+                assert abs(got - ref) < 5e-2 * ref, (n, got, ref)
+        # parameters after the whole iteration: |step| ~ lr for every weight, compare to the oracle's
+        newp = m.get_variables()
+        for n in m.d_vars + m.g_vars:
+            if float(z["gn/" + n]) < 1e-9:
+                continue      # biases in front of a training-mode BN: exactly-zero gradient, Adam amplifies noise
+            q = torch.from_numpy(z["q/" + n]).double()
+            frac_bad = float(((newp[n].double() - q).abs() > 2e-5).double().mean())
+            assert frac_bad < 0.02, (n, frac_bad)
+
+
+def test_tiny_gradients_against_live_oracle():
+    """element-wise parameter gradients (both runs, incl. the second-order GP term) vs the fp64 oracle"""
+    z = np.load(os.path.join(GOLD, "wgancls_tiny.npz"))
+    ocfg = O.OracleCfg(**TINY)
+    p = O.OrderedDict((k[2:], torch.from_numpy(z[k]).double()) for k in z.files if k.startswith("p/"))
+    f = {k[2:]: torch.from_numpy(z[k]).double() for k in z.files if k.startswith("f/")}
+    m = build(ocfg, "bf16x3", p)
+    st = O.new_state(p)
+    rd = O.d_step(p, st, f, ocfg)
+    ff = {k: v.float() for k, v in f.items()}
+    m.run([m.D_optim, m.kt_optim, m.D_loss], feed_dict(m, ff, "tn_eps"))
+    grads = m._train_engine().get_grads_tf()
+    worst = max((rel(grads[n], rd["grads"][n]), n) for n in m.d_vars if float(rd["grads"][n].abs().max()) > 0)
+    assert worst[0] < 2e-3, worst
+
+
+@pytest.mark.parametrize("precision,ftol", [("bf16x3", 1e-3), ("bf16", 3e-2)])
+def test_full_width_forward_parity_batch16(precision, ftol):
+    """BASELINE config 1 (batch 16, GF = DF = 128, 1024-d embeddings): G and D forward vs the oracle."""
+    ocfg = O.OracleCfg(batch_size=16)
+    p = O.init_params(ocfg, 0, torch.float32)
+    f = O.make_feed(ocfg, 1234, torch.float32)
+    m = build(ocfg, precision, p)
+    with torch.no_grad():
+        G, mean, ls = O.generator(p, f["z"], f["cond"], f["tn_eps"], ocfg)
+        Dx = O.discriminator(p, f["x"], f["cond"], ocfg)
+        Dg = O.discriminator(p, G, f["cond"], ocfg)
+    img, mean_g, ls_g = m.generator(f["z"], f["cond"], noise=f["tn_eps"])
+    e_g = rel(img, G)
+    e_dx = rel(m.discriminator(f["x"], f["cond"]), Dx)
+    e_dg = rel(m.discriminator(G, f["cond"]), Dg)
+    print("\n[parity] %s: G rel-L2 %.3e  D(x) rel-L2 %.3e  D(G) rel-L2 %.3e" % (precision, e_g, e_dx, e_dg))
+    assert rel(mean_g, mean) < ftol and rel(ls_g, ls) < ftol
+    assert e_g < ftol and e_dx < ftol and e_dg < ftol
+    assert img.shape == (16, 64, 64, 3) and float(img.abs().max()) <= 1.0
+
+
+def test_full_width_iteration_against_golden_b4():
+    """128-wide net, batch 4, one whole iteration in parity mode vs the committed golden."""
+    z = np.load(os.path.join(GOLD, "wgancls_full_b4.npz"))
+    ocfg = O.OracleCfg(batch_size=4)
+    p = O.init_params(ocfg, 0, torch.float32)
+    p["d_net/dense/kernel"] = p["d_net/dense/kernel"] * 4.0
+    f = O.make_feed(ocfg, 1234, torch.float32)
+    m = build(ocfg, "bf16x3", p)
+    m.run([m.D_optim, m.kt_optim, m.D_loss], feed_dict(m, f, "tn_eps"))
+    eng = m._train_engine()
+    assert rel(eng.d["img"][:4], z["o/G"]) < 1e-3
+    lg = eng.d["logit"].cpu()
+    for i, k in enumerate(["Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit"]):
+        assert rel(lg[4 * i:4 * i + 4], z["o/" + k]) < 1e-3, k
+    # Input gradients of a 1.2M-unit LeakyReLU net: a handful of units with |pre-activation| below the
+    # 1e-5 arithmetic difference flip their mask and each moves the gradient by ~0.5 %; the forward
+    # quantities above are tight, the mask-dependent ones below are bounded accordingly.
+    assert rel(eng.d["gx"], z["o/grad_x_hat"]) < 3e-2
+    assert rel(eng.d["g2"], z["o/grad_cond"]) < 3e-2
+    sc = eng.scalars_dict()
+    assert float(z["o/real_gp"]) > 0 and float(z["o/real_gp2"]) > 0
+    for k in ["wdist", "wdist2", "balance_loss", "D_loss_real", "D_loss_fake", "D_loss_mismatch"]:
+        assert abs(sc[k] - float(z["o/" + k])) < 1e-3 * max(1.0, abs(float(z["o/" + k]))), (k, sc[k], float(z["o/" + k]))
+    for k in ["D_loss", "real_gp", "real_gp2"]:
+        assert abs(sc[k] - float(z["o/" + k])) < 6e-2 * abs(float(z["o/" + k])), (k, sc[k], float(z["o/" + k]))
+    grads = eng.get_grads_tf()
+    for n in m.d_vars:
+        ref = float(z["gn/" + n])
+        if ref > 1e-9:
+            got = float(grads[n].double().norm())
+            assert abs(got - ref) < 6e-2 * ref, (n, got, ref)
+    g_loss = m.run([m.G_optim, m.G_loss], feed_dict(m, f, "tn_eps_g"))[1]
+    assert abs(g_loss - float(z["o/G_loss"])) < 2e-3 * abs(float(z["o/G_loss"]))
+    grads = eng.get_grads_tf()
+    for n in m.g_vars:
+        ref = float(z["gn/" + n])
+        if ref > 1e-6:
+            got = float(grads[n].double().norm())
+            assert abs(got - ref) < 6e-2 * ref, (n, got, ref)
+
+
+def test_properties_at_bench_size():
+    """BASELINE config 2 size (batch 256, bf16): size-independent properties instead of the oracle:
+    D is per-sample (a 4B batch equals four B batches), x_hat(eps=0) = x and x_hat(eps=1) = G,
+    determinism, finite losses, kt moves by -1e-3 * its gradient."""
+    from t2i_b200.models.wgancls.model import WGanCls
+    ocfg = O.OracleCfg(batch_size=256)
+    m = WGanCls(cfg_for(ocfg), precision="bf16")
+    m.initialize(0)
+    f = O.make_feed(ocfg, 1234, torch.float32)
+    eng = m._train_engine()
+    big = m.discriminator(torch.cat([f["x"], f["x_mismatch"]])[:256], torch.cat([f["cond"], f["cond"]])[:256])
+    a = m.discriminator(f["x"][:128], f["cond"][:128])
+    assert torch.equal(big[:128], a)                                      # bit-exact: batch-independent tiles
+    fd = feed_dict(m, f, "tn_eps")
+    fd[m.epsilon] = torch.zeros(256, 1, 1, 1)
+    m.run([m.D_optim, m.kt_optim, m.D_loss], fd)
+    assert torch.equal(eng.d["img"][768:], eng.d["img"][256:512])          # x_hat == x
+    kt0 = float(eng.kt.item())
+    fd[m.epsilon] = torch.ones(256, 1, 1, 1)
+    d_loss = m.run([m.D_optim, m.kt_optim, m.D_loss], fd)[2]
+    assert torch.equal(eng.d["img"][768:], eng.d["img"][:256])             # x_hat == G
+    sc = eng.scalars_dict()
+    assert np.isfinite(d_loss) and all(np.isfinite(v) for v in sc.values())
+    assert abs(float(eng.kt.item()) - (kt0 - 1e-3 * sc["kt_grad"])) < 1e-6
+    g_loss = m.run([m.G_optim, m.G_loss], feed_dict(m, f, "tn_eps_g"))[1]
+    assert np.isfinite(g_loss)

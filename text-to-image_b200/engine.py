@@ -49,7 +49,7 @@ class Layer:
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
-                 f32_dtype=torch.float32):
+                 f32_dtype=torch.float32, share_from=None):
         # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
         # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
@@ -62,7 +62,15 @@ class Engine:
             assert v % 8 == 0, "channel counts must be multiples of 8"
         self.d_t = 0
         self.g_t = 0
-        self._build_params()
+        if share_from is None:
+            before = set(self.__dict__)
+            self._build_params()
+            self._param_attrs = sorted(set(self.__dict__) - before)
+        else:   # a second batch size (sampler / eval) on the same parameters
+            assert (share_from.np, share_from.gf, share_from.df) == (np_, gf, df)
+            self._param_attrs = share_from._param_attrs
+            for k in self._param_attrs:
+                setattr(self, k, getattr(share_from, k))
         self._build_buffers()
 
     # ------------------------------------------------------------------ parameters
@@ -372,7 +380,7 @@ class Engine:
         res("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3")                        # :200-207
         conv("t1", "h3", "d2"); conv("c7", "d2", "t8"); self._bn(8, g["t8"], g["h4"], relu=True, train=train)  # :210-212
         conv("t2", "h4", "d3"); conv("c8", "d3", "t9"); self._bn(9, g["t9"], g["h5"], relu=True, train=train)  # :214-216
-        K.conv_gemm(S1, 1, 0, V(self._rows(g["h5"])), gl["t3"].Wf, V(g["colg"]))                        # :218 as patches
+        K.conv_gemm(S1, 1, 0, V(self._rows(g["h5"])), gl["t3"].Wf, V(g["colg"]), algo_scale=0.75)      # :218 as patches
         K.col2im_k4s2_c3(g["colg"], g["u4"], gl["t3"].b)
         K.conv3x3_c3_tanh_fwd(g["u4"], gl["c9"].w, gl["c9"].b, img_out)                                  # :219-221
 
@@ -385,8 +393,8 @@ class Engine:
         img = self.d["img"][:B]
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
         K.im2col_k4s2_c3(g["d_u4"], g["d_colg"])
-        K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw)
-        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wb, V(rows(g["d_h5"])))
+        K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
+        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wb, V(rows(g["d_h5"])), algo_scale=0.75)
 
         def bn_bwd(i, dy, y_post, x_pre, dx, relu):
             """dy: gradient w.r.t. the BN(+ReLU) output; writes the gradient w.r.t. its input."""
@@ -459,7 +467,7 @@ class Engine:
                     kw = dict(mask=y, mask_kind=K.MASK_LRELU)
             else:
                 kw = dict(bias=L.b, act=K.ACT_LRELU if act else K.ACT_NONE)
-            K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, **kw)
+            K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, algo_scale=0.75 if l == "h0" else 1.0, **kw)
 
         if not tangent:
             K.im2col_k4s2_c3(d["img"][s0:s0 + n], d["col0"][:, s0 * 1024:(s0 + n) * 1024])
@@ -500,7 +508,8 @@ class Engine:
         K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wb, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR)
         K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wb, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR)
         if gn > 0:
-            K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wb, K.View(d["d_col0"], 0, gn * 1024))
+            K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wb,
+                        K.View(d["d_col0"], 0, gn * 1024), algo_scale=0.75)
             K.col2im_k4s2_c3(d["d_col0"], d["gx"], None)
             if want_cond_grad:
                 K.conv_gemm(S1, 1, 0, K.View(d["d_e"], g0, gn), dl["efc"].Wb, K.View(d["d_cond"], 0, gn))
@@ -521,7 +530,8 @@ class Engine:
         pairs = [("h1", "a0", "d_a1", {}), ("h2", "a1", "d_a2", {}), ("h3", "a2", "d_a3", {}),
                  ("r1", "a3", "d_r1", {}), ("r2", "r1", "d_r2", {}), ("r3", "r2", "d_cat", dict(coff=0, c=df8)),
                  ("efc", "cond", "d_e", {}), ("h5", "cat", "d_a5", {}), ("h6", "a5", "d_a6", {})]
-        K.wgrad_gemm(K.CONV_S1, 1, K.View(d["col0"], 0, n * 1024), K.View(rows(d["d_a0"]), 0, n * 1024), dl["h0"].gw)
+        K.wgrad_gemm(K.CONV_S1, 1, K.View(d["col0"], 0, n * 1024), K.View(rows(d["d_a0"]), 0, n * 1024), dl["h0"].gw,
+                     algo_scale=0.75)
         K.colsum(K.View(rows(d["d_a0"]), 0, n_bias * 1024), dl["h0"].gb)
         for l, x, dy, kw in pairs:
             L = dl[l]

@@ -73,8 +73,35 @@ def _ps(t):
     return t.stride(0)
 
 
-def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE):
-    """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, w_cout, w_cin]."""
+# Optional per-launch timing of the two GEMM kernels (bench.py): when PROFILE is a list, every
+# launch appends [kernel, tag, algorithmic flops, algorithmic HBM bytes, start event, end event].
+PROFILE = None
+
+
+def _taps_per_output(mode, k):
+    return k * k if mode == CONV_S1 else 16 if mode == CONV_K4S2 else 4
+
+
+def _prof_begin():
+    if PROFILE is None:
+        return None
+    ev = torch.cuda.Event(enable_timing=True)
+    ev.record()
+    return ev
+
+
+def _prof_end(ev, kernel, tag, flops, nbytes):
+    if ev is not None:
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        PROFILE.append([kernel, tag, flops, nbytes, ev, end])
+
+
+def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
+              algo_scale=1.0):
+    """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, w_cout, w_cin].
+    algo_scale: fraction of the contraction that is algorithmic (0.75 for the 48-of-64 patch columns)."""
+    ev = _prof_begin()
     d = _lib.ConvGemmDesc()
     d.mode, d.k, d.flip, d.np = mode, k, flip, x.np
     d.x = x._act()
@@ -88,10 +115,17 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     d.mask = mask._act() if mask is not None else _null_act()
     d.act, d.mask_kind = act, mask_kind
     _lib.call("t2i_conv_gemm", C.byref(d), _stream())
+    if ev is not None:
+        opix = y.n * y.H * y.W
+        flops = 2.0 * opix * y.c * x.c * _taps_per_output(mode, k) * algo_scale * (3 if x.np == 2 else 1)
+        nbytes = 2.0 * x.np * (x.n * x.H * x.W * x.c + opix * y.c * (1 + (add is not None) + (mask is not None))
+                               + w.shape[1] * y.c * x.c)
+        _prof_end(ev, "conv_gemm", "m%d k%d %dx%dx%d ci%d co%d" % (mode, k, x.n, x.H, x.W, x.c, y.c), flops, nbytes)
 
 
-def wgrad_gemm(mode, k, x, dy, dw, split_k=0):
+def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
     """dw[tap, co, ci] += sum_pixels dy[pixel, co] * x[pixel + tap, ci]; dw fp32 [taps, cout, cin]."""
+    ev = _prof_begin()
     d = _lib.WgradDesc()
     d.mode, d.k, d.np = mode, k, x.np
     d.x, d.dy = x._act(), dy._act()
@@ -100,6 +134,12 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0):
     d.cout, d.cin = dw.shape[1], dw.shape[2]
     d.split_k = split_k
     _lib.call("t2i_wgrad_gemm", C.byref(d), _stream())
+    if ev is not None:
+        vpix = x.n * x.H * x.W if mode != CONV_K4S2 else dy.n * dy.H * dy.W
+        taps = k * k if mode == CONV_S1 else 16
+        flops = 2.0 * vpix * dy.c * x.c * taps * algo_scale * (3 if x.np == 2 else 1)
+        nbytes = 2.0 * x.np * (x.n * x.H * x.W * x.c + dy.n * dy.H * dy.W * dy.c) + 4.0 * taps * dy.c * x.c
+        _prof_end(ev, "wgrad_gemm", "m%d k%d %dx%dx%d ci%d co%d" % (mode, k, x.n, x.H, x.W, x.c, dy.c), flops, nbytes)
 
 
 def to_planes(src, dst, row_scale=None):
