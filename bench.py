@@ -131,6 +131,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--only-resident", action="store_true", help="profiling aid: skip e2e / roofline / cpu legs")
     ap.add_argument("--profile-out", default=None, help="write the per-launch GEMM table (JSON) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -199,6 +200,14 @@ def main():
     ms_per_step = float(ms.item()) / args.steps
     value = B * world / (ms_per_step * 1e-3)
     finite = all(v == v for v in eng.scalars_dict().values())
+
+    if args.only_resident:
+        if rank == 0:
+            print(json.dumps({"metric": METRIC, "value": value, "unit": "images/s", "ms_per_step": ms_per_step,
+                              "gpu_launches": int(launches), "note": "--only-resident (profiling aid)"}))
+        if world > 1:
+            dist.destroy_process_group()
+        return
 
     # ------------------------------------------------------------ end-to-end through the public API
     def e2e_step():

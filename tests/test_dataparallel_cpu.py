@@ -1,0 +1,83 @@
+"""world_size-2 gloo test of the data-parallel host logic: each rank runs the engine (CPU restatement
+of the kernels, exact fp64 storage) on its shard of a global batch; ONE allreduce of the flat
+gradient buffer (with the scalar sums in its tail) per optimizer step must reproduce the
+single-process D run on the whole batch exactly (d_net has no BatchNorm)."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+
+
+def _worker(rank, world, port, out):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import wgancls_oracle as O
+    from t2i_b200.engine import Engine
+    from test_engine_cpu import TINY, boosted_params
+    torch.set_num_threads(1)
+    cfg = O.OracleCfg(**TINY)
+    gb = cfg.batch_size
+    b = gb // world
+    p = boosted_params(cfg)
+    feed = O.make_feed(cfg, 11, torch.float64)
+    calls = []
+
+    def allreduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    eng = Engine(fk, "cpu", b, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
+                 cfg.beta1, cfg.beta2, cfg.kl_coeff, world, allreduce, act_dtype=torch.float64, f32_dtype=torch.float64)
+    eng.set_params_tf(p)
+    sl = slice(rank * b, (rank + 1) * b)
+    eng.load_feed(**{k: feed[k][sl] for k in ("x", "x_mismatch", "cond", "z", "epsilon")}, tn_eps=feed["tn_eps"][sl])
+    # the generator's BatchNorm is per replica under data parallelism; feed the D run the images of the
+    # single-process generator so that the comparison isolates the sharded D math
+    ref = Engine(fk, "cpu", gb, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
+                 cfg.beta1, cfg.beta2, cfg.kl_coeff, act_dtype=torch.float64, f32_dtype=torch.float64)
+    ref.set_params_tf(p)
+    ref.load_feed(**{k: feed[k] for k in ("x", "x_mismatch", "cond", "z", "epsilon")}, tn_eps=feed["tn_eps"])
+    ref.d_step(cfg.d_lr)
+    orig = eng.g_forward
+
+    def g_forward_fixed(z, cond, tn, img_out, kl, **kw):
+        orig(z, cond, tn, img_out, kl, **kw)
+        img_out.copy_(ref.d["img"][sl])
+    eng.g_forward = g_forward_fixed
+    eng.d_step(cfg.d_lr)
+    eng.g_forward = orig
+    g_sharded, g_full = eng.get_grads_tf(), ref.get_grads_tf()
+    worst = max(float((g_sharded[n] - g_full[n]).abs().max() / (g_full[n].abs().max() + 1e-30))
+                for n in g_full if n.startswith("d_net/"))
+    sc, scr = eng.scalars_dict(), ref.scalars_dict()
+    smax = max(abs(sc[k] - scr[k]) / max(1.0, abs(scr[k])) for k in sc)
+    eng.g_step(cfg.g_lr)      # runs; per-replica BN, gradients identical on all ranks after the allreduce
+    flat = eng.grad["g"].clone()
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    same = all(torch.equal(gathered[0], t) for t in gathered)
+    if rank == 0:
+        torch.save({"worst": worst, "smax": smax, "calls": calls, "same": same,
+                    "kt": float(eng.kt), "kt_ref": float(ref.kt)}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_d_run_equals_single_process(tmp_path):
+    out = str(tmp_path / "r.pt")
+    port = 29500 + os.getpid() % 2000
+    mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["worst"] < 1e-9, r
+    assert r["smax"] < 1e-9, r
+    assert abs(r["kt"] - r["kt_ref"]) < 1e-12
+    assert len(r["calls"]) == 2 and r["same"], r      # exactly one allreduce per optimizer step

@@ -96,8 +96,9 @@ def test_tiny_iteration_against_golden(precision):
             if float(z["gn/" + n]) < 1e-9:
                 continue      # biases in front of a training-mode BN: exactly-zero gradient, Adam amplifies noise
             q = torch.from_numpy(z["q/" + n]).double()
-            frac_bad = float(((newp[n].double() - q).abs() > 2e-5).double().mean())
-            assert frac_bad < 0.02, (n, frac_bad)
+            bad = ((newp[n].double() - q).abs() > 2e-5)
+            # sign(g) decides the step: isolated elements with |g| ~ 0 may go the other way
+            assert float(bad.double().mean()) < 0.02 or int(bad.sum()) <= 2, (n, int(bad.sum()), bad.numel())
 
 
 def test_tiny_gradients_against_live_oracle():
