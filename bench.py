@@ -53,7 +53,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                          "--format=csv,noheader,nounits", "-lms", "25"], stdout=subprocess.PIPE,
                                          stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 if self.stop_flag:
@@ -125,7 +125,7 @@ def run_reference(args, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
@@ -185,14 +185,14 @@ def main():
     barrier()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    l0 = _lib.launch_count()
+    l0 = _lib.launch_count() + eng.replayed_launches - eng.captured_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
         resident_step()
     e1.record()
     barrier()
-    launches = _lib.launch_count() - l0
+    launches = _lib.launch_count() + eng.replayed_launches - eng.captured_launches - l0
     clocks = sampler.finish()
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
@@ -235,14 +235,16 @@ def main():
     # ------------------------------------------------------------ per-launch GEMM timing (roofline)
     pk = peaks()
     roofline = None
+    # every rank runs these steps (they contain the allreduce); they run eagerly, outside the CUDA graphs
+    kernels.PROFILE = []
+    psteps = 2
+    for _ in range(psteps):
+        resident_step()
+    barrier()
+    prof = kernels.PROFILE
+    kernels.PROFILE = None
     if rank == 0:
-        kernels.PROFILE = []
-        psteps = 2
-        for _ in range(psteps):
-            resident_step()
-        torch.cuda.synchronize()
-        rows = [(k, tag, fl, nb, a.elapsed_time(b)) for k, tag, fl, nb, a, b in kernels.PROFILE]
-        kernels.PROFILE = None
+        rows = [(k, tag, fl, nb, a.elapsed_time(b)) for k, tag, fl, nb, a, b in prof]
         agg = {}
         for k, tag, fl, nb, t in rows:
             a = agg.setdefault(k, [0.0, 0.0, 0.0, 0])

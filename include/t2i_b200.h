@@ -32,6 +32,7 @@ typedef enum {
 enum { T2I_CONV_S1 = 0, T2I_CONV_K4S2 = 1, T2I_DECONV_K4S2 = 2 };
 enum { T2I_ACT_NONE = 0, T2I_ACT_LRELU = 1, T2I_ACT_RELU = 2 };
 enum { T2I_MASK_NONE = 0, T2I_MASK_LRELU = 1, T2I_MASK_RELU = 2 };
+enum { T2I_W_NK = 0, T2I_W_KN = 1 };
 
 /* View of an NHWC activation tensor stored as bf16 planes. */
 typedef struct {
@@ -49,7 +50,10 @@ typedef struct {
  * mode T2I_CONV_K4S2 : 4x4 stride 2 SAME (y is h/2 x w/2); also the input-gradient of a deconv.
  * mode T2I_DECONV_K4S2: 4x4 stride 2 SAME transposed conv as four 2x2 sub-pixel phases
  *                      (y is 2h x 2w); also the input-gradient of a 4x4/s2 conv.
- * w: packed bf16 planes [np][taps][w_cout][w_cin], contraction (w_cin) contiguous, tap = kh*k+kw.
+ * w: packed bf16 planes [np][taps][w_rows][w_cols], cols contiguous, tap = kh*k+kw.
+ *    w_layout T2I_W_NK: rows = output channels, cols = contraction (a layer's packed forward weights
+ *    used forward);  T2I_W_KN: rows = contraction, cols = output channels (the SAME packed forward
+ *    weights used for the layer's input-gradient: MN-major B operand, no transposed copy).
  * Replaces Conv2D/Conv2DBackpropInput/MatMul + BiasAdd + LeakyRelu behind utils/ops.py:61,69,87
  * (called from models/wgancls/model.py:135-160,174-219) and their tf.gradients counterparts.
  */
@@ -58,7 +62,7 @@ typedef struct {
     t2i_act x;
     const void* w;
     long long w_plane_stride;
-    int w_cout, w_cin;
+    int w_rows, w_cols, w_layout;
     t2i_act y;
     const float* bias; /* [y.c] or NULL */
     t2i_act add;       /* ptr NULL = none; same pixel grid as y */
@@ -181,16 +185,21 @@ int t2i_d_scalars(const float* sums, float* kt, float* scalars, int global_batch
 int t2i_g_sums(const float* logit_fake, int b, float* sums, void* stream);
 int t2i_g_scalars(const float* sums, float* scalars, int global_batch, int ce, float kl_coeff, void* stream);
 
-/* weights: fp32 master [taps][cout][cin] -> bf16 planes in both contraction orders
- * (fwd [taps][cout][cin], bwd [taps][cin][cout]); either destination may be NULL. */
+/* weights: fp32 master [taps][cout][cin] -> bf16 planes, same layout (fwd) and/or transposed
+ * (bwd [taps][cin][cout]); either destination may be NULL.  The engine only needs fwd (to_planes
+ * on the flat buffer / fused into t2i_adam_tf); kept for layouts that want a K-major transpose. */
 int t2i_pack_weight(const float* w, int taps, int cout, int cin, void* fwd, long long fwd_ps, void* bwd,
                     long long bwd_ps, int np, void* stream);
 
 /* TF-form Adam on a flat fp32 buffer (tf.train.AdamOptimizer at model.py:94-96,103-105):
  * m = b1 m + (1-b1) g ; v = b2 v + (1-b2) g^2 ; theta -= lr_t m / (sqrt(v) + eps),
- * lr_t = lr sqrt(1-b2^t)/(1-b1^t) computed by the caller.  grad_scale multiplies g first. */
-int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, float lr_t, float beta1,
-                float beta2, float eps, float grad_scale, void* stream);
+ * lr_t = lr sqrt(1-b2^t)/(1-b1^t) is read from DEVICE memory (*lr_t_dev) so that a captured CUDA graph
+ * replays with the current value.  beta1 == 0 skips the m slot entirely (m == g).  grad_scale
+ * multiplies g first.  packed (optional): the updated theta is also written as bf16 planes
+ * [np][n] (the tensor-core copy of the weights), fusing the re-pack into the optimizer pass. */
+int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, const float* lr_t_dev,
+                float beta1, float beta2, float eps, float grad_scale, void* packed, long long packed_ps, int np,
+                void* stream);
 
 const char* t2i_last_error(void);
 int t2i_version(void);

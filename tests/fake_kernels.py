@@ -86,9 +86,12 @@ def _conv_core(mode, k, flip, x, w):
 
 
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
-              algo_scale=1.0):
+              algo_scale=1.0, w_kn=False):
     xv = x.values()
-    wv = val(w)[:, :y.c, :xv.shape[-1]]
+    wv = val(w)
+    if w_kn:
+        wv = wv.transpose(1, 2)
+    wv = wv[:, :y.c, :xv.shape[-1]]
     v = _conv_core(mode, k, flip, xv, wv)
     if bias is not None:
         v = v + bias.double()[:y.c]
@@ -329,8 +332,12 @@ def pack_weight(w, fwd=None, bwd=None):
         put(bwd, w.double().transpose(1, 2))
 
 
-def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
+def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0, packed=None):
     g = grad * grad_scale
-    m.copy_(beta1 * m + (1 - beta1) * g)
+    mj = beta1 * m + (1 - beta1) * g
+    if beta1 != 0:
+        m.copy_(mj)
     v.copy_(beta2 * v + (1 - beta2) * g * g)
-    theta -= lr_t * m / (v.sqrt() + eps)
+    theta -= lr_t[0] * mj / (v.sqrt() + eps)
+    if packed is not None:
+        put(packed, theta.double())

@@ -93,6 +93,13 @@ def test_conv_gemm_plain(K, case, np_):
     K.conv_gemm(mode, k, flip, K.View(xg), wg, K.View(yg))
     torch.cuda.synchronize()
     check_close(name, fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    # the same product with the weights stored [tap][contraction][output channel] (MN-major B operand),
+    # which is how a layer's packed forward weights serve its input-gradient
+    w_kn = w.transpose(2, 3).contiguous()
+    yg2 = torch.full_like(y, 5.0).cuda()
+    K.conv_gemm(mode, k, flip, K.View(xg), w_kn.cuda(), K.View(yg2), w_kn=True)
+    torch.cuda.synchronize()
+    check_close(name + "_kn", fk.val(yg2.cpu()), fk.val(y), *tol(np_))
 
 
 @pytest.mark.parametrize("np_", [1, 2])
@@ -377,9 +384,15 @@ def test_gp_ca_scalar_adam_pack_kernels(K):
     n = 1003
     th, gr = torch.randn(n, generator=gen), torch.randn(n, generator=gen)
     m, v = torch.rand(n, generator=gen), torch.rand(n, generator=gen)
-    thg, mg_, vg_ = th.cuda(), m.cuda(), v.cuda()
-    fk.adam_tf(th, gr, m, v, 3e-5, 0.5, 0.9)
-    K.adam_tf(thg, gr.cuda(), mg_, vg_, 3e-5, 0.5, 0.9)
-    check_close("adam theta", thg.cpu(), th, 1e-6, 1.0)
-    check_close("adam m", mg_.cpu(), m, 1e-6, 1.0)
-    check_close("adam v", vg_.cpu(), v, 1e-6, 1.0)
+    for b1, np_ in ((0.5, 1), (0.0, 2)):
+        th1, m1, v1 = th.clone(), m.clone(), v.clone()
+        thg, mg_, vg_ = th.cuda(), m.cuda(), v.cuda()
+        pk = torch.zeros(np_, 1008, dtype=torch.bfloat16)[:, :n]      # plane stride keeps 16-byte alignment
+        pkg = torch.zeros(np_, 1008, dtype=torch.bfloat16).cuda()[:, :n]
+        lr_t = torch.tensor([3e-5])
+        fk.adam_tf(th1, gr, m1, v1, lr_t, b1, 0.9, packed=pk)
+        K.adam_tf(thg, gr.cuda(), mg_, vg_, lr_t.cuda(), b1, 0.9, packed=pkg)
+        check_close("adam theta", thg.cpu(), th1, 1e-6, 1.0)
+        check_close("adam m", mg_.cpu(), m1, 1e-6, 1.0)     # untouched when beta1 == 0
+        check_close("adam v", vg_.cpu(), v1, 1e-6, 1.0)
+        check_close("adam packed", fk.val(pkg.cpu()), fk.val(pk), 2.0 ** -7 if np_ == 1 else 1e-4, 1e-2)

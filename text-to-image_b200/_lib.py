@@ -10,6 +10,7 @@ LIB_PATH = os.path.join(_HERE, "libt2i_b200.so")
 CONV_S1, CONV_K4S2, DECONV_K4S2 = 0, 1, 2
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
 MASK_NONE, MASK_LRELU, MASK_RELU = 0, 1, 2
+W_NK, W_KN = 0, 1
 SCALARS = ["D_loss", "D_loss_real", "D_loss_fake", "D_loss_mismatch", "wdist", "wdist2", "reg_loss",
            "balance_loss", "real_gp", "real_gp2", "kt", "kt_grad", "G_loss", "G_kl_loss"]
 S_COUNT = 16
@@ -26,7 +27,8 @@ class Act(C.Structure):
 
 class ConvGemmDesc(C.Structure):
     _fields_ = [("mode", C.c_int), ("k", C.c_int), ("flip", C.c_int), ("np", C.c_int), ("x", Act),
-                ("w", C.c_void_p), ("w_plane_stride", C.c_longlong), ("w_cout", C.c_int), ("w_cin", C.c_int),
+                ("w", C.c_void_p), ("w_plane_stride", C.c_longlong), ("w_rows", C.c_int), ("w_cols", C.c_int),
+                ("w_layout", C.c_int),
                 ("y", Act), ("bias", C.c_void_p), ("add", Act), ("mask", Act), ("act", C.c_int),
                 ("mask_kind", C.c_int)]
 
@@ -69,7 +71,7 @@ SIGNATURES = {
     "t2i_g_sums": [_P, _I, _P, _P],
     "t2i_g_scalars": [_P, _P, _I, _I, _F, _P],
     "t2i_pack_weight": [_P, _I, _I, _I, _P, _LL, _P, _LL, _I, _P],
-    "t2i_adam_tf": [_P, _P, _P, _P, _LL, _F, _F, _F, _F, _F, _P],
+    "t2i_adam_tf": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P, _LL, _I, _P],
 }
 OTHER_SYMBOLS = ["t2i_last_error", "t2i_version", "t2i_launch_count"]
 

@@ -55,7 +55,10 @@ struct SmemLayout {
     static constexpr int kBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
 };
 
-template <int BLOCK_N>
+// B_KN = false: weights [tap][N][K], K contiguous (K-major B operand, forward layout used forward).
+// B_KN = true : weights [tap][K][N], N contiguous (MN-major B operand): the SAME packed forward
+//               weights serve the input-gradient convolutions, no transposed copy exists.
+template <int BLOCK_N, bool B_KN>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
     using L = SmemLayout<BLOCK_N>;
     constexpr int kStages = L::kStages;
@@ -120,8 +123,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             uint8_t* sa = smem + stage * L::kStageBytes;
                             tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, q0 + tap.dq,
                                         p0 + tap.dp, n0, pa);
-                            tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, ct * BLOCK_N,
-                                        tap.wtap, pb);
+                            if (!B_KN) {
+                                tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, ct * BLOCK_N,
+                                            tap.wtap, pb);
+                            } else {
+#pragma unroll
+                                for (int a = 0; a < BLOCK_N / 64; ++a)   // 64-channel atoms of [64 K rows x 128 B]
+                                    tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes + a * 8192,
+                                                ct * BLOCK_N + a * 64, kc * kBlockK, tap.wtap, pb);
+                            }
                             if (++stage == kStages) {
                                 stage = 0;
                                 phase ^= 1;
@@ -134,7 +144,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (one elected lane)
         if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, 0);
+            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_KN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
@@ -149,11 +159,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
                     const uint64_t da = make_sw128_desc(sa, 0, 1024);
-                    const uint64_t db = make_sw128_desc(sa + kABytes, 0, 1024);
+                    // K-major: +32 bytes per 16-element K step inside the 128B swizzle row (address >> 4);
+                    // MN-major: 16 K rows of 128 B per step, 8 KB between 64-channel atoms.
+                    const uint64_t db = B_KN ? make_sw128_desc(sa + kABytes, 8192, 1024) : make_sw128_desc(sa + kABytes, 0, 1024);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        // +32 bytes per 16-element K step inside the 128B swizzle row (address >> 4)
-                        umma_bf16(d_tmem, da + 2 * k, db + 2 * k, idesc, (kb | k) != 0);
+                        umma_bf16(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);
@@ -332,9 +343,13 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const t2i_act& x = d->x;
     const t2i_act& y = d->y;
     if (x.ptr == nullptr || y.ptr == nullptr || d->w == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
-    if (x.c > d->w_cin || d->w_cin % 8 != 0) return fail(T2I_ERR_BAD_ARG, "x.c=%d vs w_cin=%d", x.c, d->w_cin);
-    if (y.c > d->w_cout || y.c % 8 != 0 || y.pitch % 8 != 0 || y.coff % 8 != 0)
-        return fail(T2I_ERR_BAD_ARG, "bad output channels c=%d pitch=%d coff=%d w_cout=%d", y.c, y.pitch, y.coff, d->w_cout);
+    // weight matrix per tap: w_rows x w_cols, cols contiguous.  NK: rows = output channels, cols = contraction;
+    // KN: rows = contraction, cols = output channels.
+    const bool kn = d->w_layout == T2I_W_KN;
+    const int w_n = kn ? d->w_cols : d->w_rows, w_k = kn ? d->w_rows : d->w_cols;
+    if (x.c > w_k || d->w_cols % 8 != 0) return fail(T2I_ERR_BAD_ARG, "x.c=%d vs weight contraction=%d (cols %d)", x.c, w_k, d->w_cols);
+    if (y.c > w_n || y.c % 8 != 0 || y.pitch % 8 != 0 || y.coff % 8 != 0)
+        return fail(T2I_ERR_BAD_ARG, "bad output channels c=%d pitch=%d coff=%d weight n=%d", y.c, y.pitch, y.coff, w_n);
     // virtual grid and output mapping
     prm.N = x.n;
     if (d->mode == T2I_CONV_S1) {
@@ -366,10 +381,10 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     {
         const int taps = (d->mode == T2I_CONV_S1) ? d->k * d->k : 16;
         const uint64_t e = 2;
-        const uint64_t plane_bytes = (d->np == 2) ? (uint64_t)d->w_plane_stride * e : (uint64_t)taps * d->w_cout * d->w_cin * e;
-        const uint64_t dims[4] = {(uint64_t)d->w_cin, (uint64_t)d->w_cout, (uint64_t)taps, (uint64_t)d->np};
-        const uint64_t str[3] = {(uint64_t)d->w_cin * e, (uint64_t)d->w_cin * d->w_cout * e, plane_bytes};
-        const uint32_t box[4] = {(uint32_t)kBlockK, (uint32_t)block_n, 1, 1};
+        const uint64_t plane_bytes = (d->np == 2) ? (uint64_t)d->w_plane_stride * e : (uint64_t)taps * d->w_rows * d->w_cols * e;
+        const uint64_t dims[4] = {(uint64_t)d->w_cols, (uint64_t)d->w_rows, (uint64_t)taps, (uint64_t)d->np};
+        const uint64_t str[3] = {(uint64_t)d->w_cols * e, (uint64_t)d->w_cols * d->w_rows * e, plane_bytes};
+        const uint32_t box[4] = {64, kn ? 64u : (uint32_t)block_n, 1, 1};
         rc = encode_tmap_bf16(&prm.b_map, d->w, 4, dims, str, box);
         if (rc != T2I_OK) return rc;
     }
@@ -387,23 +402,17 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     if (d->mask.ptr && d->mask_kind == T2I_MASK_NONE) return fail(T2I_ERR_BAD_ARG, "mask tensor without mask_kind");
 
     const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
-    cudaError_t e;
-    if (block_n == 256) {
-        static bool attr_done = false;
-        if (!attr_done) {
-            e = cudaFuncSetAttribute(conv_gemm_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256>::kBytes);
-            if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            attr_done = true;
-        }
-        conv_gemm_kernel<256><<<grid, kThreads, SmemLayout<256>::kBytes, stream>>>(prm);
-    } else {
-        static bool attr_done = false;
-        if (!attr_done) {
-            e = cudaFuncSetAttribute(conv_gemm_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128>::kBytes);
-            if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-            attr_done = true;
-        }
-        conv_gemm_kernel<128><<<grid, kThreads, SmemLayout<128>::kBytes, stream>>>(prm);
+    typedef void (*KernelFn)(const ConvGemmParams);
+    static bool attr_done[4] = {false, false, false, false};
+    const int variant = (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
+    const KernelFn fns[4] = {conv_gemm_kernel<128, false>, conv_gemm_kernel<128, true>, conv_gemm_kernel<256, false>,
+                             conv_gemm_kernel<256, true>};
+    const int smem_bytes = block_n == 256 ? SmemLayout<256>::kBytes : SmemLayout<128>::kBytes;
+    if (!attr_done[variant]) {
+        cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_done[variant] = true;
     }
+    fns[variant]<<<grid, kThreads, smem_bytes, stream>>>(prm);
     return check_launch("conv_gemm_kernel");
 }

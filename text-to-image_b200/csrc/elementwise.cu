@@ -110,27 +110,26 @@ __global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, int n, int 
                                       const float* __restrict__ sample_scale, bf16* col, long long ps, int np) {
     const int hp = h / 2, wq = w / 2;
     const long long rows = (long long)n * hp * wq;
-    // one thread per (row, kh): 12 values = columns [kh*12, kh*12+12); kh == 4 -> zero tail
-    const long long items = rows * 5;
+    const long long items = rows * 8;   // one thread per (row, chunk of 8 columns): one 16 B store per plane
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i / 5;
-        const int kh = (int)(i % 5);
-        bf16* dst = col + r * 64;
-        if (kh == 4) {
-            for (int j = 48; j < 64; ++j) store1(dst + j, ps, np, 0.f);
-            continue;
+        const long long r = i >> 3;
+        const int chunk = (int)(i & 7);
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        if (chunk < 6) {
+            const int q = (int)(r % wq);
+            const int p = (int)((r / wq) % hp);
+            const int b = (int)(r / ((long long)wq * hp));
+            const float s = sample_scale ? sample_scale[b] : 1.f;
+            const float* base = img + (long long)b * h * w * 3;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int colj = chunk * 8 + j;
+                const int tap = colj / 3, c = colj - tap * 3;
+                const int ih = 2 * p - 1 + (tap >> 2), iw = 2 * q - 1 + (tap & 3);
+                if (ih >= 0 && ih < h && iw >= 0 && iw < w) v[j] = __ldg(base + ((long long)ih * w + iw) * 3 + c) * s;
+            }
         }
-        const int q = (int)(r % wq);
-        const int p = (int)((r / wq) % hp);
-        const int b = (int)(r / ((long long)wq * hp));
-        const float s = sample_scale ? sample_scale[b] : 1.f;
-        const int ih = 2 * p - 1 + kh;
-        for (int kw = 0; kw < 4; ++kw) {
-            const int iw = 2 * q - 1 + kw;
-            const bool in = (ih >= 0 && ih < h && iw >= 0 && iw < w);
-            const float* src = img + (((long long)b * h + ih) * w + iw) * 3;
-            for (int c = 0; c < 3; ++c) store1(dst + (kh * 4 + kw) * 3 + c, ps, np, in ? src[c] * s : 0.f);
-        }
+        store8(col + r * 64 + chunk * 8, ps, np, v);
     }
 }
 // transpose of the above: img[n, oh, ow, c] = bias[c] + sum over (kh,kw) col[(n,p,q), (kh*4+kw)*3+c]
@@ -371,24 +370,33 @@ __global__ void bn_finalize_kernel(float* mean, float* var, float* rstd, int c, 
     rstd[i] = rsqrtf(v + eps);
 }
 
+// A thread owns one group of 8 channels (its BN parameters live in registers) and strides over rows;
+// threadIdx.x % CG walks the channel groups so that a warp reads contiguous 16 B pieces of a row.
 __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps, bf16* y,
-                                long long y_ps, int np, long long rows, int c, int relu) {
-    const int cg = c / 8;
-    const long long items = rows * cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % cg) * 8;
-        const long long e = i * 8;
+                                long long y_ps, int np, long long rows, int c, int relu, int CG) {
+    const int RY = blockDim.x / CG;
+    const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
+    const int ry = threadIdx.x / CG;
+    if (ch >= c || ry >= RY) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        sc[j] = rstd[ch + j] * gamma[ch + j];
+        sh[j] = beta[ch + j] - mean[ch + j] * sc[j];
+    }
+    for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
+        const long long e = r * c + ch;
         float v[8];
         load8(x + e, x_ps, np, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = (v[j] - mean[ch + j]) * rstd[ch + j] * gamma[ch + j] + beta[ch + j];
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
         if (res != nullptr) {
-            float r[8];
-            load8(res + e, r_ps, np, r);
+            float rr[8];
+            load8(res + e, r_ps, np, rr);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += r[j];
+            for (int j = 0; j < 8; ++j) v[j] += rr[j];
         }
         if (relu) {
 #pragma unroll
@@ -403,22 +411,43 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
                                     long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
                                     const float* __restrict__ dbeta, bf16* dx, long long dx_ps, int np, long long rows,
-                                    int c, float inv_rows) {
-    const int cg = c / 8;
-    const long long items = rows * cg;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-        const int ch = (int)(i % cg) * 8;
-        const long long e = i * 8;
+                                    int c, float inv_rows, int CG) {
+    const int RY = blockDim.x / CG;
+    const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
+    const int ry = threadIdx.x / CG;
+    if (ch >= c || ry >= RY) return;
+    float mu[8], rs[8], a[8], b0[8], b1[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        mu[j] = mean[ch + j];
+        rs[j] = rstd[ch + j];
+        a[j] = gamma[ch + j] * rs[j];
+        b0[j] = dbeta[ch + j] * inv_rows;
+        b1[j] = dgamma[ch + j] * inv_rows;
+    }
+    for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
+        const long long e = r * c + ch;
         float g[8], xv[8];
         load8(dy + e, dy_ps, np, g);
         load8(x + e, x_ps, np, xv);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            const float xh = (xv[j] - mean[ch + j]) * rstd[ch + j];
-            g[j] = gamma[ch + j] * rstd[ch + j] * (g[j] - dbeta[ch + j] * inv_rows - xh * dgamma[ch + j] * inv_rows);
-        }
+        for (int j = 0; j < 8; ++j) g[j] = a[j] * (g[j] - b0[j] - (xv[j] - mu[j]) * rs[j] * b1[j]);
         store8(dx + e, dx_ps, np, g);
     }
+}
+
+// launch geometry shared by the two row-striding kernels above
+static inline void rowwise_geometry(long long rows, int c, int threads, int* CG, dim3* grid) {
+    int cg = c / 8;
+    int g = cg > 32 ? 32 : floor_pow2(cg);
+    const int RY = threads / g;
+    const int gx = ceil_div(cg, g);
+    long long gy = (rows + RY - 1) / RY;
+    const long long cap = ((long long)num_sms() * 16 + gx - 1) / gx;
+    if (gy > cap) gy = cap;
+    if (gy < 1) gy = 1;
+    *CG = g;
+    *grid = dim3(gx, (unsigned)gy);
 }
 
 __global__ void bn_update_moving_kernel(float* mm, float* mv, const float* mean, const float* var, int c, float decay,
@@ -703,32 +732,50 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
     }
 }
 
-__global__ void adam_tf_kernel(float* theta, const float* __restrict__ grad, float* m, float* v, long long n, float lr_t,
-                               float b1, float b2, float eps, float gs) {
-    const long long n4 = n / 4;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
-        float4 g = reinterpret_cast<const float4*>(grad)[i];
-        float4 mm = reinterpret_cast<float4*>(m)[i];
-        float4 vv = reinterpret_cast<float4*>(v)[i];
-        float4 th = reinterpret_cast<float4*>(theta)[i];
-        float* gp = &g.x; float* mp = &mm.x; float* vp = &vv.x; float* tp = &th.x;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const float gj = gp[j] * gs;
-            mp[j] = b1 * mp[j] + (1.f - b1) * gj;
-            vp[j] = b2 * vp[j] + (1.f - b2) * gj * gj;
-            tp[j] -= lr_t * mp[j] / (sqrtf(vp[j]) + eps);
+__global__ void adam_tf_kernel(float* theta, const float* __restrict__ grad, float* m, float* v, long long n,
+                               const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float gs, bf16* packed,
+                               long long packed_ps, int np) {
+    const float lr_t = lr_t_dev[0];
+    const long long n8 = n / 8;
+    const bool use_m = (b1 != 0.f);
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
+        float g[8], mm[8], vv[8], th[8];
+        *reinterpret_cast<float4*>(g) = reinterpret_cast<const float4*>(grad)[2 * i];
+        *reinterpret_cast<float4*>(g + 4) = reinterpret_cast<const float4*>(grad)[2 * i + 1];
+        *reinterpret_cast<float4*>(vv) = reinterpret_cast<float4*>(v)[2 * i];
+        *reinterpret_cast<float4*>(vv + 4) = reinterpret_cast<float4*>(v)[2 * i + 1];
+        *reinterpret_cast<float4*>(th) = reinterpret_cast<float4*>(theta)[2 * i];
+        *reinterpret_cast<float4*>(th + 4) = reinterpret_cast<float4*>(theta)[2 * i + 1];
+        if (use_m) {
+            *reinterpret_cast<float4*>(mm) = reinterpret_cast<float4*>(m)[2 * i];
+            *reinterpret_cast<float4*>(mm + 4) = reinterpret_cast<float4*>(m)[2 * i + 1];
         }
-        reinterpret_cast<float4*>(m)[i] = mm;
-        reinterpret_cast<float4*>(v)[i] = vv;
-        reinterpret_cast<float4*>(theta)[i] = th;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const float gj = g[j] * gs;
+            const float mj = use_m ? b1 * mm[j] + (1.f - b1) * gj : gj;
+            mm[j] = mj;
+            vv[j] = b2 * vv[j] + (1.f - b2) * gj * gj;
+            th[j] -= lr_t * mj / (sqrtf(vv[j]) + eps);
+        }
+        if (use_m) {
+            reinterpret_cast<float4*>(m)[2 * i] = *reinterpret_cast<float4*>(mm);
+            reinterpret_cast<float4*>(m)[2 * i + 1] = *reinterpret_cast<float4*>(mm + 4);
+        }
+        reinterpret_cast<float4*>(v)[2 * i] = *reinterpret_cast<float4*>(vv);
+        reinterpret_cast<float4*>(v)[2 * i + 1] = *reinterpret_cast<float4*>(vv + 4);
+        reinterpret_cast<float4*>(theta)[2 * i] = *reinterpret_cast<float4*>(th);
+        reinterpret_cast<float4*>(theta)[2 * i + 1] = *reinterpret_cast<float4*>(th + 4);
+        if (packed != nullptr) store8(packed + i * 8, packed_ps, np, th);
     }
-    // tail
-    for (long long i = n4 * 4 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    // tail (n not a multiple of 8)
+    for (long long i = n8 * 8 + blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float gj = grad[i] * gs;
-        m[i] = b1 * m[i] + (1.f - b1) * gj;
+        const float mj = use_m ? b1 * m[i] + (1.f - b1) * gj : gj;
+        if (use_m) m[i] = mj;
         v[i] = b2 * v[i] + (1.f - b2) * gj * gj;
-        theta[i] -= lr_t * m[i] / (sqrtf(v[i]) + eps);
+        theta[i] -= lr_t * mj / (sqrtf(v[i]) + eps);
+        if (packed != nullptr) store1(packed + i, packed_ps, np, theta[i]);
     }
 }
 
@@ -751,7 +798,7 @@ extern "C" int t2i_from_planes(const void* src, long long ps, int np, float* dst
 extern "C" int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sample_scale, void* col,
                                   long long ps, int np, void* stream) {
     if ((h & 1) || (w & 1)) return fail(T2I_ERR_BAD_ARG, "im2col: odd extent");
-    const long long items = (long long)n * (h / 2) * (w / 2) * 5;
+    const long long items = (long long)n * (h / 2) * (w / 2) * 8;
     im2col_k4s2_c3_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(img, n, h, w, sample_scale, static_cast<bf16*>(col), ps, np);
     return check_launch("im2col_k4s2_c3");
 }
@@ -788,9 +835,12 @@ extern "C" int t2i_bn_apply(const void* x, long long x_ps, const float* mean, co
                             const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                             long long rows, int c, int relu, void* stream) {
     if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply: c must be a multiple of 8");
-    bn_apply_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, STREAM>>>(
+    int CG;
+    dim3 grid;
+    rowwise_geometry(rows, c, 256, &CG, &grid);
+    bn_apply_kernel<<<grid, 256, 0, STREAM>>>(
         static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, beta, static_cast<const bf16*>(residual), r_ps,
-        static_cast<bf16*>(y), y_ps, np, rows, c, relu);
+        static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG);
     return check_launch("bn_apply");
 }
 extern "C" int t2i_bn_bwd_reduce(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
@@ -802,9 +852,12 @@ extern "C" int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, 
                                 const float* rstd, const float* gamma, const float* dgamma, const float* dbeta, void* dx,
                                 long long dx_ps, int np, long long rows, int c, void* stream) {
     if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_apply: c must be a multiple of 8");
-    bn_bwd_apply_kernel<<<grid_for(rows * (c / 8), 256), 256, 0, STREAM>>>(
+    int CG;
+    dim3 grid;
+    rowwise_geometry(rows, c, 256, &CG, &grid);
+    bn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dgamma, dbeta,
-        static_cast<bf16*>(dx), dx_ps, np, rows, c, 1.f / (float)rows);
+        static_cast<bf16*>(dx), dx_ps, np, rows, c, 1.f / (float)rows, CG);
     return check_launch("bn_bwd_apply");
 }
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,
@@ -917,8 +970,10 @@ extern "C" int t2i_pack_weight(const float* w, int taps, int cout, int cin, void
                                                         static_cast<bf16*>(bwd), bwd_ps, np);
     return check_launch("pack_weight");
 }
-extern "C" int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, float lr_t, float beta1,
-                           float beta2, float eps, float grad_scale, void* stream) {
-    adam_tf_kernel<<<grid_for(n / 4 + 1, 256), 256, 0, STREAM>>>(theta, grad, m, v, n, lr_t, beta1, beta2, eps, grad_scale);
+extern "C" int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, const float* lr_t_dev,
+                           float beta1, float beta2, float eps, float grad_scale, void* packed, long long packed_ps, int np,
+                           void* stream) {
+    adam_tf_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, STREAM>>>(theta, grad, m, v, n, lr_t_dev, beta1, beta2, eps,
+                                                               grad_scale, static_cast<bf16*>(packed), packed_ps, np);
     return check_launch("adam_tf");
 }

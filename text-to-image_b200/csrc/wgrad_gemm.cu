@@ -5,6 +5,10 @@
 // SBO = 8 pixel rows).  One CTA per (tap, co tile, ci tile, K split); split-K partial sums are
 // combined with vectorised fp32 reductions (red.global.add.v4.f32) into dw.
 //
+// Tile shapes (MT x 128 output channels by BN input channels): 1x128, 1x256, 2x128.  The wide
+// shapes halve the operand bytes fetched per MMA cycle (48 KB per 512 tensor cycles instead of
+// 32 KB per 256), which is what bounds the 128x128 shape (L2 -> SMEM feed).
+//
 // Replaces Conv2DBackpropFilter / MatMul-grad reached via AdamOptimizer.minimize at
 // models/wgancls/model.py:94-106 of the reference; also forms the second-order term of the
 // gradient penalty (model.py:62-70,88-91) when x holds the tangent activations.
@@ -13,17 +17,21 @@
 
 namespace t2i {
 
-constexpr int kWM = 128;       // co per tile
-constexpr int kWN = 128;       // ci per tile
-constexpr int kWK = 64;        // pixels per K block
-constexpr int kWStages = 6;
-constexpr int kWAtomBytes = kWK * 128;                  // 64 pixels x 64 channels bf16 = 8 KB
-constexpr int kWABytes = (kWM / 64) * kWAtomBytes;      // 16 KB
-constexpr int kWBBytes = (kWN / 64) * kWAtomBytes;      // 16 KB
-constexpr int kWStageBytes = kWABytes + kWBBytes;
-constexpr int kWBarOffset = kWStages * kWStageBytes;
-constexpr int kWSmemBytes = kWBarOffset + 256 + 1024;
+constexpr int kWK = 64;                       // pixels per K block
+constexpr int kWAtomBytes = kWK * 128;        // 64 pixels x 64 channels bf16 = 8 KB
 constexpr int kWThreads = 192;
+
+template <int MT, int BN>
+struct WgradCfg {
+    static constexpr int kM = MT * 128;                       // co per tile
+    static constexpr int kABytes = (kM / 64) * kWAtomBytes;
+    static constexpr int kBBytes = (BN / 64) * kWAtomBytes;
+    static constexpr int kStageBytes = kABytes + kBBytes;
+    static constexpr int kStages = (kStageBytes <= 32768) ? 6 : 4;
+    static constexpr int kBarOffset = kStages * kStageBytes;
+    static constexpr int kSmemBytes = kBarOffset + 256 + 1024;
+    static constexpr int kTmemCols = MT * BN;                 // 128 or 256
+};
 
 struct alignas(64) WgradParams {
     CUtensorMap x_maps[4];
@@ -39,12 +47,15 @@ struct alignas(64) WgradParams {
     float* dw;
 };
 
+template <int MT, int BN>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams prm) {
+    using Cfg = WgradCfg<MT, BN>;
+    constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kWBarOffset);
-    uint64_t* empty_bar = full_bar + kWStages;
-    uint64_t* tmem_full = empty_bar + kWStages;
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
+    uint64_t* empty_bar = full_bar + kStages;
+    uint64_t* tmem_full = empty_bar + kStages;
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
 
     const int warp = threadIdx.x >> 5;
@@ -66,7 +77,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&prm.x_maps[tap.map]);
         tma_prefetch_desc(&prm.dy_maps[prm.tt.n_phases > 1 ? phase_idx : 0]);
-        for (int i = 0; i < kWStages; ++i) {
+        for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
@@ -74,7 +85,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
         fence_barrier_init();
     }
     if (warp == 1) {
-        tmem_alloc(tmem_slot, kWN);
+        tmem_alloc(tmem_slot, Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
@@ -98,16 +109,16 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                         const int tn = kb / (prm.tiles_q * prm.tiles_p);
                         const int q0 = tq * prm.bq, p0 = tp * prm.bp, n0 = tn * prm.bn;
                         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-                        mbar_arrive_expect_tx(&full_bar[stage], kWStageBytes);
-                        uint8_t* sa = smem + stage * kWStageBytes;
+                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                        uint8_t* sa = smem + stage * Cfg::kStageBytes;
 #pragma unroll
-                        for (int a = 0; a < kWM / 64; ++a)
-                            tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, cot * kWM + a * 64, q0, p0, n0, pa);
+                        for (int a = 0; a < Cfg::kM / 64; ++a)
+                            tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, cot * Cfg::kM + a * 64, q0, p0, n0, pa);
 #pragma unroll
-                        for (int b = 0; b < kWN / 64; ++b)
-                            tma_load_5d(x_map, &full_bar[stage], sa + kWABytes + b * kWAtomBytes, cit * kWN + b * 64,
+                        for (int b = 0; b < BN / 64; ++b)
+                            tma_load_5d(x_map, &full_bar[stage], sa + Cfg::kABytes + b * kWAtomBytes, cit * BN + b * 64,
                                         q0 + tap.dq, p0 + tap.dp, n0, pb);
-                        if (++stage == kWStages) {
+                        if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1;
                         }
@@ -116,23 +127,26 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             }
         } else if (warp == 1) {
             if (elect_one()) {
-                constexpr uint32_t idesc = make_idesc_bf16(kWM, kWN, 1, 1);
+                constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int kb = 0; kb < n_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 200 + stage);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * kWStageBytes);
+                    const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
 #pragma unroll
                     for (int k = 0; k < kWK / 16; ++k) {
                         // 16 pixel rows of 128 B per instruction
-                        const uint64_t da = make_sw128_desc(sa + k * 2048, kWAtomBytes, 1024);
-                        const uint64_t db = make_sw128_desc(sa + kWABytes + k * 2048, kWAtomBytes, 1024);
-                        umma_bf16(tmem_base, da, db, idesc, (kb | k) != 0);
+                        const uint64_t db = make_sw128_desc(sa + Cfg::kABytes + k * 2048, kWAtomBytes, 1024);
+#pragma unroll
+                        for (int mt = 0; mt < MT; ++mt) {
+                            const uint64_t da = make_sw128_desc(sa + mt * 2 * kWAtomBytes + k * 2048, kWAtomBytes, 1024);
+                            umma_bf16(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0);
+                        }
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kb == n_kb - 1) umma_commit(tmem_full);
-                    if (++stage == kWStages) {
+                    if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -140,28 +154,31 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             }
         } else {
             const int quarter = warp & 3;
-            const int co = cot * kWM + quarter * 32 + lane;
             mbar_wait(tmem_full, 0, 400);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + (static_cast<uint32_t>(quarter * 32) << 16);
-            float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
 #pragma unroll 1
-            for (int c0 = 0; c0 < kWN; c0 += 32) {
-                const int ci0 = cit * kWN + c0;
-                if (ci0 >= prm.cin) break;
-                __syncwarp();
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c0, r);
-                tmem_ld_wait();
-                if (co < prm.cout) {
+            for (int mt = 0; mt < MT; ++mt) {
+                const int co = cot * Cfg::kM + mt * 128 + quarter * 32 + lane;
+                const uint32_t taddr = tmem_base + mt * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+                float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
+#pragma unroll 1
+                for (int c0 = 0; c0 < BN; c0 += 32) {
+                    const int ci0 = cit * BN + c0;
+                    if (ci0 >= prm.cin) break;
+                    __syncwarp();
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + c0, r);
+                    tmem_ld_wait();
+                    if (co < prm.cout) {
 #pragma unroll
-                    for (int g = 0; g < 8; ++g) {
-                        const int ci = ci0 + g * 4;
-                        if (ci < prm.cin)
-                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci),
-                                         "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
-                                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
-                                         : "memory");
+                        for (int g = 0; g < 8; ++g) {
+                            const int ci = ci0 + g * 4;
+                            if (ci < prm.cin)
+                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci),
+                                             "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
+                                             "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                                             : "memory");
+                        }
                     }
                 }
             }
@@ -173,7 +190,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, kWN);
+        tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -201,6 +218,20 @@ static int make_maps(const t2i_act& t, bool parity, int np, int bq, int bp, int 
             if (rc != T2I_OK) return rc;
         }
     return T2I_OK;
+}
+
+template <int MT, int BN>
+static int launch_wgrad(const WgradParams& prm, int grid, cudaStream_t stream) {
+    using Cfg = WgradCfg<MT, BN>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytes);
+        if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    wgrad_gemm_kernel<MT, BN><<<grid, kWThreads, Cfg::kSmemBytes, stream>>>(prm);
+    return check_launch("wgrad_gemm_kernel");
 }
 
 }  // namespace t2i
@@ -241,8 +272,12 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     prm.k_blocks = ceil_div(prm.N, prm.bn) * prm.tiles_p * prm.tiles_q;
     prm.cout = d->cout;
     prm.cin = d->cin;
-    prm.tiles_co = ceil_div(dy.c, kWM);
-    prm.tiles_ci = ceil_div(x.c, kWN);
+    // tile shape: prefer 256 input channels per tile, else 256 output channels (two accumulators)
+    int mt = 1, bnn = 128;
+    if (x.c >= 256) bnn = 256;
+    else if (dy.c >= 256) mt = 2;
+    prm.tiles_co = ceil_div(dy.c, mt * 128);
+    prm.tiles_ci = ceil_div(x.c, bnn);
     prm.jobs = prm.tt.n_phases * prm.tt.taps_per_phase;
     prm.n_pass = (d->np == 2) ? 3 : 1;
     const int tiles = prm.jobs * prm.tiles_co * prm.tiles_ci;
@@ -263,13 +298,8 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     rc = make_maps(dy, d->mode == T2I_DECONV_K4S2, d->np, prm.bq, prm.bp, prm.bn, prm.dy_maps);
     if (rc != T2I_OK) return rc;
 
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kWSmemBytes);
-        if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
-        attr_done = true;
-    }
     const int grid = tiles * prm.splits;
-    wgrad_gemm_kernel<<<grid, kWThreads, kWSmemBytes, stream>>>(prm);
-    return check_launch("wgrad_gemm_kernel");
+    if (bnn == 256) return launch_wgrad<1, 256>(prm, grid, stream);
+    if (mt == 2) return launch_wgrad<2, 128>(prm, grid, stream);
+    return launch_wgrad<1, 128>(prm, grid, stream);
 }

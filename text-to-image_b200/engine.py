@@ -43,13 +43,13 @@ class Layer:
         self.name, self.kind, self.tf_w, self.tf_b = name, kind, tf_w, tf_b
         self.mode, self.k, self.taps, self.cout, self.cin = mode, k, taps, cout, cin
         self.need_bwd = need_bwd
-        self.w = self.b = self.gw = self.gb = self.Wf = self.Wb = None
+        self.w = self.b = self.gw = self.gb = self.Wf = None
 
 
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
-                 f32_dtype=torch.float32, share_from=None):
+                 f32_dtype=torch.float32, share_from=None, use_graphs=False):
         # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
         # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
@@ -62,6 +62,10 @@ class Engine:
             assert v % 8 == 0, "channel counts must be multiples of 8"
         self.d_t = 0
         self.g_t = 0
+        self.use_graphs = use_graphs and self.dev.type == "cuda"
+        self._graphs = {}
+        self.replayed_launches = 0      # kernels executed through graph replays
+        self.captured_launches = 0      # kernels recorded (not executed) during captures
         if share_from is None:
             before = set(self.__dict__)
             self._build_params()
@@ -140,6 +144,14 @@ class Engine:
         self.adam_m = {k: torch.zeros_like(v) for k, v in self.flat.items()}
         self.adam_v = {k: torch.zeros_like(v) for k, v in self.flat.items()}
         self.sums = {"d": self.grad["d"][self.d_n:], "g": self.grad["g"][self.g_n:]}
+        # bf16-plane mirror of the whole flat master (written by Adam itself); the layers' tensor-core
+        # weights are views into it.  One layout serves forward (NK) and input-gradient (KN) GEMMs.
+        self.packed = {k: torch.zeros(self.np, v.numel(), device=self.dev, dtype=self.act_dtype)
+                       for k, v in self.flat.items()}
+        self.lr_t = {k: torch.zeros(1, **f32) for k in self.flat}
+        self.lr_host = {k: torch.zeros(1, dtype=self.f32_dtype) for k in self.flat}
+        if self.dev.type == "cuda":
+            self.lr_host = {k: v.pin_memory() for k, v in self.lr_host.items()}
         self.P, self.G = {}, {}
         for net, table in (("d", self.d_table), ("g", self.g_table)):
             for name, (off, n) in table.items():
@@ -154,8 +166,8 @@ class Engine:
                     continue
                 l.w = l.w.view(l.taps, l.cout, l.cin)
                 l.gw = l.gw.view(l.taps, l.cout, l.cin)
-                l.Wf = torch.zeros(self.np, l.taps, l.cout, l.cin, **bf)
-                l.Wb = torch.zeros(self.np, l.taps, l.cin, l.cout, **bf) if l.need_bwd else None
+                off, n = (self.d_table if net == "d" else self.g_table)[l.name + ".w"]
+                l.Wf = self.packed[net][:, off:off + n].view(self.np, l.taps, l.cout, l.cin)
         self.bn_gamma = [self.P["g.bn%d.gamma" % i] for i in range(10)]
         self.bn_beta = [self.P["g.bn%d.beta" % i] for i in range(10)]
         self.bn_dgamma = [self.G["g.bn%d.gamma" % i] for i in range(10)]
@@ -280,10 +292,8 @@ class Engine:
         return self._export(self.G, False)
 
     def repack(self, net):
-        """fp32 master -> bf16 planes in both contraction orders (after every optimizer step)."""
-        for l in (self.dl if net == "d" else self.gl).values():
-            if l.Wf is not None:
-                self.K.pack_weight(l.w, l.Wf, l.Wb)
+        """fp32 master -> its bf16-plane mirror (checkpoint load; the optimizer step does it itself)."""
+        self.K.to_planes(self.flat[net].view(-1, 64), self.packed[net].view(self.np, -1, 64))
 
     # ------------------------------------------------------------------ buffers
     def _build_buffers(self):
@@ -394,7 +404,7 @@ class Engine:
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
         K.im2col_k4s2_c3(g["d_u4"], g["d_colg"])
         K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
-        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wb, V(rows(g["d_h5"])), algo_scale=0.75)
+        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wf, V(rows(g["d_h5"])), algo_scale=0.75, w_kn=True)
 
         def bn_bwd(i, dy, y_post, x_pre, dx, relu):
             """dy: gradient w.r.t. the BN(+ReLU) output; writes the gradient w.r.t. its input."""
@@ -411,8 +421,8 @@ class Engine:
             K.wgrad_gemm(L.mode, L.k, V(g[x]), V(g[dy]), L.gw)
             if dx is not None:
                 mode = {S1: S1, DC: K4, K4: DC}[L.mode]
-                K.conv_gemm(mode, L.k, 1 if L.k == 3 else 0, V(g[dy]), L.Wb, V(g[dx]),
-                            add=None if add is None else V(add))
+                K.conv_gemm(mode, L.k, 1 if L.k == 3 else 0, V(g[dy]), L.Wf, V(g[dx]),
+                            add=None if add is None else V(add), w_kn=True)
 
         def res_bwd(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out):
             ds = g["ds"][out]
@@ -437,7 +447,7 @@ class Engine:
         L = gl["fc0"]
         K.colsum(V(flat(g["d_f0"])), L.gb)
         K.wgrad_gemm(S1, 1, V(g["zc"]), V(flat(g["d_f0"])), L.gw)
-        K.conv_gemm(S1, 1, 0, V(flat(g["d_f0"])), L.Wb, V(g["d_zc"]))
+        K.conv_gemm(S1, 1, 0, V(flat(g["d_f0"])), L.Wf, V(g["d_zc"]), w_kn=True)
         K.ca_bwd(g["ms"], g["d_zc"], g["tn"], g["d_ms"], self.Z, self.kl_coeff / (self.GB * self.ce))
         L = gl["ms"]
         K.colsum(V(g["d_ms"]), L.gb)
@@ -498,21 +508,22 @@ class Engine:
             return K.View(t, s0, n, **kw)
 
         K.dout_bwd_data(d["a6"][:, s0:s0 + n], dl["out"].w, seed[s0:s0 + n], d["d_a6"][:, s0:s0 + n])
-        K.conv_gemm(S1, 1, 0, V(d["d_a6"]), dl["h6"].Wb, V(d["d_a5"]), mask=V(d["a5"]), mask_kind=LR)
-        K.conv_gemm(S1, 3, 1, V(d["d_a5"]), dl["h5"].Wb, V(d["d_cat"]), mask=V(d["cat"]), mask_kind=LR)
+        KN = dict(w_kn=True)    # the packed forward weights, read as [contraction][output channel]
+        K.conv_gemm(S1, 1, 0, V(d["d_a6"]), dl["h6"].Wf, V(d["d_a5"]), mask=V(d["a5"]), mask_kind=LR, **KN)
+        K.conv_gemm(S1, 3, 1, V(d["d_a5"]), dl["h5"].Wf, V(d["d_cat"]), mask=V(d["cat"]), mask_kind=LR, **KN)
         K.embed_reduce(d["d_cat"][:, s0:s0 + n], d["d_e"][:, s0:s0 + n], df8)
-        K.conv_gemm(S1, 3, 1, V(d["d_cat"], coff=0, c=df8), dl["r3"].Wb, V(d["d_r2"]), mask=V(d["r2"]), mask_kind=LR)
-        K.conv_gemm(S1, 3, 1, V(d["d_r2"]), dl["r2"].Wb, V(d["d_r1"]), mask=V(d["r1"]), mask_kind=LR)
-        K.conv_gemm(S1, 1, 0, V(d["d_r1"]), dl["r1"].Wb, V(d["d_a3"]), add=V(d["d_cat"], coff=0, c=df8))
-        K.conv_gemm(DC, 4, 0, V(d["d_a3"]), dl["h3"].Wb, V(d["d_a2"]), mask=V(d["a2"]), mask_kind=LR)
-        K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wb, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR)
-        K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wb, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR)
+        K.conv_gemm(S1, 3, 1, V(d["d_cat"], coff=0, c=df8), dl["r3"].Wf, V(d["d_r2"]), mask=V(d["r2"]), mask_kind=LR, **KN)
+        K.conv_gemm(S1, 3, 1, V(d["d_r2"]), dl["r2"].Wf, V(d["d_r1"]), mask=V(d["r1"]), mask_kind=LR, **KN)
+        K.conv_gemm(S1, 1, 0, V(d["d_r1"]), dl["r1"].Wf, V(d["d_a3"]), add=V(d["d_cat"], coff=0, c=df8), **KN)
+        K.conv_gemm(DC, 4, 0, V(d["d_a3"]), dl["h3"].Wf, V(d["d_a2"]), mask=V(d["a2"]), mask_kind=LR, **KN)
+        K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wf, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR, **KN)
+        K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wf, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR, **KN)
         if gn > 0:
-            K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wb,
-                        K.View(d["d_col0"], 0, gn * 1024), algo_scale=0.75)
+            K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wf,
+                        K.View(d["d_col0"], 0, gn * 1024), algo_scale=0.75, **KN)
             K.col2im_k4s2_c3(d["d_col0"], d["gx"], None)
             if want_cond_grad:
-                K.conv_gemm(S1, 1, 0, K.View(d["d_e"], g0, gn), dl["efc"].Wb, K.View(d["d_cond"], 0, gn))
+                K.conv_gemm(S1, 1, 0, K.View(d["d_e"], g0, gn), dl["efc"].Wf, K.View(d["d_cond"], 0, gn), **KN)
                 K.from_planes(d["d_cond"], d["g2"])
 
     def d_wgrad(self, n, n_bias):
@@ -540,12 +551,15 @@ class Engine:
         K.dout_bwd_weight(d["a6"][:, :n], d["seed"][:n], dl["out"].gw, dl["out"].gb, n_bias)
 
     # ------------------------------------------------------------------ optimizer plumbing
-    def _adam(self, net, lr, t):
-        lr_t = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+    def _set_lr(self, net, lr, t):
+        """lr_t of tf.train.AdamOptimizer, staged into device memory OUTSIDE any captured graph."""
+        self.lr_host[net][0] = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        self.lr_t[net].copy_(self.lr_host[net], non_blocking=True)
+
+    def _adam(self, net):
         n = self.d_n if net == "d" else self.g_n
-        self.K.adam_tf(self.flat[net], self.grad[net][:n], self.adam_m[net], self.adam_v[net], lr_t, self.beta1,
-                       self.beta2, ADAM_EPS, 1.0)
-        self.repack(net)
+        self.K.adam_tf(self.flat[net], self.grad[net][:n], self.adam_m[net], self.adam_v[net], self.lr_t[net],
+                       self.beta1, self.beta2, ADAM_EPS, 1.0, self.packed[net])
 
     def _reduce(self, net):
         if self.world > 1:
@@ -568,8 +582,44 @@ class Engine:
         if tn_eps is not None:
             g["tn"].copy_(tn_eps, non_blocking=True)
 
+    def _run(self, name, body):
+        """Launch a step body: eagerly, or (use_graphs) captured once into a CUDA graph and replayed.
+        The body enqueues only kernels / memsets / the allreduce on the current stream; everything that
+        varies between steps reaches it through device memory (feeds, kt, lr_t)."""
+        if not self.use_graphs or self.K.__dict__.get("PROFILE") is not None:
+            return body()
+        st = self._graphs.setdefault(name, {"n": 0, "graph": None, "launches": 0})
+        st["n"] += 1
+        if st["graph"] is not None:
+            self.replayed_launches += st["launches"]     # our kernels inside the replayed graph
+            return st["graph"].replay()
+        if st["n"] < 2:          # first call eager: one-time attribute setup, allocator warm-up
+            return body()
+        torch.cuda.synchronize()
+        from . import _lib
+        graph = torch.cuda.CUDAGraph()
+        l0 = _lib.launch_count()
+        with torch.cuda.graph(graph):
+            body()
+        st["launches"] = _lib.launch_count() - l0          # counted at capture, no work was executed
+        self.captured_launches += st["launches"]
+        st["graph"] = graph
+        self.replayed_launches += st["launches"]
+        graph.replay()
+
     def d_step(self, lr_d):
         """sess.run([D_optim, kt_optim, D_loss]) -- models/wgancls/trainer.py:97."""
+        self.d_t += 1
+        self._set_lr("d", lr_d, self.d_t)
+        self._run("d_a", self._d_body)
+        self._reduce("d")                       # the one collective of the D run, outside the graphs
+        self._run("d_b", self._d_tail)
+
+    def _d_tail(self):
+        self.K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, KT_LR)  # :79-91,100
+        self._adam("d")                                                                    # :94-97
+
+    def _d_body(self):
         K, d, g, B = self.K, self.d, self.g, self.B
         S = 4 * B
         cond = self.feed["cond"]
@@ -591,13 +641,23 @@ class Engine:
         K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])
         self.d_forward(3 * B, B, tangent=True)
         self.d_wgrad(S, 3 * B)
-        self._reduce("d")
-        K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, KT_LR)     # :79-91,100
-        self.d_t += 1
-        self._adam("d", lr_d, self.d_t)                                                  # :94-97
 
     def g_step(self, lr_g):
         """sess.run([G_optim, G_loss]) -- models/wgancls/trainer.py:101."""
+        self.g_t += 1
+        self._set_lr("g", lr_g, self.g_t)
+        self._run("g_a", self._g_body)
+        self._reduce("g")
+        self._run("g_b", self._g_tail)
+
+    def _g_tail(self):
+        K = self.K
+        K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)        # model.py:92
+        for i, c in enumerate(self.bn_ch):                                               # UPDATE_OPS, :98,102
+            K.bn_update_moving(self.bn_mm[i], self.bn_mv[i], self.bn_mean[i], self.bn_var[i], g_rows(self, i), BN_DECAY)
+        self._adam("g")                                                                  # :103-106
+
+    def _g_body(self):
         K, d, g, B = self.K, self.d, self.g, self.B
         cond = self.feed["cond"]
         self.grad["g"].zero_()
@@ -607,13 +667,6 @@ class Engine:
         K.g_sums(d["logit"], B, self.sums["g"])
         self.d_backward(0, B, d["gseed"], 0, B, False)
         self.g_backward(d["gx"])
-        self._reduce("g")
-        K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)        # model.py:92
-        for i, c in enumerate(self.bn_ch):                                               # UPDATE_OPS, :98,102
-            rows = g_rows(self, i)
-            K.bn_update_moving(self.bn_mm[i], self.bn_mv[i], self.bn_mean[i], self.bn_var[i], rows, BN_DECAY)
-        self.g_t += 1
-        self._adam("g", lr_g, self.g_t)                                                  # :103-106
 
     def sample(self, z, cond, tn_eps, out, cond_noise=True):
         """generator(z, cond, is_training=False) -- the sampler of model.py:57 (batch = engine batch)."""

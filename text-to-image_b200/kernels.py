@@ -98,17 +98,19 @@ def _prof_end(ev, kernel, tag, flops, nbytes):
 
 
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
-              algo_scale=1.0):
-    """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, w_cout, w_cin].
+              algo_scale=1.0, w_kn=False):
+    """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, rows, cols].
+    w_kn=False: rows = output channels, cols = contraction (forward use of a layer's packed weights);
+    w_kn=True : rows = contraction, cols = output channels (the same weights used for the input-gradient).
     algo_scale: fraction of the contraction that is algorithmic (0.75 for the 48-of-64 patch columns)."""
     ev = _prof_begin()
     d = _lib.ConvGemmDesc()
     d.mode, d.k, d.flip, d.np = mode, k, flip, x.np
     d.x = x._act()
-    assert w.dtype == torch.bfloat16 and w.dim() == 4 and w.is_contiguous() and w.shape[0] == x.np
+    assert w.dtype == torch.bfloat16 and w.dim() == 4 and w[0].is_contiguous() and w.shape[0] == x.np
     d.w = w.data_ptr()
     d.w_plane_stride = w.stride(0)
-    d.w_cout, d.w_cin = w.shape[2], w.shape[3]
+    d.w_rows, d.w_cols, d.w_layout = w.shape[2], w.shape[3], int(w_kn)
     d.y = y._act()
     d.bias = None if bias is None else bias.data_ptr()
     d.add = add._act() if add is not None else _null_act()
@@ -301,6 +303,8 @@ def pack_weight(w, fwd=None, bwd=None):
               0 if bwd is None else _ps(bwd), ref.shape[0], _stream())
 
 
-def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0):
-    _lib.call("t2i_adam_tf", _f32(theta), _f32(grad), _f32(m), _f32(v), theta.numel(), lr_t, beta1, beta2, eps,
-              grad_scale, _stream())
+def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0, packed=None):
+    """lr_t: fp32 DEVICE tensor [1]; packed: optional bf16 planes [np, n] receiving the updated weights."""
+    _lib.call("t2i_adam_tf", _f32(theta), _f32(grad), _f32(m), _f32(v), theta.numel(), _f32(lr_t), beta1, beta2, eps,
+              grad_scale, _p(packed), 0 if packed is None else _ps(packed), 1 if packed is None else packed.shape[0],
+              _stream())

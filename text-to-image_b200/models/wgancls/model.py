@@ -46,7 +46,8 @@ def _truncated_normal(shape, device, generator=None):
 
 
 class WGanCls(object):
-    def __init__(self, cfg, build_model=True, precision="bf16", device=None, kernels=None, distributed=None):
+    def __init__(self, cfg, build_model=True, precision="bf16", device=None, kernels=None, distributed=None,
+                 use_graphs=True):
         """
         Args:
           cfg: Config specifying all the parameters of the model (reference: model.py:6-10).
@@ -56,6 +57,7 @@ class WGanCls(object):
             bf16, three tensor-core products per contraction, ~fp32-faithful).
           distributed: None, or a torch.distributed process group handle/True for batch sharding with
             one gradient allreduce per optimizer step.
+          use_graphs: capture the D run and the G run into CUDA graphs after their first eager call.
         """
         self.cfg = cfg
 
@@ -95,6 +97,7 @@ class WGanCls(object):
             self._world = dist.get_world_size(group)
             self._allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         self._engines = {}
+        self._use_graphs = use_graphs
         self._noise_gen = None
         self._built = False
 
@@ -126,7 +129,7 @@ class WGanCls(object):
             self._engines[batch] = Engine(
                 self._K, self.device, batch, self._np, self.z_dim, self.embed_dim, self.compressed_embed_dim,
                 self.gf_dim, self.df_dim, self.cfg.TRAIN.BETA1, self.cfg.TRAIN.BETA2, self.cfg.TRAIN.COEFF.KL,
-                self._world, self._allreduce, share_from=base)
+                self._world, self._allreduce, share_from=base, use_graphs=self._use_graphs)
         return self._engines[batch]
 
     def _train_engine(self):
