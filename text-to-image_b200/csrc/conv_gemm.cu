@@ -1,7 +1,10 @@
 // Implicit-GEMM convolution for sm_100a: TMA box loads (tap-shifted, OOB zero fill = padding)
 // -> 128B-swizzled shared memory -> tcgen05.mma (M = 128 pixels, N = 128/256 channels, K = 64
 // channels per step) -> fp32 accumulators in TMEM (double buffered) -> fused epilogue
-// (bias, residual add, LeakyReLU/ReLU, derivative mask) -> bf16 planes in HBM.
+// (bias, residual add, LeakyReLU/ReLU, derivative mask) -> bf16 planes staged in swizzled shared
+// memory -> TMA tensor stores.  The residual / mask tiles the epilogue needs are themselves
+// TMA-loaded (prefetched one or two 64-channel sub-tiles ahead), so every global access of the
+// kernel is a full-line bulk transfer.
 //
 // One persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
 // warps 2..5 = epilogue (each owns the 32 TMEM lanes its warp id % 4 selects).
@@ -18,57 +21,86 @@ constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kThreads = 192;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
-
-struct EpiTensor {
-    const __nv_bfloat16* ptr;
-    long long plane_stride;
-    int pitch, coff;
-};
+constexpr int kSubBytes = kBlockM * 64 * 2;     // one 128-pixel x 64-channel bf16 sub-tile = 16 KB
+constexpr int kMaxStages = 8;
+constexpr int kSmemBudget = 232448 - 1024;      // 227 KB minus alignment slack
 
 struct alignas(64) ConvGemmParams {
-    CUtensorMap a_maps[4];
-    CUtensorMap b_map;
+    CUtensorMap a_maps[4];     // input views (stride-2 convs: four parity views)
+    CUtensorMap b_map;         // packed weights
+    CUtensorMap out_maps[4];   // output views (transposed convs: one parity view per phase)
+    CUtensorMap add_maps[4];   // optional residual, same grid as the output
+    CUtensorMap mask_maps[4];  // optional derivative-mask source, same grid as the output
     TapTable tt;
-    int N, P, Q;           // virtual pixel grid (one GEMM row per point)
-    int bn, bp, bq;        // TMA box on that grid, bn*bp*bq == 128
-    int tiles_p, tiles_q;  // tiles along p and q (tiles along n = tiles_m / (tiles_p*tiles_q))
+    int N, P, Q;               // virtual pixel grid (one GEMM row per point)
+    int bn, bp, bq;            // TMA box on that grid, bn*bp*bq == 128
+    int tiles_p, tiles_q;
     int tiles_m, tiles_co, total_tiles;
-    int k_chunks;          // ceil(Cin / 64)
-    int n_pass;            // 1 (bf16) or 3 (split bf16: hi*hi, lo*hi, hi*lo)
+    int k_chunks;              // ceil(Cin / 64)
+    int n_pass;                // 1 (bf16) or 3 (split bf16: hi*hi, lo*hi, hi*lo)
     int np;
     int Cout;
-    int OH, OW, osp, osq;  // output pixel = (p*osp + op, q*osq + oq)
-    __nv_bfloat16* out;
-    long long out_plane_stride;
-    int out_pitch, out_coff;
+    int n_stages;              // mainloop pipeline depth (what fits beside the epilogue buffers)
+    int epi_depth;             // 1 or 2 staging buffers per epilogue tensor
+    int has_add, has_mask;
     const float* bias;
-    EpiTensor add, mask;
     int act, mask_kind;
 };
 
-template <int BLOCK_N>
-struct SmemLayout {
-    static constexpr int kBBytes = BLOCK_N * kBlockK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kStages = (BLOCK_N == 256) ? 4 : 6;
-    static constexpr int kBarOffset = kStages * kStageBytes;
-    static constexpr int kBytes = kBarOffset + 256 + 1024;  // barriers + alignment slack
+__device__ __forceinline__ void tma_store_5d(const void* tmap, const void* src, int c0, int c1, int c2, int c3, int c4) {
+    asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
+                     reinterpret_cast<uint64_t>(tmap)),
+                 "r"(smem_u32(src)), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
+                 : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void bulk_wait_read() {
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void bulk_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+struct TileCoord {
+    int ct, ph, q0, p0, n0;
 };
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int tile) {
+    TileCoord t;
+    t.ct = tile % prm.tiles_co;
+    const int rest = tile / prm.tiles_co;
+    const int mt = rest % prm.tiles_m;
+    t.ph = rest / prm.tiles_m;
+    t.q0 = (mt % prm.tiles_q) * prm.bq;
+    t.p0 = ((mt / prm.tiles_q) % prm.tiles_p) * prm.bp;
+    t.n0 = (mt / (prm.tiles_q * prm.tiles_p)) * prm.bn;
+    return t;
+}
 
 // B_KN = false: weights [tap][N][K], K contiguous (K-major B operand, forward layout used forward).
 // B_KN = true : weights [tap][K][N], N contiguous (MN-major B operand): the SAME packed forward
 //               weights serve the input-gradient convolutions, no transposed copy exists.
 template <int BLOCK_N, bool B_KN>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
-    using L = SmemLayout<BLOCK_N>;
-    constexpr int kStages = L::kStages;
+    constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    constexpr int kStageBytes = kABytes + kBBytes;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + L::kBarOffset);
-    uint64_t* empty_bar = full_bar + kStages;
-    uint64_t* tmem_full = empty_bar + kStages;
+    const int n_stages = prm.n_stages;
+    const int D = prm.epi_depth;
+    const int np = prm.np;
+    // carve-up: [stages][out D*np][add D*np][mask D*np][bias][barriers]
+    uint8_t* s_out = smem + n_stages * kStageBytes;
+    uint8_t* s_add = s_out + D * np * kSubBytes;
+    uint8_t* s_mask = s_add + (prm.has_add ? D * np * kSubBytes : 0);
+    float* s_bias = reinterpret_cast<float*>(s_mask + (prm.has_mask ? D * np * kSubBytes : 0));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+    uint64_t* empty_bar = full_bar + kMaxStages;
+    uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* aux_full = tmem_empty + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -76,13 +108,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.a_maps[i]);
         tma_prefetch_desc(&prm.b_map);
-        for (int i = 0; i < kStages; ++i) {
+        for (int i = 0; i < n_stages; ++i) {
             mbar_init(&full_bar[i], 1);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], 4);
+            mbar_init(&aux_full[i], 1);
         }
         fence_barrier_init();
     }
@@ -104,35 +137,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             int stage = 0;
             uint32_t phase = 0;
             for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-                const int ct = tile % prm.tiles_co;
-                const int rest = tile / prm.tiles_co;
-                const int mt = rest % prm.tiles_m;
-                const int ph = rest / prm.tiles_m;
-                const int tq = mt % prm.tiles_q;
-                const int tp = (mt / prm.tiles_q) % prm.tiles_p;
-                const int tn = mt / (prm.tiles_q * prm.tiles_p);
-                const int q0 = tq * prm.bq, p0 = tp * prm.bp, n0 = tn * prm.bn;
+                const TileCoord tc = decode_tile(prm, tile);
                 for (int pass = 0; pass < prm.n_pass; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;  // A plane: hi, lo, hi
                     const int pb = (pass == 2) ? 1 : 0;  // B plane: hi, hi, lo
                     for (int t = 0; t < tpp; ++t) {
-                        const Tap tap = prm.tt.taps[ph * tpp + t];
+                        const Tap tap = prm.tt.taps[tc.ph * tpp + t];
                         for (int kc = 0; kc < prm.k_chunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-                            mbar_arrive_expect_tx(&full_bar[stage], L::kStageBytes);
-                            uint8_t* sa = smem + stage * L::kStageBytes;
-                            tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, q0 + tap.dq,
-                                        p0 + tap.dp, n0, pa);
+                            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                            uint8_t* sa = smem + stage * kStageBytes;
+                            tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, tc.q0 + tap.dq,
+                                        tc.p0 + tap.dp, tc.n0, pa);
                             if (!B_KN) {
-                                tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, ct * BLOCK_N,
+                                tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, tc.ct * BLOCK_N,
                                             tap.wtap, pb);
                             } else {
 #pragma unroll
                                 for (int a = 0; a < BLOCK_N / 64; ++a)   // 64-channel atoms of [64 K rows x 128 B]
                                     tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes + a * 8192,
-                                                ct * BLOCK_N + a * 64, kc * kBlockK, tap.wtap, pb);
+                                                tc.ct * BLOCK_N + a * 64, kc * kBlockK, tap.wtap, pb);
                             }
-                            if (++stage == kStages) {
+                            if (++stage == n_stages) {
                                 stage = 0;
                                 phase ^= 1;
                             }
@@ -157,7 +183,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 for (int kb = 0; kb < kb_per_tile; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 200 + stage);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(smem + stage * L::kStageBytes);
+                    const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t da = make_sw128_desc(sa, 0, 1024);
                     // K-major: +32 bytes per 16-element K step inside the 128B swizzle row (address >> 4);
                     // MN-major: 16 K rows of 128 B per step, 8 KB between 64-channel atoms.
@@ -168,7 +194,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     }
                     umma_commit(&empty_bar[stage]);
                     if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);
-                    if (++stage == kStages) {
+                    if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
                     }
@@ -176,99 +202,158 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
     } else {
-        // ------------------------------------------------ epilogue warps
+        // ------------------------------------------------ epilogue warps (128 threads, thread <-> tile row)
         const int quarter = warp & 3;
         const int row = quarter * 32 + lane;
-        const int np = prm.np;
+        const bool leader = (warp == 2 && lane == 0);
+        const bool has_aux = prm.has_add || prm.has_mask;
+        const uint32_t aux_bytes = static_cast<uint32_t>((prm.has_add + prm.has_mask) * np * kSubBytes);
+        const int sw = row & 7;                       // 128B swizzle: 16B chunk j of row r lives at chunk j ^ (r & 7)
+        const uint32_t row_off = row * 128;
+        const float neg = (prm.mask_kind == T2I_MASK_LRELU) ? 0.2f : 0.0f;
+
+        // aux tiles are prefetched D sub-tiles ahead along the sequence (tile, sub) this CTA will process
+        auto issue_aux = [&](int tile, int sub, int buf) {
+            const TileCoord tc = decode_tile(prm, tile);
+            const int c0 = tc.ct * BLOCK_N + sub * 64;
+            mbar_arrive_expect_tx(&aux_full[buf], aux_bytes);
+            for (int pl = 0; pl < np; ++pl) {
+                if (prm.has_add)
+                    tma_load_5d(&prm.add_maps[tc.ph], &aux_full[buf], s_add + (buf * np + pl) * kSubBytes, c0, tc.q0, tc.p0,
+                                tc.n0, pl);
+                if (prm.has_mask)
+                    tma_load_5d(&prm.mask_maps[tc.ph], &aux_full[buf], s_mask + (buf * np + pl) * kSubBytes, c0, tc.q0,
+                                tc.p0, tc.n0, pl);
+            }
+        };
+        auto subs_of = [&](int tile) {
+            const int ct = tile % prm.tiles_co;
+            int rem = prm.Cout - ct * BLOCK_N;
+            if (rem > BLOCK_N) rem = BLOCK_N;
+            return (rem + 63) / 64;
+        };
+        // prefetch cursor (tile, sub) runs D elements ahead of the compute cursor
+        int pf_tile = blockIdx.x, pf_sub = 0;
+        auto pf_advance = [&]() {
+            if (++pf_sub >= subs_of(pf_tile)) {
+                pf_sub = 0;
+                pf_tile += gridDim.x;
+            }
+        };
+        if (has_aux && leader) {
+            for (int i = 0; i < D; ++i) {
+                if (pf_tile < prm.total_tiles) {
+                    issue_aux(pf_tile, pf_sub, i);
+                    pf_advance();
+                }
+            }
+        }
+
+        int g = 0;   // running index of 64-channel sub-tiles processed by this CTA
         int it = 0;
         for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const int ct = tile % prm.tiles_co;
-            const int rest = tile / prm.tiles_co;
-            const int mt = rest % prm.tiles_m;
-            const int ph = rest / prm.tiles_m;
-            const int tq = mt % prm.tiles_q;
-            const int tp = (mt / prm.tiles_q) % prm.tiles_p;
-            const int tn = mt / (prm.tiles_q * prm.tiles_p);
-            const int q = tq * prm.bq + row % prm.bq;
-            const int p = tp * prm.bp + (row / prm.bq) % prm.bp;
-            const int n = tn * prm.bn + row / (prm.bq * prm.bp);
-            const bool valid = (n < prm.N) && (p < prm.P) && (q < prm.Q);
-            const long long pix = (static_cast<long long>(n) * prm.OH + (p * prm.osp + prm.tt.ph_op[ph])) * prm.OW +
-                                  (q * prm.osq + prm.tt.ph_oq[ph]);
-            const int co_base = ct * BLOCK_N;
-
-            mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
-            tc_fence_after();
+            const TileCoord tc = decode_tile(prm, tile);
+            const int co_base = tc.ct * BLOCK_N;
+            const int n_sub = subs_of(tile);
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+            // stage this tile's bias slice (all threads passed the previous sub-tile's second barrier)
+            if (prm.bias != nullptr) {
+                for (int i = row; i < BLOCK_N; i += 128) s_bias[i] = (co_base + i < prm.Cout) ? __ldg(prm.bias + co_base + i) : 0.f;
+            }
+            for (int sub = 0; sub < n_sub; ++sub, ++g) {
+                const int buf = (D == 2) ? (g & 1) : 0;
+                const uint32_t aux_parity = (D == 2) ? ((g >> 1) & 1) : (g & 1);
+                if (leader) {   // the store that last used out[buf] must have finished reading it
+                    if (D == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                }
+                if (has_aux) mbar_wait(&aux_full[buf], aux_parity, 500 + buf);
+                named_bar_sync(1, 128);
+                if (sub == 0) {
+                    mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
+                    tc_fence_after();
+                }
+                uint8_t* o_hi = s_out + (buf * np) * kSubBytes + row_off;
+                const uint8_t* a_base = s_add + (buf * np) * kSubBytes + row_off;
+                const uint8_t* m_base = s_mask + (buf * np) * kSubBytes + row_off;
 #pragma unroll 1
-            for (int c0 = 0; c0 < BLOCK_N; c0 += 32) {
-                if (co_base + c0 >= prm.Cout) break;  // warp-uniform
-                __syncwarp();
-                uint32_t r[32];
-                tmem_ld_32x32(taddr + c0, r);
-                tmem_ld_wait();
-                if (!valid) continue;
+                for (int half = 0; half < 2; ++half) {
+                    __syncwarp();
+                    uint32_t r[32];
+                    tmem_ld_32x32(taddr + sub * 64 + half * 32, r);
+                    tmem_ld_wait();
 #pragma unroll
-                for (int g = 0; g < 4; ++g) {
-                    const int co = co_base + c0 + g * 8;
-                    if (co >= prm.Cout) break;
-                    float v[8];
+                    for (int gq = 0; gq < 4; ++gq) {
+                        const int chunk = half * 4 + gq;              // 16B chunk (8 channels) within the 64-channel row
+                        const uint32_t coff = static_cast<uint32_t>((chunk ^ sw) * 16);
+                        float v[8];
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[g * 8 + j]);
-                    if (prm.bias != nullptr) {
-                        const float4 b0 = __ldg(reinterpret_cast<const float4*>(prm.bias + co));
-                        const float4 b1 = __ldg(reinterpret_cast<const float4*>(prm.bias + co + 4));
-                        v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
-                        v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
-                    }
-                    if (prm.add.ptr != nullptr) {
-                        const __nv_bfloat16* ap = prm.add.ptr + pix * prm.add.pitch + prm.add.coff + co;
-                        for (int pl = 0; pl < np; ++pl) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(ap + pl * prm.add.plane_stride);
-                            v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
-                            v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+                        for (int j = 0; j < 8; ++j) v[j] = __uint_as_float(r[gq * 8 + j]);
+                        if (prm.bias != nullptr) {
+                            const float4 b0 = *reinterpret_cast<const float4*>(s_bias + sub * 64 + chunk * 8);
+                            const float4 b1 = *reinterpret_cast<const float4*>(s_bias + sub * 64 + chunk * 8 + 4);
+                            v[0] += b0.x; v[1] += b0.y; v[2] += b0.z; v[3] += b0.w;
+                            v[4] += b1.x; v[5] += b1.y; v[6] += b1.z; v[7] += b1.w;
+                        }
+                        if (prm.has_add) {
+                            for (int pl = 0; pl < np; ++pl) {
+                                const uint4 u = *reinterpret_cast<const uint4*>(a_base + pl * kSubBytes + coff);
+                                v[0] += bf16_lo(u.x); v[1] += bf16_hi(u.x); v[2] += bf16_lo(u.y); v[3] += bf16_hi(u.y);
+                                v[4] += bf16_lo(u.z); v[5] += bf16_hi(u.z); v[6] += bf16_lo(u.w); v[7] += bf16_hi(u.w);
+                            }
+                        }
+                        if (prm.act == T2I_ACT_LRELU) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
+                        } else if (prm.act == T2I_ACT_RELU) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
+                        }
+                        if (prm.has_mask) {
+                            float m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                            for (int pl = 0; pl < np; ++pl) {
+                                const uint4 u = *reinterpret_cast<const uint4*>(m_base + pl * kSubBytes + coff);
+                                m[0] += bf16_lo(u.x); m[1] += bf16_hi(u.x); m[2] += bf16_lo(u.y); m[3] += bf16_hi(u.y);
+                                m[4] += bf16_lo(u.z); m[5] += bf16_hi(u.z); m[6] += bf16_lo(u.w); m[7] += bf16_hi(u.w);
+                            }
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) v[j] *= (m[j] > 0.0f) ? 1.0f : neg;
+                        }
+                        uint4 hi;
+                        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                        *reinterpret_cast<uint4*>(o_hi + coff) = hi;
+                        if (np == 2) {
+                            uint4 lo;
+                            lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
+                            lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
+                            lo.z = pack_bf16x2(v[4] - bf16_lo(hi.z), v[5] - bf16_hi(hi.z));
+                            lo.w = pack_bf16x2(v[6] - bf16_lo(hi.w), v[7] - bf16_hi(hi.w));
+                            *reinterpret_cast<uint4*>(o_hi + kSubBytes + coff) = lo;
                         }
                     }
-                    if (prm.act == T2I_ACT_LRELU) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.2f * v[j]);
-                    } else if (prm.act == T2I_ACT_RELU) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.0f);
-                    }
-                    if (prm.mask.ptr != nullptr) {
-                        const __nv_bfloat16* mp = prm.mask.ptr + pix * prm.mask.pitch + prm.mask.coff + co;
-                        float m[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-                        for (int pl = 0; pl < np; ++pl) {
-                            const uint4 u = *reinterpret_cast<const uint4*>(mp + pl * prm.mask.plane_stride);
-                            m[0] += bf16_lo(u.x); m[1] += bf16_hi(u.x); m[2] += bf16_lo(u.y); m[3] += bf16_hi(u.y);
-                            m[4] += bf16_lo(u.z); m[5] += bf16_hi(u.z); m[6] += bf16_lo(u.w); m[7] += bf16_hi(u.w);
-                        }
-                        const float neg = (prm.mask_kind == T2I_MASK_LRELU) ? 0.2f : 0.0f;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) v[j] *= (m[j] > 0.0f) ? 1.0f : neg;
-                    }
-                    __nv_bfloat16* op = prm.out + pix * prm.out_pitch + prm.out_coff + co;
-                    uint4 hi;
-                    hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                    hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                    *reinterpret_cast<uint4*>(op) = hi;
-                    if (np == 2) {
-                        uint4 lo;
-                        lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
-                        lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
-                        lo.z = pack_bf16x2(v[4] - bf16_lo(hi.z), v[5] - bf16_hi(hi.z));
-                        lo.w = pack_bf16x2(v[6] - bf16_lo(hi.w), v[7] - bf16_hi(hi.w));
-                        *reinterpret_cast<uint4*>(op + prm.out_plane_stride) = lo;
+                }
+                if (sub == n_sub - 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                }
+                fence_proxy_async();      // generic-proxy smem writes -> visible to the TMA store
+                named_bar_sync(2, 128);
+                if (leader) {
+                    for (int pl = 0; pl < np; ++pl)
+                        tma_store_5d(&prm.out_maps[tc.ph], s_out + (buf * np + pl) * kSubBytes, co_base + sub * 64, tc.q0,
+                                     tc.p0, tc.n0, pl);
+                    bulk_commit();
+                    if (has_aux && pf_tile < prm.total_tiles) {   // aux[buf] has been consumed by every thread
+                        issue_aux(pf_tile, pf_sub, buf);
+                        pf_advance();
                     }
                 }
             }
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&tmem_empty[acc]);
         }
+        if (leader) bulk_wait_all();
     }
 
     tc_fence_before();
@@ -280,7 +365,9 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
 }
 
-static int make_act_maps(const t2i_act& x, int mode, int np, int bq, int bp, int bn, CUtensorMap* maps, int n_maps) {
+// Tensor maps of an NHWC planes view on the kernel's pixel grid: one map, or the four stride-2
+// parity views (view (rh, rw) holds pixels (2p + rh, 2q + rw)).
+static int make_act_maps(const t2i_act& x, bool parity, int np, int bq, int bp, int bn, CUtensorMap* maps) {
     if (x.pitch % 8 != 0 || x.coff % 8 != 0 || x.c % 8 != 0)
         return fail(T2I_ERR_BAD_ARG, "activation channels must be multiples of 8 (c=%d pitch=%d coff=%d)", x.c,
                     x.pitch, x.coff);
@@ -288,14 +375,13 @@ static int make_act_maps(const t2i_act& x, int mode, int np, int bq, int bp, int
     const uint64_t plane_bytes = (np == 2) ? (uint64_t)x.plane_stride * e : (uint64_t)x.n * x.h * x.w * x.pitch * e;
     const uint32_t box[5] = {(uint32_t)kBlockK, (uint32_t)bq, (uint32_t)bp, (uint32_t)bn, 1};
     const __nv_bfloat16* base = static_cast<const __nv_bfloat16*>(x.ptr) + x.coff;
-    if (n_maps == 1) {
+    if (!parity) {
         const uint64_t dims[5] = {(uint64_t)x.c, (uint64_t)x.w, (uint64_t)x.h, (uint64_t)x.n, (uint64_t)np};
         const uint64_t str[4] = {(uint64_t)x.pitch * e, (uint64_t)x.w * x.pitch * e, (uint64_t)x.h * x.w * x.pitch * e,
                                  plane_bytes};
         return encode_tmap_bf16(&maps[0], base, 5, dims, str, box);
     }
-    // stride-2 parity views: view (rh, rw) holds pixels (2*p + rh, 2*q + rw)
-    if ((x.h & 1) || (x.w & 1)) return fail(T2I_ERR_BAD_ARG, "K4S2 needs even h, w (got %d x %d)", x.h, x.w);
+    if ((x.h & 1) || (x.w & 1)) return fail(T2I_ERR_BAD_ARG, "stride-2 views need even h, w (got %d x %d)", x.h, x.w);
     for (int rh = 0; rh < 2; ++rh)
         for (int rw = 0; rw < 2; ++rw) {
             const uint64_t dims[5] = {(uint64_t)x.c, (uint64_t)x.w / 2, (uint64_t)x.h / 2, (uint64_t)x.n, (uint64_t)np};
@@ -308,7 +394,7 @@ static int make_act_maps(const t2i_act& x, int mode, int np, int bq, int bp, int
 }
 
 // Box on the virtual grid with bq*bp*bn == rows (a power of two).
-static void choose_box(int N, int P, int Q, int rows, int* bn, int* bp, int* bq) {
+static void choose_box(int P, int Q, int rows, int* bn, int* bp, int* bq) {
     int q = floor_pow2(Q);
     if (q > rows) q = rows;
     int p = floor_pow2(P);
@@ -316,16 +402,6 @@ static void choose_box(int N, int P, int Q, int rows, int* bn, int* bp, int* bq)
     *bq = q;
     *bp = p;
     *bn = rows / (q * p);
-    (void)N;
-}
-
-static EpiTensor epi_of(const t2i_act& a) {
-    EpiTensor e;
-    e.ptr = static_cast<const __nv_bfloat16*>(a.ptr);
-    e.plane_stride = a.plane_stride;
-    e.pitch = a.pitch;
-    e.coff = a.coff;
-    return e;
 }
 
 }  // namespace t2i
@@ -350,19 +426,19 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     if (x.c > w_k || d->w_cols % 8 != 0) return fail(T2I_ERR_BAD_ARG, "x.c=%d vs weight contraction=%d (cols %d)", x.c, w_k, d->w_cols);
     if (y.c > w_n || y.c % 8 != 0 || y.pitch % 8 != 0 || y.coff % 8 != 0)
         return fail(T2I_ERR_BAD_ARG, "bad output channels c=%d pitch=%d coff=%d weight n=%d", y.c, y.pitch, y.coff, w_n);
-    // virtual grid and output mapping
+    // virtual grid and output extent
+    int OH, OW;
     prm.N = x.n;
     if (d->mode == T2I_CONV_S1) {
-        prm.P = x.h; prm.Q = x.w; prm.OH = x.h; prm.OW = x.w; prm.osp = prm.osq = 1;
+        prm.P = x.h; prm.Q = x.w; OH = x.h; OW = x.w;
     } else if (d->mode == T2I_CONV_K4S2) {
-        prm.P = x.h / 2; prm.Q = x.w / 2; prm.OH = x.h / 2; prm.OW = x.w / 2; prm.osp = prm.osq = 1;
+        prm.P = x.h / 2; prm.Q = x.w / 2; OH = x.h / 2; OW = x.w / 2;
     } else {
-        prm.P = x.h; prm.Q = x.w; prm.OH = 2 * x.h; prm.OW = 2 * x.w; prm.osp = prm.osq = 2;
+        prm.P = x.h; prm.Q = x.w; OH = 2 * x.h; OW = 2 * x.w;
     }
-    if (y.n != x.n || y.h != prm.OH || y.w != prm.OW)
-        return fail(T2I_ERR_BAD_ARG, "output shape [%d,%d,%d] does not match expected [%d,%d,%d]", y.n, y.h, y.w, x.n,
-                    prm.OH, prm.OW);
-    choose_box(prm.N, prm.P, prm.Q, kBlockM, &prm.bn, &prm.bp, &prm.bq);
+    if (y.n != x.n || y.h != OH || y.w != OW)
+        return fail(T2I_ERR_BAD_ARG, "output shape [%d,%d,%d] does not match expected [%d,%d,%d]", y.n, y.h, y.w, x.n, OH, OW);
+    choose_box(prm.P, prm.Q, kBlockM, &prm.bn, &prm.bp, &prm.bq);
     prm.tiles_q = ceil_div(prm.Q, prm.bq);
     prm.tiles_p = ceil_div(prm.P, prm.bp);
     prm.tiles_m = ceil_div(prm.N, prm.bn) * prm.tiles_p * prm.tiles_q;
@@ -370,14 +446,46 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     prm.k_chunks = ceil_div(x.c, kBlockK);
     prm.np = d->np;
     prm.n_pass = (d->np == 2) ? 3 : 1;
+    prm.has_add = d->add.ptr != nullptr;
+    prm.has_mask = d->mask.ptr != nullptr;
+    if (prm.has_mask && d->mask_kind == T2I_MASK_NONE) return fail(T2I_ERR_BAD_ARG, "mask tensor without mask_kind");
+    for (const t2i_act* a : {&d->add, &d->mask})
+        if (a->ptr != nullptr && (a->n != y.n || a->h != y.h || a->w != y.w || a->c < y.c))
+            return fail(T2I_ERR_BAD_ARG, "epilogue tensor [%d,%d,%d,%d] does not cover the output [%d,%d,%d,%d]", a->n, a->h,
+                        a->w, a->c, y.n, y.h, y.w, y.c);
     const int sms = num_sms();
     int block_n = 128;
     if (y.c > 128 && (long long)prm.tt.n_phases * prm.tiles_m * ceil_div(y.c, 256) >= sms) block_n = 256;
     prm.tiles_co = ceil_div(y.c, block_n);
     prm.total_tiles = prm.tt.n_phases * prm.tiles_m * prm.tiles_co;
+    // shared memory plan: epilogue staging first, the mainloop pipeline takes what is left
+    prm.epi_depth = (d->np == 1) ? 2 : 1;
+    const int stage_bytes = kABytes + block_n * kBlockK * 2;
+    const int epi_bytes = (1 + prm.has_add + prm.has_mask) * prm.epi_depth * d->np * kSubBytes;
+    const int tail_bytes = block_n * 4 + 256;   // bias slice + barriers
+    int stages = (kSmemBudget - epi_bytes - tail_bytes) / stage_bytes;
+    if (stages > kMaxStages) stages = kMaxStages;
+    if (stages < 2) return fail(T2I_ERR_BAD_ARG, "shared memory plan leaves %d pipeline stages", stages);
+    prm.n_stages = stages;
+    const int smem_bytes = stages * stage_bytes + epi_bytes + tail_bytes + 1024;
 
-    rc = make_act_maps(x, d->mode, d->np, prm.bq, prm.bp, prm.bn, prm.a_maps, prm.tt.n_maps);
+    const bool parity_in = d->mode == T2I_CONV_K4S2, parity_out = d->mode == T2I_DECONV_K4S2;
+    rc = make_act_maps(x, parity_in, d->np, prm.bq, prm.bp, prm.bn, prm.a_maps);
     if (rc != T2I_OK) return rc;
+    rc = make_act_maps(y, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.out_maps);
+    if (rc != T2I_OK) return rc;
+    if (prm.has_add) {
+        t2i_act a = d->add;
+        a.c = y.c;
+        rc = make_act_maps(a, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.add_maps);
+        if (rc != T2I_OK) return rc;
+    }
+    if (prm.has_mask) {
+        t2i_act a = d->mask;
+        a.c = y.c;
+        rc = make_act_maps(a, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.mask_maps);
+        if (rc != T2I_OK) return rc;
+    }
     {
         const int taps = (d->mode == T2I_CONV_S1) ? d->k * d->k : 16;
         const uint64_t e = 2;
@@ -388,18 +496,9 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         rc = encode_tmap_bf16(&prm.b_map, d->w, 4, dims, str, box);
         if (rc != T2I_OK) return rc;
     }
-    prm.out = static_cast<__nv_bfloat16*>(y.ptr);
-    prm.out_plane_stride = y.plane_stride;
-    prm.out_pitch = y.pitch;
-    prm.out_coff = y.coff;
     prm.bias = d->bias;
-    prm.add = epi_of(d->add);
-    prm.mask = epi_of(d->mask);
     prm.act = d->act;
     prm.mask_kind = d->mask_kind;
-    if (d->add.ptr && (d->add.pitch % 8 || d->add.coff % 8)) return fail(T2I_ERR_BAD_ARG, "add tensor misaligned");
-    if (d->mask.ptr && (d->mask.pitch % 8 || d->mask.coff % 8)) return fail(T2I_ERR_BAD_ARG, "mask tensor misaligned");
-    if (d->mask.ptr && d->mask_kind == T2I_MASK_NONE) return fail(T2I_ERR_BAD_ARG, "mask tensor without mask_kind");
 
     const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
     typedef void (*KernelFn)(const ConvGemmParams);
@@ -407,9 +506,8 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const int variant = (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
     const KernelFn fns[4] = {conv_gemm_kernel<128, false>, conv_gemm_kernel<128, true>, conv_gemm_kernel<256, false>,
                              conv_gemm_kernel<256, true>};
-    const int smem_bytes = block_n == 256 ? SmemLayout<256>::kBytes : SmemLayout<128>::kBytes;
     if (!attr_done[variant]) {
-        cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
+        cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_done[variant] = true;
     }
