@@ -236,13 +236,24 @@ def main():
     pk = peaks()
     roofline = None
     # every rank runs these steps (they contain the allreduce); they run eagerly, outside the CUDA graphs
+    # and single-stream (side stream off), so that each kernel's event pair times that kernel alone
+    side, eng.side_stream = eng.side_stream, None
     kernels.PROFILE = []
     psteps = 2
     for _ in range(psteps):
         resident_step()
     barrier()
     prof = kernels.PROFILE
+    timeline = None
+    if args.profile_out:     # a second pair of steps with an event pair around EVERY C-ABI call
+        kernels.PROFILE = []
+        _lib.TIMELINE = []
+        for _ in range(psteps):
+            resident_step()
+        barrier()
+        timeline, _lib.TIMELINE = _lib.TIMELINE, None
     kernels.PROFILE = None
+    eng.side_stream = side
     if rank == 0:
         rows = [(k, tag, fl, nb, a.elapsed_time(b)) for k, tag, fl, nb, a, b in prof]
         agg = {}
@@ -269,8 +280,14 @@ def main():
             table = [{"launch": k, "calls_per_step": v[3] / psteps, "ms_per_step": v[2] / psteps,
                       "tflops": v[0] / (v[2] * 1e-3) / 1e12, "algo_gbytes_per_s": v[1] / (v[2] * 1e-3) / 1e9}
                      for k, v in sorted(per.items(), key=lambda kv: -kv[1][2])]
+            ep = {}
+            for name, a, b in timeline:
+                v = ep.setdefault(name, [0.0, 0])
+                v[0] += a.elapsed_time(b); v[1] += 1
+            entry = [{"entry_point": k, "calls_per_step": v[1] / psteps, "ms_per_step": v[0] / psteps}
+                     for k, v in sorted(ep.items(), key=lambda kv: -kv[1][0])]
             with open(args.profile_out, "w") as f:
-                json.dump({"ms_per_step": ms_per_step, "table": table}, f, indent=1)
+                json.dump({"ms_per_step": ms_per_step, "table": table, "entry_points": entry}, f, indent=1)
 
     # ------------------------------------------------------------ CPU baseline (rank 0, N = 1)
     cpu = None

@@ -115,8 +115,9 @@ int t2i_conv3x3_c3_tanh_bwd(const float* x, const float* w, const float* y, cons
 int t2i_colsum(const void* src, long long plane_stride, int np, long long rows, int c, int pitch, int coff,
                float* out, void* stream);
 
-/* Training-mode batch norm (utils/ops.py:7-29 via model.py:176-216): statistics, apply, backward. */
-int t2i_bn_stats(const void* x, long long plane_stride, int np, long long rows, int c, float* mean,
+/* Training-mode batch norm (utils/ops.py:7-29 via model.py:176-216): statistics, apply, backward.
+ * sums: caller-owned fp32 scratch [2*c], zero on entry and left zero on return (no memset per call). */
+int t2i_bn_stats(const void* x, long long plane_stride, int np, long long rows, int c, float* sums, float* mean,
                  float* rstd, float* var, float eps, void* stream);
 int t2i_bn_apply(const void* x, long long x_ps, const float* mean, const float* rstd, const float* gamma,
                  const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,

@@ -179,7 +179,7 @@ def colsum(src, out):
     out[:src.c] += src.values().reshape(-1, src.c).sum(0)
 
 
-def bn_stats(x, mean, rstd, var, eps):
+def bn_stats(x, sums, mean, rstd, var, eps):
     v = val(x).reshape(-1, x.shape[-1])
     m = v.mean(0)
     s = v.var(0, unbiased=False)

@@ -239,9 +239,12 @@ def test_batch_norm_kernels(K, np_, rows, c):
     res, resg = both(np_, (rows, c), gen)
     gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
     mean, rstd, var = torch.zeros(c), torch.zeros(c), torch.zeros(c)
-    fk.bn_stats(x, mean, rstd, var, 1e-5)
+    fk.bn_stats(x, None, mean, rstd, var, 1e-5)
     mg, rg, vg = [torch.zeros(c, device="cuda") for _ in range(3)]
-    K.bn_stats(xg, mg, rg, vg, 1e-5)
+    scratch = torch.zeros(2 * c, device="cuda")
+    K.bn_stats(xg, scratch, mg, rg, vg, 1e-5)
+    K.bn_stats(xg, scratch, mg, rg, vg, 1e-5)          # the scratch is left zeroed: a second call is identical
+    assert float(scratch.abs().max()) == 0.0
     check_close("bn mean", mg.cpu(), mean, 1e-4, 1.0)
     check_close("bn var", vg.cpu(), var, 1e-4, 1.0)
     check_close("bn rstd", rg.cpu(), rstd, 1e-4, 1.0)

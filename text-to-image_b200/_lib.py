@@ -50,7 +50,7 @@ SIGNATURES = {
     "t2i_conv3x3_c3_tanh_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "t2i_conv3x3_c3_tanh_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "t2i_colsum": [_P, _LL, _I, _LL, _I, _I, _I, _P, _P],
-    "t2i_bn_stats": [_P, _LL, _I, _LL, _I, _P, _P, _P, _F, _P],
+    "t2i_bn_stats": [_P, _LL, _I, _LL, _I, _P, _P, _P, _P, _F, _P],
     "t2i_bn_apply": [_P, _LL, _P, _P, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P],
     "t2i_bn_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _I, _P, _P, _P],
     "t2i_bn_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
@@ -98,9 +98,20 @@ def load():
     return lib
 
 
+TIMELINE = None     # bench.py: when a list, every C-ABI call appends [entry point, start event, end event]
+
+
 def call(name, *args):
     lib = load()
-    rc = getattr(lib, name)(*args)
+    if TIMELINE is not None:
+        import torch
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ev0.record()
+        rc = getattr(lib, name)(*args)
+        ev1.record()
+        TIMELINE.append([name, ev0, ev1])
+    else:
+        rc = getattr(lib, name)(*args)
     if rc != 0:
         raise T2IError("%s failed (%d): %s" % (name, rc, lib.t2i_last_error().decode()))
 

@@ -359,12 +359,16 @@ static int launch_col_reduce(const void* a, long long a_ps, const void* x, long 
 }
 
 // (sum, sumsq) -> (mean, biased var, rstd), in place on the accumulators
-__global__ void bn_finalize_kernel(float* mean, float* var, float* rstd, int c, float inv_rows, float eps) {
+// sums[0:c] = sum x, sums[c:2c] = sum x^2 (accumulated by col_reduce) -> mean, biased var, rstd;
+// the accumulators are re-zeroed here so that the next bn_stats call needs no memset.
+__global__ void bn_finalize_kernel(float* sums, float* mean, float* var, float* rstd, int c, float inv_rows, float eps) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
-    const float m = mean[i] * inv_rows;
-    float v = var[i] * inv_rows - m * m;
+    const float m = sums[i] * inv_rows;
+    float v = sums[c + i] * inv_rows - m * m;
     v = fmaxf(v, 0.f);
+    sums[i] = 0.f;
+    sums[c + i] = 0.f;
     mean[i] = m;
     var[i] = v;
     rstd[i] = rsqrtf(v + eps);
@@ -822,13 +826,11 @@ extern "C" int t2i_colsum(const void* src, long long ps, int np, long long rows,
                           void* stream) {
     return launch_col_reduce<RED_SUM>(src, ps, nullptr, 0, nullptr, nullptr, np, rows, c, pitch, coff, out, nullptr, STREAM);
 }
-extern "C" int t2i_bn_stats(const void* x, long long ps, int np, long long rows, int c, float* mean, float* rstd,
-                            float* var, float eps, void* stream) {
-    cudaMemsetAsync(mean, 0, sizeof(float) * c, STREAM);
-    cudaMemsetAsync(var, 0, sizeof(float) * c, STREAM);
-    int rc = launch_col_reduce<RED_STATS>(x, ps, nullptr, 0, nullptr, nullptr, np, rows, c, c, 0, mean, var, STREAM);
+extern "C" int t2i_bn_stats(const void* x, long long ps, int np, long long rows, int c, float* sums, float* mean,
+                            float* rstd, float* var, float eps, void* stream) {
+    int rc = launch_col_reduce<RED_STATS>(x, ps, nullptr, 0, nullptr, nullptr, np, rows, c, c, 0, sums, sums + c, STREAM);
     if (rc != T2I_OK) return rc;
-    bn_finalize_kernel<<<ceil_div(c, 256), 256, 0, STREAM>>>(mean, var, rstd, c, 1.f / (float)rows, eps);
+    bn_finalize_kernel<<<ceil_div(c, 256), 256, 0, STREAM>>>(sums, mean, var, rstd, c, 1.f / (float)rows, eps);
     return check_launch("bn_finalize");
 }
 extern "C" int t2i_bn_apply(const void* x, long long x_ps, const float* mean, const float* rstd, const float* gamma,

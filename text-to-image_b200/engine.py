@@ -17,6 +17,7 @@ buffers beside them; conversion to/from the reference's TF variable layout happe
 ``set_params_tf`` / ``get_params_tf`` (checkpoint boundary).  ``K`` is the kernel module
 (text-to-image_b200/kernels.py); tests inject their CPU restatement to check this file on CPU.
 """
+import contextlib
 import math
 from collections import OrderedDict
 
@@ -49,7 +50,7 @@ class Layer:
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
-                 f32_dtype=torch.float32, share_from=None, use_graphs=False):
+                 f32_dtype=torch.float32, share_from=None, use_graphs=False, concurrent=True):
         # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
         # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
@@ -64,6 +65,7 @@ class Engine:
         self.g_t = 0
         self.use_graphs = use_graphs and self.dev.type == "cuda"
         self._graphs = {}
+        self.side_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.replayed_launches = 0      # kernels executed through graph replays
         self.captured_launches = 0      # kernels recorded (not executed) during captures
         if share_from is None:
@@ -177,6 +179,7 @@ class Engine:
         self.bn_mean = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_var = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_rstd = [torch.zeros(c, **f32) for c in self.bn_ch]
+        self.bn_sums = [torch.zeros(2 * c, **f32) for c in self.bn_ch]     # zero between bn_stats calls
         for gmm in self.bn_gamma:
             gmm.fill_(1.0)
         self.kt = torch.full((1,), KT_INIT, **f32)
@@ -358,7 +361,7 @@ class Engine:
     def _bn(self, i, x, y, residual=None, relu=False, train=True):
         K = self.K
         if train:
-            K.bn_stats(x, self.bn_mean[i], self.bn_rstd[i], self.bn_var[i], BN_EPS)
+            K.bn_stats(x, self.bn_sums[i], self.bn_mean[i], self.bn_rstd[i], self.bn_var[i], BN_EPS)
             mean, rstd = self.bn_mean[i], self.bn_rstd[i]
         else:   # inference: moving statistics (sampler, model.py:57) -- not on the training path
             mean, rstd = self.bn_mm[i], torch.rsqrt(self.bn_mv[i] + BN_EPS)
@@ -403,7 +406,8 @@ class Engine:
         img = self.d["img"][:B]
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
         K.im2col_k4s2_c3(g["d_u4"], g["d_colg"])
-        K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
+        with self._side():
+            K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
         K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wf, V(rows(g["d_h5"])), algo_scale=0.75, w_kn=True)
 
         def bn_bwd(i, dy, y_post, x_pre, dx, relu):
@@ -417,8 +421,9 @@ class Engine:
         def conv_bwd(l, x, dy, dx, add=None):
             """weight/bias gradient of layer l (input x, output gradient dy) and input gradient -> dx."""
             L = gl[l]
-            K.colsum(V(g[dy]), L.gb)
-            K.wgrad_gemm(L.mode, L.k, V(g[x]), V(g[dy]), L.gw)
+            with self._side():
+                K.colsum(V(g[dy]), L.gb)
+                K.wgrad_gemm(L.mode, L.k, V(g[x]), V(g[dy]), L.gw)
             if dx is not None:
                 mode = {S1: S1, DC: K4, K4: DC}[L.mode]
                 K.conv_gemm(mode, L.k, 1 if L.k == 3 else 0, V(g[dy]), L.Wf, V(g[dx]),
@@ -445,16 +450,18 @@ class Engine:
         flat = lambda t: t.view(np_, B, -1)
         bn_bwd(0, flat(g["d_h0"]), None, flat(g["f0"]), flat(g["d_f0"]), relu=False)
         L = gl["fc0"]
-        K.colsum(V(flat(g["d_f0"])), L.gb)
-        K.wgrad_gemm(S1, 1, V(g["zc"]), V(flat(g["d_f0"])), L.gw)
+        with self._side():
+            K.colsum(V(flat(g["d_f0"])), L.gb)
+            K.wgrad_gemm(S1, 1, V(g["zc"]), V(flat(g["d_f0"])), L.gw)
         K.conv_gemm(S1, 1, 0, V(flat(g["d_f0"])), L.Wf, V(g["d_zc"]), w_kn=True)
         K.ca_bwd(g["ms"], g["d_zc"], g["tn"], g["d_ms"], self.Z, self.kl_coeff / (self.GB * self.ce))
         L = gl["ms"]
         K.colsum(V(g["d_ms"]), L.gb)
         K.wgrad_gemm(S1, 1, V(g["cond"]), V(g["d_ms"]), L.gw)
+        self._join()
 
     # ------------------------------------------------------------------ discriminator
-    def d_forward(self, s0, n, tangent=False):
+    def d_forward(self, s0, n, tangent=False, after=None):
         """models/wgancls/model.py:129-161 on samples [s0, s0+n) of the D buffers.  tangent=True
         propagates a tangent instead: no biases, LeakyReLU replaced by its saved derivative mask,
         written in place over the forward activations of those samples (no logit)."""
@@ -479,19 +486,21 @@ class Engine:
                 kw = dict(bias=L.b, act=K.ACT_LRELU if act else K.ACT_NONE)
             K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, algo_scale=0.75 if l == "h0" else 1.0, **kw)
 
+        done = after if after is not None else (lambda buf: None)   # `buf` holds its final values for this pass
         if not tangent:
             K.im2col_k4s2_c3(d["img"][s0:s0 + n], d["col0"][:, s0 * 1024:(s0 + n) * 1024])
-        cg("h0", R(d["col0"]), R(rows(d["a0"])))                                   # :135
-        cg("h1", V(d["a0"]), V(d["a1"]))                                            # :136
-        cg("h2", V(d["a1"]), V(d["a2"]))                                            # :137
-        cg("h3", V(d["a2"]), V(d["a3"]), act=False)                                 # :138
-        cg("r1", V(d["a3"]), V(d["r1"]))                                            # :142
-        cg("r2", V(d["r1"]), V(d["r2"]))                                            # :143
+        done("col0"); done("cond")
+        cg("h0", R(d["col0"]), R(rows(d["a0"]))); done("a0")                       # :135
+        cg("h1", V(d["a0"]), V(d["a1"])); done("a1")                                # :136
+        cg("h2", V(d["a1"]), V(d["a2"])); done("a2")                                # :137
+        cg("h3", V(d["a2"]), V(d["a3"]), act=False); done("a3")                     # :138
+        cg("r1", V(d["a3"]), V(d["r1"])); done("r1")                                # :142
+        cg("r2", V(d["r1"]), V(d["r2"])); done("r2")                                # :143
         cg("r3", V(d["r2"]), V(d["cat"], coff=0, c=df8), add=V(d["a3"]))            # :144-146
         cg("efc", V(d["cond"]), V(d["e"]))                                          # :150
-        K.embed_tile(d["e"][:, s0:s0 + n], d["cat"][:, s0:s0 + n], df8)             # :153-155
-        cg("h5", V(d["cat"]), V(d["a5"]))                                           # :157
-        cg("h6", V(d["a5"]), V(d["a6"]))                                            # :158
+        K.embed_tile(d["e"][:, s0:s0 + n], d["cat"][:, s0:s0 + n], df8); done("cat")   # :153-155
+        cg("h5", V(d["cat"]), V(d["a5"])); done("a5")                               # :157
+        cg("h6", V(d["a5"]), V(d["a6"])); done("a6")                                # :158
         if not tangent:
             K.dout_fwd(d["a6"][:, s0:s0 + n], dl["out"].w, dl["out"].b, d["logit"][s0:s0 + n])   # :160
 
@@ -526,29 +535,34 @@ class Engine:
                 K.conv_gemm(S1, 1, 0, K.View(d["d_e"], g0, gn), dl["efc"].Wf, K.View(d["d_cond"], 0, gn), **KN)
                 K.from_planes(d["d_cond"], d["g2"])
 
-    def d_wgrad(self, n, n_bias):
-        """Weight gradients over samples [0, n) (activations x input gradients), biases over [0, n_bias)."""
+    # weight-gradient jobs of d_net: name -> (buffer holding the layer input, buffer holding the output gradient)
+    D_WGRAD = OrderedDict([("h0", ("col0", "d_a0")), ("h1", ("a0", "d_a1")), ("h2", ("a1", "d_a2")), ("h3", ("a2", "d_a3")),
+                           ("r1", ("a3", "d_r1")), ("r2", ("r1", "d_r2")), ("r3", ("r2", "d_cat")), ("efc", ("cond", "d_e")),
+                           ("h5", ("cat", "d_a5")), ("h6", ("a5", "d_a6")), ("out", ("a6", None))])
+
+    def d_wgrad_layer(self, l, n, n_bias):
+        """Weight gradient of one d_net layer over samples [0, n): (layer input) x (seeded output gradient)."""
         K, d, dl = self.K, self.d, self.dl
         rows = self._rows
-        df8 = 8 * self.df
+        x, dy = self.D_WGRAD[l]
+        if l == "h0":
+            K.wgrad_gemm(K.CONV_S1, 1, K.View(d["col0"], 0, n * 1024), K.View(rows(d["d_a0"]), 0, n * 1024), dl["h0"].gw,
+                         algo_scale=0.75)
+        elif l == "out":
+            K.dout_bwd_weight(d["a6"][:, :n], d["seed"][:n], dl["out"].gw, dl["out"].gb, n_bias)
+        else:
+            kw = dict(coff=0, c=8 * self.df) if l == "r3" else {}
+            K.wgrad_gemm(dl[l].mode, dl[l].k, K.View(d[x], 0, n), K.View(d[dy], 0, n, **kw), dl[l].gw)
 
-        def V(t, **kw):
-            return K.View(t, 0, n, **kw)
-
-        def Vb(t, **kw):
-            return K.View(t, 0, n_bias, **kw)
-
-        pairs = [("h1", "a0", "d_a1", {}), ("h2", "a1", "d_a2", {}), ("h3", "a2", "d_a3", {}),
-                 ("r1", "a3", "d_r1", {}), ("r2", "r1", "d_r2", {}), ("r3", "r2", "d_cat", dict(coff=0, c=df8)),
-                 ("efc", "cond", "d_e", {}), ("h5", "cat", "d_a5", {}), ("h6", "a5", "d_a6", {})]
-        K.wgrad_gemm(K.CONV_S1, 1, K.View(d["col0"], 0, n * 1024), K.View(rows(d["d_a0"]), 0, n * 1024), dl["h0"].gw,
-                     algo_scale=0.75)
-        K.colsum(K.View(rows(d["d_a0"]), 0, n_bias * 1024), dl["h0"].gb)
-        for l, x, dy, kw in pairs:
-            L = dl[l]
-            K.wgrad_gemm(L.mode, L.k, V(d[x]), V(d[dy], **kw), L.gw)
-            K.colsum(Vb(d[dy], **kw), L.gb)
-        K.dout_bwd_weight(d["a6"][:, :n], d["seed"][:n], dl["out"].gw, dl["out"].gb, n_bias)
+    def d_bias_grads(self, n_bias):
+        """Bias gradients of d_net: sums of the output gradients over samples [0, n_bias)."""
+        K, d, dl = self.K, self.d, self.dl
+        K.colsum(K.View(self._rows(d["d_a0"]), 0, n_bias * 1024), dl["h0"].gb)
+        for l, (x, dy) in self.D_WGRAD.items():
+            if l in ("h0", "out"):
+                continue
+            kw = dict(coff=0, c=8 * self.df) if l == "r3" else {}
+            K.colsum(K.View(d[dy], 0, n_bias, **kw), dl[l].gb)
 
     # ------------------------------------------------------------------ optimizer plumbing
     def _set_lr(self, net, lr, t):
@@ -581,6 +595,23 @@ class Engine:
             self.feed["epsilon"].copy_(epsilon.reshape(-1), non_blocking=True)
         if tn_eps is not None:
             g["tn"].copy_(tn_eps, non_blocking=True)
+
+    @contextlib.contextmanager
+    def _side(self):
+        """Enqueue the enclosed launches on the side stream, ordered after everything enqueued so far on
+        the current stream: weight/bias gradients run beside the critical chain (input gradients, tangent
+        pass) and fill its tail waves.  Captured graphs record the same fork/join dependencies."""
+        if self.side_stream is None:
+            yield
+            return
+        main = torch.cuda.current_stream()
+        self.side_stream.wait_stream(main)
+        with torch.cuda.stream(self.side_stream):
+            yield
+
+    def _join(self):
+        if self.side_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.side_stream)
 
     def _run(self, name, body):
         """Launch a step body: eagerly, or (use_graphs) captured once into a CUDA graph and replayed.
@@ -639,8 +670,16 @@ class Engine:
         # second-order term: tangent (coef * g) through d_net, in place over the x_hat segment
         K.im2col_k4s2_c3(d["gx"], d["col0"][:, 3 * B * 1024:], d["coef"])
         K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])
-        self.d_forward(3 * B, B, tangent=True)
-        self.d_wgrad(S, 3 * B)
+        with self._side():
+            self.d_bias_grads(3 * B)             # first-order only (the JVP does not depend on biases)
+        consumer = {x: l for l, (x, dy) in self.D_WGRAD.items()}
+
+        def wgrad_when_ready(buf):               # layer input final -> its merged weight gradient can start
+            with self._side():
+                self.d_wgrad_layer(consumer[buf], S, 3 * B)
+
+        self.d_forward(3 * B, B, tangent=True, after=wgrad_when_ready)
+        self._join()
 
     def g_step(self, lr_g):
         """sess.run([G_optim, G_loss]) -- models/wgancls/trainer.py:101."""

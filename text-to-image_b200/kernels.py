@@ -188,9 +188,11 @@ def _rows_c(t):
     return t[0].numel() // c, c
 
 
-def bn_stats(x, mean, rstd, var, eps):
+def bn_stats(x, sums, mean, rstd, var, eps):
+    """sums: fp32 scratch [2c], zero on entry, left zero on return."""
     rows, c = _rows_c(x)
-    _lib.call("t2i_bn_stats", _p(x), _ps(x), x.shape[0], rows, c, _f32(mean), _f32(rstd), _f32(var), eps, _stream())
+    _lib.call("t2i_bn_stats", _p(x), _ps(x), x.shape[0], rows, c, _f32(sums), _f32(mean), _f32(rstd), _f32(var), eps,
+              _stream())
 
 
 def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):

@@ -288,7 +288,7 @@ def batch_norm(x, train, init=None, act=None, name=None, eps=1e-5, decay=0.9, df
     pad = lambda v, fill: torch.cat([v, torch.full((cp - c,), fill, device=v.device)]) if cp != c else v
     if train:
         mean, rstd, var = (torch.empty(cp, device=x.device) for _ in range(3))
-        K.bn_stats(xp, mean, rstd, var, eps)
+        K.bn_stats(xp, torch.zeros(2 * cp, device=x.device), mean, rstd, var, eps)
         _S.update_ops.append((mm, mv, mean[:c].clone(), var[:c].clone(), rows, decay))
     else:
         mean, rstd = pad(mm, 0.0), torch.rsqrt(pad(mv, 1.0) + eps)
