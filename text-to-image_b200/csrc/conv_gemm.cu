@@ -7,7 +7,8 @@
 // kernel is a full-line bulk transfer.
 //
 // One persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
-// warps 2..5 = epilogue (each owns the 32 TMEM lanes its warp id % 4 selects).
+// warps 2..9 = epilogue (a warp reaches the 32 TMEM lanes its id % 4 selects; two warps share each
+// lane quarter and split the 64 columns of a sub-tile between them).
 //
 // Replaces the TF ops behind utils/ops.py:61,69,87 of the reference (Conv2D,
 // Conv2DBackpropInput, MatMul + BiasAdd + activation) for every dense contraction on the
@@ -19,7 +20,8 @@ namespace t2i {
 
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;                  // 2 control warps + 8 epilogue warps
+constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSubBytes = kBlockM * 64 * 2;     // one 128-pixel x 64-channel bf16 sub-tile = 16 KB
 constexpr int kMaxStages = 8;
@@ -68,10 +70,12 @@ struct TileCoord {
 };
 __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int tile) {
     TileCoord t;
+    // order: output-channel tile fastest, then phase, then pixel tile -- the four phases of a transposed
+    // conv re-read the same input rows, so they run back to back and hit in L2
     t.ct = tile % prm.tiles_co;
     const int rest = tile / prm.tiles_co;
-    const int mt = rest % prm.tiles_m;
-    t.ph = rest / prm.tiles_m;
+    t.ph = rest % prm.tt.n_phases;
+    const int mt = rest / prm.tt.n_phases;
     t.q0 = (mt % prm.tiles_q) * prm.bq;
     t.p0 = ((mt / prm.tiles_q) % prm.tiles_p) * prm.bp;
     t.n0 = (mt / (prm.tiles_q * prm.tiles_p)) * prm.bn;
@@ -114,7 +118,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], kEpiThreads / 32);
             mbar_init(&aux_full[i], 1);
         }
         fence_barrier_init();
@@ -202,8 +206,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
     } else {
-        // ------------------------------------------------ epilogue warps (128 threads, thread <-> tile row)
+        // ------------------------------------------------ epilogue warps (256 threads: thread <-> tile row x column half)
         const int quarter = warp & 3;
+        const int half = (warp - 2) >> 2;             // which 32 of the 64 columns of a sub-tile
+        const int et = threadIdx.x - 64;              // epilogue thread index
         const int row = quarter * 32 + lane;
         const bool leader = (warp == 2 && lane == 0);
         const bool has_aux = prm.has_add || prm.has_mask;
@@ -260,7 +266,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
             // stage this tile's bias slice (all threads passed the previous sub-tile's second barrier)
             if (prm.bias != nullptr) {
-                for (int i = row; i < BLOCK_N; i += 128) s_bias[i] = (co_base + i < prm.Cout) ? __ldg(prm.bias + co_base + i) : 0.f;
+                for (int i = et; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (co_base + i < prm.Cout) ? __ldg(prm.bias + co_base + i) : 0.f;
             }
             for (int sub = 0; sub < n_sub; ++sub, ++g) {
                 const int buf = (D == 2) ? (g & 1) : 0;
@@ -269,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (D == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                 }
                 if (has_aux) mbar_wait(&aux_full[buf], aux_parity, 500 + buf);
-                named_bar_sync(1, 128);
+                named_bar_sync(1, kEpiThreads);
                 if (sub == 0) {
                     mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
                     tc_fence_after();
@@ -277,8 +283,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 uint8_t* o_hi = s_out + (buf * np) * kSubBytes + row_off;
                 const uint8_t* a_base = s_add + (buf * np) * kSubBytes + row_off;
                 const uint8_t* m_base = s_mask + (buf * np) * kSubBytes + row_off;
-#pragma unroll 1
-                for (int half = 0; half < 2; ++half) {
+                {
                     __syncwarp();
                     uint32_t r[32];
                     tmem_ld_32x32(taddr + sub * 64 + half * 32, r);
@@ -340,7 +345,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     if (lane == 0) mbar_arrive(&tmem_empty[acc]);
                 }
                 fence_proxy_async();      // generic-proxy smem writes -> visible to the TMA store
-                named_bar_sync(2, 128);
+                named_bar_sync(2, kEpiThreads);
                 if (leader) {
                     for (int pl = 0; pl < np; ++pl)
                         tma_store_5d(&prm.out_maps[tc.ph], s_out + (buf * np + pl) * kSubBytes, co_base + sub * 64, tc.q0,
