@@ -132,6 +132,7 @@ def main():
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--only-resident", action="store_true", help="profiling aid: skip e2e / roofline / cpu legs")
+    ap.add_argument("--no-graphs", action="store_true", help="profiling aid: eager launches (ncu launch lists)")
     ap.add_argument("--profile-out", default=None, help="write the per-launch GEMM table (JSON) here")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
@@ -151,7 +152,8 @@ def main():
     from t2i_b200.models.wgancls.model import WGanCls
 
     B = args.batch
-    model = WGanCls(model_cfg(B), precision=args.precision, device=dev, distributed=True if world > 1 else None)
+    model = WGanCls(model_cfg(B), precision=args.precision, device=dev, distributed=True if world > 1 else None,
+                    use_graphs=not args.no_graphs)
     model.initialize(0)                       # reference init, identical on all ranks
     eng = model._train_engine()
     gen = torch.Generator().manual_seed(1234 + rank)

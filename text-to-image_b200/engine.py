@@ -66,6 +66,7 @@ class Engine:
         self.use_graphs = use_graphs and self.dev.type == "cuda"
         self._graphs = {}
         self.side_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
+        self.comm_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.replayed_launches = 0      # kernels executed through graph replays
         self.captured_launches = 0      # kernels recorded (not executed) during captures
         if share_from is None:
@@ -248,24 +249,56 @@ class Engine:
         leaf = "/bias" if l.kind in ("dense", "ms", "fc0") else "/biases"
         return [n + leaf for n in (l.tf_b if isinstance(l.tf_b, tuple) else (l.tf_b,))]
 
-    def set_params_tf(self, p):
-        """Load parameters given in the reference's TF variable layout (oracle / checkpoint names)."""
+    def _views(self, flats):
+        """name -> view for a pair of flat buffers laid out like the parameters ({"d": ..., "g": ...})"""
+        out = {}
+        for net, table in (("d", self.d_table), ("g", self.g_table)):
+            for name, (off, n) in table.items():
+                out[net + "." + name] = flats[net][off:off + n]
+        return out
+
+    def _import(self, p, views, with_moving):
         p = {k: torch.as_tensor(v).detach().to("cpu", self.f32_dtype) for k, v in p.items()}
         for net, layers in (("d", self.dl), ("g", self.gl)):
             for l in layers.values():
-                self.P["%s.%s.w" % (net, l.name)].copy_(self._w_to_kernel(l, p).reshape(-1))
+                views["%s.%s.w" % (net, l.name)].copy_(self._w_to_kernel(l, p).reshape(-1))
                 b = torch.cat([p[n] for n in self._b_names(l)])
                 if l.kind == "fc0":
                     b = self._perm_fc0(b)
-                self.P["%s.%s.b" % (net, l.name)].copy_(b)
+                views["%s.%s.b" % (net, l.name)].copy_(b)
         for i, scope in enumerate(self.bn_tf):
             perm = (lambda v: self._perm_fc0(v)) if i == 0 else (lambda v: v)
-            self.bn_gamma[i].copy_(perm(p[scope + "/gamma"]))
-            self.bn_beta[i].copy_(perm(p[scope + "/beta"]))
-            self.bn_mm[i].copy_(perm(p[scope + "/moving_mean"]))
-            self.bn_mv[i].copy_(perm(p[scope + "/moving_variance"]))
+            views["g.bn%d.gamma" % i].copy_(perm(p[scope + "/gamma"]))
+            views["g.bn%d.beta" % i].copy_(perm(p[scope + "/beta"]))
+            if with_moving:
+                self.bn_mm[i].copy_(perm(p[scope + "/moving_mean"]))
+                self.bn_mv[i].copy_(perm(p[scope + "/moving_variance"]))
+
+    def set_params_tf(self, p):
+        """Load parameters given in the reference's TF variable layout (oracle / checkpoint names)."""
+        self.join_comm()
+        self._import(p, self.P, True)
         self.repack("d")
         self.repack("g")
+
+    def get_adam_tf(self):
+        """Adam slots in TF layout ('m/<variable>', 'v/<variable>') and the two step counters."""
+        self.join_comm()
+        out = OrderedDict()
+        for tag, flats in (("m", self.adam_m), ("v", self.adam_v)):
+            for k, v in self._export(self._views(flats), False).items():
+                out[tag + "/" + k] = v
+        out["d_t"], out["g_t"] = torch.tensor(self.d_t), torch.tensor(self.g_t)
+        return out
+
+    def set_adam_tf(self, state):
+        self.join_comm()
+        for tag, flats in (("m", self.adam_m), ("v", self.adam_v)):
+            sub = {k[2:]: v for k, v in state.items() if k.startswith(tag + "/")}
+            if sub:
+                self._import(sub, self._views(flats), False)
+        self.d_t = int(state.get("d_t", self.d_t))
+        self.g_t = int(state.get("g_t", self.g_t))
 
     def _export(self, flat_views, include_moving):
         out = OrderedDict()
@@ -288,10 +321,12 @@ class Engine:
         return out
 
     def get_params_tf(self):
+        self.join_comm()
         return self._export(self.P, True)
 
     def get_grads_tf(self):
         """Gradients of the last d_step / g_step in TF layout (the other net's entries are stale)."""
+        self.join_comm()
         return self._export(self.G, False)
 
     def repack(self, net):
@@ -469,6 +504,8 @@ class Engine:
         S1, K4 = K.CONV_S1, K.CONV_K4S2
         rows = self._rows
         df8 = 8 * self.df
+        if self.comm_stream is not None and not torch.cuda.is_current_stream_capturing():
+            self.join_comm()    # d_net weights may still be in flight on the communication stream
 
         def V(t, **kw):
             return K.View(t, s0, n, **kw)
@@ -613,6 +650,20 @@ class Engine:
         if self.side_stream is not None:
             torch.cuda.current_stream().wait_stream(self.side_stream)
 
+    @contextlib.contextmanager
+    def _on_comm(self):
+        if self.comm_stream is None:
+            yield
+            return
+        self.comm_stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.comm_stream):
+            yield
+
+    def join_comm(self):
+        """Make the current stream wait for the D update running on the communication stream."""
+        if self.comm_stream is not None:
+            torch.cuda.current_stream().wait_stream(self.comm_stream)
+
     def _run(self, name, body):
         """Launch a step body: eagerly, or (use_graphs) captured once into a CUDA graph and replayed.
         The body enqueues only kernels / memsets / the allreduce on the current stream; everything that
@@ -641,10 +692,14 @@ class Engine:
     def d_step(self, lr_d):
         """sess.run([D_optim, kt_optim, D_loss]) -- models/wgancls/trainer.py:97."""
         self.d_t += 1
+        self.join_comm()                        # a previous D update must have landed (N_CRITIC > 1)
         self._set_lr("d", lr_d, self.d_t)
         self._run("d_a", self._d_body)
-        self._reduce("d")                       # the one collective of the D run, outside the graphs
-        self._run("d_b", self._d_tail)
+        # The collective of the D run, the kt step and Adam go to the communication stream: the G run's
+        # generator forward does not depend on them and overlaps (it joins before its d_net forward).
+        with self._on_comm():
+            self._reduce("d")                   # outside the graphs
+            self._run("d_b", self._d_tail)
 
     def _d_tail(self):
         self.K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, KT_LR)  # :79-91,100
@@ -685,7 +740,9 @@ class Engine:
         """sess.run([G_optim, G_loss]) -- models/wgancls/trainer.py:101."""
         self.g_t += 1
         self._set_lr("g", lr_g, self.g_t)
-        self._run("g_a", self._g_body)
+        self._run("g_a1", self._g_body_fwd)
+        self.join_comm()                        # d_net's weights of this iteration are final from here on
+        self._run("g_a2", self._g_body)
         self._reduce("g")
         self._run("g_b", self._g_tail)
 
@@ -696,12 +753,15 @@ class Engine:
             K.bn_update_moving(self.bn_mm[i], self.bn_mv[i], self.bn_mean[i], self.bn_var[i], g_rows(self, i), BN_DECAY)
         self._adam("g")                                                                  # :103-106
 
-    def _g_body(self):
+    def _g_body_fwd(self):
         K, d, g, B = self.K, self.d, self.g, self.B
         cond = self.feed["cond"]
         self.grad["g"].zero_()
         self.g_forward(g["z"], cond, g["tn"], d["img"][:B], self.sums["g"][1:2])
         K.to_planes(cond, d["cond"][:, :B])
+
+    def _g_body(self):
+        K, d, g, B = self.K, self.d, self.g, self.B
         self.d_forward(0, B)
         K.g_sums(d["logit"], B, self.sums["g"])
         self.d_backward(0, B, d["gseed"], 0, B, False)
@@ -714,6 +774,7 @@ class Engine:
 
     def scalars_dict(self):
         from ._lib import SCALARS
+        self.join_comm()
         vals = self.scalars.detach().cpu().tolist()
         return {n: vals[i] for i, n in enumerate(SCALARS)}
 

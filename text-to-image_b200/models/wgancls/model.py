@@ -176,6 +176,15 @@ class WGanCls(object):
         if "global_step" in variables:
             self.global_step = int(variables["global_step"])
 
+    def get_optimizer_state(self):
+        """Adam slots (TF layout, 'm/<variable>' / 'v/<variable>') and step counters: what a full
+        tf.train.Saver checkpoint holds beside the variables (trainer.py:52)."""
+        return self._train_engine().get_adam_tf()
+
+    def set_optimizer_state(self, state):
+        if state:
+            self._train_engine().set_adam_tf(state)
+
     def initialize(self, seed=0):
         """tf.global_variables_initializer(): the reference initialisation (utils/ops.py:60,68,86:
         He truncated normal; zero biases; gamma 1, beta 0; moving 0/1; kt 0.7 at model.py:77)."""
