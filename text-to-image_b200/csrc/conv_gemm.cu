@@ -108,6 +108,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();   // the next kernel may run its prologue under this grid's tail
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.a_maps[i]);
@@ -131,6 +132,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                // prologue done; from here on global memory of earlier kernels is read
 
     const int tpp = prm.tt.taps_per_phase;
     const int kb_per_tile = prm.n_pass * tpp * prm.k_chunks;
@@ -516,6 +518,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_done[variant] = true;
     }
-    fns[variant]<<<grid, kThreads, smem_bytes, stream>>>(prm);
+    cudaError_t le = launch_pdl(fns[variant], grid, kThreads, smem_bytes, stream, prm);
+    if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");
 }

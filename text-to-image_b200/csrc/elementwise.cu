@@ -79,6 +79,7 @@ static inline int grid_for(long long work_items, int threads, int max_blocks_per
 // fp32 <-> planes
 __global__ void to_planes_kernel(const float* __restrict__ src, bf16* dst, long long ps, int np, long long rows,
                                  int cols, const float* __restrict__ row_scale) {
+    pdl_launch_dependents();
     const long long n8 = rows * cols / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 8;
@@ -94,6 +95,7 @@ __global__ void to_planes_kernel(const float* __restrict__ src, bf16* dst, long 
     }
 }
 __global__ void from_planes_kernel(const bf16* __restrict__ src, long long ps, int np, float* dst, long long n) {
+    pdl_launch_dependents();
     const long long n8 = n / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         float v[8];
@@ -108,6 +110,7 @@ __global__ void from_planes_kernel(const bf16* __restrict__ src, long long ps, i
 // (kh*4 + kw)*3 + c holds img[n, 2p-1+kh, 2q-1+kw, c] (zero outside); columns 48..63 are zero.
 __global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, int n, int h, int w,
                                       const float* __restrict__ sample_scale, bf16* col, long long ps, int np) {
+    pdl_launch_dependents();
     const int hp = h / 2, wq = w / 2;
     const long long rows = (long long)n * hp * wq;
     const long long items = rows * 8;   // one thread per (row, chunk of 8 columns): one 16 B store per plane
@@ -136,6 +139,7 @@ __global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, int n, int 
 // with oh = 2p-1+kh, ow = 2q-1+kw.
 __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps, int np, int n, int h, int w,
                                       const float* __restrict__ bias3, float* img) {
+    pdl_launch_dependents();
     const int hp = h / 2, wq = w / 2;
     const long long pixels = (long long)n * h * w;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
@@ -163,6 +167,7 @@ __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps
 // g_net's last conv: 3 -> 3 channels, 3x3 stride 1 SAME, then tanh.  w is TF HWIO [3][3][3][3].
 __global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                            const float* __restrict__ b, float* y, int n, int h, int wd) {
+    pdl_launch_dependents();
     __shared__ float sw[81 + 3];
     if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
     if (threadIdx.x < 3) sw[81 + threadIdx.x] = b[threadIdx.x];
@@ -199,6 +204,7 @@ __global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const fl
 __global__ void conv3x3_c3_tanh_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                            const float* __restrict__ y, const float* __restrict__ dy, float* dx,
                                            float* dw, float* db, float* dx_sum, int n, int h, int wd) {
+    pdl_launch_dependents();
     __shared__ float sw[81];
     __shared__ float sred[87];
     if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
@@ -284,6 +290,7 @@ template <int MODE>
 __global__ void col_reduce_kernel(const bf16* __restrict__ a, long long a_ps, const bf16* __restrict__ x, long long x_ps,
                                   const float* __restrict__ mean, const float* __restrict__ rstd, int np,
                                   long long rows, int c, int pitch, int coff, int CG, float* out0, float* out1) {
+    pdl_launch_dependents();
     extern __shared__ float sh[];  // [2][RY][CG*8]
     const int RY = blockDim.x / CG;
     const int cgl = threadIdx.x % CG, ry = threadIdx.x / CG;
@@ -362,6 +369,7 @@ static int launch_col_reduce(const void* a, long long a_ps, const void* x, long 
 // sums[0:c] = sum x, sums[c:2c] = sum x^2 (accumulated by col_reduce) -> mean, biased var, rstd;
 // the accumulators are re-zeroed here so that the next bn_stats call needs no memset.
 __global__ void bn_finalize_kernel(float* sums, float* mean, float* var, float* rstd, int c, float inv_rows, float eps) {
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     const float m = sums[i] * inv_rows;
@@ -380,6 +388,7 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, cons
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
                                 const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps, bf16* y,
                                 long long y_ps, int np, long long rows, int c, int relu, int CG) {
+    pdl_launch_dependents();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
     const int ry = threadIdx.x / CG;
@@ -416,6 +425,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
                                     const float* __restrict__ dbeta, bf16* dx, long long dx_ps, int np, long long rows,
                                     int c, float inv_rows, int CG) {
+    pdl_launch_dependents();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
     const int ry = threadIdx.x / CG;
@@ -456,6 +466,7 @@ static inline void rowwise_geometry(long long rows, int c, int threads, int* CG,
 
 __global__ void bn_update_moving_kernel(float* mm, float* mv, const float* mean, const float* var, int c, float decay,
                                         float bessel) {
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     mm[i] = decay * mm[i] + (1.f - decay) * mean[i];
@@ -464,6 +475,7 @@ __global__ void bn_update_moving_kernel(float* mm, float* mv, const float* mean,
 
 __global__ void act_bwd_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ y, long long y_ps,
                                bf16* dst, long long dst_ps, int np, long long n8, float neg) {
+    pdl_launch_dependents();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         float g[8], a[8];
         load8(dy + i * 8, dy_ps, np, g);
@@ -478,6 +490,7 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, long long dy_ps, con
 // d_net embedding replicate / reduce
 __global__ void embed_tile_kernel(const bf16* __restrict__ e, long long e_ps, bf16* cat, long long cat_ps, int np, int s,
                                   int c, int pitch, int coff, int hw) {
+    pdl_launch_dependents();
     const int cg = c / 8;
     const long long items = (long long)s * hw * cg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -491,6 +504,7 @@ __global__ void embed_tile_kernel(const bf16* __restrict__ e, long long e_ps, bf
 }
 __global__ void embed_reduce_kernel(const bf16* __restrict__ dcat, long long dcat_ps, bf16* de, long long de_ps, int np,
                                     int s, int c, int pitch, int coff, int hw) {
+    pdl_launch_dependents();
     const int cg = c / 8;
     const long long items = (long long)s * cg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -511,6 +525,7 @@ __global__ void embed_reduce_kernel(const bf16* __restrict__ dcat, long long dca
 // d_net output layer: per-sample dot product over k = 4*4*C values (NHWC order == TF HWIO order)
 __global__ void dout_fwd_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ w,
                                 const float* __restrict__ b, float* logit, int k) {
+    pdl_launch_dependents();
     __shared__ float sh[32];
     const long long s = blockIdx.x;
     float acc = 0.f;
@@ -526,6 +541,7 @@ __global__ void dout_fwd_kernel(const bf16* __restrict__ a, long long a_ps, int 
 }
 __global__ void dout_bwd_data_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ w,
                                      const float* __restrict__ seed, bf16* da, long long da_ps, int s, int k) {
+    pdl_launch_dependents();
     const int kg = k / 8;
     const long long items = (long long)s * kg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -545,6 +561,7 @@ __global__ void dout_bwd_data_kernel(const bf16* __restrict__ a, long long a_ps,
 // dw[k] += sum_s seed[s] * a[s, k]; blockIdx.y strides over samples
 __global__ void dout_bwd_weight_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ seed,
                                        float* dw, int s, int k) {
+    pdl_launch_dependents();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g * 8 >= k) return;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -559,6 +576,7 @@ __global__ void dout_bwd_weight_kernel(const bf16* __restrict__ a, long long a_p
     for (int j = 0; j < 8; ++j) atomicAdd(dw + g * 8 + j, acc[j]);
 }
 __global__ void seed_sum_kernel(const float* __restrict__ seed, int n, float* out) {
+    pdl_launch_dependents();
     __shared__ float sh[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += seed[i];
@@ -570,6 +588,7 @@ __global__ void seed_sum_kernel(const float* __restrict__ seed, int n, float* ou
 // gradient penalty path
 __global__ void gp_interp_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ eps,
                                  float* xhat, long long n4, int per_sample4) {
+    pdl_launch_dependents();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float e = eps[i / per_sample4];
         const float4 a = reinterpret_cast<const float4*>(g)[i];
@@ -582,6 +601,7 @@ __global__ void gp_interp_kernel(const float* __restrict__ g, const float* __res
 }
 __global__ void gp_penalty_kernel(const float* __restrict__ grad, int per_sample, float weight, float inv_batch,
                                   float* slope, float* coef, float* pen_sum) {
+    pdl_launch_dependents();
     __shared__ float sh[32];
     const long long b = blockIdx.x;
     const float* gp = grad + b * per_sample;
@@ -605,6 +625,7 @@ __global__ void gp_penalty_kernel(const float* __restrict__ grad, int per_sample
 __global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, const float* __restrict__ z,
                               const float* __restrict__ tn, bf16* zc, long long zc_ps, int np, int b, int z_dim, int ce,
                               float* kl_sum) {
+    pdl_launch_dependents();
     __shared__ float sh[32];
     const int width = z_dim + ce;
     float kl = 0.f;
@@ -630,6 +651,7 @@ __global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
 __global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, const bf16* __restrict__ dzc, long long dzc_ps,
                               const float* __restrict__ tn, bf16* dms, long long dms_ps, int np, int b, int z_dim, int ce,
                               float kl_scale) {
+    pdl_launch_dependents();
     const int width = z_dim + ce;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)b * ce;
          i += (long long)gridDim.x * blockDim.x) {
@@ -650,6 +672,7 @@ __global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
 // ------------------------------------------------------------------------------------------
 // scalars
 __global__ void d_seeds_kernel(const float* kt, float* seed, int b, float inv_gb) {
+    pdl_launch_dependents();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 4 * b) return;
     const float k = kt[0];
@@ -658,6 +681,7 @@ __global__ void d_seeds_kernel(const float* kt, float* seed, int b, float inv_gb
     seed[i] = (seg == 0) ? inv_gb : (seg == 1) ? -(1.f + k) * inv_gb : (seg == 2) ? k * inv_gb : 1.f;
 }
 __global__ void d_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
+    pdl_launch_dependents();
     __shared__ float sh[32];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = threadIdx.x; i < b; i += blockDim.x) {
@@ -673,6 +697,7 @@ __global__ void d_sums_kernel(const float* __restrict__ logit, int b, float* sum
     }
 }
 __global__ void d_scalars_kernel(const float* sums, float* kt, float* sc, float inv_gb, float gp_weight, float kt_lr) {
+    pdl_launch_dependents();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float fake = sums[0] * inv_gb, real = sums[1] * inv_gb, mis = sums[2] * inv_gb;
     const float reg = sums[3] * inv_gb, gp = sums[4] * inv_gb, gp2 = sums[5] * inv_gb;
@@ -696,6 +721,7 @@ __global__ void d_scalars_kernel(const float* sums, float* kt, float* sc, float 
     sc[T2I_S_KT] = nk;
 }
 __global__ void g_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
+    pdl_launch_dependents();
     __shared__ float sh[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < b; i += blockDim.x) acc += logit[i];
@@ -703,6 +729,7 @@ __global__ void g_sums_kernel(const float* __restrict__ logit, int b, float* sum
     if (threadIdx.x == 0) atomicAdd(&sums[0], t);
 }
 __global__ void g_scalars_kernel(const float* sums, float* sc, float inv_gb, float inv_gb_ce, float kl_coeff) {
+    pdl_launch_dependents();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float fake = sums[0] * inv_gb;
     const float kl = sums[1] * inv_gb_ce;
@@ -714,6 +741,7 @@ __global__ void g_scalars_kernel(const float* sums, float* sc, float inv_gb, flo
 // weights: fp32 [taps][cout][cin] -> planes fwd (same layout) and bwd ([taps][cin][cout]); 32x32 tiles
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, bf16* fwd, long long fwd_ps, bf16* bwd,
                                    long long bwd_ps, int np) {
+    pdl_launch_dependents();
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -739,6 +767,7 @@ __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int ci
 __global__ void adam_tf_kernel(float* theta, const float* __restrict__ grad, float* m, float* v, long long n,
                                const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float gs, bf16* packed,
                                long long packed_ps, int np) {
+    pdl_launch_dependents();
     const float lr_t = lr_t_dev[0];
     const long long n8 = n / 8;
     const bool use_m = (b1 != 0.f);

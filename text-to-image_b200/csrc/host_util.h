@@ -35,6 +35,24 @@ struct TapTable {
 // Tap tables for the three conv forms (see include/t2i_b200.h); returns 0 or sets the error.
 int build_taps(int mode, int k, int flip, TapTable* t);
 
+// Launch with programmatic stream serialization (PDL): the kernel may begin while its predecessor in
+// the stream drains; it must call pdl_wait() before touching global memory.
+template <typename Params>
+inline cudaError_t launch_pdl(void (*kernel)(const Params), int grid, int block, size_t smem, cudaStream_t stream,
+                              const Params& prm) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(block);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, prm);
+}
+
 inline int floor_pow2(int v) {
     int p = 1;
     while (p * 2 <= v) p *= 2;

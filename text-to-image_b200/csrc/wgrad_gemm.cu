@@ -60,6 +60,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
+    pdl_launch_dependents();
 
     // work decode: split fastest so the CTAs of one output tile run together
     int w = blockIdx.x;
@@ -92,6 +93,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();
 
     if (n_kb > 0) {
         if (warp == 0) {
@@ -230,7 +232,8 @@ static int launch_wgrad(const WgradParams& prm, int grid, cudaStream_t stream) {
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    wgrad_gemm_kernel<MT, BN><<<grid, kWThreads, Cfg::kSmemBytes, stream>>>(prm);
+    cudaError_t le = launch_pdl(wgrad_gemm_kernel<MT, BN>, grid, kWThreads, Cfg::kSmemBytes, stream, prm);
+    if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "wgrad_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("wgrad_gemm_kernel");
 }
 
