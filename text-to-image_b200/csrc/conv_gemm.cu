@@ -6,6 +6,10 @@
 // TMA-loaded (prefetched one or two 64-channel sub-tiles ahead), so every global access of the
 // kernel is a full-line bulk transfer.
 //
+// CTA2 = true pairs two CTAs of a cluster (cta_group::2): a 256-pixel x N tile, each CTA stages its own
+// 128 pixel rows and half of the weight tile, the leader CTA issues M = 256 MMAs, each CTA runs the
+// epilogue of its own 128 accumulator rows.  Operand bytes per MMA cycle drop by a third.
+//
 // One persistent CTA per SM; warp 0 = TMA producer, warp 1 = MMA issuer (+TMEM owner),
 // warps 2..9 = epilogue (a warp reaches the 32 TMEM lanes its id % 4 selects; two warps share each
 // lane quarter and split the 64 columns of a sub-tile between them).
@@ -68,14 +72,16 @@ __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
 struct TileCoord {
     int ct, ph, q0, p0, n0;
 };
-__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int tile) {
+// `tile` indexes (pixel tile [or pixel-tile pair], phase, channel tile); pair > 1 selects this CTA's
+// pixel tile inside the pair by its cluster rank.
+__device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int tile, int pair = 1, int rank = 0) {
     TileCoord t;
     // order: output-channel tile fastest, then phase, then pixel tile -- the four phases of a transposed
     // conv re-read the same input rows, so they run back to back and hit in L2
     t.ct = tile % prm.tiles_co;
     const int rest = tile / prm.tiles_co;
     t.ph = rest % prm.tt.n_phases;
-    const int mt = rest / prm.tt.n_phases;
+    const int mt = (rest / prm.tt.n_phases) * pair + rank;
     t.q0 = (mt % prm.tiles_q) * prm.bq;
     t.p0 = ((mt / prm.tiles_q) % prm.tiles_p) * prm.bp;
     t.n0 = (mt / (prm.tiles_q * prm.tiles_p)) * prm.bn;
@@ -85,10 +91,15 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int 
 // B_KN = false: weights [tap][N][K], K contiguous (K-major B operand, forward layout used forward).
 // B_KN = true : weights [tap][K][N], N contiguous (MN-major B operand): the SAME packed forward
 //               weights serve the input-gradient convolutions, no transposed copy exists.
-template <int BLOCK_N, bool B_KN>
+template <int BLOCK_N, bool B_KN, bool CTA2>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
-    constexpr int kBBytes = BLOCK_N * kBlockK * 2;
+    constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;     // weight rows (output channels) staged by this CTA
+    constexpr int kBBytes = kBRows * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
+    constexpr int kPair = CTA2 ? 2 : 1;
+    const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
+    const int unit0 = blockIdx.x / kPair;                     // first tile (pair) of this CTA (pair)
+    const int unit_stride = gridDim.x / kPair;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int n_stages = prm.n_stages;
@@ -114,22 +125,28 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.a_maps[i]);
         tma_prefetch_desc(&prm.b_map);
         for (int i = 0; i < n_stages; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], kPair);     // one arrival per producer of the pair (used in the leader)
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kEpiThreads / 32);
+            mbar_init(&tmem_empty[i], kPair * (kEpiThreads / 32));   // epilogue warps of both CTAs (leader's copy)
             mbar_init(&aux_full[i], 1);
         }
         fence_barrier_init();
     }
+    if (CTA2) cluster_sync_all();               // peer barriers exist before anything can target them
     if (warp == 1) {
-        tmem_alloc(tmem_slot, 2 * BLOCK_N);
-        tmem_relinquish();
+        if (CTA2) {
+            tmem_alloc_2sm(tmem_slot, 2 * BLOCK_N);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, 2 * BLOCK_N);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();                // prologue done; from here on global memory of earlier kernels is read
@@ -142,8 +159,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         if (elect_one()) {
             int stage = 0;
             uint32_t phase = 0;
-            for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x) {
-                const TileCoord tc = decode_tile(prm, tile);
+            for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride) {
+                const TileCoord tc = decode_tile(prm, tile, kPair, rank);
                 for (int pass = 0; pass < prm.n_pass; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;  // A plane: hi, lo, hi
                     const int pb = (pass == 2) ? 1 : 0;  // B plane: hi, hi, lo
@@ -151,18 +168,34 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         const Tap tap = prm.tt.taps[tc.ph * tpp + t];
                         for (int kc = 0; kc < prm.k_chunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-                            mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                             uint8_t* sa = smem + stage * kStageBytes;
-                            tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, tc.q0 + tap.dq,
-                                        tc.p0 + tap.dp, tc.n0, pa);
-                            if (!B_KN) {
-                                tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, tc.ct * BLOCK_N,
-                                            tap.wtap, pb);
-                            } else {
+                            const int brow = tc.ct * BLOCK_N + rank * kBRows;   // this CTA's slice of the weight tile
+                            if (!CTA2) {
+                                mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
+                                tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, tc.q0 + tap.dq,
+                                            tc.p0 + tap.dp, tc.n0, pa);
+                                if (!B_KN) {
+                                    tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, brow, tap.wtap, pb);
+                                } else {
 #pragma unroll
-                                for (int a = 0; a < BLOCK_N / 64; ++a)   // 64-channel atoms of [64 K rows x 128 B]
-                                    tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes + a * 8192,
-                                                tc.ct * BLOCK_N + a * 64, kc * kBlockK, tap.wtap, pb);
+                                    for (int a = 0; a < kBRows / 64; ++a)   // 64-channel atoms of [64 K rows x 128 B]
+                                        tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes + a * 8192, brow + a * 64,
+                                                    kc * kBlockK, tap.wtap, pb);
+                                }
+                            } else {
+                                // both producers arrive on the LEADER's barrier; it expects the bytes of both CTAs
+                                if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * kStageBytes);
+                                else mbar_arrive_cluster(&full_bar[stage], 0);
+                                tma_load_5d_2sm(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, tc.q0 + tap.dq,
+                                                tc.p0 + tap.dp, tc.n0, pa);
+                                if (!B_KN) {
+                                    tma_load_4d_2sm(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, brow, tap.wtap, pb);
+                                } else {
+#pragma unroll
+                                    for (int a = 0; a < kBRows / 64; ++a)
+                                        tma_load_4d_2sm(&prm.b_map, &full_bar[stage], sa + kABytes + a * 8192, brow + a * 64,
+                                                        kc * kBlockK, tap.wtap, pb);
+                                }
                             }
                             if (++stage == n_stages) {
                                 stage = 0;
@@ -175,12 +208,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         }
     } else if (warp == 1) {
         // ------------------------------------------------ MMA issuer (one elected lane)
-        if (elect_one()) {
-            constexpr uint32_t idesc = make_idesc_bf16(kBlockM, BLOCK_N, 0, B_KN ? 1 : 0);
+        if (rank == 0 && elect_one()) {         // in a CTA pair only the leader issues
+            constexpr uint32_t idesc = make_idesc_bf16(kPair * kBlockM, BLOCK_N, 0, B_KN ? 1 : 0);
             int stage = 0;
             uint32_t phase = 0;
             int it = 0;
-            for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
+            for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride, ++it) {
                 const int acc = it & 1;
                 const uint32_t acc_phase = (it >> 1) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 300 + acc);
@@ -196,10 +229,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     const uint64_t db = B_KN ? make_sw128_desc(sa + kABytes, 8192, 1024) : make_sw128_desc(sa + kABytes, 0, 1024);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        umma_bf16(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
+                        if (CTA2) umma_bf16_2sm(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
+                        else umma_bf16(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);
+                    if (CTA2) {     // free the stage / publish the accumulator in BOTH CTAs
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kb == kb_per_tile - 1) umma_commit_2sm(&tmem_full[acc]);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);
+                    }
                     if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -222,7 +261,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
         // aux tiles are prefetched D sub-tiles ahead along the sequence (tile, sub) this CTA will process
         auto issue_aux = [&](int tile, int sub, int buf) {
-            const TileCoord tc = decode_tile(prm, tile);
+            const TileCoord tc = decode_tile(prm, tile, kPair, rank);
             const int c0 = tc.ct * BLOCK_N + sub * 64;
             mbar_arrive_expect_tx(&aux_full[buf], aux_bytes);
             for (int pl = 0; pl < np; ++pl) {
@@ -241,11 +280,11 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             return (rem + 63) / 64;
         };
         // prefetch cursor (tile, sub) runs D elements ahead of the compute cursor
-        int pf_tile = blockIdx.x, pf_sub = 0;
+        int pf_tile = unit0, pf_sub = 0;
         auto pf_advance = [&]() {
             if (++pf_sub >= subs_of(pf_tile)) {
                 pf_sub = 0;
-                pf_tile += gridDim.x;
+                pf_tile += unit_stride;
             }
         };
         if (has_aux && leader) {
@@ -259,10 +298,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 
         int g = 0;   // running index of 64-channel sub-tiles processed by this CTA
         int it = 0;
-        for (int tile = blockIdx.x; tile < prm.total_tiles; tile += gridDim.x, ++it) {
+        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride, ++it) {
             const int acc = it & 1;
             const uint32_t acc_phase = (it >> 1) & 1;
-            const TileCoord tc = decode_tile(prm, tile);
+            const TileCoord tc = decode_tile(prm, tile, kPair, rank);
             const int co_base = tc.ct * BLOCK_N;
             const int n_sub = subs_of(tile);
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -344,7 +383,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (sub == n_sub - 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
-                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    if (lane == 0) {
+                        if (CTA2 && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                        else mbar_arrive(&tmem_empty[acc]);
+                    }
                 }
                 fence_proxy_async();      // generic-proxy smem writes -> visible to the TMA store
                 named_bar_sync(2, kEpiThreads);
@@ -364,11 +406,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();   // the peer may still be read by the leader's MMAs
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BLOCK_N);
+        if (CTA2) tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
+        else tmem_dealloc(tmem_base, 2 * BLOCK_N);
     }
 }
 
@@ -461,13 +504,19 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
             return fail(T2I_ERR_BAD_ARG, "epilogue tensor [%d,%d,%d,%d] does not cover the output [%d,%d,%d,%d]", a->n, a->h,
                         a->w, a->c, y.n, y.h, y.w, y.c);
     const int sms = num_sms();
+    // CTA pairs (cta_group::2, 256-pixel tiles) whenever there are at least two pixel tiles
+    static const bool allow_cta2 = [] { const char* e = getenv("T2I_CONV_CTA2"); return !(e && e[0] == '0'); }();
+    const bool cta2 = allow_cta2 && prm.tiles_m >= 2;
+    const int units_m = cta2 ? ceil_div(prm.tiles_m, 2) : prm.tiles_m;     // schedulable pixel tiles (pairs)
+    const int workers = cta2 ? sms / 2 : sms;                              // CTAs or CTA pairs
     int block_n = 128;
-    if (y.c > 128 && (long long)prm.tt.n_phases * prm.tiles_m * ceil_div(y.c, 256) >= sms) block_n = 256;
+    if (y.c > 128 && (long long)prm.tt.n_phases * units_m * ceil_div(y.c, 256) >= workers) block_n = 256;
     prm.tiles_co = ceil_div(y.c, block_n);
-    prm.total_tiles = prm.tt.n_phases * prm.tiles_m * prm.tiles_co;
+    prm.total_tiles = prm.tt.n_phases * units_m * prm.tiles_co;
     // shared memory plan: epilogue staging first, the mainloop pipeline takes what is left
     prm.epi_depth = (d->np == 1) ? 2 : 1;
-    const int stage_bytes = kABytes + block_n * kBlockK * 2;
+    const int b_rows = cta2 ? block_n / 2 : block_n;                       // weight rows staged per CTA
+    const int stage_bytes = kABytes + b_rows * kBlockK * 2;
     const int epi_bytes = (1 + prm.has_add + prm.has_mask) * prm.epi_depth * d->np * kSubBytes;
     const int tail_bytes = block_n * 4 + 256;   // bias slice + barriers
     int stages = (kSmemBudget - epi_bytes - tail_bytes) / stage_bytes;
@@ -499,7 +548,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         const uint64_t plane_bytes = (d->np == 2) ? (uint64_t)d->w_plane_stride * e : (uint64_t)taps * d->w_rows * d->w_cols * e;
         const uint64_t dims[4] = {(uint64_t)d->w_cols, (uint64_t)d->w_rows, (uint64_t)taps, (uint64_t)d->np};
         const uint64_t str[3] = {(uint64_t)d->w_cols * e, (uint64_t)d->w_cols * d->w_rows * e, plane_bytes};
-        const uint32_t box[4] = {64, kn ? 64u : (uint32_t)block_n, 1, 1};
+        const uint32_t box[4] = {64, kn ? 64u : (uint32_t)b_rows, 1, 1};
         rc = encode_tmap_bf16(&prm.b_map, d->w, 4, dims, str, box);
         if (rc != T2I_OK) return rc;
     }
@@ -507,18 +556,20 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     prm.act = d->act;
     prm.mask_kind = d->mask_kind;
 
-    const int grid = prm.total_tiles < sms ? prm.total_tiles : sms;
+    const int grid = (prm.total_tiles < workers ? prm.total_tiles : workers) * (cta2 ? 2 : 1);
     typedef void (*KernelFn)(const ConvGemmParams);
-    static bool attr_done[4] = {false, false, false, false};
-    const int variant = (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
-    const KernelFn fns[4] = {conv_gemm_kernel<128, false>, conv_gemm_kernel<128, true>, conv_gemm_kernel<256, false>,
-                             conv_gemm_kernel<256, true>};
+    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
+    const int variant = (cta2 ? 4 : 0) + (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
+    const KernelFn fns[8] = {conv_gemm_kernel<128, false, false>, conv_gemm_kernel<128, true, false>,
+                             conv_gemm_kernel<256, false, false>, conv_gemm_kernel<256, true, false>,
+                             conv_gemm_kernel<128, false, true>,  conv_gemm_kernel<128, true, true>,
+                             conv_gemm_kernel<256, false, true>,  conv_gemm_kernel<256, true, true>};
     if (!attr_done[variant]) {
         cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_done[variant] = true;
     }
-    cudaError_t le = launch_pdl(fns[variant], grid, kThreads, smem_bytes, stream, prm);
+    cudaError_t le = launch_pdl(fns[variant], grid, kThreads, smem_bytes, stream, prm, cta2 ? 2 : 1);
     if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "conv_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("conv_gemm_kernel");
 }

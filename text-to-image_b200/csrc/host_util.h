@@ -39,17 +39,25 @@ int build_taps(int mode, int k, int flip, TapTable* t);
 // the stream drains; it must call pdl_wait() before touching global memory.
 template <typename Params>
 inline cudaError_t launch_pdl(void (*kernel)(const Params), int grid, int block, size_t smem, cudaStream_t stream,
-                              const Params& prm) {
+                              const Params& prm, int cluster = 1) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(block);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = stream;
-    cudaLaunchAttribute attr[1];
+    cudaLaunchAttribute attr[2];
     attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
     attr[0].val.programmaticStreamSerializationAllowed = 1;
+    int n = 1;
+    if (cluster > 1) {   // thread-block cluster (CTA pair on one TPC) for cta_group::2 kernels
+        attr[1].id = cudaLaunchAttributeClusterDimension;
+        attr[1].val.clusterDim.x = cluster;
+        attr[1].val.clusterDim.y = 1;
+        attr[1].val.clusterDim.z = 1;
+        n = 2;
+    }
     cfg.attrs = attr;
-    cfg.numAttrs = 1;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, prm);
 }
 
