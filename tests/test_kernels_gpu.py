@@ -149,6 +149,10 @@ WGRAD_CASES = [
     ("k4s2_8", fk.CONV_K4S2, 4, 16, 8, 8, 64, 256),
     ("deconv_4", fk.DECONV_K4S2, 4, 16, 4, 4, 128, 64),
     ("deconv_16", fk.DECONV_K4S2, 4, 2, 16, 16, 256, 128),
+    # >= 256 channels on both sides: the CTA-pair (cta_group::2) tile
+    ("c3_pair", fk.CONV_S1, 3, 8, 4, 4, 256, 512),
+    ("k4s2_pair", fk.CONV_K4S2, 4, 4, 16, 16, 256, 256),
+    ("deconv_pair", fk.DECONV_K4S2, 4, 4, 4, 4, 512, 320),
 ]
 
 

@@ -21,11 +21,14 @@ constexpr int kWK = 64;                       // pixels per K block
 constexpr int kWAtomBytes = kWK * 128;        // 64 pixels x 64 channels bf16 = 8 KB
 constexpr int kWThreads = 192;
 
-template <int MT, int BN>
+// CTA2: a CTA pair (cta_group::2) computes 256 output channels x BN input channels; each CTA stages its
+// own 128 output channels of dy and HALF of the x tile, and reduces its own 128 accumulator rows.
+template <int MT, int BN, bool CTA2 = false>
 struct WgradCfg {
-    static constexpr int kM = MT * 128;                       // co per tile
+    static constexpr int kM = MT * 128;                       // co per CTA
+    static constexpr int kBCols = CTA2 ? BN / 2 : BN;         // ci staged by this CTA
     static constexpr int kABytes = (kM / 64) * kWAtomBytes;
-    static constexpr int kBBytes = (BN / 64) * kWAtomBytes;
+    static constexpr int kBBytes = (kBCols / 64) * kWAtomBytes;
     static constexpr int kStageBytes = kABytes + kBBytes;
     static constexpr int kStages = (kStageBytes <= 32768) ? 6 : 4;
     static constexpr int kBarOffset = kStages * kStageBytes;
@@ -47,9 +50,12 @@ struct alignas(64) WgradParams {
     float* dw;
 };
 
-template <int MT, int BN>
+template <int MT, int BN, bool CTA2>
 __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams prm) {
-    using Cfg = WgradCfg<MT, BN>;
+    using Cfg = WgradCfg<MT, BN, CTA2>;
+    static_assert(!CTA2 || MT == 1, "the CTA-pair variant uses one accumulator per CTA");
+    constexpr int kPair = CTA2 ? 2 : 1;
+    const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int kStages = Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -63,7 +69,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     pdl_launch_dependents();
 
     // work decode: split fastest so the CTAs of one output tile run together
-    int w = blockIdx.x;
+    int w = blockIdx.x / kPair;
     const int split = w % prm.splits; w /= prm.splits;
     const int cit = w % prm.tiles_ci; w /= prm.tiles_ci;
     const int cot = w % prm.tiles_co; w /= prm.tiles_co;
@@ -79,21 +85,29 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
         tma_prefetch_desc(&prm.x_maps[tap.map]);
         tma_prefetch_desc(&prm.dy_maps[prm.tt.n_phases > 1 ? phase_idx : 0]);
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full_bar[i], 1);
+            mbar_init(&full_bar[i], kPair);
             mbar_init(&empty_bar[i], 1);
         }
         mbar_init(tmem_full, 1);
         fence_barrier_init();
     }
+    if (CTA2) cluster_sync_all();
     if (warp == 1) {
-        tmem_alloc(tmem_slot, Cfg::kTmemCols);
-        tmem_relinquish();
+        if (CTA2) {
+            tmem_alloc_2sm(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish_2sm();
+        } else {
+            tmem_alloc(tmem_slot, Cfg::kTmemCols);
+            tmem_relinquish();
+        }
     }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
+    const int co_cta = (cot * kPair + rank) * Cfg::kM;        // first output channel of this CTA
+    const int ci_cta = cit * BN + rank * Cfg::kBCols;         // first input channel staged by this CTA
 
     if (n_kb > 0) {
         if (warp == 0) {
@@ -111,15 +125,27 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                         const int tn = kb / (prm.tiles_q * prm.tiles_p);
                         const int q0 = tq * prm.bq, p0 = tp * prm.bp, n0 = tn * prm.bn;
                         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
-                        mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
+                        if (!CTA2) {
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
 #pragma unroll
-                        for (int a = 0; a < Cfg::kM / 64; ++a)
-                            tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, cot * Cfg::kM + a * 64, q0, p0, n0, pa);
+                            for (int a = 0; a < Cfg::kM / 64; ++a)
+                                tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, co_cta + a * 64, q0, p0, n0, pa);
 #pragma unroll
-                        for (int b = 0; b < BN / 64; ++b)
-                            tma_load_5d(x_map, &full_bar[stage], sa + Cfg::kABytes + b * kWAtomBytes, cit * BN + b * 64,
-                                        q0 + tap.dq, p0 + tap.dp, n0, pb);
+                            for (int b = 0; b < Cfg::kBCols / 64; ++b)
+                                tma_load_5d(x_map, &full_bar[stage], sa + Cfg::kABytes + b * kWAtomBytes, ci_cta + b * 64,
+                                            q0 + tap.dq, p0 + tap.dp, n0, pb);
+                        } else {
+                            if (rank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2 * Cfg::kStageBytes);
+                            else mbar_arrive_cluster(&full_bar[stage], 0);
+#pragma unroll
+                            for (int a = 0; a < Cfg::kM / 64; ++a)
+                                tma_load_5d_2sm(dy_map, &full_bar[stage], sa + a * kWAtomBytes, co_cta + a * 64, q0, p0, n0, pa);
+#pragma unroll
+                            for (int b = 0; b < Cfg::kBCols / 64; ++b)
+                                tma_load_5d_2sm(x_map, &full_bar[stage], sa + Cfg::kABytes + b * kWAtomBytes, ci_cta + b * 64,
+                                                q0 + tap.dq, p0 + tap.dp, n0, pb);
+                        }
                         if (++stage == kStages) {
                             stage = 0;
                             phase ^= 1;
@@ -128,8 +154,8 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                 }
             }
         } else if (warp == 1) {
-            if (elect_one()) {
-                constexpr uint32_t idesc = make_idesc_bf16(128, BN, 1, 1);
+            if (rank == 0 && elect_one()) {
+                constexpr uint32_t idesc = make_idesc_bf16(kPair * 128, BN, 1, 1);
                 int stage = 0;
                 uint32_t phase = 0;
                 for (int kb = 0; kb < n_kb; ++kb) {
@@ -143,11 +169,17 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             const uint64_t da = make_sw128_desc(sa + mt * 2 * kWAtomBytes + k * 2048, kWAtomBytes, 1024);
-                            umma_bf16(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0);
+                            if (CTA2) umma_bf16_2sm(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0);
+                            else umma_bf16(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0);
                         }
                     }
-                    umma_commit(&empty_bar[stage]);
-                    if (kb == n_kb - 1) umma_commit(tmem_full);
+                    if (CTA2) {
+                        umma_commit_2sm(&empty_bar[stage]);
+                        if (kb == n_kb - 1) umma_commit_2sm(tmem_full);
+                    } else {
+                        umma_commit(&empty_bar[stage]);
+                        if (kb == n_kb - 1) umma_commit(tmem_full);
+                    }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
@@ -160,7 +192,7 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
             tc_fence_after();
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
-                const int co = cot * Cfg::kM + mt * 128 + quarter * 32 + lane;
+                const int co = co_cta + mt * 128 + quarter * 32 + lane;
                 const uint32_t taddr = tmem_base + mt * BN + (static_cast<uint32_t>(quarter * 32) << 16);
                 float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
 #pragma unroll 1
@@ -188,11 +220,12 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        tmem_dealloc(tmem_base, Cfg::kTmemCols);
+        if (CTA2) tmem_dealloc_2sm(tmem_base, Cfg::kTmemCols);
+        else tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
 }
 
@@ -222,17 +255,18 @@ static int make_maps(const t2i_act& t, bool parity, int np, int bq, int bp, int 
     return T2I_OK;
 }
 
-template <int MT, int BN>
+template <int MT, int BN, bool CTA2>
 static int launch_wgrad(const WgradParams& prm, int grid, cudaStream_t stream) {
-    using Cfg = WgradCfg<MT, BN>;
+    using Cfg = WgradCfg<MT, BN, CTA2>;
     static bool attr_done = false;
     if (!attr_done) {
-        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<MT, BN>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<MT, BN, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              Cfg::kSmemBytes);
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
         attr_done = true;
     }
-    cudaError_t le = launch_pdl(wgrad_gemm_kernel<MT, BN>, grid, kWThreads, Cfg::kSmemBytes, stream, prm);
+    cudaError_t le = launch_pdl(wgrad_gemm_kernel<MT, BN, CTA2>, grid * (CTA2 ? 2 : 1), kWThreads, Cfg::kSmemBytes, stream,
+                                prm, CTA2 ? 2 : 1);
     if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "wgrad_gemm_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("wgrad_gemm_kernel");
 }
@@ -279,6 +313,9 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     int mt = 1, bnn = 128;
     if (x.c >= 256) bnn = 256;
     else if (dy.c >= 256) mt = 2;
+    static const bool allow_cta2 = [] { const char* e = getenv("T2I_WGRAD_CTA2"); return !(e && e[0] == '0'); }();
+    const bool cta2 = allow_cta2 && bnn == 256 && dy.c >= 256;      // CTA pair: 256 co x 256 ci
+    if (cta2) mt = 2;                                               // tile covers 256 output channels (128 per CTA)
     prm.tiles_co = ceil_div(dy.c, mt * 128);
     prm.tiles_ci = ceil_div(x.c, bnn);
     prm.jobs = prm.tt.n_phases * prm.tt.taps_per_phase;
@@ -286,7 +323,7 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     const int tiles = prm.jobs * prm.tiles_co * prm.tiles_ci;
     int splits = d->split_k;
     if (splits <= 0) {
-        splits = ceil_div(2 * num_sms(), tiles);
+        splits = ceil_div((cta2 ? 1 : 2) * num_sms(), tiles);   // ~2 CTAs per SM in total (a pair counts twice)
         const int max_splits = prm.k_blocks / 8 > 0 ? prm.k_blocks / 8 : 1;  // >= 8 K blocks per CTA
         if (splits > max_splits) splits = max_splits;
         if (splits < 1) splits = 1;
@@ -302,7 +339,8 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     if (rc != T2I_OK) return rc;
 
     const int grid = tiles * prm.splits;
-    if (bnn == 256) return launch_wgrad<1, 256>(prm, grid, stream);
-    if (mt == 2) return launch_wgrad<2, 128>(prm, grid, stream);
-    return launch_wgrad<1, 128>(prm, grid, stream);
+    if (cta2) return launch_wgrad<1, 256, true>(prm, grid, stream);
+    if (bnn == 256) return launch_wgrad<1, 256, false>(prm, grid, stream);
+    if (mt == 2) return launch_wgrad<2, 128, false>(prm, grid, stream);
+    return launch_wgrad<1, 128, false>(prm, grid, stream);
 }
