@@ -67,6 +67,7 @@ class Engine:
         self._graphs = {}
         self.side_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.comm_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
+        self.copy_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.replayed_launches = 0      # kernels executed through graph replays
         self.captured_launches = 0      # kernels recorded (not executed) during captures
         if share_from is None:
@@ -620,10 +621,17 @@ class Engine:
     def load_feed(self, x=None, x_mismatch=None, cond=None, z=None, epsilon=None, tn_eps=None):
         """Stage inputs (fp32 host or device tensors) into the engine's device buffers."""
         B, d, g = self.B, self.d, self.g
-        if x is not None:
-            d["img"][B:2 * B].copy_(x, non_blocking=True)
-        if x_mismatch is not None:
-            d["img"][2 * B:3 * B].copy_(x_mismatch, non_blocking=True)
+        if x is not None or x_mismatch is not None:
+            # The two image batches are 90 % of the feed bytes and are first needed AFTER the generator
+            # forward of the D run: copy them on their own stream so that the transfer hides under it.
+            cs = self.copy_stream if (self.copy_stream is not None and not torch.as_tensor(x if x is not None else x_mismatch).is_cuda) else None
+            if cs is not None:
+                cs.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(cs) if cs is not None else contextlib.nullcontext()):
+                if x is not None:
+                    d["img"][B:2 * B].copy_(x, non_blocking=True)
+                if x_mismatch is not None:
+                    d["img"][2 * B:3 * B].copy_(x_mismatch, non_blocking=True)
         if cond is not None:
             self.feed["cond"].copy_(cond, non_blocking=True)
         if z is not None:
@@ -694,6 +702,9 @@ class Engine:
         self.d_t += 1
         self.join_comm()                        # a previous D update must have landed (N_CRITIC > 1)
         self._set_lr("d", lr_d, self.d_t)
+        self._run("d_a1", self._d_body_gen)
+        if self.copy_stream is not None:        # the real / mismatching images arrive on the copy stream
+            torch.cuda.current_stream().wait_stream(self.copy_stream)
         self._run("d_a", self._d_body)
         # The collective of the D run, the kt step and Adam go to the communication stream: the G run's
         # generator forward does not depend on them and overlaps (it joins before its d_net forward).
@@ -705,13 +716,16 @@ class Engine:
         self.K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, KT_LR)  # :79-91,100
         self._adam("d")                                                                    # :94-97
 
+    def _d_body_gen(self):
+        g = self.g
+        self.grad["d"].zero_()
+        g["kl_scratch"].zero_()
+        self.g_forward(g["z"], self.feed["cond"], g["tn"], self.d["img"][:self.B], g["kl_scratch"])   # model.py:48
+
     def _d_body(self):
         K, d, g, B = self.K, self.d, self.g, self.B
         S = 4 * B
         cond = self.feed["cond"]
-        self.grad["d"].zero_()
-        g["kl_scratch"].zero_()
-        self.g_forward(g["z"], cond, g["tn"], d["img"][:B], g["kl_scratch"])              # model.py:48
         K.gp_interp(d["img"][:B], d["img"][B:2 * B], self.feed["epsilon"], d["img"][3 * B:])   # model.py:53
         for seg in range(4):
             K.to_planes(cond, d["cond"][:, seg * B:(seg + 1) * B])                        # cond_inp = cond (:54)
