@@ -323,10 +323,20 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     const int tiles = prm.jobs * prm.tiles_co * prm.tiles_ci;
     int splits = d->split_k;
     if (splits <= 0) {
-        splits = ceil_div((cta2 ? 1 : 2) * num_sms(), tiles);   // ~2 CTAs per SM in total (a pair counts twice)
+        // Cost model: the launch runs in ceil(tiles * s / workers) waves; one wave costs the K blocks of a split
+        // plus a fixed prologue/epilogue (about 10 K-block times).  Pick the split count with the least total.
+        const int workers = cta2 ? num_sms() / 2 : num_sms();
         const int max_splits = prm.k_blocks / 8 > 0 ? prm.k_blocks / 8 : 1;  // >= 8 K blocks per CTA
-        if (splits > max_splits) splits = max_splits;
-        if (splits < 1) splits = 1;
+        long long best = -1;
+        splits = 1;
+        for (int sct = 1; sct <= max_splits && sct <= 64; ++sct) {
+            const long long waves = ceil_div(tiles * sct, workers);
+            const long long cost = waves * (ceil_div(prm.k_blocks, sct) * prm.n_pass + 10);
+            if (best < 0 || cost < best) {
+                best = cost;
+                splits = sct;
+            }
+        }
     }
     if (splits > prm.k_blocks) splits = prm.k_blocks;
     prm.kb_per_split = ceil_div(prm.k_blocks, splits);
