@@ -305,6 +305,7 @@ __global__ void col_reduce_kernel(const bf16* __restrict__ a, long long a_ps, co
 #pragma unroll
             for (int j = 0; j < 8; ++j) { mu[j] = mean[ch + j]; rs[j] = rstd[ch + j]; }
         }
+#pragma unroll 4
         for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
             float v[8];
             load8(a + r * pitch + coff + ch, a_ps, np, v);
@@ -386,8 +387,8 @@ __global__ void bn_finalize_kernel(float* sums, float* mean, float* var, float* 
 // threadIdx.x % CG walks the channel groups so that a warp reads contiguous 16 B pieces of a row.
 __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, const float* __restrict__ mean,
                                 const float* __restrict__ rstd, const float* __restrict__ gamma,
-                                const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps, bf16* y,
-                                long long y_ps, int np, long long rows, int c, int relu, int CG) {
+                                const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
+                                bf16* __restrict__ y, long long y_ps, int np, long long rows, int c, int relu, int CG) {
     pdl_launch_dependents();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
@@ -399,6 +400,7 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, cons
         sc[j] = rstd[ch + j] * gamma[ch + j];
         sh[j] = beta[ch + j] - mean[ch + j] * sc[j];
     }
+#pragma unroll 4
     for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
         const long long e = r * c + ch;
         float v[8];
@@ -423,8 +425,8 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, cons
 __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ x,
                                     long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ dgamma,
-                                    const float* __restrict__ dbeta, bf16* dx, long long dx_ps, int np, long long rows,
-                                    int c, float inv_rows, int CG) {
+                                    const float* __restrict__ dbeta, bf16* __restrict__ dx, long long dx_ps, int np,
+                                    long long rows, int c, float inv_rows, int CG) {
     pdl_launch_dependents();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
@@ -439,6 +441,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
         b0[j] = dbeta[ch + j] * inv_rows;
         b1[j] = dgamma[ch + j] * inv_rows;
     }
+#pragma unroll 4
     for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
         const long long e = r * c + ch;
         float g[8], xv[8];
