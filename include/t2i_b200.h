@@ -68,6 +68,18 @@ typedef struct {
     t2i_act add;       /* ptr NULL = none; same pixel grid as y */
     t2i_act mask;      /* ptr NULL = none; same pixel grid as y */
     int act, mask_kind;
+    /* Optional per-channel statistics of the output values v (fp32, after act / mask, before the bf16
+     * rounding), accumulated (+=, fp32 atomics; the caller zeroes) over the samples [0, stat_n) and the
+     * output channels [0, stat_c) (0 = all):  stat_sum[c] += sum v;  stat_sq[c] += sum v^2;
+     * stat_dot[c] += sum v * stat_x (a tensor on the output grid).  They fuse what would be separate passes
+     * over y: BatchNorm batch statistics (utils/ops.py:20-29) of a conv output, bias gradients (sum of an
+     * input-gradient over pixels) and the two reductions of the BatchNorm backward.  stat_sq and stat_dot
+     * are mutually exclusive; any pointer may be NULL. */
+    float* stat_sum;
+    float* stat_sq;
+    float* stat_dot;
+    t2i_act stat_x;
+    int stat_n, stat_c;
 } t2i_conv_gemm_desc;
 int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
 
@@ -128,6 +140,20 @@ int t2i_bn_bwd_reduce(const void* dy, long long dy_ps, const void* x, long long 
 int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                      const float* rstd, const float* gamma, const float* dgamma, const float* dbeta, void* dx,
                      long long dx_ps, int np, long long rows, int c, void* stream);
+/* The fused forms the training step uses.  t2i_bn_apply_train: sums = [sum x | sum x^2] (2*c floats, produced by
+ * t2i_conv_gemm's stat_sum / stat_sq); derives mean / biased variance / rstd (written out for the backward
+ * pass), applies gamma / beta (+ residual) (+ ReLU), and when moving_mean / moving_var are given also steps the
+ * moving statistics (UPDATE_OPS of the G run, model.py:98,102).  t2i_bn_bwd_fused: dbeta = sum dy and
+ * dot = sum dy * x were accumulated by the kernel that produced dy (stat_sum / stat_dot);
+ * dgamma[c] += rstd * (dot - mean * dbeta); dx as t2i_bn_bwd_apply; dx_sum[c] += sum dx (optional: the bias
+ * gradient of the conv in front of the BatchNorm). */
+int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
+                       const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
+                       long long rows, int c, int relu, float* mean, float* rstd, float* var, float* moving_mean,
+                       float* moving_var, float decay, void* stream);
+int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
+                     const float* rstd, const float* gamma, const float* dot, const float* dbeta, float* dgamma,
+                     void* dx, long long dx_ps, float* dx_sum, int np, long long rows, int c, void* stream);
 int t2i_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var,
                          long long rows, int c, float decay, void* stream);
 /* dst = dy * act'(y)  (relu / lrelu masks on post-activation values) */

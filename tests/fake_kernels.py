@@ -86,7 +86,8 @@ def _conv_core(mode, k, flip, x, w):
 
 
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
-              algo_scale=1.0, w_kn=False):
+              algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
+              stat_c=0):
     xv = x.values()
     wv = val(w)
     if w_kn:
@@ -106,6 +107,15 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
         neg = 0.2 if mask_kind == MASK_LRELU else 0.0
         v = v * torch.where(m > 0, torch.ones_like(m), torch.full_like(m, neg))
     y.put(v)
+    n_lim = stat_n if 0 < stat_n < v.shape[0] else v.shape[0]
+    c_lim = stat_c if 0 < stat_c < v.shape[-1] else v.shape[-1]
+    vs = v[:n_lim, ..., :c_lim].reshape(-1, c_lim)
+    if stat_sum is not None:
+        stat_sum[:c_lim] += vs.sum(0)
+    if stat_sq is not None:
+        stat_sq[:c_lim] += (vs * vs).sum(0)
+    if stat_dot is not None:
+        stat_dot[:c_lim] += (vs * stat_x.values()[:n_lim, ..., :c_lim].reshape(-1, c_lim)).sum(0)
 
 
 def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
@@ -193,6 +203,31 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
     if relu:
         v = torch.relu(v)
     put(y, v)
+
+
+def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
+                   decay=0.9):
+    c = x.shape[-1]
+    rows = x[0].numel() // c
+    m = sums[:c].double() / rows
+    s = torch.clamp(sums[c:2 * c].double() / rows - m * m, min=0)
+    mean.copy_(m); var.copy_(s); rstd.copy_(torch.rsqrt(s + eps))
+    if moving is not None:
+        bn_update_moving(moving[0], moving[1], mean, var, rows, decay)
+    bn_apply(x, mean, rstd, gamma, beta, y, residual, relu)
+
+
+def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None):
+    c = x.shape[-1]
+    rows = x[0].numel() // c
+    dg = rstd.double() * (dot.double() - mean.double() * dbeta.double())
+    dgamma += dg
+    g = val(dy)
+    xh = (val(x) - mean.double()) * rstd.double()
+    out = gamma.double() * rstd.double() * (g - dbeta.double() / rows - xh * dg / rows)
+    put(dx, out)
+    if dx_sum is not None:
+        dx_sum += out.reshape(-1, c).sum(0)
 
 
 def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta):

@@ -138,6 +138,129 @@ def test_conv_gemm_epilogue_and_windows(K, np_):
     check_close("inplace_mask", fk.val(yg2.cpu()), fk.val(yref2), *tol(np_))
 
 
+
+STAT_CASES = [
+    # name, mode, k, N, H, W, Cin, Cout, stat_n, stat_c
+    ("fc_rows", fk.CONV_S1, 1, 300, 1, 1, 64, 384, 0, 0),              # ragged last tile: OOB rows must not count
+    ("fc_few", fk.CONV_S1, 1, 4, 1, 1, 64, 256, 0, 0),                 # fewer rows than one tile
+    ("c3_4x4_lim", fk.CONV_S1, 3, 24, 4, 4, 128, 320, 17, 256),        # sample limit inside a tile, channel limit
+    ("c3_pair", fk.CONV_S1, 3, 64, 4, 4, 128, 256, 48, 0),             # CTA-pair tiles, limit on a tile boundary
+    ("c3_32x32", fk.CONV_S1, 3, 3, 32, 32, 64, 128, 2, 0),
+    ("k4s2_16", fk.CONV_K4S2, 4, 6, 16, 16, 64, 128, 0, 0),
+    ("deconv_8", fk.DECONV_K4S2, 4, 5, 8, 8, 128, 64, 3, 0),           # four output phases
+    ("tinych", fk.CONV_S1, 3, 4, 4, 4, 8, 16, 0, 0),                   # Cout < one 64-channel sub-tile
+]
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("case", STAT_CASES, ids=[c[0] for c in STAT_CASES])
+def test_conv_gemm_epilogue_statistics(K, case, np_):
+    """stat_sum / stat_sq / stat_dot of the epilogue against the restatement, with bias + activation + mask in
+    front of them, ragged tiles, sample / channel limits and accumulation (+=) semantics."""
+    name, mode, k, N, H, W, Cin, Cout, stat_n, stat_c = case
+    gen = torch.Generator().manual_seed(hash(name) % 1000 + 7)
+    taps = k * k if mode == fk.CONV_S1 else 16
+    oh, ow = out_hw(mode, H, W)
+    x = rand_planes(np_, (N, H, W, Cin), gen)
+    w = rand_planes(np_, (taps, Cout, Cin), gen, scale=(taps * Cin / (16 if mode == fk.DECONV_K4S2 else 1)) ** -0.5)
+    bias = torch.randn(Cout, generator=gen) * 0.5
+    maskbuf = rand_planes(np_, (N, oh, ow, Cout), gen)
+    sx = rand_planes(np_, (N, oh, ow, Cout), gen)
+    lim = dict(stat_n=stat_n, stat_c=stat_c)
+    ftol = 3e-5 if np_ == 2 else 2e-4
+    # (a) BatchNorm-forward form: bias, then sum and sum of squares
+    y = torch.zeros(np_, N, oh, ow, Cout, dtype=torch.bfloat16)
+    s1, s2 = torch.zeros(Cout, dtype=torch.float64), torch.zeros(Cout, dtype=torch.float64)
+    fk.conv_gemm(mode, k, 0, fk.View(x), w, fk.View(y), bias=bias, stat_sum=s1, stat_sq=s2, **lim)
+    yg = torch.zeros_like(y).cuda()
+    s1g, s2g = torch.ones(Cout, device="cuda"), torch.full((Cout,), 2.0, device="cuda")     # += semantics
+    K.conv_gemm(mode, k, 0, K.View(x.cuda()), w.cuda(), K.View(yg), bias=bias.cuda(), stat_sum=s1g, stat_sq=s2g, **lim)
+    torch.cuda.synchronize()
+    check_close(name + " y", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    check_close(name + " sum", s1g.cpu() - 1.0, s1, ftol, 10.0)
+    check_close(name + " sq", s2g.cpu() - 2.0, s2, ftol, 10.0)
+    if stat_c:
+        assert torch.all(s1g.cpu()[stat_c:] == 1.0) and torch.all(s2g.cpu()[stat_c:] == 2.0)
+    # (b) BatchNorm-backward form: ReLU derivative mask, then sum and dot with a second tensor
+    d1, d2 = torch.zeros(Cout, dtype=torch.float64), torch.zeros(Cout, dtype=torch.float64)
+    fk.conv_gemm(mode, k, 0, fk.View(x), w, fk.View(y), mask=fk.View(maskbuf), mask_kind=fk.MASK_RELU, stat_sum=d1,
+                 stat_dot=d2, stat_x=fk.View(sx), **lim)
+    d1g, d2g = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+    K.conv_gemm(mode, k, 0, K.View(x.cuda()), w.cuda(), K.View(yg), mask=K.View(maskbuf.cuda()), mask_kind=K.MASK_RELU,
+                stat_sum=d1g, stat_dot=d2g, stat_x=K.View(sx.cuda()), **lim)
+    torch.cuda.synchronize()
+    check_close(name + " masked y", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    check_close(name + " dsum", d1g.cpu(), d1, ftol, 10.0)
+    check_close(name + " ddot", d2g.cpu(), d2, ftol, 10.0)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_conv_gemm_statistics_with_residual_and_kn(K, np_):
+    """three epilogue tensors at once (residual add + mask + dot factor) on the KN (input-gradient) weight layout."""
+    gen = torch.Generator().manual_seed(21)
+    N, H, W, Cin, Cout = 20, 4, 4, 256, 192
+    x = rand_planes(np_, (N, H, W, Cin), gen)
+    w = rand_planes(np_, (9, Cin, Cout), gen, scale=(9 * Cin) ** -0.5)     # [tap][contraction][output channel]
+    add, mask, sx = [rand_planes(np_, (N, H, W, Cout), gen) for _ in range(3)]
+    y = torch.zeros(np_, N, H, W, Cout, dtype=torch.bfloat16)
+    d1, d2 = torch.zeros(Cout, dtype=torch.float64), torch.zeros(Cout, dtype=torch.float64)
+    fk.conv_gemm(fk.CONV_S1, 3, 1, fk.View(x), w, fk.View(y), add=fk.View(add), mask=fk.View(mask),
+                 mask_kind=fk.MASK_LRELU, w_kn=True, stat_sum=d1, stat_dot=d2, stat_x=fk.View(sx))
+    yg = torch.zeros_like(y).cuda()
+    d1g, d2g = torch.zeros(Cout, device="cuda"), torch.zeros(Cout, device="cuda")
+    K.conv_gemm(K.CONV_S1, 3, 1, K.View(x.cuda()), w.cuda(), K.View(yg), add=K.View(add.cuda()), mask=K.View(mask.cuda()),
+                mask_kind=K.MASK_LRELU, w_kn=True, stat_sum=d1g, stat_dot=d2g, stat_x=K.View(sx.cuda()))
+    torch.cuda.synchronize()
+    check_close("y", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    check_close("dsum", d1g.cpu(), d1, 3e-5 if np_ == 2 else 2e-4, 10.0)
+    check_close("ddot", d2g.cpu(), d2, 3e-5 if np_ == 2 else 2e-4, 10.0)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("rows,c", [(64, 16384), (4096, 256), (2048, 24), (70000, 128)])
+def test_fused_batch_norm_kernels(K, np_, rows, c):
+    """bn_apply_train (statistics finished in the apply kernel, moving statistics stepped) and bn_bwd_fused
+    (reductions supplied, dgamma / bias gradient produced) against the restatement."""
+    gen = torch.Generator().manual_seed(13)
+    x, xg = both(np_, (rows, c), gen, 2.0)
+    dy, dyg = both(np_, (rows, c), gen)
+    res, resg = both(np_, (rows, c), gen)
+    gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    xv = fk.val(x)
+    sums = torch.cat([xv.sum(0), (xv * xv).sum(0)]).float()
+    mean, rstd, var = torch.zeros(c), torch.zeros(c), torch.zeros(c)
+    mm, mv = torch.randn(c, generator=gen), torch.rand(c, generator=gen)
+    mmg, mvg = mm.cuda(), mv.cuda()
+    y = torch.zeros_like(x)
+    fk.bn_apply_train(x, sums.double(), 1e-5, gamma, beta, y, mean, rstd, var, residual=res, relu=True, moving=(mm, mv))
+    yg = torch.zeros_like(x).cuda()
+    mg, rg, vg = [torch.zeros(c, device="cuda") for _ in range(3)]
+    K.bn_apply_train(xg, sums.cuda(), 1e-5, gamma.cuda(), beta.cuda(), yg, mg, rg, vg, residual=resg, relu=True,
+                     moving=(mmg, mvg))
+    check_close("mean", mg.cpu(), mean, 1e-4, 1.0)
+    check_close("var", vg.cpu(), var, 1e-4, 1.0)
+    check_close("rstd", rg.cpu(), rstd, 1e-4, 1.0)
+    check_close("y", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    check_close("mm", mmg.cpu(), mm, 1e-5, 1.0)
+    check_close("mv", mvg.cpu(), mv, 1e-4, 1.0)
+    # without the moving pair nothing else may change
+    K.bn_apply_train(xg, sums.cuda(), 1e-5, gamma.cuda(), beta.cuda(), yg, mg, rg, vg)
+    check_close("mm untouched", mmg.cpu(), mm, 1e-5, 1.0)
+    dyv = fk.val(dy)
+    dbeta, dot = dyv.sum(0).float(), (dyv * xv).sum(0).float()
+    dga, dxs = torch.full((c,), 0.25, dtype=torch.float64), torch.zeros(c, dtype=torch.float64)
+    dx = torch.zeros_like(x)
+    fk.bn_bwd_fused(dy, x, mean, rstd, gamma, dot.double(), dbeta.double(), dga, dx, dxs)
+    dgag, dxsg = torch.full((c,), 0.25, device="cuda"), torch.zeros(c, device="cuda")
+    dxg = torch.zeros_like(x).cuda()
+    K.bn_bwd_fused(dyg, xg, mean.cuda(), rstd.cuda(), gamma.cuda(), dot.cuda(), dbeta.cuda(), dgag, dxg, dxsg)
+    check_close("dgamma", dgag.cpu(), dga, 5e-4, 5.0)
+    check_close("dx", fk.val(dxg.cpu()), fk.val(dx), *tol(np_))
+    # sum of dx is zero up to rounding (a bias in front of a BatchNorm has no gradient): bound it by the rounding scale
+    scale = float(fk.val(dx).abs().sum(0).max())
+    assert float((dxsg.cpu().double() - dxs).abs().max()) < (2.0 ** -8 if np_ == 1 else 1e-4) * scale + 1e-6
+
+
 WGRAD_CASES = [
     ("fc", fk.CONV_S1, 1, 256, 1, 1, 128, 128),
     ("fc_ragged", fk.CONV_S1, 1, 200, 1, 1, 256, 384),

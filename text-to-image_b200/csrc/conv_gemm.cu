@@ -37,21 +37,53 @@ struct alignas(64) ConvGemmParams {
     CUtensorMap out_maps[4];   // output views (transposed convs: one parity view per phase)
     CUtensorMap add_maps[4];   // optional residual, same grid as the output
     CUtensorMap mask_maps[4];  // optional derivative-mask source, same grid as the output
+    CUtensorMap sx_maps[4];    // optional second factor of the per-channel dot statistic, same grid as the output
     TapTable tt;
     int N, P, Q;               // virtual pixel grid (one GEMM row per point)
     int bn, bp, bq;            // TMA box on that grid, bn*bp*bq == 128
     int tiles_p, tiles_q;
     int tiles_m, tiles_co, total_tiles;
+    FastDiv fd_co, fd_ph, fd_q, fd_p;   // divisors of the tile index: tiles_co, n_phases, tiles_q, tiles_p
+    int lg_bq, lg_bqp;         // log2(bq), log2(bq * bp): row -> (q, p, n) inside the (power-of-two) box
     int k_chunks;              // ceil(Cin / 64)
     int n_pass;                // 1 (bf16) or 3 (split bf16: hi*hi, lo*hi, hi*lo)
     int np;
     int Cout;
     int n_stages;              // mainloop pipeline depth (what fits beside the epilogue buffers)
     int epi_depth;             // 1 or 2 staging buffers per epilogue tensor
-    int has_add, has_mask;
+    int has_add, has_mask, has_sx;
     const float* bias;
     int act, mask_kind;
+    // per-channel statistics of the output values (fp32 atomics): sum, and sum of squares (second_kind 1)
+    // or dot with the sx tile (second_kind 2); rows of samples >= stat_n / channels >= stat_c are left out
+    float* stat_sum;
+    float* stat_second;
+    int second_kind;
+    int stat_n, stat_c;
+    int stat_acc;              // channels of per-CTA shared accumulators (flushed once at the end), 0 = none
+    int dbg;                   // T2I_STAT_DBG bit field (tools/bench_conv.py): skip parts of the statistics path
 };
+
+// Column totals of a 32 x 32 block held one row per lane, 32 values per lane: after the five folds lane l
+// holds the total of column l (31 shuffles instead of 32 x 5).
+template <int STEP>
+__device__ __forceinline__ void fold_cols(float (&s)[32], int lane) {
+    const bool upper = (lane & STEP) != 0;
+#pragma unroll
+    for (int i = 0; i < STEP; ++i) {
+        const float send = upper ? s[i] : s[i + STEP];
+        const float keep = upper ? s[i + STEP] : s[i];
+        s[i] = keep + __shfl_xor_sync(0xffffffffu, send, STEP);
+    }
+}
+__device__ __forceinline__ float warp_col_totals(float (&s)[32], int lane) {
+    fold_cols<16>(s, lane);
+    fold_cols<8>(s, lane);
+    fold_cols<4>(s, lane);
+    fold_cols<2>(s, lane);
+    fold_cols<1>(s, lane);
+    return s[0];
+}
 
 __device__ __forceinline__ void tma_store_5d(const void* tmap, const void* src, int c0, int c1, int c2, int c3, int c4) {
     asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];" ::"l"(
@@ -78,20 +110,25 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int 
     TileCoord t;
     // order: output-channel tile fastest, then phase, then pixel tile -- the four phases of a transposed
     // conv re-read the same input rows, so they run back to back and hit in L2
-    t.ct = tile % prm.tiles_co;
-    const int rest = tile / prm.tiles_co;
-    t.ph = rest % prm.tt.n_phases;
-    const int mt = (rest / prm.tt.n_phases) * pair + rank;
-    t.q0 = (mt % prm.tiles_q) * prm.bq;
-    t.p0 = ((mt / prm.tiles_q) % prm.tiles_p) * prm.bp;
-    t.n0 = (mt / (prm.tiles_q * prm.tiles_p)) * prm.bn;
+    const int rest = fast_div(tile, prm.fd_co);
+    t.ct = tile - rest * prm.tiles_co;
+    const int rest2 = fast_div(rest, prm.fd_ph);
+    t.ph = rest - rest2 * prm.tt.n_phases;
+    const int mt = rest2 * pair + rank;
+    const int mq = fast_div(mt, prm.fd_q);
+    t.q0 = (mt - mq * prm.tiles_q) * prm.bq;
+    const int mp = fast_div(mq, prm.fd_p);
+    t.p0 = (mq - mp * prm.tiles_p) * prm.bp;
+    t.n0 = mp * prm.bn;
     return t;
 }
 
 // B_KN = false: weights [tap][N][K], K contiguous (K-major B operand, forward layout used forward).
 // B_KN = true : weights [tap][K][N], N contiguous (MN-major B operand): the SAME packed forward
 //               weights serve the input-gradient convolutions, no transposed copy exists.
-template <int BLOCK_N, bool B_KN, bool CTA2>
+// STATS = true adds the per-channel statistics of the epilogue (a separate instantiation so that plain
+// launches keep the lean epilogue).
+template <int BLOCK_N, bool B_KN, bool CTA2, bool STATS>
 __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
     constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;     // weight rows (output channels) staged by this CTA
     constexpr int kBBytes = kBRows * kBlockK * 2;
@@ -105,12 +142,15 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     const int n_stages = prm.n_stages;
     const int D = prm.epi_depth;
     const int np = prm.np;
-    // carve-up: [stages][out D*np][add D*np][mask D*np][bias][barriers]
+    // carve-up: [stages][out D*np][add D*np][mask D*np][sx D*np][bias][stat partials][barriers]
     uint8_t* s_out = smem + n_stages * kStageBytes;
     uint8_t* s_add = s_out + D * np * kSubBytes;
     uint8_t* s_mask = s_add + (prm.has_add ? D * np * kSubBytes : 0);
-    float* s_bias = reinterpret_cast<float*>(s_mask + (prm.has_mask ? D * np * kSubBytes : 0));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bias + BLOCK_N);
+    uint8_t* s_sx = s_mask + (prm.has_mask ? D * np * kSubBytes : 0);
+    float* s_bias = reinterpret_cast<float*>(s_sx + (prm.has_sx ? D * np * kSubBytes : 0));
+    float* s_stat = s_bias + BLOCK_N;               // STATS: [2 statistics][2 column halves][4 lane quarters][32]
+    float* s_acc = s_stat + (STATS ? 512 : 0);      // STATS: per-CTA running totals [2][stat_acc] (0 = straight to global)
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_acc + (STATS ? 2 * prm.stat_acc : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -253,11 +293,21 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         const int et = threadIdx.x - 64;              // epilogue thread index
         const int row = quarter * 32 + lane;
         const bool leader = (warp == 2 && lane == 0);
-        const bool has_aux = prm.has_add || prm.has_mask;
-        const uint32_t aux_bytes = static_cast<uint32_t>((prm.has_add + prm.has_mask) * np * kSubBytes);
+        const bool has_aux = prm.has_add || prm.has_mask || prm.has_sx;
+        const uint32_t aux_bytes = static_cast<uint32_t>((prm.has_add + prm.has_mask + prm.has_sx) * np * kSubBytes);
+        if (STATS) {   // running per-CTA totals: thread et owns channels == et mod 64 of statistic et / 64
+            for (int i = et; i < 2 * prm.stat_acc; i += kEpiThreads) s_acc[i] = 0.f;
+        }
         const int sw = row & 7;                       // 128B swizzle: 16B chunk j of row r lives at chunk j ^ (r & 7)
         const uint32_t row_off = row * 128;
         const float neg = (prm.mask_kind == T2I_MASK_LRELU) ? 0.2f : 0.0f;
+        // shared addresses of this thread's row in the staging tiles, and its four 16-byte chunks inside the row
+        const uint32_t so_u32 = smem_u32(s_out) + row_off, sa_u32 = smem_u32(s_add) + row_off;
+        const uint32_t sm_u32 = smem_u32(s_mask) + row_off, sx_u32 = smem_u32(s_sx) + row_off;
+        const uint32_t sb_u32 = smem_u32(s_bias) + static_cast<uint32_t>(half * 32) * 4;
+        uint32_t coff4[4];
+#pragma unroll
+        for (int gq = 0; gq < 4; ++gq) coff4[gq] = static_cast<uint32_t>(((half * 4 + gq) ^ sw) * 16);
 
         // aux tiles are prefetched D sub-tiles ahead along the sequence (tile, sub) this CTA will process
         auto issue_aux = [&](int tile, int sub, int buf) {
@@ -271,10 +321,13 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 if (prm.has_mask)
                     tma_load_5d(&prm.mask_maps[tc.ph], &aux_full[buf], s_mask + (buf * np + pl) * kSubBytes, c0, tc.q0,
                                 tc.p0, tc.n0, pl);
+                if (prm.has_sx)
+                    tma_load_5d(&prm.sx_maps[tc.ph], &aux_full[buf], s_sx + (buf * np + pl) * kSubBytes, c0, tc.q0,
+                                tc.p0, tc.n0, pl);
             }
         };
         auto subs_of = [&](int tile) {
-            const int ct = tile % prm.tiles_co;
+            const int ct = tile - fast_div(tile, prm.fd_co) * prm.tiles_co;
             int rem = prm.Cout - ct * BLOCK_N;
             if (rem > BLOCK_N) rem = BLOCK_N;
             return (rem + 63) / 64;
@@ -305,6 +358,14 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             const int co_base = tc.ct * BLOCK_N;
             const int n_sub = subs_of(tile);
             const uint32_t taddr = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+            // statistics: does this tile contribute at all, and is this thread's row a real, counted pixel?
+            const bool tile_stats = STATS && tc.n0 < prm.stat_n && co_base < prm.stat_c;
+            // ragged tiles (box beyond the grid, or straddling the sample limit) mask their rows individually
+            const bool tile_ragged = STATS && (tc.n0 + prm.bn > prm.stat_n || tc.p0 + prm.bp > prm.P || tc.q0 + prm.bq > prm.Q);
+            bool row_ok = true;
+            if (tile_ragged)
+                row_ok = tc.n0 + (row >> prm.lg_bqp) < prm.stat_n && tc.p0 + ((row >> prm.lg_bq) & (prm.bp - 1)) < prm.P &&
+                         tc.q0 + (row & (prm.bq - 1)) < prm.Q;
             // stage this tile's bias slice (all threads passed the previous sub-tile's second barrier)
             if (prm.bias != nullptr) {
                 for (int i = et; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (co_base + i < prm.Cout) ? __ldg(prm.bias + co_base + i) : 0.f;
@@ -324,13 +385,89 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 uint8_t* o_hi = s_out + (buf * np) * kSubBytes + row_off;
                 const uint8_t* a_base = s_add + (buf * np) * kSubBytes + row_off;
                 const uint8_t* m_base = s_mask + (buf * np) * kSubBytes + row_off;
+                const uint8_t* x_base = s_sx + (buf * np) * kSubBytes + row_off;
                 {
                     __syncwarp();
                     uint32_t r[32];
+                    float r2[32];     // second statistic's per-element terms (only live when requested)
                     tmem_ld_32x32(taddr + sub * 64 + half * 32, r);
                     tmem_ld_wait();
+                    if (np == 1) {
+                        // Throughput path (single bf16 plane): every optional stage is ONE uniform branch around
+                        // straight-line code over the thread's 32 values (independent chains keep the two epilogue
+                        // warps of a scheduler issuing back to back), shared memory through 32-bit addresses.
+                        float v[32];
 #pragma unroll
-                    for (int gq = 0; gq < 4; ++gq) {
+                        for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+                        const uint32_t boff = static_cast<uint32_t>(buf) * kSubBytes;
+                        if (prm.bias != nullptr) {
+                            const uint32_t sb = sb_u32 + static_cast<uint32_t>(sub) * 256;
+#pragma unroll
+                            for (int q4 = 0; q4 < 8; ++q4) {
+                                const uint4 b = lds128(sb + q4 * 16);
+                                v[4 * q4 + 0] += __uint_as_float(b.x); v[4 * q4 + 1] += __uint_as_float(b.y);
+                                v[4 * q4 + 2] += __uint_as_float(b.z); v[4 * q4 + 3] += __uint_as_float(b.w);
+                            }
+                        }
+                        if (prm.has_add) {
+#pragma unroll
+                            for (int gq = 0; gq < 4; ++gq) {
+                                const uint4 u = lds128(sa_u32 + boff + coff4[gq]);
+                                v[gq * 8 + 0] += bf16_lo(u.x); v[gq * 8 + 1] += bf16_hi(u.x);
+                                v[gq * 8 + 2] += bf16_lo(u.y); v[gq * 8 + 3] += bf16_hi(u.y);
+                                v[gq * 8 + 4] += bf16_lo(u.z); v[gq * 8 + 5] += bf16_hi(u.z);
+                                v[gq * 8 + 6] += bf16_lo(u.w); v[gq * 8 + 7] += bf16_hi(u.w);
+                            }
+                        }
+                        if (prm.act == T2I_ACT_LRELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.2f * v[i]);
+                        } else if (prm.act == T2I_ACT_RELU) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) v[i] = fmaxf(v[i], 0.0f);
+                        }
+                        if (prm.has_mask) {
+                            // bf16 m > 0  <=>  its bits, as a signed integer, are > 0 (low half shifted up; high half
+                            // compared against 0xffff so that the low half does not matter)
+#pragma unroll
+                            for (int gq = 0; gq < 4; ++gq) {
+                                const uint4 u = lds128(sm_u32 + boff + coff4[gq]);
+                                const uint32_t w4[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+                                for (int k = 0; k < 4; ++k) {
+                                    const float a = v[gq * 8 + 2 * k], b = v[gq * 8 + 2 * k + 1];
+                                    v[gq * 8 + 2 * k] = (static_cast<int>(w4[k] << 16) > 0) ? a : a * neg;
+                                    v[gq * 8 + 2 * k + 1] = (static_cast<int>(w4[k]) > 0xffff) ? b : b * neg;
+                                }
+                            }
+                        }
+                        if (tile_stats) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(v[i]);
+                            if (prm.second_kind == 1) {
+#pragma unroll
+                                for (int i = 0; i < 32; ++i) r2[i] = v[i] * v[i];
+                            } else if (prm.second_kind == 2) {
+#pragma unroll
+                                for (int gq = 0; gq < 4; ++gq) {
+                                    const uint4 u = lds128(sx_u32 + boff + coff4[gq]);
+                                    r2[gq * 8 + 0] = v[gq * 8 + 0] * bf16_lo(u.x); r2[gq * 8 + 1] = v[gq * 8 + 1] * bf16_hi(u.x);
+                                    r2[gq * 8 + 2] = v[gq * 8 + 2] * bf16_lo(u.y); r2[gq * 8 + 3] = v[gq * 8 + 3] * bf16_hi(u.y);
+                                    r2[gq * 8 + 4] = v[gq * 8 + 4] * bf16_lo(u.z); r2[gq * 8 + 5] = v[gq * 8 + 5] * bf16_hi(u.z);
+                                    r2[gq * 8 + 6] = v[gq * 8 + 6] * bf16_lo(u.w); r2[gq * 8 + 7] = v[gq * 8 + 7] * bf16_hi(u.w);
+                                }
+                            }
+                        }
+#pragma unroll
+                        for (int gq = 0; gq < 4; ++gq) {
+                            uint4 hi;
+                            hi.x = pack_bf16x2(v[gq * 8 + 0], v[gq * 8 + 1]); hi.y = pack_bf16x2(v[gq * 8 + 2], v[gq * 8 + 3]);
+                            hi.z = pack_bf16x2(v[gq * 8 + 4], v[gq * 8 + 5]); hi.w = pack_bf16x2(v[gq * 8 + 6], v[gq * 8 + 7]);
+                            sts128(so_u32 + boff + coff4[gq], hi);
+                        }
+                    } else
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) {   // parity path (np == 2: hi + lo planes), generic form
                         const int chunk = half * 4 + gq;              // 16B chunk (8 channels) within the 64-channel row
                         const uint32_t coff = static_cast<uint32_t>((chunk ^ sw) * 16);
                         float v[8];
@@ -366,6 +503,23 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
 #pragma unroll
                             for (int j = 0; j < 8; ++j) v[j] *= (m[j] > 0.0f) ? 1.0f : neg;
                         }
+                        if (tile_stats) {
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) r[gq * 8 + j] = __float_as_uint(v[j]);
+                            if (prm.second_kind == 1) {
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) r2[gq * 8 + j] = v[j] * v[j];
+                            } else if (prm.second_kind == 2) {
+                                float xs[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+                                for (int pl = 0; pl < np; ++pl) {
+                                    const uint4 u = *reinterpret_cast<const uint4*>(x_base + pl * kSubBytes + coff);
+                                    xs[0] += bf16_lo(u.x); xs[1] += bf16_hi(u.x); xs[2] += bf16_lo(u.y); xs[3] += bf16_hi(u.y);
+                                    xs[4] += bf16_lo(u.z); xs[5] += bf16_hi(u.z); xs[6] += bf16_lo(u.w); xs[7] += bf16_hi(u.w);
+                                }
+#pragma unroll
+                                for (int j = 0; j < 8; ++j) r2[gq * 8 + j] = v[j] * xs[j];
+                            }
+                        }
                         uint4 hi;
                         hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
                         hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
@@ -379,6 +533,19 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             *reinterpret_cast<uint4*>(o_hi + kSubBytes + coff) = lo;
                         }
                     }
+                    if (tile_stats) {   // column totals of this warp's 32 x 32 block -> shared partials
+                        float s1[32];
+#pragma unroll
+                        for (int i = 0; i < 32; ++i) s1[i] = __uint_as_float(r[i]);
+                        if (!row_ok) {
+#pragma unroll
+                            for (int i = 0; i < 32; ++i) { s1[i] = 0.f; r2[i] = 0.f; }
+                        }
+                        if (!(prm.dbg & 1)) {
+                        s_stat[(half * 4 + quarter) * 32 + lane] = warp_col_totals(s1, lane);
+                        if (prm.second_kind != 0) s_stat[256 + (half * 4 + quarter) * 32 + lane] = warp_col_totals(r2, lane);
+                        }
+                    }
                 }
                 if (sub == n_sub - 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
@@ -390,6 +557,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
                 fence_proxy_async();      // generic-proxy smem writes -> visible to the TMA store
                 named_bar_sync(2, kEpiThreads);
+                if (tile_stats && et < 128 && !(prm.dbg & 2)) {   // (statistic, channel) totals of the sub-tile
+                    const int which = et >> 6, hc = et & 63;          // hc = column inside the 64-channel sub-tile
+                    float* dst = which == 0 ? prm.stat_sum : prm.stat_second;
+                    const int ch = co_base + sub * 64 + hc;
+                    if (dst != nullptr && ch < prm.stat_c && (which == 0 || prm.second_kind != 0)) {
+                        const float* sp = s_stat + which * 256 + (hc >> 5) * 128 + (hc & 31);
+                        const float t = sp[0] + sp[32] + sp[64] + sp[96];
+                        if (prm.stat_acc > 0) s_acc[which * prm.stat_acc + ch] += t;   // this thread alone owns the slot
+                        else atomicAdd(dst + ch, t);
+                    }
+                }
                 if (leader) {
                     for (int pl = 0; pl < np; ++pl)
                         tma_store_5d(&prm.out_maps[tc.ph], s_out + (buf * np + pl) * kSubBytes, co_base + sub * 64, tc.q0,
@@ -403,6 +581,16 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
             }
         }
         if (leader) bulk_wait_all();
+        if (STATS && prm.stat_acc > 0 && et < 128 && !(prm.dbg & 4)) {   // one global atomic per channel this CTA contributed to
+            const int which = et >> 6;
+            float* dst = which == 0 ? prm.stat_sum : prm.stat_second;
+            if (dst != nullptr) {
+                for (int ch = et & 63; ch < prm.stat_c; ch += 64) {
+                    const float t = s_acc[which * prm.stat_acc + ch];
+                    if (t != 0.f) atomicAdd(dst + ch, t);
+                }
+            }
+        }
     }
 
     tc_fence_before();
@@ -499,7 +687,15 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     prm.has_add = d->add.ptr != nullptr;
     prm.has_mask = d->mask.ptr != nullptr;
     if (prm.has_mask && d->mask_kind == T2I_MASK_NONE) return fail(T2I_ERR_BAD_ARG, "mask tensor without mask_kind");
-    for (const t2i_act* a : {&d->add, &d->mask})
+    prm.has_sx = d->stat_dot != nullptr;
+    if (prm.has_sx && d->stat_x.ptr == nullptr) return fail(T2I_ERR_BAD_ARG, "stat_dot without stat_x");
+    if (d->stat_sq != nullptr && d->stat_dot != nullptr) return fail(T2I_ERR_BAD_ARG, "stat_sq and stat_dot are exclusive");
+    prm.stat_sum = d->stat_sum;
+    prm.stat_second = d->stat_sq != nullptr ? d->stat_sq : d->stat_dot;
+    prm.second_kind = d->stat_sq != nullptr ? 1 : d->stat_dot != nullptr ? 2 : 0;
+    prm.stat_n = (d->stat_n > 0 && d->stat_n < x.n) ? d->stat_n : x.n;
+    prm.stat_c = (d->stat_c > 0 && d->stat_c < y.c) ? d->stat_c : y.c;
+    for (const t2i_act* a : {&d->add, &d->mask, &d->stat_x})
         if (a->ptr != nullptr && (a->n != y.n || a->h != y.h || a->w != y.w || a->c < y.c))
             return fail(T2I_ERR_BAD_ARG, "epilogue tensor [%d,%d,%d,%d] does not cover the output [%d,%d,%d,%d]", a->n, a->h,
                         a->w, a->c, y.n, y.h, y.w, y.c);
@@ -513,12 +709,29 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     if (y.c > 128 && (long long)prm.tt.n_phases * units_m * ceil_div(y.c, 256) >= workers) block_n = 256;
     prm.tiles_co = ceil_div(y.c, block_n);
     prm.total_tiles = prm.tt.n_phases * units_m * prm.tiles_co;
+    prm.fd_co = make_fastdiv(prm.tiles_co);
+    prm.fd_ph = make_fastdiv(prm.tt.n_phases);
+    prm.fd_q = make_fastdiv(prm.tiles_q);
+    prm.fd_p = make_fastdiv(prm.tiles_p);
+    for (prm.lg_bq = 0; (1 << prm.lg_bq) < prm.bq; ++prm.lg_bq) {}
+    for (prm.lg_bqp = 0; (1 << prm.lg_bqp) < prm.bq * prm.bp; ++prm.lg_bqp) {}
     // shared memory plan: epilogue staging first, the mainloop pipeline takes what is left
     prm.epi_depth = (d->np == 1) ? 2 : 1;
     const int b_rows = cta2 ? block_n / 2 : block_n;                       // weight rows staged per CTA
     const int stage_bytes = kABytes + b_rows * kBlockK * 2;
-    const int epi_bytes = (1 + prm.has_add + prm.has_mask) * prm.epi_depth * d->np * kSubBytes;
-    const int tail_bytes = block_n * 4 + 256;   // bias slice + barriers
+    const int n_aux = prm.has_add + prm.has_mask + prm.has_sx;
+    if (n_aux == 3) prm.epi_depth = 1;
+    const int epi_bytes = (1 + n_aux) * prm.epi_depth * d->np * kSubBytes;
+    const bool stats = prm.stat_sum != nullptr || prm.stat_second != nullptr;
+    // per-CTA running totals in shared memory (one flush per CTA instead of one atomic per tile and channel:
+    // thousands of tiles hammering the same few L2 lines serialise); very wide outputs have few tiles -> direct
+    prm.stat_acc = (stats && prm.stat_c <= 2048) ? (prm.stat_c + 63) / 64 * 64 : 0;
+    {
+        const char* e = getenv("T2I_STAT_DBG");
+        prm.dbg = e ? atoi(e) : 0;
+        if (prm.dbg & 8) prm.stat_acc = 0;
+    }
+    const int tail_bytes = block_n * 4 + (stats ? 2048 + 8 * prm.stat_acc : 0) + 256;   // bias, statistics, barriers
     int stages = (kSmemBudget - epi_bytes - tail_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return fail(T2I_ERR_BAD_ARG, "shared memory plan leaves %d pipeline stages", stages);
@@ -542,6 +755,12 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         rc = make_act_maps(a, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.mask_maps);
         if (rc != T2I_OK) return rc;
     }
+    if (prm.has_sx) {
+        t2i_act a = d->stat_x;
+        a.c = y.c;
+        rc = make_act_maps(a, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.sx_maps);
+        if (rc != T2I_OK) return rc;
+    }
     {
         const int taps = (d->mode == T2I_CONV_S1) ? d->k * d->k : 16;
         const uint64_t e = 2;
@@ -558,12 +777,17 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
 
     const int grid = (prm.total_tiles < workers ? prm.total_tiles : workers) * (cta2 ? 2 : 1);
     typedef void (*KernelFn)(const ConvGemmParams);
-    static bool attr_done[8] = {false, false, false, false, false, false, false, false};
-    const int variant = (cta2 ? 4 : 0) + (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
-    const KernelFn fns[8] = {conv_gemm_kernel<128, false, false>, conv_gemm_kernel<128, true, false>,
-                             conv_gemm_kernel<256, false, false>, conv_gemm_kernel<256, true, false>,
-                             conv_gemm_kernel<128, false, true>,  conv_gemm_kernel<128, true, true>,
-                             conv_gemm_kernel<256, false, true>,  conv_gemm_kernel<256, true, true>};
+    static bool attr_done[16] = {};
+    const int variant = (stats ? 8 : 0) + (cta2 ? 4 : 0) + (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
+    const KernelFn fns[16] = {
+        conv_gemm_kernel<128, false, false, false>, conv_gemm_kernel<128, true, false, false>,
+        conv_gemm_kernel<256, false, false, false>, conv_gemm_kernel<256, true, false, false>,
+        conv_gemm_kernel<128, false, true, false>,  conv_gemm_kernel<128, true, true, false>,
+        conv_gemm_kernel<256, false, true, false>,  conv_gemm_kernel<256, true, true, false>,
+        conv_gemm_kernel<128, false, false, true>,  conv_gemm_kernel<128, true, false, true>,
+        conv_gemm_kernel<256, false, false, true>,  conv_gemm_kernel<256, true, false, true>,
+        conv_gemm_kernel<128, false, true, true>,   conv_gemm_kernel<128, true, true, true>,
+        conv_gemm_kernel<256, false, true, true>,   conv_gemm_kernel<256, true, true, true>};
     if (!attr_done[variant]) {
         cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));

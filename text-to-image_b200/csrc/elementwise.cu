@@ -453,7 +453,121 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
     }
 }
 
-// launch geometry shared by the two row-striding kernels above
+
+// Training-mode BatchNorm apply that finishes the statistics itself: sums = [sum x | sum x^2] per channel
+// (accumulated by the producing conv_gemm's epilogue).  Every thread derives mean / rstd of its 8 channels;
+// block row 0 also publishes mean / biased variance / rstd for the backward pass and, when asked (the G run:
+// UPDATE_OPS, model.py:98,102), steps the moving statistics (utils/ops.py:20-29: decay 0.9, unbiased variance).
+__global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps, const float* __restrict__ sums,
+                                      float inv_rows, float eps, const float* __restrict__ gamma,
+                                      const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
+                                      bf16* __restrict__ y, long long y_ps, int np, long long rows, int c, int relu, int CG,
+                                      float* mean_out, float* rstd_out, float* var_out, float* mm, float* mv, float decay,
+                                      float bessel) {
+    pdl_launch_dependents();
+    const int RY = blockDim.x / CG;
+    const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
+    const int ry = threadIdx.x / CG;
+    if (ch >= c || ry >= RY) return;
+    float sc[8], sh[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const float m = sums[ch + j] * inv_rows;
+        const float v = fmaxf(sums[c + ch + j] * inv_rows - m * m, 0.f);
+        const float rs = rsqrtf(v + eps);
+        if (blockIdx.y == 0 && ry == 0) {
+            mean_out[ch + j] = m;
+            var_out[ch + j] = v;
+            rstd_out[ch + j] = rs;
+            if (mm != nullptr) {
+                mm[ch + j] = decay * mm[ch + j] + (1.f - decay) * m;
+                mv[ch + j] = decay * mv[ch + j] + (1.f - decay) * v * bessel;
+            }
+        }
+        sc[j] = rs * gamma[ch + j];
+        sh[j] = beta[ch + j] - m * sc[j];
+    }
+#pragma unroll 4
+    for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
+        const long long e = r * c + ch;
+        float v[8];
+        load8(x + e, x_ps, np, v);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+        if (res != nullptr) {
+            float rr[8];
+            load8(res + e, r_ps, np, rr);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] += rr[j];
+        }
+        if (relu) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
+        }
+        store8(y + e, y_ps, np, v);
+    }
+}
+
+// BatchNorm input-gradient with the reductions already done by the kernel that produced dy:
+// dbeta = sum dy, dot = sum dy * x (raw pre-normalisation input).  dgamma = rstd * (dot - mean * dbeta);
+// dx = gamma * rstd * (dy - dbeta/R - xhat * dgamma/R).  Block row 0 adds dgamma into the gradient buffer;
+// dx_sum (optional) accumulates the per-channel sum of dx = the bias gradient of the conv in front of the BN.
+__global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ x,
+                                    long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
+                                    const float* __restrict__ gamma, const float* __restrict__ dot,
+                                    const float* __restrict__ dbeta, float* dgamma_out, bf16* __restrict__ dx,
+                                    long long dx_ps, float* dx_sum, int np, long long rows, int c, float inv_rows, int CG) {
+    pdl_launch_dependents();
+    __shared__ float sh[256 * 8];
+    const int RY = blockDim.x / CG;
+    const int cgl = threadIdx.x % CG;
+    const int ch = (blockIdx.x * CG + cgl) * 8;
+    const int ry = threadIdx.x / CG;
+    float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    if (ch < c && ry < RY) {
+        float mu[8], rs[8], a[8], b0[8], b1[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            mu[j] = mean[ch + j];
+            rs[j] = rstd[ch + j];
+            const float db = dbeta[ch + j];
+            const float dg = rs[j] * (dot[ch + j] - mu[j] * db);
+            if (blockIdx.y == 0 && ry == 0) dgamma_out[ch + j] += dg;
+            a[j] = gamma[ch + j] * rs[j];
+            b0[j] = db * inv_rows;
+            b1[j] = dg * inv_rows;
+        }
+#pragma unroll 4
+        for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
+            const long long e = r * c + ch;
+            float g[8], xv[8];
+            load8(dy + e, dy_ps, np, g);
+            load8(x + e, x_ps, np, xv);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                g[j] = a[j] * (g[j] - b0[j] - (xv[j] - mu[j]) * rs[j] * b1[j]);
+                acc[j] += g[j];
+            }
+            store8(dx + e, dx_ps, np, g);
+        }
+    }
+    if (dx_sum == nullptr) return;
+    const int W = CG * 8;
+    if (ry < RY) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sh[ry * W + cgl * 8 + j] = acc[j];
+    }
+    __syncthreads();
+    for (int col = threadIdx.x; col < W; col += blockDim.x) {
+        const int chn = blockIdx.x * W + col;
+        if (chn >= c) continue;
+        float t = 0.f;
+        for (int k = 0; k < RY; ++k) t += sh[k * W + col];
+        atomicAdd(dx_sum + chn, t);
+    }
+}
+
+// launch geometry shared by the row-striding kernels above
 static inline void rowwise_geometry(long long rows, int c, int threads, int* CG, dim3* grid) {
     int cg = c / 8;
     int g = cg > 32 ? 32 : floor_pow2(cg);
@@ -893,6 +1007,34 @@ extern "C" int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, 
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dgamma, dbeta,
         static_cast<bf16*>(dx), dx_ps, np, rows, c, 1.f / (float)rows, CG);
     return check_launch("bn_bwd_apply");
+}
+extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
+                                  const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
+                                  long long rows, int c, int relu, float* mean, float* rstd, float* var,
+                                  float* moving_mean, float* moving_var, float decay, void* stream) {
+    if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: c must be a multiple of 8");
+    if ((moving_mean == nullptr) != (moving_var == nullptr)) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: moving pair");
+    int CG;
+    dim3 grid;
+    rowwise_geometry(rows, c, 256, &CG, &grid);
+    const float bessel = rows > 1 ? (float)rows / (float)(rows - 1) : 1.f;
+    bn_apply_train_kernel<<<grid, 256, 0, STREAM>>>(
+        static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)rows, eps, gamma, beta, static_cast<const bf16*>(residual),
+        r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel);
+    return check_launch("bn_apply_train");
+}
+extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
+                                const float* rstd, const float* gamma, const float* dot, const float* dbeta,
+                                float* dgamma, void* dx, long long dx_ps, float* dx_sum, int np, long long rows, int c,
+                                void* stream) {
+    if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: c must be a multiple of 8");
+    int CG;
+    dim3 grid;
+    rowwise_geometry(rows, c, 256, &CG, &grid);
+    bn_bwd_fused_kernel<<<grid, 256, 0, STREAM>>>(
+        static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,
+        static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)rows, CG);
+    return check_launch("bn_bwd_fused");
 }
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,
                                     float decay, void* stream) {

@@ -61,6 +61,26 @@ inline cudaError_t launch_pdl(void (*kernel)(const Params), int grid, int block,
     return cudaLaunchKernelEx(&cfg, kernel, prm);
 }
 
+// Division by a runtime constant as multiply-high + shift (Granlund-Montgomery, round-up variant), valid for
+// 0 <= n < 2^31: q = (umulhi(mul, n) + n) >> shr.  The kernels decode tile indices with it.
+struct FastDiv {
+    uint32_t mul, shr, d;
+};
+inline FastDiv make_fastdiv(int d) {
+    FastDiv f;
+    f.d = (uint32_t)d;
+    uint32_t l = 0;
+    while ((1u << l) < (uint32_t)d) ++l;
+    f.shr = l;
+    f.mul = (uint32_t)(((1ull << 32) * ((1ull << l) - (uint64_t)d)) / (uint64_t)d + 1);
+    return f;
+}
+#ifdef __CUDACC__
+__device__ __forceinline__ int fast_div(int n, const FastDiv& f) {
+    return (int)((__umulhi(f.mul, (uint32_t)n) + (uint32_t)n) >> f.shr);
+}
+#endif
+
 inline int floor_pow2(int v) {
     int p = 1;
     while (p * 2 <= v) p *= 2;

@@ -181,7 +181,6 @@ class Engine:
         self.bn_mean = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_var = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_rstd = [torch.zeros(c, **f32) for c in self.bn_ch]
-        self.bn_sums = [torch.zeros(2 * c, **f32) for c in self.bn_ch]     # zero between bn_stats calls
         for gmm in self.bn_gamma:
             gmm.fill_(1.0)
         self.kt = torch.full((1,), KT_INIT, **f32)
@@ -386,6 +385,15 @@ class Engine:
         g["tn"] = torch.zeros(B, ce, **f32)
         g["z"] = torch.zeros(B, Z, **f32)
         g["kl_scratch"] = torch.zeros(1, **f32)
+        # BatchNorm accumulators fed by the conv epilogues: per layer [sum x | sum x^2] (forward) and
+        # sum dy * x (backward), one contiguous buffer cleared by a single memset per generator forward
+        tot = sum(self.bn_ch)
+        self.bn_scratch = torch.zeros(3 * tot, **f32)
+        self.bn_fwd_sums, self.bn_dot, off = [], [], 0
+        for c in self.bn_ch:
+            self.bn_fwd_sums.append(self.bn_scratch[off:off + 2 * c]); off += 2 * c
+        for c in self.bn_ch:
+            self.bn_dot.append(self.bn_scratch[off:off + c]); off += c
         self.feed = {"cond": torch.zeros(B, E, **f32), "epsilon": torch.zeros(B, **f32)}
 
     @staticmethod
@@ -394,97 +402,129 @@ class Engine:
         return t.view(t.shape[0], -1, t.shape[-1])
 
     # ------------------------------------------------------------------ generator
-    def _bn(self, i, x, y, residual=None, relu=False, train=True):
+    def _bn(self, i, x, y, residual=None, relu=False, train=True, update_moving=False):
+        """BatchNorm i on x -> y.  Training mode: the conv that produced x left [sum x | sum x^2] in
+        bn_fwd_sums[i] (epilogue statistics); one kernel finishes them, normalises and (G run) steps the
+        moving statistics.  Inference (sampler, model.py:57): moving statistics."""
         K = self.K
         if train:
-            K.bn_stats(x, self.bn_sums[i], self.bn_mean[i], self.bn_rstd[i], self.bn_var[i], BN_EPS)
-            mean, rstd = self.bn_mean[i], self.bn_rstd[i]
-        else:   # inference: moving statistics (sampler, model.py:57) -- not on the training path
-            mean, rstd = self.bn_mm[i], torch.rsqrt(self.bn_mv[i] + BN_EPS)
-        K.bn_apply(x, mean, rstd, self.bn_gamma[i], self.bn_beta[i], y, residual, relu)
+            K.bn_apply_train(x, self.bn_fwd_sums[i], BN_EPS, self.bn_gamma[i], self.bn_beta[i], y, self.bn_mean[i],
+                             self.bn_rstd[i], self.bn_var[i], residual=residual, relu=relu,
+                             moving=(self.bn_mm[i], self.bn_mv[i]) if update_moving else None, decay=BN_DECAY)
+        else:
+            K.bn_apply(x, self.bn_mm[i], torch.rsqrt(self.bn_mv[i] + BN_EPS), self.bn_gamma[i], self.bn_beta[i], y,
+                       residual, relu)
 
-    def g_forward(self, z, cond, tn_eps, img_out, kl_sum, train=True, cond_noise=True):
-        """models/wgancls/model.py:163-225.  z, cond, tn_eps: fp32 device tensors; image -> img_out."""
+    def g_forward(self, z, cond, tn_eps, img_out, kl_sum, train=True, cond_noise=True, update_moving=False):
+        """models/wgancls/model.py:163-225.  z, cond, tn_eps: fp32 device tensors; image -> img_out.
+        update_moving: also run the UPDATE_OPS of utils/ops.py:20-29 (the G run, model.py:98,102)."""
         K, g, gl, V = self.K, self.g, self.gl, self.K.View
         S1, DC = K.CONV_S1, K.DECONV_K4S2
+        if train:
+            self.bn_scratch.zero_()
+
+        def stats(i):     # batch statistics of BatchNorm i, accumulated by the epilogue of the conv in front of it
+            if not train:
+                return {}
+            c = self.bn_ch[i]
+            return dict(stat_sum=self.bn_fwd_sums[i][:c], stat_sq=self.bn_fwd_sums[i][c:])
+
+        def bn(i, x, y, **kw):
+            self._bn(i, x, y, train=train, update_moving=update_moving, **kw)
+
         K.to_planes(cond, g["cond"])
         K.conv_gemm(S1, 1, 0, V(g["cond"]), gl["ms"].Wf, V(g["ms"]), bias=gl["ms"].b, act=K.ACT_LRELU)   # :113-114
         if not cond_noise:
             tn_eps = torch.zeros_like(tn_eps)
         K.ca_fwd(g["ms"], z, tn_eps, g["zc"], kl_sum)                                                   # :117-122,174
         f0r = g["f0"].view(self.np, self.B, -1)
-        K.conv_gemm(S1, 1, 0, V(g["zc"]), gl["fc0"].Wf, V(f0r), bias=gl["fc0"].b)                        # :175
-        self._bn(0, f0r, g["h0"].view(self.np, self.B, -1), train=train)                                 # :176
+        K.conv_gemm(S1, 1, 0, V(g["zc"]), gl["fc0"].Wf, V(f0r), bias=gl["fc0"].b, **stats(0))            # :175
+        bn(0, f0r, g["h0"].view(self.np, self.B, -1))                                                    # :176
 
-        def conv(l, x, y):
-            K.conv_gemm(gl[l].mode, gl[l].k, 0, V(g[x]), gl[l].Wf, V(g[y]), bias=gl[l].b)
+        def conv(l, x, y, bn_i=None):
+            K.conv_gemm(gl[l].mode, gl[l].k, 0, V(g[x]), gl[l].Wf, V(g[y]), bias=gl[l].b,
+                        **(stats(bn_i) if bn_i is not None else {}))
 
         def res(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out):
-            conv(c_a, x, t_a); self._bn(bn_a, g[t_a], g[u_a], relu=True, train=train)
-            conv(c_b, u_a, t_b); self._bn(bn_b, g[t_b], g[u_b], relu=True, train=train)
-            conv(c_c, u_b, t_c); self._bn(bn_c, g[t_c], g[out], residual=g[x], relu=True, train=train)
+            conv(c_a, x, t_a, bn_a); bn(bn_a, g[t_a], g[u_a], relu=True)
+            conv(c_b, u_a, t_b, bn_b); bn(bn_b, g[t_b], g[u_b], relu=True)
+            conv(c_c, u_b, t_c, bn_c); bn(bn_c, g[t_c], g[out], residual=g[x], relu=True)
 
         res("h0", "c0", "t1", 1, "u1", "c1", "t2", 2, "u2", "c2", "t3", 3, "h1")                        # :184-191
-        conv("t0", "h1", "d1"); conv("c3", "d1", "t4"); self._bn(4, g["t4"], g["h2"], train=train)      # :194-196
+        conv("t0", "h1", "d1"); conv("c3", "d1", "t4", 4); bn(4, g["t4"], g["h2"])                       # :194-196
         res("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3")                        # :200-207
-        conv("t1", "h3", "d2"); conv("c7", "d2", "t8"); self._bn(8, g["t8"], g["h4"], relu=True, train=train)  # :210-212
-        conv("t2", "h4", "d3"); conv("c8", "d3", "t9"); self._bn(9, g["t9"], g["h5"], relu=True, train=train)  # :214-216
+        conv("t1", "h3", "d2"); conv("c7", "d2", "t8", 8); bn(8, g["t8"], g["h4"], relu=True)            # :210-212
+        conv("t2", "h4", "d3"); conv("c8", "d3", "t9", 9); bn(9, g["t9"], g["h5"], relu=True)            # :214-216
         K.conv_gemm(S1, 1, 0, V(self._rows(g["h5"])), gl["t3"].Wf, V(g["colg"]), algo_scale=0.75)      # :218 as patches
         K.col2im_k4s2_c3(g["colg"], g["u4"], gl["t3"].b)
         K.conv3x3_c3_tanh_fwd(g["u4"], gl["c9"].w, gl["c9"].b, img_out)                                  # :219-221
 
     def g_backward(self, d_img):
-        """Backward of g_forward given dLoss/d image (fp32 [B,64,64,3]); fills the g gradient buffer."""
+        """Backward of g_forward given dLoss/d image (fp32 [B,64,64,3]); fills the g gradient buffer.
+        Every input-gradient GEMM whose output is the gradient at a BatchNorm(+ReLU) output applies the ReLU
+        derivative mask and accumulates that BatchNorm's two backward reductions (sum dy -> dbeta, sum dy * x)
+        in its epilogue; bn_bwd_fused then needs one pass.  Bias gradients ride along the same way."""
         K, g, gl, V = self.K, self.g, self.gl, self.K.View
         S1, K4, DC = K.CONV_S1, K.CONV_K4S2, K.DECONV_K4S2
         B, np_ = self.B, self.np
         rows = self._rows
+        RELU = K.MASK_RELU
         img = self.d["img"][:B]
+
+        def bn_red(i, x_pre):
+            return dict(stat_sum=self.bn_dbeta[i], stat_dot=self.bn_dot[i], stat_x=V(x_pre))
+
+        def bn_bwd(i, dy, x_pre, dx, conv_bias_grad):
+            """dy: gradient at the BatchNorm output (already masked); dx: gradient at its input = at the output
+            of the conv in front, whose bias gradient is the per-channel sum of dx."""
+            K.bn_bwd_fused(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_gamma[i], self.bn_dot[i],
+                           self.bn_dbeta[i], self.bn_dgamma[i], dx, conv_bias_grad)
+
+        def conv_bwd(l, x, dy, dx, **epi):
+            """weight gradient of layer l (input x, output gradient dy) and its input gradient -> dx (+ epilogue)."""
+            L = gl[l]
+            with self._side():
+                K.wgrad_gemm(L.mode, L.k, V(g[x]), V(g[dy]), L.gw)
+            mode = {S1: S1, DC: K4, K4: DC}[L.mode]
+            K.conv_gemm(mode, L.k, 1 if L.k == 3 else 0, V(g[dy]), L.Wf, V(dx), w_kn=True, **epi)
+
+        def relu_of(y_post):
+            return dict(mask=V(g[y_post]), mask_kind=RELU)
+
+        def res_bwd(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out, **last_epi):
+            ds = g["ds"][out]          # gradient at (x + bn(t_c)), ReLU mask applied by its producer
+            bn_bwd(bn_c, ds, g[t_c], g["d_" + t_c], gl[c_c].gb)
+            conv_bwd(c_c, u_b, "d_" + t_c, g["d_" + u_b], **relu_of(u_b), **bn_red(bn_b, g[t_b]))
+            bn_bwd(bn_b, g["d_" + u_b], g[t_b], g["d_" + t_b], gl[c_b].gb)
+            conv_bwd(c_b, u_a, "d_" + t_b, g["d_" + u_a], **relu_of(u_a), **bn_red(bn_a, g[t_a]))
+            bn_bwd(bn_a, g["d_" + u_a], g[t_a], g["d_" + t_a], gl[c_a].gb)
+            conv_bwd(c_a, x, "d_" + t_a, g["d_" + x], add=V(ds), **last_epi)     # skip connection joins here
+
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
         K.im2col_k4s2_c3(g["d_u4"], g["d_colg"])
         with self._side():
             K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
-        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wf, V(rows(g["d_h5"])), algo_scale=0.75, w_kn=True)
-
-        def bn_bwd(i, dy, y_post, x_pre, dx, relu):
-            """dy: gradient w.r.t. the BN(+ReLU) output; writes the gradient w.r.t. its input."""
-            if relu:
-                K.act_bwd(dy, y_post, dy, K.MASK_RELU)
-            K.bn_bwd_reduce(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_dgamma[i], self.bn_dbeta[i])
-            K.bn_bwd_apply(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_gamma[i], self.bn_dgamma[i],
-                           self.bn_dbeta[i], dx)
-
-        def conv_bwd(l, x, dy, dx, add=None):
-            """weight/bias gradient of layer l (input x, output gradient dy) and input gradient -> dx."""
-            L = gl[l]
-            with self._side():
-                K.colsum(V(g[dy]), L.gb)
-                K.wgrad_gemm(L.mode, L.k, V(g[x]), V(g[dy]), L.gw)
-            if dx is not None:
-                mode = {S1: S1, DC: K4, K4: DC}[L.mode]
-                K.conv_gemm(mode, L.k, 1 if L.k == 3 else 0, V(g[dy]), L.Wf, V(g[dx]),
-                            add=None if add is None else V(add), w_kn=True)
-
-        def res_bwd(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out):
-            ds = g["ds"][out]
-            K.act_bwd(g["d_" + out], g[out], ds, K.MASK_RELU)          # gradient at (x + bn(t_c))
-            bn_bwd(bn_c, ds, None, g[t_c], g["d_" + t_c], relu=False)
-            conv_bwd(c_c, u_b, "d_" + t_c, "d_" + u_b)
-            bn_bwd(bn_b, g["d_" + u_b], g[u_b], g[t_b], g["d_" + t_b], relu=True)
-            conv_bwd(c_b, u_a, "d_" + t_b, "d_" + u_a)
-            bn_bwd(bn_a, g["d_" + u_a], g[u_a], g[t_a], g["d_" + t_a], relu=True)
-            conv_bwd(c_a, x, "d_" + t_a, "d_" + x, add=ds)            # skip connection joins here
-
-        bn_bwd(9, g["d_h5"], g["h5"], g["t9"], g["d_t9"], relu=True)
-        conv_bwd("c8", "d3", "d_t9", "d_d3"); conv_bwd("t2", "h4", "d_d3", "d_h4")
-        bn_bwd(8, g["d_h4"], g["h4"], g["t8"], g["d_t8"], relu=True)
-        conv_bwd("c7", "d2", "d_t8", "d_d2"); conv_bwd("t1", "h3", "d_d2", "d_h3")
-        res_bwd("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3")
-        bn_bwd(4, g["d_h2"], None, g["t4"], g["d_t4"], relu=False)
-        conv_bwd("c3", "d1", "d_t4", "d_d1"); conv_bwd("t0", "h1", "d_d1", "d_h1")
+        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wf, V(rows(g["d_h5"])), algo_scale=0.75, w_kn=True,
+                    mask=V(rows(g["h5"])), mask_kind=RELU, stat_sum=self.bn_dbeta[9], stat_dot=self.bn_dot[9],
+                    stat_x=V(rows(g["t9"])))
+        bn_bwd(9, g["d_h5"], g["t9"], g["d_t9"], gl["c8"].gb)
+        conv_bwd("c8", "d3", "d_t9", g["d_d3"], stat_sum=gl["t2"].gb)      # gradient at t2's output: its bias gradient
+        conv_bwd("t2", "h4", "d_d3", g["d_h4"], **relu_of("h4"), **bn_red(8, g["t8"]))
+        bn_bwd(8, g["d_h4"], g["t8"], g["d_t8"], gl["c7"].gb)
+        conv_bwd("c7", "d2", "d_t8", g["d_d2"], stat_sum=gl["t1"].gb)
+        conv_bwd("t1", "h3", "d_d2", g["ds"]["h3"], **relu_of("h3"), **bn_red(7, g["t7"]))
+        res_bwd("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3", **bn_red(4, g["t4"]))
+        bn_bwd(4, g["d_h2"], g["t4"], g["d_t4"], gl["c3"].gb)
+        conv_bwd("c3", "d1", "d_t4", g["d_d1"], stat_sum=gl["t0"].gb)
+        conv_bwd("t0", "h1", "d_d1", g["ds"]["h1"], **relu_of("h1"), **bn_red(3, g["t3"]))
         res_bwd("h0", "c0", "t1", 1, "u1", "c1", "t2", 2, "u2", "c2", "t3", 3, "h1")
+        # BatchNorm 0 normalises per FEATURE of the [B, 16*C8] dense output (model.py:176), not per channel of the
+        # 4x4 map the conv above wrote, so its reductions stay a separate pass
         flat = lambda t: t.view(np_, B, -1)
-        bn_bwd(0, flat(g["d_h0"]), None, flat(g["f0"]), flat(g["d_f0"]), relu=False)
+        K.bn_bwd_reduce(flat(g["d_h0"]), flat(g["f0"]), self.bn_mean[0], self.bn_rstd[0], self.bn_dgamma[0],
+                        self.bn_dbeta[0])
+        K.bn_bwd_apply(flat(g["d_h0"]), flat(g["f0"]), self.bn_mean[0], self.bn_rstd[0], self.bn_gamma[0],
+                       self.bn_dgamma[0], self.bn_dbeta[0], flat(g["d_f0"]))
         L = gl["fc0"]
         with self._side():
             K.colsum(V(flat(g["d_f0"])), L.gb)
@@ -542,9 +582,11 @@ class Engine:
         if not tangent:
             K.dout_fwd(d["a6"][:, s0:s0 + n], dl["out"].w, dl["out"].b, d["logit"][s0:s0 + n])   # :160
 
-    def d_backward(self, s0, n, seed, g0, gn, want_cond_grad):
+    def d_backward(self, s0, n, seed, g0, gn, want_cond_grad, bias_n=0):
         """Seeded backward of d_forward through the inputs of every layer (no weight gradients).
-        Samples [g0, g0+gn) additionally get dD/d image -> d['gx'] (and dD/d cond -> d['g2'])."""
+        Samples [g0, g0+gn) additionally get dD/d image -> d['gx'] (and dD/d cond -> d['g2']).
+        bias_n > 0: the first bias_n samples' output gradients are summed into the bias gradients of the
+        layers by the epilogues that produce them (d_bias_grads covers the two that no GEMM writes)."""
         K, d, dl = self.K, self.d, self.dl
         S1, DC = K.CONV_S1, K.DECONV_K4S2
         rows = self._rows
@@ -554,17 +596,23 @@ class Engine:
         def V(t, **kw):
             return K.View(t, s0, n, **kw)
 
+        def bias_of(l, c=0):    # this GEMM's output is the gradient at layer l's output: column sums = l's bias gradient
+            return dict(stat_sum=dl[l].gb, stat_n=bias_n, stat_c=c) if bias_n > 0 else {}
+
         K.dout_bwd_data(d["a6"][:, s0:s0 + n], dl["out"].w, seed[s0:s0 + n], d["d_a6"][:, s0:s0 + n])
         KN = dict(w_kn=True)    # the packed forward weights, read as [contraction][output channel]
-        K.conv_gemm(S1, 1, 0, V(d["d_a6"]), dl["h6"].Wf, V(d["d_a5"]), mask=V(d["a5"]), mask_kind=LR, **KN)
-        K.conv_gemm(S1, 3, 1, V(d["d_a5"]), dl["h5"].Wf, V(d["d_cat"]), mask=V(d["cat"]), mask_kind=LR, **KN)
+        K.conv_gemm(S1, 1, 0, V(d["d_a6"]), dl["h6"].Wf, V(d["d_a5"]), mask=V(d["a5"]), mask_kind=LR, **KN, **bias_of("h5"))
+        K.conv_gemm(S1, 3, 1, V(d["d_a5"]), dl["h5"].Wf, V(d["d_cat"]), mask=V(d["cat"]), mask_kind=LR, **KN,
+                    **bias_of("r3", df8))
         K.embed_reduce(d["d_cat"][:, s0:s0 + n], d["d_e"][:, s0:s0 + n], df8)
-        K.conv_gemm(S1, 3, 1, V(d["d_cat"], coff=0, c=df8), dl["r3"].Wf, V(d["d_r2"]), mask=V(d["r2"]), mask_kind=LR, **KN)
-        K.conv_gemm(S1, 3, 1, V(d["d_r2"]), dl["r2"].Wf, V(d["d_r1"]), mask=V(d["r1"]), mask_kind=LR, **KN)
-        K.conv_gemm(S1, 1, 0, V(d["d_r1"]), dl["r1"].Wf, V(d["d_a3"]), add=V(d["d_cat"], coff=0, c=df8), **KN)
-        K.conv_gemm(DC, 4, 0, V(d["d_a3"]), dl["h3"].Wf, V(d["d_a2"]), mask=V(d["a2"]), mask_kind=LR, **KN)
-        K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wf, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR, **KN)
-        K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wf, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR, **KN)
+        K.conv_gemm(S1, 3, 1, V(d["d_cat"], coff=0, c=df8), dl["r3"].Wf, V(d["d_r2"]), mask=V(d["r2"]), mask_kind=LR, **KN,
+                    **bias_of("r2"))
+        K.conv_gemm(S1, 3, 1, V(d["d_r2"]), dl["r2"].Wf, V(d["d_r1"]), mask=V(d["r1"]), mask_kind=LR, **KN, **bias_of("r1"))
+        K.conv_gemm(S1, 1, 0, V(d["d_r1"]), dl["r1"].Wf, V(d["d_a3"]), add=V(d["d_cat"], coff=0, c=df8), **KN,
+                    **bias_of("h3"))
+        K.conv_gemm(DC, 4, 0, V(d["d_a3"]), dl["h3"].Wf, V(d["d_a2"]), mask=V(d["a2"]), mask_kind=LR, **KN, **bias_of("h2"))
+        K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wf, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR, **KN, **bias_of("h1"))
+        K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wf, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR, **KN, **bias_of("h0"))
         if gn > 0:
             K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wf,
                         K.View(d["d_col0"], 0, gn * 1024), algo_scale=0.75, **KN)
@@ -593,14 +641,11 @@ class Engine:
             K.wgrad_gemm(dl[l].mode, dl[l].k, K.View(d[x], 0, n), K.View(d[dy], 0, n, **kw), dl[l].gw)
 
     def d_bias_grads(self, n_bias):
-        """Bias gradients of d_net: sums of the output gradients over samples [0, n_bias)."""
+        """Bias gradients of the two d_net layers whose output gradient no GEMM epilogue produces (h6: from
+        dout_bwd_data, efc: from embed_reduce): sums over samples [0, n_bias).  The others: d_backward(bias_n=)."""
         K, d, dl = self.K, self.d, self.dl
-        K.colsum(K.View(self._rows(d["d_a0"]), 0, n_bias * 1024), dl["h0"].gb)
-        for l, (x, dy) in self.D_WGRAD.items():
-            if l in ("h0", "out"):
-                continue
-            kw = dict(coff=0, c=8 * self.df) if l == "r3" else {}
-            K.colsum(K.View(d[dy], 0, n_bias, **kw), dl[l].gb)
+        K.colsum(K.View(d["d_a6"], 0, n_bias), dl["h6"].gb)
+        K.colsum(K.View(d["d_e"], 0, n_bias), dl["efc"].gb)
 
     # ------------------------------------------------------------------ optimizer plumbing
     def _set_lr(self, net, lr, t):
@@ -732,7 +777,7 @@ class Engine:
         self.d_forward(0, S)                                                             # model.py:49-55
         K.d_seeds(self.kt, d["seed"], B, 1.0 / self.GB)
         K.d_sums(d["logit"], B, self.sums["d"])
-        self.d_backward(0, S, d["seed"], 3 * B, B, True)                                 # tf.gradients, :63,68
+        self.d_backward(0, S, d["seed"], 3 * B, B, True, bias_n=3 * B)                   # tf.gradients, :63,68
         inv = 1.0 / self.GB
         K.gp_penalty(d["gx"], GP_WEIGHT, inv, d["slope"], d["coef"], self.sums["d"][4:5])       # :62-65
         K.gp_penalty(d["g2"], GP_WEIGHT, inv, d["slope2"], d["coef2"], self.sums["d"][5:6])     # :67-70
@@ -763,15 +808,14 @@ class Engine:
     def _g_tail(self):
         K = self.K
         K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)        # model.py:92
-        for i, c in enumerate(self.bn_ch):                                               # UPDATE_OPS, :98,102
-            K.bn_update_moving(self.bn_mm[i], self.bn_mv[i], self.bn_mean[i], self.bn_var[i], g_rows(self, i), BN_DECAY)
         self._adam("g")                                                                  # :103-106
 
     def _g_body_fwd(self):
         K, d, g, B = self.K, self.d, self.g, self.B
         cond = self.feed["cond"]
         self.grad["g"].zero_()
-        self.g_forward(g["z"], cond, g["tn"], d["img"][:B], self.sums["g"][1:2])
+        # UPDATE_OPS (moving statistics, model.py:98,102) ride in the BatchNorm kernels of this forward
+        self.g_forward(g["z"], cond, g["tn"], d["img"][:B], self.sums["g"][1:2], update_moving=True)
         K.to_planes(cond, d["cond"][:, :B])
 
     def _g_body(self):
@@ -791,9 +835,3 @@ class Engine:
         self.join_comm()
         vals = self.scalars.detach().cpu().tolist()
         return {n: vals[i] for i, n in enumerate(SCALARS)}
-
-
-def g_rows(eng, i):
-    """number of values per channel the i-th BatchNorm of g_net normalises over"""
-    B = eng.B
-    return [B, 16 * B, 16 * B, 16 * B, 64 * B, 64 * B, 64 * B, 64 * B, 256 * B, 1024 * B][i]

@@ -98,11 +98,14 @@ def _prof_end(ev, kernel, tag, flops, nbytes):
 
 
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
-              algo_scale=1.0, w_kn=False):
+              algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
+              stat_c=0):
     """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, rows, cols].
     w_kn=False: rows = output channels, cols = contraction (forward use of a layer's packed weights);
     w_kn=True : rows = contraction, cols = output channels (the same weights used for the input-gradient).
-    algo_scale: fraction of the contraction that is algorithmic (0.75 for the 48-of-64 patch columns)."""
+    algo_scale: fraction of the contraction that is algorithmic (0.75 for the 48-of-64 patch columns).
+    stat_*: fp32 per-channel accumulators fed by the epilogue (+=): sum of the outputs, sum of squares, or
+    dot with stat_x (a View on the output grid), over samples [0, stat_n) / channels [0, stat_c) (0 = all)."""
     ev = _prof_begin()
     d = _lib.ConvGemmDesc()
     d.mode, d.k, d.flip, d.np = mode, k, flip, x.np
@@ -116,6 +119,11 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     d.add = add._act() if add is not None else _null_act()
     d.mask = mask._act() if mask is not None else _null_act()
     d.act, d.mask_kind = act, mask_kind
+    d.stat_sum = None if stat_sum is None else _f32(stat_sum).value
+    d.stat_sq = None if stat_sq is None else _f32(stat_sq).value
+    d.stat_dot = None if stat_dot is None else _f32(stat_dot).value
+    d.stat_x = stat_x._act() if stat_x is not None else _null_act()
+    d.stat_n, d.stat_c = stat_n, stat_c
     _lib.call("t2i_conv_gemm", C.byref(d), _stream())
     if ev is not None:
         opix = y.n * y.H * y.W
@@ -199,6 +207,23 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
     rows, c = _rows_c(x)
     _lib.call("t2i_bn_apply", _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(beta), _p(residual),
               0 if residual is None else _ps(residual), _p(y), _ps(y), x.shape[0], rows, c, int(relu), _stream())
+
+
+def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
+                   decay=0.9):
+    """sums: fp32 [2c] = [sum x | sum x^2] from conv_gemm(stat_sum=, stat_sq=); moving: (mm, mv) or None."""
+    rows, c = _rows_c(x)
+    mm, mv = moving if moving is not None else (None, None)
+    _lib.call("t2i_bn_apply_train", _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(beta), _p(residual),
+              0 if residual is None else _ps(residual), _p(y), _ps(y), x.shape[0], rows, c, int(relu), _f32(mean),
+              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, _stream())
+
+
+def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None):
+    """dbeta / dot: the reductions conv_gemm(stat_sum=dbeta, stat_dot=dot, stat_x=x) produced with dy."""
+    rows, c = _rows_c(x)
+    _lib.call("t2i_bn_bwd_fused", _p(dy), _ps(dy), _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(dot),
+              _f32(dbeta), _f32(dgamma), _p(dx), _ps(dx), _p(dx_sum), x.shape[0], rows, c, _stream())
 
 
 def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta):
