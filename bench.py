@@ -30,6 +30,16 @@ METRIC = "images/sec (G+D+GP step) 64x64 wgancls"
 GFLOP_PER_IMAGE = 28.585          # 2 * (4 G_f + 15 D_f) MACs per image per iteration
 
 
+def measured_traffic(kernel):
+    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None"""
+    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as f:
+        t = json.load(f)
+    return t.get(kernel, {}).get("dram_bytes_per_launch")
+
+
 def peaks():
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -62,10 +72,18 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
-    def finish(self):
+    def mark(self):
+        """index of the next sample: rows before it were taken outside the timed region"""
+        return len(self.rows)
+
+    def finish(self, first=0, last=None):
         self.stop_flag = True
         if self.proc is not None:
             self.proc.terminate()
+        rows = self.rows[first:last]
+        if len(rows) < 3:      # a very short timed region: fall back to the samples around it (still under load)
+            rows = self.rows[max(0, first - 3):]
+        self.rows = rows
         sm = sorted(int(float(r[0])) for r in self.rows if r and r[0].replace(".", "").isdigit())
         reasons = set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
@@ -182,11 +200,18 @@ def main():
         eng.g["tn"].copy_(tn[1])
         eng.g_step(lr)
 
+    sampler = ClockSampler(local_rank)
+    sampler.start()                      # started before the warm-up: nvidia-smi needs ~0.3 s to deliver its first row
     for _ in range(args.warmup):
         resident_step()
     barrier()
-    sampler = ClockSampler(local_rank)
-    sampler.start()
+    if sampler.mark() == 0:              # keep the GPU loaded until the sampler is live
+        for _ in range(30):
+            resident_step()
+            if sampler.mark() > 0:
+                break
+        barrier()
+    s_first = sampler.mark()
     l0 = _lib.launch_count() + eng.replayed_launches - eng.captured_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -195,7 +220,7 @@ def main():
     e1.record()
     barrier()
     launches = _lib.launch_count() + eng.replayed_launches - eng.captured_launches - l0
-    clocks = sampler.finish()
+    clocks = sampler.finish(s_first, sampler.mark())
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
@@ -266,7 +291,9 @@ def main():
         fl, nb, t, n = agg[top]
         achieved = fl / (t * 1e-3) / 1e12
         roofline = {"kernel": top + "_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
-                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"], "traffic": None,
+                    "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
+                    "traffic": measured_traffic(top + "_kernel"), "traffic_unit": "dram bytes per launch (ncu, mean over the "
+                    "launches of one step; profiles/r01_traffic.json)", "algorithmic_bytes_per_launch": nb / n,
                     "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
                     "launches_per_step": n // psteps, "ms_per_step_in_kernel": t / psteps,
                     "share_of_step": (t / psteps) / ms_per_step,

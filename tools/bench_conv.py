@@ -17,6 +17,13 @@ SHAPES = {
     "t2_dgrad": (K.CONV_K4S2, 4, 0, 256, 32, 32, 128, 256, True),
     "t3_dgrad": (K.CONV_S1, 1, 0, 262144, 1, 1, 64, 128, True),
     "c7_fwd": (K.CONV_S1, 3, 0, 256, 16, 16, 256, 256, False),
+    # small generator layers at batch 256 (launch / latency bound) and a one-k-block launch (fixed cost)
+    "c1_fwd": (K.CONV_S1, 3, 0, 256, 4, 4, 256, 256, False),
+    "c2_fwd": (K.CONV_S1, 3, 0, 256, 4, 4, 256, 1024, False),
+    "c5_fwd": (K.CONV_S1, 3, 0, 256, 8, 8, 128, 128, False),
+    "c3_fwd": (K.CONV_S1, 3, 0, 256, 8, 8, 512, 512, False),
+    "t0_fwd": (K.DECONV_K4S2, 4, 0, 256, 4, 4, 1024, 512, False),
+    "floor": (K.CONV_S1, 1, 0, 256, 8, 8, 64, 128, False),
 }
 
 
@@ -42,6 +49,28 @@ def run(name, variant, reps=int(os.environ.get('REPS', '20')), warm=int(os.envir
         kw.update(stat_dot=s2, stat_x=K.View(sx))
     if "lim" in variant:
         kw.update(stat_n=3 * N // 4)
+    if "chain" in variant:      # 20 back-to-back launches replayed from a CUDA graph: per-launch time in a real step
+        for k2 in ("mask", "mask_kind", "stat_sum", "stat_sq", "stat_dot", "stat_x", "stat_n"):
+            kw.pop(k2, None)
+        K.conv_gemm(mode, k, flip, K.View(x), w, K.View(y), **kw)
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            for _ in range(20):
+                K.conv_gemm(mode, k, flip, K.View(x), w, K.View(y), **kw)
+        ts = []
+        for i in range(8):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b) / 20)
+        ts.sort()
+        flops = 2.0 * N * oh * ow * Co * Ci * (k * k if mode == K.CONV_S1 else 16 if mode == K.CONV_K4S2 else 4)
+        print("%-10s %-18s per launch in a 20-launch graph: median %.4f ms  min %.4f  %.0f TFLOP/s" % (
+            name, variant, ts[len(ts) // 2], ts[0], flops / ts[len(ts) // 2] / 1e9))
+        return
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     ts = []
     for i in range(reps + warm):

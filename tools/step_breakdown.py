@@ -1,0 +1,58 @@
+"""Times the captured CUDA graphs of one wgancls iteration one by one (events on the launch stream), next to the
+algorithmic GEMM FLOPs each contains.  Development aid:  python tools/step_breakdown.py [--batch 256]"""
+import argparse
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+from bench import model_cfg  # noqa: E402
+from t2i_b200.models.wgancls.model import WGanCls  # noqa: E402
+
+G_F, D_F = 969.478e6, 694.305e6      # forward MACs per image
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=256)
+    ap.add_argument("--reps", type=int, default=20)
+    args = ap.parse_args()
+    B = args.batch
+    dev = torch.device("cuda", 0)
+    model = WGanCls(model_cfg(B), precision="bf16", device=dev, use_graphs=True)
+    model.initialize(0)
+    eng = model._train_engine()
+    gen = torch.Generator().manual_seed(1)
+    eng.load_feed(x=torch.rand(B, 64, 64, 3, generator=gen) * 2 - 1, x_mismatch=torch.rand(B, 64, 64, 3, generator=gen) * 2 - 1,
+                  cond=torch.randn(B, 1024, generator=gen), z=torch.randn(B, 128, generator=gen),
+                  epsilon=torch.rand(B, 1, 1, 1, generator=gen), tn_eps=torch.randn(B, 128, generator=gen).clamp_(-2, 2))
+    for _ in range(4):
+        eng.d_step(1e-4)
+        eng.g_step(1e-4)
+    torch.cuda.synchronize()
+    flops = {"d_a1": 2 * G_F * B, "d_a": 2 * 13 * D_F * B, "d_b": 0.0, "g_a1": 2 * G_F * B, "g_a2": 2 * (2 * G_F + 2 * D_F) * B,
+             "g_b": 0.0}
+    total = 0.0
+    for name in ("d_a1", "d_a", "d_b", "g_a1", "g_a2", "g_b"):
+        graph = eng._graphs[name]["graph"]
+        ts = []
+        for _ in range(args.reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        med = ts[len(ts) // 2]
+        total += med
+        print("%-5s %7.3f ms  launches %3d  %s" % (name, med, eng._graphs[name]["launches"],
+                                                  "%.0f TFLOP/s" % (flops[name] / med / 1e9) if flops[name] else ""))
+    print("sum of graphs %.3f ms (serial; the step overlaps d_b with g_a1)" % total)
+
+
+if __name__ == "__main__":
+    main()

@@ -17,6 +17,8 @@ def launches(path):
     lines = [l for l in open(path) if not l.startswith("==")]
     agg = collections.defaultdict(lambda: [0, 0.0])
     for row in csv.DictReader(lines):
+        if row.get("Metric Name", "gpu__time_duration.sum") != "gpu__time_duration.sum":
+            continue
         v = float(row["Metric Value"].replace(",", ""))
         v *= {"ns": 1e-3, "us": 1.0, "usecond": 1.0, "ms": 1e3, "msecond": 1e3, "nsecond": 1e-3}.get(row["Metric Unit"], 1.0)
         k = row["Kernel Name"].split("(")[0]
@@ -27,6 +29,33 @@ def launches(path):
         sum(v[0] for v in agg.values()), tot))
     for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
         print("%-58s n=%4d  us=%9.1f  %5.1f%%" % (k[:58], v[0], v[1], 100 * v[1] / tot))
+
+
+def traffic(path, out_json=None):
+    """dram bytes (read + write) per kernel from a launch list that also collected dram__bytes_{read,write}.sum"""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    agg = collections.defaultdict(lambda: {"launches": set(), "bytes": 0.0, "us": 0.0})
+    for row in csv.DictReader(lines):
+        k = row["Kernel Name"].split("(")[0].replace("void ", "").replace("t2i::", "").split("<")[0]
+        v = float(row["Metric Value"].replace(",", ""))
+        a = agg[k]
+        a["launches"].add(row["ID"])
+        if row["Metric Name"] in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            a["bytes"] += v * scale.get(row["Metric Unit"], 1.0)
+        elif row["Metric Name"] == "gpu__time_duration.sum":
+            a["us"] += v * {"ns": 1e-3, "us": 1.0, "ms": 1e3}.get(row["Metric Unit"], 1.0)
+    res = {}
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["bytes"]):
+        n = len(a["launches"])
+        res[k] = {"launches": n, "dram_bytes_total": a["bytes"], "dram_bytes_per_launch": a["bytes"] / n,
+                  "dram_gbytes_per_s_under_ncu": a["bytes"] / (a["us"] * 1e-6) / 1e9 if a["us"] else None}
+        print("%-34s n=%4d  dram %9.1f MB total  %8.2f MB/launch  %7.0f GB/s (serialised)" % (
+            k[:34], n, a["bytes"] / 1e6, a["bytes"] / n / 1e6, res[k]["dram_gbytes_per_s_under_ncu"] or 0))
+    if out_json:
+        with open(out_json, "w") as f:
+            json.dump(res, f, indent=1)
 
 
 def full(path):
@@ -42,4 +71,7 @@ def full(path):
 
 
 if __name__ == "__main__":
-    (launches if sys.argv[1] == "launches" else full)(sys.argv[2])
+    if sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+    else:
+        (launches if sys.argv[1] == "launches" else full)(sys.argv[2])
