@@ -144,16 +144,21 @@ int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x
  * t2i_conv_gemm's stat_sum / stat_sq); derives mean / biased variance / rstd (written out for the backward
  * pass), applies gamma / beta (+ residual) (+ ReLU), and when moving_mean / moving_var are given also steps the
  * moving statistics (UPDATE_OPS of the G run, model.py:98,102).  t2i_bn_bwd_fused: dbeta = sum dy and
- * dot = sum dy * x were accumulated by the kernel that produced dy (stat_sum / stat_dot);
- * dgamma[c] += rstd * (dot - mean * dbeta); dx as t2i_bn_bwd_apply; dx_sum[c] += sum dx (optional: the bias
- * gradient of the conv in front of the BatchNorm). */
+ * dot = sum dy * x were accumulated by the kernel that produced dy (stat_sum / stat_dot; dot_normalised = 1:
+ * dot already is sum dy * xhat); dgamma[c] += out_scale * rstd * (dot - mean * dbeta);
+ * dbeta_out[c] += out_scale * dbeta (optional); dx as t2i_bn_bwd_apply; dx_sum[c] += sum dx (optional: the bias
+ * gradient of the conv in front of the BatchNorm).
+ * stat_rows (0 = rows): number of values per channel behind the sums when they were all-reduced over the
+ * data-parallel ranks (synchronised BatchNorm = the reference's whole-batch statistics, utils/ops.py:20-29);
+ * out_scale = 1 / world then keeps the later gradient all-reduce(sum) exact. */
 int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
                        const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                        long long rows, int c, int relu, float* mean, float* rstd, float* var, float* moving_mean,
-                       float* moving_var, float decay, void* stream);
+                       float* moving_var, float decay, long long stat_rows, void* stream);
 int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                      const float* rstd, const float* gamma, const float* dot, const float* dbeta, float* dgamma,
-                     void* dx, long long dx_ps, float* dx_sum, int np, long long rows, int c, void* stream);
+                     float* dbeta_out, float out_scale, int dot_normalised, void* dx, long long dx_ps, float* dx_sum,
+                     int np, long long rows, int c, long long stat_rows, void* stream);
 int t2i_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var,
                          long long rows, int c, float decay, void* stream);
 /* dst = dy * act'(y)  (relu / lrelu masks on post-activation values) */

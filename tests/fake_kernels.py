@@ -206,9 +206,9 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 
 
 def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
-                   decay=0.9):
+                   decay=0.9, stat_rows=0):
     c = x.shape[-1]
-    rows = x[0].numel() // c
+    rows = stat_rows if stat_rows > 0 else x[0].numel() // c
     m = sums[:c].double() / rows
     s = torch.clamp(sums[c:2 * c].double() / rows - m * m, min=0)
     mean.copy_(m); var.copy_(s); rstd.copy_(torch.rsqrt(s + eps))
@@ -217,14 +217,18 @@ def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None,
     bn_apply(x, mean, rstd, gamma, beta, y, residual, relu)
 
 
-def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None):
+def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, dbeta_out=None, out_scale=1.0,
+                 dot_normalised=False, stat_rows=0):
     c = x.shape[-1]
-    rows = x[0].numel() // c
-    dg = rstd.double() * (dot.double() - mean.double() * dbeta.double())
-    dgamma += dg
+    rows = stat_rows if stat_rows > 0 else x[0].numel() // c
+    db = dbeta.double().clone()
+    dg = dot.double().clone() if dot_normalised else rstd.double() * (dot.double() - mean.double() * db)
+    dgamma += dg * out_scale
+    if dbeta_out is not None:
+        dbeta_out += db * out_scale
     g = val(dy)
     xh = (val(x) - mean.double()) * rstd.double()
-    out = gamma.double() * rstd.double() * (g - dbeta.double() / rows - xh * dg / rows)
+    out = gamma.double() * rstd.double() * (g - db / rows - xh * dg / rows)
     put(dx, out)
     if dx_sum is not None:
         dx_sum += out.reshape(-1, c).sum(0)

@@ -72,6 +72,79 @@ def _worker(rank, world, port, out):
     dist.destroy_process_group()
 
 
+def _worker_sync_bn(rank, world, port, out):
+    """whole iteration with sync_bn=True on 2 ranks == the single-process iteration on the global batch"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import wgancls_oracle as O
+    from t2i_b200.engine import Engine
+    from test_engine_cpu import TINY, boosted_params
+    torch.set_num_threads(1)
+    cfg = O.OracleCfg(**TINY)
+    gb = cfg.batch_size
+    b = gb // world
+    p = boosted_params(cfg)
+    feed = O.make_feed(cfg, 12, torch.float64)
+    calls = []
+
+    def allreduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    exact = dict(act_dtype=torch.float64, f32_dtype=torch.float64)
+    eng = Engine(fk, "cpu", b, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
+                 cfg.beta1, cfg.beta2, cfg.kl_coeff, world, allreduce, sync_bn=True, **exact)
+    ref = Engine(fk, "cpu", gb, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
+                 cfg.beta1, cfg.beta2, cfg.kl_coeff, **exact)
+    sl = slice(rank * b, (rank + 1) * b)
+    keys = ("x", "x_mismatch", "cond", "z", "epsilon")
+    res = {}
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.set_params_tf(p)
+        e.load_feed(**{k: feed[k][sel] for k in keys}, tn_eps=feed["tn_eps"][sel])
+        e.d_step(cfg.d_lr)
+    res["img"] = float((eng.d["img"][:b] - ref.d["img"][:gb][sl]).abs().max())
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    res["d_grads"] = max(float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)) for n in gf if n.startswith("d_net/"))
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.load_feed(tn_eps=feed["tn_eps_g"][sel])
+        e.g_step(cfg.g_lr)
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    res["g_grads"] = max((float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)), n)
+                         for n in gf if n.startswith("g_net/") and float(gf[n].abs().max()) > 1e-12
+                         and not (n.endswith("biases") and "Conv2d_transpose" not in n and "Conv_9" not in n)
+                         and not n.endswith("dense_2/bias"))     # biases in front of a BatchNorm: exactly-zero gradient
+    sc, scr = eng.scalars_dict(), ref.scalars_dict()
+    res["scalars"] = max(abs(sc[k] - scr[k]) / max(1.0, abs(scr[k])) for k in sc)
+    ps, pf = eng.get_params_tf(), ref.get_params_tf()
+    res["moving"] = max(float((ps[n] - pf[n]).abs().max()) for n in pf if "moving" in n)
+    res["calls"] = calls
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_sync_bn_iteration_equals_single_process(tmp_path):
+    """with synchronised BatchNorm sums the sharded iteration IS the reference's whole-batch
+    iteration (exact storage, so any difference is a logic error)."""
+    out = str(tmp_path / "s.pt")
+    port = 31500 + os.getpid() % 2000
+    mp.spawn(_worker_sync_bn, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["img"] < 1e-10, r
+    assert r["d_grads"] < 1e-8, r
+    assert r["g_grads"][0] < 1e-7, r
+    assert r["scalars"] < 1e-9, r
+    assert r["moving"] < 1e-10, r
+    # D run: 10 BatchNorm layers in the generator forward + 1 gradient all-reduce;
+    # G run: 10 forward + 10 backward BatchNorm all-reduces + 1 gradient all-reduce
+    assert len(r["calls"]) == 11 + 21, r["calls"]
+
+
 def test_two_rank_d_run_equals_single_process(tmp_path):
     out = str(tmp_path / "r.pt")
     port = 29500 + os.getpid() % 2000

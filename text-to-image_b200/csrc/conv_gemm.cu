@@ -701,12 +701,17 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
                         a->w, a->c, y.n, y.h, y.w, y.c);
     const int sms = num_sms();
     // CTA pairs (cta_group::2, 256-pixel tiles) whenever there are at least two pixel tiles
-    static const bool allow_cta2 = [] { const char* e = getenv("T2I_CONV_CTA2"); return !(e && e[0] == '0'); }();
+    const bool allow_cta2 = [] { const char* e = getenv("T2I_CONV_CTA2"); return !(e && e[0] == '0'); }();
     const bool cta2 = allow_cta2 && prm.tiles_m >= 2;
     const int units_m = cta2 ? ceil_div(prm.tiles_m, 2) : prm.tiles_m;     // schedulable pixel tiles (pairs)
     const int workers = cta2 ? sms / 2 : sms;                              // CTAs or CTA pairs
     int block_n = 128;
     if (y.c > 128 && (long long)prm.tt.n_phases * units_m * ceil_div(y.c, 256) >= workers) block_n = 256;
+    {   // tools/bench_conv.py: force the channel tile (development aid)
+        const char* e = getenv("T2I_CONV_BN");
+        if (e && atoi(e) == 256 && y.c > 128) block_n = 256;
+        if (e && atoi(e) == 128) block_n = 128;
+    }
     prm.tiles_co = ceil_div(y.c, block_n);
     prm.total_tiles = prm.tt.n_phases * units_m * prm.tiles_co;
     prm.fd_co = make_fastdiv(prm.tiles_co);

@@ -515,8 +515,9 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
 __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ x,
                                     long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
                                     const float* __restrict__ gamma, const float* __restrict__ dot,
-                                    const float* __restrict__ dbeta, float* dgamma_out, bf16* __restrict__ dx,
-                                    long long dx_ps, float* dx_sum, int np, long long rows, int c, float inv_rows, int CG) {
+                                    const float* __restrict__ dbeta, float* dgamma_out, float* dbeta_out, float out_scale,
+                                    int dot_normalised, bf16* __restrict__ dx, long long dx_ps, float* dx_sum, int np,
+                                    long long rows, int c, float inv_rows, int CG) {
     pdl_launch_dependents();
     __shared__ float sh[256 * 8];
     const int RY = blockDim.x / CG;
@@ -531,8 +532,11 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
             mu[j] = mean[ch + j];
             rs[j] = rstd[ch + j];
             const float db = dbeta[ch + j];
-            const float dg = rs[j] * (dot[ch + j] - mu[j] * db);
-            if (blockIdx.y == 0 && ry == 0) dgamma_out[ch + j] += dg;
+            const float dg = dot_normalised ? dot[ch + j] : rs[j] * (dot[ch + j] - mu[j] * db);
+            if (blockIdx.y == 0 && ry == 0) {
+                dgamma_out[ch + j] += dg * out_scale;
+                if (dbeta_out != nullptr) dbeta_out[ch + j] += db * out_scale;
+            }
             a[j] = gamma[ch + j] * rs[j];
             b0[j] = db * inv_rows;
             b1[j] = dg * inv_rows;
@@ -1011,29 +1015,32 @@ extern "C" int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, 
 extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
                                   const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                                   long long rows, int c, int relu, float* mean, float* rstd, float* var,
-                                  float* moving_mean, float* moving_var, float decay, void* stream) {
+                                  float* moving_mean, float* moving_var, float decay, long long stat_rows, void* stream) {
     if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: c must be a multiple of 8");
     if ((moving_mean == nullptr) != (moving_var == nullptr)) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: moving pair");
     int CG;
     dim3 grid;
     rowwise_geometry(rows, c, 256, &CG, &grid);
-    const float bessel = rows > 1 ? (float)rows / (float)(rows - 1) : 1.f;
+    const long long n = stat_rows > 0 ? stat_rows : rows;     // values per channel behind the sums
+    const float bessel = n > 1 ? (float)n / (float)(n - 1) : 1.f;
     bn_apply_train_kernel<<<grid, 256, 0, STREAM>>>(
-        static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)rows, eps, gamma, beta, static_cast<const bf16*>(residual),
+        static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)n, eps, gamma, beta, static_cast<const bf16*>(residual),
         r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel);
     return check_launch("bn_apply_train");
 }
 extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                                 const float* rstd, const float* gamma, const float* dot, const float* dbeta,
-                                float* dgamma, void* dx, long long dx_ps, float* dx_sum, int np, long long rows, int c,
+                                float* dgamma, float* dbeta_out, float out_scale, int dot_normalised, void* dx,
+                                long long dx_ps, float* dx_sum, int np, long long rows, int c, long long stat_rows,
                                 void* stream) {
     if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: c must be a multiple of 8");
     int CG;
     dim3 grid;
     rowwise_geometry(rows, c, 256, &CG, &grid);
+    const long long n = stat_rows > 0 ? stat_rows : rows;
     bn_bwd_fused_kernel<<<grid, 256, 0, STREAM>>>(
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,
-        static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)rows, CG);
+        dbeta_out, out_scale, dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)n, CG);
     return check_launch("bn_bwd_fused");
 }
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,

@@ -50,7 +50,7 @@ class Layer:
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
-                 f32_dtype=torch.float32, share_from=None, use_graphs=False, concurrent=True):
+                 f32_dtype=torch.float32, share_from=None, use_graphs=False, concurrent=True, sync_bn=False):
         # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
         # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
@@ -58,12 +58,16 @@ class Engine:
         self.Z, self.E, self.ce, self.gf, self.df = z_dim, embed_dim, ce, gf, df
         self.beta1, self.beta2, self.kl_coeff = beta1, beta2, kl_coeff
         self.world, self.allreduce = world, allreduce
+        # sync_bn: all-reduce g_net's BatchNorm sums over the ranks (forward and backward), i.e. normalise over the
+        # GLOBAL batch exactly as the single-device reference does (utils/ops.py:20-29); default: per-replica
+        # statistics and a single all-reduce per optimizer step
+        self.sync_bn = bool(sync_bn) and world > 1
         self.GB = batch * world
         for v in (z_dim, embed_dim, ce, gf, df):
             assert v % 8 == 0, "channel counts must be multiples of 8"
         self.d_t = 0
         self.g_t = 0
-        self.use_graphs = use_graphs and self.dev.type == "cuda"
+        self.use_graphs = use_graphs and self.dev.type == "cuda" and not self.sync_bn   # collectives stay outside graphs
         self._graphs = {}
         self.side_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.comm_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
@@ -388,12 +392,14 @@ class Engine:
         # BatchNorm accumulators fed by the conv epilogues: per layer [sum x | sum x^2] (forward) and
         # sum dy * x (backward), one contiguous buffer cleared by a single memset per generator forward
         tot = sum(self.bn_ch)
-        self.bn_scratch = torch.zeros(3 * tot, **f32)
-        self.bn_fwd_sums, self.bn_dot, off = [], [], 0
+        self.bn_scratch = torch.zeros(4 * tot, **f32)
+        self.bn_fwd_sums, self.bn_bwd_sums, off = [], [], 0
         for c in self.bn_ch:
             self.bn_fwd_sums.append(self.bn_scratch[off:off + 2 * c]); off += 2 * c
-        for c in self.bn_ch:
-            self.bn_dot.append(self.bn_scratch[off:off + c]); off += c
+        for c in self.bn_ch:      # backward: [sum dy | sum dy * x]; the first half is used only under sync_bn / by BN 0
+            self.bn_bwd_sums.append(self.bn_scratch[off:off + 2 * c]); off += 2 * c
+        self.bn_dsum = [t[:c] for t, c in zip(self.bn_bwd_sums, self.bn_ch)]
+        self.bn_dot = [t[c:] for t, c in zip(self.bn_bwd_sums, self.bn_ch)]
         self.feed = {"cond": torch.zeros(B, E, **f32), "epsilon": torch.zeros(B, **f32)}
 
     @staticmethod
@@ -408,9 +414,14 @@ class Engine:
         moving statistics.  Inference (sampler, model.py:57): moving statistics."""
         K = self.K
         if train:
+            stat_rows = 0
+            if self.sync_bn:      # whole-batch statistics: sum the per-rank sums
+                self.allreduce(self.bn_fwd_sums[i])
+                stat_rows = (x[0].numel() // x.shape[-1]) * self.world
             K.bn_apply_train(x, self.bn_fwd_sums[i], BN_EPS, self.bn_gamma[i], self.bn_beta[i], y, self.bn_mean[i],
                              self.bn_rstd[i], self.bn_var[i], residual=residual, relu=relu,
-                             moving=(self.bn_mm[i], self.bn_mv[i]) if update_moving else None, decay=BN_DECAY)
+                             moving=(self.bn_mm[i], self.bn_mv[i]) if update_moving else None, decay=BN_DECAY,
+                             stat_rows=stat_rows)
         else:
             K.bn_apply(x, self.bn_mm[i], torch.rsqrt(self.bn_mv[i] + BN_EPS), self.bn_gamma[i], self.bn_beta[i], y,
                        residual, relu)
@@ -471,14 +482,26 @@ class Engine:
         RELU = K.MASK_RELU
         img = self.d["img"][:B]
 
-        def bn_red(i, x_pre):
-            return dict(stat_sum=self.bn_dbeta[i], stat_dot=self.bn_dot[i], stat_x=V(x_pre))
+        sync = self.sync_bn
 
-        def bn_bwd(i, dy, x_pre, dx, conv_bias_grad):
+        def bn_red(i, x_pre):
+            # sum dy goes straight into the dbeta gradient; under sync_bn into the scratch that is all-reduced first
+            return dict(stat_sum=self.bn_dsum[i] if sync else self.bn_dbeta[i], stat_dot=self.bn_dot[i], stat_x=V(x_pre))
+
+        def bn_bwd(i, dy, x_pre, dx, conv_bias_grad, via_scratch=False, dot_normalised=False):
             """dy: gradient at the BatchNorm output (already masked); dx: gradient at its input = at the output
             of the conv in front, whose bias gradient is the per-channel sum of dx."""
-            K.bn_bwd_fused(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_gamma[i], self.bn_dot[i],
-                           self.bn_dbeta[i], self.bn_dgamma[i], dx, conv_bias_grad)
+            kw = {}
+            if sync:
+                self.allreduce(self.bn_bwd_sums[i])
+                kw = dict(out_scale=1.0 / self.world, stat_rows=(x_pre[0].numel() // x_pre.shape[-1]) * self.world)
+            if sync or via_scratch:
+                K.bn_bwd_fused(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_gamma[i], self.bn_dot[i],
+                               self.bn_dsum[i], self.bn_dgamma[i], dx, conv_bias_grad, dbeta_out=self.bn_dbeta[i],
+                               dot_normalised=dot_normalised, **kw)
+            else:
+                K.bn_bwd_fused(dy, x_pre, self.bn_mean[i], self.bn_rstd[i], self.bn_gamma[i], self.bn_dot[i],
+                               self.bn_dbeta[i], self.bn_dgamma[i], dx, conv_bias_grad)
 
         def conv_bwd(l, x, dy, dx, **epi):
             """weight gradient of layer l (input x, output gradient dy) and its input gradient -> dx (+ epilogue)."""
@@ -505,8 +528,7 @@ class Engine:
         with self._side():
             K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
         K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wf, V(rows(g["d_h5"])), algo_scale=0.75, w_kn=True,
-                    mask=V(rows(g["h5"])), mask_kind=RELU, stat_sum=self.bn_dbeta[9], stat_dot=self.bn_dot[9],
-                    stat_x=V(rows(g["t9"])))
+                    mask=V(rows(g["h5"])), mask_kind=RELU, **bn_red(9, rows(g["t9"])))
         bn_bwd(9, g["d_h5"], g["t9"], g["d_t9"], gl["c8"].gb)
         conv_bwd("c8", "d3", "d_t9", g["d_d3"], stat_sum=gl["t2"].gb)      # gradient at t2's output: its bias gradient
         conv_bwd("t2", "h4", "d_d3", g["d_h4"], **relu_of("h4"), **bn_red(8, g["t8"]))
@@ -521,13 +543,10 @@ class Engine:
         # BatchNorm 0 normalises per FEATURE of the [B, 16*C8] dense output (model.py:176), not per channel of the
         # 4x4 map the conv above wrote, so its reductions stay a separate pass
         flat = lambda t: t.view(np_, B, -1)
-        K.bn_bwd_reduce(flat(g["d_h0"]), flat(g["f0"]), self.bn_mean[0], self.bn_rstd[0], self.bn_dgamma[0],
-                        self.bn_dbeta[0])
-        K.bn_bwd_apply(flat(g["d_h0"]), flat(g["f0"]), self.bn_mean[0], self.bn_rstd[0], self.bn_gamma[0],
-                       self.bn_dgamma[0], self.bn_dbeta[0], flat(g["d_f0"]))
         L = gl["fc0"]
+        K.bn_bwd_reduce(flat(g["d_h0"]), flat(g["f0"]), self.bn_mean[0], self.bn_rstd[0], self.bn_dot[0], self.bn_dsum[0])
+        bn_bwd(0, flat(g["d_h0"]), flat(g["f0"]), flat(g["d_f0"]), L.gb, via_scratch=True, dot_normalised=True)
         with self._side():
-            K.colsum(V(flat(g["d_f0"])), L.gb)
             K.wgrad_gemm(S1, 1, V(g["zc"]), V(flat(g["d_f0"])), L.gw)
         K.conv_gemm(S1, 1, 0, V(flat(g["d_f0"])), L.Wf, V(g["d_zc"]), w_kn=True)
         K.ca_bwd(g["ms"], g["d_zc"], g["tn"], g["d_ms"], self.Z, self.kl_coeff / (self.GB * self.ce))

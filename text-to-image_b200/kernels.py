@@ -210,20 +210,25 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 
 
 def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
-                   decay=0.9):
-    """sums: fp32 [2c] = [sum x | sum x^2] from conv_gemm(stat_sum=, stat_sq=); moving: (mm, mv) or None."""
+                   decay=0.9, stat_rows=0):
+    """sums: fp32 [2c] = [sum x | sum x^2] from conv_gemm(stat_sum=, stat_sq=); moving: (mm, mv) or None;
+    stat_rows: values per channel behind the sums when they were all-reduced over ranks (0 = this tensor's rows)."""
     rows, c = _rows_c(x)
     mm, mv = moving if moving is not None else (None, None)
     _lib.call("t2i_bn_apply_train", _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(beta), _p(residual),
               0 if residual is None else _ps(residual), _p(y), _ps(y), x.shape[0], rows, c, int(relu), _f32(mean),
-              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, _stream())
+              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, stat_rows, _stream())
 
 
-def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None):
-    """dbeta / dot: the reductions conv_gemm(stat_sum=dbeta, stat_dot=dot, stat_x=x) produced with dy."""
+def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, dbeta_out=None, out_scale=1.0,
+                 dot_normalised=False, stat_rows=0):
+    """dbeta / dot: the reductions conv_gemm(stat_sum=dbeta, stat_dot=dot, stat_x=x) produced with dy
+    (dot_normalised: dot = sum dy * xhat, as bn_bwd_reduce writes it).  dgamma += out_scale * (...),
+    dbeta_out += out_scale * dbeta (when the sums live in a scratch that was all-reduced)."""
     rows, c = _rows_c(x)
     _lib.call("t2i_bn_bwd_fused", _p(dy), _ps(dy), _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(dot),
-              _f32(dbeta), _f32(dgamma), _p(dx), _ps(dx), _p(dx_sum), x.shape[0], rows, c, _stream())
+              _f32(dbeta), _f32(dgamma), _p(dbeta_out), out_scale, int(dot_normalised), _p(dx), _ps(dx), _p(dx_sum),
+              x.shape[0], rows, c, stat_rows, _stream())
 
 
 def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta):

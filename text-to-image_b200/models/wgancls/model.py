@@ -47,7 +47,7 @@ def _truncated_normal(shape, device, generator=None):
 
 class WGanCls(object):
     def __init__(self, cfg, build_model=True, precision="bf16", device=None, kernels=None, distributed=None,
-                 use_graphs=True):
+                 use_graphs=True, sync_bn=False):
         """
         Args:
           cfg: Config specifying all the parameters of the model (reference: model.py:6-10).
@@ -58,6 +58,9 @@ class WGanCls(object):
           distributed: None, or a torch.distributed process group handle/True for batch sharding with
             one gradient allreduce per optimizer step.
           use_graphs: capture the D run and the G run into CUDA graphs after their first eager call.
+          sync_bn: with ``distributed``, all-reduce g_net's BatchNorm sums so that the statistics are those of
+            the GLOBAL batch, exactly what the single-device reference computes (utils/ops.py:20-29); default
+            False = per-replica statistics and one all-reduce per optimizer step.
         """
         self.cfg = cfg
 
@@ -98,6 +101,7 @@ class WGanCls(object):
             self._allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         self._engines = {}
         self._use_graphs = use_graphs
+        self._sync_bn = sync_bn
         self._noise_gen = None
         self._built = False
 
@@ -129,7 +133,7 @@ class WGanCls(object):
             self._engines[batch] = Engine(
                 self._K, self.device, batch, self._np, self.z_dim, self.embed_dim, self.compressed_embed_dim,
                 self.gf_dim, self.df_dim, self.cfg.TRAIN.BETA1, self.cfg.TRAIN.BETA2, self.cfg.TRAIN.COEFF.KL,
-                self._world, self._allreduce, share_from=base, use_graphs=self._use_graphs)
+                self._world, self._allreduce, share_from=base, use_graphs=self._use_graphs, sync_bn=self._sync_bn)
         return self._engines[batch]
 
     def _train_engine(self):

@@ -24,6 +24,22 @@ SHAPES = {
     "c3_fwd": (K.CONV_S1, 3, 0, 256, 8, 8, 512, 512, False),
     "t0_fwd": (K.DECONV_K4S2, 4, 0, 256, 4, 4, 1024, 512, False),
     "floor": (K.CONV_S1, 1, 0, 256, 8, 8, 64, 128, False),
+    # the remaining distinct batch-256 shapes of the step (generator + the B-sample discriminator passes)
+    "c0_fwd": (K.CONV_S1, 1, 0, 256, 4, 4, 1024, 256, False),
+    "c4_fwd": (K.CONV_S1, 1, 0, 256, 8, 8, 512, 128, False),
+    "c6_fwd": (K.CONV_S1, 3, 0, 256, 8, 8, 128, 512, False),
+    "t1_fwd": (K.DECONV_K4S2, 4, 0, 256, 8, 8, 512, 256, False),
+    "t2_fwd": (K.DECONV_K4S2, 4, 0, 256, 16, 16, 256, 128, False),
+    "dh1_fwd": (K.CONV_K4S2, 4, 0, 256, 32, 32, 128, 256, False),
+    "dh2_fwd": (K.CONV_K4S2, 4, 0, 256, 16, 16, 256, 512, False),
+    "dh3_fwd": (K.CONV_K4S2, 4, 0, 256, 8, 8, 512, 1024, False),
+    "dr1_fwd": (K.CONV_S1, 1, 0, 256, 4, 4, 1024, 256, False),
+    "dr2_fwd": (K.CONV_S1, 3, 0, 256, 4, 4, 256, 512, False),
+    "dr3_fwd": (K.CONV_S1, 3, 0, 256, 4, 4, 512, 1024, False),
+    "dh5_fwd": (K.CONV_S1, 3, 0, 256, 4, 4, 1152, 1024, False),
+    "dh6_fwd": (K.CONV_S1, 1, 0, 256, 4, 4, 1024, 1024, False),
+    "fc0_fwd": (K.CONV_S1, 1, 0, 256, 1, 1, 256, 16384, False),
+    "fc0_dgrad": (K.CONV_S1, 1, 0, 256, 1, 1, 16384, 256, True),
 }
 
 

@@ -53,6 +53,44 @@ def main():
                                                   "%.0f TFLOP/s" % (flops[name] / med / 1e9) if flops[name] else ""))
     print("sum of graphs %.3f ms (serial; the step overlaps d_b with g_a1)" % total)
 
+    def timed(label, body):
+        body()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            body()
+        ts = []
+        for _ in range(args.reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        print("%-44s %7.3f ms" % (label, ts[len(ts) // 2]))
+
+    g, d = eng.g, eng.d
+    timed("g_forward", lambda: eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"]))
+    timed("g_forward + moving statistics", lambda: eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"],
+                                                                  update_moving=True))
+    timed("_g_body_fwd (fresh capture)", eng._g_body_fwd)
+    timed("_d_body_gen (fresh capture)", eng._d_body_gen)
+    timed("zero g + g_forward(sums tail) ", lambda: (eng.grad["g"].zero_(), eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], eng.sums["g"][1:2])))
+    timed("g_forward + to_planes(cond)", lambda: (eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"]),
+                                                 eng.K.to_planes(eng.feed["cond"], d["cond"][:, :B])))
+    timed("grad[g].zero_", lambda: eng.grad["g"].zero_())
+    timed("grad[d].zero_", lambda: eng.grad["d"].zero_())
+    timed("d_forward(B)", lambda: eng.d_forward(0, B))
+    timed("d_forward(4B)", lambda: eng.d_forward(0, 4 * B))
+    timed("d_backward(B)", lambda: eng.d_backward(0, B, d["gseed"], 0, B, False))
+    timed("d_backward(4B) + bias statistics", lambda: eng.d_backward(0, 4 * B, d["seed"], 3 * B, B, True, bias_n=3 * B))
+    timed("g_backward (side stream joins)", lambda: eng.g_backward(d["gx"]))
+    timed("tangent d_forward(B) + merged wgrad(4B)", lambda: (eng.d_forward(3 * B, B, tangent=True, after=lambda buf: None),
+                                                              [eng.d_wgrad_layer(l, 4 * B, 3 * B) for l in eng.D_WGRAD]))
+    timed("merged wgrad(4B) alone", lambda: [eng.d_wgrad_layer(l, 4 * B, 3 * B) for l in eng.D_WGRAD])
+    timed("adam d", lambda: eng._adam("d"))
+
 
 if __name__ == "__main__":
     main()
