@@ -80,6 +80,7 @@ static inline int grid_for(long long work_items, int threads, int max_blocks_per
 __global__ void to_planes_kernel(const float* __restrict__ src, bf16* dst, long long ps, int np, long long rows,
                                  int cols, const float* __restrict__ row_scale) {
     pdl_launch_dependents();
+    pdl_wait();
     const long long n8 = rows * cols / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         const long long e = i * 8;
@@ -96,6 +97,7 @@ __global__ void to_planes_kernel(const float* __restrict__ src, bf16* dst, long 
 }
 __global__ void from_planes_kernel(const bf16* __restrict__ src, long long ps, int np, float* dst, long long n) {
     pdl_launch_dependents();
+    pdl_wait();
     const long long n8 = n / 8;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         float v[8];
@@ -108,58 +110,108 @@ __global__ void from_planes_kernel(const bf16* __restrict__ src, long long ps, i
 // ------------------------------------------------------------------------------------------
 // 3-channel 4x4/s2 patch matrix.  Row r = (n, p, q) of the (h/2 x w/2) grid, column
 // (kh*4 + kw)*3 + c holds img[n, 2p-1+kh, 2q-1+kw, c] (zero outside); columns 48..63 are zero.
+// A block stages the 2*PR + 2 image rows that PR rows of patches need in shared memory (coalesced 16 B loads,
+// each image row read ~1.25 times instead of 2 x 12 scattered scalars per patch), then every thread assembles
+// 16-byte chunks of patch rows from it.
+constexpr int kIm2colPR = 4;
 __global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, int n, int h, int w,
                                       const float* __restrict__ sample_scale, bf16* col, long long ps, int np) {
     pdl_launch_dependents();
-    const int hp = h / 2, wq = w / 2;
-    const long long rows = (long long)n * hp * wq;
-    const long long items = rows * 8;   // one thread per (row, chunk of 8 columns): one 16 B store per plane
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-        const long long r = i >> 3;
-        const int chunk = (int)(i & 7);
-        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-        if (chunk < 6) {
-            const int q = (int)(r % wq);
-            const int p = (int)((r / wq) % hp);
-            const int b = (int)(r / ((long long)wq * hp));
-            const float s = sample_scale ? sample_scale[b] : 1.f;
-            const float* base = img + (long long)b * h * w * 3;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int colj = chunk * 8 + j;
-                const int tap = colj / 3, c = colj - tap * 3;
-                const int ih = 2 * p - 1 + (tap >> 2), iw = 2 * q - 1 + (tap & 3);
-                if (ih >= 0 && ih < h && iw >= 0 && iw < w) v[j] = __ldg(base + ((long long)ih * w + iw) * 3 + c) * s;
-            }
+    pdl_wait();
+    extern __shared__ float s_rows[];             // [2*PR + 2][w*3]
+    const int hp = h / 2, wq = w / 2, rw = w * 3;
+    const int groups = (hp + kIm2colPR - 1) / kIm2colPR;
+    for (int blk = blockIdx.x; blk < n * groups; blk += gridDim.x) {
+        const int b = blk / groups, p0 = (blk - b * groups) * kIm2colPR;
+        const float sc = sample_scale ? sample_scale[b] : 1.f;
+        const float* base = img + (long long)b * h * rw;
+        const int ih0 = 2 * p0 - 1;
+        __syncthreads();                          // the previous group's readers are done
+        for (int i = threadIdx.x; i < (2 * kIm2colPR + 2) * (rw / 4); i += blockDim.x) {
+            const int r = i / (rw / 4), c4 = i - r * (rw / 4);
+            const int ih = ih0 + r;
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (ih >= 0 && ih < h) v = __ldg(reinterpret_cast<const float4*>(base + (long long)ih * rw) + c4);
+            v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+            reinterpret_cast<float4*>(s_rows + r * rw)[c4] = v;
         }
-        store8(col + r * 64 + chunk * 8, ps, np, v);
+        __syncthreads();
+        const int pr = min(kIm2colPR, hp - p0);
+        for (int i = threadIdx.x; i < pr * wq * 8; i += blockDim.x) {
+            const int chunk = i & 7, q = (i >> 3) % wq, pl = (i >> 3) / wq;
+            float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+            if (chunk < 6) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const int colj = chunk * 8 + j;
+                    const int kh = colj / 12, rem = colj - kh * 12;      // rem = kw*3 + c
+                    const int x0 = (2 * q - 1) * 3 + rem;               // float index inside the image row
+                    if (x0 >= 0 && x0 < rw) v[j] = s_rows[(2 * pl + kh) * rw + x0];
+                }
+            }
+            const long long r = ((long long)b * hp + p0 + pl) * wq + q;
+            store8(col + r * 64 + chunk * 8, ps, np, v);
+        }
     }
 }
 // transpose of the above: img[n, oh, ow, c] = bias[c] + sum over (kh,kw) col[(n,p,q), (kh*4+kw)*3+c]
 // with oh = 2p-1+kh, ow = 2q-1+kw.
+// A block produces kCol2imR image rows: it stages the R/2 + 2 rows of patches they gather from in shared memory
+// (16 B loads), then each thread sums the (up to) four patches that reach one pixel.
+constexpr int kCol2imR = 16;
 __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps, int np, int n, int h, int w,
                                       const float* __restrict__ bias3, float* img) {
     pdl_launch_dependents();
+    pdl_wait();
+    extern __shared__ float s_col[];               // [R/2 + 2][wq][48] fp32 values of the patch rows
     const int hp = h / 2, wq = w / 2;
-    const long long pixels = (long long)n * h * w;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
-        const int ow = (int)(i % w);
-        const int oh = (int)((i / w) % h);
-        const int b = (int)(i / ((long long)w * h));
-        float acc[3] = {0.f, 0.f, 0.f};
-        if (bias3) { acc[0] = bias3[0]; acc[1] = bias3[1]; acc[2] = bias3[2]; }
-        for (int kh = (oh + 1) & 1; kh < 4; kh += 2) {
-            const int p = (oh + 1 - kh) / 2;
-            if (p < 0 || p >= hp) continue;
-            for (int kw = (ow + 1) & 1; kw < 4; kw += 2) {
-                const int q = (ow + 1 - kw) / 2;
-                if (q < 0 || q >= wq) continue;
-                const bf16* src = col + (((long long)b * hp + p) * wq + q) * 64 + (kh * 4 + kw) * 3;
-                for (int c = 0; c < 3; ++c) acc[c] += load1(src + c, ps, np);
+    const int groups = (h + kCol2imR - 1) / kCol2imR;
+    constexpr int PRows = kCol2imR / 2 + 2;
+    const float b0 = bias3 ? bias3[0] : 0.f, b1 = bias3 ? bias3[1] : 0.f, b2 = bias3 ? bias3[2] : 0.f;
+    for (int blk = blockIdx.x; blk < n * groups; blk += gridDim.x) {
+        const int b = blk / groups, oh0 = (blk - b * groups) * kCol2imR;
+        const int pbase = oh0 / 2 - 1;             // first patch row that can reach image row oh0
+        __syncthreads();
+        const int total = PRows * wq * 6;
+        for (int base = 0; base < total; base += blockDim.x * 4) {      // four 16-byte loads in flight per thread
+            float v[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * blockDim.x + threadIdx.x;
+                const int chunk = i % 6, q = (i / 6) % wq, pl = i / (6 * wq);
+                const int p = pbase + pl;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
+                if (i < total && p >= 0 && p < hp) load8(col + (((long long)b * hp + p) * wq + q) * 64 + chunk * 8, ps, np, v[u]);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const int i = base + u * blockDim.x + threadIdx.x;
+                if (i < total) {
+                    float* dst = s_col + (long long)(i / 6) * 48 + (i % 6) * 8;     // (pl * wq + q) * 48 + chunk * 8
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dst[j] = v[u][j];
+                }
             }
         }
-        float* dst = img + i * 3;
-        dst[0] = acc[0]; dst[1] = acc[1]; dst[2] = acc[2];
+        __syncthreads();
+        const int rows = min(kCol2imR, h - oh0);
+        for (int i = threadIdx.x; i < rows * w; i += blockDim.x) {
+            const int ow = i % w, oh = oh0 + i / w;
+            float acc0 = b0, acc1 = b1, acc2 = b2;
+            for (int kh = (oh + 1) & 1; kh < 4; kh += 2) {
+                const int p = (oh + 1 - kh) / 2;
+                if (p < 0 || p >= hp) continue;
+                for (int kw = (ow + 1) & 1; kw < 4; kw += 2) {
+                    const int q = (ow + 1 - kw) / 2;
+                    if (q < 0 || q >= wq) continue;
+                    const float* src = s_col + ((long long)(p - pbase) * wq + q) * 48 + (kh * 4 + kw) * 3;
+                    acc0 += src[0]; acc1 += src[1]; acc2 += src[2];
+                }
+            }
+            float* dst = img + (((long long)b * h + oh) * w + ow) * 3;
+            dst[0] = acc0; dst[1] = acc1; dst[2] = acc2;
+        }
     }
 }
 
@@ -168,6 +220,7 @@ __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps
 __global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                            const float* __restrict__ b, float* y, int n, int h, int wd) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sw[81 + 3];
     if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
     if (threadIdx.x < 3) sw[81 + threadIdx.x] = b[threadIdx.x];
@@ -200,79 +253,105 @@ __global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const fl
         y[i * 3 + 2] = tanhf(acc[2]);
     }
 }
-// backward: dl = dy * (1 - y^2); dx = conv^T(dl); dw[kh,kw,ci,co] += sum x[.+k-1, ci] dl[., co]; db += sum dl
-__global__ void conv3x3_c3_tanh_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                           const float* __restrict__ y, const float* __restrict__ dy, float* dx,
-                                           float* dw, float* db, float* dx_sum, int n, int h, int wd) {
+// backward: dl = dy * (1 - y^2); dx = conv^T(dl); dw[kh,kw,ci,co] += sum x[.+k-1, ci] dl[., co]; db += sum dl.
+// A block walks tiles of kC9R image rows: x and dl (with a one-pixel halo) are staged in shared memory once, each
+// thread then forms dx and its 81 weight-gradient products for its pixels from shared memory; the weight / bias
+// sums stay in registers across all tiles of the block and are reduced once at the end.
+constexpr int kC9R = 8;
+__global__ void __launch_bounds__(256) conv3x3_c3_tanh_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                                  const float* __restrict__ y, const float* __restrict__ dy,
+                                                                  float* dx, float* dw, float* db, float* dx_sum, int n, int h,
+                                                                  int wd) {
     pdl_launch_dependents();
-    __shared__ float sw[81];
-    __shared__ float sred[87];
+    pdl_wait();
+    extern __shared__ float s_c9[];               // x tile [(R+2)][(wd+2)*3], dl tile the same, then w[81], red[87]
+    const int tw = (wd + 2) * 3;
+    float* s_x = s_c9;
+    float* s_dl = s_x + (kC9R + 2) * tw;
+    float* sw = s_dl + (kC9R + 2) * tw;
+    float* sred = sw + 81;
     if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
     if (threadIdx.x < 87) sred[threadIdx.x] = 0.f;
-    __syncthreads();
     float gw[81];
     float gb[3] = {0.f, 0.f, 0.f};
     float gs[3] = {0.f, 0.f, 0.f};
 #pragma unroll
     for (int j = 0; j < 81; ++j) gw[j] = 0.f;
-    const long long pixels = (long long)n * h * wd;
-    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
-        const int ow = (int)(i % wd);
-        const int oh = (int)((i / wd) % h);
-        const long long base = i - (long long)oh * wd - ow;
-        // this pixel as an OUTPUT position: weight/bias gradient contributions
-        float dl[3];
+    const int groups = (h + kC9R - 1) / kC9R;
+    for (int blk = blockIdx.x; blk < n * groups; blk += gridDim.x) {
+        const int b = blk / groups, r0 = (blk - b * groups) * kC9R;
+        const long long ibase = (long long)b * h * wd * 3;
+        __syncthreads();
+        // staging: 8 elements x 3 tensors per thread with all loads issued before the first use (one memory latency
+        // per tile; a one-load-at-a-time loop left the block, 8 warps on the SM, waiting 8 latencies)
+        const int total = (kC9R + 2) * tw;
+        for (int base = 0; base < total; base += blockDim.x * 8) {
+            float xv[8], yv[8], dv[8];
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-            const float yv = y[i * 3 + c];
-            dl[c] = dy[i * 3 + c] * (1.f - yv * yv);
-            gb[c] += dl[c];
-        }
-        // this pixel as an INPUT position: dx[i, ci] = sum_k dl[i - (k-1), co] w[k, ci, co]
-        float gx[3] = {0.f, 0.f, 0.f};
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * blockDim.x + threadIdx.x;
+                const int r = i / tw, cc = i - r * tw;
+                const int ih = r0 - 1 + r, iw3 = cc - 3;          // float index inside the image row
+                const bool ok = i < total && ih >= 0 && ih < h && iw3 >= 0 && iw3 < wd * 3;
+                const long long e = ok ? ibase + (long long)ih * wd * 3 + iw3 : 0;
+                xv[u] = ok ? __ldg(x + e) : 0.f;
+                yv[u] = ok ? __ldg(y + e) : 0.f;
+                dv[u] = ok ? __ldg(dy + e) : 0.f;
+            }
 #pragma unroll
-        for (int kh = 0; kh < 3; ++kh) {
-#pragma unroll
-            for (int kw = 0; kw < 3; ++kw) {
-                const int ih = oh + kh - 1, iw = ow + kw - 1;   // input read by output i through tap (kh,kw)
-                if (ih >= 0 && ih < h && iw >= 0 && iw < wd) {
-                    const float* xp = x + (base + (long long)ih * wd + iw) * 3;
-#pragma unroll
-                    for (int ci = 0; ci < 3; ++ci) {
-                        const float xv = xp[ci];
-#pragma unroll
-                        for (int co = 0; co < 3; ++co) gw[(kh * 3 + kw) * 9 + ci * 3 + co] += xv * dl[co];
-                    }
-                }
-                const int oh2 = oh - kh + 1, ow2 = ow - kw + 1;  // output that reads input i through (kh,kw)
-                if (oh2 >= 0 && oh2 < h && ow2 >= 0 && ow2 < wd) {
-                    const long long o = base + (long long)oh2 * wd + ow2;
-                    const float* wp = sw + (kh * 3 + kw) * 9;
-#pragma unroll
-                    for (int co = 0; co < 3; ++co) {
-                        const float yv = y[o * 3 + co];
-                        const float d = dy[o * 3 + co] * (1.f - yv * yv);
-#pragma unroll
-                        for (int ci = 0; ci < 3; ++ci) gx[ci] += d * wp[ci * 3 + co];
-                    }
+            for (int u = 0; u < 8; ++u) {
+                const int i = base + u * blockDim.x + threadIdx.x;
+                if (i < total) {
+                    s_x[i] = xv[u];
+                    s_dl[i] = dv[u] * (1.f - yv[u] * yv[u]);
                 }
             }
         }
-        dx[i * 3 + 0] = gx[0]; dx[i * 3 + 1] = gx[1]; dx[i * 3 + 2] = gx[2];
-        gs[0] += gx[0]; gs[1] += gx[1]; gs[2] += gx[2];
+        __syncthreads();
+        const int rows = min(kC9R, h - r0);
+        for (int i = threadIdx.x; i < rows * wd; i += blockDim.x) {
+            const int ow = i % wd, lr = i / wd;                   // pixel (r0 + lr, ow); halo offset +1 in both directions
+            const float* cx = s_x + (lr + 1) * tw + (ow + 1) * 3;
+            const float* cd = s_dl + (lr + 1) * tw + (ow + 1) * 3;
+            const float d0 = cd[0], d1 = cd[1], d2 = cd[2];       // dl of this pixel as an OUTPUT position
+            gb[0] += d0; gb[1] += d1; gb[2] += d2;
+            float g0 = 0.f, g1 = 0.f, g2 = 0.f;
+#pragma unroll
+            for (int kh = 0; kh < 3; ++kh) {
+#pragma unroll
+                for (int kw = 0; kw < 3; ++kw) {
+                    const int off = (kh - 1) * tw + (kw - 1) * 3;
+                    const float* wp = sw + (kh * 3 + kw) * 9;
+                    // input read by this output through tap (kh, kw): weight gradient (zero halo = padding)
+                    const float x0 = cx[off], x1 = cx[off + 1], x2 = cx[off + 2];
+                    float* gp = gw + (kh * 3 + kw) * 9;
+                    gp[0] += x0 * d0; gp[1] += x0 * d1; gp[2] += x0 * d2;
+                    gp[3] += x1 * d0; gp[4] += x1 * d1; gp[5] += x1 * d2;
+                    gp[6] += x2 * d0; gp[7] += x2 * d1; gp[8] += x2 * d2;
+                    // output that reads this pixel as input through tap (kh, kw): input gradient
+                    const float e0 = cd[-off], e1 = cd[-off + 1], e2 = cd[-off + 2];
+                    g0 += e0 * wp[0] + e1 * wp[1] + e2 * wp[2];
+                    g1 += e0 * wp[3] + e1 * wp[4] + e2 * wp[5];
+                    g2 += e0 * wp[6] + e1 * wp[7] + e2 * wp[8];
+                }
+            }
+            float* dst = dx + ibase + ((long long)(r0 + lr) * wd + ow) * 3;
+            dst[0] = g0; dst[1] = g1; dst[2] = g2;
+            gs[0] += g0; gs[1] += g1; gs[2] += g2;
+        }
     }
     const int lane = threadIdx.x & 31;
 #pragma unroll
     for (int j = 0; j < 81; ++j) {
-        const float s = warp_sum(gw[j]);
-        if (lane == 0) atomicAdd(&sred[j], s);
+        const float t = warp_sum(gw[j]);
+        if (lane == 0) atomicAdd(&sred[j], t);
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float s = warp_sum(gb[c]);
-        if (lane == 0) atomicAdd(&sred[81 + c], s);
-        const float s2 = warp_sum(gs[c]);
-        if (lane == 0) atomicAdd(&sred[84 + c], s2);
+        const float t = warp_sum(gb[c]);
+        if (lane == 0) atomicAdd(&sred[81 + c], t);
+        const float t2 = warp_sum(gs[c]);
+        if (lane == 0) atomicAdd(&sred[84 + c], t2);
     }
     __syncthreads();
     if (threadIdx.x < 81) atomicAdd(&dw[threadIdx.x], sred[threadIdx.x]);
@@ -291,6 +370,7 @@ __global__ void col_reduce_kernel(const bf16* __restrict__ a, long long a_ps, co
                                   const float* __restrict__ mean, const float* __restrict__ rstd, int np,
                                   long long rows, int c, int pitch, int coff, int CG, float* out0, float* out1) {
     pdl_launch_dependents();
+    pdl_wait();
     extern __shared__ float sh[];  // [2][RY][CG*8]
     const int RY = blockDim.x / CG;
     const int cgl = threadIdx.x % CG, ry = threadIdx.x / CG;
@@ -360,7 +440,7 @@ static int launch_col_reduce(const void* a, long long a_ps, const void* x, long 
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
     const size_t shm = (size_t)2 * RY * CG * 8 * sizeof(float);
-    col_reduce_kernel<MODE><<<dim3(gx, (unsigned)gy), threads, shm, stream>>>(
+    launch_ew(col_reduce_kernel<MODE>, dim3(dim3(gx, (unsigned)gy)), dim3(threads), shm, stream, 
         static_cast<const bf16*>(a), a_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, np, rows, c, pitch, coff, CG,
         out0, out1);
     return check_launch("col_reduce_kernel");
@@ -371,6 +451,7 @@ static int launch_col_reduce(const void* a, long long a_ps, const void* x, long 
 // the accumulators are re-zeroed here so that the next bn_stats call needs no memset.
 __global__ void bn_finalize_kernel(float* sums, float* mean, float* var, float* rstd, int c, float inv_rows, float eps) {
     pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     const float m = sums[i] * inv_rows;
@@ -390,6 +471,7 @@ __global__ void bn_apply_kernel(const bf16* __restrict__ x, long long x_ps, cons
                                 const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
                                 bf16* __restrict__ y, long long y_ps, int np, long long rows, int c, int relu, int CG) {
     pdl_launch_dependents();
+    pdl_wait();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
     const int ry = threadIdx.x / CG;
@@ -428,6 +510,7 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
                                     const float* __restrict__ dbeta, bf16* __restrict__ dx, long long dx_ps, int np,
                                     long long rows, int c, float inv_rows, int CG) {
     pdl_launch_dependents();
+    pdl_wait();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
     const int ry = threadIdx.x / CG;
@@ -465,6 +548,7 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
                                       float* mean_out, float* rstd_out, float* var_out, float* mm, float* mv, float decay,
                                       float bessel) {
     pdl_launch_dependents();
+    pdl_wait();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
     const int ry = threadIdx.x / CG;
@@ -519,6 +603,7 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
                                     int dot_normalised, bf16* __restrict__ dx, long long dx_ps, float* dx_sum, int np,
                                     long long rows, int c, float inv_rows, int CG) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[256 * 8];
     const int RY = blockDim.x / CG;
     const int cgl = threadIdx.x % CG;
@@ -588,6 +673,7 @@ static inline void rowwise_geometry(long long rows, int c, int threads, int* CG,
 __global__ void bn_update_moving_kernel(float* mm, float* mv, const float* mean, const float* var, int c, float decay,
                                         float bessel) {
     pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= c) return;
     mm[i] = decay * mm[i] + (1.f - decay) * mean[i];
@@ -597,6 +683,7 @@ __global__ void bn_update_moving_kernel(float* mm, float* mv, const float* mean,
 __global__ void act_bwd_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ y, long long y_ps,
                                bf16* dst, long long dst_ps, int np, long long n8, float neg) {
     pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         float g[8], a[8];
         load8(dy + i * 8, dy_ps, np, g);
@@ -612,6 +699,7 @@ __global__ void act_bwd_kernel(const bf16* __restrict__ dy, long long dy_ps, con
 __global__ void embed_tile_kernel(const bf16* __restrict__ e, long long e_ps, bf16* cat, long long cat_ps, int np, int s,
                                   int c, int pitch, int coff, int hw) {
     pdl_launch_dependents();
+    pdl_wait();
     const int cg = c / 8;
     const long long items = (long long)s * hw * cg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -626,6 +714,7 @@ __global__ void embed_tile_kernel(const bf16* __restrict__ e, long long e_ps, bf
 __global__ void embed_reduce_kernel(const bf16* __restrict__ dcat, long long dcat_ps, bf16* de, long long de_ps, int np,
                                     int s, int c, int pitch, int coff, int hw) {
     pdl_launch_dependents();
+    pdl_wait();
     const int cg = c / 8;
     const long long items = (long long)s * cg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -647,6 +736,7 @@ __global__ void embed_reduce_kernel(const bf16* __restrict__ dcat, long long dca
 __global__ void dout_fwd_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ w,
                                 const float* __restrict__ b, float* logit, int k) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[32];
     const long long s = blockIdx.x;
     float acc = 0.f;
@@ -663,6 +753,7 @@ __global__ void dout_fwd_kernel(const bf16* __restrict__ a, long long a_ps, int 
 __global__ void dout_bwd_data_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ w,
                                      const float* __restrict__ seed, bf16* da, long long da_ps, int s, int k) {
     pdl_launch_dependents();
+    pdl_wait();
     const int kg = k / 8;
     const long long items = (long long)s * kg;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
@@ -683,6 +774,7 @@ __global__ void dout_bwd_data_kernel(const bf16* __restrict__ a, long long a_ps,
 __global__ void dout_bwd_weight_kernel(const bf16* __restrict__ a, long long a_ps, int np, const float* __restrict__ seed,
                                        float* dw, int s, int k) {
     pdl_launch_dependents();
+    pdl_wait();
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g * 8 >= k) return;
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
@@ -698,6 +790,7 @@ __global__ void dout_bwd_weight_kernel(const bf16* __restrict__ a, long long a_p
 }
 __global__ void seed_sum_kernel(const float* __restrict__ seed, int n, float* out) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < n; i += blockDim.x) acc += seed[i];
@@ -710,6 +803,7 @@ __global__ void seed_sum_kernel(const float* __restrict__ seed, int n, float* ou
 __global__ void gp_interp_kernel(const float* __restrict__ g, const float* __restrict__ x, const float* __restrict__ eps,
                                  float* xhat, long long n4, int per_sample4) {
     pdl_launch_dependents();
+    pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
         const float e = eps[i / per_sample4];
         const float4 a = reinterpret_cast<const float4*>(g)[i];
@@ -723,6 +817,7 @@ __global__ void gp_interp_kernel(const float* __restrict__ g, const float* __res
 __global__ void gp_penalty_kernel(const float* __restrict__ grad, int per_sample, float weight, float inv_batch,
                                   float* slope, float* coef, float* pen_sum) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[32];
     const long long b = blockIdx.x;
     const float* gp = grad + b * per_sample;
@@ -747,6 +842,7 @@ __global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
                               const float* __restrict__ tn, bf16* zc, long long zc_ps, int np, int b, int z_dim, int ce,
                               float* kl_sum) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[32];
     const int width = z_dim + ce;
     float kl = 0.f;
@@ -773,6 +869,7 @@ __global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
                               const float* __restrict__ tn, bf16* dms, long long dms_ps, int np, int b, int z_dim, int ce,
                               float kl_scale) {
     pdl_launch_dependents();
+    pdl_wait();
     const int width = z_dim + ce;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < (long long)b * ce;
          i += (long long)gridDim.x * blockDim.x) {
@@ -794,6 +891,7 @@ __global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
 // scalars
 __global__ void d_seeds_kernel(const float* kt, float* seed, int b, float inv_gb) {
     pdl_launch_dependents();
+    pdl_wait();
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= 4 * b) return;
     const float k = kt[0];
@@ -803,6 +901,7 @@ __global__ void d_seeds_kernel(const float* kt, float* seed, int b, float inv_gb
 }
 __global__ void d_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[32];
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int i = threadIdx.x; i < b; i += blockDim.x) {
@@ -819,6 +918,7 @@ __global__ void d_sums_kernel(const float* __restrict__ logit, int b, float* sum
 }
 __global__ void d_scalars_kernel(const float* sums, float* kt, float* sc, float inv_gb, float gp_weight, float kt_lr) {
     pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float fake = sums[0] * inv_gb, real = sums[1] * inv_gb, mis = sums[2] * inv_gb;
     const float reg = sums[3] * inv_gb, gp = sums[4] * inv_gb, gp2 = sums[5] * inv_gb;
@@ -843,6 +943,7 @@ __global__ void d_scalars_kernel(const float* sums, float* kt, float* sc, float 
 }
 __global__ void g_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float sh[32];
     float acc = 0.f;
     for (int i = threadIdx.x; i < b; i += blockDim.x) acc += logit[i];
@@ -851,6 +952,7 @@ __global__ void g_sums_kernel(const float* __restrict__ logit, int b, float* sum
 }
 __global__ void g_scalars_kernel(const float* sums, float* sc, float inv_gb, float inv_gb_ce, float kl_coeff) {
     pdl_launch_dependents();
+    pdl_wait();
     if (threadIdx.x != 0 || blockIdx.x != 0) return;
     const float fake = sums[0] * inv_gb;
     const float kl = sums[1] * inv_gb_ce;
@@ -863,6 +965,7 @@ __global__ void g_scalars_kernel(const float* sums, float* sc, float inv_gb, flo
 __global__ void pack_weight_kernel(const float* __restrict__ w, int cout, int cin, bf16* fwd, long long fwd_ps, bf16* bwd,
                                    long long bwd_ps, int np) {
     pdl_launch_dependents();
+    pdl_wait();
     __shared__ float tile[32][33];
     const int tap = blockIdx.z;
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
@@ -889,6 +992,7 @@ __global__ void adam_tf_kernel(float* theta, const float* __restrict__ grad, flo
                                const float* __restrict__ lr_t_dev, float b1, float b2, float eps, float gs, bf16* packed,
                                long long packed_ps, int np) {
     pdl_launch_dependents();
+    pdl_wait();
     const float lr_t = lr_t_dev[0];
     const long long n8 = n / 8;
     const bool use_m = (b1 != 0.f);
@@ -941,35 +1045,55 @@ using namespace t2i;
 extern "C" int t2i_to_planes(const float* src, void* dst, long long ps, int np, long long rows, int cols,
                              const float* row_scale, void* stream) {
     if ((rows * cols) % 8 != 0 || cols % 8 != 0) return fail(T2I_ERR_BAD_ARG, "to_planes: cols must be a multiple of 8");
-    to_planes_kernel<<<grid_for(rows * cols / 8, 256), 256, 0, STREAM>>>(src, static_cast<bf16*>(dst), ps, np, rows, cols, row_scale);
+    launch_ew(to_planes_kernel, dim3(grid_for(rows * cols / 8, 256)), dim3(256), 0, STREAM, src, static_cast<bf16*>(dst), ps, np, rows, cols, row_scale);
     return check_launch("to_planes");
 }
 extern "C" int t2i_from_planes(const void* src, long long ps, int np, float* dst, long long n, void* stream) {
     if (n % 8 != 0) return fail(T2I_ERR_BAD_ARG, "from_planes: n must be a multiple of 8");
-    from_planes_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(static_cast<const bf16*>(src), ps, np, dst, n);
+    launch_ew(from_planes_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, STREAM, static_cast<const bf16*>(src), ps, np, dst, n);
     return check_launch("from_planes");
 }
 extern "C" int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sample_scale, void* col,
                                   long long ps, int np, void* stream) {
     if ((h & 1) || (w & 1)) return fail(T2I_ERR_BAD_ARG, "im2col: odd extent");
-    const long long items = (long long)n * (h / 2) * (w / 2) * 8;
-    im2col_k4s2_c3_kernel<<<grid_for(items, 256, 16), 256, 0, STREAM>>>(img, n, h, w, sample_scale, static_cast<bf16*>(col), ps, np);
+    if (w % 4) return fail(T2I_ERR_BAD_ARG, "im2col: w must be a multiple of 4");
+    const size_t shm = (size_t)(2 * kIm2colPR + 2) * w * 3 * sizeof(float);
+    if (shm > 48 * 1024) return fail(T2I_ERR_BAD_ARG, "im2col: image rows too wide (%d)", w);
+    const long long groups = (long long)n * ceil_div(h / 2, kIm2colPR);
+    const long long cap = (long long)num_sms() * 8;
+    launch_ew(im2col_k4s2_c3_kernel, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256), shm, STREAM, img, n, h, w, sample_scale,
+                                                                                      static_cast<bf16*>(col), ps, np);
     return check_launch("im2col_k4s2_c3");
 }
 extern "C" int t2i_col2im_k4s2_c3(const void* col, long long ps, int np, int n, int h, int w, const float* bias3,
                                   float* img, void* stream) {
     if ((h & 1) || (w & 1)) return fail(T2I_ERR_BAD_ARG, "col2im: odd extent");
-    col2im_k4s2_c3_kernel<<<grid_for((long long)n * h * w, 256, 16), 256, 0, STREAM>>>(static_cast<const bf16*>(col), ps, np, n, h, w, bias3, img);
+    const size_t shm = (size_t)(kCol2imR / 2 + 2) * (w / 2) * 48 * sizeof(float);
+    if (shm > 96 * 1024) return fail(T2I_ERR_BAD_ARG, "col2im: image rows too wide (%d)", w);
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaFuncSetAttribute(col2im_k4s2_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+        attr_done = true;
+    }
+    const long long groups = (long long)n * ceil_div(h, kCol2imR);
+    const long long cap = (long long)num_sms() * 4;
+    launch_ew(col2im_k4s2_c3_kernel, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256), shm, STREAM, static_cast<const bf16*>(col), ps, np,
+                                                                                      n, h, w, bias3, img);
     return check_launch("col2im_k4s2_c3");
 }
 extern "C" int t2i_conv3x3_c3_tanh_fwd(const float* x, const float* w, const float* b, float* y, int n, int h, int wd,
                                        void* stream) {
-    conv3x3_c3_tanh_fwd_kernel<<<grid_for((long long)n * h * wd, 256, 16), 256, 0, STREAM>>>(x, w, b, y, n, h, wd);
+    launch_ew(conv3x3_c3_tanh_fwd_kernel, dim3(grid_for((long long)n * h * wd, 256, 16)), dim3(256), 0, STREAM, x, w, b, y, n, h, wd);
     return check_launch("conv3x3_c3_tanh_fwd");
 }
 extern "C" int t2i_conv3x3_c3_tanh_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
                                        float* dw, float* db, float* dx_sum, int n, int h, int wd, void* stream) {
-    conv3x3_c3_tanh_bwd_kernel<<<grid_for((long long)n * h * wd, 128, 4), 128, 0, STREAM>>>(x, w, y, dy, dx, dw, db, dx_sum, n, h, wd);
+    const size_t shm = ((size_t)2 * (kC9R + 2) * (wd + 2) * 3 + 81 + 87) * sizeof(float);
+    if (shm > 48 * 1024) return fail(T2I_ERR_BAD_ARG, "conv3x3_c3_tanh_bwd: image rows too wide (%d)", wd);
+    const long long groups = (long long)n * ceil_div(h, kC9R);
+    const long long cap = (long long)num_sms();      // 214 registers x 256 threads: one block per SM, ~14 tiles each
+    launch_ew(conv3x3_c3_tanh_bwd_kernel, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256), shm, STREAM, x, w, y, dy, dx, dw, db, dx_sum,
+                                                                                           n, h, wd);
     return check_launch("conv3x3_c3_tanh_bwd");
 }
 extern "C" int t2i_colsum(const void* src, long long ps, int np, long long rows, int c, int pitch, int coff, float* out,
@@ -980,7 +1104,7 @@ extern "C" int t2i_bn_stats(const void* x, long long ps, int np, long long rows,
                             float* rstd, float* var, float eps, void* stream) {
     int rc = launch_col_reduce<RED_STATS>(x, ps, nullptr, 0, nullptr, nullptr, np, rows, c, c, 0, sums, sums + c, STREAM);
     if (rc != T2I_OK) return rc;
-    bn_finalize_kernel<<<ceil_div(c, 256), 256, 0, STREAM>>>(sums, mean, var, rstd, c, 1.f / (float)rows, eps);
+    launch_ew(bn_finalize_kernel, dim3(ceil_div(c, 256)), dim3(256), 0, STREAM, sums, mean, var, rstd, c, 1.f / (float)rows, eps);
     return check_launch("bn_finalize");
 }
 extern "C" int t2i_bn_apply(const void* x, long long x_ps, const float* mean, const float* rstd, const float* gamma,
@@ -990,7 +1114,7 @@ extern "C" int t2i_bn_apply(const void* x, long long x_ps, const float* mean, co
     int CG;
     dim3 grid;
     rowwise_geometry(rows, c, 256, &CG, &grid);
-    bn_apply_kernel<<<grid, 256, 0, STREAM>>>(
+    launch_ew(bn_apply_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, beta, static_cast<const bf16*>(residual), r_ps,
         static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG);
     return check_launch("bn_apply");
@@ -1007,7 +1131,7 @@ extern "C" int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, 
     int CG;
     dim3 grid;
     rowwise_geometry(rows, c, 256, &CG, &grid);
-    bn_bwd_apply_kernel<<<grid, 256, 0, STREAM>>>(
+    launch_ew(bn_bwd_apply_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dgamma, dbeta,
         static_cast<bf16*>(dx), dx_ps, np, rows, c, 1.f / (float)rows, CG);
     return check_launch("bn_bwd_apply");
@@ -1023,7 +1147,7 @@ extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* su
     rowwise_geometry(rows, c, 256, &CG, &grid);
     const long long n = stat_rows > 0 ? stat_rows : rows;     // values per channel behind the sums
     const float bessel = n > 1 ? (float)n / (float)(n - 1) : 1.f;
-    bn_apply_train_kernel<<<grid, 256, 0, STREAM>>>(
+    launch_ew(bn_apply_train_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)n, eps, gamma, beta, static_cast<const bf16*>(residual),
         r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel);
     return check_launch("bn_apply_train");
@@ -1038,7 +1162,7 @@ extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, 
     dim3 grid;
     rowwise_geometry(rows, c, 256, &CG, &grid);
     const long long n = stat_rows > 0 ? stat_rows : rows;
-    bn_bwd_fused_kernel<<<grid, 256, 0, STREAM>>>(
+    launch_ew(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,
         dbeta_out, out_scale, dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)n, CG);
     return check_launch("bn_bwd_fused");
@@ -1046,41 +1170,41 @@ extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, 
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,
                                     float decay, void* stream) {
     const float bessel = rows > 1 ? (float)rows / (float)(rows - 1) : 1.f;
-    bn_update_moving_kernel<<<ceil_div(c, 256), 256, 0, STREAM>>>(mm, mv, mean, var, c, decay, bessel);
+    launch_ew(bn_update_moving_kernel, dim3(ceil_div(c, 256)), dim3(256), 0, STREAM, mm, mv, mean, var, c, decay, bessel);
     return check_launch("bn_update_moving");
 }
 extern "C" int t2i_act_bwd(const void* dy, long long dy_ps, const void* y, long long y_ps, void* dst, long long dst_ps,
                            int np, long long n, int mask_kind, void* stream) {
     if (n % 8) return fail(T2I_ERR_BAD_ARG, "act_bwd: n must be a multiple of 8");
     const float neg = (mask_kind == T2I_MASK_LRELU) ? 0.2f : 0.f;
-    act_bwd_kernel<<<grid_for(n / 8, 256), 256, 0, STREAM>>>(static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(y),
+    launch_ew(act_bwd_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, STREAM, static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(y),
                                                             y_ps, static_cast<bf16*>(dst), dst_ps, np, n / 8, neg);
     return check_launch("act_bwd");
 }
 extern "C" int t2i_embed_tile(const void* e, long long e_ps, void* cat, long long cat_ps, int np, int s, int c, int pitch,
                               int coff, int hw, void* stream) {
     if (c % 8 || pitch % 8 || coff % 8) return fail(T2I_ERR_BAD_ARG, "embed_tile: channels must be multiples of 8");
-    embed_tile_kernel<<<grid_for((long long)s * hw * (c / 8), 256), 256, 0, STREAM>>>(
+    launch_ew(embed_tile_kernel, dim3(grid_for((long long)s * hw * (c / 8), 256)), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(e), e_ps, static_cast<bf16*>(cat), cat_ps, np, s, c, pitch, coff, hw);
     return check_launch("embed_tile");
 }
 extern "C" int t2i_embed_reduce(const void* dcat, long long dcat_ps, void* de, long long de_ps, int np, int s, int c,
                                 int pitch, int coff, int hw, void* stream) {
     if (c % 8 || pitch % 8 || coff % 8) return fail(T2I_ERR_BAD_ARG, "embed_reduce: channels must be multiples of 8");
-    embed_reduce_kernel<<<grid_for((long long)s * (c / 8), 128), 128, 0, STREAM>>>(
+    launch_ew(embed_reduce_kernel, dim3(grid_for((long long)s * (c / 8), 128)), dim3(128), 0, STREAM, 
         static_cast<const bf16*>(dcat), dcat_ps, static_cast<bf16*>(de), de_ps, np, s, c, pitch, coff, hw);
     return check_launch("embed_reduce");
 }
 extern "C" int t2i_dout_fwd(const void* a, long long a_ps, int np, const float* w, const float* b, float* logit, int s,
                             int k, void* stream) {
     if (k % 8) return fail(T2I_ERR_BAD_ARG, "dout_fwd: k must be a multiple of 8");
-    dout_fwd_kernel<<<s, 256, 0, STREAM>>>(static_cast<const bf16*>(a), a_ps, np, w, b, logit, k);
+    launch_ew(dout_fwd_kernel, dim3(s), dim3(256), 0, STREAM, static_cast<const bf16*>(a), a_ps, np, w, b, logit, k);
     return check_launch("dout_fwd");
 }
 extern "C" int t2i_dout_bwd_data(const void* a, long long a_ps, int np, const float* w, const float* seed, void* da,
                                  long long da_ps, int s, int k, void* stream) {
     if (k % 8) return fail(T2I_ERR_BAD_ARG, "dout_bwd_data: k must be a multiple of 8");
-    dout_bwd_data_kernel<<<grid_for((long long)s * (k / 8), 256), 256, 0, STREAM>>>(
+    launch_ew(dout_bwd_data_kernel, dim3(grid_for((long long)s * (k / 8), 256)), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(a), a_ps, np, w, seed, static_cast<bf16*>(da), da_ps, s, k);
     return check_launch("dout_bwd_data");
 }
@@ -1089,11 +1213,11 @@ extern "C" int t2i_dout_bwd_weight(const void* a, long long a_ps, int np, const 
     if (k % 8) return fail(T2I_ERR_BAD_ARG, "dout_bwd_weight: k must be a multiple of 8");
     const int gx = ceil_div(k / 8, 128);
     int gy = s < 32 ? s : 32;
-    dout_bwd_weight_kernel<<<dim3(gx, gy), 128, 0, STREAM>>>(static_cast<const bf16*>(a), a_ps, np, seed, dw, s, k);
+    launch_ew(dout_bwd_weight_kernel, dim3(dim3(gx, gy)), dim3(128), 0, STREAM, static_cast<const bf16*>(a), a_ps, np, seed, dw, s, k);
     int rc = check_launch("dout_bwd_weight");
     if (rc != T2I_OK) return rc;
     if (db != nullptr && s_bias > 0) {
-        seed_sum_kernel<<<1, 256, 0, STREAM>>>(seed, s_bias, db);
+        launch_ew(seed_sum_kernel, dim3(1), dim3(256), 0, STREAM, seed, s_bias, db);
         rc = check_launch("seed_sum");
     }
     return rc;
@@ -1102,61 +1226,61 @@ extern "C" int t2i_gp_interp(const float* g, const float* x, const float* eps, f
                              void* stream) {
     if (per_sample % 4) return fail(T2I_ERR_BAD_ARG, "gp_interp: per_sample must be a multiple of 4");
     const long long n4 = (long long)n * per_sample / 4;
-    gp_interp_kernel<<<grid_for(n4, 256), 256, 0, STREAM>>>(g, x, eps, xhat, n4, per_sample / 4);
+    launch_ew(gp_interp_kernel, dim3(grid_for(n4, 256)), dim3(256), 0, STREAM, g, x, eps, xhat, n4, per_sample / 4);
     return check_launch("gp_interp");
 }
 extern "C" int t2i_gp_penalty(const float* grad, int n, int per_sample, float weight, float inv_global_batch,
                               float* slope, float* coef, float* pen_sum, void* stream) {
     if (per_sample % 4) return fail(T2I_ERR_BAD_ARG, "gp_penalty: per_sample must be a multiple of 4");
-    gp_penalty_kernel<<<n, 256, 0, STREAM>>>(grad, per_sample, weight, inv_global_batch, slope, coef, pen_sum);
+    launch_ew(gp_penalty_kernel, dim3(n), dim3(256), 0, STREAM, grad, per_sample, weight, inv_global_batch, slope, coef, pen_sum);
     return check_launch("gp_penalty");
 }
 extern "C" int t2i_ca_fwd(const void* ms, long long ms_ps, const float* z, const float* tn_eps, void* zc, long long zc_ps,
                           int np, int b, int z_dim, int ce, float* kl_sum, void* stream) {
-    ca_fwd_kernel<<<grid_for((long long)b * (z_dim + ce), 256, 1), 256, 0, STREAM>>>(
+    launch_ew(ca_fwd_kernel, dim3(grid_for((long long)b * (z_dim + ce), 256, 1)), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(ms), ms_ps, z, tn_eps, static_cast<bf16*>(zc), zc_ps, np, b, z_dim, ce, kl_sum);
     return check_launch("ca_fwd");
 }
 extern "C" int t2i_ca_bwd(const void* ms, long long ms_ps, const void* dzc, long long dzc_ps, const float* tn_eps,
                           void* dms, long long dms_ps, int np, int b, int z_dim, int ce, float kl_scale, void* stream) {
-    ca_bwd_kernel<<<grid_for((long long)b * ce, 256, 1), 256, 0, STREAM>>>(
+    launch_ew(ca_bwd_kernel, dim3(grid_for((long long)b * ce, 256, 1)), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(ms), ms_ps, static_cast<const bf16*>(dzc), dzc_ps, tn_eps, static_cast<bf16*>(dms), dms_ps,
         np, b, z_dim, ce, kl_scale);
     return check_launch("ca_bwd");
 }
 extern "C" int t2i_d_seeds(const float* kt, float* seed, int b, float inv_global_batch, void* stream) {
-    d_seeds_kernel<<<ceil_div(4 * b, 256), 256, 0, STREAM>>>(kt, seed, b, inv_global_batch);
+    launch_ew(d_seeds_kernel, dim3(ceil_div(4 * b, 256)), dim3(256), 0, STREAM, kt, seed, b, inv_global_batch);
     return check_launch("d_seeds");
 }
 extern "C" int t2i_d_sums(const float* logit, int b, float* sums, void* stream) {
-    d_sums_kernel<<<1, 256, 0, STREAM>>>(logit, b, sums);
+    launch_ew(d_sums_kernel, dim3(1), dim3(256), 0, STREAM, logit, b, sums);
     return check_launch("d_sums");
 }
 extern "C" int t2i_d_scalars(const float* sums, float* kt, float* scalars, int global_batch, float gp_weight, float kt_lr,
                              void* stream) {
-    d_scalars_kernel<<<1, 32, 0, STREAM>>>(sums, kt, scalars, 1.f / (float)global_batch, gp_weight, kt_lr);
+    launch_ew(d_scalars_kernel, dim3(1), dim3(32), 0, STREAM, sums, kt, scalars, 1.f / (float)global_batch, gp_weight, kt_lr);
     return check_launch("d_scalars");
 }
 extern "C" int t2i_g_sums(const float* logit_fake, int b, float* sums, void* stream) {
-    g_sums_kernel<<<1, 256, 0, STREAM>>>(logit_fake, b, sums);
+    launch_ew(g_sums_kernel, dim3(1), dim3(256), 0, STREAM, logit_fake, b, sums);
     return check_launch("g_sums");
 }
 extern "C" int t2i_g_scalars(const float* sums, float* scalars, int global_batch, int ce, float kl_coeff, void* stream) {
-    g_scalars_kernel<<<1, 32, 0, STREAM>>>(sums, scalars, 1.f / (float)global_batch,
+    launch_ew(g_scalars_kernel, dim3(1), dim3(32), 0, STREAM, sums, scalars, 1.f / (float)global_batch,
                                            1.f / ((float)global_batch * (float)ce), kl_coeff);
     return check_launch("g_scalars");
 }
 extern "C" int t2i_pack_weight(const float* w, int taps, int cout, int cin, void* fwd, long long fwd_ps, void* bwd,
                                long long bwd_ps, int np, void* stream) {
     dim3 grid(ceil_div(cin, 32), ceil_div(cout, 32), taps);
-    pack_weight_kernel<<<grid, dim3(32, 8), 0, STREAM>>>(w, cout, cin, static_cast<bf16*>(fwd), fwd_ps,
+    launch_ew(pack_weight_kernel, grid, dim3(32, 8), 0, STREAM, w, cout, cin, static_cast<bf16*>(fwd), fwd_ps,
                                                         static_cast<bf16*>(bwd), bwd_ps, np);
     return check_launch("pack_weight");
 }
 extern "C" int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n, const float* lr_t_dev,
                            float beta1, float beta2, float eps, float grad_scale, void* packed, long long packed_ps, int np,
                            void* stream) {
-    adam_tf_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, STREAM>>>(theta, grad, m, v, n, lr_t_dev, beta1, beta2, eps,
+    launch_ew(adam_tf_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), 0, STREAM, theta, grad, m, v, n, lr_t_dev, beta1, beta2, eps,
                                                                grad_scale, static_cast<bf16*>(packed), packed_ps, np);
     return check_launch("adam_tf");
 }

@@ -61,6 +61,24 @@ inline cudaError_t launch_pdl(void (*kernel)(const Params), int grid, int block,
     return cudaLaunchKernelEx(&cfg, kernel, prm);
 }
 
+// Elementwise / reduction kernels: the same programmatic-serialization attribute, so that a kernel's launch latency
+// hides under its predecessor's tail; every such kernel calls pdl_wait() before it touches global memory.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_ew(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream,
+                             Args&&... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // Division by a runtime constant as multiply-high + shift (Granlund-Montgomery, round-up variant), valid for
 // 0 <= n < 2^31: q = (umulhi(mul, n) + n) >> shr.  The kernels decode tile indices with it.
 struct FastDiv {
