@@ -36,6 +36,12 @@ __device__ __forceinline__ void store8(bf16* p, long long ps, int np, const floa
         *reinterpret_cast<uint4*>(p + ps) = lo;
     }
 }
+// 8 consecutive fp32 values (32-byte aligned)
+__device__ __forceinline__ void load_f8(const float* p, float* v) {
+    const float4 a = *reinterpret_cast<const float4*>(p);
+    const float4 b = *reinterpret_cast<const float4*>(p + 4);
+    v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+}
 __device__ __forceinline__ float load1(const bf16* p, long long ps, int np) {
     float v = __bfloat162float(p[0]);
     if (np == 2) v += __bfloat162float(p[ps]);
@@ -554,41 +560,60 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
     const int ry = threadIdx.x / CG;
     if (ch >= c || ry >= RY) return;
     float sc[8], sh[8];
+    {
+        float s1[8], s2[8], ga[8], be[8];
+        load_f8(sums + ch, s1);
+        load_f8(sums + c + ch, s2);
+        load_f8(gamma + ch, ga);
+        load_f8(beta + ch, be);
+        const bool publish = blockIdx.y == 0 && ry == 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-        const float m = sums[ch + j] * inv_rows;
-        const float v = fmaxf(sums[c + ch + j] * inv_rows - m * m, 0.f);
-        const float rs = rsqrtf(v + eps);
-        if (blockIdx.y == 0 && ry == 0) {
-            mean_out[ch + j] = m;
-            var_out[ch + j] = v;
-            rstd_out[ch + j] = rs;
-            if (mm != nullptr) {
-                mm[ch + j] = decay * mm[ch + j] + (1.f - decay) * m;
-                mv[ch + j] = decay * mv[ch + j] + (1.f - decay) * v * bessel;
+        for (int j = 0; j < 8; ++j) {
+            const float m = s1[j] * inv_rows;
+            const float v = fmaxf(s2[j] * inv_rows - m * m, 0.f);
+            const float rs = rsqrtf(v + eps);
+            if (publish) {
+                mean_out[ch + j] = m;
+                var_out[ch + j] = v;
+                rstd_out[ch + j] = rs;
+                if (mm != nullptr) {
+                    mm[ch + j] = decay * mm[ch + j] + (1.f - decay) * m;
+                    mv[ch + j] = decay * mv[ch + j] + (1.f - decay) * v * bessel;
+                }
+            }
+            sc[j] = rs * ga[j];
+            sh[j] = be[j] - m * sc[j];
+        }
+    }
+    // four rows per trip, all loads issued before the first use
+    const long long stride = (long long)gridDim.y * RY;
+    for (long long r0 = (long long)blockIdx.y * RY + ry; r0 < rows; r0 += 4 * stride) {
+        float v[4][8], rr[4][8];
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < rows) {
+                load8(x + r * c + ch, x_ps, np, v[u]);
+                if (res != nullptr) load8(res + r * c + ch, r_ps, np, rr[u]);
             }
         }
-        sc[j] = rs * gamma[ch + j];
-        sh[j] = beta[ch + j] - m * sc[j];
-    }
-#pragma unroll 4
-    for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
-        const long long e = r * c + ch;
-        float v[8];
-        load8(x + e, x_ps, np, v);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
-        if (res != nullptr) {
-            float rr[8];
-            load8(res + e, r_ps, np, rr);
+        for (int u = 0; u < 4; ++u) {
+            const long long r = r0 + u * stride;
+            if (r < rows) {
 #pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] += rr[j];
+                for (int j = 0; j < 8; ++j) v[u][j] = v[u][j] * sc[j] + sh[j];
+                if (res != nullptr) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u][j] += rr[u][j];
+                }
+                if (relu) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
+                }
+                store8(y + r * c + ch, y_ps, np, v[u]);
+            }
         }
-        if (relu) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], 0.f);
-        }
-        store8(y + e, y_ps, np, v);
     }
 }
 
@@ -612,32 +637,50 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (ch < c && ry < RY) {
         float mu[8], rs[8], a[8], b0[8], b1[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            mu[j] = mean[ch + j];
-            rs[j] = rstd[ch + j];
-            const float db = dbeta[ch + j];
-            const float dg = dot_normalised ? dot[ch + j] : rs[j] * (dot[ch + j] - mu[j] * db);
-            if (blockIdx.y == 0 && ry == 0) {
-                dgamma_out[ch + j] += dg * out_scale;
-                if (dbeta_out != nullptr) dbeta_out[ch + j] += db * out_scale;
-            }
-            a[j] = gamma[ch + j] * rs[j];
-            b0[j] = db * inv_rows;
-            b1[j] = dg * inv_rows;
-        }
-#pragma unroll 4
-        for (long long r = (long long)blockIdx.y * RY + ry; r < rows; r += (long long)gridDim.y * RY) {
-            const long long e = r * c + ch;
-            float g[8], xv[8];
-            load8(dy + e, dy_ps, np, g);
-            load8(x + e, x_ps, np, xv);
+        {
+            float ga[8], dt[8], db8[8];
+            load_f8(mean + ch, mu);
+            load_f8(rstd + ch, rs);
+            load_f8(gamma + ch, ga);
+            load_f8(dot + ch, dt);
+            load_f8(dbeta + ch, db8);
+            const bool publish = blockIdx.y == 0 && ry == 0;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                g[j] = a[j] * (g[j] - b0[j] - (xv[j] - mu[j]) * rs[j] * b1[j]);
-                acc[j] += g[j];
+                const float db = db8[j];
+                const float dg = dot_normalised ? dt[j] : rs[j] * (dt[j] - mu[j] * db);
+                if (publish) {
+                    dgamma_out[ch + j] += dg * out_scale;
+                    if (dbeta_out != nullptr) dbeta_out[ch + j] += db * out_scale;
+                }
+                a[j] = ga[j] * rs[j];
+                b0[j] = db * inv_rows;
+                b1[j] = dg * inv_rows;
             }
-            store8(dx + e, dx_ps, np, g);
+        }
+        const long long stride = (long long)gridDim.y * RY;
+        for (long long r0 = (long long)blockIdx.y * RY + ry; r0 < rows; r0 += 4 * stride) {
+            float g[4][8], xv[4][8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long r = r0 + u * stride;
+                if (r < rows) {
+                    load8(dy + r * c + ch, dy_ps, np, g[u]);
+                    load8(x + r * c + ch, x_ps, np, xv[u]);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long r = r0 + u * stride;
+                if (r < rows) {
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        g[u][j] = a[j] * (g[u][j] - b0[j] - (xv[u][j] - mu[j]) * rs[j] * b1[j]);
+                        acc[j] += g[u][j];
+                    }
+                    store8(dx + r * c + ch, dx_ps, np, g[u]);
+                }
+            }
         }
     }
     if (dx_sum == nullptr) return;
@@ -657,12 +700,14 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
 }
 
 // launch geometry shared by the row-striding kernels above
-static inline void rowwise_geometry(long long rows, int c, int threads, int* CG, dim3* grid) {
+static inline void rowwise_geometry(long long rows, int c, int threads, int* CG, dim3* grid, int rows_per_thread = 1) {
     int cg = c / 8;
     int g = cg > 32 ? 32 : floor_pow2(cg);
     const int RY = threads / g;
     const int gx = ceil_div(cg, g);
-    long long gy = (rows + RY - 1) / RY;
+    // rows_per_thread > 1: the per-thread parameter prologue (8 channels x several arrays) is amortised over that
+    // many 16-byte payload accesses instead of being paid once per access
+    long long gy = (rows + (long long)RY * rows_per_thread - 1) / ((long long)RY * rows_per_thread);
     const long long cap = ((long long)num_sms() * 16 + gx - 1) / gx;
     if (gy > cap) gy = cap;
     if (gy < 1) gy = 1;
@@ -1144,7 +1189,7 @@ extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* su
     if ((moving_mean == nullptr) != (moving_var == nullptr)) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: moving pair");
     int CG;
     dim3 grid;
-    rowwise_geometry(rows, c, 256, &CG, &grid);
+    rowwise_geometry(rows, c, 256, &CG, &grid, 8);
     const long long n = stat_rows > 0 ? stat_rows : rows;     // values per channel behind the sums
     const float bessel = n > 1 ? (float)n / (float)(n - 1) : 1.f;
     launch_ew(bn_apply_train_kernel, dim3(grid), dim3(256), 0, STREAM, 
@@ -1160,7 +1205,7 @@ extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, 
     if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: c must be a multiple of 8");
     int CG;
     dim3 grid;
-    rowwise_geometry(rows, c, 256, &CG, &grid);
+    rowwise_geometry(rows, c, 256, &CG, &grid, 8);
     const long long n = stat_rows > 0 ? stat_rows : rows;
     launch_ew(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,

@@ -74,6 +74,24 @@ def main():
     timed("g_forward", lambda: eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"]))
     timed("g_forward + moving statistics", lambda: eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"],
                                                                   update_moving=True))
+    K = eng.K
+    real_conv, real_bn, real_wgrad, real_bnb = K.conv_gemm, K.bn_apply_train, K.wgrad_gemm, K.bn_bwd_fused
+    gf = lambda: eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"])
+    K.conv_gemm = lambda *a, **k: None
+    timed("g_forward without its GEMMs", gf)
+    K.bn_apply_train = lambda *a, **k: None
+    timed("g_forward without GEMMs and BatchNorm", gf)
+    K.conv_gemm = real_conv
+    timed("g_forward without BatchNorm", gf)
+    K.bn_apply_train = real_bn
+    gb = lambda: eng.g_backward(d["gx"])
+    K.wgrad_gemm = lambda *a, **k: None
+    timed("g_backward without weight gradients", gb)
+    K.bn_bwd_fused = lambda *a, **k: None
+    timed("g_backward without weight gradients, BatchNorm", gb)
+    K.conv_gemm = lambda *a, **k: None
+    timed("g_backward: the rest (c9 bwd, im2col, bn0, ca)", gb)
+    K.conv_gemm, K.wgrad_gemm, K.bn_bwd_fused = real_conv, real_wgrad, real_bnb
     timed("_g_body_fwd (fresh capture)", eng._g_body_fwd)
     timed("_d_body_gen (fresh capture)", eng._d_body_gen)
     timed("zero g + g_forward(sums tail) ", lambda: (eng.grad["g"].zero_(), eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], eng.sums["g"][1:2])))
