@@ -150,15 +150,17 @@ int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x
  * gradient of the conv in front of the BatchNorm).
  * stat_rows (0 = rows): number of values per channel behind the sums when they were all-reduced over the
  * data-parallel ranks (synchronised BatchNorm = the reference's whole-batch statistics, utils/ops.py:20-29);
- * out_scale = 1 / world then keeps the later gradient all-reduce(sum) exact. */
+ * out_scale = 1 / world then keeps the later gradient all-reduce(sum) exact.
+ * relu: 0 none, 1 ReLU, 2 LeakyReLU(0.2).  y_pitch / dy_pitch (0 = c): channels per pixel in memory of y / dy when
+ * they are the leading channels of a wider buffer (the discriminator's concat buffer). */
 int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
                        const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                        long long rows, int c, int relu, float* mean, float* rstd, float* var, float* moving_mean,
-                       float* moving_var, float decay, long long stat_rows, void* stream);
+                       float* moving_var, float decay, long long stat_rows, int y_pitch, void* stream);
 int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                      const float* rstd, const float* gamma, const float* dot, const float* dbeta, float* dgamma,
                      float* dbeta_out, float out_scale, int dot_normalised, void* dx, long long dx_ps, float* dx_sum,
-                     int np, long long rows, int c, long long stat_rows, void* stream);
+                     int np, long long rows, int c, long long stat_rows, int dy_pitch, void* stream);
 int t2i_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var,
                          long long rows, int c, float decay, void* stream);
 /* dst = dy * act'(y)  (relu / lrelu masks on post-activation values) */
@@ -215,6 +217,15 @@ int t2i_d_sums(const float* logit, int b, float* sums, void* stream);
 int t2i_d_scalars(const float* sums, float* kt, float* scalars, int global_batch, float gp_weight, float kt_lr,
                   void* stream);
 int t2i_g_sums(const float* logit_fake, int b, float* sums, void* stream);
+/* StackGAN stage-I (models/stackgan/stageI/trainer.py:21-44): seed[i] = weight * (sigmoid(logit) - label) / B, the
+ * backward seed of weight * mean sigmoid_cross_entropy_with_logits(logit, label); *loss_sum += sum of the
+ * cross-entropy terms.  t2i_s1_scalars: sums = [CE(syn,0), CE(real,0.9), CE(mismatch,0), CE(syn,1), KL terms] ->
+ * which = 0: scalars[0..3] = D_loss, D_synthetic_loss, D_real_match_loss, D_real_mismatch_loss;
+ * which = 1: scalars[4..6] = G_loss, G_gan_loss, G_kl_loss. */
+int t2i_ce_seeds(const float* logit, int n, float label, float weight, float inv_global_batch, float* seed,
+                 float* loss_sum, void* stream);
+int t2i_s1_scalars(const float* sums, float* scalars, int global_batch, int ce, float alpha, float kl_coeff, int which,
+                   void* stream);
 int t2i_g_scalars(const float* sums, float* scalars, int global_batch, int ce, float kl_coeff, void* stream);
 
 /* weights: fp32 master [taps][cout][cin] -> bf16 planes, same layout (fwd) and/or transposed

@@ -225,9 +225,12 @@ def batch_norm(p, scope, x, train, act=None, new_moving=None):
 
 # ----------------------------------------------------------------------------- the networks
 
-def generator(p, z, embed, tn_eps, cfg: OracleCfg, is_training=True, cond_noise=True, new_moving=None):
+def generator(p, z, embed, tn_eps, cfg: OracleCfg, is_training=True, cond_noise=True, new_moving=None,
+              fc_reshape="nchw"):
     """models/wgancls/model.py:163-225 (+ :108-122).  ``tn_eps`` is the truncated-normal draw of
-    :119 made explicit.  Returns (image NHWC, mean, log_sigma)."""
+    :119 made explicit.  Returns (image NHWC, mean, log_sigma).
+    fc_reshape="nhwc": the dense output is reshaped [-1, s16, s16, C] as the (otherwise layer-for-layer
+    identical) StackGAN stage-I generator does (models/stackgan/stageI/model.py:129)."""
     g = "g_net/"
     gf = cfg.gf_dim
     s16 = cfg.output_size // 16
@@ -237,7 +240,10 @@ def generator(p, z, embed, tn_eps, cfg: OracleCfg, is_training=True, cond_noise=
     c = mean + torch.exp(log_sigma) * tn_eps if cond_noise else mean   # :117-122
     h0 = fc(p, g + "dense_2", torch.cat([z, c], 1))              # :174-175
     h0 = batch_norm(p, g + "BatchNorm", h0, **bnk)               # :176
-    h0 = h0.reshape(-1, gf * 8, s16, s16)                        # :179 (NCHW)
+    if fc_reshape == "nchw":
+        h0 = h0.reshape(-1, gf * 8, s16, s16)                    # :179 (NCHW)
+    else:
+        h0 = h0.reshape(-1, s16, s16, gf * 8).permute(0, 3, 1, 2)
 
     def res(x, c1, b1, c2, b2, c3, b3):
         n = conv2d(p, g + c1, x, 1, 1, "valid")

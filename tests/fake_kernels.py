@@ -206,7 +206,7 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 
 
 def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
-                   decay=0.9, stat_rows=0):
+                   decay=0.9, stat_rows=0, y_pitch=0):
     c = x.shape[-1]
     rows = stat_rows if stat_rows > 0 else x[0].numel() // c
     m = sums[:c].double() / rows
@@ -214,19 +214,30 @@ def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None,
     mean.copy_(m); var.copy_(s); rstd.copy_(torch.rsqrt(s + eps))
     if moving is not None:
         bn_update_moving(moving[0], moving[1], mean, var, rows, decay)
-    bn_apply(x, mean, rstd, gamma, beta, y, residual, relu)
+    v = (val(x) - mean.double()) * rstd.double() * gamma.double() + beta.double()
+    if residual is not None:
+        v = v + val(residual)
+    if relu:
+        v = torch.maximum(v, (0.2 if int(relu) == 2 else 0.0) * v)
+    if y_pitch in (0, c):
+        put(y, v)
+    else:       # y: the leading c channels of a [np, rows, y_pitch] window starting at y's first element
+        yw = y.as_strided((y.shape[0], v.numel() // c, c), (y.stride(0), y_pitch, 1))
+        put(yw, v.reshape(-1, c))
 
 
 def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, dbeta_out=None, out_scale=1.0,
-                 dot_normalised=False, stat_rows=0):
+                 dot_normalised=False, stat_rows=0, dy_pitch=0):
     c = x.shape[-1]
     rows = stat_rows if stat_rows > 0 else x[0].numel() // c
+    if dy_pitch not in (0, c):
+        dy = dy.as_strided((dy.shape[0], x[0].numel() // c, c), (dy.stride(0), dy_pitch, 1))
     db = dbeta.double().clone()
     dg = dot.double().clone() if dot_normalised else rstd.double() * (dot.double() - mean.double() * db)
     dgamma += dg * out_scale
     if dbeta_out is not None:
         dbeta_out += db * out_scale
-    g = val(dy)
+    g = val(dy).reshape(val(x).shape)
     xh = (val(x) - mean.double()) * rstd.double()
     out = gamma.double() * rstd.double() * (g - db / rows - xh * dg / rows)
     put(dx, out)
@@ -351,6 +362,25 @@ def d_scalars(sums, kt, scalars, global_batch, gp_weight, kt_lr):
     kt[0] = out["kt"]
     for n, v in out.items():
         scalars[S[n]] = v
+
+
+def ce_seeds(logit, n, label, weight, inv_global_batch, seed, loss_sum):
+    x = logit[:n].double()
+    seed[:n] = weight * (torch.sigmoid(x) - label) * inv_global_batch
+    if loss_sum is not None:
+        loss_sum += (torch.clamp(x, min=0) - x * label + torch.log1p(torch.exp(-x.abs()))).sum()
+
+
+def s1_scalars(sums, scalars, global_batch, ce, alpha, kl_coeff, which):
+    s = sums.double()
+    if which == 0:
+        syn, real, mis = float(s[0]) / global_batch, float(s[1]) / global_batch, float(s[2]) / global_batch
+        scalars[0] = real + alpha * mis + (1 - alpha) * syn
+        scalars[1], scalars[2], scalars[3] = syn, real, mis
+    else:
+        gan, kl = float(s[3]) / global_batch, float(s[4]) / (global_batch * ce)
+        scalars[4] = gan + kl_coeff * kl
+        scalars[5], scalars[6] = gan, kl
 
 
 def g_sums(logit_fake, b, sums):

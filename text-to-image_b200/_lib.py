@@ -55,8 +55,10 @@ SIGNATURES = {
     "t2i_bn_apply": [_P, _LL, _P, _P, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P],
     "t2i_bn_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _I, _P, _P, _P],
     "t2i_bn_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
-    "t2i_bn_apply_train": [_P, _LL, _P, _F, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _F, _LL, _P],
-    "t2i_bn_bwd_fused": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _F, _I, _P, _LL, _P, _I, _LL, _I, _LL, _P],
+    "t2i_bn_apply_train": [_P, _LL, _P, _F, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _F, _LL, _I, _P],
+    "t2i_bn_bwd_fused": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _F, _I, _P, _LL, _P, _I, _LL, _I, _LL, _I, _P],
+    "t2i_ce_seeds": [_P, _I, _F, _F, _F, _P, _P, _P],
+    "t2i_s1_scalars": [_P, _P, _I, _I, _F, _F, _I, _P],
     "t2i_bn_update_moving": [_P, _P, _P, _P, _LL, _I, _F, _P],
     "t2i_act_bwd": [_P, _LL, _P, _LL, _P, _LL, _I, _LL, _I, _P],
     "t2i_embed_tile": [_P, _LL, _P, _LL, _I, _I, _I, _I, _I, _I, _P],

@@ -695,10 +695,12 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     prm.second_kind = d->stat_sq != nullptr ? 1 : d->stat_dot != nullptr ? 2 : 0;
     prm.stat_n = (d->stat_n > 0 && d->stat_n < x.n) ? d->stat_n : x.n;
     prm.stat_c = (d->stat_c > 0 && d->stat_c < y.c) ? d->stat_c : y.c;
-    for (const t2i_act* a : {&d->add, &d->mask, &d->stat_x})
-        if (a->ptr != nullptr && (a->n != y.n || a->h != y.h || a->w != y.w || a->c < y.c))
+    for (const t2i_act* a : {&d->add, &d->mask, &d->stat_x}) {
+        const int need_c = (a == &d->stat_x) ? prm.stat_c : y.c;     // the dot factor only has to cover the counted channels
+        if (a->ptr != nullptr && (a->n != y.n || a->h != y.h || a->w != y.w || a->c < need_c))
             return fail(T2I_ERR_BAD_ARG, "epilogue tensor [%d,%d,%d,%d] does not cover the output [%d,%d,%d,%d]", a->n, a->h,
-                        a->w, a->c, y.n, y.h, y.w, y.c);
+                        a->w, a->c, y.n, y.h, y.w, need_c);
+    }
     const int sms = num_sms();
     // CTA pairs (cta_group::2, 256-pixel tiles) whenever there are at least two pixel tiles
     const bool allow_cta2 = [] { const char* e = getenv("T2I_CONV_CTA2"); return !(e && e[0] == '0'); }();
@@ -762,7 +764,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     }
     if (prm.has_sx) {
         t2i_act a = d->stat_x;
-        a.c = y.c;
+        if (a.c > y.c) a.c = y.c;      // channels beyond its extent are out of bounds for the map: zero filled, not counted
         rc = make_act_maps(a, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.sx_maps);
         if (rc != T2I_OK) return rc;
     }

@@ -552,13 +552,14 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
                                       const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
                                       bf16* __restrict__ y, long long y_ps, int np, long long rows, int c, int relu, int CG,
                                       float* mean_out, float* rstd_out, float* var_out, float* mm, float* mv, float decay,
-                                      float bessel) {
+                                      float bessel, int y_pitch) {
     pdl_launch_dependents();
     pdl_wait();
     const int RY = blockDim.x / CG;
     const int ch = (blockIdx.x * CG + threadIdx.x % CG) * 8;
     const int ry = threadIdx.x / CG;
     if (ch >= c || ry >= RY) return;
+    const float act_neg = (relu == 2) ? 0.2f : 0.f;      // relu: 0 none, 1 ReLU, 2 LeakyReLU(0.2)
     float sc[8], sh[8];
     {
         float s1[8], s2[8], ga[8], be[8];
@@ -609,9 +610,9 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
                 }
                 if (relu) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], 0.f);
+                    for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], act_neg * v[u][j]);
                 }
-                store8(y + r * c + ch, y_ps, np, v[u]);
+                store8(y + r * y_pitch + ch, y_ps, np, v[u]);
             }
         }
     }
@@ -626,7 +627,7 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
                                     const float* __restrict__ gamma, const float* __restrict__ dot,
                                     const float* __restrict__ dbeta, float* dgamma_out, float* dbeta_out, float out_scale,
                                     int dot_normalised, bf16* __restrict__ dx, long long dx_ps, float* dx_sum, int np,
-                                    long long rows, int c, float inv_rows, int CG) {
+                                    long long rows, int c, float inv_rows, int CG, int dy_pitch) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sh[256 * 8];
@@ -665,7 +666,7 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
             for (int u = 0; u < 4; ++u) {
                 const long long r = r0 + u * stride;
                 if (r < rows) {
-                    load8(dy + r * c + ch, dy_ps, np, g[u]);
+                    load8(dy + r * dy_pitch + ch, dy_ps, np, g[u]);
                     load8(x + r * c + ch, x_ps, np, xv[u]);
                 }
             }
@@ -986,6 +987,39 @@ __global__ void d_scalars_kernel(const float* sums, float* kt, float* sc, float 
     kt[0] = nk;
     sc[T2I_S_KT] = nk;
 }
+// StackGAN stage-I losses (models/stackgan/stageI/trainer.py:21-44): per-sample backward seed of
+// weight * mean_b sigmoid_cross_entropy(logit, label) and the running sum of the cross-entropy terms.
+__global__ void ce_seeds_kernel(const float* __restrict__ logit, int n, float label, float weight, float inv_gb, float* seed,
+                                float* loss_sum) {
+    pdl_launch_dependents();
+    pdl_wait();
+    __shared__ float sh[32];
+    float acc = 0.f;
+    for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const float x = logit[i];
+        const float sg = 1.f / (1.f + expf(-x));
+        seed[i] = weight * (sg - label) * inv_gb;
+        acc += fmaxf(x, 0.f) - x * label + log1pf(expf(-fabsf(x)));
+    }
+    const float t = block_sum(acc, sh);
+    if (threadIdx.x == 0 && loss_sum != nullptr) atomicAdd(loss_sum, t);
+}
+// sums: [0] CE(synthetic, 0)  [1] CE(real match, 0.9)  [2] CE(real mismatch, 0)  [3] CE(synthetic, 1)  [4] KL terms
+__global__ void s1_scalars_kernel(const float* sums, float* sc, float inv_gb, float inv_gb_ce, float alpha, float kl_coeff,
+                                  int which) {
+    pdl_launch_dependents();
+    pdl_wait();
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    if (which == 0) {
+        const float syn = sums[0] * inv_gb, real = sums[1] * inv_gb, mis = sums[2] * inv_gb;
+        sc[0] = real + alpha * mis + (1.f - alpha) * syn;      // D_loss
+        sc[1] = syn; sc[2] = real; sc[3] = mis;
+    } else {
+        const float gan = sums[3] * inv_gb, kl = sums[4] * inv_gb_ce;
+        sc[4] = gan + kl_coeff * kl;                           // G_loss
+        sc[5] = gan; sc[6] = kl;
+    }
+}
 __global__ void g_sums_kernel(const float* __restrict__ logit, int b, float* sums) {
     pdl_launch_dependents();
     pdl_wait();
@@ -1184,8 +1218,11 @@ extern "C" int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, 
 extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
                                   const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                                   long long rows, int c, int relu, float* mean, float* rstd, float* var,
-                                  float* moving_mean, float* moving_var, float decay, long long stat_rows, void* stream) {
-    if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: c must be a multiple of 8");
+                                  float* moving_mean, float* moving_var, float decay, long long stat_rows, int y_pitch,
+                                  void* stream) {
+    if (c % 8 || y_pitch % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: c and y_pitch must be multiples of 8");
+    if (y_pitch == 0) y_pitch = c;
+    if (y_pitch < c) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: y_pitch %d < c %d", y_pitch, c);
     if ((moving_mean == nullptr) != (moving_var == nullptr)) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: moving pair");
     int CG;
     dim3 grid;
@@ -1194,22 +1231,25 @@ extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* su
     const float bessel = n > 1 ? (float)n / (float)(n - 1) : 1.f;
     launch_ew(bn_apply_train_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)n, eps, gamma, beta, static_cast<const bf16*>(residual),
-        r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel);
+        r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel,
+        y_pitch);
     return check_launch("bn_apply_train");
 }
 extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                                 const float* rstd, const float* gamma, const float* dot, const float* dbeta,
                                 float* dgamma, float* dbeta_out, float out_scale, int dot_normalised, void* dx,
                                 long long dx_ps, float* dx_sum, int np, long long rows, int c, long long stat_rows,
-                                void* stream) {
-    if (c % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: c must be a multiple of 8");
+                                int dy_pitch, void* stream) {
+    if (c % 8 || dy_pitch % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: c and dy_pitch must be multiples of 8");
+    if (dy_pitch == 0) dy_pitch = c;
     int CG;
     dim3 grid;
     rowwise_geometry(rows, c, 256, &CG, &grid, 8);
     const long long n = stat_rows > 0 ? stat_rows : rows;
     launch_ew(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,
-        dbeta_out, out_scale, dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)n, CG);
+        dbeta_out, out_scale, dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)n, CG,
+        dy_pitch);
     return check_launch("bn_bwd_fused");
 }
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,
@@ -1305,6 +1345,17 @@ extern "C" int t2i_d_scalars(const float* sums, float* kt, float* scalars, int g
                              void* stream) {
     launch_ew(d_scalars_kernel, dim3(1), dim3(32), 0, STREAM, sums, kt, scalars, 1.f / (float)global_batch, gp_weight, kt_lr);
     return check_launch("d_scalars");
+}
+extern "C" int t2i_ce_seeds(const float* logit, int n, float label, float weight, float inv_global_batch, float* seed,
+                            float* loss_sum, void* stream) {
+    launch_ew(ce_seeds_kernel, dim3(1), dim3(256), 0, STREAM, logit, n, label, weight, inv_global_batch, seed, loss_sum);
+    return check_launch("ce_seeds");
+}
+extern "C" int t2i_s1_scalars(const float* sums, float* scalars, int global_batch, int ce, float alpha, float kl_coeff,
+                              int which, void* stream) {
+    launch_ew(s1_scalars_kernel, dim3(1), dim3(32), 0, STREAM, sums, scalars, 1.f / (float)global_batch,
+              1.f / ((float)global_batch * (float)ce), alpha, kl_coeff, which);
+    return check_launch("s1_scalars");
 }
 extern "C" int t2i_g_sums(const float* logit_fake, int b, float* sums, void* stream) {
     launch_ew(g_sums_kernel, dim3(1), dim3(256), 0, STREAM, logit_fake, b, sums);

@@ -210,25 +210,34 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 
 
 def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
-                   decay=0.9, stat_rows=0):
+                   decay=0.9, stat_rows=0, y_pitch=0):
     """sums: fp32 [2c] = [sum x | sum x^2] from conv_gemm(stat_sum=, stat_sq=); moving: (mm, mv) or None;
-    stat_rows: values per channel behind the sums when they were all-reduced over ranks (0 = this tensor's rows)."""
+    relu: False / True (ReLU) / 2 (LeakyReLU 0.2); stat_rows: values per channel behind the sums when they were
+    all-reduced over ranks (0 = this tensor's rows); y_pitch: y is the leading c channels of a [.., y_pitch] buffer."""
     rows, c = _rows_c(x)
     mm, mv = moving if moving is not None else (None, None)
     _lib.call("t2i_bn_apply_train", _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(beta), _p(residual),
               0 if residual is None else _ps(residual), _p(y), _ps(y), x.shape[0], rows, c, int(relu), _f32(mean),
-              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, stat_rows, _stream())
+              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, stat_rows, y_pitch, _stream())
 
 
 def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, dbeta_out=None, out_scale=1.0,
-                 dot_normalised=False, stat_rows=0):
+                 dot_normalised=False, stat_rows=0, dy_pitch=0):
     """dbeta / dot: the reductions conv_gemm(stat_sum=dbeta, stat_dot=dot, stat_x=x) produced with dy
     (dot_normalised: dot = sum dy * xhat, as bn_bwd_reduce writes it).  dgamma += out_scale * (...),
     dbeta_out += out_scale * dbeta (when the sums live in a scratch that was all-reduced)."""
     rows, c = _rows_c(x)
     _lib.call("t2i_bn_bwd_fused", _p(dy), _ps(dy), _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(dot),
               _f32(dbeta), _f32(dgamma), _p(dbeta_out), out_scale, int(dot_normalised), _p(dx), _ps(dx), _p(dx_sum),
-              x.shape[0], rows, c, stat_rows, _stream())
+              x.shape[0], rows, c, stat_rows, dy_pitch, _stream())
+
+
+def ce_seeds(logit, n, label, weight, inv_global_batch, seed, loss_sum):
+    _lib.call("t2i_ce_seeds", _f32(logit), n, label, weight, inv_global_batch, _f32(seed), _p(loss_sum), _stream())
+
+
+def s1_scalars(sums, scalars, global_batch, ce, alpha, kl_coeff, which):
+    _lib.call("t2i_s1_scalars", _f32(sums), _f32(scalars), global_batch, ce, alpha, kl_coeff, which, _stream())
 
 
 def bn_bwd_reduce(dy, x, mean, rstd, dgamma, dbeta):
