@@ -137,9 +137,10 @@ def discriminator(p, x_nhwc, embed, cfg: Stage1Cfg, new_moving=None):
 
 
 def sigmoid_ce(logits, label):
-    """tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x z + log(1 + exp(-|x|)), mean over the batch."""
+    """tf.nn.sigmoid_cross_entropy_with_logits: max(x,0) - x z + log(1 + exp(-|x|)) = log(1 + e^x) - x z, mean over
+    the batch (written with logaddexp so that autograd gives sigmoid(x) - z at x = 0 too)."""
     x = logits.reshape(-1)
-    return (torch.clamp(x, min=0) - x * label + torch.log1p(torch.exp(-x.abs()))).mean()
+    return (torch.logaddexp(x, torch.zeros_like(x)) - x * label).mean()
 
 
 def adam_tf(theta, grad, m, v, lr, beta1, t):

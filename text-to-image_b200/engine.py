@@ -50,13 +50,18 @@ class Layer:
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
-                 f32_dtype=torch.float32, share_from=None, use_graphs=False, concurrent=True, sync_bn=False):
+                 f32_dtype=torch.float32, share_from=None, use_graphs=False, concurrent=True, sync_bn=False,
+                 beta1_g=None):
         # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
         # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
         self.act_dtype, self.f32_dtype = act_dtype, f32_dtype
+        # the generator's dense input [z | c] needs a multiple of 8 columns (16-byte TMA strides): z is zero-padded
+        self.Z_tf = z_dim
+        z_dim = _align(z_dim, 8)
         self.Z, self.E, self.ce, self.gf, self.df = z_dim, embed_dim, ce, gf, df
         self.beta1, self.beta2, self.kl_coeff = beta1, beta2, kl_coeff
+        self.beta1_net = {"d": beta1, "g": beta1 if beta1_g is None else beta1_g}
         self.world, self.allreduce = world, allreduce
         # sync_bn: all-reduce g_net's BatchNorm sums over the ranks (forward and backward), i.e. normalise over the
         # GLOBAL batch exactly as the single-device reference does (utils/ops.py:20-29); default: per-replica
@@ -79,21 +84,22 @@ class Engine:
             self._build_params()
             self._param_attrs = sorted(set(self.__dict__) - before)
         else:   # a second batch size (sampler / eval) on the same parameters
-            assert (share_from.np, share_from.gf, share_from.df) == (np_, gf, df)
+            assert (share_from.np, share_from.gf, share_from.df) == (np_, gf, df) and type(share_from) is type(self)
             self._param_attrs = share_from._param_attrs
             for k in self._param_attrs:
                 setattr(self, k, getattr(share_from, k))
         self._build_buffers()
 
     # ------------------------------------------------------------------ parameters
-    def _build_params(self):
+    FC0_NCHW = True      # dense output features ordered c*16 + hw (wgancls reshapes to NCHW, model.py:179)
+
+    def _d_layers(self):
+        """d_net contraction layers in creation order (models/wgancls/model.py:129-161) and its BatchNorm list."""
         K = self.K
-        gf, df, ce, E, Z = self.gf, self.df, self.ce, self.E, self.Z
-        C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
-        S1, K4, DC = K.CONV_S1, K.CONV_K4S2, K.DECONV_K4S2
-        d, g = "d_net/", "g_net/"
-        L = Layer
-        self.dl = OrderedDict((l.name, l) for l in [
+        df, ce, E = self.df, self.ce, self.E
+        S1, K4 = K.CONV_S1, K.CONV_K4S2
+        d, L = "d_net/", Layer
+        layers = [
             L("h0", "col_in", d + "Conv", d + "Conv", S1, 1, 1, df, 64),
             L("h1", "conv", d + "Conv_1", d + "Conv_1", K4, 4, 16, 2 * df, df),
             L("h2", "conv", d + "Conv_2", d + "Conv_2", K4, 4, 16, 4 * df, 2 * df),
@@ -105,7 +111,18 @@ class Engine:
             L("h5", "conv", d + "Conv_7", d + "Conv_7", S1, 3, 9, 8 * df, 8 * df + ce),
             L("h6", "conv", d + "Conv_8", d + "Conv_8", S1, 1, 1, 8 * df, 8 * df),
             L("out", "dout", d + "Conv_9", d + "Conv_9", None, 4, 1, 1, 16 * 8 * df, need_bwd=False),
-        ])
+        ]
+        return layers, [], []       # layers, BatchNorm channel counts, BatchNorm TF scopes
+
+    def _build_params(self):
+        K = self.K
+        gf, df, ce, E, Z = self.gf, self.df, self.ce, self.E, self.Z
+        C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
+        S1, K4, DC = K.CONV_S1, K.CONV_K4S2, K.DECONV_K4S2
+        d, g = "d_net/", "g_net/"
+        L = Layer
+        d_layers, self.dbn_ch, self.dbn_tf = self._d_layers()
+        self.dl = OrderedDict((l.name, l) for l in d_layers)
         self.gl = OrderedDict((l.name, l) for l in [
             L("ms", "ms", (g + "dense", g + "dense_1"), (g + "dense", g + "dense_1"), S1, 1, 1, 2 * ce, E,
               need_bwd=False),
@@ -132,20 +149,19 @@ class Engine:
         def bias_len(l):
             return {"dout": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)
 
-        def layout(layers, with_bn):
+        def layout(layers, bn_ch):
             off, table = 0, OrderedDict()
             for l in layers.values():
                 wn = l.taps * l.cout * l.cin if l.kind not in ("dout", "c9") else (l.cin if l.kind == "dout" else 81)
                 table[l.name + ".w"] = (off, wn); off = _align(off + wn)
                 table[l.name + ".b"] = (off, bias_len(l)); off = _align(off + bias_len(l))
-            if with_bn:
-                for i, c in enumerate(self.bn_ch):
-                    table["bn%d.gamma" % i] = (off, c); off = _align(off + c)
-                    table["bn%d.beta" % i] = (off, c); off = _align(off + c)
+            for i, c in enumerate(bn_ch):
+                table["bn%d.gamma" % i] = (off, c); off = _align(off + c)
+                table["bn%d.beta" % i] = (off, c); off = _align(off + c)
             return off, table
 
-        self.d_n, self.d_table = layout(self.dl, False)
-        self.g_n, self.g_table = layout(self.gl, True)
+        self.d_n, self.d_table = layout(self.dl, self.dbn_ch)
+        self.g_n, self.g_table = layout(self.gl, self.bn_ch)
         f32 = dict(device=self.dev, dtype=self.f32_dtype)
         self.flat = {"d": torch.zeros(self.d_n, **f32), "g": torch.zeros(self.g_n, **f32)}
         self.grad = {"d": torch.zeros(self.d_n + SUMS, **f32), "g": torch.zeros(self.g_n + SUMS, **f32)}
@@ -185,7 +201,18 @@ class Engine:
         self.bn_mean = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_var = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_rstd = [torch.zeros(c, **f32) for c in self.bn_ch]
-        for gmm in self.bn_gamma:
+        # d_net BatchNorm (none in wgancls; StackGAN stage-I has seven)
+        nd = range(len(self.dbn_ch))
+        self.dbn_gamma = [self.P["d.bn%d.gamma" % i] for i in nd]
+        self.dbn_beta = [self.P["d.bn%d.beta" % i] for i in nd]
+        self.dbn_dgamma = [self.G["d.bn%d.gamma" % i] for i in nd]
+        self.dbn_dbeta = [self.G["d.bn%d.beta" % i] for i in nd]
+        self.dbn_mm = [torch.zeros(c, **f32) for c in self.dbn_ch]
+        self.dbn_mv = [torch.ones(c, **f32) for c in self.dbn_ch]
+        self.dbn_mean = [torch.zeros(c, **f32) for c in self.dbn_ch]
+        self.dbn_var = [torch.zeros(c, **f32) for c in self.dbn_ch]
+        self.dbn_rstd = [torch.zeros(c, **f32) for c in self.dbn_ch]
+        for gmm in self.bn_gamma + self.dbn_gamma:
             gmm.fill_(1.0)
         self.kt = torch.full((1,), KT_INIT, **f32)
         self.scalars = torch.zeros(16, **f32)
@@ -193,6 +220,8 @@ class Engine:
     # -- layout conversion between the reference's TF variables and the kernel layout ---------
     def _perm_fc0(self, v_tf, inverse=False):
         """feature order: TF c*16 + hw (NCHW reshape, model.py:179)  <->  kernel hw*C8 + c (NHWC)."""
+        if not self.FC0_NCHW:      # NHWC reshape: the dense features already are hw*C8 + c
+            return v_tf
         C8 = 8 * self.gf
         lead = v_tf.shape[:-1]
         if not inverse:
@@ -209,8 +238,12 @@ class Engine:
             return p[l.tf_w + "/kernel"].t().reshape(1, l.cout, l.cin)
         if l.kind == "ms":
             return torch.cat([p[l.tf_w[0] + "/kernel"].t(), p[l.tf_w[1] + "/kernel"].t()], 0).reshape(1, l.cout, l.cin)
-        if l.kind == "fc0":
-            return self._perm_fc0(p[l.tf_w + "/kernel"]).t().reshape(1, l.cout, l.cin)
+        if l.kind == "fc0":      # TF rows [z (Z_tf) | c (ce)] -> kernel columns [z padded to Z | c]
+            w = self._perm_fc0(p[l.tf_w + "/kernel"]).t()
+            out = torch.zeros(l.cout, l.cin, dtype=w.dtype)
+            out[:, :self.Z_tf] = w[:, :self.Z_tf]
+            out[:, self.Z:] = w[:, self.Z_tf:]
+            return out.reshape(1, l.cout, l.cin)
         if l.kind == "col_in":   # [4,4,3,co] -> [co, (kh*4+kw)*3+c], zero padded to 64 columns
             w = p[l.tf_w + "/weights"]
             out = torch.zeros(1, l.cout, 64, dtype=w.dtype)
@@ -239,7 +272,9 @@ class Engine:
             out[l.tf_w[0] + "/kernel"] = w2[:self.ce].t().contiguous()
             out[l.tf_w[1] + "/kernel"] = w2[self.ce:].t().contiguous()
         elif l.kind == "fc0":
-            out[l.tf_w + "/kernel"] = self._perm_fc0(w.reshape(l.cout, l.cin).t(), inverse=True).contiguous()
+            w2 = w.reshape(l.cout, l.cin)
+            w2 = torch.cat([w2[:, :self.Z_tf], w2[:, self.Z:]], 1)
+            out[l.tf_w + "/kernel"] = self._perm_fc0(w2.t(), inverse=True).contiguous()
         elif l.kind == "col_in":
             out[l.tf_w + "/weights"] = w.reshape(l.cout, 64)[:, :48].t().reshape(4, 4, 3, l.cout).contiguous()
         elif l.kind == "col_out":
@@ -277,6 +312,12 @@ class Engine:
             if with_moving:
                 self.bn_mm[i].copy_(perm(p[scope + "/moving_mean"]))
                 self.bn_mv[i].copy_(perm(p[scope + "/moving_variance"]))
+        for i, scope in enumerate(self.dbn_tf):
+            views["d.bn%d.gamma" % i].copy_(p[scope + "/gamma"])
+            views["d.bn%d.beta" % i].copy_(p[scope + "/beta"])
+            if with_moving:
+                self.dbn_mm[i].copy_(p[scope + "/moving_mean"])
+                self.dbn_mv[i].copy_(p[scope + "/moving_variance"])
 
     def set_params_tf(self, p):
         """Load parameters given in the reference's TF variable layout (oracle / checkpoint names)."""
@@ -322,6 +363,12 @@ class Engine:
             if include_moving:
                 out[scope + "/moving_mean"] = perm(self.bn_mm[i].detach().cpu()).clone()
                 out[scope + "/moving_variance"] = perm(self.bn_mv[i].detach().cpu()).clone()
+        for i, scope in enumerate(self.dbn_tf):
+            out[scope + "/gamma"] = flat_views["d.bn%d.gamma" % i].detach().cpu().clone()
+            out[scope + "/beta"] = flat_views["d.bn%d.beta" % i].detach().cpu().clone()
+            if include_moving:
+                out[scope + "/moving_mean"] = self.dbn_mm[i].detach().cpu().clone()
+                out[scope + "/moving_variance"] = self.dbn_mv[i].detach().cpu().clone()
         return out
 
     def get_params_tf(self):
@@ -339,15 +386,17 @@ class Engine:
 
     # ------------------------------------------------------------------ buffers
     def _build_buffers(self):
-        B, S, np_ = self.B, 4 * self.B, self.np
-        df, gf, ce, E, Z = self.df, self.gf, self.ce, self.E, self.Z
-        C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
-        bf = dict(device=self.dev, dtype=self.act_dtype)
+        self._build_d_buffers()
+        self._build_g_buffers()
+
+    def _planes(self, *shape):
+        return torch.zeros(self.np, *shape, device=self.dev, dtype=self.act_dtype)
+
+    def _build_d_buffers(self):
+        B, S = self.B, 4 * self.B
+        df, ce, E = self.df, self.ce, self.E
         f32 = dict(device=self.dev, dtype=self.f32_dtype)
-
-        def planes(*shape):
-            return torch.zeros(np_, *shape, **bf)
-
+        planes = self._planes
         d = self.d = {}
         d["img"] = torch.zeros(S, IMG, IMG, 3, **f32)     # [fake | real | mismatch | x_hat]
         d["col0"] = planes(S * 1024, 64)
@@ -370,6 +419,12 @@ class Engine:
         for n in ("slope", "coef", "slope2", "coef2"):
             d[n] = torch.zeros(B, **f32)
 
+    def _build_g_buffers(self):
+        B = self.B
+        gf, ce, E, Z = self.gf, self.ce, self.E, self.Z
+        C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
+        f32 = dict(device=self.dev, dtype=self.f32_dtype)
+        planes = self._planes
         g = self.g = {}
         gshapes = {"f0": (B, 4, 4, C8), "h0": (B, 4, 4, C8), "t1": (B, 4, 4, C2), "u1": (B, 4, 4, C2),
                    "t2": (B, 4, 4, C2), "u2": (B, 4, 4, C2), "t3": (B, 4, 4, C8), "h1": (B, 4, 4, C8),
@@ -669,13 +724,13 @@ class Engine:
     # ------------------------------------------------------------------ optimizer plumbing
     def _set_lr(self, net, lr, t):
         """lr_t of tf.train.AdamOptimizer, staged into device memory OUTSIDE any captured graph."""
-        self.lr_host[net][0] = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1 ** t)
+        self.lr_host[net][0] = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1_net[net] ** t)
         self.lr_t[net].copy_(self.lr_host[net], non_blocking=True)
 
     def _adam(self, net):
         n = self.d_n if net == "d" else self.g_n
         self.K.adam_tf(self.flat[net], self.grad[net][:n], self.adam_m[net], self.adam_v[net], self.lr_t[net],
-                       self.beta1, self.beta2, ADAM_EPS, 1.0, self.packed[net])
+                       self.beta1_net[net], self.beta2, ADAM_EPS, 1.0, self.packed[net])
 
     def _reduce(self, net):
         if self.world > 1:
@@ -699,7 +754,7 @@ class Engine:
         if cond is not None:
             self.feed["cond"].copy_(cond, non_blocking=True)
         if z is not None:
-            g["z"].copy_(z, non_blocking=True)
+            g["z"][:, :self.Z_tf].copy_(z, non_blocking=True)      # columns Z_tf..Z stay zero (padding)
         if epsilon is not None:
             self.feed["epsilon"].copy_(epsilon.reshape(-1), non_blocking=True)
         if tn_eps is not None:
