@@ -145,6 +145,57 @@ def test_two_rank_sync_bn_iteration_equals_single_process(tmp_path):
     assert len(r["calls"]) == 11 + 21, r["calls"]
 
 
+def _worker_stage1(rank, world, port, out):
+    """StackGAN stage-I under data parallelism: one gradient all-reduce per optimizer step, replicas stay identical"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import stackgan1_oracle as S
+    from t2i_b200.engine_stage1 import StageIEngine
+    from test_stackgan1_cpu import TINY, boosted_params
+    torch.set_num_threads(1)
+    cfg = S.Stage1Cfg(**TINY)
+    b = cfg.batch_size // world
+    p = boosted_params(cfg)
+    feed = S.make_feed(cfg, 21, torch.float64)
+    calls = []
+
+    def allreduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    eng = StageIEngine(fk, "cpu", b, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
+                       cfg.d_beta1, cfg.g_beta1, cfg.alpha_mismatch, cfg.kl_coeff, world, allreduce,
+                       act_dtype=torch.float64, f32_dtype=torch.float64)
+    eng.set_params_tf(p)
+    sl = slice(rank * b, (rank + 1) * b)
+    eng.load_feed(x=feed["x"][sl], x_mismatch=feed["x_mismatch"][sl], cond=feed["cond"][sl], z=feed["z"][sl],
+                  tn_eps=feed["tn_eps"][sl])
+    eng.d_step(cfg.lr)
+    eng.load_feed(tn_eps=feed["tn_eps_g"][sl])
+    eng.g_step(cfg.lr)
+    flat = torch.cat([eng.flat["d"], eng.flat["g"]])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    sc = eng.scalars_dict()
+    if rank == 0:
+        torch.save({"calls": calls, "same": all(torch.equal(gathered[0], t) for t in gathered),
+                    "finite": all(v == v for v in sc.values()), "d_n": eng.d_n + 8, "g_n": eng.g_n + 8}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_stage1_iteration(tmp_path):
+    out = str(tmp_path / "s1.pt")
+    port = 33500 + os.getpid() % 2000
+    mp.spawn(_worker_stage1, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["calls"] == [r["d_n"], r["g_n"]], r        # exactly one all-reduce per optimizer step
+    assert r["same"] and r["finite"], r                  # replicas hold identical parameters afterwards
+
+
 def test_two_rank_d_run_equals_single_process(tmp_path):
     out = str(tmp_path / "r.pt")
     port = 29500 + os.getpid() % 2000

@@ -36,7 +36,6 @@ class StageIEngine(Engine):
                  g_beta1=0.5, alpha=0.5, kl_coeff=2.0, world=1, allreduce=None, **kw):
         self.alpha = alpha
         assert not kw.get("sync_bn"), "synchronised BatchNorm is implemented for wgancls only"
-        kw["use_graphs"] = False      # eager launches (graph capture of the three-call D run: later)
         super().__init__(K, device, batch, np_, z_dim, embed_dim, ce, gf, df, beta1=d_beta1, beta2=0.999,
                          kl_coeff=kl_coeff, world=world, allreduce=allreduce, beta1_g=g_beta1, **kw)
 
@@ -208,14 +207,19 @@ class StageIEngine(Engine):
     # ------------------------------------------------------------------ the two runs of an iteration
     def d_step(self, lr):
         """sess.run([D_optim, D_loss, ...]) -- models/stackgan/stageI/trainer.py:139-140."""
-        K, d, g, B = self.K, self.d, self.g, self.B
         self.d_t += 1
         self.join_comm()
         self._set_lr("d", lr, self.d_t)
+        if self.copy_stream is not None:        # the real / mismatching images arrive on the copy stream
+            torch.cuda.current_stream().wait_stream(self.copy_stream)
+        self._run("s1_d", self._s1_d_body)
+        self._reduce("d")                       # outside the graphs
+        self._run("s1_d_tail", self._s1_d_tail)
+
+    def _s1_d_body(self):
+        K, d, g, B = self.K, self.d, self.g, self.B
         self.grad["d"].zero_()
         g["kl_scratch"].zero_()
-        if self.copy_stream is not None:
-            torch.cuda.current_stream().wait_stream(self.copy_stream)
         self.g_forward(g["z"], self.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"], update_moving=True)   # model.py:44
         K.to_planes(self.feed["cond"], d["cond"])
         inv = 1.0 / self.GB
@@ -226,15 +230,21 @@ class StageIEngine(Engine):
             K.ce_seeds(d["logit"][k * B:(k + 1) * B], B, label, weight, inv, d["seed"], self.sums["d"][k:k + 1])
             self.d_backward_s1(want_wgrad=True, want_gx=False)
         self._join()
-        self._reduce("d")
-        K.s1_scalars(self.sums["d"], self.scalars, self.GB, self.ce, self.alpha, self.kl_coeff, 0)
+
+    def _s1_d_tail(self):
+        self.K.s1_scalars(self.sums["d"], self.scalars, self.GB, self.ce, self.alpha, self.kl_coeff, 0)
         self._adam("d")
 
     def g_step(self, lr):
         """sess.run([G_optim, G_loss, ...]) -- models/stackgan/stageI/trainer.py:144-145."""
-        K, d, g, B = self.K, self.d, self.g, self.B
         self.g_t += 1
         self._set_lr("g", lr, self.g_t)
+        self._run("s1_g", self._s1_g_body)
+        self._reduce("g")
+        self._run("s1_g_tail", self._s1_g_tail)
+
+    def _s1_g_body(self):
+        K, d, g, B = self.K, self.d, self.g, self.B
         self.grad["g"].zero_()
         self.g_forward(g["z"], self.feed["cond"], g["tn"], d["img"][:B], self.sums["g"][4:5], update_moving=True)
         K.to_planes(self.feed["cond"], d["cond"])
@@ -243,8 +253,9 @@ class StageIEngine(Engine):
         K.ce_seeds(d["logit"][:B], B, 1.0, 1.0, 1.0 / self.GB, d["seed"], self.sums["g"][3:4])    # trainer.py:32-34
         self.d_backward_s1(want_wgrad=False, want_gx=True)
         self.g_backward(d["gx"])
-        self._reduce("g")
-        K.s1_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.alpha, self.kl_coeff, 1)
+
+    def _s1_g_tail(self):
+        self.K.s1_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.alpha, self.kl_coeff, 1)
         self._adam("g")
 
     def scalars_dict(self):

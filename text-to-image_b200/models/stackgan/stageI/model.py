@@ -17,7 +17,8 @@ from ...wgancls.model import Fetch, Placeholder, _truncated_normal
 
 
 class ConditionalGan(object):
-    def __init__(self, cfg, build_model=True, precision="bf16", device=None, kernels=None, distributed=None):
+    def __init__(self, cfg, build_model=True, precision="bf16", device=None, kernels=None, distributed=None,
+                 use_graphs=True):
         """
         Args:
           cfg: Config specifying all the parameters of the model (reference: model.py:6-10).
@@ -61,6 +62,7 @@ class ConditionalGan(object):
             self._world = dist.get_world_size(group)
             self._allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         self._engines = {}
+        self._use_graphs = use_graphs
         self._noise_gen = None
         self._built = False
         self._train_engine()
@@ -74,7 +76,7 @@ class ConditionalGan(object):
             self._engines[batch] = StageIEngine(
                 self._K, self.device, batch, self._np, self.z_dim, self.embed_dim, self.compressed_embed_dim,
                 self.gf_dim, self.df_dim, t.D_BETA_DECAY, t.G_BETA_DECAY, t.COEFF.ALPHA_MISMATCH_LOSS, t.COEFF.KL,
-                self._world, self._allreduce, share_from=base)
+                self._world, self._allreduce, share_from=base, use_graphs=self._use_graphs)
         return self._engines[batch]
 
     def _train_engine(self):
