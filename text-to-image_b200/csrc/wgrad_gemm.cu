@@ -2,8 +2,11 @@
 // The contraction runs over pixels, which is the slow (row) index of NHWC tensors, so both
 // operands are MN-major: TMA loads [64 pixels x 64 channels] boxes (128B swizzle) and the UMMA
 // descriptors walk 16 pixel rows per instruction (LBO = distance between 64-channel atoms,
-// SBO = 8 pixel rows).  One CTA per (tap, co tile, ci tile, K split); split-K partial sums are
-// combined with vectorised fp32 reductions (red.global.add.v4.f32) into dw.
+// SBO = 8 pixel rows).  Work items are (tap, co tile, ci tile, K split); split-K partial sums are
+// combined with vectorised fp32 reductions (red.global.add.v4.f32) into dw.  The kernel is persistent:
+// each CTA (pair) walks its work items with the accumulator double-buffered in TMEM, so that the reduction
+// of one item and the pipeline fill of the next overlap the MMAs (one CTA per item left 7 waves of
+// un-overlapped fill / drain on the split-K launches).
 //
 // Tile shapes (MT x 128 output channels by BN input channels): 1x128, 1x256, 2x128.  The wide
 // shapes halve the operand bytes fetched per MMA cycle (48 KB per 512 tensor cycles instead of
@@ -33,7 +36,8 @@ struct WgradCfg {
     static constexpr int kStages = (kStageBytes <= 32768) ? 6 : 4;
     static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kSmemBytes = kBarOffset + 256 + 1024;
-    static constexpr int kTmemCols = MT * BN;                 // 128 or 256
+    static constexpr int kAccCols = MT * BN;                  // 128 or 256 columns per accumulator
+    static constexpr int kTmemCols = 2 * MT * BN;             // double buffered
 };
 
 struct alignas(64) WgradParams {
@@ -45,6 +49,7 @@ struct alignas(64) WgradParams {
     int tiles_p, tiles_q, k_blocks;  // k_blocks = pixel boxes covering the virtual grid
     int tiles_co, tiles_ci, jobs;    // jobs = n_phases * taps_per_phase
     int splits, kb_per_split;
+    int total_work;        // jobs * tiles_co * tiles_ci * splits
     int n_pass;
     int cout, cin;
     float* dw;
@@ -62,33 +67,24 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* tmem_empty = tmem_full + 2;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     pdl_launch_dependents();
 
-    // work decode: split fastest so the CTAs of one output tile run together
-    int w = blockIdx.x / kPair;
-    const int split = w % prm.splits; w /= prm.splits;
-    const int cit = w % prm.tiles_ci; w /= prm.tiles_ci;
-    const int cot = w % prm.tiles_co; w /= prm.tiles_co;
-    const int job = w;  // phase * taps_per_phase + t
-    const int phase_idx = job / prm.tt.taps_per_phase;
-    const Tap tap = prm.tt.taps[job];
-    const int kb_begin = split * prm.kb_per_split;
-    int kb_end = kb_begin + prm.kb_per_split;
-    if (kb_end > prm.k_blocks) kb_end = prm.k_blocks;
-    const int n_kb = (kb_end > kb_begin) ? (kb_end - kb_begin) * prm.n_pass : 0;
-
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&prm.x_maps[tap.map]);
-        tma_prefetch_desc(&prm.dy_maps[prm.tt.n_phases > 1 ? phase_idx : 0]);
+        for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.x_maps[i]);
+        for (int i = 0; i < (prm.tt.n_phases > 1 ? prm.tt.n_phases : 1); ++i) tma_prefetch_desc(&prm.dy_maps[i]);
         for (int i = 0; i < kStages; ++i) {
             mbar_init(&full_bar[i], kPair);
             mbar_init(&empty_bar[i], 1);
         }
-        mbar_init(tmem_full, 1);
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&tmem_full[i], 1);
+            mbar_init(&tmem_empty[i], kPair * 4);      // the four reduction warps of both CTAs (leader's copy)
+        }
         fence_barrier_init();
     }
     if (CTA2) cluster_sync_all();
@@ -106,20 +102,40 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     pdl_wait();
-    const int co_cta = (cot * kPair + rank) * Cfg::kM;        // first output channel of this CTA
-    const int ci_cta = cit * BN + rank * Cfg::kBCols;         // first input channel staged by this CTA
 
-    if (n_kb > 0) {
-        if (warp == 0) {
-            if (elect_one()) {
-                const CUtensorMap* dy_map = &prm.dy_maps[prm.tt.n_phases > 1 ? phase_idx : 0];
+    // work decode: split fastest so that the CTAs of one output tile run together
+    struct Work {
+        int split, cit, cot, job, kb_begin, kb_end, n_kb;
+    };
+    auto decode = [&](int w) {
+        Work k;
+        k.split = w % prm.splits; w /= prm.splits;
+        k.cit = w % prm.tiles_ci; w /= prm.tiles_ci;
+        k.cot = w % prm.tiles_co; w /= prm.tiles_co;
+        k.job = w;   // phase * taps_per_phase + t
+        k.kb_begin = k.split * prm.kb_per_split;
+        k.kb_end = k.kb_begin + prm.kb_per_split;
+        if (k.kb_end > prm.k_blocks) k.kb_end = prm.k_blocks;
+        k.n_kb = (k.kb_end > k.kb_begin) ? (k.kb_end - k.kb_begin) * prm.n_pass : 0;
+        return k;
+    };
+    const int w0 = blockIdx.x / kPair, w_stride = gridDim.x / kPair;
+
+    if (warp == 0) {
+        if (elect_one()) {
+            int stage = 0;
+            uint32_t phase = 0;
+            for (int w = w0; w < prm.total_work; w += w_stride) {
+                const Work wk = decode(w);
+                const Tap tap = prm.tt.taps[wk.job];
+                const CUtensorMap* dy_map = &prm.dy_maps[prm.tt.n_phases > 1 ? wk.job / prm.tt.taps_per_phase : 0];
                 const CUtensorMap* x_map = &prm.x_maps[tap.map];
-                int stage = 0;
-                uint32_t phase = 0;
+                const int co_cta = (wk.cot * kPair + rank) * Cfg::kM;        // first output channel of this CTA
+                const int ci_cta = wk.cit * BN + rank * Cfg::kBCols;         // first input channel staged by this CTA
                 for (int pass = 0; pass < prm.n_pass; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;  // dy plane: hi, lo, hi
                     const int pb = (pass == 2) ? 1 : 0;  // x  plane: hi, hi, lo
-                    for (int kb = kb_begin; kb < kb_end; ++kb) {
+                    for (int kb = wk.kb_begin; kb < wk.kb_end; ++kb) {
                         const int tq = kb % prm.tiles_q;
                         const int tp = (kb / prm.tiles_q) % prm.tiles_p;
                         const int tn = kb / (prm.tiles_q * prm.tiles_p);
@@ -153,12 +169,21 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                     }
                 }
             }
-        } else if (warp == 1) {
-            if (rank == 0 && elect_one()) {
-                constexpr uint32_t idesc = make_idesc_bf16(kPair * 128, BN, 1, 1);
-                int stage = 0;
-                uint32_t phase = 0;
-                for (int kb = 0; kb < n_kb; ++kb) {
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && elect_one()) {
+            constexpr uint32_t idesc = make_idesc_bf16(kPair * 128, BN, 1, 1);
+            int stage = 0;
+            uint32_t phase = 0;
+            int it = 0;
+            for (int w = w0; w < prm.total_work; w += w_stride) {
+                const Work wk = decode(w);
+                if (wk.n_kb == 0) continue;
+                const int acc = it & 1;
+                mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, 300 + acc);
+                tc_fence_after();
+                const uint32_t d_tmem = tmem_base + acc * Cfg::kAccCols;
+                for (int kb = 0; kb < wk.n_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 200 + stage);
                     tc_fence_after();
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
@@ -169,35 +194,45 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
 #pragma unroll
                         for (int mt = 0; mt < MT; ++mt) {
                             const uint64_t da = make_sw128_desc(sa + mt * 2 * kWAtomBytes + k * 2048, kWAtomBytes, 1024);
-                            if (CTA2) umma_bf16_2sm(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0);
-                            else umma_bf16(tmem_base + mt * BN, da, db, idesc, (kb | k) != 0);
+                            if (CTA2) umma_bf16_2sm(d_tmem + mt * BN, da, db, idesc, (kb | k) != 0);
+                            else umma_bf16(d_tmem + mt * BN, da, db, idesc, (kb | k) != 0);
                         }
                     }
                     if (CTA2) {
                         umma_commit_2sm(&empty_bar[stage]);
-                        if (kb == n_kb - 1) umma_commit_2sm(tmem_full);
+                        if (kb == wk.n_kb - 1) umma_commit_2sm(&tmem_full[acc]);
                     } else {
                         umma_commit(&empty_bar[stage]);
-                        if (kb == n_kb - 1) umma_commit(tmem_full);
+                        if (kb == wk.n_kb - 1) umma_commit(&tmem_full[acc]);
                     }
                     if (++stage == kStages) {
                         stage = 0;
                         phase ^= 1;
                     }
                 }
+                ++it;
             }
-        } else {
-            const int quarter = warp & 3;
-            mbar_wait(tmem_full, 0, 400);
+        }
+    } else {
+        // reduction warps: accumulator -> red.global.add into dw, while the MMAs of the next item run
+        const int quarter = warp & 3;
+        int it = 0;
+        for (int w = w0; w < prm.total_work; w += w_stride) {
+            const Work wk = decode(w);
+            if (wk.n_kb == 0) continue;
+            const int acc = it & 1;
+            const Tap tap = prm.tt.taps[wk.job];
+            const int co_cta = (wk.cot * kPair + rank) * Cfg::kM;
+            mbar_wait(&tmem_full[acc], (it >> 1) & 1, 400 + acc);
             tc_fence_after();
 #pragma unroll 1
             for (int mt = 0; mt < MT; ++mt) {
                 const int co = co_cta + mt * 128 + quarter * 32 + lane;
-                const uint32_t taddr = tmem_base + mt * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+                const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + mt * BN + (static_cast<uint32_t>(quarter * 32) << 16);
                 float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
 #pragma unroll 1
                 for (int c0 = 0; c0 < BN; c0 += 32) {
-                    const int ci0 = cit * BN + c0;
+                    const int ci0 = wk.cit * BN + c0;
                     if (ci0 >= prm.cin) break;
                     __syncwarp();
                     uint32_t r[32];
@@ -216,6 +251,14 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                     }
                 }
             }
+            // accumulator read: hand the TMEM buffer back to the MMA warp (of the leader CTA)
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) {
+                if (CTA2 && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                else mbar_arrive(&tmem_empty[acc]);
+            }
+            ++it;
         }
     }
 
@@ -348,7 +391,9 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     rc = make_maps(dy, d->mode == T2I_DECONV_K4S2, d->np, prm.bq, prm.bp, prm.bn, prm.dy_maps);
     if (rc != T2I_OK) return rc;
 
-    const int grid = tiles * prm.splits;
+    prm.total_work = tiles * prm.splits;
+    const int workers_all = cta2 ? num_sms() / 2 : num_sms();
+    const int grid = prm.total_work < workers_all ? prm.total_work : workers_all;     // persistent CTAs (pairs)
     if (cta2) return launch_wgrad<1, 256, true>(prm, grid, stream);
     if (bnn == 256) return launch_wgrad<1, 256, false>(prm, grid, stream);
     if (mt == 2) return launch_wgrad<2, 128, false>(prm, grid, stream);
