@@ -438,7 +438,6 @@ class Engine:
         for n, sh in {"cond": (B, E), "ms": (B, 2 * ce), "zc": (B, Z + ce), "colg": (B * 1024, 64)}.items():
             g[n] = planes(*sh)
             g["d_" + n] = planes(*sh)
-        g["ds"] = {"h1": planes(B, 4, 4, C8), "h3": planes(B, 8, 8, C4)}   # gradient at the residual sums
         g["u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
         g["d_u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
         g["tn"] = torch.zeros(B, ce, **f32)
@@ -570,7 +569,7 @@ class Engine:
             return dict(mask=V(g[y_post]), mask_kind=RELU)
 
         def res_bwd(x, c_a, t_a, bn_a, u_a, c_b, t_b, bn_b, u_b, c_c, t_c, bn_c, out, **last_epi):
-            ds = g["ds"][out]          # gradient at (x + bn(t_c)), ReLU mask applied by its producer
+            ds = g["d_" + out]         # gradient at the residual sum x + bn(t_c): ReLU mask already applied by its producer
             bn_bwd(bn_c, ds, g[t_c], g["d_" + t_c], gl[c_c].gb)
             conv_bwd(c_c, u_b, "d_" + t_c, g["d_" + u_b], **relu_of(u_b), **bn_red(bn_b, g[t_b]))
             bn_bwd(bn_b, g["d_" + u_b], g[t_b], g["d_" + t_b], gl[c_b].gb)
@@ -589,11 +588,11 @@ class Engine:
         conv_bwd("t2", "h4", "d_d3", g["d_h4"], **relu_of("h4"), **bn_red(8, g["t8"]))
         bn_bwd(8, g["d_h4"], g["t8"], g["d_t8"], gl["c7"].gb)
         conv_bwd("c7", "d2", "d_t8", g["d_d2"], stat_sum=gl["t1"].gb)
-        conv_bwd("t1", "h3", "d_d2", g["ds"]["h3"], **relu_of("h3"), **bn_red(7, g["t7"]))
+        conv_bwd("t1", "h3", "d_d2", g["d_h3"], **relu_of("h3"), **bn_red(7, g["t7"]))
         res_bwd("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3", **bn_red(4, g["t4"]))
         bn_bwd(4, g["d_h2"], g["t4"], g["d_t4"], gl["c3"].gb)
         conv_bwd("c3", "d1", "d_t4", g["d_d1"], stat_sum=gl["t0"].gb)
-        conv_bwd("t0", "h1", "d_d1", g["ds"]["h1"], **relu_of("h1"), **bn_red(3, g["t3"]))
+        conv_bwd("t0", "h1", "d_d1", g["d_h1"], **relu_of("h1"), **bn_red(3, g["t3"]))
         res_bwd("h0", "c0", "t1", 1, "u1", "c1", "t2", 2, "u2", "c2", "t3", 3, "h1")
         # BatchNorm 0 normalises per FEATURE of the [B, 16*C8] dense output (model.py:176), not per channel of the
         # 4x4 map the conv above wrote, so its reductions stay a separate pass
