@@ -45,8 +45,8 @@ typedef struct {
 
 /* Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, accumulators in TMEM):
  *   y = act( conv(x, w) + bias + add ) * mask'(mask)
- * mode T2I_CONV_S1   : k x k (k = 1 or 3) stride 1, SAME.  flip = 1 correlates with the taps
- *                      mirrored (input-gradient of a k3 conv).  A dense layer is k = 1, h = w = 1.
+ * mode T2I_CONV_S1   : k x k (k = 1, 3 or 4) stride 1, SAME (k = 4: TF's asymmetric padding, 1 before / 2 after).
+ *                      flip = 1 correlates with the taps mirrored (input-gradient).  A dense layer is k = 1, h = w = 1.
  * mode T2I_CONV_K4S2 : 4x4 stride 2 SAME (y is h/2 x w/2); also the input-gradient of a deconv.
  * mode T2I_DECONV_K4S2: 4x4 stride 2 SAME transposed conv as four 2x2 sub-pixel phases
  *                      (y is 2h x 2w); also the input-gradient of a 4x4/s2 conv.
@@ -114,6 +114,15 @@ int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sampl
                        long long plane_stride, int np, void* stream);
 int t2i_col2im_k4s2_c3(const void* col, long long plane_stride, int np, int n, int h, int w,
                        const float* bias3, float* img, void* stream);
+
+/* 3-channel image -> 3x3/s1 SAME patch matrix [n*h*w, 32] (col = (kh*3+kw)*3 + c, 27 used): StackGAN stage-II's
+ * first generator conv (models/stackgan/stageII/model.py:139).  t2i_tanh_c3_fwd / _bwd: the 3 leading channels of an
+ * 8-channel planes tensor (the padded output of the last 3x3 conv, :172) -> tanh -> fp32 NHWC image, and
+ * dlogit = dy * (1 - y^2) back into 8-channel planes (channels 3..7 zero). */
+int t2i_im2col_k3s1_c3(const float* img, int n, int h, int w, void* col, long long plane_stride, int np, void* stream);
+int t2i_tanh_c3_fwd(const void* logits8, long long plane_stride, int np, float* img, long long pixels, void* stream);
+int t2i_tanh_c3_bwd(const float* img, const float* dimg, void* dlogits8, long long plane_stride, int np, long long pixels,
+                    void* stream);
 
 /* g_net's last conv 3->3 k3 s1 + tanh (model.py:219-221), direct; and its backward
  * (dw, db, dx_sum are accumulated: dx_sum[c] += sum of dx over pixels = bias gradient of the

@@ -73,9 +73,11 @@ def _conv_core(mode, k, flip, x, w):
     taps, co, ci = w.shape
     if mode == CONV_S1:
         wk = w.view(k, k, co, ci).permute(2, 3, 0, 1)
+        lo, hi = (k - 1) // 2, k - 1 - (k - 1) // 2      # TF SAME: k = 4 pads 1 before, 2 after
         if flip:
             wk = wk.flip(2, 3)
-        y = F.conv2d(xc, wk, padding=(k - 1) // 2)
+            lo, hi = hi, lo
+        y = F.conv2d(F.pad(xc, (lo, hi, lo, hi)), wk)
     elif mode == CONV_K4S2:
         wk = w.view(4, 4, co, ci).permute(2, 3, 0, 1)
         y = F.conv2d(xc, wk, stride=2, padding=1)
@@ -163,6 +165,26 @@ def col2im_k4s2_c3(col, img, bias3=None):
     if bias3 is not None:
         out = out + bias3.double()
     img.copy_(out)
+
+
+def im2col_k3s1_c3(img, col):
+    n, h, w, _ = img.shape
+    xp = F.pad(img.double(), (0, 0, 1, 1, 1, 1))
+    out = torch.zeros(n, h, w, 32, dtype=torch.float64)
+    for kh in range(3):
+        for kw in range(3):
+            out[..., (kh * 3 + kw) * 3:(kh * 3 + kw) * 3 + 3] = xp[:, kh:kh + h, kw:kw + w, :]
+    put(col, out.reshape(-1, 32))
+
+
+def tanh_c3_fwd(logits8, img):
+    img.copy_(torch.tanh(val(logits8)[..., :3]).reshape(img.shape))
+
+
+def tanh_c3_bwd(img, dimg, dlogits8):
+    v = torch.zeros(dlogits8.shape[1:], dtype=torch.float64)
+    v[..., :3] = (dimg.double() * (1 - img.double() ** 2)).reshape(v[..., :3].shape)
+    put(dlogits8, v)
 
 
 def conv3x3_c3_tanh_fwd(x, w, b, y):

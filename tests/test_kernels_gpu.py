@@ -64,6 +64,8 @@ CONV_CASES = [
     ("c3_32x32", fk.CONV_S1, 3, 0, 2, 32, 32, 128, 128),
     ("c3_flip", fk.CONV_S1, 3, 1, 4, 8, 8, 128, 64),
     ("c3_tinych", fk.CONV_S1, 3, 0, 4, 4, 4, 8, 16),
+    ("k4s1_4x4", fk.CONV_S1, 4, 0, 16, 4, 4, 128, 128),          # TF SAME for k = 4, s = 1: pad 1 before, 2 after
+    ("k4s1_16_flip", fk.CONV_S1, 4, 1, 3, 16, 16, 64, 128),
     ("k4s2_32", fk.CONV_K4S2, 4, 0, 2, 32, 32, 128, 256),
     ("k4s2_8", fk.CONV_K4S2, 4, 0, 16, 8, 8, 64, 128),
     ("k4s2_tiny", fk.CONV_K4S2, 4, 0, 2, 8, 8, 16, 32),
@@ -268,6 +270,8 @@ WGRAD_CASES = [
     ("c3_4x4", fk.CONV_S1, 3, 16, 4, 4, 128, 128),
     ("c3_16x16", fk.CONV_S1, 3, 3, 16, 16, 64, 128),
     ("c3_tiny", fk.CONV_S1, 3, 4, 4, 4, 8, 16),
+    ("k4s1_8x8", fk.CONV_S1, 4, 6, 8, 8, 64, 128),
+    ("c3_to8", fk.CONV_S1, 3, 2, 16, 16, 32, 8),                 # 8 padded output channels (stage-II image conv)
     ("k4s2_32", fk.CONV_K4S2, 4, 2, 32, 32, 128, 128),
     ("k4s2_8", fk.CONV_K4S2, 4, 16, 8, 8, 64, 256),
     ("deconv_4", fk.DECONV_K4S2, 4, 16, 4, 4, 128, 64),
@@ -334,6 +338,42 @@ def test_planes_im2col_col2im(K, np_):
     og = torch.zeros(3, 16, 16, 3, device="cuda")
     K.col2im_k4s2_c3(c2g, og, bias.cuda())
     check_close("col2im", og.cpu(), out, 1e-5, 1.0)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_stage2_image_end_kernels(K, np_):
+    gen = torch.Generator().manual_seed(8)
+    img = torch.rand(2, 16, 16, 3, generator=gen) * 2 - 1
+    col = torch.zeros(np_, 2 * 256, 32, dtype=torch.bfloat16)
+    fk.im2col_k3s1_c3(img, col)
+    cg = torch.full_like(col, 3.0).cuda()
+    K.im2col_k3s1_c3(img.cuda(), cg)
+    check_close("im2col3", fk.val(cg.cpu()), fk.val(col), 2.0 ** -8 if np_ == 1 else 1e-5, 1e-3)
+    lg, lgg = both(np_, (2, 16, 16, 8), gen)
+    y = torch.zeros(2, 16, 16, 3)
+    fk.tanh_c3_fwd(lg, y)
+    yg = torch.zeros_like(y).cuda()
+    K.tanh_c3_fwd(lgg, yg)
+    check_close("tanh fwd", yg.cpu(), y, 1e-5, 1.0)
+    dy = torch.randn(2, 16, 16, 3, generator=gen)
+    dl = torch.zeros_like(lg)
+    fk.tanh_c3_bwd(y, dy, dl)
+    dlg = torch.full_like(lg, 1.0).cuda()
+    K.tanh_c3_bwd(yg, dy.cuda(), dlg)
+    check_close("tanh bwd", fk.val(dlg.cpu()), fk.val(dl), *tol(np_))
+    # the 32 -> 3 image conv as a GEMM with 8 padded output channels, forward and input-gradient
+    x, xg = both(np_, (2, 16, 16, 32), gen)
+    w = rand_planes(np_, (9, 8, 32), gen, scale=(9 * 32) ** -0.5)
+    out = torch.zeros(np_, 2, 16, 16, 8, dtype=torch.bfloat16)
+    fk.conv_gemm(fk.CONV_S1, 3, 0, fk.View(x), w, fk.View(out))
+    og = torch.zeros_like(out).cuda()
+    K.conv_gemm(K.CONV_S1, 3, 0, K.View(xg), w.cuda(), K.View(og))
+    check_close("conv to 8", fk.val(og.cpu()), fk.val(out), *tol(np_))
+    dx = torch.zeros_like(x)
+    fk.conv_gemm(fk.CONV_S1, 3, 1, fk.View(out), w, fk.View(dx), w_kn=True)
+    dxg = torch.zeros_like(x).cuda()
+    K.conv_gemm(K.CONV_S1, 3, 1, K.View(out.cuda()), w.cuda(), K.View(dxg), w_kn=True)     # same input planes as the restatement
+    check_close("dgrad from 8", fk.val(dxg.cpu()), fk.val(dx), *tol(np_))
 
 
 def test_conv3x3_c3_tanh(K):

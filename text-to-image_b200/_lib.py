@@ -48,6 +48,9 @@ SIGNATURES = {
     "t2i_from_planes": [_P, _LL, _I, _P, _LL, _P],
     "t2i_im2col_k4s2_c3": [_P, _I, _I, _I, _P, _P, _LL, _I, _P],
     "t2i_col2im_k4s2_c3": [_P, _LL, _I, _I, _I, _I, _P, _P, _P],
+    "t2i_im2col_k3s1_c3": [_P, _I, _I, _I, _P, _LL, _I, _P],
+    "t2i_tanh_c3_fwd": [_P, _LL, _I, _P, _LL, _P],
+    "t2i_tanh_c3_bwd": [_P, _P, _P, _LL, _I, _LL, _P],
     "t2i_conv3x3_c3_tanh_fwd": [_P, _P, _P, _P, _I, _I, _I, _P],
     "t2i_conv3x3_c3_tanh_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _I, _I, _I, _P],
     "t2i_colsum": [_P, _LL, _I, _LL, _I, _I, _I, _P, _P],

@@ -221,6 +221,51 @@ __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps
     }
 }
 
+// 3x3 / stride 1 patches of a 3-channel image: row = pixel, column (kh*3 + kw)*3 + c (27 of 32 used)
+__global__ void im2col_k3s1_c3_kernel(const float* __restrict__ img, int n, int h, int w, bf16* col, long long ps, int np) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long items = (long long)n * h * w * 4;     // (pixel, chunk of 8 columns)
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+        const long long r = i >> 2;
+        const int chunk = (int)(i & 3);
+        const int ow = (int)(r % w), oh = (int)((r / w) % h);
+        const float* base = img + (r - (long long)oh * w - ow) * 3;     // pixel (b, 0, 0)
+        float v[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int colj = chunk * 8 + j;
+            const int tap = colj / 3, c = colj - tap * 3;
+            const int ih = oh + tap / 3 - 1, iw = ow + tap % 3 - 1;
+            v[j] = (colj < 27 && ih >= 0 && ih < h && iw >= 0 && iw < w) ? __ldg(base + ((long long)ih * w + iw) * 3 + c) : 0.f;
+        }
+        store8(col + r * 32 + chunk * 8, ps, np, v);
+    }
+}
+__global__ void tanh_c3_fwd_kernel(const bf16* __restrict__ lg, long long ps, int np, float* img, long long pixels) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+        float v[8];
+        load8(lg + i * 8, ps, np, v);
+        img[i * 3 + 0] = tanhf(v[0]); img[i * 3 + 1] = tanhf(v[1]); img[i * 3 + 2] = tanhf(v[2]);
+    }
+}
+__global__ void tanh_c3_bwd_kernel(const float* __restrict__ img, const float* __restrict__ dimg, bf16* dlg, long long ps,
+                                   int np, long long pixels) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < pixels; i += (long long)gridDim.x * blockDim.x) {
+        float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            const float y = img[i * 3 + c];
+            v[c] = dimg[i * 3 + c] * (1.f - y * y);
+        }
+        store8(dlg + i * 8, ps, np, v);
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // g_net's last conv: 3 -> 3 channels, 3x3 stride 1 SAME, then tanh.  w is TF HWIO [3][3][3][3].
 __global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
@@ -1159,6 +1204,22 @@ extern "C" int t2i_col2im_k4s2_c3(const void* col, long long ps, int np, int n, 
     launch_ew(col2im_k4s2_c3_kernel, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256), shm, STREAM, static_cast<const bf16*>(col), ps, np,
                                                                                       n, h, w, bias3, img);
     return check_launch("col2im_k4s2_c3");
+}
+extern "C" int t2i_im2col_k3s1_c3(const float* img, int n, int h, int w, void* col, long long ps, int np, void* stream) {
+    launch_ew(im2col_k3s1_c3_kernel, dim3(grid_for((long long)n * h * w * 4, 256, 16)), dim3(256), 0, STREAM, img, n, h, w,
+              static_cast<bf16*>(col), ps, np);
+    return check_launch("im2col_k3s1_c3");
+}
+extern "C" int t2i_tanh_c3_fwd(const void* logits8, long long ps, int np, float* img, long long pixels, void* stream) {
+    launch_ew(tanh_c3_fwd_kernel, dim3(grid_for(pixels, 256, 16)), dim3(256), 0, STREAM, static_cast<const bf16*>(logits8), ps,
+              np, img, pixels);
+    return check_launch("tanh_c3_fwd");
+}
+extern "C" int t2i_tanh_c3_bwd(const float* img, const float* dimg, void* dlogits8, long long ps, int np, long long pixels,
+                               void* stream) {
+    launch_ew(tanh_c3_bwd_kernel, dim3(grid_for(pixels, 256, 16)), dim3(256), 0, STREAM, img, dimg, static_cast<bf16*>(dlogits8),
+              ps, np, pixels);
+    return check_launch("tanh_c3_bwd");
 }
 extern "C" int t2i_conv3x3_c3_tanh_fwd(const float* x, const float* w, const float* b, float* y, int n, int h, int wd,
                                        void* stream) {

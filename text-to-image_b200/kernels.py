@@ -172,6 +172,22 @@ def col2im_k4s2_c3(col, img, bias3=None):
     _lib.call("t2i_col2im_k4s2_c3", _p(col), _ps(col), col.shape[0], n, h, w, _p(bias3), _f32(img), _stream())
 
 
+def im2col_k3s1_c3(img, col):
+    """fp32 NHWC 3-channel image -> planes [np, n*h*w, 32] of 3x3 / stride-1 SAME patches (27 columns used)"""
+    n, h, w, _ = img.shape
+    _lib.call("t2i_im2col_k3s1_c3", _f32(img), n, h, w, _p(col), _ps(col), col.shape[0], _stream())
+
+
+def tanh_c3_fwd(logits8, img):
+    """planes [np, ..., 8] (3 channels used) -> tanh -> fp32 [..., 3]"""
+    _lib.call("t2i_tanh_c3_fwd", _p(logits8), _ps(logits8), logits8.shape[0], _f32(img), img.numel() // 3, _stream())
+
+
+def tanh_c3_bwd(img, dimg, dlogits8):
+    _lib.call("t2i_tanh_c3_bwd", _f32(img), _f32(dimg), _p(dlogits8), _ps(dlogits8), dlogits8.shape[0], img.numel() // 3,
+              _stream())
+
+
 def conv3x3_c3_tanh_fwd(x, w, b, y):
     n, h, wd, _ = x.shape
     _lib.call("t2i_conv3x3_c3_tanh_fwd", _f32(x), _f32(w), _f32(b), _f32(y), n, h, wd, _stream())
