@@ -180,8 +180,11 @@ def conv2d(p, scope, x, k, s, padding="SAME", act=None):
     w = p[scope + "/weights"].permute(3, 2, 0, 1)
     pad = 0
     if padding.upper() == "SAME":
-        assert (k, s) in ((4, 2), (3, 1), (1, 1)), "only the path's symmetric SAME cases"
-        pad = {4: 1, 3: 1, 1: 0}[k]
+        assert (k, s) in ((4, 2), (3, 1), (1, 1), (4, 1)), "only the SAME cases of the implemented paths"
+        if (k, s) == (4, 1):     # pad_total = 3: TF puts 1 before and 2 after (StackGAN stage-II)
+            x = F.pad(x, (1, 2, 1, 2))
+        else:
+            pad = {4: 1, 3: 1, 1: 0}[k]
     y = F.conv2d(x, w, p[scope + "/biases"], stride=s, padding=pad)
     return act(y) if act is not None else y
 
