@@ -80,6 +80,10 @@ typedef struct {
     float* stat_dot;
     t2i_act stat_x;
     int stat_n, stat_c;
+    /* first output channel inside the weight matrix: y's c channels are output channels [w_n0, w_n0 + y.c) of w
+     * (an output-channel window, e.g. the two halves of a concat gradient with different epilogues); bias,
+     * add / mask / stat_x and the stat_* vectors are indexed by the WINDOW's channels. */
+    int w_n0;
 } t2i_conv_gemm_desc;
 int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
 
@@ -161,15 +165,17 @@ int t2i_bn_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x
  * data-parallel ranks (synchronised BatchNorm = the reference's whole-batch statistics, utils/ops.py:20-29);
  * out_scale = 1 / world then keeps the later gradient all-reduce(sum) exact.
  * relu: 0 none, 1 ReLU, 2 LeakyReLU(0.2).  y_pitch / dy_pitch (0 = c): channels per pixel in memory of y / dy when
- * they are the leading channels of a wider buffer (the discriminator's concat buffer). */
+ * they are the leading channels of a wider buffer (the discriminator's concat buffer).  affine_scale multiplies gamma
+ * and beta (StackGAN stage-II adds a BatchNorm output to itself, models/stackgan/stageII/model.py:117; pass
+ * out_scale = affine_scale backward so that dgamma / dbeta are those of the unscaled parameters). */
 int t2i_bn_apply_train(const void* x, long long x_ps, const float* sums, float eps, const float* gamma,
                        const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                        long long rows, int c, int relu, float* mean, float* rstd, float* var, float* moving_mean,
-                       float* moving_var, float decay, long long stat_rows, int y_pitch, void* stream);
+                       float* moving_var, float decay, long long stat_rows, int y_pitch, float affine_scale, void* stream);
 int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                      const float* rstd, const float* gamma, const float* dot, const float* dbeta, float* dgamma,
                      float* dbeta_out, float out_scale, int dot_normalised, void* dx, long long dx_ps, float* dx_sum,
-                     int np, long long rows, int c, long long stat_rows, int dy_pitch, void* stream);
+                     int np, long long rows, int c, long long stat_rows, int dy_pitch, float affine_scale, void* stream);
 int t2i_bn_update_moving(float* moving_mean, float* moving_var, const float* mean, const float* var,
                          long long rows, int c, float decay, void* stream);
 /* dst = dy * act'(y)  (relu / lrelu masks on post-activation values) */

@@ -89,12 +89,12 @@ def _conv_core(mode, k, flip, x, w):
 
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
               algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
-              stat_c=0):
+              stat_c=0, w_n0=0):
     xv = x.values()
     wv = val(w)
     if w_kn:
         wv = wv.transpose(1, 2)
-    wv = wv[:, :y.c, :xv.shape[-1]]
+    wv = wv[:, w_n0:w_n0 + y.c, :xv.shape[-1]]
     v = _conv_core(mode, k, flip, xv, wv)
     if bias is not None:
         v = v + bias.double()[:y.c]
@@ -228,7 +228,7 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 
 
 def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
-                   decay=0.9, stat_rows=0, y_pitch=0):
+                   decay=0.9, stat_rows=0, y_pitch=0, affine_scale=1.0):
     c = x.shape[-1]
     rows = stat_rows if stat_rows > 0 else x[0].numel() // c
     m = sums[:c].double() / rows
@@ -236,7 +236,7 @@ def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None,
     mean.copy_(m); var.copy_(s); rstd.copy_(torch.rsqrt(s + eps))
     if moving is not None:
         bn_update_moving(moving[0], moving[1], mean, var, rows, decay)
-    v = (val(x) - mean.double()) * rstd.double() * gamma.double() + beta.double()
+    v = ((val(x) - mean.double()) * rstd.double() * gamma.double() + beta.double()) * affine_scale
     if residual is not None:
         v = v + val(residual)
     if relu:
@@ -249,7 +249,7 @@ def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None,
 
 
 def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, dbeta_out=None, out_scale=1.0,
-                 dot_normalised=False, stat_rows=0, dy_pitch=0):
+                 dot_normalised=False, stat_rows=0, dy_pitch=0, affine_scale=1.0):
     c = x.shape[-1]
     rows = stat_rows if stat_rows > 0 else x[0].numel() // c
     if dy_pitch not in (0, c):
@@ -261,7 +261,7 @@ def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, 
         dbeta_out += db * out_scale
     g = val(dy).reshape(val(x).shape)
     xh = (val(x) - mean.double()) * rstd.double()
-    out = gamma.double() * rstd.double() * (g - db / rows - xh * dg / rows)
+    out = gamma.double() * affine_scale * rstd.double() * (g - db / rows - xh * dg / rows)
     put(dx, out)
     if dx_sum is not None:
         dx_sum += out.reshape(-1, c).sum(0)

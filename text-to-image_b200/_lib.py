@@ -31,7 +31,7 @@ class ConvGemmDesc(C.Structure):
                 ("w_layout", C.c_int),
                 ("y", Act), ("bias", C.c_void_p), ("add", Act), ("mask", Act), ("act", C.c_int),
                 ("mask_kind", C.c_int), ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("stat_dot", C.c_void_p),
-                ("stat_x", Act), ("stat_n", C.c_int), ("stat_c", C.c_int)]
+                ("stat_x", Act), ("stat_n", C.c_int), ("stat_c", C.c_int), ("w_n0", C.c_int)]
 
 
 class WgradDesc(C.Structure):
@@ -58,8 +58,8 @@ SIGNATURES = {
     "t2i_bn_apply": [_P, _LL, _P, _P, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P],
     "t2i_bn_bwd_reduce": [_P, _LL, _P, _LL, _P, _P, _I, _LL, _I, _P, _P, _P],
     "t2i_bn_bwd_apply": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _LL, _I, _LL, _I, _P],
-    "t2i_bn_apply_train": [_P, _LL, _P, _F, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _F, _LL, _I, _P],
-    "t2i_bn_bwd_fused": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _F, _I, _P, _LL, _P, _I, _LL, _I, _LL, _I, _P],
+    "t2i_bn_apply_train": [_P, _LL, _P, _F, _P, _P, _P, _LL, _P, _LL, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _F, _LL, _I, _F, _P],
+    "t2i_bn_bwd_fused": [_P, _LL, _P, _LL, _P, _P, _P, _P, _P, _P, _P, _F, _I, _P, _LL, _P, _I, _LL, _I, _LL, _I, _F, _P],
     "t2i_ce_seeds": [_P, _I, _F, _F, _F, _P, _P, _P],
     "t2i_s1_scalars": [_P, _P, _I, _I, _F, _F, _I, _P],
     "t2i_bn_update_moving": [_P, _P, _P, _P, _LL, _I, _F, _P],

@@ -60,6 +60,7 @@ struct alignas(64) ConvGemmParams {
     float* stat_second;
     int second_kind;
     int stat_n, stat_c;
+    int w_n0;                  // first output channel inside the weight matrix (output-channel window)
     int stat_acc;              // channels of per-CTA shared accumulators (flushed once at the end), 0 = none
     int dbg;                   // T2I_STAT_DBG bit field (tools/bench_conv.py): skip parts of the statistics path
 };
@@ -209,7 +210,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                         for (int kc = 0; kc < prm.k_chunks; ++kc) {
                             mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                             uint8_t* sa = smem + stage * kStageBytes;
-                            const int brow = tc.ct * BLOCK_N + rank * kBRows;   // this CTA's slice of the weight tile
+                            const int brow = prm.w_n0 + tc.ct * BLOCK_N + rank * kBRows;   // this CTA's slice of the weight tile
                             if (!CTA2) {
                                 mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                                 tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, tc.q0 + tap.dq,
@@ -662,7 +663,9 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const bool kn = d->w_layout == T2I_W_KN;
     const int w_n = kn ? d->w_cols : d->w_rows, w_k = kn ? d->w_rows : d->w_cols;
     if (x.c > w_k || d->w_cols % 8 != 0) return fail(T2I_ERR_BAD_ARG, "x.c=%d vs weight contraction=%d (cols %d)", x.c, w_k, d->w_cols);
-    if (y.c > w_n || y.c % 8 != 0 || y.pitch % 8 != 0 || y.coff % 8 != 0)
+    if (d->w_n0 < 0 || d->w_n0 % 8 != 0) return fail(T2I_ERR_BAD_ARG, "w_n0 must be a non-negative multiple of 8");
+    prm.w_n0 = d->w_n0;
+    if (d->w_n0 + y.c > w_n || y.c % 8 != 0 || y.pitch % 8 != 0 || y.coff % 8 != 0)
         return fail(T2I_ERR_BAD_ARG, "bad output channels c=%d pitch=%d coff=%d weight n=%d", y.c, y.pitch, y.coff, w_n);
     // virtual grid and output extent
     int OH, OW;

@@ -597,7 +597,7 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
                                       const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
                                       bf16* __restrict__ y, long long y_ps, int np, long long rows, int c, int relu, int CG,
                                       float* mean_out, float* rstd_out, float* var_out, float* mm, float* mv, float decay,
-                                      float bessel, int y_pitch) {
+                                      float bessel, int y_pitch, float affine_scale) {
     pdl_launch_dependents();
     pdl_wait();
     const int RY = blockDim.x / CG;
@@ -627,8 +627,8 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
                     mv[ch + j] = decay * mv[ch + j] + (1.f - decay) * v * bessel;
                 }
             }
-            sc[j] = rs * ga[j];
-            sh[j] = be[j] - m * sc[j];
+            sc[j] = rs * ga[j] * affine_scale;
+            sh[j] = be[j] * affine_scale - m * sc[j];
         }
     }
     // four rows per trip, all loads issued before the first use
@@ -672,7 +672,7 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
                                     const float* __restrict__ gamma, const float* __restrict__ dot,
                                     const float* __restrict__ dbeta, float* dgamma_out, float* dbeta_out, float out_scale,
                                     int dot_normalised, bf16* __restrict__ dx, long long dx_ps, float* dx_sum, int np,
-                                    long long rows, int c, float inv_rows, int CG, int dy_pitch) {
+                                    long long rows, int c, float inv_rows, int CG, int dy_pitch, float affine_scale) {
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sh[256 * 8];
@@ -699,7 +699,7 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
                     dgamma_out[ch + j] += dg * out_scale;
                     if (dbeta_out != nullptr) dbeta_out[ch + j] += db * out_scale;
                 }
-                a[j] = ga[j] * rs[j];
+                a[j] = ga[j] * affine_scale * rs[j];
                 b0[j] = db * inv_rows;
                 b1[j] = dg * inv_rows;
             }
@@ -1280,7 +1280,7 @@ extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* su
                                   const float* beta, const void* residual, long long r_ps, void* y, long long y_ps, int np,
                                   long long rows, int c, int relu, float* mean, float* rstd, float* var,
                                   float* moving_mean, float* moving_var, float decay, long long stat_rows, int y_pitch,
-                                  void* stream) {
+                                  float affine_scale, void* stream) {
     if (c % 8 || y_pitch % 8) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: c and y_pitch must be multiples of 8");
     if (y_pitch == 0) y_pitch = c;
     if (y_pitch < c) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: y_pitch %d < c %d", y_pitch, c);
@@ -1293,14 +1293,14 @@ extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* su
     launch_ew(bn_apply_train_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)n, eps, gamma, beta, static_cast<const bf16*>(residual),
         r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel,
-        y_pitch);
+        y_pitch, affine_scale);
     return check_launch("bn_apply_train");
 }
 extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
                                 const float* rstd, const float* gamma, const float* dot, const float* dbeta,
                                 float* dgamma, float* dbeta_out, float out_scale, int dot_normalised, void* dx,
                                 long long dx_ps, float* dx_sum, int np, long long rows, int c, long long stat_rows,
-                                int dy_pitch, void* stream) {
+                                int dy_pitch, float affine_scale, void* stream) {
     if (c % 8 || dy_pitch % 8) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: c and dy_pitch must be multiples of 8");
     if (dy_pitch == 0) dy_pitch = c;
     int CG;
@@ -1310,7 +1310,7 @@ extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, 
     launch_ew(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, STREAM, 
         static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,
         dbeta_out, out_scale, dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)n, CG,
-        dy_pitch);
+        dy_pitch, affine_scale);
     return check_launch("bn_bwd_fused");
 }
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,

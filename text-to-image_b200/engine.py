@@ -114,16 +114,14 @@ class Engine:
         ]
         return layers, [], []       # layers, BatchNorm channel counts, BatchNorm TF scopes
 
-    def _build_params(self):
+    def _g_layers(self):
+        """g_net contraction layers in creation order (models/wgancls/model.py:163-225) and its BatchNorm list."""
         K = self.K
-        gf, df, ce, E, Z = self.gf, self.df, self.ce, self.E, self.Z
+        gf, ce, E, Z = self.gf, self.ce, self.E, self.Z
         C1, C2, C4, C8 = gf, 2 * gf, 4 * gf, 8 * gf
-        S1, K4, DC = K.CONV_S1, K.CONV_K4S2, K.DECONV_K4S2
-        d, g = "d_net/", "g_net/"
-        L = Layer
-        d_layers, self.dbn_ch, self.dbn_tf = self._d_layers()
-        self.dl = OrderedDict((l.name, l) for l in d_layers)
-        self.gl = OrderedDict((l.name, l) for l in [
+        S1, DC = K.CONV_S1, K.DECONV_K4S2
+        g, L = "g_net/", Layer
+        layers = [
             L("ms", "ms", (g + "dense", g + "dense_1"), (g + "dense", g + "dense_1"), S1, 1, 1, 2 * ce, E,
               need_bwd=False),
             L("fc0", "fc0", g + "dense_2", g + "dense_2", S1, 1, 1, 16 * C8, Z + ce),
@@ -141,13 +139,20 @@ class Engine:
             L("c8", "conv", g + "Conv_8", g + "Conv_8", S1, 3, 9, C1, C1),
             L("t3", "col_out", g + "Conv2d_transpose_3", g + "Conv2d_transpose_3", S1, 1, 1, 64, C1),
             L("c9", "c9", g + "Conv_9", g + "Conv_9", None, 3, 9, 3, 3, need_bwd=False),
-        ])
-        # BatchNorm layers of g_net in creation order (model.py:176-216): (tf scope, channels)
-        self.bn_ch = [16 * C8, C2, C2, C8, C4, C1, C1, C4, C2, C1]
-        self.bn_tf = [g + "BatchNorm" + ("" if i == 0 else "_%d" % i) for i in range(10)]
+        ]
+        # BatchNorm layers of g_net in creation order (model.py:176-216)
+        bn_ch = [16 * C8, C2, C2, C8, C4, C1, C1, C4, C2, C1]
+        bn_tf = [g + "BatchNorm" + ("" if i == 0 else "_%d" % i) for i in range(10)]
+        return layers, bn_ch, bn_tf
+
+    def _build_params(self):
+        d_layers, self.dbn_ch, self.dbn_tf = self._d_layers()
+        g_layers, self.bn_ch, self.bn_tf = self._g_layers()
+        self.dl = OrderedDict((l.name, l) for l in d_layers)
+        self.gl = OrderedDict((l.name, l) for l in g_layers)
 
         def bias_len(l):
-            return {"dout": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)
+            return {"dout": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)     # img_out: 8 (3 used, zero padded)
 
         def layout(layers, bn_ch):
             off, table = 0, OrderedDict()
@@ -192,10 +197,11 @@ class Engine:
                 l.gw = l.gw.view(l.taps, l.cout, l.cin)
                 off, n = (self.d_table if net == "d" else self.g_table)[l.name + ".w"]
                 l.Wf = self.packed[net][:, off:off + n].view(self.np, l.taps, l.cout, l.cin)
-        self.bn_gamma = [self.P["g.bn%d.gamma" % i] for i in range(10)]
-        self.bn_beta = [self.P["g.bn%d.beta" % i] for i in range(10)]
-        self.bn_dgamma = [self.G["g.bn%d.gamma" % i] for i in range(10)]
-        self.bn_dbeta = [self.G["g.bn%d.beta" % i] for i in range(10)]
+        ng = range(len(self.bn_ch))
+        self.bn_gamma = [self.P["g.bn%d.gamma" % i] for i in ng]
+        self.bn_beta = [self.P["g.bn%d.beta" % i] for i in ng]
+        self.bn_dgamma = [self.G["g.bn%d.gamma" % i] for i in ng]
+        self.bn_dbeta = [self.G["g.bn%d.beta" % i] for i in ng]
         self.bn_mm = [torch.zeros(c, **f32) for c in self.bn_ch]
         self.bn_mv = [torch.ones(c, **f32) for c in self.bn_ch]
         self.bn_mean = [torch.zeros(c, **f32) for c in self.bn_ch]
@@ -254,6 +260,16 @@ class Engine:
             out = torch.zeros(1, 64, l.cin, dtype=w.dtype)
             out[0, :48] = w.reshape(48, l.cin)
             return out
+        if l.kind == "col3_in":  # 3x3 conv on 3 channels: [3,3,3,co] -> [co, (kh*3+kw)*3+c], zero padded to 32 columns
+            w = p[l.tf_w + "/weights"]
+            out = torch.zeros(1, l.cout, 32, dtype=w.dtype)
+            out[0, :, :27] = w.reshape(27, l.cout).t()
+            return out
+        if l.kind == "img_out":  # 3x3 conv to 3 channels: [3,3,ci,3] -> [tap][8][ci], output rows 3..7 zero
+            w = p[l.tf_w + "/weights"]
+            out = torch.zeros(9, 8, l.cin, dtype=w.dtype)
+            out[:, :3] = w.permute(0, 1, 3, 2).reshape(9, 3, l.cin)
+            return out
         if l.kind == "dout":     # [4,4,C,1] -> (kh,kw,c) flat == NHWC order of the 4x4xC activation
             return p[l.tf_w + "/weights"].reshape(-1)
         if l.kind == "c9":
@@ -279,6 +295,10 @@ class Engine:
             out[l.tf_w + "/weights"] = w.reshape(l.cout, 64)[:, :48].t().reshape(4, 4, 3, l.cout).contiguous()
         elif l.kind == "col_out":
             out[l.tf_w + "/weights"] = w.reshape(64, l.cin)[:48].reshape(4, 4, 3, l.cin).clone()
+        elif l.kind == "col3_in":
+            out[l.tf_w + "/weights"] = w.reshape(l.cout, 32)[:, :27].t().reshape(3, 3, 3, l.cout).contiguous()
+        elif l.kind == "img_out":
+            out[l.tf_w + "/weights"] = w.reshape(3, 3, 8, l.cin)[:, :, :3].permute(0, 1, 3, 2).contiguous()
         elif l.kind == "dout":
             out[l.tf_w + "/weights"] = w.reshape(4, 4, -1, 1).clone()
         elif l.kind == "c9":
@@ -304,6 +324,8 @@ class Engine:
                 b = torch.cat([p[n] for n in self._b_names(l)])
                 if l.kind == "fc0":
                     b = self._perm_fc0(b)
+                if l.kind == "img_out":
+                    b = torch.cat([b, torch.zeros(5, dtype=b.dtype)])
                 views["%s.%s.b" % (net, l.name)].copy_(b)
         for i, scope in enumerate(self.bn_tf):
             perm = (lambda v: self._perm_fc0(v)) if i == 0 else (lambda v: v)
@@ -353,6 +375,8 @@ class Engine:
                 b = flat_views["%s.%s.b" % (net, l.name)].detach().cpu()
                 if l.kind == "fc0":
                     b = self._perm_fc0(b, inverse=True)
+                if l.kind == "img_out":
+                    b = b[:3]
                 names = self._b_names(l)
                 for j, n in enumerate(names):
                     out[n] = b.reshape(len(names), -1)[j].clone()

@@ -99,8 +99,9 @@ def _prof_end(ev, kernel, tag, flops, nbytes):
 
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
               algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
-              stat_c=0):
+              stat_c=0, w_n0=0):
     """y = act(conv(x, w) + bias + add) * mask'(mask); w: planes [np, taps, rows, cols].
+    w_n0: y's channels are output channels [w_n0, w_n0 + y.c) of the weight matrix (output-channel window).
     w_kn=False: rows = output channels, cols = contraction (forward use of a layer's packed weights);
     w_kn=True : rows = contraction, cols = output channels (the same weights used for the input-gradient).
     algo_scale: fraction of the contraction that is algorithmic (0.75 for the 48-of-64 patch columns).
@@ -124,6 +125,7 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     d.stat_dot = None if stat_dot is None else _f32(stat_dot).value
     d.stat_x = stat_x._act() if stat_x is not None else _null_act()
     d.stat_n, d.stat_c = stat_n, stat_c
+    d.w_n0 = w_n0
     _lib.call("t2i_conv_gemm", C.byref(d), _stream())
     if ev is not None:
         opix = y.n * y.H * y.W
@@ -226,7 +228,7 @@ def bn_apply(x, mean, rstd, gamma, beta, y, residual=None, relu=False):
 
 
 def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None, relu=False, moving=None,
-                   decay=0.9, stat_rows=0, y_pitch=0):
+                   decay=0.9, stat_rows=0, y_pitch=0, affine_scale=1.0):
     """sums: fp32 [2c] = [sum x | sum x^2] from conv_gemm(stat_sum=, stat_sq=); moving: (mm, mv) or None;
     relu: False / True (ReLU) / 2 (LeakyReLU 0.2); stat_rows: values per channel behind the sums when they were
     all-reduced over ranks (0 = this tensor's rows); y_pitch: y is the leading c channels of a [.., y_pitch] buffer."""
@@ -234,18 +236,18 @@ def bn_apply_train(x, sums, eps, gamma, beta, y, mean, rstd, var, residual=None,
     mm, mv = moving if moving is not None else (None, None)
     _lib.call("t2i_bn_apply_train", _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(beta), _p(residual),
               0 if residual is None else _ps(residual), _p(y), _ps(y), x.shape[0], rows, c, int(relu), _f32(mean),
-              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, stat_rows, y_pitch, _stream())
+              _f32(rstd), _f32(var), _p(mm), _p(mv), decay, stat_rows, y_pitch, affine_scale, _stream())
 
 
 def bn_bwd_fused(dy, x, mean, rstd, gamma, dot, dbeta, dgamma, dx, dx_sum=None, dbeta_out=None, out_scale=1.0,
-                 dot_normalised=False, stat_rows=0, dy_pitch=0):
+                 dot_normalised=False, stat_rows=0, dy_pitch=0, affine_scale=1.0):
     """dbeta / dot: the reductions conv_gemm(stat_sum=dbeta, stat_dot=dot, stat_x=x) produced with dy
     (dot_normalised: dot = sum dy * xhat, as bn_bwd_reduce writes it).  dgamma += out_scale * (...),
     dbeta_out += out_scale * dbeta (when the sums live in a scratch that was all-reduced)."""
     rows, c = _rows_c(x)
     _lib.call("t2i_bn_bwd_fused", _p(dy), _ps(dy), _p(x), _ps(x), _f32(mean), _f32(rstd), _f32(gamma), _f32(dot),
               _f32(dbeta), _f32(dgamma), _p(dbeta_out), out_scale, int(dot_normalised), _p(dx), _ps(dx), _p(dx_sum),
-              x.shape[0], rows, c, stat_rows, dy_pitch, _stream())
+              x.shape[0], rows, c, stat_rows, dy_pitch, affine_scale, _stream())
 
 
 def ce_seeds(logit, n, label, weight, inv_global_batch, seed, loss_sum):
