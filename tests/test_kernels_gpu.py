@@ -566,3 +566,63 @@ def test_gp_ca_scalar_adam_pack_kernels(K):
         check_close("adam m", mg_.cpu(), m1, 1e-6, 1.0)     # untouched when beta1 == 0
         check_close("adam v", vg_.cpu(), v1, 1e-6, 1.0)
         check_close("adam packed", fk.val(pkg.cpu()), fk.val(pk), 2.0 ** -7 if np_ == 1 else 1e-4, 1e-2)
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_conv_gemm_output_channel_window(K, np_):
+    """w_n0: the output is a window of the weight matrix's output channels (stage-II splits the gradient of the
+    generator's concat buffer into two windows with different epilogues), in both weight layouts."""
+    gen = torch.Generator().manual_seed(23)
+    N, H, W, Cin, Cout = 16, 4, 4, 128, 640
+    x, xg = both(np_, (N, H, W, Cin), gen)
+    w = rand_planes(np_, (9, Cout, Cin), gen, scale=(9 * Cin) ** -0.5)
+    w_kn = w.transpose(2, 3).contiguous()
+    ybuf = rand_planes(np_, (N, H, W, Cout), gen)
+    mask, maskg = both(np_, (N, H, W, Cout), gen)
+    for n0, c, epi in ((0, 512, True), (512, 128, False), (128, 192, False)):
+        yref = ybuf.clone()
+        kw_f = dict(mask=fk.View(mask, coff=n0, c=c), mask_kind=fk.MASK_RELU) if epi else {}
+        fk.conv_gemm(fk.CONV_S1, 3, 1, fk.View(x), w, fk.View(yref, coff=n0, c=c), w_n0=n0, **kw_f)
+        for kn in (False, True):
+            yg = ybuf.cuda()
+            kw_g = dict(mask=K.View(maskg, coff=n0, c=c), mask_kind=K.MASK_RELU) if epi else {}
+            K.conv_gemm(K.CONV_S1, 3, 1, K.View(xg), (w_kn if kn else w).cuda(), K.View(yg, coff=n0, c=c), w_kn=kn,
+                        w_n0=n0, **kw_g)
+            torch.cuda.synchronize()
+            check_close("window %d+%d kn=%d" % (n0, c, kn), fk.val(yg.cpu()), fk.val(yref), *tol(np_))
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_fused_batch_norm_pitch_and_affine_scale(K, np_):
+    """y_pitch / dy_pitch (the tensor is the leading channels of a wider concat buffer) and affine_scale = 2
+    (models/stackgan/stageII/model.py:117 adds a BatchNorm output to itself), LeakyReLU activation."""
+    gen = torch.Generator().manual_seed(29)
+    rows, c, pitch = 512, 64, 96
+    x, xg = both(np_, (rows, c), gen, 2.0)
+    gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    xv = fk.val(x)
+    sums = torch.cat([xv.sum(0), (xv * xv).sum(0)]).float()
+    mean, rstd, var = torch.zeros(c), torch.zeros(c), torch.zeros(c)
+    ybuf = rand_planes(np_, (rows, pitch), gen)
+    y = ybuf.clone()
+    fk.bn_apply_train(x, sums.double(), 1e-5, gamma, beta, y, mean, rstd, var, relu=2, y_pitch=pitch, affine_scale=2.0)
+    yg = ybuf.cuda()
+    mg, rg, vg = [torch.zeros(c, device="cuda") for _ in range(3)]
+    K.bn_apply_train(xg, sums.cuda(), 1e-5, gamma.cuda(), beta.cuda(), yg, mg, rg, vg, relu=2, y_pitch=pitch,
+                     affine_scale=2.0)
+    check_close("y", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    assert torch.equal(yg.cpu()[..., c:], ybuf[..., c:])          # the trailing channels are not touched
+    dybuf, dybufg = both(np_, (rows, pitch), gen)
+    dyv = fk.val(dybuf)[:, :c]
+    dbeta, dot = dyv.sum(0).float(), (dyv * xv).sum(0).float()
+    dga, dbo = torch.full((c,), 0.5, dtype=torch.float64), torch.full((c,), -1.0, dtype=torch.float64)
+    dx = torch.zeros_like(x)
+    fk.bn_bwd_fused(dybuf, x, mean, rstd, gamma, dot.double(), dbeta.double(), dga, dx, dbeta_out=dbo, out_scale=2.0,
+                    dy_pitch=pitch, affine_scale=2.0)
+    dgag, dbog = torch.full((c,), 0.5, device="cuda"), torch.full((c,), -1.0, device="cuda")
+    dxg = torch.zeros_like(x).cuda()
+    K.bn_bwd_fused(dybufg, xg, mean.cuda(), rstd.cuda(), gamma.cuda(), dot.cuda(), dbeta.cuda(), dgag, dxg,
+                   dbeta_out=dbog, out_scale=2.0, dy_pitch=pitch, affine_scale=2.0)
+    check_close("dgamma", dgag.cpu(), dga, 5e-4, 5.0)
+    check_close("dbeta", dbog.cpu(), dbo, 5e-4, 5.0)
+    check_close("dx", fk.val(dxg.cpu()), fk.val(dx), *tol(np_))

@@ -120,3 +120,95 @@ def test_iteration_matches_oracle(np_):
         for n in p:
             if "moving" in n and not n.startswith(S2.D2):
                 assert rel(newp[n], p[n]) < 1e-9, n
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference-facing mirrors (models/stackgan/stageII/{model,trainer}.py) on the CPU restatement of the kernels
+def _cfgs(tmp_path, o):
+    from t2i_b200.utils.config import AttrDict
+    model = {"Z_DIM": o.z_dim, "EMBED_DIM": o.embed_dim, "COMPRESSED_EMBED_DIM": o.compressed_embed_dim}
+    train = {"BATCH_SIZE": o.batch_size, "SAMPLE_NUM": 2, "D_LR": o.lr, "G_LR": o.lr, "EPOCH": 1,
+             "D_BETA_DECAY": o.d_beta1, "G_BETA_DECAY": o.g_beta1, "CHECKPOINTS_TO_KEEP": 2,
+             "COEFF": {"ALPHA_MISMATCH_LOSS": o.alpha_mismatch, "KL": o.kl_coeff}}
+    c1 = AttrDict({"CHECKPOINT_DIR": str(tmp_path / "s1"), "TRAIN": dict(train),
+                   "MODEL": dict(model, OUTPUT_SIZE=64, GF_DIM=o.s1_gf_dim, DF_DIM=8,
+                                 IMAGE_SHAPE={"W": 64, "H": 64, "D": 3})})
+    c2 = AttrDict({"CHECKPOINT_DIR": str(tmp_path / "s2"), "TRAIN": dict(train),
+                   "MODEL": dict(model, OUTPUT_SIZE=256, GF_DIM=o.gf_dim, DF_DIM=o.df_dim,
+                                 IMAGE_SHAPE={"W": 256, "H": 256, "D": 3})})
+    return c1, c2
+
+
+def _models(tmp_path, o):
+    from t2i_b200.models.stackgan.stageI.model import ConditionalGan as StageI
+    from t2i_b200.models.stackgan.stageII.model import ConditionalGan as StageII
+    c1, c2 = _cfgs(tmp_path, o)
+    s1 = StageI(c1, precision="bf16x3", device="cpu", kernels=fk, use_graphs=False)
+    s2 = StageII(s1, c2)
+    return s1, s2, c1, c2
+
+
+def test_model_mirror_shares_stage1_generator_and_matches_oracle(tmp_path):
+    cfg = S2.Stage2Cfg(**TINY)
+    p = boosted_params(cfg)
+    s1, s2, c1, c2 = _models(tmp_path, cfg)
+    s2.set_variables(p)
+    # one copy of g_net/*: what stage-II received is what stage-I now holds
+    v1 = s1.get_variables()
+    for n in (k for k in p if k.startswith("g_net/")):
+        assert torch.equal(torch.as_tensor(v1[n]), p[n].float()), n
+    assert all(n.startswith(S2.G2) for n in s2.g_vars) and all(n.startswith(S2.D2) for n in s2.d_vars)
+    assert set(s2.g_vars) == set(S2.g_var_names(p)) and set(s2.d_vars) == set(S2.d_var_names(p))
+    feed = S2.make_feed(cfg, 3, torch.float32)
+    pf = {k: v.float() for k, v in p.items()}
+    with torch.no_grad():
+        img64, _, _ = S2.S1.generator(pf, feed["z"], feed["cond"], feed["tn_s1"], cfg.stage1())
+        G, mean, ls = S2.generator(pf, img64, feed["cond"], feed["tn_eps"], cfg)
+        Dx = S2.discriminator(pf, feed["x"], feed["cond"], cfg)
+    got64, _, _ = s1.generator(feed["z"], feed["cond"], noise=feed["tn_s1"])
+    img, mean_g, ls_g = s2.generator(got64, feed["cond"], noise=feed["tn_eps"])
+    assert rel(got64, img64) < 1e-3 and rel(img, G) < 5e-3 and rel(mean_g, mean) < 1e-3 and rel(ls_g, ls) < 1e-3
+    prob, logits = s2.discriminator(feed["x"], feed["cond"])
+    assert logits.shape == (cfg.batch_size, 1, 1, 1) and rel(logits, Dx) < 1e-2
+    assert torch.allclose(prob, torch.sigmoid(logits))
+    with pytest.raises(ValueError):
+        bad = _cfgs(tmp_path, cfg)[1]
+        bad.MODEL.OUTPUT_SIZE = 128
+        type(s2)(s1, bad)
+
+
+def test_trainer_two_checkpoint_restore(tmp_path):
+    from t2i_b200.models.stackgan.stageII.trainer import ConditionalGanTrainer
+    from t2i_b200.models.wgancls.trainer import SyntheticTextDataset
+    from t2i_b200.utils import saver
+    cfg = S2.Stage2Cfg(**TINY)
+    s1, s2, c1, c2 = _models(tmp_path, cfg)
+    # a stage-I checkpoint with recognisable generator weights (written by the stage-I model itself)
+    s1.initialize(seed=11)
+    saver.save(s1, c1.CHECKPOINT_DIR, 7)
+    g1 = {k: torch.as_tensor(v).clone() for k, v in s1.get_variables().items() if k.startswith("g_net/")}
+    s1.initialize(seed=12)       # clobber; the trainer must restore seed 11's generator from the stage-I directory
+    data = SyntheticTextDataset(embed_dim=cfg.embed_dim, num_examples=16, image_size=256)
+    tr = ConditionalGanTrainer(None, s2, data, c2, c1)
+    tr.train(max_updates=1)
+    assert len(tr.log) == 1 and np.isfinite(tr.log[0]["d_loss"]) and np.isfinite(tr.log[0]["g_loss"])
+    after = s2.get_variables()
+    for n, w in g1.items():
+        if "moving" not in n:      # frozen: the two runs did not touch the stage-I generator's trainables
+            assert torch.equal(torch.as_tensor(after[n]), w), n
+    # counter 2 -> a stage-II checkpoint that holds only the stage-II scopes (trainer.py:48-52,175-176)
+    import os
+    assert os.listdir(c2.CHECKPOINT_DIR) == ["wgancls-2.npz"]
+    z = np.load(os.path.join(c2.CHECKPOINT_DIR, "wgancls-2.npz"))
+    assert all(k.startswith((S2.G2, S2.D2, "__adam__/")) for k in z.files)
+    s2.initialize(seed=99)
+    tr2 = ConditionalGanTrainer(None, s2, data, c2, c1)
+    tr2.define_losses()
+    assert saver.load(tr2.stageii_saver, c2.CHECKPOINT_DIR) == (True, 2)
+    again = s2.get_variables()
+    for n in again:
+        if n.startswith((S2.G2, S2.D2)):
+            assert torch.equal(torch.as_tensor(again[n]), torch.as_tensor(after[n])), n
+    samples = s2.run(s2.sampler, feed_dict={s2.z_sample: np.random.normal(0, 1, (2, cfg.z_dim)),
+                                           s2.embed_sample: np.random.normal(0, 1, (2, cfg.embed_dim))})
+    assert samples.shape == (2, 256, 256, 3) and float(np.abs(samples).max()) <= 1.0

@@ -28,15 +28,23 @@ class StageIIEngine(Engine):
     FC0_NCHW = False
 
     def __init__(self, K, device, batch, np_=1, z_dim=100, embed_dim=1024, ce=128, gf=128, df=64, d_beta1=0.5,
-                 g_beta1=0.5, alpha=0.5, kl_coeff=2.0, world=1, allreduce=None, s1_gf=128, image=256, **kw):
+                 g_beta1=0.5, alpha=0.5, kl_coeff=2.0, world=1, allreduce=None, s1_gf=128, image=256, s1_engine=None,
+                 **kw):
         assert gf % 32 == 0, "stage-II needs GF_DIM to be a multiple of 32 (GF_DIM / 4 channels at 256x256)"
         assert image == 256, "the reference's stage-II is defined for 256x256 output (model.py:79: s16 = size // 64)"
         assert not kw.get("sync_bn")
         self.alpha, self.image = alpha, image
         share = kw.get("share_from")
-        # the frozen stage-I generator: parameters 'g_net/*', training-mode BatchNorm, moving statistics keep stepping
-        self.s1 = StageIEngine(K, device, batch, np_, z_dim, embed_dim, ce, s1_gf, 8, world=world,
-                               share_from=None if share is None else share.s1,
+        # the frozen stage-I generator: parameters 'g_net/*', training-mode BatchNorm, moving statistics keep stepping.
+        # s1_engine: a StageIEngine whose parameters are shared (the reference's stage-II graph contains the stage-I
+        # model object it was constructed with, models/stackgan/stageII/model.py:8,50); its d_net is never run here.
+        if share is None and s1_engine is not None:
+            s1_gf, s1_df, s1_from = s1_engine.gf, s1_engine.df, s1_engine
+        else:
+            s1_df, s1_from = (8, None) if share is None else (share.s1.df, share.s1)
+            s1_gf = s1_gf if share is None else share.s1.gf
+        self.s1 = StageIEngine(K, device, batch, np_, z_dim, embed_dim, ce, s1_gf, s1_df, world=world,
+                               share_from=s1_from,
                                **{k: v for k, v in kw.items() if k in ("act_dtype", "f32_dtype")}, use_graphs=False,
                                concurrent=False)
         super().__init__(K, device, batch, np_, z_dim, embed_dim, ce, gf, df, beta1=d_beta1, beta2=0.999,
@@ -228,8 +236,9 @@ class StageIIEngine(Engine):
                             dy_pitch=dy_pitch, affine_scale=affine_scale)
 
     # ------------------------------------------------------------------ generator
-    def g2_forward(self, img_out, kl_sum, train=True, cond_noise=True, update_moving=True):
-        """stage-I generator (training-mode BatchNorm when train) -> stage-II generator; image -> img_out fp32 NHWC."""
+    def g2_forward(self, img_out, kl_sum, train=True, cond_noise=True, update_moving=True, run_stage1=True):
+        """stage-I generator (training-mode BatchNorm when train) -> stage-II generator; image -> img_out fp32 NHWC.
+        run_stage1=False: the 64x64 input image is already in g['img64'] (eager ``generator(image, embed)`` calls)."""
         K, g, gl, V = self.K, self.g, self.gl, self.K.View
         S1 = K.CONV_S1
         rows = self._rows
@@ -238,9 +247,10 @@ class StageIIEngine(Engine):
         bn = lambda i, x, y, act, **kw: self._bn("g", g, i, x, y, act, train=train, update_moving=update_moving, **kw)
         # model.py:50-51: the stage-I generator runs inside the stage-II graph
         s1 = self.s1
-        s1.g["kl_scratch"].zero_()
-        s1.g_forward(g["z"], self.feed["cond"], g["tn1"], g["img64"], s1.g["kl_scratch"], train=train,
-                     cond_noise=cond_noise, update_moving=train and update_moving)
+        if run_stage1:
+            s1.g["kl_scratch"].zero_()
+            s1.g_forward(g["z"], self.feed["cond"], g["tn1"], g["img64"], s1.g["kl_scratch"], train=train,
+                         cond_noise=cond_noise, update_moving=train and update_moving)
         if train:
             self.gbn_scratch.zero_()
         K.im2col_k3s1_c3(g["img64"], g["col"])

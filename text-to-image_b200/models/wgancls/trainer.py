@@ -19,25 +19,26 @@ class SyntheticTextDataset(object):
     benchmark: images ~ U(-1, 1), 1024-d embeddings ~ N(0, 1)."""
 
     class _Split(object):
-        def __init__(self, num_examples, embed_dim, seed):
+        def __init__(self, num_examples, embed_dim, seed, size=64):
             self.num_examples = num_examples
+            self._size = size
             self._embed_dim = embed_dim
             self._rng = np.random.RandomState(seed)
 
         def next_batch(self, batch_size, window=None, wrong_img=False, embeddings=False, labels=False):
-            img = self._rng.uniform(-1, 1, (batch_size, 64, 64, 3)).astype(np.float32)
-            wrong = self._rng.uniform(-1, 1, (batch_size, 64, 64, 3)).astype(np.float32) if wrong_img else None
+            img = self._rng.uniform(-1, 1, (batch_size, self._size, self._size, 3)).astype(np.float32)
+            wrong = self._rng.uniform(-1, 1, (batch_size, self._size, self._size, 3)).astype(np.float32) if wrong_img else None
             emb = self._rng.normal(0, 1, (batch_size, self._embed_dim)).astype(np.float32) if embeddings else None
             return [img, wrong, emb, None, None]
 
         def next_batch_test(self, batch_size, start, max_captions):
-            img = self._rng.uniform(-1, 1, (batch_size, 64, 64, 3)).astype(np.float32)
+            img = self._rng.uniform(-1, 1, (batch_size, self._size, self._size, 3)).astype(np.float32)
             emb = self._rng.normal(0, 1, (1, batch_size, self._embed_dim)).astype(np.float32)
             return img, emb, None, [["synthetic caption %d" % i] for i in range(batch_size)]
 
-    def __init__(self, embed_dim=1024, num_examples=8192, seed=0):
-        self.train = self._Split(num_examples, embed_dim, seed)
-        self.test = self._Split(num_examples // 8, embed_dim, seed + 1)
+    def __init__(self, embed_dim=1024, num_examples=8192, seed=0, image_size=64):
+        self.train = self._Split(num_examples, embed_dim, seed, image_size)
+        self.test = self._Split(num_examples // 8, embed_dim, seed + 1, image_size)
 
 
 class WGanClsTrainer(object):
