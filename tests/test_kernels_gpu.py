@@ -338,6 +338,20 @@ def test_planes_im2col_col2im(K, np_):
     og = torch.zeros(3, 16, 16, 3, device="cuda")
     K.col2im_k4s2_c3(c2g, og, bias.cuda())
     check_close("col2im", og.cpu(), out, 1e-5, 1.0)
+    # 256-wide images (StackGAN stage-II discriminator): the patch rows are staged in 64-pixel column strips
+    for (n, h, w) in ((1, 20, 256), (2, 256, 256), (1, 6, 136)):
+        img = torch.rand(n, h, w, 3, generator=gen) * 2 - 1
+        col = torch.zeros(np_, n * (h // 2) * (w // 2), 64, dtype=torch.bfloat16)
+        fk.im2col_k4s2_c3(img, col, None)
+        cg = torch.full_like(col, 3.0).cuda()
+        K.im2col_k4s2_c3(img.cuda(), cg, None)
+        check_close("im2col %dx%d" % (h, w), fk.val(cg.cpu()), fk.val(col), 2.0 ** -8 if np_ == 1 else 1e-5, 1e-3)
+        c2, c2g = both(np_, (n * (h // 2) * (w // 2), 64), gen)
+        out = torch.zeros(n, h, w, 3)
+        fk.col2im_k4s2_c3(c2, out, None)
+        og = torch.full((n, h, w, 3), 9.0, device="cuda")
+        K.col2im_k4s2_c3(c2g, og, None)
+        check_close("col2im %dx%d" % (h, w), og.cpu(), out, 1e-5, 1.0)
 
 
 @pytest.mark.parametrize("np_", [1, 2])

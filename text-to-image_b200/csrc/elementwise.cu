@@ -165,45 +165,51 @@ __global__ void im2col_k4s2_c3_kernel(const float* __restrict__ img, int n, int 
 // A block produces kCol2imR image rows: it stages the R/2 + 2 rows of patches they gather from in shared memory
 // (16 B loads), then each thread sums the (up to) four patches that reach one pixel.
 constexpr int kCol2imR = 16;
+// Wide images (256x256 in StackGAN stage-II) are cut into column strips of `ws` pixels so that the staged patches fit
+// in shared memory: a strip stages sw = ws/2 + 2 patch columns starting at q0 = ow0/2 - 1 (one strip: sw = w/2, q0 = 0).
 __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps, int np, int n, int h, int w,
-                                      const float* __restrict__ bias3, float* img) {
+                                      const float* __restrict__ bias3, float* img, int ws, int sw) {
     pdl_launch_dependents();
     pdl_wait();
-    extern __shared__ float s_col[];               // [R/2 + 2][wq][48] fp32 values of the patch rows
+    extern __shared__ float s_col[];               // [R/2 + 2][sw][48] fp32 values of the patch rows
     const int hp = h / 2, wq = w / 2;
-    const int groups = (h + kCol2imR - 1) / kCol2imR;
+    const int rgroups = (h + kCol2imR - 1) / kCol2imR;
+    const int strips = (w + ws - 1) / ws;
     constexpr int PRows = kCol2imR / 2 + 2;
     const float b0 = bias3 ? bias3[0] : 0.f, b1 = bias3 ? bias3[1] : 0.f, b2 = bias3 ? bias3[2] : 0.f;
-    for (int blk = blockIdx.x; blk < n * groups; blk += gridDim.x) {
-        const int b = blk / groups, oh0 = (blk - b * groups) * kCol2imR;
+    for (int blk = blockIdx.x; blk < n * rgroups * strips; blk += gridDim.x) {
+        const int strip = blk % strips, rg = (blk / strips) % rgroups, b = blk / (strips * rgroups);
+        const int oh0 = rg * kCol2imR, ow0 = strip * ws;
         const int pbase = oh0 / 2 - 1;             // first patch row that can reach image row oh0
+        const int qbase = strips > 1 ? ow0 / 2 - 1 : 0;
         __syncthreads();
-        const int total = PRows * wq * 6;
+        const int total = PRows * sw * 6;
         for (int base = 0; base < total; base += blockDim.x * 4) {      // four 16-byte loads in flight per thread
             float v[4][8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = base + u * blockDim.x + threadIdx.x;
-                const int chunk = i % 6, q = (i / 6) % wq, pl = i / (6 * wq);
+                const int chunk = i % 6, q = qbase + (i / 6) % sw, pl = i / (6 * sw);
                 const int p = pbase + pl;
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[u][j] = 0.f;
-                if (i < total && p >= 0 && p < hp) load8(col + (((long long)b * hp + p) * wq + q) * 64 + chunk * 8, ps, np, v[u]);
+                if (i < total && p >= 0 && p < hp && q >= 0 && q < wq)
+                    load8(col + (((long long)b * hp + p) * wq + q) * 64 + chunk * 8, ps, np, v[u]);
             }
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
                 const int i = base + u * blockDim.x + threadIdx.x;
                 if (i < total) {
-                    float* dst = s_col + (long long)(i / 6) * 48 + (i % 6) * 8;     // (pl * wq + q) * 48 + chunk * 8
+                    float* dst = s_col + (long long)(i / 6) * 48 + (i % 6) * 8;     // (pl * sw + q - qbase) * 48 + chunk * 8
 #pragma unroll
                     for (int j = 0; j < 8; ++j) dst[j] = v[u][j];
                 }
             }
         }
         __syncthreads();
-        const int rows = min(kCol2imR, h - oh0);
-        for (int i = threadIdx.x; i < rows * w; i += blockDim.x) {
-            const int ow = i % w, oh = oh0 + i / w;
+        const int rows = min(kCol2imR, h - oh0), cols = min(ws, w - ow0);
+        for (int i = threadIdx.x; i < rows * cols; i += blockDim.x) {
+            const int ow = ow0 + i % cols, oh = oh0 + i / cols;
             float acc0 = b0, acc1 = b1, acc2 = b2;
             for (int kh = (oh + 1) & 1; kh < 4; kh += 2) {
                 const int p = (oh + 1 - kh) / 2;
@@ -211,7 +217,7 @@ __global__ void col2im_k4s2_c3_kernel(const bf16* __restrict__ col, long long ps
                 for (int kw = (ow + 1) & 1; kw < 4; kw += 2) {
                     const int q = (ow + 1 - kw) / 2;
                     if (q < 0 || q >= wq) continue;
-                    const float* src = s_col + ((long long)(p - pbase) * wq + q) * 48 + (kh * 4 + kw) * 3;
+                    const float* src = s_col + ((long long)(p - pbase) * sw + (q - qbase)) * 48 + (kh * 4 + kw) * 3;
                     acc0 += src[0]; acc1 += src[1]; acc2 += src[2];
                 }
             }
@@ -1192,17 +1198,20 @@ extern "C" int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const f
 extern "C" int t2i_col2im_k4s2_c3(const void* col, long long ps, int np, int n, int h, int w, const float* bias3,
                                   float* img, void* stream) {
     if ((h & 1) || (w & 1)) return fail(T2I_ERR_BAD_ARG, "col2im: odd extent");
-    const size_t shm = (size_t)(kCol2imR / 2 + 2) * (w / 2) * 48 * sizeof(float);
+    // one strip when the whole patch row fits (w <= 64), otherwise 64-pixel column strips with a one-patch halo
+    const int ws = w <= 64 ? w : 64;
+    const int sw = w <= 64 ? w / 2 : ws / 2 + 2;
+    const size_t shm = (size_t)(kCol2imR / 2 + 2) * sw * 48 * sizeof(float);
     if (shm > 96 * 1024) return fail(T2I_ERR_BAD_ARG, "col2im: image rows too wide (%d)", w);
     static bool attr_done = false;
     if (!attr_done) {
         cudaFuncSetAttribute(col2im_k4s2_c3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
         attr_done = true;
     }
-    const long long groups = (long long)n * ceil_div(h, kCol2imR);
+    const long long groups = (long long)n * ceil_div(h, kCol2imR) * ceil_div(w, ws);
     const long long cap = (long long)num_sms() * 4;
     launch_ew(col2im_k4s2_c3_kernel, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256), shm, STREAM, static_cast<const bf16*>(col), ps, np,
-                                                                                      n, h, w, bias3, img);
+                                                                                      n, h, w, bias3, img, ws, sw);
     return check_launch("col2im_k4s2_c3");
 }
 extern "C" int t2i_im2col_k3s1_c3(const float* img, int n, int h, int w, void* col, long long ps, int np, void* stream) {
