@@ -259,6 +259,43 @@ int t2i_adam_tf(float* theta, const float* grad, float* m, float* v, long long n
                 float beta1, float beta2, float eps, float grad_scale, void* packed, long long packed_ps, int np,
                 void* stream);
 
+/* ---- conditional progressive-growing WGAN (models/pggan/pggan.py; op wrappers utils/ops.py:74-81,100-111) ----
+ * layer_norm = tf.contrib.layers.layer_norm(begin_norm_axis=1, begin_params_axis=-1): per-SAMPLE statistics over the
+ * m = rows * c values of a sample, gamma / beta per channel (rank 2: rows = 1, c = features).
+ *   t2i_ln_stats:      sums[n][2] += [sum x | sum x^2]   (the caller zeroes sums)
+ *   t2i_ln_apply:      y = act((x - mean_n) * rstd_n * gamma[c] + beta[c]), rstd = rsqrt(biased var + eps); relu 0 / 1
+ *   t2i_ln_bwd_reduce: dsums[n][2] += [sum g | sum g * xhat], g = dy * gamma; dgamma += sum dy * xhat; dbeta += sum dy
+ *   t2i_ln_bwd_apply:  dx = rstd_n * (g - mean_m(g) - xhat * mean_m(g * xhat)); dx_sum[c] += sum dx (the bias gradient
+ *                      of the conv / dense layer in front; may be NULL)
+ * dy is the gradient at the layer-norm OUTPUT with the activation's derivative already applied (the producing
+ * input-gradient GEMM masks it in its epilogue). */
+int t2i_ln_stats(const void* x, long long ps, int np, int n, long long m, float* sums, void* stream);
+int t2i_ln_apply(const void* x, long long x_ps, const float* sums, float eps, const float* gamma, const float* beta,
+                 void* y, long long y_ps, int np, int n, long long rows, int c, int relu, void* stream);
+int t2i_ln_bwd_reduce(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* sums, float eps,
+                      const float* gamma, float* dsums, float* dgamma, float* dbeta, int np, int n, long long rows, int c,
+                      void* stream);
+int t2i_ln_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* sums, float eps,
+                     const float* gamma, const float* dsums, void* dx, long long dx_ps, float* dx_sum, int np, int n,
+                     long long rows, int c, void* stream);
+/* NHWC planes.  upscale2x (utils/ops.py:109-111 resize_nearest_neighbor x2): y[n,i,j,:] = scale * x[n,i/2,j/2,:],
+ * x is h x w.  pool2x (utils/ops.py:100-101 tf.nn.pool AVG 2 with scale = 1/4): y[n,p,q,:] = scale * sum of the 2x2
+ * block, x is h x w (even).  Each is the transpose of the other (pool backward = upscale2x(scale 1/4), upscale
+ * backward = pool2x(scale 1)). */
+int t2i_upscale2x(const void* x, long long x_ps, void* y, long long y_ps, int np, int n, int h, int w, int c, float scale,
+                  void* stream);
+int t2i_pool2x(const void* x, long long x_ps, void* y, long long y_ps, int np, int n, int h, int w, int c, float scale,
+               void* stream);
+/* out = ab[0] * x + ab[1] * z over n values (z NULL: out = ab[0] * x); ab in DEVICE memory: the fade-in blend
+ * alpha * x + (1 - alpha) * x_iden of pggan.py:268,313 and its backward, capturable in CUDA graphs. */
+int t2i_axpby(const void* x, long long x_ps, const void* z, long long z_ps, void* out, long long o_ps, int np, long long n,
+              const float* ab, void* stream);
+/* fp32 NHWC 3-channel image <-> planes with 8 channels (3..7 zero): the operand of from_rgb's 1x1 conv (pggan.py:343-345)
+ * and the output of to_rgb's (pggan.py:367-371).  sample_scale (optional, [n]) multiplies sample i. */
+int t2i_img_to_c8(const float* img, int n, long long pix_per_sample, const float* sample_scale, void* dst, long long ps,
+                  int np, void* stream);
+int t2i_c8_to_img(const void* src, long long ps, int np, float* img, long long pixels, void* stream);
+
 const char* t2i_last_error(void);
 int t2i_version(void);
 /* number of kernels this library has launched in this process (bench.py's gpu_launches) */

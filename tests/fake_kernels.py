@@ -432,3 +432,77 @@ def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0, pac
     theta -= lr_t[0] * mj / (v.sqrt() + eps)
     if packed is not None:
         put(packed, theta.double())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conditional PGGAN kernels (text-to-image_b200/csrc/pggan_ops.cu)
+def ln_stats(x, sums):
+    v = val(x).reshape(x.shape[1], -1)
+    sums[:, 0] += v.sum(1).to(sums.dtype)
+    sums[:, 1] += (v * v).sum(1).to(sums.dtype)
+
+
+def _ln_mr(x, sums, eps):
+    n = x.shape[1]
+    m = x[0, 0].numel()
+    mean = sums[:, 0].double() / m
+    var = (sums[:, 1].double() / m - mean * mean).clamp_min(0.0)
+    shape = [n] + [1] * (x.dim() - 2)
+    return mean.reshape(shape), torch.rsqrt(var + eps).reshape(shape), m
+
+
+def ln_apply(x, sums, eps, gamma, beta, y, relu=False):
+    mean, rstd, _ = _ln_mr(x, sums, eps)
+    v = (val(x) - mean) * rstd * gamma.double() + beta.double()
+    put(y, v.clamp_min(0.0) if relu else v)
+
+
+def ln_bwd_reduce(dy, x, sums, eps, gamma, dsums, dgamma, dbeta):
+    mean, rstd, _ = _ln_mr(x, sums, eps)
+    xh = (val(x) - mean) * rstd
+    d = val(dy)
+    g = d * gamma.double()
+    n, c = x.shape[1], x.shape[-1]
+    dsums[:, 0] += g.reshape(n, -1).sum(1).to(dsums.dtype)
+    dsums[:, 1] += (g * xh).reshape(n, -1).sum(1).to(dsums.dtype)
+    dgamma += (d * xh).reshape(-1, c).sum(0).to(dgamma.dtype)
+    dbeta += d.reshape(-1, c).sum(0).to(dbeta.dtype)
+
+
+def ln_bwd_apply(dy, x, sums, eps, gamma, dsums, dx, dx_sum=None):
+    mean, rstd, m = _ln_mr(x, sums, eps)
+    xh = (val(x) - mean) * rstd
+    g = val(dy) * gamma.double()
+    shape = [x.shape[1]] + [1] * (x.dim() - 2)
+    out = rstd * (g - (dsums[:, 0].double() / m).reshape(shape) - xh * (dsums[:, 1].double() / m).reshape(shape))
+    put(dx, out)
+    if dx_sum is not None:
+        dx_sum += out.reshape(-1, x.shape[-1]).sum(0).to(dx_sum.dtype)
+
+
+def upscale2x(x, y, scale=1.0):
+    put(y, scale * val(x).repeat_interleave(2, 1).repeat_interleave(2, 2))
+
+
+def pool2x(x, y, scale=0.25):
+    v = val(x)
+    n, h, w, c = v.shape
+    put(y, scale * v.reshape(n, h // 2, 2, w // 2, 2, c).sum((2, 4)))
+
+
+def axpby(x, z, out, ab):
+    v = float(ab[0]) * val(x)
+    if z is not None:
+        v = v + float(ab[1]) * val(z)
+    put(out, v)
+
+
+def img_to_c8(img, dst, sample_scale=None):
+    v = img.double()
+    if sample_scale is not None:
+        v = v * sample_scale.double().reshape(-1, 1, 1, 1)
+    put(dst, torch.cat([v, torch.zeros(*v.shape[:-1], 5, dtype=v.dtype)], -1))
+
+
+def c8_to_img(src, img):
+    img.copy_(val(src)[..., :3].reshape(img.shape).to(img.dtype))

@@ -66,6 +66,8 @@ CONV_CASES = [
     ("c3_tinych", fk.CONV_S1, 3, 0, 4, 4, 4, 8, 16),
     ("k4s1_4x4", fk.CONV_S1, 4, 0, 16, 4, 4, 128, 128),          # TF SAME for k = 4, s = 1: pad 1 before, 2 after
     ("k4s1_16_flip", fk.CONV_S1, 4, 1, 3, 16, 16, 64, 128),
+    ("k2s1_8x8", fk.CONV_S1, 2, 0, 6, 8, 8, 64, 16),              # TF SAME for k = 2: pad 0 before, 1 after (PGGAN to_rgb)
+    ("k2s1_flip", fk.CONV_S1, 2, 1, 3, 16, 16, 16, 64),
     ("k4s2_32", fk.CONV_K4S2, 4, 0, 2, 32, 32, 128, 256),
     ("k4s2_8", fk.CONV_K4S2, 4, 0, 16, 8, 8, 64, 128),
     ("k4s2_tiny", fk.CONV_K4S2, 4, 0, 2, 8, 8, 16, 32),
@@ -271,6 +273,7 @@ WGRAD_CASES = [
     ("c3_16x16", fk.CONV_S1, 3, 3, 16, 16, 64, 128),
     ("c3_tiny", fk.CONV_S1, 3, 4, 4, 4, 8, 16),
     ("k4s1_8x8", fk.CONV_S1, 4, 6, 8, 8, 64, 128),
+    ("k2s1_16", fk.CONV_S1, 2, 3, 16, 16, 64, 16),                # PGGAN to_rgb: 2x2 SAME conv to 16 (9 used) channels
     ("c3_to8", fk.CONV_S1, 3, 2, 16, 16, 32, 8),                 # 8 padded output channels (stage-II image conv)
     ("k4s2_32", fk.CONV_K4S2, 4, 2, 32, 32, 128, 128),
     ("k4s2_8", fk.CONV_K4S2, 4, 16, 8, 8, 64, 256),
@@ -640,3 +643,82 @@ def test_fused_batch_norm_pitch_and_affine_scale(K, np_):
     check_close("dgamma", dgag.cpu(), dga, 5e-4, 5.0)
     check_close("dbeta", dbog.cpu(), dbo, 5e-4, 5.0)
     check_close("dx", fk.val(dxg.cpu()), fk.val(dx), *tol(np_))
+
+
+LN_CASES = [(6, 1, 1, 8192), (5, 4, 4, 512), (3, 32, 32, 64), (2, 64, 64, 32), (4, 8, 8, 8), (7, 16, 16, 24)]
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+@pytest.mark.parametrize("case", LN_CASES, ids=["%dx%dx%dx%d" % c for c in LN_CASES])
+def test_layer_norm_kernels(K, case, np_):
+    """per-sample layer normalisation (utils/ops.py:74-81) forward and backward, incl. the rank-2 case (rows = 1,
+    c = 16 * nf features: channel groups do not divide the block) and a channel count whose groups do not divide 256"""
+    n, h, w, c = case
+    gen = torch.Generator().manual_seed(31)
+    shape = (n, h, w, c) if h > 1 else (n, c)
+    x, xg = both(np_, shape, gen, 1.5)
+    dy, dyg = both(np_, shape, gen)
+    gamma, beta = torch.rand(c, generator=gen) + 0.5, torch.randn(c, generator=gen)
+    sums = torch.zeros(n, 2, dtype=torch.float64)
+    fk.ln_stats(x, sums)
+    sg = torch.zeros(n, 2, device="cuda")
+    K.ln_stats(xg, sg)
+    check_close("sums", sg.cpu(), sums, 2e-5, 1.0)
+    y = torch.zeros_like(x)
+    fk.ln_apply(x, sums, 1e-12, gamma, beta, y, relu=True)
+    yg = torch.zeros_like(x).cuda()
+    K.ln_apply(xg, sg, 1e-12, gamma.cuda(), beta.cuda(), yg, relu=True)
+    check_close("y", fk.val(yg.cpu()), fk.val(y), *tol(np_))
+    ds, dga, dbe = torch.zeros(n, 2, dtype=torch.float64), torch.full((c,), 0.5, dtype=torch.float64), torch.zeros(c, dtype=torch.float64)
+    fk.ln_bwd_reduce(dy, x, sums, 1e-12, gamma, ds, dga, dbe)
+    dsg, dgag, dbeg = torch.zeros(n, 2, device="cuda"), torch.full((c,), 0.5, device="cuda"), torch.zeros(c, device="cuda")
+    K.ln_bwd_reduce(dyg, xg, sg, 1e-12, gamma.cuda(), dsg, dgag, dbeg)
+    check_close("dsums", dsg.cpu(), ds, 1e-4, 5.0)
+    check_close("dgamma", dgag.cpu(), dga, 1e-4, 5.0)
+    check_close("dbeta", dbeg.cpu(), dbe, 1e-4, 5.0)
+    dx, dxs = torch.zeros_like(x), torch.zeros(c, dtype=torch.float64)
+    fk.ln_bwd_apply(dy, x, sums, 1e-12, gamma, ds, dx, dxs)
+    dxg, dxsg = torch.zeros_like(x).cuda(), torch.zeros(c, device="cuda")
+    K.ln_bwd_apply(dyg, xg, sg, 1e-12, gamma.cuda(), dsg, dxg, dxsg)
+    check_close("dx", fk.val(dxg.cpu()), fk.val(dx), *tol(np_))
+    scale = float(fk.val(dx).abs().reshape(-1, c).sum(0).max())
+    assert float((dxsg.cpu().double() - dxs).abs().max()) < (2.0 ** -8 if np_ == 1 else 1e-4) * scale + 1e-6
+
+
+@pytest.mark.parametrize("np_", [1, 2])
+def test_resample_blend_and_image_padding_kernels(K, np_):
+    gen = torch.Generator().manual_seed(37)
+    x, xg = both(np_, (5, 6, 10, 24), gen)
+    up = torch.zeros(np_, 5, 12, 20, 24, dtype=torch.bfloat16)
+    fk.upscale2x(x, up, 0.25)
+    upg = torch.zeros_like(up).cuda()
+    K.upscale2x(xg, upg, 0.25)
+    check_close("upscale", fk.val(upg.cpu()), fk.val(up), *tol(np_))
+    # sample sub-range (views along the sample axis keep the plane stride of the whole buffer)
+    po = torch.zeros(np_, 5, 3, 5, 24, dtype=torch.bfloat16)
+    fk.pool2x(x[:, 1:4], po[:, 1:4], 0.25)
+    pog = torch.zeros_like(po).cuda()
+    K.pool2x(xg[:, 1:4], pog[:, 1:4], 0.25)
+    check_close("pool", fk.val(pog.cpu()), fk.val(po), *tol(np_))
+    z, zg = both(np_, (5, 6, 10, 24), gen)
+    ab = torch.tensor([0.3, 0.7])
+    out = torch.zeros_like(x)
+    fk.axpby(x, z, out, ab)
+    og = torch.zeros_like(x).cuda()
+    K.axpby(xg, zg, og, ab.cuda())
+    check_close("axpby", fk.val(og.cpu()), fk.val(out), *tol(np_))
+    fk.axpby(x, None, out, ab[1:])
+    K.axpby(xg, None, xg, ab.cuda()[1:])            # in place
+    check_close("scale", fk.val(xg.cpu()), fk.val(out), *tol(np_))
+    img = torch.rand(3, 8, 8, 3, generator=gen) * 2 - 1
+    sc = torch.rand(3, generator=gen) + 0.5
+    c8 = torch.zeros(np_, 3, 8, 8, 8, dtype=torch.bfloat16)
+    fk.img_to_c8(img, c8, sc)
+    c8g = torch.full_like(c8, 3.0).cuda()
+    K.img_to_c8(img.cuda(), c8g, sc.cuda())
+    check_close("img_to_c8", fk.val(c8g.cpu()), fk.val(c8), 2.0 ** -8 if np_ == 1 else 1e-5, 1e-3)
+    back = torch.zeros(3, 8, 8, 3)
+    fk.c8_to_img(c8, back)
+    bg = torch.zeros(3, 8, 8, 3, device="cuda")
+    K.c8_to_img(c8g, bg)
+    check_close("c8_to_img", bg.cpu(), back, 1e-6, 1.0)

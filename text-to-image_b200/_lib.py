@@ -80,6 +80,15 @@ SIGNATURES = {
     "t2i_g_scalars": [_P, _P, _I, _I, _F, _P],
     "t2i_pack_weight": [_P, _I, _I, _I, _P, _LL, _P, _LL, _I, _P],
     "t2i_adam_tf": [_P, _P, _P, _P, _LL, _P, _F, _F, _F, _F, _P, _LL, _I, _P],
+    "t2i_ln_stats": [_P, _LL, _I, _I, _LL, _P, _P],
+    "t2i_ln_apply": [_P, _LL, _P, _F, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _P],
+    "t2i_ln_bwd_reduce": [_P, _LL, _P, _LL, _P, _F, _P, _P, _P, _P, _I, _I, _LL, _I, _P],
+    "t2i_ln_bwd_apply": [_P, _LL, _P, _LL, _P, _F, _P, _P, _P, _LL, _P, _I, _I, _LL, _I, _P],
+    "t2i_upscale2x": [_P, _LL, _P, _LL, _I, _I, _I, _I, _I, _F, _P],
+    "t2i_pool2x": [_P, _LL, _P, _LL, _I, _I, _I, _I, _I, _F, _P],
+    "t2i_axpby": [_P, _LL, _P, _LL, _P, _LL, _I, _LL, _P, _P],
+    "t2i_img_to_c8": [_P, _I, _LL, _P, _P, _LL, _I, _P],
+    "t2i_c8_to_img": [_P, _LL, _I, _P, _LL, _P],
 }
 OTHER_SYMBOLS = ["t2i_last_error", "t2i_version", "t2i_launch_count"]
 

@@ -86,7 +86,7 @@ int encode_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_
 int build_taps(int mode, int k, int flip, TapTable* t) {
     memset(t, 0, sizeof(*t));
     if (mode == T2I_CONV_S1) {
-        if (k != 1 && k != 3 && k != 4) return fail(T2I_ERR_BAD_ARG, "CONV_S1 supports k = 1, 3 or 4, got %d", k);
+        if (k < 1 || k > 4) return fail(T2I_ERR_BAD_ARG, "CONV_S1 supports k = 1 .. 4, got %d", k);
         // SAME: pad_total = k - 1, before = pad_total / 2 (k = 4: 1 before, 2 after -- TF's asymmetric case, used by
         // StackGAN stage-II's 4x4 stride-1 convs, models/stackgan/stageII/model.py:102,105,151,154)
         const int pad = (k - 1) / 2;

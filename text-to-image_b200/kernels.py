@@ -367,3 +367,65 @@ def adam_tf(theta, grad, m, v, lr_t, beta1, beta2, eps=1e-8, grad_scale=1.0, pac
     _lib.call("t2i_adam_tf", _f32(theta), _f32(grad), _f32(m), _f32(v), theta.numel(), _f32(lr_t), beta1, beta2, eps,
               grad_scale, _p(packed), 0 if packed is None else _ps(packed), 1 if packed is None else packed.shape[0],
               _stream())
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# conditional PGGAN (models/pggan/pggan.py): planes tensors [np, n, h, w, c] (or [np, n, c]); slices along the sample
+# axis are fine (the plane stride travels separately)
+def _nrc(t):
+    """[np, n, ..., c] -> (n, rows per sample, c)"""
+    n, c = t.shape[1], t.shape[-1]
+    return n, t[0, 0].numel() // c, c
+
+
+def ln_stats(x, sums):
+    """sums fp32 [n, 2] += [sum x | sum x^2] per sample (layer_norm, utils/ops.py:74-81); the caller zeroes sums."""
+    n, rows, c = _nrc(x)
+    _lib.call("t2i_ln_stats", _p(x), _ps(x), x.shape[0], n, rows * c, _f32(sums), _stream())
+
+
+def ln_apply(x, sums, eps, gamma, beta, y, relu=False):
+    n, rows, c = _nrc(x)
+    _lib.call("t2i_ln_apply", _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(beta), _p(y), _ps(y), x.shape[0], n, rows,
+              c, int(relu), _stream())
+
+
+def ln_bwd_reduce(dy, x, sums, eps, gamma, dsums, dgamma, dbeta):
+    n, rows, c = _nrc(x)
+    _lib.call("t2i_ln_bwd_reduce", _p(dy), _ps(dy), _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(dsums),
+              _f32(dgamma), _f32(dbeta), x.shape[0], n, rows, c, _stream())
+
+
+def ln_bwd_apply(dy, x, sums, eps, gamma, dsums, dx, dx_sum=None):
+    n, rows, c = _nrc(x)
+    _lib.call("t2i_ln_bwd_apply", _p(dy), _ps(dy), _p(x), _ps(x), _f32(sums), eps, _f32(gamma), _f32(dsums), _p(dx),
+              _ps(dx), _p(dx_sum), x.shape[0], n, rows, c, _stream())
+
+
+def upscale2x(x, y, scale=1.0):
+    """y[n, i, j] = scale * x[n, i // 2, j // 2] (resize_nearest_neighbor x2, utils/ops.py:109-111)"""
+    _, n, h, w, c = x.shape
+    _lib.call("t2i_upscale2x", _p(x), _ps(x), _p(y), _ps(y), x.shape[0], n, h, w, c, scale, _stream())
+
+
+def pool2x(x, y, scale=0.25):
+    """y = scale * sum over 2x2 blocks (scale 1/4: tf.nn.pool AVG 2, utils/ops.py:100-101)"""
+    _, n, h, w, c = x.shape
+    _lib.call("t2i_pool2x", _p(x), _ps(x), _p(y), _ps(y), x.shape[0], n, h, w, c, scale, _stream())
+
+
+def axpby(x, z, out, ab):
+    """out = ab[0] * x + ab[1] * z (z None: out = ab[0] * x); ab: fp32 DEVICE tensor"""
+    _lib.call("t2i_axpby", _p(x), _ps(x), _p(z), 0 if z is None else _ps(z), _p(out), _ps(out), x.shape[0], x[0].numel(),
+              _f32(ab), _stream())
+
+
+def img_to_c8(img, dst, sample_scale=None):
+    """fp32 NHWC [n, h, w, 3] -> planes [np, n, h, w, 8] (channels 3..7 zero), optionally scaled per sample"""
+    n = img.shape[0]
+    _lib.call("t2i_img_to_c8", _f32(img), n, img[0].numel() // 3, _p(sample_scale), _p(dst), _ps(dst), dst.shape[0],
+              _stream())
+
+
+def c8_to_img(src, img):
+    _lib.call("t2i_c8_to_img", _p(src), _ps(src), src.shape[0], _f32(img), img.numel() // 3, _stream())
