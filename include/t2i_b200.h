@@ -281,15 +281,20 @@ int t2i_ln_bwd_apply(const void* dy, long long dy_ps, const void* x, long long x
 /* NHWC planes.  upscale2x (utils/ops.py:109-111 resize_nearest_neighbor x2): y[n,i,j,:] = scale * x[n,i/2,j/2,:],
  * x is h x w.  pool2x (utils/ops.py:100-101 tf.nn.pool AVG 2 with scale = 1/4): y[n,p,q,:] = scale * sum of the 2x2
  * block, x is h x w (even).  Each is the transpose of the other (pool backward = upscale2x(scale 1/4), upscale
- * backward = pool2x(scale 1)). */
+ * backward = pool2x(scale 1)).  upscale2x's optional mask (shaped like y, post-activation values; mask_kind as
+ * t2i_conv_gemm_desc.mask_kind) multiplies by the activation derivative of the layer in front of the pool. */
 int t2i_upscale2x(const void* x, long long x_ps, void* y, long long y_ps, int np, int n, int h, int w, int c, float scale,
-                  void* stream);
+                  const void* mask, long long m_ps, int mask_kind, void* stream);
 int t2i_pool2x(const void* x, long long x_ps, void* y, long long y_ps, int np, int n, int h, int w, int c, float scale,
                void* stream);
 /* out = ab[0] * x + ab[1] * z over n values (z NULL: out = ab[0] * x); ab in DEVICE memory: the fade-in blend
  * alpha * x + (1 - alpha) * x_iden of pggan.py:268,313 and its backward, capturable in CUDA graphs. */
 int t2i_axpby(const void* x, long long x_ps, const void* z, long long z_ps, void* out, long long o_ps, int np, long long n,
               const float* ab, void* stream);
+/* dst[row, d_coff + k] = src[row, s_coff + k] for k < c: channel window of one pitched planes buffer into another
+ * (image part of the discriminator's concat buffer, pggan.py:318-322, and of its gradient). */
+int t2i_copy_window(const void* src, long long s_ps, int s_pitch, int s_coff, void* dst, long long d_ps, int d_pitch,
+                    int d_coff, int np, long long rows, int c, void* stream);
 /* fp32 NHWC 3-channel image <-> planes with 8 channels (3..7 zero): the operand of from_rgb's 1x1 conv (pggan.py:343-345)
  * and the output of to_rgb's (pggan.py:367-371).  sample_scale (optional, [n]) multiplies sample i. */
 int t2i_img_to_c8(const float* img, int n, long long pix_per_sample, const float* sample_scale, void* dst, long long ps,

@@ -48,6 +48,7 @@ class PgganCfg:
     nf_base: int = 1024       # get_nf(i) = min(base // 2**i * 4, cap), get_dnf(i) = min(base // 2**i * 2, cap)
     nf_cap: int = 512
     rgb_mid: int = 9          # to_rgb: conv 2x2 -> 9 channels -> conv 1x1 -> 3 (:369-370)
+    d_embed: int = 128        # the discriminator's compressed embedding, literal 128 (:271)
     lr: float = 0.000002      # :111-112
     beta1: float = 0.0
     beta2: float = 0.99
@@ -101,8 +102,8 @@ def param_shapes(cfg: PgganCfg):
         s = d + "conv_stage_%d/" % i
         conv(s + "Conv", 3, cfg.dnf(i), cfg.dnf(i)); conv(s + "Conv_1", 3, cfg.dnf(i), cfg.dnf(i - 1))
     s0 = d + "conv_stage_0/"
-    dense(s0 + "dense", E, 128)                                               # :271
-    conv(s0 + "Conv", 3, cfg.dnf(0) + 128, cfg.dnf(0))                        # :273
+    dense(s0 + "dense", E, cfg.d_embed)                                       # :271
+    conv(s0 + "Conv", 3, cfg.dnf(0) + cfg.d_embed, cfg.dnf(0))                # :273
     conv(s0 + "Conv_1", 4, cfg.dnf(0), cfg.dnf(0))                            # :274
     dense(s0 + "dense_1", cfg.dnf(0), 1)                                      # :275
     return sh

@@ -480,8 +480,16 @@ def ln_bwd_apply(dy, x, sums, eps, gamma, dsums, dx, dx_sum=None):
         dx_sum += out.reshape(-1, x.shape[-1]).sum(0).to(dx_sum.dtype)
 
 
-def upscale2x(x, y, scale=1.0):
-    put(y, scale * val(x).repeat_interleave(2, 1).repeat_interleave(2, 2))
+def upscale2x(x, y, scale=1.0, mask=None, mask_kind=MASK_NONE):
+    v = scale * val(x).repeat_interleave(2, 1).repeat_interleave(2, 2)
+    if mask is not None and mask_kind != MASK_NONE:
+        a = val(mask)
+        v = v * torch.where(a > 0, torch.ones_like(a), torch.full_like(a, 0.2 if mask_kind == MASK_LRELU else 0.0))
+    put(y, v)
+
+
+def copy_window(src, s_coff, dst, d_coff, c):
+    dst[..., d_coff:d_coff + c] = src[..., s_coff:s_coff + c]
 
 
 def pool2x(x, y, scale=0.25):

@@ -694,6 +694,14 @@ def test_resample_blend_and_image_padding_kernels(K, np_):
     upg = torch.zeros_like(up).cuda()
     K.upscale2x(xg, upg, 0.25)
     check_close("upscale", fk.val(upg.cpu()), fk.val(up), *tol(np_))
+    m, mg = both(np_, (5, 12, 20, 24), gen)
+    fk.upscale2x(x, up, 0.25, mask=m, mask_kind=fk.MASK_LRELU)
+    K.upscale2x(xg, upg, 0.25, mask=mg, mask_kind=K.MASK_LRELU)
+    check_close("upscale_masked", fk.val(upg.cpu()), fk.val(up), *tol(np_))
+    wide, wideg = both(np_, (5, 6, 10, 40), gen)
+    fk.copy_window(x[:, 1:3], 8, wide[:, 1:3], 16, 16)
+    K.copy_window(xg[:, 1:3], 8, wideg[:, 1:3], 16, 16)
+    assert torch.equal(wideg.cpu(), wide)
     # sample sub-range (views along the sample axis keep the plane stride of the whole buffer)
     po = torch.zeros(np_, 5, 3, 5, 24, dtype=torch.bfloat16)
     fk.pool2x(x[:, 1:4], po[:, 1:4], 0.25)

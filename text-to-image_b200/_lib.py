@@ -84,7 +84,8 @@ SIGNATURES = {
     "t2i_ln_apply": [_P, _LL, _P, _F, _P, _P, _P, _LL, _I, _I, _LL, _I, _I, _P],
     "t2i_ln_bwd_reduce": [_P, _LL, _P, _LL, _P, _F, _P, _P, _P, _P, _I, _I, _LL, _I, _P],
     "t2i_ln_bwd_apply": [_P, _LL, _P, _LL, _P, _F, _P, _P, _P, _LL, _P, _I, _I, _LL, _I, _P],
-    "t2i_upscale2x": [_P, _LL, _P, _LL, _I, _I, _I, _I, _I, _F, _P],
+    "t2i_upscale2x": [_P, _LL, _P, _LL, _I, _I, _I, _I, _I, _F, _P, _LL, _I, _P],
+    "t2i_copy_window": [_P, _LL, _I, _I, _P, _LL, _I, _I, _I, _LL, _I, _P],
     "t2i_pool2x": [_P, _LL, _P, _LL, _I, _I, _I, _I, _I, _F, _P],
     "t2i_axpby": [_P, _LL, _P, _LL, _P, _LL, _I, _LL, _P, _P],
     "t2i_img_to_c8": [_P, _I, _LL, _P, _P, _LL, _I, _P],

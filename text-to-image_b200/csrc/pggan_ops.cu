@@ -208,8 +208,18 @@ __global__ void ln_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
 // ---- resampling ---------------------------------------------------------------------------------------------------
 // y[n, i, j, :] = scale * x[n, i / 2, j / 2, :]   (x: h x w, y: 2h x 2w) -- resize_nearest_neighbor x2; with
 // scale = 1/4 the transpose of the 2x2 average pool
+// optional mask (shaped like y, post-activation values): y *= act'(mask), mask_kind 1 LeakyReLU(0.2) / 2 ReLU -- the
+// pool's input-gradient and the activation derivative of the conv in front of the pool in one pass
+__device__ __forceinline__ void apply_mask8(float* v, const bf16* m, long long m_ps, int np, int mask_kind) {
+    float a[8];
+    load8(m, m_ps, np, a);
+    const float neg = (mask_kind == 1) ? 0.2f : 0.f;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] *= (a[j] > 0.f) ? 1.f : neg;
+}
 __global__ void upscale2x_kernel(const bf16* __restrict__ x, long long x_ps, bf16* y, long long y_ps, int np, long long total8,
-                                 int h, int w, int cg, float scale) {
+                                 int h, int w, int cg, float scale, const bf16* __restrict__ mask, long long m_ps,
+                                 int mask_kind) {
     pdl_launch_dependents();
     pdl_wait();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
@@ -222,12 +232,17 @@ __global__ void upscale2x_kernel(const bf16* __restrict__ x, long long x_ps, bf1
         load8(x + i * 8, x_ps, np, v);
 #pragma unroll
         for (int j = 0; j < 8; ++j) v[j] *= scale;
-        bf16* o = y + (((nn * 2 * h + 2 * p) * 2 * w + 2 * q) * cg + c8) * 8;
+        const long long o0 = (((nn * 2 * h + 2 * p) * 2 * w + 2 * q) * cg + c8) * 8;
         const long long rs = (long long)2 * w * cg * 8;
-        store8(o, y_ps, np, v);
-        store8(o + cg * 8, y_ps, np, v);
-        store8(o + rs, y_ps, np, v);
-        store8(o + rs + cg * 8, y_ps, np, v);
+        const long long offs[4] = {o0, o0 + cg * 8, o0 + rs, o0 + rs + cg * 8};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+            float u[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) u[j] = v[j];
+            if (mask != nullptr) apply_mask8(u, mask + offs[t], m_ps, np, mask_kind);
+            store8(y + offs[t], y_ps, np, u);
+        }
     }
 }
 // y[n, p, q, :] = scale * sum of the 2x2 block of x   (x: h x w, y: h/2 x w/2) -- scale 1/4: tf.nn.pool AVG 2;
@@ -275,6 +290,23 @@ __global__ void axpby_kernel(const bf16* __restrict__ x, long long x_ps, const b
             for (int j = 0; j < 8; ++j) v[j] *= a;
         }
         store8(out + i * 8, o_ps, np, v);
+    }
+}
+
+// dst[row, d_coff + k] = src[row, s_coff + k], k < c: a channel window of one pitched buffer into another (the
+// discriminator's concat buffer, pggan.py:318-322, and the gradient of its image part)
+__global__ void copy_window_kernel(const bf16* __restrict__ src, long long s_ps, int s_pitch, int s_coff, bf16* dst,
+                                   long long d_ps, int d_pitch, int d_coff, int np, long long total8, int cg) {
+    pdl_launch_dependents();
+    pdl_wait();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total8; i += (long long)gridDim.x * blockDim.x) {
+        const long long row = i / cg;
+        const int c8 = (int)(i % cg) * 8;
+        const uint4 hi = *reinterpret_cast<const uint4*>(src + row * s_pitch + s_coff + c8);
+        *reinterpret_cast<uint4*>(dst + row * d_pitch + d_coff + c8) = hi;
+        if (np == 2)
+            *reinterpret_cast<uint4*>(dst + d_ps + row * d_pitch + d_coff + c8) =
+                *reinterpret_cast<const uint4*>(src + s_ps + row * s_pitch + s_coff + c8);
     }
 }
 
@@ -364,11 +396,11 @@ extern "C" int t2i_ln_bwd_apply(const void* dy, long long dy_ps, const void* x, 
     return check_launch("ln_bwd_apply");
 }
 extern "C" int t2i_upscale2x(const void* x, long long x_ps, void* y, long long y_ps, int np, int n, int h, int w, int c,
-                             float scale, void* stream) {
+                             float scale, const void* mask, long long m_ps, int mask_kind, void* stream) {
     if (c % 8 != 0) return fail(T2I_ERR_BAD_ARG, "upscale2x: c must be a multiple of 8");
     const long long total8 = (long long)n * h * w * (c / 8);
     launch_ew(upscale2x_kernel, dim3(grid_for(total8, 256)), dim3(256), 0, STREAM, static_cast<const bf16*>(x), x_ps,
-              static_cast<bf16*>(y), y_ps, np, total8, h, w, c / 8, scale);
+              static_cast<bf16*>(y), y_ps, np, total8, h, w, c / 8, scale, static_cast<const bf16*>(mask), m_ps, mask_kind);
     return check_launch("upscale2x");
 }
 extern "C" int t2i_pool2x(const void* x, long long x_ps, void* y, long long y_ps, int np, int n, int h, int w, int c,
@@ -385,6 +417,16 @@ extern "C" int t2i_axpby(const void* x, long long x_ps, const void* z, long long
     launch_ew(axpby_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, STREAM, static_cast<const bf16*>(x), x_ps,
               static_cast<const bf16*>(z), z_ps, static_cast<bf16*>(out), o_ps, np, n / 8, ab);
     return check_launch("axpby");
+}
+extern "C" int t2i_copy_window(const void* src, long long s_ps, int s_pitch, int s_coff, void* dst, long long d_ps,
+                               int d_pitch, int d_coff, int np, long long rows, int c, void* stream) {
+    if (c % 8 || s_pitch % 8 || s_coff % 8 || d_pitch % 8 || d_coff % 8)
+        return fail(T2I_ERR_BAD_ARG, "copy_window: channel counts and offsets must be multiples of 8");
+    if (s_coff + c > s_pitch || d_coff + c > d_pitch) return fail(T2I_ERR_BAD_ARG, "copy_window: window outside the buffer");
+    const long long total8 = rows * (c / 8);
+    launch_ew(copy_window_kernel, dim3(grid_for(total8, 256)), dim3(256), 0, STREAM, static_cast<const bf16*>(src), s_ps, s_pitch,
+              s_coff, static_cast<bf16*>(dst), d_ps, d_pitch, d_coff, np, total8, c / 8);
+    return check_launch("copy_window");
 }
 extern "C" int t2i_img_to_c8(const float* img, int n, long long pix_per_sample, const float* sample_scale, void* dst,
                              long long ps, int np, void* stream) {

@@ -45,6 +45,8 @@ class Layer:
         self.mode, self.k, self.taps, self.cout, self.cin = mode, k, taps, cout, cin
         self.need_bwd = need_bwd
         self.w = self.b = self.gw = self.gb = self.Wf = None
+        # kind "conv_pad": the TF tensor has cin_tf x cout_tf channels, zero-padded to cin x cout in kernel layout
+        self.cin_tf = self.cout_tf = None
 
 
 class Engine:
@@ -92,6 +94,7 @@ class Engine:
 
     # ------------------------------------------------------------------ parameters
     FC0_NCHW = True      # dense output features ordered c*16 + hw (wgancls reshapes to NCHW, model.py:179)
+    NORM_MOVING = True   # the normalisation layers carry moving statistics (BatchNorm; PGGAN's LayerNorm does not)
 
     def _d_layers(self):
         """d_net contraction layers in creation order (models/wgancls/model.py:129-161) and its BatchNorm list."""
@@ -152,12 +155,12 @@ class Engine:
         self.gl = OrderedDict((l.name, l) for l in g_layers)
 
         def bias_len(l):
-            return {"dout": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)     # img_out: 8 (3 used, zero padded)
+            return {"dout": 1, "dout_fc": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)     # img_out: 8 (3 used, zero padded)
 
         def layout(layers, bn_ch):
             off, table = 0, OrderedDict()
             for l in layers.values():
-                wn = l.taps * l.cout * l.cin if l.kind not in ("dout", "c9") else (l.cin if l.kind == "dout" else 81)
+                wn = l.taps * l.cout * l.cin if l.kind not in ("dout", "dout_fc", "c9") else (81 if l.kind == "c9" else l.cin)
                 table[l.name + ".w"] = (off, wn); off = _align(off + wn)
                 table[l.name + ".b"] = (off, bias_len(l)); off = _align(off + bias_len(l))
             for i, c in enumerate(bn_ch):
@@ -191,7 +194,7 @@ class Engine:
             for l in layers.values():
                 l.w, l.b = self.P["%s.%s.w" % (net, l.name)], self.P["%s.%s.b" % (net, l.name)]
                 l.gw, l.gb = self.G["%s.%s.w" % (net, l.name)], self.G["%s.%s.b" % (net, l.name)]
-                if l.kind in ("dout", "c9"):
+                if l.kind in ("dout", "dout_fc", "c9"):
                     continue
                 l.w = l.w.view(l.taps, l.cout, l.cin)
                 l.gw = l.gw.view(l.taps, l.cout, l.cin)
@@ -272,6 +275,16 @@ class Engine:
             return out
         if l.kind == "dout":     # [4,4,C,1] -> (kh,kw,c) flat == NHWC order of the 4x4xC activation
             return p[l.tf_w + "/weights"].reshape(-1)
+        if l.kind == "dout_fc":  # dense [C, 1] on the last axis of a [B,1,1,C] tensor (models/pggan/pggan.py:275)
+            return p[l.tf_w + "/kernel"].reshape(-1)
+        if l.kind == "conv_pad":  # [k,k,ci_tf,co_tf] -> [tap][co][ci], zero padded in both channel counts
+            w = p[l.tf_w + "/weights"]
+            out = torch.zeros(l.taps, l.cout, l.cin, dtype=w.dtype)
+            out[:, :l.cout_tf, :l.cin_tf] = w.permute(0, 1, 3, 2).reshape(l.taps, l.cout_tf, l.cin_tf)
+            return out
+        if l.kind == "flat4":    # 4x4 VALID conv on a 4x4 map = dense over the NHWC-flattened map: [4,4,ci,co] -> [co][(kh,kw,ci)]
+            w = p[l.tf_w + "/weights"]
+            return w.reshape(-1, l.cout).t().reshape(1, l.cout, l.cin)
         if l.kind == "c9":
             return p[l.tf_w + "/weights"].reshape(-1)
         raise ValueError(l.kind)
@@ -301,11 +314,18 @@ class Engine:
             out[l.tf_w + "/weights"] = w.reshape(3, 3, 8, l.cin)[:, :, :3].permute(0, 1, 3, 2).contiguous()
         elif l.kind == "dout":
             out[l.tf_w + "/weights"] = w.reshape(4, 4, -1, 1).clone()
+        elif l.kind == "dout_fc":
+            out[l.tf_w + "/kernel"] = w.reshape(-1, 1).clone()
+        elif l.kind == "conv_pad":
+            w = w.reshape(l.k, l.k, l.cout, l.cin)[:, :, :l.cout_tf, :l.cin_tf]
+            out[l.tf_w + "/weights"] = w.permute(0, 1, 3, 2).contiguous()
+        elif l.kind == "flat4":
+            out[l.tf_w + "/weights"] = w.reshape(l.cout, l.cin).t().reshape(4, 4, l.cin // 16, l.cout).contiguous()
         elif l.kind == "c9":
             out[l.tf_w + "/weights"] = w.reshape(3, 3, 3, 3).clone()
 
     def _b_names(self, l):
-        leaf = "/bias" if l.kind in ("dense", "ms", "fc0") else "/biases"
+        leaf = "/bias" if l.kind in ("dense", "ms", "fc0", "dout_fc") else "/biases"
         return [n + leaf for n in (l.tf_b if isinstance(l.tf_b, tuple) else (l.tf_b,))]
 
     def _views(self, flats):
@@ -326,12 +346,14 @@ class Engine:
                     b = self._perm_fc0(b)
                 if l.kind == "img_out":
                     b = torch.cat([b, torch.zeros(5, dtype=b.dtype)])
+                if l.kind == "conv_pad":
+                    b = torch.cat([b, torch.zeros(l.cout - l.cout_tf, dtype=b.dtype)])
                 views["%s.%s.b" % (net, l.name)].copy_(b)
         for i, scope in enumerate(self.bn_tf):
             perm = (lambda v: self._perm_fc0(v)) if i == 0 else (lambda v: v)
             views["g.bn%d.gamma" % i].copy_(perm(p[scope + "/gamma"]))
             views["g.bn%d.beta" % i].copy_(perm(p[scope + "/beta"]))
-            if with_moving:
+            if with_moving and self.NORM_MOVING:
                 self.bn_mm[i].copy_(perm(p[scope + "/moving_mean"]))
                 self.bn_mv[i].copy_(perm(p[scope + "/moving_variance"]))
         for i, scope in enumerate(self.dbn_tf):
@@ -377,6 +399,8 @@ class Engine:
                     b = self._perm_fc0(b, inverse=True)
                 if l.kind == "img_out":
                     b = b[:3]
+                if l.kind == "conv_pad":
+                    b = b[:l.cout_tf]
                 names = self._b_names(l)
                 for j, n in enumerate(names):
                     out[n] = b.reshape(len(names), -1)[j].clone()
@@ -384,7 +408,7 @@ class Engine:
             perm = (lambda v: self._perm_fc0(v, inverse=True)) if i == 0 else (lambda v: v)
             out[scope + "/gamma"] = perm(flat_views["g.bn%d.gamma" % i].detach().cpu()).clone()
             out[scope + "/beta"] = perm(flat_views["g.bn%d.beta" % i].detach().cpu()).clone()
-            if include_moving:
+            if include_moving and self.NORM_MOVING:
                 out[scope + "/moving_mean"] = perm(self.bn_mm[i].detach().cpu()).clone()
                 out[scope + "/moving_variance"] = perm(self.bn_mv[i].detach().cpu()).clone()
         for i, scope in enumerate(self.dbn_tf):

@@ -402,10 +402,20 @@ def ln_bwd_apply(dy, x, sums, eps, gamma, dsums, dx, dx_sum=None):
               _ps(dx), _p(dx_sum), x.shape[0], n, rows, c, _stream())
 
 
-def upscale2x(x, y, scale=1.0):
-    """y[n, i, j] = scale * x[n, i // 2, j // 2] (resize_nearest_neighbor x2, utils/ops.py:109-111)"""
+def upscale2x(x, y, scale=1.0, mask=None, mask_kind=MASK_NONE):
+    """y[n, i, j] = scale * x[n, i // 2, j // 2] (resize_nearest_neighbor x2, utils/ops.py:109-111), optionally times
+    act'(mask) (mask: post-activation values shaped like y)"""
     _, n, h, w, c = x.shape
-    _lib.call("t2i_upscale2x", _p(x), _ps(x), _p(y), _ps(y), x.shape[0], n, h, w, c, scale, _stream())
+    _lib.call("t2i_upscale2x", _p(x), _ps(x), _p(y), _ps(y), x.shape[0], n, h, w, c, scale, _p(mask),
+              0 if mask is None else _ps(mask), mask_kind if mask is not None else MASK_NONE, _stream())
+
+
+def copy_window(src, s_coff, dst, d_coff, c):
+    """dst[..., d_coff : d_coff + c] = src[..., s_coff : s_coff + c] (planes [np, n, ..., pitch])"""
+    rows = src[0].numel() // src.shape[-1]
+    assert rows == dst[0].numel() // dst.shape[-1]
+    _lib.call("t2i_copy_window", _p(src), _ps(src), src.shape[-1], s_coff, _p(dst), _ps(dst), dst.shape[-1], d_coff,
+              src.shape[0], rows, c, _stream())
 
 
 def pool2x(x, y, scale=0.25):
