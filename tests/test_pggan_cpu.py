@@ -164,3 +164,52 @@ def test_iteration_matches_oracle(stage, trans, np_):
             sure = g.abs() > 1e-3 * g.abs().max()
             if bool(sure.any()):
                 assert float((newp[n].double() - p[n])[sure].abs().max()) < 1e-9, n
+
+
+# --------------------------------------------------------------------------------------------- the mirrors
+def _model(tmp_path, stage, trans, steps=40, **kw):
+    from t2i_b200.models.pggan.pggan import PGGAN
+    from t2i_b200.models.wgancls.trainer import SyntheticTextDataset
+    data = SyntheticTextDataset(embed_dim=32, num_examples=32, image_size=4 * 2 ** (stage - 1))
+    prev = stage - 1 if trans else stage
+    return PGGAN(3, steps, str(tmp_path / ("stage%d" % stage)), str(tmp_path / ("stage%d" % prev)), data, str(tmp_path / "s"),
+                 str(tmp_path / "l"), stage, trans, precision="bf16x3", device="cpu", kernels=fk, use_graphs=False,
+                 nf_base=16, nf_cap=16, z_dim=16, embed_dim=32, compr_embed_dim=8, sample_num=2, **kw)
+
+
+def test_schedule_matches_reference():
+    from t2i_b200.models.pggan.train_pggan import schedule
+    s = schedule()
+    assert len(s) == 15 and s[0] == (1, 1, False, 16, 37500) and s[1] == (2, 1, True, 16, 37500)
+    assert s[2] == (2, 2, False, 16, 37500) and s[9] == (6, 5, True, 8, 75000) and s[14] == (8, 8, False, 8, 75000)
+    assert [t for (_, _, t, _, _) in s] == [i % 2 == 1 for i in range(15)]
+
+
+def test_mirror_stage_to_stage_restore_and_fade_in(tmp_path):
+    import os
+    m1 = _model(tmp_path, 1, False)
+    assert m1.output_size == 4 and m1.get_nf(0) == 16 and m1.get_dnf(2) == 8
+    assert m1.get_variables_up_to_stage(1) == ["d_net/rgb_stage_0/", "g_net/rgb_stage_0/", "d_net/conv_stage_0/",
+                                               "g_net/conv_stage_0/"]
+    m1.train(max_updates=2)
+    assert os.listdir(m1.check_dir_write) == ["wgancls-2.npz"]
+    v1 = m1.get_variables()
+    # the transition graph of stage 2 restores everything of stage 1 and initialises its new layers
+    m2 = _model(tmp_path, 2, True)
+    assert m2.restore is not None and set(m2.d_vars + m2.g_vars) == set(m2.variable_names())
+    m2.train(max_updates=1)
+    assert abs(m2.alpha_tra - 1.0 / 40) < 1e-12                     # alpha_assign: iter / steps (pggan.py:78-79)
+    v2 = m2.get_variables()
+    moved = [n for n in v1 if not torch.equal(torch.as_tensor(v1[n]), torch.as_tensor(v2[n]))]
+    assert moved, "one update must move the restored variables"
+    for n in v1:       # restored, then one Adam step of at most ~lr * 10 per weight
+        assert float((torch.as_tensor(v2[n]).double() - torch.as_tensor(v1[n]).double()).abs().max()) < 1e-4, n
+    assert any(n.startswith("g_net/conv_stage_1/") for n in v2) and any(n.startswith("d_net/rgb_stage_1/") for n in v2)
+    # eager sub-graphs at this object's stage only
+    img, mean, ls = m2.generator(np.random.normal(0, 1, (3, 16)), np.random.normal(0, 1, (3, 32)))
+    assert img.shape == (3, 8, 8, 3) and mean.shape == (3, 8)
+    assert m2.discriminator(img, np.random.normal(0, 1, (3, 32))).shape == (3, 1, 1, 1)
+    with pytest.raises(NotImplementedError):
+        m2.generator(np.zeros((3, 16)), np.zeros((3, 32)), stages=1, t=False)
+    with pytest.raises(RuntimeError):
+        _model(tmp_path / "elsewhere", 2, True).train(max_updates=1)      # no stage-1 checkpoint to fade in from (:149-151)
