@@ -13,8 +13,8 @@ TF semantics restated (recalled from TF 1.4; cannot be checked against TF here):
   * tf.nn.pool AVG 2x2 stride 2 SAME on even extents = plain 2x2 mean; resize_nearest_neighbor x2: out[i,j] = in[i//2,j//2].
   * conv2d 2x2 stride 1 SAME: pad_total = 1 -> 0 before, 1 after (bottom / right).
   * the graph is NHWC throughout (utils/ops.py default df=NHWC); the dense output is reshaped to [-1, 4, 4, C].
-  * `epsilon` is fed by the trainer (pggan.py:205) but the graph OVERWRITES it with tf.random_uniform (:68): the draw is
-    an explicit input here (feed['epsilon']).
+  * the graph rebinds self.epsilon to a tf.random_uniform tensor (:68) and the trainer feeds THAT tensor (:205), so the
+    fed U(0,1) draw is the value used: an explicit input here (feed['epsilon']).
   * alpha_tra = iter / steps is assigned under a control dependency of D_optim only (:84,119); the forward ops read the
     variable unordered with respect to the assign.  Deterministic choice (also the product's): the assign happens
     first, both runs of iteration `iter` use alpha = iter / steps.
