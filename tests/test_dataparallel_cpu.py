@@ -205,3 +205,123 @@ def test_two_rank_d_run_equals_single_process(tmp_path):
     assert r["smax"] < 1e-9, r
     assert abs(r["kt"] - r["kt_ref"]) < 1e-12
     assert len(r["calls"]) == 2 and r["same"], r      # exactly one allreduce per optimizer step
+
+
+def _worker_pggan(rank, world, port, out):
+    """conditional PGGAN (transition stage) on 2 ranks == the single-process iteration on the global batch: layer_norm is
+    per sample and d_net has no normalisation, so ONE gradient all-reduce per optimizer step is exact"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import pggan_oracle as P
+    from t2i_b200.engine_pggan import PgganEngine
+    from test_pggan_cpu import TINY, boosted_params
+    torch.set_num_threads(1)
+    cfg = P.PgganCfg(stage=2, trans=True, **dict(TINY, batch_size=4))
+    gb = cfg.batch_size
+    b = gb // world
+    p = boosted_params(cfg)
+    feed = P.make_feed(cfg, 12, torch.float64)
+    calls = []
+
+    def allreduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    exact = dict(act_dtype=torch.float64, f32_dtype=torch.float64)
+    args = (cfg.stage, cfg.trans, cfg.z_dim, cfg.embed_dim, cfg.compr_embed_dim, cfg.nf_base, cfg.nf_cap, cfg.d_embed, cfg.rgb_mid)
+    eng = PgganEngine(fk, "cpu", b, 1, *args, world, allreduce, **exact)
+    ref = PgganEngine(fk, "cpu", gb, 1, *args, **exact)
+    sl = slice(rank * b, (rank + 1) * b)
+    keys = ("x", "x_mismatch", "cond", "z", "epsilon")
+    res = {}
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.set_params_tf(p)
+        e.load_feed(**{k: feed[k][sel] for k in keys}, tn_eps=feed["tn_eps"][sel])
+        e.d_step(0.4)
+    res["img"] = float((eng.d["img"][:b] - ref.d["img"][:gb][sl]).abs().max())
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    res["d_grads"] = max(float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)) for n in gf if n.startswith("d_net/"))
+    sc, scr = eng.scalars_dict(), ref.scalars_dict()
+    res["gp"] = scr["real_gp"]
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.load_feed(tn_eps=feed["tn_eps_g"][sel])
+        e.g_step()
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    res["g_grads"] = max(float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)) for n in gf if n.startswith("g_net/"))
+    sc, scr = eng.scalars_dict(), ref.scalars_dict()
+    res["scalars"] = max(abs(sc[k] - scr[k]) / max(1.0, abs(scr[k])) for k in sc)
+    ps, pf = eng.get_params_tf(), ref.get_params_tf()
+    res["params"] = max(float((ps[n] - pf[n]).abs().max()) for n in pf)
+    res["calls"], res["d_n"], res["g_n"] = calls, eng.d_n + 8, eng.g_n + 8
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_pggan_iteration_equals_single_process(tmp_path):
+    out = str(tmp_path / "p.pt")
+    port = 35500 + os.getpid() % 2000
+    mp.spawn(_worker_pggan, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["gp"] > 1e-3, r                                # the penalty (and its second-order term) is active
+    assert r["img"] < 1e-10 and r["d_grads"] < 1e-8 and r["g_grads"] < 1e-8, r
+    assert r["scalars"] < 1e-9 and r["params"] < 1e-10, r
+    assert r["calls"] == [r["d_n"], r["g_n"]], r            # exactly one all-reduce per optimizer step
+
+
+def _worker_stage2(rank, world, port, out):
+    """StackGAN stage-II under data parallelism: one gradient all-reduce per optimizer step, replicas stay identical,
+    the frozen stage-I generator is never touched"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import stackgan2_oracle as S2
+    from t2i_b200.engine_stage2 import StageIIEngine
+    from test_stackgan2_cpu import TINY, boosted_params
+    torch.set_num_threads(1)
+    cfg = S2.Stage2Cfg(**dict(TINY, batch_size=4))
+    b = cfg.batch_size // world
+    p = boosted_params(cfg)
+    feed = S2.make_feed(cfg, 21, torch.float64)
+    calls = []
+
+    def allreduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    eng = StageIIEngine(fk, "cpu", b, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
+                        cfg.d_beta1, cfg.g_beta1, cfg.alpha_mismatch, cfg.kl_coeff, world, allreduce, s1_gf=cfg.s1_gf_dim,
+                        act_dtype=torch.float64, f32_dtype=torch.float64)
+    eng.set_params_tf(p)
+    sl = slice(rank * b, (rank + 1) * b)
+    eng.load_feed(x=feed["x"][sl], x_mismatch=feed["x_mismatch"][sl], cond=feed["cond"][sl], z=feed["z"][sl],
+                  tn_eps=feed["tn_eps"][sl], tn_s1=feed["tn_s1"][sl])
+    eng.d_step(cfg.lr)
+    eng.load_feed(tn_eps=feed["tn_eps_g"][sl], tn_s1=feed["tn_s1_g"][sl])
+    eng.g_step(cfg.lr)
+    flat = torch.cat([eng.flat["d"], eng.flat["g"]])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    sc = eng.scalars_dict()
+    q = eng.get_params_tf()
+    frozen = all(torch.equal(q[n].double(), p[n]) for n in p if n.startswith("g_net/") and "moving" not in n)
+    if rank == 0:
+        torch.save({"calls": calls, "same": all(torch.equal(gathered[0], t) for t in gathered), "frozen": frozen,
+                    "finite": all(v == v for v in sc.values()), "d_n": eng.d_n + 8, "g_n": eng.g_n + 8}, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_stage2_iteration(tmp_path):
+    out = str(tmp_path / "s2.pt")
+    port = 37500 + os.getpid() % 2000
+    mp.spawn(_worker_stage2, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["calls"] == [r["d_n"], r["g_n"]], r        # exactly one all-reduce per optimizer step
+    assert r["same"] and r["finite"] and r["frozen"], r
