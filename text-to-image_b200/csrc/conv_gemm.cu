@@ -61,6 +61,7 @@ struct alignas(64) ConvGemmParams {
     int second_kind;
     int stat_n, stat_c;
     int w_n0;                  // first output channel inside the weight matrix (output-channel window)
+    int last_k_steps;          // 16-channel MMA steps of the LAST K chunk (input channels beyond x.c are zero fill: skipped)
     int stat_acc;              // channels of per-CTA shared accumulators (flushed once at the end), 0 = none
     int dbg;                   // T2I_STAT_DBG bit field (tools/bench_conv.py): skip parts of the statistics path
 };
@@ -260,9 +261,12 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 300 + acc);
                 tc_fence_after();
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+                int kc = 0;     // K chunk inside the tap: the last one may hold fewer than 64 real input channels
                 for (int kb = 0; kb < kb_per_tile; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 200 + stage);
                     tc_fence_after();
+                    const int k_steps = (kc == prm.k_chunks - 1) ? prm.last_k_steps : kBlockK / 16;
+                    if (++kc == prm.k_chunks) kc = 0;
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
                     const uint64_t da = make_sw128_desc(sa, 0, 1024);
                     // K-major: +32 bytes per 16-element K step inside the 128B swizzle row (address >> 4);
@@ -270,8 +274,10 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                     const uint64_t db = B_KN ? make_sw128_desc(sa + kABytes, 8192, 1024) : make_sw128_desc(sa + kABytes, 0, 1024);
 #pragma unroll
                     for (int k = 0; k < kBlockK / 16; ++k) {
-                        if (CTA2) umma_bf16_2sm(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
-                        else umma_bf16(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
+                        if (k < k_steps) {
+                            if (CTA2) umma_bf16_2sm(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
+                            else umma_bf16(d_tmem, da + 2 * k, db + (B_KN ? 128 * k : 2 * k), idesc, (kb | k) != 0);
+                        }
                     }
                     if (CTA2) {     // free the stage / publish the accumulator in BOTH CTAs
                         umma_commit_2sm(&empty_bar[stage]);
@@ -685,6 +691,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     prm.tiles_m = ceil_div(prm.N, prm.bn) * prm.tiles_p * prm.tiles_q;
     prm.Cout = y.c;
     prm.k_chunks = ceil_div(x.c, kBlockK);
+    prm.last_k_steps = ceil_div(x.c - (prm.k_chunks - 1) * kBlockK, 16);
     prm.np = d->np;
     prm.n_pass = (d->np == 2) ? 3 : 1;
     prm.has_add = d->add.ptr != nullptr;
@@ -707,15 +714,20 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const int sms = num_sms();
     // CTA pairs (cta_group::2, 256-pixel tiles) whenever there are at least two pixel tiles
     const bool allow_cta2 = [] { const char* e = getenv("T2I_CONV_CTA2"); return !(e && e[0] == '0'); }();
-    const bool cta2 = allow_cta2 && prm.tiles_m >= 2;
+    // at most 64 output channels (the 128x128 / 256x256 maps of StackGAN stage-II and PGGAN): a 64-wide channel tile
+    // halves the MMA work of the 128-wide one.  With MN-major weights a CTA pair would stage half a 64-channel
+    // atom per CTA, so those launches stay single-CTA.
+    static const bool allow_n64 = [] { const char* e = getenv("T2I_CONV_N64"); return !(e && e[0] == '0'); }();
+    const bool small_n = allow_n64 && y.c <= 64;
+    const bool cta2 = allow_cta2 && prm.tiles_m >= 2 && !(small_n && kn);
     const int units_m = cta2 ? ceil_div(prm.tiles_m, 2) : prm.tiles_m;     // schedulable pixel tiles (pairs)
     const int workers = cta2 ? sms / 2 : sms;                              // CTAs or CTA pairs
-    int block_n = 128;
+    int block_n = small_n ? 64 : 128;
     if (y.c > 128 && (long long)prm.tt.n_phases * units_m * ceil_div(y.c, 256) >= workers) block_n = 256;
     {   // tools/bench_conv.py: force the channel tile (development aid)
         const char* e = getenv("T2I_CONV_BN");
         if (e && atoi(e) == 256 && y.c > 128) block_n = 256;
-        if (e && atoi(e) == 128) block_n = 128;
+        if (e && atoi(e) == 128 && !small_n) block_n = 128;
     }
     prm.tiles_co = ceil_div(y.c, block_n);
     prm.total_tiles = prm.tt.n_phases * units_m * prm.tiles_co;
@@ -787,17 +799,22 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
 
     const int grid = (prm.total_tiles < workers ? prm.total_tiles : workers) * (cta2 ? 2 : 1);
     typedef void (*KernelFn)(const ConvGemmParams);
-    static bool attr_done[16] = {};
-    const int variant = (stats ? 8 : 0) + (cta2 ? 4 : 0) + (block_n == 256 ? 2 : 0) + (kn ? 1 : 0);
-    const KernelFn fns[16] = {
+    static bool attr_done[24] = {};
+    const int variant = (stats ? 12 : 0) + (cta2 ? 6 : 0) + (block_n == 256 ? 2 : block_n == 64 ? 4 : 0) + (kn ? 1 : 0);
+    const KernelFn fns[24] = {
         conv_gemm_kernel<128, false, false, false>, conv_gemm_kernel<128, true, false, false>,
         conv_gemm_kernel<256, false, false, false>, conv_gemm_kernel<256, true, false, false>,
+        conv_gemm_kernel<64, false, false, false>,  conv_gemm_kernel<64, true, false, false>,
         conv_gemm_kernel<128, false, true, false>,  conv_gemm_kernel<128, true, true, false>,
         conv_gemm_kernel<256, false, true, false>,  conv_gemm_kernel<256, true, true, false>,
+        conv_gemm_kernel<64, false, true, false>,   nullptr,
         conv_gemm_kernel<128, false, false, true>,  conv_gemm_kernel<128, true, false, true>,
         conv_gemm_kernel<256, false, false, true>,  conv_gemm_kernel<256, true, false, true>,
+        conv_gemm_kernel<64, false, false, true>,   conv_gemm_kernel<64, true, false, true>,
         conv_gemm_kernel<128, false, true, true>,   conv_gemm_kernel<128, true, true, true>,
-        conv_gemm_kernel<256, false, true, true>,   conv_gemm_kernel<256, true, true, true>};
+        conv_gemm_kernel<256, false, true, true>,   conv_gemm_kernel<256, true, true, true>,
+        conv_gemm_kernel<64, false, true, true>,    nullptr};
+    if (fns[variant] == nullptr) return fail(T2I_ERR_BAD_ARG, "no kernel variant %d", variant);
     if (!attr_done[variant]) {
         cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
         if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));

@@ -50,6 +50,7 @@ struct alignas(64) WgradParams {
     int tiles_co, tiles_ci, jobs;    // jobs = n_phases * taps_per_phase
     int splits, kb_per_split;
     int total_work;        // jobs * tiles_co * tiles_ci * splits
+    int tap_fast;          // work order: taps fastest (the taps of one pixel range run together and share x / dy in L2)
     int n_pass;
     int cout, cin;
     float* dw;
@@ -109,10 +110,16 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
     };
     auto decode = [&](int w) {
         Work k;
-        k.split = w % prm.splits; w /= prm.splits;
-        k.cit = w % prm.tiles_ci; w /= prm.tiles_ci;
-        k.cot = w % prm.tiles_co; w /= prm.tiles_co;
-        k.job = w;   // phase * taps_per_phase + t
+        if (prm.tap_fast) {   // single channel tile, operands far larger than L2: every tap of a pixel range at once
+            k.job = w % prm.jobs; w /= prm.jobs;
+            k.split = w;
+            k.cit = k.cot = 0;
+        } else {
+            k.split = w % prm.splits; w /= prm.splits;
+            k.cit = w % prm.tiles_ci; w /= prm.tiles_ci;
+            k.cot = w % prm.tiles_co; w /= prm.tiles_co;
+            k.job = w;   // phase * taps_per_phase + t
+        }
         k.kb_begin = k.split * prm.kb_per_split;
         k.kb_end = k.kb_begin + prm.kb_per_split;
         if (k.kb_end > prm.k_blocks) k.kb_end = prm.k_blocks;
@@ -352,10 +359,12 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     prm.k_blocks = ceil_div(prm.N, prm.bn) * prm.tiles_p * prm.tiles_q;
     prm.cout = d->cout;
     prm.cin = d->cin;
-    // tile shape: prefer 256 input channels per tile, else 256 output channels (two accumulators)
+    // tile shape: prefer 256 input channels per tile, else 256 output channels (two accumulators); layers with at
+    // most 64 input channels (the 128x128 / 256x256 maps of StackGAN stage-II and PGGAN) take a 64-wide tile
     int mt = 1, bnn = 128;
     if (x.c >= 256) bnn = 256;
     else if (dy.c >= 256) mt = 2;
+    else if (x.c <= 64) bnn = 64;
     static const bool allow_cta2 = [] { const char* e = getenv("T2I_WGRAD_CTA2"); return !(e && e[0] == '0'); }();
     const bool cta2 = allow_cta2 && bnn == 256 && dy.c >= 256;      // CTA pair: 256 co x 256 ci
     if (cta2) mt = 2;                                               // tile covers 256 output channels (128 per CTA)
@@ -364,6 +373,10 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     prm.jobs = prm.tt.n_phases * prm.tt.taps_per_phase;
     prm.n_pass = (d->np == 2) ? 3 : 1;
     const int tiles = prm.jobs * prm.tiles_co * prm.tiles_ci;
+    // one channel tile, several taps, and operands that cannot stay in L2 between taps (each tap is a full pass over
+    // x and dy): order the work taps-fastest so that a pixel range is fetched from HBM once
+    const long long operand_bytes = (long long)prm.k_blocks * kWK * (x.c + dy.c) * 2 * d->np;
+    prm.tap_fast = (prm.tiles_co * prm.tiles_ci == 1 && prm.jobs > 1 && operand_bytes > (64ll << 20)) ? 1 : 0;
     int splits = d->split_k;
     if (splits <= 0) {
         // Cost model: the launch runs in ceil(tiles * s / workers) waves; one wave costs the K blocks of a split
@@ -381,6 +394,17 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
             }
         }
     }
+    if (prm.tap_fast && d->split_k <= 0) {
+        // short pixel ranges (~96 K blocks = 6144 pixels) so that the taps of a range, launched side by side, stay
+        // within L2 reach of each other; round the item count up to whole waves
+        const int workers = num_sms();
+        long long sct = prm.k_blocks / 96;
+        if (sct < splits) sct = splits;
+        if (sct > 4096) sct = 4096;
+        const long long waves = ceil_div((int)(sct * prm.jobs), workers);
+        sct = waves * workers / prm.jobs;
+        if (sct >= 1) splits = (int)sct;
+    }
     if (splits > prm.k_blocks) splits = prm.k_blocks;
     prm.kb_per_split = ceil_div(prm.k_blocks, splits);
     prm.splits = ceil_div(prm.k_blocks, prm.kb_per_split);
@@ -393,9 +417,11 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
 
     prm.total_work = tiles * prm.splits;
     const int workers_all = cta2 ? num_sms() / 2 : num_sms();
+    if (prm.total_work <= workers_all) prm.tap_fast = 0;       // a single wave: the order does not matter
     const int grid = prm.total_work < workers_all ? prm.total_work : workers_all;     // persistent CTAs (pairs)
     if (cta2) return launch_wgrad<1, 256, true>(prm, grid, stream);
     if (bnn == 256) return launch_wgrad<1, 256, false>(prm, grid, stream);
     if (mt == 2) return launch_wgrad<2, 128, false>(prm, grid, stream);
+    if (bnn == 64) return launch_wgrad<1, 64, false>(prm, grid, stream);
     return launch_wgrad<1, 128, false>(prm, grid, stream);
 }

@@ -20,6 +20,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--no-graphs", action="store_true", help="eager launches (ncu launch lists)")
     args = ap.parse_args()
     mdir = os.path.join(ROOT, "text-to-image_b200", "models", "stackgan")
     c1 = config_from_yaml(os.path.join(mdir, "stageI", "cfg", "flowers.yml"))
@@ -27,16 +29,16 @@ def main():
     B = args.batch
     c1.TRAIN.BATCH_SIZE = c2.TRAIN.BATCH_SIZE = B
     c1.TRAIN.SAMPLE_NUM = c2.TRAIN.SAMPLE_NUM = B
-    s1 = StageI(c1, precision="bf16")
+    s1 = StageI(c1, precision="bf16", use_graphs=not args.no_graphs)
     s1.initialize(0)
-    m = StageII(s1, c2)
+    m = StageII(s1, c2, use_graphs=not args.no_graphs)
     m.initialize(1)
     eng = m._train_engine()
     gen = torch.Generator().manual_seed(1)
     eng.load_feed(x=torch.rand(B, 256, 256, 3, generator=gen) * 2 - 1, x_mismatch=torch.rand(B, 256, 256, 3, generator=gen) * 2 - 1,
                   cond=torch.randn(B, 1024, generator=gen), z=torch.randn(B, 100, generator=gen),
                   tn_eps=torch.randn(B, 128, generator=gen).clamp_(-2, 2), tn_s1=torch.randn(B, 128, generator=gen).clamp_(-2, 2))
-    for _ in range(3):
+    for _ in range(args.warmup):
         eng.d_step(2e-4)
         eng.g_step(2e-4)
     torch.cuda.synchronize()
