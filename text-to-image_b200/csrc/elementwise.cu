@@ -522,12 +522,39 @@ __global__ void bn_bwd_apply_kernel(const bf16* __restrict__ dy, long long dy_ps
 // (accumulated by the producing conv_gemm's epilogue).  Every thread derives mean / rstd of its 8 channels;
 // block row 0 also publishes mean / biased variance / rstd for the backward pass and, when asked (the G run:
 // UPDATE_OPS, model.py:98,102), steps the moving statistics (utils/ops.py:20-29: decay 0.9, unbiased variance).
-__global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps, const float* __restrict__ sums,
-                                      float inv_rows, float eps, const float* __restrict__ gamma,
-                                      const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
-                                      bf16* __restrict__ y, long long y_ps, int np, long long rows, int c, int relu, int CG,
-                                      float* mean_out, float* rstd_out, float* var_out, float* mm, float* mv, float decay,
-                                      float bessel, int y_pitch, float affine_scale) {
+// Raw 16-byte register staging: the loads of a trip stay packed (4 registers per 8 values and plane) until they are
+// used, which keeps these streaming kernels at 3 (np = 1) / 2 resident blocks per SM.  With the values unpacked up
+// front the kernels needed 114 / 146 registers -> 2 / 1 blocks per SM and ~32 KB in flight per SM, a third of what
+// the HBM latency-bandwidth product asks for (measured 1.6-2.4 TB/s).
+template <int NP>
+struct Raw8 {
+    uint4 r[NP];
+};
+template <int NP>
+__device__ __forceinline__ void ld_raw(const bf16* p, long long ps, Raw8<NP>& o) {
+    o.r[0] = *reinterpret_cast<const uint4*>(p);
+    if (NP == 2) o.r[NP - 1] = *reinterpret_cast<const uint4*>(p + ps);
+}
+template <int NP>
+__device__ __forceinline__ void raw_f(const Raw8<NP>& o, float* v) {
+    unpack8(o.r[0], v);
+    if (NP == 2) {
+        float l[8];
+        unpack8(o.r[NP - 1], l);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j] += l[j];
+    }
+}
+
+template <int NP, bool RES>
+__global__ void __launch_bounds__(256, NP == 1 ? 3 : 2)
+bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps, const float* __restrict__ sums,
+                      float inv_rows, float eps, const float* __restrict__ gamma,
+                      const float* __restrict__ beta, const bf16* __restrict__ res, long long r_ps,
+                      bf16* __restrict__ y, long long y_ps, long long rows, int c, int relu, int CG,
+                      float* mean_out, float* rstd_out, float* var_out, float* mm, float* mv, float decay,
+                      float bessel, int y_pitch, float affine_scale) {
+    constexpr int U = (NP == 1 && !RES) ? 8 : 4;      // rows per thread and trip, all loads issued before the first use
     pdl_launch_dependents();
     pdl_wait();
     const int RY = blockDim.x / CG;
@@ -561,33 +588,36 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
             sh[j] = be[j] * affine_scale - m * sc[j];
         }
     }
-    // four rows per trip, all loads issued before the first use
     const long long stride = (long long)gridDim.y * RY;
-    for (long long r0 = (long long)blockIdx.y * RY + ry; r0 < rows; r0 += 4 * stride) {
-        float v[4][8], rr[4][8];
+    for (long long r0 = (long long)blockIdx.y * RY + ry; r0 < rows; r0 += U * stride) {
+        Raw8<NP> xr[U], rr[RES ? U : 1];
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * stride;
             if (r < rows) {
-                load8(x + r * c + ch, x_ps, np, v[u]);
-                if (res != nullptr) load8(res + r * c + ch, r_ps, np, rr[u]);
+                ld_raw<NP>(x + r * c + ch, x_ps, xr[u]);
+                if (RES) ld_raw<NP>(res + r * c + ch, r_ps, rr[RES ? u : 0]);
             }
         }
 #pragma unroll
-        for (int u = 0; u < 4; ++u) {
+        for (int u = 0; u < U; ++u) {
             const long long r = r0 + u * stride;
             if (r < rows) {
+                float v[8];
+                raw_f<NP>(xr[u], v);
 #pragma unroll
-                for (int j = 0; j < 8; ++j) v[u][j] = v[u][j] * sc[j] + sh[j];
-                if (res != nullptr) {
+                for (int j = 0; j < 8; ++j) v[j] = v[j] * sc[j] + sh[j];
+                if (RES) {
+                    float q[8];
+                    raw_f<NP>(rr[RES ? u : 0], q);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[u][j] += rr[u][j];
+                    for (int j = 0; j < 8; ++j) v[j] += q[j];
                 }
                 if (relu) {
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) v[u][j] = fmaxf(v[u][j], act_neg * v[u][j]);
+                    for (int j = 0; j < 8; ++j) v[j] = fmaxf(v[j], act_neg * v[j]);
                 }
-                store8(y + r * y_pitch + ch, y_ps, np, v[u]);
+                store8(y + r * y_pitch + ch, y_ps, NP, v);
             }
         }
     }
@@ -595,14 +625,18 @@ __global__ void bn_apply_train_kernel(const bf16* __restrict__ x, long long x_ps
 
 // BatchNorm input-gradient with the reductions already done by the kernel that produced dy:
 // dbeta = sum dy, dot = sum dy * x (raw pre-normalisation input).  dgamma = rstd * (dot - mean * dbeta);
-// dx = gamma * rstd * (dy - dbeta/R - xhat * dgamma/R).  Block row 0 adds dgamma into the gradient buffer;
-// dx_sum (optional) accumulates the per-channel sum of dx = the bias gradient of the conv in front of the BN.
-__global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ x,
-                                    long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
-                                    const float* __restrict__ gamma, const float* __restrict__ dot,
-                                    const float* __restrict__ dbeta, float* dgamma_out, float* dbeta_out, float out_scale,
-                                    int dot_normalised, bf16* __restrict__ dx, long long dx_ps, float* dx_sum, int np,
-                                    long long rows, int c, float inv_rows, int CG, int dy_pitch, float affine_scale) {
+// dx = gamma * rstd * (dy - dbeta/R - xhat * dgamma/R) = A * dy + B * x + C per channel.  Block row 0 adds dgamma into
+// the gradient buffer; dx_sum (optional) accumulates the per-channel sum of dx = the bias gradient of the conv in
+// front of the BN.
+template <int NP>
+__global__ void __launch_bounds__(256, NP == 1 ? 3 : 2)
+bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps, const bf16* __restrict__ x,
+                    long long x_ps, const float* __restrict__ mean, const float* __restrict__ rstd,
+                    const float* __restrict__ gamma, const float* __restrict__ dot,
+                    const float* __restrict__ dbeta, float* dgamma_out, float* dbeta_out, float out_scale,
+                    int dot_normalised, bf16* __restrict__ dx, long long dx_ps, float* dx_sum,
+                    long long rows, int c, float inv_rows, int CG, int dy_pitch, float affine_scale) {
+    constexpr int U = 4;
     pdl_launch_dependents();
     pdl_wait();
     __shared__ float sh[256 * 8];
@@ -612,9 +646,9 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
     const int ry = threadIdx.x / CG;
     float acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (ch < c && ry < RY) {
-        float mu[8], rs[8], a[8], b0[8], b1[8];
+        float A[8], B[8], C[8];
         {
-            float ga[8], dt[8], db8[8];
+            float mu[8], rs[8], ga[8], dt[8], db8[8];
             load_f8(mean + ch, mu);
             load_f8(rstd + ch, rs);
             load_f8(gamma + ch, ga);
@@ -629,32 +663,36 @@ __global__ void bn_bwd_fused_kernel(const bf16* __restrict__ dy, long long dy_ps
                     dgamma_out[ch + j] += dg * out_scale;
                     if (dbeta_out != nullptr) dbeta_out[ch + j] += db * out_scale;
                 }
-                a[j] = ga[j] * affine_scale * rs[j];
-                b0[j] = db * inv_rows;
-                b1[j] = dg * inv_rows;
+                const float a = ga[j] * affine_scale * rs[j];
+                A[j] = a;
+                B[j] = -a * rs[j] * dg * inv_rows;
+                C[j] = -a * db * inv_rows - B[j] * mu[j];
             }
         }
         const long long stride = (long long)gridDim.y * RY;
-        for (long long r0 = (long long)blockIdx.y * RY + ry; r0 < rows; r0 += 4 * stride) {
-            float g[4][8], xv[4][8];
+        for (long long r0 = (long long)blockIdx.y * RY + ry; r0 < rows; r0 += U * stride) {
+            Raw8<NP> gr[U], xr[U];
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const long long r = r0 + u * stride;
                 if (r < rows) {
-                    load8(dy + r * dy_pitch + ch, dy_ps, np, g[u]);
-                    load8(x + r * c + ch, x_ps, np, xv[u]);
+                    ld_raw<NP>(dy + r * dy_pitch + ch, dy_ps, gr[u]);
+                    ld_raw<NP>(x + r * c + ch, x_ps, xr[u]);
                 }
             }
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
+            for (int u = 0; u < U; ++u) {
                 const long long r = r0 + u * stride;
                 if (r < rows) {
+                    float g[8], xv[8];
+                    raw_f<NP>(gr[u], g);
+                    raw_f<NP>(xr[u], xv);
 #pragma unroll
                     for (int j = 0; j < 8; ++j) {
-                        g[u][j] = a[j] * (g[u][j] - b0[j] - (xv[u][j] - mu[j]) * rs[j] * b1[j]);
-                        acc[j] += g[u][j];
+                        g[j] = A[j] * g[j] + B[j] * xv[j] + C[j];
+                        acc[j] += g[j];
                     }
-                    store8(dx + r * c + ch, dx_ps, np, g[u]);
+                    store8(dx + r * c + ch, dx_ps, NP, g);
                 }
             }
         }
@@ -1220,13 +1258,21 @@ extern "C" int t2i_bn_apply_train(const void* x, long long x_ps, const float* su
     if ((moving_mean == nullptr) != (moving_var == nullptr)) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: moving pair");
     int CG;
     dim3 grid;
-    rowwise_geometry(rows, c, 256, &CG, &grid, 8);
+    if (np != 1 && np != 2) return fail(T2I_ERR_BAD_ARG, "bn_apply_train: np must be 1 or 2");
+    const bool has_res = residual != nullptr;
+    rowwise_geometry(rows, c, 256, &CG, &grid, (np == 1 && !has_res) ? 8 : 4);
     const long long n = stat_rows > 0 ? stat_rows : rows;     // values per channel behind the sums
     const float bessel = n > 1 ? (float)n / (float)(n - 1) : 1.f;
-    launch_ew(bn_apply_train_kernel, dim3(grid), dim3(256), 0, STREAM, 
-        static_cast<const bf16*>(x), x_ps, sums, 1.f / (float)n, eps, gamma, beta, static_cast<const bf16*>(residual),
-        r_ps, static_cast<bf16*>(y), y_ps, np, rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel,
-        y_pitch, affine_scale);
+#define T2I_BN_APPLY(NP, RES)                                                                                            \
+    launch_ew(bn_apply_train_kernel<NP, RES>, dim3(grid), dim3(256), 0, STREAM, static_cast<const bf16*>(x), x_ps, sums, \
+              1.f / (float)n, eps, gamma, beta, static_cast<const bf16*>(residual), r_ps, static_cast<bf16*>(y), y_ps,  \
+              rows, c, relu, CG, mean, rstd, var, moving_mean, moving_var, decay, bessel, y_pitch, affine_scale)
+    if (np == 1) {
+        if (has_res) T2I_BN_APPLY(1, true); else T2I_BN_APPLY(1, false);
+    } else {
+        if (has_res) T2I_BN_APPLY(2, true); else T2I_BN_APPLY(2, false);
+    }
+#undef T2I_BN_APPLY
     return check_launch("bn_apply_train");
 }
 extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, long long x_ps, const float* mean,
@@ -1238,12 +1284,15 @@ extern "C" int t2i_bn_bwd_fused(const void* dy, long long dy_ps, const void* x, 
     if (dy_pitch == 0) dy_pitch = c;
     int CG;
     dim3 grid;
+    if (np != 1 && np != 2) return fail(T2I_ERR_BAD_ARG, "bn_bwd_fused: np must be 1 or 2");
     rowwise_geometry(rows, c, 256, &CG, &grid, 8);
     const long long n = stat_rows > 0 ? stat_rows : rows;
-    launch_ew(bn_bwd_fused_kernel, dim3(grid), dim3(256), 0, STREAM, 
-        static_cast<const bf16*>(dy), dy_ps, static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma,
-        dbeta_out, out_scale, dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, np, rows, c, 1.f / (float)n, CG,
-        dy_pitch, affine_scale);
+#define T2I_BN_BWD(NP)                                                                                                   \
+    launch_ew(bn_bwd_fused_kernel<NP>, dim3(grid), dim3(256), 0, STREAM, static_cast<const bf16*>(dy), dy_ps,            \
+              static_cast<const bf16*>(x), x_ps, mean, rstd, gamma, dot, dbeta, dgamma, dbeta_out, out_scale,           \
+              dot_normalised, static_cast<bf16*>(dx), dx_ps, dx_sum, rows, c, 1.f / (float)n, CG, dy_pitch, affine_scale)
+    if (np == 1) T2I_BN_BWD(1); else T2I_BN_BWD(2);
+#undef T2I_BN_BWD
     return check_launch("bn_bwd_fused");
 }
 extern "C" int t2i_bn_update_moving(float* mm, float* mv, const float* mean, const float* var, long long rows, int c,

@@ -139,6 +139,9 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                 const CUtensorMap* x_map = &prm.x_maps[tap.map];
                 const int co_cta = (wk.cot * kPair + rank) * Cfg::kM;        // first output channel of this CTA
                 const int ci_cta = wk.cit * BN + rank * Cfg::kBCols;         // first input channel staged by this CTA
+                int a_atoms = (prm.cout - co_cta + 63) / 64;                 // atoms of dy with at least one real channel
+                if (a_atoms > Cfg::kM / 64) a_atoms = Cfg::kM / 64;
+                if (a_atoms < 1) a_atoms = 1;
                 for (int pass = 0; pass < prm.n_pass; ++pass) {
                     const int pa = (pass == 1) ? 1 : 0;  // dy plane: hi, lo, hi
                     const int pb = (pass == 2) ? 1 : 0;  // x  plane: hi, hi, lo
@@ -150,10 +153,13 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
                         if (!CTA2) {
-                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kStageBytes);
+                            // 64-channel atoms of dy that lie entirely beyond cout are not fetched: their accumulator
+                            // rows are never written out, so whatever the shared memory holds there is harmless
+                            mbar_arrive_expect_tx(&full_bar[stage], a_atoms * kWAtomBytes + Cfg::kBBytes);
 #pragma unroll
                             for (int a = 0; a < Cfg::kM / 64; ++a)
-                                tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, co_cta + a * 64, q0, p0, n0, pa);
+                                if (a < a_atoms)
+                                    tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, co_cta + a * 64, q0, p0, n0, pa);
 #pragma unroll
                             for (int b = 0; b < Cfg::kBCols / 64; ++b)
                                 tma_load_5d(x_map, &full_bar[stage], sa + Cfg::kABytes + b * kWAtomBytes, ci_cta + b * 64,
