@@ -79,6 +79,8 @@ class Engine:
         self.side_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.comm_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self.copy_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
+        self._scalars_host = self._scalars_event = None
+        self._scalars_published = False
         self.replayed_launches = 0      # kernels executed through graph replays
         self.captured_launches = 0      # kernels recorded (not executed) during captures
         if share_from is None:
@@ -876,11 +878,28 @@ class Engine:
         # generator forward does not depend on them and overlaps (it joins before its d_net forward).
         with self._on_comm():
             self._reduce("d")                   # outside the graphs
-            self._run("d_b", self._d_tail)
+            self._run("d_b", self._d_tail_scalars)
+            self._publish_scalars()             # the losses are final here: a fetch need not wait for Adam
+            self._run("d_c", self._d_tail_adam)
 
-    def _d_tail(self):
+    def _d_tail_scalars(self):
         self.K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, KT_LR)  # :79-91,100
+
+    def _d_tail_adam(self):
         self._adam("d")                                                                    # :94-97
+
+    def _publish_scalars(self):
+        """Copy the scalars vector to pinned host memory on the current stream and mark the point with an event:
+        ``scalars_dict`` (the D_loss / G_loss fetch of sess.run) then waits for the losses only, not for the
+        optimizer kernels queued behind them."""
+        if self.dev.type != "cuda":
+            return
+        if self._scalars_host is None:
+            self._scalars_host = torch.zeros(16, dtype=self.f32_dtype).pin_memory()
+            self._scalars_event = torch.cuda.Event()
+        self._scalars_host.copy_(self.scalars, non_blocking=True)
+        self._scalars_event.record()
+        self._scalars_published = True
 
     def _d_body_gen(self):
         g = self.g
@@ -924,11 +943,14 @@ class Engine:
         self.join_comm()                        # d_net's weights of this iteration are final from here on
         self._run("g_a2", self._g_body)
         self._reduce("g")
-        self._run("g_b", self._g_tail)
+        self._run("g_b", self._g_tail_scalars)
+        self._publish_scalars()
+        self._run("g_c", self._g_tail_adam)
 
-    def _g_tail(self):
-        K = self.K
-        K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)        # model.py:92
+    def _g_tail_scalars(self):
+        self.K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)   # model.py:92
+
+    def _g_tail_adam(self):
         self._adam("g")                                                                  # :103-106
 
     def _g_body_fwd(self):
@@ -953,6 +975,10 @@ class Engine:
 
     def scalars_dict(self):
         from ._lib import SCALARS
+        if self._scalars_published:             # wait for the published copy only (see _publish_scalars)
+            self._scalars_event.synchronize()
+            vals = self._scalars_host.tolist()
+            return {n: vals[i] for i, n in enumerate(SCALARS)}
         self.join_comm()
         vals = self.scalars.detach().cpu().tolist()
         return {n: vals[i] for i, n in enumerate(SCALARS)}

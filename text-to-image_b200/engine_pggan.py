@@ -458,9 +458,8 @@ class PgganEngine(Engine):
             cs("d_y0", "rgb0")
 
     # ------------------------------------------------------------------ the D run
-    def _d_tail(self):
+    def _d_tail_scalars(self):
         self.K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, 0.0)     # kt stays 1 (:94-108)
-        self._adam("d")                                                                     # :111,119
 
     def _d_body(self):
         K, d, B = self.K, self.d, self.B
