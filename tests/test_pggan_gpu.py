@@ -31,7 +31,7 @@ def build(o, precision, root, params=None, steps=100, use_graphs=True):
     prev = o.stage - 1 if o.trans else o.stage
     m = PGGAN(o.batch_size, steps, os.path.join(root, "stage%d" % o.stage), os.path.join(root, "stage%d" % prev), data,
               os.path.join(root, "s"), os.path.join(root, "l"), o.stage, o.trans, precision=precision, nf_base=o.nf_base,
-              nf_cap=o.nf_cap, z_dim=o.z_dim, embed_dim=o.embed_dim, compr_embed_dim=o.compr_embed_dim, sample_num=4,
+              nf_cap=o.nf_cap, z_dim=o.z_dim, embed_dim=o.embed_dim, compr_embed_dim=o.compr_embed_dim, sample_num=4, d_embed=o.d_embed,
               use_graphs=use_graphs)
     if params is not None:
         m.set_variables(params)
@@ -82,10 +82,12 @@ def test_tiny_iteration_against_oracle(stage, trans, tmp_path):
 
 
 @pytest.mark.parametrize("stage,trans,batch,precision,ftol", [(5, True, 4, "bf16x3", 1e-3), (5, True, 4, "bf16", 5e-2),
-                                                             (7, False, 2, "bf16x3", 1e-3)])
+                                                             (7, False, 2, "bf16x3", 1e-3),
+                                                             (8, True, 2, "bf16x3", 1e-3)])
 def test_reference_width_forward_parity(stage, trans, batch, precision, ftol, tmp_path):
-    """the reference's channel schedule (get_nf / get_dnf, pggan.py:339-343) at 64x64 (fade-in) and 256x256: G and D
-    forward against the oracle."""
+    """the reference's channel schedule (get_nf / get_dnf, pggan.py:339-343) at 64x64 (fade-in), 256x256 and the last
+    entry of the schedule, 512x512 during fade-in (16 / 32 channels at full resolution): G and D forward against the
+    oracle."""
     ocfg = P.PgganCfg(batch_size=batch, stage=stage, trans=trans)
     p = P.init_params(ocfg, 0, torch.float32)
     f = P.make_feed(ocfg, 7, torch.float32)

@@ -48,7 +48,7 @@ class PGGAN(object):
     # build model
     def __init__(self, batch_size, steps, check_dir_write, check_dir_read, dataset, sample_path, log_dir, stage, trans,
                  build_model=True, precision="bf16", device=None, kernels=None, distributed=None, use_graphs=True,
-                 nf_base=1024, nf_cap=512, z_dim=128, embed_dim=1024, compr_embed_dim=128, sample_num=64):
+                 nf_base=1024, nf_cap=512, z_dim=128, embed_dim=1024, compr_embed_dim=128, sample_num=64, d_embed=128):
         """The first ten arguments are the reference's (pggan.py:15-16).  precision / device / kernels / distributed /
         use_graphs as for WGanCls; the remaining keywords default to the reference's literals (:28-38, :339-343)."""
         self.batch_size = batch_size
@@ -72,7 +72,7 @@ class PGGAN(object):
         self.output_size = 4 * pow(2, stage - 1)
 
         self.alpha_tra = 0.0
-        self._nf_base, self._nf_cap = nf_base, nf_cap
+        self._nf_base, self._nf_cap, self._d_embed = nf_base, nf_cap, d_embed      # d_embed: the literal 128 of pggan.py:271
         self.precision = precision
         self._np = {"bf16": 1, "bf16x3": 2}[precision]
         if kernels is None:
@@ -105,7 +105,7 @@ class PGGAN(object):
             base = next(iter(self._engines.values()), None)
             self._engines[batch] = PgganEngine(
                 self._K, self.device, batch, self._np, self.stage, self.trans, self.z_dim, self.embed_dim,
-                self.compr_embed_dim, self._nf_base, self._nf_cap, 128, 9, self._world, self._allreduce,
+                self.compr_embed_dim, self._nf_base, self._nf_cap, self._d_embed, 9, self._world, self._allreduce,
                 share_from=base, use_graphs=self._use_graphs)
         return self._engines[batch]
 
