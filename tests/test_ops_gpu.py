@@ -84,3 +84,53 @@ def test_generator_side_ops():
     zi = ops.batch_norm(y, train=False, act=ops.relu, name="BatchNorm", df=ops.NCHW) if False else None
     xn = ops.to_nhwc(x)
     assert xn.shape == (6, 8, 8, 16) and torch.equal(ops.to_nchw(xn), x)
+
+
+def test_pggan_side_ops():
+    """layer_norm / pool / upscale / the 2x2 and 4x4 stride-1 SAME convs (utils/ops.py:58-63,74-81,100-111) against the
+    PGGAN oracle's restatement; TF default variable names (LayerNorm, LayerNorm_1)."""
+    from oracle import pggan_oracle as P
+    from t2i_b200.utils import ops
+    ops.reset_variables(seed=3)
+    g = torch.Generator().manual_seed(2)
+    x = torch.randn(3, 8, 8, 16, generator=g).cuda()
+    with ops.variable_scope("g_net"):
+        with ops.variable_scope("conv_stage_1"):
+            u = ops.upscale(x, 2)
+            c = ops.conv2d(u, 24, ks=(3, 3), s=(1, 1))
+            y = ops.layer_norm(c, act=ops.relu)
+            f = ops.layer_norm(ops.fc(torch.randn(3, 40, generator=g).cuda(), 64))
+        with ops.variable_scope("rgb_stage_1"):
+            r = ops.conv2d(ops.conv2d(y, 9, ks=(2, 2), s=(1, 1), act=ops.relu), 3, ks=(1, 1), s=(1, 1))
+        k4 = ops.conv2d(y, 8, ks=(4, 4), s=(1, 1))
+        v = ops.conv2d(torch.randn(3, 4, 4, 16, generator=g).cuda(), 8, ks=(4, 4), s=(1, 1), padding='VALID')
+    names = list(ops.global_variables("g_net/conv_stage_1/"))
+    assert names == ["g_net/conv_stage_1/Conv/weights", "g_net/conv_stage_1/Conv/biases", "g_net/conv_stage_1/LayerNorm/beta",
+                     "g_net/conv_stage_1/LayerNorm/gamma", "g_net/conv_stage_1/dense/kernel", "g_net/conv_stage_1/dense/bias",
+                     "g_net/conv_stage_1/LayerNorm_1/beta", "g_net/conv_stage_1/LayerNorm_1/gamma"]
+    gv = ops.global_variables()
+    gv["g_net/conv_stage_1/LayerNorm/gamma"].uniform_(0.5, 1.5)
+    gv["g_net/conv_stage_1/LayerNorm/beta"].normal_()
+    y = None
+    with ops.variable_scope("g_net", reuse=True):
+        with ops.variable_scope("conv_stage_1", reuse=True):
+            y = ops.layer_norm(c, act=ops.relu)
+    p = {k: t.cpu().double() for k, t in gv.items()}
+    xo = x.cpu().double()
+    uo = P.upscale(xo)
+    co = P.conv2d(p, "g_net/conv_stage_1/Conv", uo, 3)
+    yo = P.layer_norm(p, "g_net/conv_stage_1/LayerNorm", co, torch.relu)
+    assert u.shape == (3, 16, 16, 16) and rel(u, uo) < 1e-4 and rel(c, co) < 1e-4 and rel(y, yo) < 1e-4
+    assert f.shape == (3, 64) and float(f.mean(1).abs().max()) < 1e-3
+    with ops.variable_scope("g_net", reuse=True):
+        with ops.variable_scope("rgb_stage_1", reuse=True):
+            r = ops.conv2d(ops.conv2d(y, 9, ks=(2, 2), s=(1, 1), act=ops.relu), 3, ks=(1, 1), s=(1, 1))
+    ro = P.conv2d(p, "g_net/rgb_stage_1/Conv_1", P.conv2d(p, "g_net/rgb_stage_1/Conv", yo, 2, act=torch.relu), 1)
+    assert r.shape == (3, 16, 16, 3) and rel(r, ro) < 1e-3       # the 2x2 SAME conv pads bottom / right (TF)
+    yb = ops.pool(y)
+    assert yb.shape == (3, 8, 8, 24) and rel(yb, P.pool(yo)) < 1e-4
+    assert k4.shape == (3, 16, 16, 8) and v.shape == (3, 1, 1, 8)
+    with pytest.raises(ValueError):
+        ops.pool(y, 3)
+    with pytest.raises(ValueError):
+        ops.layer_norm(torch.randn(2, 4, 4, 12).cuda())

@@ -1,6 +1,7 @@
-"""The op wrappers of the reference's ``utils/ops.py`` (subset on the wgancls path: conv2d :58-63,
-conv2d_transpose :66-71, batch_norm :7-29, fc :84-87, to_nchw/to_nhwc :129-134, lrelu_act :90-91)
-with the same names, arguments and defaults, executed eagerly by the CUDA library.
+"""The op wrappers of the reference's ``utils/ops.py`` (conv2d :58-63, conv2d_transpose :66-71, batch_norm :7-29,
+fc :84-87, to_nchw/to_nhwc :129-134, lrelu_act :90-91 of the wgancls / StackGAN paths; layer_norm :74-81, pool :100-101,
+resize_nearest_neighbor / upscale :104-111 of the PGGAN path) with the same names, arguments and defaults, executed
+eagerly by the CUDA library.
 
 Like the TF originals each wrapper owns its variables: they are created on first use under the
 current ``variable_scope`` with TF's default names (``Conv``, ``Conv_1``, ``Conv2d_transpose``,
@@ -10,8 +11,9 @@ Inputs/outputs are fp32 CUDA tensors in the requested data format.  The fused tr
 (``t2i_b200.engine``) does not go through this module; it exists so that code written against the
 reference's op surface (the other models' graphs) keeps working on the same kernels.
 
-Supported geometries (everything the path uses): k1/k3 stride 1 SAME (k1 also VALID), k4 stride 2 SAME,
-k4 stride 4 VALID on a 4x4 input, transposed k4 stride 2 SAME.  Other shapes raise ValueError, as TF
+Supported geometries (everything the paths use): k1/k2/k3/k4 stride 1 SAME (TF's asymmetric padding for even k; k1
+also VALID), k4 stride 2 SAME, k4 VALID on a 4x4 input (stride 4 or 1: one output pixel), transposed k4 stride 2 SAME,
+2x2 average pool, 2x nearest-neighbour upscale.  Other shapes raise ValueError, as TF
 raises on invalid arguments; channel counts that are not multiples of 8 are zero-padded internally.
 """
 import contextlib
@@ -211,14 +213,14 @@ def conv2d(x, f, ks=(4, 4), s=(2, 2), padding='SAME', act=None, init=None, name=
     if ks[0] != ks[1] or s[0] != s[1]:
         raise ValueError("only square kernels and strides are supported")
     k, st = ks[0], s[0]
-    if k == 4 and st == 4 and pad == 'VALID' and h == 4 and w == 4:
+    if k == 4 and st in (1, 4) and pad == 'VALID' and h == 4 and w == 4:
         # model.py:160: one dot product per sample and output channel (GEMM with H = W = 1 over the 16*Cin patch)
         xp = _planes_from(xn.reshape(n, 1, 1, 16 * cin))
         wk = _pack(wv.reshape(16 * cin, f).t().reshape(1, f, 16 * cin))
         y = torch.empty(PRECISION_PLANES, n, 1, 1, _pad8(f), device=x.device, dtype=torch.bfloat16)
         K.conv_gemm(K.CONV_S1, 1, 0, K.View(xp), wk, K.View(y), bias=_bias8(bv, f), act=fused)
     else:
-        if k in (1, 3) and st == 1 and (pad == 'SAME' or k == 1):
+        if k in (1, 2, 3, 4) and st == 1 and (pad == 'SAME' or k == 1):
             mode, oh, ow = K.CONV_S1, h, w
         elif (k, st) == (4, 2) and pad == 'SAME':
             mode, oh, ow = K.CONV_K4S2, h // 2, w // 2
@@ -308,3 +310,64 @@ def run_update_ops():
     for mm, mv, mean, var, rows, decay in _S.update_ops:
         K.bn_update_moving(mm, mv, mean.contiguous(), var.contiguous(), rows, decay)
     _S.update_ops.clear()
+
+
+def layer_norm(x, act=None, scope=None, df=NHWC):
+    """tf.contrib.layers.layer_norm(begin_norm_axis=1, begin_params_axis=-1 / 1) (utils/ops.py:74-81): statistics per
+    sample over all non-batch axes (epsilon 1e-12), gamma / beta per channel (rank 2: per feature)."""
+    if df not in (NHWC, NCHW):
+        raise ValueError('Invalid data format %s' % df)
+    rank2 = x.dim() == 2
+    xn = x.reshape(x.shape[0], 1, 1, x.shape[1]) if rank2 else _in_nhwc(x, df)
+    n, c = xn.shape[0], xn.shape[-1]
+    if c % 8 != 0:
+        raise ValueError("layer_norm: the channel count must be a multiple of 8 (zero padding would change the statistics)")
+    full = _layer_scope("LayerNorm", scope)
+    beta = _get_variable(full + "/beta", (c,), "zeros", x.device)
+    gamma = _get_variable(full + "/gamma", (c,), "ones", x.device)
+    xp = _planes_from(xn)
+    sums = torch.zeros(n, 2, device=x.device)
+    K.ln_stats(xp, sums)
+    fused, post = _fused(act)
+    y = torch.empty_like(xp)
+    K.ln_apply(xp, sums, 1e-12, gamma, beta, y, fused == K.ACT_RELU)
+    out = _planes_to(y, c)
+    if fused == K.ACT_LRELU:
+        out = torch.maximum(out, 0.2 * out)
+    if post is not None:
+        out = post(out)
+    return out.reshape(x.shape[0], c) if rank2 else _out_df(out, df)
+
+
+def pool(x, s=2, p_type='AVG', df=NHWC):
+    """tf.nn.pool(window [s, s], strides [s, s], SAME) (utils/ops.py:100-101); AVG with s = 2 on even extents."""
+    xn = _in_nhwc(x, df)
+    n, h, w, c = xn.shape
+    if s != 2 or p_type != 'AVG' or (h & 1) or (w & 1):
+        raise ValueError("pool: only the 2x2 average pool on even extents is supported")
+    xp = _planes_from(xn)
+    y = torch.empty(PRECISION_PLANES, n, h // 2, w // 2, xp.shape[-1], device=x.device, dtype=torch.bfloat16)
+    K.pool2x(xp, y, 0.25)
+    return _out_df(_planes_to(y, c), df)
+
+
+def resize_nearest_neighbor(x, new_size):
+    """tf.image.resize_nearest_neighbor (utils/ops.py:104-106), NHWC; the 2x case."""
+    n, h, w, c = x.shape
+    if tuple(new_size) != (2 * h, 2 * w):
+        raise ValueError("resize_nearest_neighbor: only the 2x upscale is supported")
+    xp = _planes_from(x)
+    y = torch.empty(PRECISION_PLANES, n, 2 * h, 2 * w, xp.shape[-1], device=x.device, dtype=torch.bfloat16)
+    K.upscale2x(xp, y, 1.0)
+    return _planes_to(y, c).contiguous()
+
+
+def upscale(x, s=2):
+    """utils/ops.py:109-111"""
+    _, h, w, _ = get_conv_shape(x)
+    return resize_nearest_neighbor(x, (h * s, w * s))
+
+
+def get_conv_shape(tensor):
+    """utils/ops.py:119-126"""
+    return [int(d) for d in tensor.shape]
