@@ -241,7 +241,7 @@ def test_graph_replay_and_side_stream_match_eager_schedule():
     v0 = m.get_variables()
     runs = [one_iteration(m, v0) for _ in range(3)]
     eng = m._train_engine()
-    assert all(eng._graphs[k]["graph"] is not None for k in ("d_a", "d_b", "g_a1", "g_a2", "g_b"))
+    assert all(eng._graphs[k]["graph"] is not None for k in ("d_a", "d_b", "d_c", "g_a1", "g_a2", "g_b", "g_c"))
     assert eng.replayed_launches > 0 and eng.side_stream is not None
     plain = WGanCls(cfg_for(ocfg), precision="bf16x3", use_graphs=False)
     plain._train_engine().side_stream = None

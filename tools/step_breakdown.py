@@ -33,10 +33,10 @@ def main():
         eng.d_step(1e-4)
         eng.g_step(1e-4)
     torch.cuda.synchronize()
-    flops = {"d_a1": 2 * G_F * B, "d_a": 2 * 13 * D_F * B, "d_b": 0.0, "g_a1": 2 * G_F * B, "g_a2": 2 * (2 * G_F + 2 * D_F) * B,
-             "g_b": 0.0}
+    flops = {"d_a1": 2 * G_F * B, "d_a": 2 * 13 * D_F * B, "d_b": 0.0, "d_c": 0.0, "g_a1": 2 * G_F * B,
+             "g_a2": 2 * (2 * G_F + 2 * D_F) * B, "g_b": 0.0, "g_c": 0.0}
     total = 0.0
-    for name in ("d_a1", "d_a", "d_b", "g_a1", "g_a2", "g_b"):
+    for name in ("d_a1", "d_a", "d_b", "d_c", "g_a1", "g_a2", "g_b", "g_c"):      # d_b / g_b: loss scalars, d_c / g_c: Adam
         graph = eng._graphs[name]["graph"]
         ts = []
         for _ in range(args.reps):
@@ -51,7 +51,7 @@ def main():
         total += med
         print("%-5s %7.3f ms  launches %3d  %s" % (name, med, eng._graphs[name]["launches"],
                                                   "%.0f TFLOP/s" % (flops[name] / med / 1e9) if flops[name] else ""))
-    print("sum of graphs %.3f ms (serial; the step overlaps d_b with g_a1)" % total)
+    print("sum of graphs %.3f ms (serial; the step overlaps d_b / d_c with g_a1)" % total)
 
     def timed(label, body):
         body()
