@@ -212,3 +212,58 @@ def test_trainer_two_checkpoint_restore(tmp_path):
     samples = s2.run(s2.sampler, feed_dict={s2.z_sample: np.random.normal(0, 1, (2, cfg.z_dim)),
                                            s2.embed_sample: np.random.normal(0, 1, (2, cfg.embed_dim))})
     assert samples.shape == (2, 256, 256, 3) and float(np.abs(samples).max()) <= 1.0
+
+
+def test_oracle_k4s1_same_padding_against_naive_loops():
+    """TF SAME for a 4x4 stride-1 conv: pad_total = 3 -> 1 before, 2 after (models/stackgan/stageII/model.py:102,105,
+    151,154 via utils/ops.py:58-63).  The oracle's conv2d against explicit loops, and the self-added residual branch
+    (model.py:117) against its literal reading."""
+    from oracle import wgancls_oracle as W
+    g = torch.Generator().manual_seed(4)
+    x = torch.randn(2, 3, 5, 6, generator=g, dtype=torch.float64)          # NCHW
+    p = {"c/weights": torch.randn(4, 4, 3, 2, generator=g, dtype=torch.float64),
+         "c/biases": torch.randn(2, generator=g, dtype=torch.float64)}
+    y = W.conv2d(p, "c", x, 4, 1)
+    assert y.shape == (2, 2, 5, 6)
+    xp = torch.zeros(2, 3, 5 + 3, 6 + 3, dtype=torch.float64)
+    xp[:, :, 1:6, 1:7] = x
+    for n in range(2):
+        for i in range(5):
+            for j in range(6):
+                ref = p["c/biases"].clone()
+                for kh in range(4):
+                    for kw in range(4):
+                        ref = ref + xp[n, :, i + kh, j + kw] @ p["c/weights"][kh, kw]
+                assert torch.allclose(y[n, :, i, j], ref, atol=1e-12)
+    # lrelu(net + net): doubling the BatchNorm output equals doubling gamma and beta
+    cfg = S2.Stage2Cfg(**TINY)
+    q = boosted_params(cfg)
+    f = S2.make_feed(cfg, 3, torch.float64)
+    a = S2.discriminator(q, f["x"], f["cond"], cfg)
+    q2 = dict(q)
+    q2[S2.D2 + "BatchNorm_9/gamma"] = 2 * q[S2.D2 + "BatchNorm_9/gamma"]
+    q2[S2.D2 + "BatchNorm_9/beta"] = 2 * q[S2.D2 + "BatchNorm_9/beta"]
+
+    def single(pp, x_nhwc, embed):     # the same graph with h8 = lrelu(n) instead of lrelu(n + n)
+        import torch.nn.functional as F
+        from oracle.wgancls_oracle import batch_norm, conv2d, fc, lrelu
+        d, bnk = S2.D2, dict(train=True, new_moving=None)
+        h = conv2d(pp, d + "Conv", x_nhwc.permute(0, 3, 1, 2), 4, 2, act=lrelu)
+        for i in range(5):
+            h = batch_norm(pp, d + ("BatchNorm" if i == 0 else "BatchNorm_%d" % i), conv2d(pp, d + "Conv_%d" % (1 + i), h, 4, 2),
+                           act=lrelu, **bnk)
+        h = batch_norm(pp, d + "BatchNorm_5", conv2d(pp, d + "Conv_6", h, 4, 1), act=lrelu, **bnk)
+        h7 = batch_norm(pp, d + "BatchNorm_6", conv2d(pp, d + "Conv_7", h, 4, 1), **bnk)
+        n_ = batch_norm(pp, d + "BatchNorm_7", conv2d(pp, d + "Conv_8", h7, 1, 1), act=lrelu, **bnk)
+        n_ = batch_norm(pp, d + "BatchNorm_8", conv2d(pp, d + "Conv_9", n_, 3, 1), act=lrelu, **bnk)
+        n_ = batch_norm(pp, d + "BatchNorm_9", conv2d(pp, d + "Conv_10", n_, 3, 1), **bnk)
+        h8 = lrelu(n_)
+        e = fc(pp, d + "dense", embed, lrelu)
+        s = h8.shape[-1]
+        h9 = batch_norm(pp, d + "BatchNorm_10", conv2d(pp, d + "Conv_11", torch.cat([h8, e[:, :, None, None].expand(-1, -1, s, s)], 1),
+                                                       1, 1), act=lrelu, **bnk)
+        w = pp[d + "Conv_12/weights"].permute(3, 2, 0, 1)
+        return F.conv2d(h9, w, pp[d + "Conv_12/biases"], stride=cfg.output_size // 64).permute(0, 2, 3, 1)
+
+    b = single(q2, f["x"], f["cond"])
+    assert rel(a, b) < 1e-12
