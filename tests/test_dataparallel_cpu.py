@@ -325,3 +325,57 @@ def test_two_rank_stage2_iteration(tmp_path):
     r = torch.load(out)
     assert r["calls"] == [r["d_n"], r["g_n"]], r        # exactly one all-reduce per optimizer step
     assert r["same"] and r["finite"] and r["frozen"], r
+
+
+def _worker_pggan_mirror(rank, world, port, out):
+    """the reference-facing PGGAN object with distributed=True (gloo): every rank feeds its shard through run();
+    the fetched losses are those of the GLOBAL batch and the replicas end up identical"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import pggan_oracle as P
+    from t2i_b200.models.pggan.pggan import PGGAN
+    from test_pggan_cpu import TINY, boosted_params
+    torch.set_num_threads(1)
+    cfg = P.PgganCfg(stage=2, trans=True, **dict(TINY, batch_size=4))
+    gb, b = cfg.batch_size, cfg.batch_size // world
+    p = boosted_params(cfg)
+    feed = P.make_feed(cfg, 12, torch.float64)
+    kw = dict(precision="bf16x3", device="cpu", kernels=fk, use_graphs=False, nf_base=cfg.nf_base, nf_cap=cfg.nf_cap,
+              z_dim=cfg.z_dim, embed_dim=cfg.embed_dim, compr_embed_dim=cfg.compr_embed_dim, sample_num=2, d_embed=cfg.d_embed)
+    m = PGGAN(b, 10, "/tmp/w", "/tmp/r", None, "/tmp/s", "/tmp/l", 2, True, distributed=True, **kw)
+    m.set_variables(p)
+    sl = slice(rank * b, (rank + 1) * b)
+
+    def fd(model, sel, noise):
+        return {model.x: feed["x"][sel].float(), model.x_mismatch: feed["x_mismatch"][sel].float(),
+                model.cond: feed["cond"][sel].float(), model.z: feed["z"][sel].float(),
+                model.epsilon: feed["epsilon"][sel].float(), model.cond_noise: feed[noise][sel].float(), model.iter: 4}
+    _, d_loss, gp = m.run([m.D_optim, m.D_loss, m.real_gp], fd(m, sl, "tn_eps"))
+    _, g_loss = m.run([m.G_optim, m.G_loss], fd(m, sl, "tn_eps_g"))
+    eng = m._train_engine()
+    flat = torch.cat([eng.flat["d"], eng.flat["g"]])
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    res = {"same": all(torch.equal(gathered[0], t) for t in gathered), "d_loss": d_loss, "g_loss": g_loss, "gp": gp,
+           "alpha": m.alpha_tra}
+    if rank == 0:
+        ref = PGGAN(gb, 10, "/tmp/w", "/tmp/r", None, "/tmp/s", "/tmp/l", 2, True, **kw)
+        ref.set_variables(p)
+        _, res["d_ref"], res["gp_ref"] = ref.run([ref.D_optim, ref.D_loss, ref.real_gp], fd(ref, slice(None), "tn_eps"))
+        _, res["g_ref"] = ref.run([ref.G_optim, ref.G_loss], fd(ref, slice(None), "tn_eps_g"))
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_pggan_mirror_fetches_global_losses(tmp_path):
+    out = str(tmp_path / "pm.pt")
+    port = 39500 + os.getpid() % 2000
+    mp.spawn(_worker_pggan_mirror, args=(2, port, out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["same"] and abs(r["alpha"] - 0.4) < 1e-12, r
+    for a, b in (("d_loss", "d_ref"), ("gp", "gp_ref"), ("g_loss", "g_ref")):       # split-bf16 rounding only
+        assert abs(r[a] - r[b]) < 2e-3 * max(1.0, abs(r[b])), (a, r[a], r[b])
