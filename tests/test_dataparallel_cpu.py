@@ -14,6 +14,14 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(HERE)
 
 
+def _free_port():
+    """a TCP port that is free right now (a fixed pid-derived port can still be in TIME_WAIT from an earlier run)"""
+    import socket
+    with socket.socket(socket.AF_INET, socket.SOCK_STREAM) as sk:
+        sk.bind(("127.0.0.1", 0))
+        return sk.getsockname()[1]
+
+
 def _worker(rank, world, port, out):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
@@ -132,7 +140,7 @@ def test_two_rank_sync_bn_iteration_equals_single_process(tmp_path):
     """with synchronised BatchNorm sums the sharded iteration IS the reference's whole-batch
     iteration (exact storage, so any difference is a logic error)."""
     out = str(tmp_path / "s.pt")
-    port = 31500 + os.getpid() % 2000
+    port = _free_port()
     mp.spawn(_worker_sync_bn, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["img"] < 1e-10, r
@@ -189,7 +197,7 @@ def _worker_stage1(rank, world, port, out):
 
 def test_two_rank_stage1_iteration(tmp_path):
     out = str(tmp_path / "s1.pt")
-    port = 33500 + os.getpid() % 2000
+    port = _free_port()
     mp.spawn(_worker_stage1, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["calls"] == [r["d_n"], r["g_n"]], r        # exactly one all-reduce per optimizer step
@@ -198,7 +206,7 @@ def test_two_rank_stage1_iteration(tmp_path):
 
 def test_two_rank_d_run_equals_single_process(tmp_path):
     out = str(tmp_path / "r.pt")
-    port = 29500 + os.getpid() % 2000
+    port = _free_port()
     mp.spawn(_worker, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["worst"] < 1e-9, r
@@ -264,7 +272,7 @@ def _worker_pggan(rank, world, port, out):
 
 def test_two_rank_pggan_iteration_equals_single_process(tmp_path):
     out = str(tmp_path / "p.pt")
-    port = 35500 + os.getpid() % 2000
+    port = _free_port()
     mp.spawn(_worker_pggan, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["gp"] > 1e-3, r                                # the penalty (and its second-order term) is active
@@ -320,7 +328,7 @@ def _worker_stage2(rank, world, port, out):
 
 def test_two_rank_stage2_iteration(tmp_path):
     out = str(tmp_path / "s2.pt")
-    port = 37500 + os.getpid() % 2000
+    port = _free_port()
     mp.spawn(_worker_stage2, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["calls"] == [r["d_n"], r["g_n"]], r        # exactly one all-reduce per optimizer step
@@ -373,7 +381,7 @@ def _worker_pggan_mirror(rank, world, port, out):
 
 def test_two_rank_pggan_mirror_fetches_global_losses(tmp_path):
     out = str(tmp_path / "pm.pt")
-    port = 39500 + os.getpid() % 2000
+    port = _free_port()
     mp.spawn(_worker_pggan_mirror, args=(2, port, out), nprocs=2, join=True)
     r = torch.load(out)
     assert r["same"] and abs(r["alpha"] - 0.4) < 1e-12, r
