@@ -56,26 +56,26 @@ def test_deconv_matches_naive_and_is_conv_transpose():
 def test_batch_norm_train_and_moving():
     g = torch.Generator().manual_seed(3)
     x = torch.randn(6, 5, 3, 3, generator=g, dtype=torch.float64) * 2 + 1
-    p = {"b/gamma": torch.rand(5, dtype=torch.float64) + .5, "b/beta": torch.randn(5, dtype=torch.float64),
+    p = {"b/gamma": torch.rand(5, generator=g, dtype=torch.float64) + .5, "b/beta": torch.randn(5, generator=g, dtype=torch.float64),
          "b/moving_mean": torch.zeros(5, dtype=torch.float64), "b/moving_variance": torch.ones(5, dtype=torch.float64)}
     nm = {}
     y = O.batch_norm(p, "b", x, True, new_moving=nm)
     xm = x.permute(1, 0, 2, 3).reshape(5, -1)
     mean, var = xm.mean(1), ((xm - xm.mean(1, keepdim=True)) ** 2).mean(1)
     ref = ((xm - mean[:, None]) / torch.sqrt(var[:, None] + 1e-5)) * p["b/gamma"][:, None] + p["b/beta"][:, None]
-    np.testing.assert_allclose(y.permute(1, 0, 2, 3).reshape(5, -1).numpy(), ref.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(y.permute(1, 0, 2, 3).reshape(5, -1).numpy(), ref.numpy(), rtol=1e-12, atol=1e-12)
     n = xm.shape[1]
-    np.testing.assert_allclose(nm["b/moving_mean"].numpy(), (0.1 * mean).numpy(), rtol=1e-12)
-    np.testing.assert_allclose(nm["b/moving_variance"].numpy(), (0.9 + 0.1 * var * n / (n - 1)).numpy(), rtol=1e-12)
+    np.testing.assert_allclose(nm["b/moving_mean"].numpy(), (0.1 * mean).numpy(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(nm["b/moving_variance"].numpy(), (0.9 + 0.1 * var * n / (n - 1)).numpy(), rtol=1e-12, atol=1e-12)
     # rank-2: per feature over the batch (generator fc0, model.py:176)
     x2 = torch.randn(7, 5, generator=g, dtype=torch.float64)
     y2 = O.batch_norm(p, "b", x2, True)
     ref2 = (x2 - x2.mean(0)) / torch.sqrt(x2.var(0, unbiased=False) + 1e-5) * p["b/gamma"] + p["b/beta"]
-    np.testing.assert_allclose(y2.numpy(), ref2.numpy(), rtol=1e-12)
+    np.testing.assert_allclose(y2.numpy(), ref2.numpy(), rtol=1e-12, atol=1e-12)
     # inference uses the moving statistics
     y3 = O.batch_norm(p, "b", x, False)
     np.testing.assert_allclose(y3.numpy(), (x / math.sqrt(1 + 1e-5) * p["b/gamma"].view(1, -1, 1, 1)
-                                            + p["b/beta"].view(1, -1, 1, 1)).numpy(), rtol=1e-12)
+                                            + p["b/beta"].view(1, -1, 1, 1)).numpy(), rtol=1e-12, atol=1e-12)
 
 
 def test_adam_tf_closed_form():
