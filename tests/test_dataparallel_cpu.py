@@ -387,3 +387,128 @@ def test_two_rank_pggan_mirror_fetches_global_losses(tmp_path):
     assert r["same"] and abs(r["alpha"] - 0.4) < 1e-12, r
     for a, b in (("d_loss", "d_ref"), ("gp", "gp_ref"), ("g_loss", "g_ref")):       # split-bf16 rounding only
         assert abs(r[a] - r[b]) < 2e-3 * max(1.0, abs(r[b])), (a, r[a], r[b])
+
+
+def _worker_stage1_sync_bn(rank, world, port, out):
+    """StackGAN stage-I with sync_bn=True on 2 ranks == the single-process iteration on the global batch: d_net has a
+    BatchNorm after almost every conv (models/stackgan/stageI/model.py:81-112), so the equivalence needs the
+    per-call statistics and the backward reductions of BOTH networks summed over the ranks"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import stackgan1_oracle as S
+    from t2i_b200.engine_stage1 import StageIEngine
+    from test_stackgan1_cpu import TINY, boosted_params, _bias_before_bn
+    torch.set_num_threads(1)
+    cfg = S.Stage1Cfg(**TINY)
+    gb, b = cfg.batch_size, cfg.batch_size // world
+    p = boosted_params(cfg)
+    feed = S.make_feed(cfg, 21, torch.float64)
+    calls = []
+
+    def allreduce(t):
+        calls.append(t.numel())
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    exact = dict(act_dtype=torch.float64, f32_dtype=torch.float64)
+    args = (cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim, cfg.d_beta1, cfg.g_beta1,
+            cfg.alpha_mismatch, cfg.kl_coeff)
+    eng = StageIEngine(fk, "cpu", b, 1, *args, world, allreduce, sync_bn=True, **exact)
+    ref = StageIEngine(fk, "cpu", gb, 1, *args, **exact)
+    sl = slice(rank * b, (rank + 1) * b)
+    res = {}
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.set_params_tf(p)
+        e.load_feed(x=feed["x"][sel], x_mismatch=feed["x_mismatch"][sel], cond=feed["cond"][sel], z=feed["z"][sel],
+                    tn_eps=feed["tn_eps"][sel])
+        e.d_step(cfg.lr)
+    res["img"] = float((eng.d["img"][:b] - ref.d["img"][:gb][sl]).abs().max())
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    ok = lambda n: float(gf[n].abs().max()) > 1e-12 and not _bias_before_bn(n)
+    res["d_grads"] = max((float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)), n) for n in gf
+                         if n.startswith("d_net/") and ok(n))
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.load_feed(tn_eps=feed["tn_eps_g"][sel])
+        e.g_step(cfg.lr)
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    res["g_grads"] = max((float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)), n) for n in gf
+                         if n.startswith("g_net/") and ok(n))
+    sc, scr = eng.scalars_dict(), ref.scalars_dict()
+    res["scalars"] = max(abs(sc[k] - scr[k]) / max(1.0, abs(scr[k])) for k in sc)
+    ps, pf = eng.get_params_tf(), ref.get_params_tf()
+    res["moving"] = max(float((ps[n] - pf[n]).abs().max()) for n in pf if "moving" in n)
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_stage1_sync_bn_iteration_equals_single_process(tmp_path):
+    out = str(tmp_path / "s1s.pt")
+    mp.spawn(_worker_stage1_sync_bn, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["img"] < 1e-10 and r["d_grads"][0] < 1e-8 and r["g_grads"][0] < 1e-7, r
+    assert r["scalars"] < 1e-9 and r["moving"] < 1e-10, r
+
+
+def _worker_stage2_sync_bn(rank, world, port, out):
+    """StackGAN stage-II with sync_bn=True on 2 ranks == the single-process iteration on the global batch (the frozen
+    stage-I generator, stageII_g_net and stageII_d_net all normalise with whole-batch statistics)"""
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, HERE)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    import fake_kernels as fk
+    from oracle import stackgan2_oracle as S2
+    from t2i_b200.engine_stage2 import StageIIEngine
+    from test_stackgan2_cpu import TINY, boosted_params, _bias_before_bn
+    torch.set_num_threads(1)
+    cfg = S2.Stage2Cfg(**dict(TINY, batch_size=4))
+    gb, b = cfg.batch_size, cfg.batch_size // world
+    p = boosted_params(cfg)
+    feed = S2.make_feed(cfg, 21, torch.float64)
+
+    def allreduce(t):
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+
+    exact = dict(act_dtype=torch.float64, f32_dtype=torch.float64)
+    args = (cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim, cfg.d_beta1, cfg.g_beta1,
+            cfg.alpha_mismatch, cfg.kl_coeff)
+    eng = StageIIEngine(fk, "cpu", b, 1, *args, world, allreduce, s1_gf=cfg.s1_gf_dim, sync_bn=True, **exact)
+    ref = StageIIEngine(fk, "cpu", gb, 1, *args, s1_gf=cfg.s1_gf_dim, **exact)
+    sl = slice(rank * b, (rank + 1) * b)
+    res = {}
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.set_params_tf(p)
+        e.load_feed(x=feed["x"][sel], x_mismatch=feed["x_mismatch"][sel], cond=feed["cond"][sel], z=feed["z"][sel],
+                    tn_eps=feed["tn_eps"][sel], tn_s1=feed["tn_s1"][sel])
+        e.d_step(cfg.lr)
+    res["img"] = float((eng.d["img"][:b] - ref.d["img"][:gb][sl]).abs().max())
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    ok = lambda n: float(gf[n].abs().max()) > 1e-12 and not _bias_before_bn(n)
+    res["d_grads"] = max((float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)), n) for n in gf
+                         if n.startswith(S2.D2) and ok(n))
+    for e, sel in ((eng, sl), (ref, slice(None))):
+        e.load_feed(tn_eps=feed["tn_eps_g"][sel], tn_s1=feed["tn_s1_g"][sel])
+        e.g_step(cfg.lr)
+    gs, gf = eng.get_grads_tf(), ref.get_grads_tf()
+    res["g_grads"] = max((float((gs[n] - gf[n]).abs().max() / (gf[n].abs().max() + 1e-30)), n) for n in gf
+                         if n.startswith(S2.G2) and ok(n))
+    sc, scr = eng.scalars_dict(), ref.scalars_dict()
+    res["scalars"] = max(abs(sc[k] - scr[k]) / max(1.0, abs(scr[k])) for k in sc)
+    ps, pf = eng.get_params_tf(), ref.get_params_tf()
+    res["moving"] = max(float((ps[n] - pf[n]).abs().max()) for n in pf if "moving" in n)
+    if rank == 0:
+        torch.save(res, out)
+    dist.destroy_process_group()
+
+
+def test_two_rank_stage2_sync_bn_iteration_equals_single_process(tmp_path):
+    out = str(tmp_path / "s2s.pt")
+    mp.spawn(_worker_stage2_sync_bn, args=(2, _free_port(), out), nprocs=2, join=True)
+    r = torch.load(out)
+    assert r["img"] < 1e-10 and r["d_grads"][0] < 1e-8 and r["g_grads"][0] < 1e-7, r
+    assert r["scalars"] < 1e-9 and r["moving"] < 1e-10, r

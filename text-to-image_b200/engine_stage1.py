@@ -35,7 +35,6 @@ class StageIEngine(Engine):
     def __init__(self, K, device, batch, np_=1, z_dim=100, embed_dim=1024, ce=128, gf=128, df=64, d_beta1=0.5,
                  g_beta1=0.5, alpha=0.5, kl_coeff=2.0, world=1, allreduce=None, **kw):
         self.alpha = alpha
-        assert not kw.get("sync_bn"), "synchronised BatchNorm is implemented for wgancls only"
         super().__init__(K, device, batch, np_, z_dim, embed_dim, ce, gf, df, beta1=d_beta1, beta2=0.999,
                          kl_coeff=kl_coeff, world=world, allreduce=allreduce, beta1_g=g_beta1, **kw)
 
@@ -111,10 +110,14 @@ class StageIEngine(Engine):
                         stat_sq=self.dbn_fwd[i][c:])
 
         def bn(i, x, y, act, residual=None, y_pitch=0):
+            stat_rows = 0
+            if self.sync_bn:      # whole-batch statistics of this call: sum the per-rank sums (utils/ops.py:20-29)
+                self.allreduce(self.dbn_fwd[i])
+                stat_rows = (d[x][0].numel() // d[x].shape[-1]) * self.world
             K.bn_apply_train(d[x], self.dbn_fwd[i], BN_EPS, self.dbn_gamma[i], self.dbn_beta[i], d[y], self.dbn_mean[i],
                              self.dbn_rstd[i], self.dbn_var[i], residual=None if residual is None else d[residual],
                              relu=act, moving=(self.dbn_mm[i], self.dbn_mv[i]) if update_moving else None,
-                             decay=BN_DECAY, y_pitch=y_pitch)
+                             decay=BN_DECAY, stat_rows=stat_rows, y_pitch=y_pitch)
 
         K.im2col_k4s2_c3(d["img"][k * B:(k + 1) * B], d["col0"])
         K.conv_gemm(S1, 1, 0, V(d["col0"]), dl["h0"].Wf, V(rows(d["a0"])), bias=dl["h0"].b, act=K.ACT_LRELU,
@@ -147,9 +150,13 @@ class StageIEngine(Engine):
 
         def bn_bwd(i, dy, x_pre, dx, bias_of, dot_normalised=False, dy_pitch=0):
             c = self.dbn_ch[i]
+            kw = {}
+            if self.sync_bn:      # the two reductions run over the whole batch; every rank then holds the full dgamma /
+                self.allreduce(self.dbn_bwd[i])      # dbeta, scaled by 1 / world for the gradient all-reduce(sum)
+                kw = dict(out_scale=1.0 / self.world, stat_rows=(d[x_pre][0].numel() // d[x_pre].shape[-1]) * self.world)
             K.bn_bwd_fused(d[dy], d[x_pre], self.dbn_mean[i], self.dbn_rstd[i], self.dbn_gamma[i], self.dbn_bwd[i][c:],
                            self.dbn_bwd[i][:c], self.dbn_dgamma[i], d[dx], dl[bias_of].gb if want_wgrad else None,
-                           dbeta_out=self.dbn_dbeta[i], dot_normalised=dot_normalised, dy_pitch=dy_pitch)
+                           dbeta_out=self.dbn_dbeta[i], dot_normalised=dot_normalised, dy_pitch=dy_pitch, **kw)
 
         def wgrad(l, x, dy, **kw):
             if want_wgrad:

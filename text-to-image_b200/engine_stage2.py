@@ -32,7 +32,6 @@ class StageIIEngine(Engine):
                  **kw):
         assert gf % 32 == 0, "stage-II needs GF_DIM to be a multiple of 32 (GF_DIM / 4 channels at 256x256)"
         assert image == 256, "the reference's stage-II is defined for 256x256 output (model.py:79: s16 = size // 64)"
-        assert not kw.get("sync_bn")
         self.alpha, self.image = alpha, image
         share = kw.get("share_from")
         # the frozen stage-I generator: parameters 'g_net/*', training-mode BatchNorm, moving statistics keep stepping.
@@ -43,10 +42,10 @@ class StageIIEngine(Engine):
         else:
             s1_df, s1_from = (8, None) if share is None else (share.s1.df, share.s1)
             s1_gf = s1_gf if share is None else share.s1.gf
-        self.s1 = StageIEngine(K, device, batch, np_, z_dim, embed_dim, ce, s1_gf, s1_df, world=world,
+        self.s1 = StageIEngine(K, device, batch, np_, z_dim, embed_dim, ce, s1_gf, s1_df, world=world, allreduce=allreduce,
                                share_from=s1_from,
-                               **{k: v for k, v in kw.items() if k in ("act_dtype", "f32_dtype")}, use_graphs=False,
-                               concurrent=False)
+                               **{k: v for k, v in kw.items() if k in ("act_dtype", "f32_dtype", "sync_bn")},
+                               use_graphs=False, concurrent=False)
         super().__init__(K, device, batch, np_, z_dim, embed_dim, ce, gf, df, beta1=d_beta1, beta2=0.999,
                          kl_coeff=kl_coeff, world=world, allreduce=allreduce, beta1_g=g_beta1, **kw)
 
@@ -217,9 +216,13 @@ class StageIIEngine(Engine):
         ch, fwd, _, gamma, beta, _, _, mean, rstd, var, mm, mv = self._bnp(net)
         res = None if residual is None else buf[residual]
         if train:
+            stat_rows = 0
+            if self.sync_bn:      # whole-batch statistics: sum the per-rank sums (utils/ops.py:20-29)
+                self.allreduce(fwd[i])
+                stat_rows = (buf[x][0].numel() // buf[x].shape[-1]) * self.world
             K.bn_apply_train(buf[x], fwd[i], BN_EPS, gamma[i], beta[i], buf[y], mean[i], rstd[i], var[i], residual=res,
-                             relu=act, moving=(mm[i], mv[i]) if update_moving else None, decay=BN_DECAY, y_pitch=y_pitch,
-                             affine_scale=affine_scale)
+                             relu=act, moving=(mm[i], mv[i]) if update_moving else None, decay=BN_DECAY,
+                             stat_rows=stat_rows, y_pitch=y_pitch, affine_scale=affine_scale)
         else:       # inference (sampler): moving statistics; never combined with y_pitch / affine_scale on this path
             assert y_pitch == 0 and affine_scale == 1.0 and act in (0, RELU_ACT)
             K.bn_apply(buf[x], mm[i], torch.rsqrt(mv[i] + BN_EPS), gamma[i], beta[i], buf[y], res, act == RELU_ACT)
@@ -231,9 +234,14 @@ class StageIIEngine(Engine):
     def _bn_bwd(self, net, buf, i, dy, x_pre, dx, bias_grad, dot_normalised=False, dy_pitch=0, affine_scale=1.0):
         ch, _, bwd, gamma, _, dgamma, dbeta, mean, rstd = self._bnp(net)[:9]
         c = ch[i]
+        out_scale, kw = affine_scale, {}
+        if self.sync_bn:      # reductions over the whole batch; 1 / world keeps the gradient all-reduce(sum) exact
+            self.allreduce(bwd[i])
+            out_scale = affine_scale / self.world
+            kw = dict(stat_rows=(buf[x_pre][0].numel() // buf[x_pre].shape[-1]) * self.world)
         self.K.bn_bwd_fused(buf[dy], buf[x_pre], mean[i], rstd[i], gamma[i], bwd[i][c:], bwd[i][:c], dgamma[i], buf[dx],
-                            bias_grad, dbeta_out=dbeta[i], out_scale=affine_scale, dot_normalised=dot_normalised,
-                            dy_pitch=dy_pitch, affine_scale=affine_scale)
+                            bias_grad, dbeta_out=dbeta[i], out_scale=out_scale, dot_normalised=dot_normalised,
+                            dy_pitch=dy_pitch, affine_scale=affine_scale, **kw)
 
     # ------------------------------------------------------------------ generator
     def g2_forward(self, img_out, kl_sum, train=True, cond_noise=True, update_moving=True, run_stage1=True):

@@ -18,11 +18,12 @@ from ...wgancls.model import Fetch, Placeholder, _truncated_normal
 
 class ConditionalGan(object):
     def __init__(self, cfg, build_model=True, precision="bf16", device=None, kernels=None, distributed=None,
-                 use_graphs=True):
+                 use_graphs=True, sync_bn=False):
         """
         Args:
           cfg: Config specifying all the parameters of the model (reference: model.py:6-10).
-          precision / device / kernels / distributed: as for WGanCls (models/wgancls/model.py of this package).
+          precision / device / kernels / distributed / sync_bn: as for WGanCls (models/wgancls/model.py of this
+            package); sync_bn covers the BatchNorms of BOTH networks (d_net has one after almost every conv).
         """
         self.name = 'ConditionalGAN/StageI'
         self.cfg = cfg
@@ -63,6 +64,7 @@ class ConditionalGan(object):
             self._allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         self._engines = {}
         self._use_graphs = use_graphs
+        self._sync_bn = sync_bn
         self._noise_gen = None
         self._built = False
         self._train_engine()
@@ -76,7 +78,7 @@ class ConditionalGan(object):
             self._engines[batch] = StageIEngine(
                 self._K, self.device, batch, self._np, self.z_dim, self.embed_dim, self.compressed_embed_dim,
                 self.gf_dim, self.df_dim, t.D_BETA_DECAY, t.G_BETA_DECAY, t.COEFF.ALPHA_MISMATCH_LOSS, t.COEFF.KL,
-                self._world, self._allreduce, share_from=base, use_graphs=self._use_graphs)
+                self._world, self._allreduce, share_from=base, use_graphs=self._use_graphs, sync_bn=self._sync_bn)
         return self._engines[batch]
 
     def _train_engine(self):

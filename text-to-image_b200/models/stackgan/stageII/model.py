@@ -19,13 +19,15 @@ from ...wgancls.model import Fetch, Placeholder, _truncated_normal
 
 class ConditionalGan(object):
     def __init__(self, stagei, cfg, build_model=True, precision=None, device=None, kernels=None, distributed=None,
-                 use_graphs=True):
+                 use_graphs=True, sync_bn=False):
         """
         Args:
           stagei: the stage-I ``ConditionalGan`` of this package (models/stackgan/stageI/model.py); its generator
             parameters are shared with the stage-II engine, exactly one copy exists.
           cfg: Config specifying all the parameters of the model (reference: model.py:8-12).
           precision / device / kernels: default to those of ``stagei``.
+          distributed / sync_bn: as for WGanCls; sync_bn makes all three networks (frozen stage-I generator, stageII_g_net,
+            stageII_d_net) normalise with the statistics of the GLOBAL batch, as the single-device reference does.
         """
         self.name = 'ConditionalGAN/StageII'
         self.stagei = stagei
@@ -65,6 +67,7 @@ class ConditionalGan(object):
             self._allreduce = lambda t: dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
         self._engines = {}
         self._use_graphs = use_graphs
+        self._sync_bn = sync_bn
         self._noise_gen = None
         self._built = False
         self._train_engine()
@@ -79,7 +82,7 @@ class ConditionalGan(object):
                 self._K, self.device, batch, self._np, self.z_dim, self.embed_dim, self.compressed_embed_dim,
                 self.gf_dim, self.df_dim, t.D_BETA_DECAY, t.G_BETA_DECAY, t.COEFF.ALPHA_MISMATCH_LOSS, t.COEFF.KL,
                 self._world, self._allreduce, s1_engine=self.stagei._train_engine(), share_from=base,
-                use_graphs=self._use_graphs)
+                use_graphs=self._use_graphs, sync_bn=self._sync_bn)
         return self._engines[batch]
 
     def _train_engine(self):
