@@ -88,3 +88,43 @@ def test_lr_decay_matches_reference_formula():
     for idx, n_critic in ((9999, 1), (10000, 1), (20000, 2), (40001, 2)):
         kiter = (idx // n_critic) // 10000
         assert abs(1e-4 * 0.95 ** kiter - 1e-4 * 0.95 ** ((idx // n_critic) // 10000)) == 0
+
+
+def test_run_mode_dispatch(tmp_path):
+    """models/wgancls/run.py:19-70: --cfg YAML -> directories, dataset, EVAL / TRAIN / visualise dispatch; the TRAIN mode
+    runs the real WGanCls + WGanClsTrainer on the CPU restatement of the kernels (tiny widths)."""
+    import yaml
+    import pytest
+    import fake_kernels as fk
+    from t2i_b200.models.wgancls import run
+    base = {"CONFIG_NAME": "t", "DATASET_NAME": "flowers", "DATASET_DIR": str(tmp_path / "data"),
+            "CHECKPOINT_DIR": str(tmp_path / "ckpt"), "LOGS_DIR": str(tmp_path / "logs"), "SAMPLE_DIR": str(tmp_path / "samples"),
+            "MODEL": {"Z_DIM": 8, "OUTPUT_SIZE": 64, "EMBED_DIM": 32, "COMPRESSED_EMBED_DIM": 8, "GF_DIM": 8, "DF_DIM": 8,
+                      "IMAGE_SHAPE": {"W": 64, "H": 64, "D": 3}},
+            "TRAIN": {"FLAG": True, "MAX_STEPS": 4, "BATCH_SIZE": 2, "SAMPLE_NUM": 2, "D_LR": 1e-4, "G_LR": 1e-4, "BETA1": 0.0,
+                      "BETA2": 0.9, "SUMMARY_PERIOD": 1, "N_CRITIC": 1, "NUM_EMBEDDINGS": 4, "CHECKPOINTS_TO_KEEP": 3,
+                      "SAMPLE_PERIOD": 300, "COEFF": {"KL": 1.0, "LAMBDA": 100.0}},
+            "EVAL": {"FLAG": False, "SAMPLE_SIZE": 4, "SIZE": 8}}
+    kw = dict(precision="bf16x3", device="cpu", kernels=fk, use_graphs=False)
+
+    def write(cfg, name):
+        p = tmp_path / name
+        p.write_text(yaml.safe_dump(cfg))
+        return str(p)
+
+    tr = run.main(write(base, "train.yml"), **kw)
+    assert [r["idx"] for r in tr.log] == [1, 2, 3] and all(np.isfinite(r["D_loss"]) and np.isfinite(r["G_loss"]) for r in tr.log)
+    for d in ("ckpt", "logs", "samples"):
+        assert os.path.isdir(str(tmp_path / d))
+    assert os.listdir(str(tmp_path / "ckpt")) == ["wgancls-2.npz"]
+    ev = dict(base, EVAL=dict(base["EVAL"], FLAG=True))
+    with pytest.raises(NotImplementedError, match="Inception"):
+        run.main(write(ev, "eval.yml"), **kw)
+    vis = dict(base, TRAIN=dict(base["TRAIN"], FLAG=False))
+    with pytest.raises(NotImplementedError, match="visualis"):
+        run.main(write(vis, "vis.yml"), **kw)
+    (tmp_path / "data").mkdir()
+    (tmp_path / "data" / "train").write_text("x")
+    (tmp_path / "data" / "test").write_text("x")
+    with pytest.raises(NotImplementedError, match="pickled"):
+        run.main(write(base, "train2.yml"), **kw)
