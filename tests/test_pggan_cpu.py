@@ -213,3 +213,26 @@ def test_mirror_stage_to_stage_restore_and_fade_in(tmp_path):
         m2.generator(np.zeros((3, 16)), np.zeros((3, 32)), stages=1, t=False)
     with pytest.raises(RuntimeError):
         _model(tmp_path / "elsewhere", 2, True).train(max_updates=1)      # no stage-1 checkpoint to fade in from (:149-151)
+
+
+def test_schedule_driver_runs_consecutive_passes(tmp_path):
+    """train_pggan.py:20-69: pass 0 (stage 1) writes stage1/, pass 1 (stage 2, transition) reads stage1/ and writes stage2/"""
+    import os
+    from t2i_b200.models.pggan import train_pggan
+    from t2i_b200.models.wgancls.trainer import SyntheticTextDataset
+    from t2i_b200.utils.config import AttrDict
+    cfg = AttrDict({"CHECKPOINT_DIR": str(tmp_path / "ck"), "SAMPLE_DIR": str(tmp_path / "s"), "LOGS_DIR": str(tmp_path / "l"),
+                    "MODEL": {"SIZES": [4, 8, 16, 32, 64, 128, 256, 512], "EMBED_DIM": 32}})
+    seen = []
+
+    def data(size):
+        seen.append(size)
+        return SyntheticTextDataset(embed_dim=32, num_examples=64, image_size=size)
+
+    ms = train_pggan.train(cfg, data, images=160, passes=[0, 1], max_updates=2, precision="bf16x3", device="cpu", kernels=fk,
+                           use_graphs=False, nf_base=16, nf_cap=16, z_dim=16, embed_dim=32, compr_embed_dim=8, sample_num=2,
+                           d_embed=8)
+    assert seen == [4, 8] and [(m.stage, m.trans, m.batch_size, m.steps) for m in ms] == [(1, False, 16, 10), (2, True, 16, 10)]
+    assert os.listdir(os.path.join(cfg.CHECKPOINT_DIR, "stage1")) == ["wgancls-2.npz"]
+    assert os.listdir(os.path.join(cfg.CHECKPOINT_DIR, "stage2")) == ["wgancls-2.npz"]
+    assert abs(ms[1].alpha_tra - 0.2) < 1e-12

@@ -267,3 +267,29 @@ def test_oracle_k4s1_same_padding_against_naive_loops():
 
     b = single(q2, f["x"], f["cond"])
     assert rel(a, b) < 1e-12
+
+
+def test_run_entry_point_trains_stage2_around_a_stage1_generator(tmp_path):
+    """models/stackgan/stageII/run.py:26-86: two configs, directories, TRAIN dispatch (stage-I built with
+    build_model=False, only its generator is used), one update on the CPU restatement of the kernels."""
+    import os
+    import yaml
+    from t2i_b200.models.stackgan.stageII import run
+    cfg = S2.Stage2Cfg(**TINY)
+    c1, c2 = _cfgs(tmp_path, cfg)
+    for c, tag in ((c1, "s1"), (c2, "s2")):
+        c["DATASET_DIR"] = str(tmp_path / "data")
+        c["LOGS_DIR"], c["SAMPLE_DIR"] = str(tmp_path / tag / "logs"), str(tmp_path / tag / "samples")
+        c["TRAIN"]["FLAG"], c["EVAL"] = True, {"FLAG": False}
+    plain = lambda d: {k: (plain(v) if isinstance(v, dict) else v) for k, v in d.items()}
+    p1, p2 = tmp_path / "c1.yml", tmp_path / "c2.yml"
+    p1.write_text(yaml.safe_dump(plain(c1)))
+    p2.write_text(yaml.safe_dump(plain(c2)))
+    from t2i_b200.models.wgancls.trainer import SyntheticTextDataset
+    data = SyntheticTextDataset(embed_dim=cfg.embed_dim, num_examples=16, image_size=256)
+    tr = run.main(str(p1), str(p2), dataset=data, max_updates=1, precision="bf16x3", device="cpu", kernels=fk, use_graphs=False)
+    assert len(tr.log) == 1 and np.isfinite(tr.log[0]["d_loss"]) and os.path.isdir(c2["SAMPLE_DIR"])
+    c2["TRAIN"]["FLAG"] = False
+    p2.write_text(yaml.safe_dump(plain(c2)))
+    with pytest.raises(NotImplementedError, match="visualis"):
+        run.main(str(p1), str(p2), dataset=data, precision="bf16x3", device="cpu", kernels=fk, use_graphs=False)

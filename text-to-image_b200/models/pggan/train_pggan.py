@@ -40,3 +40,21 @@ def train(cfg, dataset_for_size, images=600000, passes=None, max_updates=None, *
         pggan.train(max_updates=max_updates)
         models.append(pggan)
     return models
+
+
+if __name__ == "__main__":
+    # python -m t2i_b200.models.pggan.train_pggan --cfg <yml> [--passes 0,1] [--max-updates N]   (synthetic batches: the
+    # reference's pickled datasets, preprocess/dataset.py, are out of scope)
+    import argparse
+
+    from ...utils.config import config_from_yaml
+    from ..wgancls.trainer import SyntheticTextDataset
+
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--cfg", required=True, help="YAML with CHECKPOINT_DIR, SAMPLE_DIR, LOGS_DIR, MODEL.SIZES (models/pggan/cfg/*.yml)")
+    ap.add_argument("--passes", default=None, help="comma-separated indices into the 15-entry schedule")
+    ap.add_argument("--max-updates", type=int, default=None)
+    a = ap.parse_args()
+    cfg = config_from_yaml(a.cfg)
+    train(cfg, lambda size: SyntheticTextDataset(embed_dim=cfg.MODEL.EMBED_DIM, image_size=size),
+          passes=None if a.passes is None else [int(x) for x in a.passes.split(",")], max_updates=a.max_updates)
