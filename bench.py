@@ -27,6 +27,25 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 METRIC = "images/sec (G+D+GP step) 64x64 wgancls"
+
+_REAL_STDOUT = None
+
+
+def claim_stdout():
+    """The contract is ONE JSON line on stdout.  Libraries write there too (NCCL prints its version banner on stdout when
+    NCCL_DEBUG is set in the environment): keep a private handle of the real stdout for the result line and point file
+    descriptor 1 at stderr for everything else."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(line):
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(line) + "\n")
+    out.flush()
 GFLOP_PER_IMAGE = 28.585          # SURVEY.md 8(d): 2 * (4 G_f + 15 D_f) MACs per image per iteration
 
 
@@ -137,7 +156,7 @@ def run_reference(args, rank):
                                        % args.steps},
             "e2e": {"value": ips, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    emit(line)
 
 
 def main():
@@ -153,6 +172,7 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="profiling aid: eager launches (ncu launch lists)")
     ap.add_argument("--profile-out", default=None, help="write the per-launch GEMM table (JSON) here")
     args = ap.parse_args()
+    claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -230,8 +250,8 @@ def main():
 
     if args.only_resident:
         if rank == 0:
-            print(json.dumps({"metric": METRIC, "value": value, "unit": "images/s", "ms_per_step": ms_per_step,
-                              "gpu_launches": int(launches), "note": "--only-resident (profiling aid)"}))
+            emit({"metric": METRIC, "value": value, "unit": "images/s", "ms_per_step": ms_per_step,
+                  "gpu_launches": int(launches), "note": "--only-resident (profiling aid)"})
         if world > 1:
             dist.destroy_process_group()
         return
@@ -340,7 +360,7 @@ def main():
                 "roofline": roofline, "cpu_baseline": cpu,
                 "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h},
                 "gpu_launches": int(launches), "clocks": clocks, "finite": bool(finite)}
-        print(json.dumps(line))
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
