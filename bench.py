@@ -140,6 +140,11 @@ def model_cfg(batch):
     return cfg
 
 
+def workload_name(batch, world):
+    return ("wgancls 64x64, batch=%d per GPU (BASELINE config %s), 1024-d random text embeds, GF=DF=128, one D+GP run then "
+            "one G run per step (N_CRITIC=1), TF-form Adam, reference init" % (batch, "2" if world == 1 else "3-style weak scaling"))
+
+
 def run_reference(args, rank):
     """--impl reference: the CPU arm.  Rank 0 alone works; other ranks exit 0."""
     if rank != 0:
@@ -149,8 +154,10 @@ def run_reference(args, rank):
     line = {"impl": "reference", "metric": METRIC, "value": ips, "unit": "images/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": spi * 1e3, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "wgancls 64x64, batch=16 per step (BASELINE config 1), 1024-d random text embeds, "
-                                   "CPU restatement of the reference's TF-1.4 graph (TF 1.4 not installable)"},
+            "config": {"workload": workload_name(args.batch, int(os.environ.get("WORLD_SIZE", "1"))),
+                       "sample": "each step is one full iteration on a 16-image batch of that workload (BASELINE config 1: "
+                                 "the reference's CPU-runnable case), executed by the CPU restatement of the reference's "
+                                 "TF-1.4 graph (TF 1.4 is not installable, SURVEY.md 8c)"},
             "cpu_baseline": {"value": ips, "unit": "images/s", "cores": os.cpu_count(), "kind": "port",
                              "sample": "%d full iterations (D run + G run) at batch 16, fp32, PyTorch-CPU, all host threads"
                                        % args.steps},
@@ -351,9 +358,7 @@ def main():
                 "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "bf16" if args.precision == "bf16" else "bf16 (split x3, parity mode)",
                 "data": "synthetic",
-                "config": {"workload": "wgancls 64x64, batch=%d per GPU (BASELINE config %s), 1024-d random text embeds, "
-                                       "GF=DF=128, one D+GP run then one G run per step (N_CRITIC=1), TF-form Adam, "
-                                       "reference init" % (B, "2" if world == 1 else "3-style weak scaling"),
+                "config": {"workload": workload_name(B, world),
                            "global_batch": B * world, "parallelism": "dp%d (batch shards, one NCCL allreduce per optimizer step)" % world,
                            "l2": "per-step working set (activations + gradients > 2 GB) exceeds the 126 MB L2; no explicit flush",
                            "bn": "per-replica batch statistics" if world > 1 else "single replica"},
