@@ -192,7 +192,7 @@ def test_mirror_stage_to_stage_restore_and_fade_in(tmp_path):
     assert m1.get_variables_up_to_stage(1) == ["d_net/rgb_stage_0/", "g_net/rgb_stage_0/", "d_net/conv_stage_0/",
                                                "g_net/conv_stage_0/"]
     m1.train(max_updates=2)
-    assert os.listdir(m1.check_dir_write) == ["wgancls-2.npz"]
+    assert sorted(os.listdir(m1.check_dir_write)) == ["checkpoint", "pggan-2.npz"]
     v1 = m1.get_variables()
     # the transition graph of stage 2 restores everything of stage 1 and initialises its new layers
     m2 = _model(tmp_path, 2, True)
@@ -233,6 +233,6 @@ def test_schedule_driver_runs_consecutive_passes(tmp_path):
                            use_graphs=False, nf_base=16, nf_cap=16, z_dim=16, embed_dim=32, compr_embed_dim=8, sample_num=2,
                            d_embed=8)
     assert seen == [4, 8] and [(m.stage, m.trans, m.batch_size, m.steps) for m in ms] == [(1, False, 16, 10), (2, True, 16, 10)]
-    assert os.listdir(os.path.join(cfg.CHECKPOINT_DIR, "stage1")) == ["wgancls-2.npz"]
-    assert os.listdir(os.path.join(cfg.CHECKPOINT_DIR, "stage2")) == ["wgancls-2.npz"]
+    assert sorted(os.listdir(os.path.join(cfg.CHECKPOINT_DIR, "stage1"))) == ["checkpoint", "pggan-2.npz"]
+    assert sorted(os.listdir(os.path.join(cfg.CHECKPOINT_DIR, "stage2"))) == ["checkpoint", "pggan-2.npz"]
     assert abs(ms[1].alpha_tra - 0.2) < 1e-12

@@ -185,7 +185,7 @@ def test_trainer_two_checkpoint_restore(tmp_path):
     s1, s2, c1, c2 = _models(tmp_path, cfg)
     # a stage-I checkpoint with recognisable generator weights (written by the stage-I model itself)
     s1.initialize(seed=11)
-    saver.save(s1, c1.CHECKPOINT_DIR, 7)
+    saver.save(s1, c1.CHECKPOINT_DIR, 7, prefix="stageI")
     g1 = {k: torch.as_tensor(v).clone() for k, v in s1.get_variables().items() if k.startswith("g_net/")}
     s1.initialize(seed=12)       # clobber; the trainer must restore seed 11's generator from the stage-I directory
     data = SyntheticTextDataset(embed_dim=cfg.embed_dim, num_examples=16, image_size=256)
@@ -198,13 +198,13 @@ def test_trainer_two_checkpoint_restore(tmp_path):
             assert torch.equal(torch.as_tensor(after[n]), w), n
     # counter 2 -> a stage-II checkpoint that holds only the stage-II scopes (trainer.py:48-52,175-176)
     import os
-    assert os.listdir(c2.CHECKPOINT_DIR) == ["wgancls-2.npz"]
-    z = np.load(os.path.join(c2.CHECKPOINT_DIR, "wgancls-2.npz"))
+    assert sorted(os.listdir(c2.CHECKPOINT_DIR)) == ["checkpoint", "stageII-2.npz"]
+    z = np.load(os.path.join(c2.CHECKPOINT_DIR, "stageII-2.npz"))
     assert all(k.startswith((S2.G2, S2.D2, "__adam__/")) for k in z.files)
     s2.initialize(seed=99)
     tr2 = ConditionalGanTrainer(None, s2, data, c2, c1)
     tr2.define_losses()
-    assert saver.load(tr2.stageii_saver, c2.CHECKPOINT_DIR) == (True, 2)
+    assert saver.load(tr2.stageii_saver, c2.CHECKPOINT_DIR, prefix="stageII") == (True, 2)
     again = s2.get_variables()
     for n in again:
         if n.startswith((S2.G2, S2.D2)):

@@ -141,4 +141,4 @@ def test_trainer_loop_sampler_and_graphs(tmp_path):
     samples = m.run(m.sampler, feed_dict={m.z_sample: np.random.normal(0, 1, (4, ocfg.z_dim)),
                                          m.embed_sample: np.random.normal(0, 1, (4, ocfg.embed_dim))})
     assert samples.shape == (4, 256, 256, 3) and float(np.abs(samples).max()) <= 1.0
-    assert os.listdir(c2.CHECKPOINT_DIR) == ["wgancls-2.npz"]
+    assert sorted(os.listdir(c2.CHECKPOINT_DIR)) == ["checkpoint", "stageII-2.npz"]

@@ -71,16 +71,45 @@ def test_trainer_step_order_schedule_and_checkpoints(tmp_path):
     assert abs(fd["learning_rate_d"] - 1e-4) < 1e-12 and abs(fd["learning_rate_g"] - 2e-4) < 1e-12
     assert [r["idx"] for r in tr.log] == [5, 10] and "wdist" in tr.log[0]
     assert samples == [(6, (6, 64, 64, 3), 6), (12, (6, 64, 64, 3), 6)]
-    assert sorted(os.listdir(cfg.CHECKPOINT_DIR)) == ["wgancls-2.npz"]  # idx % 500 == 2
+    assert sorted(os.listdir(cfg.CHECKPOINT_DIR)) == ["checkpoint", "wgancls-2.npz"]  # idx % 500 == 2
     # resume: the step is parsed from the file name with the reference's regex
     m2 = StubModel()
     ok, counter = saver.load(m2, cfg.CHECKPOINT_DIR)
     assert ok and counter == 2 and np.allclose(m2.vars["w"], np.arange(3.0))
     for step in (502, 1002, 1502):
         saver.save(m, cfg.CHECKPOINT_DIR, step, max_to_keep=3)
-    assert sorted(os.listdir(cfg.CHECKPOINT_DIR)) == ["wgancls-1002.npz", "wgancls-1502.npz", "wgancls-502.npz"]
+    assert sorted(os.listdir(cfg.CHECKPOINT_DIR)) == ["checkpoint", "wgancls-1002.npz", "wgancls-1502.npz", "wgancls-502.npz"]
     assert saver.load(m2, cfg.CHECKPOINT_DIR) == (True, 1502)
     assert saver.load(m2, str(tmp_path / "missing")) == (False, 0)
+
+
+def test_saver_latest_is_most_recently_written_not_highest_step(tmp_path):
+    """tf.train.Saver semantics (utils/saver.py:16 get_checkpoint_state): a second pass that restarts its step counter
+    in a directory an earlier, LONGER pass filled (the PGGAN stabilisation pass after its transition pass,
+    models/pggan/train_pggan.py:17-69) must (a) not have its fresh checkpoints pruned because older files carry
+    larger step numbers, and (b) be the one a later load() restores."""
+    d = str(tmp_path / "stage3")
+    first, second = StubModel(), StubModel()
+    first.vars = {"w": np.full(3, 1.0), "kt": np.float32(0.7)}
+    for step in (2000, 4000, 6000):                 # transition pass: idx up to 6000, keeps 2
+        saver.save(first, d, step, max_to_keep=2, prefix="pggan")
+    assert sorted(f for f in os.listdir(d) if f.endswith(".npz")) == ["pggan-4000.npz", "pggan-6000.npz"]
+    second.vars = {"w": np.full(3, 2.0), "kt": np.float32(0.7)}
+    p = saver.save(second, d, 2000, max_to_keep=2, prefix="pggan")     # shorter second pass: ends at idx 2000
+    assert os.path.exists(p), "the checkpoint just written must survive its own save() call"
+    assert saver.latest_checkpoint(d, "pggan") == "pggan-2000.npz"
+    m = StubModel()
+    assert saver.load(m, d, prefix="pggan") == (True, 2000) and np.allclose(m.vars["w"], 2.0)
+    # the second saver prunes only what IT wrote; the first pass's files are not its to delete
+    saver.save(second, d, 3000, max_to_keep=2, prefix="pggan")
+    saver.save(second, d, 3500, max_to_keep=2, prefix="pggan")
+    names = sorted(f for f in os.listdir(d) if f.endswith(".npz"))
+    assert names == ["pggan-3000.npz", "pggan-3500.npz", "pggan-4000.npz", "pggan-6000.npz"]
+    assert saver.load(m, d, prefix="pggan") == (True, 3500)
+    # no state file (directory written by an older version): newest modification time wins
+    os.remove(os.path.join(d, saver.STATE_FILE))
+    os.utime(os.path.join(d, "pggan-3000.npz"), (2e9, 2e9))
+    assert saver.load(m, d, prefix="pggan") == (True, 3000)
 
 
 def test_lr_decay_matches_reference_formula():
@@ -116,7 +145,7 @@ def test_run_mode_dispatch(tmp_path):
     assert [r["idx"] for r in tr.log] == [1, 2, 3] and all(np.isfinite(r["D_loss"]) and np.isfinite(r["G_loss"]) for r in tr.log)
     for d in ("ckpt", "logs", "samples"):
         assert os.path.isdir(str(tmp_path / d))
-    assert os.listdir(str(tmp_path / "ckpt")) == ["wgancls-2.npz"]
+    assert sorted(os.listdir(str(tmp_path / "ckpt"))) == ["checkpoint", "wgancls-2.npz"]
     ev = dict(base, EVAL=dict(base["EVAL"], FLAG=True))
     with pytest.raises(NotImplementedError, match="Inception"):
         run.main(write(ev, "eval.yml"), **kw)

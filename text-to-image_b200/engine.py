@@ -49,6 +49,35 @@ class Layer:
         self.cin_tf = self.cout_tf = None
 
 
+class HostScalarRing:
+    """Small host -> device scalar uploads that stay correct when the host runs ahead of the device.
+
+    A single pinned staging slot is wrong: ``dst.copy_(slot, non_blocking=True)`` only ENQUEUES the copy, so the host
+    can overwrite the slot with step t+1's value before the copy for step t has executed (a loop that never fetches a
+    loss, e.g. bench.py's resident steps, does not synchronise).  Here every upload takes the next of ``depth`` pinned
+    slots and records an event behind its copy; a slot is rewritten only after its previous copy has completed."""
+
+    def __init__(self, width, dtype, cuda, depth=16):
+        self.cuda, self.i = cuda, 0
+        self.slots = [torch.zeros(width, dtype=dtype) for _ in range(depth if cuda else 1)]
+        if cuda:
+            self.slots = [t.pin_memory() for t in self.slots]
+        self.events = [None] * len(self.slots)
+
+    def upload(self, values, dst):
+        slot, ev = self.slots[self.i], self.events[self.i]
+        if ev is not None:
+            ev.synchronize()                 # normally long done: `depth` uploads ago
+        for j, v in enumerate(values):
+            slot[j] = v
+        dst.copy_(slot, non_blocking=True)
+        if self.cuda:
+            if ev is None:
+                ev = self.events[self.i] = torch.cuda.Event()
+            ev.record()
+        self.i = (self.i + 1) % len(self.slots)
+
+
 class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
@@ -183,9 +212,7 @@ class Engine:
         self.packed = {k: torch.zeros(self.np, v.numel(), device=self.dev, dtype=self.act_dtype)
                        for k, v in self.flat.items()}
         self.lr_t = {k: torch.zeros(1, **f32) for k in self.flat}
-        self.lr_host = {k: torch.zeros(1, dtype=self.f32_dtype) for k in self.flat}
-        if self.dev.type == "cuda":
-            self.lr_host = {k: v.pin_memory() for k, v in self.lr_host.items()}
+        self.lr_ring = HostScalarRing(1, self.f32_dtype, self.dev.type == "cuda")
         self.P, self.G = {}, {}
         for net, table in (("d", self.d_table), ("g", self.g_table)):
             for name, (off, n) in table.items():
@@ -773,8 +800,7 @@ class Engine:
     # ------------------------------------------------------------------ optimizer plumbing
     def _set_lr(self, net, lr, t):
         """lr_t of tf.train.AdamOptimizer, staged into device memory OUTSIDE any captured graph."""
-        self.lr_host[net][0] = lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1_net[net] ** t)
-        self.lr_t[net].copy_(self.lr_host[net], non_blocking=True)
+        self.lr_ring.upload([lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1_net[net] ** t)], self.lr_t[net])
 
     def _adam(self, net):
         n = self.d_n if net == "d" else self.g_n

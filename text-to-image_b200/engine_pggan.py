@@ -25,7 +25,7 @@ from collections import OrderedDict
 
 import torch
 
-from .engine import Engine, Layer
+from .engine import Engine, HostScalarRing, Layer
 
 GP_WEIGHT = 200.0      # pggan.py:108
 KL_COEFF = 5.0         # pggan.py:109
@@ -142,9 +142,7 @@ class PgganEngine(Engine):
         d = self.d = {}
         # fade-in coefficients [alpha, 1 - alpha] in device memory (pggan.py:78-79), staged by set_alpha()
         self.ab = torch.tensor([1.0, 0.0], **f32)
-        self.ab_host = torch.tensor([1.0, 0.0], dtype=self.f32_dtype)
-        if self.dev.type == "cuda":
-            self.ab_host = self.ab_host.pin_memory()
+        self.ab_ring = HostScalarRing(2, self.f32_dtype, self.dev.type == "cuda")
         d["img"] = torch.zeros(S4, S, S, 3, **f32)          # [fake | real | mismatch | x_hat]
         d["x8"] = self._planes(S4, S, S, 8)
         d["d_x8"] = self._planes(B, S, S, 8)
@@ -212,9 +210,7 @@ class PgganEngine(Engine):
 
     def set_alpha(self, alpha):
         """alpha_tra = iter / steps (pggan.py:78-79), staged into device memory OUTSIDE any captured graph."""
-        self.ab_host[0] = float(alpha)
-        self.ab_host[1] = 1.0 - float(alpha)
-        self.ab.copy_(self.ab_host, non_blocking=True)
+        self.ab_ring.upload([float(alpha), 1.0 - float(alpha)], self.ab)
 
     # ------------------------------------------------------------------ generator
     def _ln(self, i, x, y, relu):

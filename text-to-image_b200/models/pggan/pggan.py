@@ -337,11 +337,11 @@ class PGGAN(object):
         self.initialize()
         if self.stage != 1:
             if self.trans:
-                could_load, _ = load(self.restore, self.check_dir_read)
+                could_load, _ = load(self.restore, self.check_dir_read, prefix="pggan")
                 if not could_load:
                     raise RuntimeError('Could not load previous stage during transition')
             else:
-                could_load, _ = load(self.saver, self.check_dir_read)
+                could_load, _ = load(self.saver, self.check_dir_read, prefix="pggan")
                 if not could_load:
                     raise RuntimeError('Could not load current stage')
 
@@ -384,16 +384,22 @@ class PGGAN(object):
                       % (epoch, idx, time.time() - start_time, err_d, err_g))
 
             if np.mod(idx, 2000) == 0:
-                samples = self.run(self.sampler, feed_dict={self.z_sample: sample_z, self.cond_sample: sample_cond})
-                samples = np.clip(samples, -1., 1.)
-                if self.out_size > 256:
-                    samples = samples[:4]
-                if on_samples is not None:
-                    on_samples(epoch, idx, samples, captions)
+                try:                                  # pggan.py:228-244: a failed sample is logged, the pass goes on
+                    samples = self.run(self.sampler, feed_dict={self.z_sample: sample_z, self.cond_sample: sample_cond})
+                    samples = np.clip(samples, -1., 1.)
+                    if self.out_size > 256:
+                        samples = samples[:4]
+                    if on_samples is not None:
+                        on_samples(epoch, idx, samples, captions)
+                except Exception as e:
+                    print("Failed to generate sample image")
+                    print(type(e))
+                    print(e.args)
+                    print(e)
 
             done += 1
             last = idx == self.steps - 1 or (max_updates is not None and done >= max_updates)
             if np.mod(idx, 2000) == 0 or last:
-                save(self.saver, self.check_dir_write, idx, 2)
+                save(self.saver, self.check_dir_write, idx, 2, prefix="pggan")
             if last:
                 break

@@ -41,7 +41,7 @@ class ConditionalGanTrainer(object):
         counter = 1
         start_time = time.time()
         m.initialize()
-        could_load, checkpoint_counter = load(m, cfg.CHECKPOINT_DIR)
+        could_load, checkpoint_counter = load(m, cfg.CHECKPOINT_DIR, prefix="stageI")
         if could_load:
             counter = checkpoint_counter
             print(" [*] Load SUCCESS")
@@ -74,7 +74,7 @@ class ConditionalGanTrainer(object):
                     samples = m.run(m.sampler, feed_dict={m.z_sample: sample_z, m.embed_sample: sample_embed})
                     if self.on_samples is not None:
                         self.on_samples(epoch, idx, samples, captions)
-                    save(m, cfg.CHECKPOINT_DIR, counter, cfg.TRAIN.CHECKPOINTS_TO_KEEP)
+                    save(m, cfg.CHECKPOINT_DIR, counter, cfg.TRAIN.CHECKPOINTS_TO_KEEP, prefix="stageI")
                 done += 1
                 if max_updates is not None and done >= max_updates:
                     return

@@ -68,14 +68,14 @@ class ConditionalGanTrainer(object):
         start_time = time.time()
         m.initialize()       # initialize_uninitialized (trainer.py:111): whatever the two loads below do not restore
 
-        could_load, checkpoint_counter = load(self.stageii_saver, cfg.CHECKPOINT_DIR)
+        could_load, checkpoint_counter = load(self.stageii_saver, cfg.CHECKPOINT_DIR, prefix="stageII")
         if could_load:
             counter = checkpoint_counter
             print(" [*] Load SUCCESS: Stage II networks are loaded.")
         else:
             print(" [!] Load failed for stage II networks...")
 
-        could_load, checkpoint_counter = load(self.stagei_g_saver, self.cfg_stage_i.CHECKPOINT_DIR)
+        could_load, checkpoint_counter = load(self.stagei_g_saver, self.cfg_stage_i.CHECKPOINT_DIR, prefix="stageI")
         if could_load:
             print(" [*] Load SUCCESS: Stage I generator is loaded")
         else:
@@ -108,7 +108,7 @@ class ConditionalGanTrainer(object):
                     if self.on_samples is not None:
                         self.on_samples(epoch, idx, samples, captions)
                 if np.mod(counter, 500) == 2:
-                    save(self.stageii_saver, cfg.CHECKPOINT_DIR, counter, cfg.TRAIN.CHECKPOINTS_TO_KEEP)
+                    save(self.stageii_saver, cfg.CHECKPOINT_DIR, counter, cfg.TRAIN.CHECKPOINTS_TO_KEEP, prefix="stageII")
                 done += 1
                 if max_updates is not None and done >= max_updates:
                     return

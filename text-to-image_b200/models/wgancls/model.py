@@ -285,8 +285,12 @@ class WGanCls(object):
                 if not ran and sc is None and f.name != "kt":
                     raise RuntimeError("scalar '%s' is produced by the D/G run; fetch it together with the "
                                        "train op or after it" % f.name)
-                sc = sc or eng.scalars_dict()
-                out.append(float(eng.kt.item()) if f.name == "kt" else sc[f.name])
+                if f.name == "kt" and not ran:
+                    eng.join_comm()                  # the kt step of the last D run lives on the communication stream
+                    out.append(float(eng.kt.item()))
+                    continue
+                sc = sc or eng.scalars_dict()        # 'kt' there is the value after this iteration's kt_optim
+                out.append(sc[f.name])
             elif f.name == "sampler":
                 z = self._dev(feed_dict[self.z_sample])
                 cond = self._dev(feed_dict[self.cond_sample])
@@ -295,6 +299,19 @@ class WGanCls(object):
                 out.append(img.cpu().numpy())
             elif f.name == "G":
                 out.append(eng.d["img"][:self.batch_size].cpu().numpy())
+            # the remaining tensors of build_model (model.py:48-55) live in the engine's buffers after a D run:
+            # image segments [fake | real | mismatch | x_hat] and one logit per sample of the 4B batch
+            elif f.name == "x_hat":
+                b = self.batch_size
+                out.append(eng.d["img"][3 * b:].cpu().numpy())
+            elif f.name in ("Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit"):
+                b = self.batch_size
+                k = ("Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit").index(f.name)
+                out.append(eng.d["logit"][k * b:(k + 1) * b].cpu().numpy().reshape(b, 1, 1, 1))
+            elif f.name in ("embed_mean", "embed_log_sigma"):
+                ce = self.compressed_embed_dim
+                ms = eng.ms_f32()
+                out.append((ms[:, :ce] if f.name == "embed_mean" else ms[:, ce:]).cpu().numpy())
             else:
                 raise KeyError("fetch '%s' is not materialised by this implementation" % f.name)
         return out[0] if single else out
