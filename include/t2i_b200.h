@@ -84,6 +84,12 @@ typedef struct {
      * (an output-channel window, e.g. the two halves of a concat gradient with different epilogues); bias,
      * add / mask / stat_x and the stat_* vectors are indexed by the WINDOW's channels. */
     int w_n0;
+    /* The 3-channel ends (d_net's first conv, model.py:135; the input gradient of g_net's last transposed conv, :218):
+     * x_img != NULL makes the A operand the 4x4 / stride-2 SAME patch matrix of this fp32 NHWC image [x.n][x.h][x.w][3]
+     * (row = output pixel, column (kh*4 + kw)*3 + c, 48 columns), assembled in shared memory from the image -- no patch
+     * matrix in HBM.  mode = T2I_CONV_K4S2, k = 4, x.ptr ignored, x.c = 48; w is [np][1][w_rows][w_cols] with 64
+     * (48 used) along the contraction; y is [x.n][x.h/2][x.w/2][c].  Everything else (bias, act, mask, stat_*) as above. */
+    const float* x_img;
 } t2i_conv_gemm_desc;
 int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
 
@@ -110,6 +116,29 @@ int t2i_to_planes(const float* src, void* dst, long long plane_stride, int np, l
                   const float* row_scale, void* stream);
 /* bf16 planes -> fp32 */
 int t2i_from_planes(const void* src, long long plane_stride, int np, float* dst, long long n, void* stream);
+
+/* ---- the 3-channel ends as direct kernels (img_gemm.cu; see also t2i_conv_gemm_desc.x_img) ----
+ *
+ * t2i_deconv_img: transpose of a 4x4 / stride-2 SAME convolution whose image side has 3 channels, on tcgen05 with the
+ * overlap-add (col2im) done on chip:
+ *     out[n, 2p-1+kh, 2q-1+kw, c] = bias3[c] + sum over the <= 4 patches (p, q) and ci of a[n, p, q, ci] * W[(kh*4+kw)*3 + c][ci]
+ * a: bf16 planes [n][h][w][c <= 256], w a power of two <= 128, h*w a multiple of 128.  W: bf16 planes, 64 (48 used) along
+ * the (tap, channel) axis: w_layout T2I_W_NK = [64][K] (g_net's last transposed conv, model.py:218, forward) or
+ * T2I_W_KN = [K][64] (d_net's first conv, model.py:135, used for its input gradient).  out: fp32 NHWC [n][2h][2w][3].
+ * w9 / b9 / img (all or none): additionally img = tanh(conv3x3(out, w9 HWIO [3][3][3][3]) + b9), model.py:219-221. */
+int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane_stride, int w_rows, int w_cols, int w_layout, int np,
+                   const float* bias3, float* out, const float* w9, const float* b9, float* img, void* stream);
+/* Weight gradient of a 4x4 / stride-2 conv between a 3-channel fp32 NHWC image [n][h][w][3] (patches assembled on chip)
+ * and a bf16-plane tensor on the [n][h/2][w/2] grid, on tcgen05, dw += (the caller zeroes):
+ *   img_side 1 (the image is the conv INPUT, model.py:135):        dw[co][64] (48 used) += sum other[pixel][co] * patch[pixel][:]
+ *   img_side 2 (the image is the gradient at a deconv OUTPUT, :218): dw[64][ci] (48 used) += sum patch[pixel][:] * other[pixel][ci] */
+int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_act* other, int img_side, int np, float* dw, int cout,
+                  int cin, void* stream);
+/* y[r][o] = act(sum_k x[r][k] * w[o][k] + bias[o]) in fp32 (the conditioning head, model.py:113-114). */
+int t2i_dense_f32(const float* x, int rows, int cin, const float* w, const float* bias, int cout, int act, float* y,
+                  void* stream);
+/* dst[r][:] = row_scale[r] * src[r][:], fp32 (gradient-penalty tangent seed, model.py:62-65). */
+int t2i_scale_rows(const float* src, const float* row_scale, float* dst, long long rows, int cols, void* stream);
 
 /* 3-channel image <-> 4x4/s2 patch matrix [n*(h/2)*(w/2), 64] (col = (kh*4+kw)*3 + c, 48 used).
  * im2col feeds d_net's first conv (model.py:135) and the input-gradient of g_net's last deconv
@@ -207,13 +236,14 @@ int t2i_gp_interp(const float* g, const float* x, const float* eps, float* xhat,
 int t2i_gp_penalty(const float* grad, int n, int per_sample, float weight, float inv_global_batch,
                    float* slope, float* coef, float* pen_sum, void* stream);
 
-/* conditioning augmentation (model.py:108-127): ms = [mean | log_sigma] (post-LeakyReLU) [b,2*ce].
+/* conditioning augmentation (model.py:108-127): ms = [mean | log_sigma] (post-LeakyReLU), an fp32 [b,2*ce] tensor
+ * produced by t2i_dense_f32 (log_sigma feeds exp(): it is kept out of bf16 storage).
  * fwd: zc[b, z_dim + j] = mean + exp(log_sigma) * tn_eps ; zc[b, :z_dim] = z ; *kl_sum += KL terms.
  * bwd: dms = lrelu'(ms) * ( [dc | dc*eps*exp(ls)] + kl_scale * [mean | exp(2 ls) - 1] ),
  *      kl_scale = kl_coeff / (global_batch * ce). */
-int t2i_ca_fwd(const void* ms, long long ms_ps, const float* z, const float* tn_eps, void* zc, long long zc_ps,
+int t2i_ca_fwd(const float* ms, const float* z, const float* tn_eps, void* zc, long long zc_ps,
                int np, int b, int z_dim, int ce, float* kl_sum, void* stream);
-int t2i_ca_bwd(const void* ms, long long ms_ps, const void* dzc, long long dzc_ps, const float* tn_eps,
+int t2i_ca_bwd(const float* ms, const void* dzc, long long dzc_ps, const float* tn_eps,
                void* dms, long long dms_ps, int np, int b, int z_dim, int ce, float kl_scale, void* stream);
 
 /* Scalars of the two runs (model.py:79-92,100).  The per-rank sums live at the tail of the flat

@@ -67,6 +67,34 @@ class View:
             w[1].copy_((v - hi.float()).to(torch.bfloat16))
 
 
+class ImgPatches:
+    """kernels.ImgPatches: the 4x4 / s2 SAME patch matrix of an fp32 NHWC 3-channel image, as a conv_gemm operand"""
+
+    def __init__(self, img, planes_like=None):
+        self.img, self.np = img, None
+        self.n, self.H, self.W, self.c = img.shape[0], img.shape[1], img.shape[2], 48
+        self.planes_like = planes_like      # the planes tensor (weights / other operand) that fixes np and the storage type
+
+    def values(self):
+        """[n, h/2, w/2, 48], column (kh*4 + kw)*3 + c.  The kernel forms the patches as bf16 planes on chip: the image
+        values the tensor core sees are bf16(x) (np = 1) or bf16(x) + bf16(x - bf16(x)) (np = 2)."""
+        n, h, w, _ = self.img.shape
+        x = self.img.double()
+        ref = self.planes_like
+        if ref is not None and ref.dtype == torch.bfloat16:
+            x32 = self.img.float()
+            hi = x32.to(torch.bfloat16).float()
+            x = hi.double()
+            if ref.shape[0] == 2:
+                x = x + (x32 - hi).to(torch.bfloat16).double()
+        xp = F.pad(x, (0, 0, 1, 1, 1, 1))
+        out = torch.zeros(n, h // 2, w // 2, 48, dtype=torch.float64)
+        for kh in range(4):
+            for kw in range(4):
+                out[..., (kh * 4 + kw) * 3:(kh * 4 + kw) * 3 + 3] = xp[:, kh:kh + h:2, kw:kw + w:2, :]
+        return out
+
+
 def _conv_core(mode, k, flip, x, w):
     """x [N,H,W,Ci] fp64, w [taps, Co, Ci] fp64 -> y [N,OH,OW,Co]"""
     xc = x.permute(0, 3, 1, 2)
@@ -90,12 +118,17 @@ def _conv_core(mode, k, flip, x, w):
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
               algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
               stat_c=0, w_n0=0):
+    if isinstance(x, ImgPatches):
+        x.planes_like = w
     xv = x.values()
     wv = val(w)
     if w_kn:
         wv = wv.transpose(1, 2)
     wv = wv[:, w_n0:w_n0 + y.c, :xv.shape[-1]]
-    v = _conv_core(mode, k, flip, xv, wv)
+    if isinstance(x, ImgPatches):      # one contraction block of 48 per output pixel
+        v = torch.einsum("nhwk,ok->nhwo", xv, wv[0])
+    else:
+        v = _conv_core(mode, k, flip, xv, wv)
     if bias is not None:
         v = v + bias.double()[:y.c]
     if add is not None:
@@ -128,6 +161,51 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
     y = _conv_core(mode, k, 0, xv, w)
     (g,) = torch.autograd.grad((y * dyv).sum(), [w])
     dw[:, :g.shape[1], :g.shape[2]] += g
+
+
+def wgrad_img(img, other, dw, img_side):
+    pv = ImgPatches(img, other.t).values().reshape(-1, 48)
+    ov = other.values().reshape(-1, other.c)
+    if img_side == 1:
+        dw[0, :other.c, :48] += ov.t() @ pv
+    else:
+        dw[0, :48, :other.c] += pv.t() @ ov
+
+
+def deconv_img(a, w, out, bias3=None, w_kn=False, w9=None, b9=None, img=None):
+    av = a.values()
+    wv = val(w)[0]
+    if w_kn:
+        wv = wv.t()
+    col = torch.einsum("nhwk,ok->nhwo", av, wv[:, :av.shape[-1]])        # [n, h, w, 64], 48 used
+    n, h, wd, _ = av.shape
+    acc = torch.zeros(n, 2 * h + 2, 2 * wd + 2, 3, dtype=torch.float64)
+    for kh in range(4):
+        for kw in range(4):
+            acc[:, kh:kh + 2 * h:2, kw:kw + 2 * wd:2, :] += col[..., (kh * 4 + kw) * 3:(kh * 4 + kw) * 3 + 3]
+    o = acc[:, 1:2 * h + 1, 1:2 * wd + 1, :]
+    if bias3 is not None:
+        o = o + bias3.double()
+    out.copy_(o)
+    if w9 is not None:
+        wk = w9.double().view(3, 3, 3, 3).permute(3, 2, 0, 1)
+        v = F.conv2d(out.double().permute(0, 3, 1, 2), wk, b9.double(), padding=1)
+        img.copy_(torch.tanh(v).permute(0, 2, 3, 1))
+
+
+def dense_f32(x, w, bias, y, act=ACT_NONE):
+    v = x.double() @ w.double().t()
+    if bias is not None:
+        v = v + bias.double()
+    if act == ACT_LRELU:
+        v = torch.maximum(v, 0.2 * v)
+    elif act == ACT_RELU:
+        v = torch.relu(v)
+    y.copy_(v)
+
+
+def scale_rows(src, row_scale, dst):
+    dst.copy_(src.double() * row_scale.double().view(-1, *([1] * (src.dim() - 1))))
 
 
 def to_planes(src, dst, row_scale=None):
@@ -338,7 +416,7 @@ def gp_penalty(grad, weight, inv_global_batch, slope, coef, pen_sum):
 
 def ca_fwd(ms, z, tn_eps, zc, kl_sum):
     ce = tn_eps.shape[1]
-    m = val(ms)
+    m = ms.double()                       # fp32 tensor (dense_f32)
     mean, ls = m[:, :ce], m[:, ce:]
     c = mean + torch.exp(ls) * tn_eps.double()
     put(zc, torch.cat([z.double(), c], 1))
@@ -348,7 +426,7 @@ def ca_fwd(ms, z, tn_eps, zc, kl_sum):
 
 def ca_bwd(ms, dzc, tn_eps, dms, z_dim, kl_scale):
     ce = tn_eps.shape[1]
-    m = val(ms)
+    m = ms.double()
     mean, ls = m[:, :ce], m[:, ce:]
     dc = val(dzc)[:, z_dim:]
     dmean = (dc + kl_scale * mean) * torch.where(mean > 0, 1.0, 0.2)

@@ -202,12 +202,12 @@ def test_properties_at_bench_size():
     assert torch.equal(big[:128], a)                                      # bit-exact: batch-independent tiles
     fd = feed_dict(m, f, "tn_eps")
     fd[m.epsilon] = torch.zeros(256, 1, 1, 1)
-    m.run([m.D_optim, m.kt_optim, m.D_loss], fd)
-    assert torch.equal(eng.d["img"][768:], eng.d["img"][256:512])          # x_hat == x
+    xh = m.run([m.D_optim, m.kt_optim, m.D_loss, m.x_hat], fd)[3]
+    assert np.array_equal(xh, eng.d["img"][256:512].cpu().numpy())         # x_hat == x
     kt0 = float(eng.kt.item())
     fd[m.epsilon] = torch.ones(256, 1, 1, 1)
-    d_loss = m.run([m.D_optim, m.kt_optim, m.D_loss], fd)[2]
-    assert torch.equal(eng.d["img"][768:], eng.d["img"][:256])             # x_hat == G
+    d_loss, xh = m.run([m.D_optim, m.kt_optim, m.D_loss, m.x_hat], fd)[2:]
+    assert np.array_equal(xh, eng.d["img"][:256].cpu().numpy())            # x_hat == G
     sc = eng.scalars_dict()
     assert np.isfinite(d_loss) and all(np.isfinite(v) for v in sc.values())
     assert abs(float(eng.kt.item()) - (kt0 - 1e-3 * sc["kt_grad"])) < 1e-6

@@ -31,7 +31,8 @@ class ConvGemmDesc(C.Structure):
                 ("w_layout", C.c_int),
                 ("y", Act), ("bias", C.c_void_p), ("add", Act), ("mask", Act), ("act", C.c_int),
                 ("mask_kind", C.c_int), ("stat_sum", C.c_void_p), ("stat_sq", C.c_void_p), ("stat_dot", C.c_void_p),
-                ("stat_x", Act), ("stat_n", C.c_int), ("stat_c", C.c_int), ("w_n0", C.c_int)]
+                ("stat_x", Act), ("stat_n", C.c_int), ("stat_c", C.c_int), ("w_n0", C.c_int),
+                ("x_img", C.c_void_p)]
 
 
 class WgradDesc(C.Structure):
@@ -71,8 +72,12 @@ SIGNATURES = {
     "t2i_dout_bwd_weight": [_P, _LL, _I, _P, _P, _P, _I, _I, _I, _P],
     "t2i_gp_interp": [_P, _P, _P, _P, _I, _I, _P],
     "t2i_gp_penalty": [_P, _I, _I, _F, _F, _P, _P, _P, _P],
-    "t2i_ca_fwd": [_P, _LL, _P, _P, _P, _LL, _I, _I, _I, _I, _P, _P],
-    "t2i_ca_bwd": [_P, _LL, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _F, _P],
+    "t2i_ca_fwd": [_P, _P, _P, _P, _LL, _I, _I, _I, _I, _P, _P],
+    "t2i_ca_bwd": [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _F, _P],
+    "t2i_deconv_img": [C.POINTER(Act), _P, _LL, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
+    "t2i_wgrad_img": [_P, _I, _I, _I, C.POINTER(Act), _I, _I, _P, _I, _I, _P],
+    "t2i_dense_f32": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
+    "t2i_scale_rows": [_P, _P, _P, _LL, _I, _P],
     "t2i_d_seeds": [_P, _P, _I, _F, _P],
     "t2i_d_sums": [_P, _I, _P, _P],
     "t2i_d_scalars": [_P, _P, _P, _I, _F, _F, _P],

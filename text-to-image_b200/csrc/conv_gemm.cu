@@ -25,6 +25,8 @@ namespace t2i {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kThreads = 320;                  // 2 control warps + 8 epilogue warps
+constexpr int kImgProducers = 64;              // A_IMG: two more warps assemble the patch rows of the A tile
+constexpr int kThreadsImg = kThreads + kImgProducers;
 constexpr int kEpiThreads = 256;
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSubBytes = kBlockM * 64 * 2;     // one 128-pixel x 64-channel bf16 sub-tile = 16 KB
@@ -64,6 +66,10 @@ struct alignas(64) ConvGemmParams {
     int last_k_steps;          // 16-channel MMA steps of the LAST K chunk (input channels beyond x.c are zero fill: skipped)
     int stat_acc;              // channels of per-CTA shared accumulators (flushed once at the end), 0 = none
     int dbg;                   // T2I_STAT_DBG bit field (tools/bench_conv.py): skip parts of the statistics path
+    // A_IMG: the A operand is the 4x4 / stride-2 patch matrix of this fp32 NHWC 3-channel image (row = output pixel,
+    // column (kh*4 + kw)*3 + c, 48 columns), assembled in shared memory by two producer warps -- never in HBM
+    const float* img;
+    int img_h, img_w;
 };
 
 // Column totals of a 32 x 32 block held one row per lane, 32 values per lane: after the five folds lane l
@@ -130,8 +136,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int 
 //               weights serve the input-gradient convolutions, no transposed copy exists.
 // STATS = true adds the per-channel statistics of the epilogue (a separate instantiation so that plain
 // launches keep the lean epilogue).
-template <int BLOCK_N, bool B_KN, bool CTA2, bool STATS>
-__global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
+// A_IMG = true (single CTA, BLOCK_N = 128): the 3-channel ends.  One K block of 48 (= 3 MMA steps) per tile and pass;
+// warp 0 fetches only the weights, warps 10-11 stage the 2*bp + 2 image rows of the tile in shared memory (coalesced
+// 16-byte loads, zero rows = SAME padding) and write each pixel's 48 patch values as bf16 into the 128B-swizzled
+// K-major A tile (fence.proxy.async, then they arrive on the stage's full barrier next to the weight TMA).
+template <int BLOCK_N, bool B_KN, bool CTA2, bool STATS, bool A_IMG = false>
+__global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
+    static_assert(!A_IMG || (!CTA2 && BLOCK_N == 128), "the image-patch producer exists for single-CTA 128-wide tiles");
     constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;     // weight rows (output channels) staged by this CTA
     constexpr int kBBytes = kBRows * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
@@ -152,7 +163,8 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
     float* s_bias = reinterpret_cast<float*>(s_sx + (prm.has_sx ? D * np * kSubBytes : 0));
     float* s_stat = s_bias + BLOCK_N;               // STATS: [2 statistics][2 column halves][4 lane quarters][32]
     float* s_acc = s_stat + (STATS ? 512 : 0);      // STATS: per-CTA running totals [2][stat_acc] (0 = straight to global)
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_acc + (STATS ? 2 * prm.stat_acc : 0));
+    float* s_img = s_acc + (STATS ? 2 * prm.stat_acc : 0);   // A_IMG: [2*bp + 2][img_w * 3] staged image rows
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_img + (A_IMG ? (2 * prm.bp + 2) * prm.img_w * 3 : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -167,7 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
         for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.a_maps[i]);
         tma_prefetch_desc(&prm.b_map);
         for (int i = 0; i < n_stages; ++i) {
-            mbar_init(&full_bar[i], kPair);     // one arrival per producer of the pair (used in the leader)
+            mbar_init(&full_bar[i], A_IMG ? 1 + kImgProducers : kPair);   // one arrival per producer (pair: in the leader)
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -212,7 +224,17 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                             mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                             uint8_t* sa = smem + stage * kStageBytes;
                             const int brow = prm.w_n0 + tc.ct * BLOCK_N + rank * kBRows;   // this CTA's slice of the weight tile
-                            if (!CTA2) {
+                            if (A_IMG) {       // the weights only; the A tile comes from the producer warps
+                                mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
+                                if (!B_KN) {
+                                    tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, brow, tap.wtap, pb);
+                                } else {
+#pragma unroll
+                                    for (int a = 0; a < kBRows / 64; ++a)
+                                        tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes + a * 8192, brow + a * 64,
+                                                    kc * kBlockK, tap.wtap, pb);
+                                }
+                            } else if (!CTA2) {
                                 mbar_arrive_expect_tx(&full_bar[stage], kStageBytes);
                                 tma_load_5d(&prm.a_maps[tap.map], &full_bar[stage], sa, kc * kBlockK, tc.q0 + tap.dq,
                                             tc.p0 + tap.dp, tc.n0, pa);
@@ -293,7 +315,68 @@ __global__ void __launch_bounds__(kThreads, 1) conv_gemm_kernel(const __grid_con
                 }
             }
         }
-    } else {
+    } else if (A_IMG && warp >= 10) {
+        // ------------------------------------------------ image-patch producers (64 threads, two tile rows each)
+        const int pt = threadIdx.x - kThreads;
+        const int iw3 = prm.img_w * 3, iw3q = iw3 >> 2;
+        const int n_rows = 2 * prm.bp + 2;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride) {
+            const TileCoord tc = decode_tile(prm, tile, 1, 0);
+            named_bar_sync(3, kImgProducers);                  // the previous tile's patch rows have been read
+            const float* base = prm.img + static_cast<long long>(tc.n0) * prm.img_h * iw3;
+            const int ih0 = 2 * tc.p0 - 1;
+            for (int i = pt; i < n_rows * iw3q; i += kImgProducers) {
+                const int r = i / iw3q, c4 = i - r * iw3q;
+                const int ih = ih0 + r;
+                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (ih >= 0 && ih < prm.img_h) v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(ih) * iw3) + c4);
+                reinterpret_cast<float4*>(s_img)[i] = v;
+            }
+            named_bar_sync(3, kImgProducers);
+            for (int pass = 0; pass < prm.n_pass; ++pass) {
+                const bool lo_plane = (pass == 1);             // A plane: hi, lo, hi
+                mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
+                uint8_t* sa = smem + stage * kStageBytes;
+#pragma unroll 1
+                for (int half_r = 0; half_r < 2; ++half_r) {
+                    const int row = pt + half_r * kImgProducers;
+                    const int q = tc.q0 + (row & (prm.bq - 1)), pl = row >> prm.lg_bq;   // bn == 1: rows = (pl, q)
+                    uint8_t* dst = sa + (row >> 3) * 1024 + (row & 7) * 128;
+#pragma unroll
+                    for (int chunk = 0; chunk < 6; ++chunk) {
+                        float v[8];
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            const int colj = chunk * 8 + j;
+                            const int kh = colj / 12, rem = colj - kh * 12;     // rem = kw*3 + c
+                            const int x0 = (2 * q - 1) * 3 + rem;               // float index inside the image row
+                            v[j] = (x0 >= 0 && x0 < iw3) ? s_img[(2 * pl + kh) * iw3 + x0] : 0.f;
+                        }
+                        uint4 hi;
+                        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                        if (lo_plane) {
+                            uint4 lo;
+                            lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
+                            lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
+                            lo.z = pack_bf16x2(v[4] - bf16_lo(hi.z), v[5] - bf16_hi(hi.z));
+                            lo.w = pack_bf16x2(v[6] - bf16_lo(hi.w), v[7] - bf16_hi(hi.w));
+                            hi = lo;
+                        }
+                        *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) * 16)) = hi;
+                    }
+                }
+                fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
+                mbar_arrive(&full_bar[stage]);
+                if (++stage == n_stages) {
+                    stage = 0;
+                    phase ^= 1;
+                }
+            }
+        }
+    } else if (!A_IMG || warp < 10) {
         // ------------------------------------------------ epilogue warps (256 threads: thread <-> tile row x column half)
         const int quarter = warp & 3;
         const int half = (warp - 2) >> 2;             // which 32 of the 64 columns of a sub-tile
@@ -658,12 +741,22 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     ConvGemmParams prm;
     memset(&prm, 0, sizeof(prm));
-    int rc = build_taps(d->mode, d->k, d->flip, &prm.tt);
-    if (rc != T2I_OK) return rc;
+    const bool a_img = d->x_img != nullptr;
+    int rc = T2I_OK;
+    if (a_img) {
+        // the image form: ONE contraction block of 48 = (kh, kw, c) per output pixel; the weights are [1][rows][cols]
+        if (d->mode != T2I_CONV_K4S2 || d->k != 4 || d->flip != 0)
+            return fail(T2I_ERR_BAD_ARG, "x_img goes with mode T2I_CONV_K4S2, k = 4");
+        prm.tt.n_phases = 1; prm.tt.taps_per_phase = 1; prm.tt.n_maps = 0;
+    } else {
+        rc = build_taps(d->mode, d->k, d->flip, &prm.tt);
+        if (rc != T2I_OK) return rc;
+    }
     if (d->np != 1 && d->np != 2) return fail(T2I_ERR_BAD_ARG, "np must be 1 or 2");
     const t2i_act& x = d->x;
     const t2i_act& y = d->y;
-    if (x.ptr == nullptr || y.ptr == nullptr || d->w == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
+    if ((x.ptr == nullptr && !a_img) || y.ptr == nullptr || d->w == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
+    if (a_img && (x.c != 48 || x.w % 4 != 0)) return fail(T2I_ERR_BAD_ARG, "x_img: x.c must be 48 and the width a multiple of 4");
     // weight matrix per tap: w_rows x w_cols, cols contiguous.  NK: rows = output channels, cols = contraction;
     // KN: rows = contraction, cols = output channels.
     const bool kn = d->w_layout == T2I_W_KN;
@@ -718,13 +811,14 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     // halves the MMA work of the 128-wide one.  With MN-major weights a CTA pair would stage half a 64-channel
     // atom per CTA, so those launches stay single-CTA.
     static const bool allow_n64 = [] { const char* e = getenv("T2I_CONV_N64"); return !(e && e[0] == '0'); }();
-    const bool small_n = allow_n64 && y.c <= 64;
-    const bool cta2 = allow_cta2 && prm.tiles_m >= 2 && !(small_n && kn);
+    const bool small_n = allow_n64 && y.c <= 64 && !a_img;
+    const bool cta2 = allow_cta2 && prm.tiles_m >= 2 && !(small_n && kn) && !a_img;
+    if (a_img && prm.bn != 1) return fail(T2I_ERR_BAD_ARG, "x_img needs at least 128 output pixels per image (got %d x %d)", prm.P, prm.Q);
     const int units_m = cta2 ? ceil_div(prm.tiles_m, 2) : prm.tiles_m;     // schedulable pixel tiles (pairs)
     const int workers = cta2 ? sms / 2 : sms;                              // CTAs or CTA pairs
     int block_n = small_n ? 64 : 128;
-    if (y.c > 128 && (long long)prm.tt.n_phases * units_m * ceil_div(y.c, 256) >= workers) block_n = 256;
-    {   // tools/bench_conv.py: force the channel tile (development aid)
+    if (y.c > 128 && (long long)prm.tt.n_phases * units_m * ceil_div(y.c, 256) >= workers && !a_img) block_n = 256;
+    if (!a_img) {   // tools/bench_conv.py: force the channel tile (development aid)
         const char* e = getenv("T2I_CONV_BN");
         if (e && atoi(e) == 256 && y.c > 128) block_n = 256;
         if (e && atoi(e) == 128 && !small_n) block_n = 128;
@@ -753,7 +847,11 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         prm.dbg = e ? atoi(e) : 0;
         if (prm.dbg & 8) prm.stat_acc = 0;
     }
-    const int tail_bytes = block_n * 4 + (stats ? 2048 + 8 * prm.stat_acc : 0) + 256;   // bias, statistics, barriers
+    prm.img = d->x_img;
+    prm.img_h = x.h;
+    prm.img_w = x.w;
+    const int img_bytes = a_img ? (2 * prm.bp + 2) * x.w * 3 * 4 : 0;
+    const int tail_bytes = block_n * 4 + (stats ? 2048 + 8 * prm.stat_acc : 0) + img_bytes + 256;   // bias, statistics, image rows, barriers
     int stages = (kSmemBudget - epi_bytes - tail_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return fail(T2I_ERR_BAD_ARG, "shared memory plan leaves %d pipeline stages", stages);
@@ -761,8 +859,10 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const int smem_bytes = stages * stage_bytes + epi_bytes + tail_bytes + 1024;
 
     const bool parity_in = d->mode == T2I_CONV_K4S2, parity_out = d->mode == T2I_DECONV_K4S2;
-    rc = make_act_maps(x, parity_in, d->np, prm.bq, prm.bp, prm.bn, prm.a_maps);
-    if (rc != T2I_OK) return rc;
+    if (!a_img) {
+        rc = make_act_maps(x, parity_in, d->np, prm.bq, prm.bp, prm.bn, prm.a_maps);
+        if (rc != T2I_OK) return rc;
+    }
     rc = make_act_maps(y, parity_out, d->np, prm.bq, prm.bp, prm.bn, prm.out_maps);
     if (rc != T2I_OK) return rc;
     if (prm.has_add) {
@@ -784,7 +884,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         if (rc != T2I_OK) return rc;
     }
     {
-        const int taps = (d->mode == T2I_CONV_S1) ? d->k * d->k : 16;
+        const int taps = a_img ? 1 : (d->mode == T2I_CONV_S1) ? d->k * d->k : 16;
         const uint64_t e = 2;
         const uint64_t plane_bytes = (d->np == 2) ? (uint64_t)d->w_plane_stride * e : (uint64_t)taps * d->w_rows * d->w_cols * e;
         const uint64_t dims[4] = {(uint64_t)d->w_cols, (uint64_t)d->w_rows, (uint64_t)taps, (uint64_t)d->np};
@@ -814,6 +914,20 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         conv_gemm_kernel<128, false, true, true>,   conv_gemm_kernel<128, true, true, true>,
         conv_gemm_kernel<256, false, true, true>,   conv_gemm_kernel<256, true, true, true>,
         conv_gemm_kernel<64, false, true, true>,    nullptr};
+    if (a_img) {
+        static bool img_attr_done[4] = {};
+        const KernelFn img_fns[4] = {conv_gemm_kernel<128, false, false, false, true>, conv_gemm_kernel<128, true, false, false, true>,
+                                     conv_gemm_kernel<128, false, false, true, true>, conv_gemm_kernel<128, true, false, true, true>};
+        const int iv = (stats ? 2 : 0) + (kn ? 1 : 0);
+        if (!img_attr_done[iv]) {
+            cudaError_t e = cudaFuncSetAttribute(img_fns[iv], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+            if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+            img_attr_done[iv] = true;
+        }
+        cudaError_t le = launch_pdl(img_fns[iv], grid, kThreadsImg, smem_bytes, stream, prm, 1);
+        if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "conv_gemm_kernel (image patches) launch: %s", cudaGetErrorString(le));
+        return check_launch("conv_gemm_kernel");
+    }
     if (fns[variant] == nullptr) return fail(T2I_ERR_BAD_ARG, "no kernel variant %d", variant);
     if (!attr_done[variant]) {
         cudaError_t e = cudaFuncSetAttribute(fns[variant], cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);

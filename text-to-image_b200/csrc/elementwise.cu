@@ -37,6 +37,20 @@ __global__ void from_planes_kernel(const bf16* __restrict__ src, long long ps, i
     }
 }
 
+// dst[r][:] = row_scale[r] * src[r][:] (fp32; the gradient-penalty tangent seed: coef[n] * dD/dx_hat[n], model.py:62-65)
+__global__ void scale_rows_kernel(const float* __restrict__ src, const float* __restrict__ row_scale, float* dst, long long rows,
+                                  int cols) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const long long n4 = rows * cols / 4;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n4; i += (long long)gridDim.x * blockDim.x) {
+        const float sc = row_scale[i * 4 / cols];
+        float4 v = *reinterpret_cast<const float4*>(src + i * 4);
+        v.x *= sc; v.y *= sc; v.z *= sc; v.w *= sc;
+        *reinterpret_cast<float4*>(dst + i * 4) = v;
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // 3-channel 4x4/s2 patch matrix.  Row r = (n, p, q) of the (h/2 x w/2) grid, column
 // (kh*4 + kw)*3 + c holds img[n, 2p-1+kh, 2q-1+kw, c] (zero outside); columns 48..63 are zero.
@@ -897,7 +911,8 @@ __global__ void gp_penalty_kernel(const float* __restrict__ grad, int per_sample
 
 // ------------------------------------------------------------------------------------------
 // conditioning augmentation
-__global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, const float* __restrict__ z,
+// ms = [mean | log_sigma] is an fp32 tensor (t2i_dense_f32): log_sigma feeds exp(), see img_gemm.cu
+__global__ void ca_fwd_kernel(const float* __restrict__ ms, const float* __restrict__ z,
                               const float* __restrict__ tn, bf16* zc, long long zc_ps, int np, int b, int z_dim, int ce,
                               float* kl_sum) {
     pdl_launch_dependents();
@@ -914,8 +929,8 @@ __global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
             v = z[row * z_dim + col];
         } else {
             const int j = col - z_dim;
-            const float mean = load1(ms + row * 2 * ce + j, ms_ps, np);
-            const float ls = load1(ms + row * 2 * ce + ce + j, ms_ps, np);
+            const float mean = ms[row * 2 * ce + j];
+            const float ls = ms[row * 2 * ce + ce + j];
             v = mean + expf(ls) * tn[row * ce + j];
             kl += -ls + 0.5f * (-1.f + expf(2.f * ls) + mean * mean);
         }
@@ -924,7 +939,7 @@ __global__ void ca_fwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
     const float t = block_sum(kl, sh);
     if (threadIdx.x == 0 && kl_sum != nullptr) atomicAdd(kl_sum, t);
 }
-__global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, const bf16* __restrict__ dzc, long long dzc_ps,
+__global__ void ca_bwd_kernel(const float* __restrict__ ms, const bf16* __restrict__ dzc, long long dzc_ps,
                               const float* __restrict__ tn, bf16* dms, long long dms_ps, int np, int b, int z_dim, int ce,
                               float kl_scale) {
     pdl_launch_dependents();
@@ -934,8 +949,8 @@ __global__ void ca_bwd_kernel(const bf16* __restrict__ ms, long long ms_ps, cons
          i += (long long)gridDim.x * blockDim.x) {
         const int j = (int)(i % ce);
         const long long row = i / ce;
-        const float mean = load1(ms + row * 2 * ce + j, ms_ps, np);
-        const float ls = load1(ms + row * 2 * ce + ce + j, ms_ps, np);
+        const float mean = ms[row * 2 * ce + j];
+        const float ls = ms[row * 2 * ce + ce + j];
         const float dc = load1(dzc + row * width + z_dim + j, dzc_ps, np);
         float dmean = dc + kl_scale * mean;
         float dls = dc * tn[row * ce + j] * expf(ls) + kl_scale * (expf(2.f * ls) - 1.f);
@@ -1144,6 +1159,11 @@ extern "C" int t2i_from_planes(const void* src, long long ps, int np, float* dst
     if (n % 8 != 0) return fail(T2I_ERR_BAD_ARG, "from_planes: n must be a multiple of 8");
     launch_ew(from_planes_kernel, dim3(grid_for(n / 8, 256)), dim3(256), 0, STREAM, static_cast<const bf16*>(src), ps, np, dst, n);
     return check_launch("from_planes");
+}
+extern "C" int t2i_scale_rows(const float* src, const float* row_scale, float* dst, long long rows, int cols, void* stream) {
+    if (cols % 4 != 0) return fail(T2I_ERR_BAD_ARG, "scale_rows: cols=%d must be a multiple of 4", cols);
+    launch_ew(scale_rows_kernel, dim3(grid_for(rows * cols / 4, 256)), dim3(256), 0, STREAM, src, row_scale, dst, rows, cols);
+    return check_launch("scale_rows");
 }
 extern "C" int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sample_scale, void* col,
                                   long long ps, int np, void* stream) {
@@ -1363,16 +1383,16 @@ extern "C" int t2i_gp_penalty(const float* grad, int n, int per_sample, float we
     launch_ew(gp_penalty_kernel, dim3(n), dim3(256), 0, STREAM, grad, per_sample, weight, inv_global_batch, slope, coef, pen_sum);
     return check_launch("gp_penalty");
 }
-extern "C" int t2i_ca_fwd(const void* ms, long long ms_ps, const float* z, const float* tn_eps, void* zc, long long zc_ps,
+extern "C" int t2i_ca_fwd(const float* ms, const float* z, const float* tn_eps, void* zc, long long zc_ps,
                           int np, int b, int z_dim, int ce, float* kl_sum, void* stream) {
-    launch_ew(ca_fwd_kernel, dim3(grid_for((long long)b * (z_dim + ce), 256, 1)), dim3(256), 0, STREAM, 
-        static_cast<const bf16*>(ms), ms_ps, z, tn_eps, static_cast<bf16*>(zc), zc_ps, np, b, z_dim, ce, kl_sum);
+    launch_ew(ca_fwd_kernel, dim3(grid_for((long long)b * (z_dim + ce), 256, 1)), dim3(256), 0, STREAM,
+        ms, z, tn_eps, static_cast<bf16*>(zc), zc_ps, np, b, z_dim, ce, kl_sum);
     return check_launch("ca_fwd");
 }
-extern "C" int t2i_ca_bwd(const void* ms, long long ms_ps, const void* dzc, long long dzc_ps, const float* tn_eps,
+extern "C" int t2i_ca_bwd(const float* ms, const void* dzc, long long dzc_ps, const float* tn_eps,
                           void* dms, long long dms_ps, int np, int b, int z_dim, int ce, float kl_scale, void* stream) {
-    launch_ew(ca_bwd_kernel, dim3(grid_for((long long)b * ce, 256, 1)), dim3(256), 0, STREAM, 
-        static_cast<const bf16*>(ms), ms_ps, static_cast<const bf16*>(dzc), dzc_ps, tn_eps, static_cast<bf16*>(dms), dms_ps,
+    launch_ew(ca_bwd_kernel, dim3(grid_for((long long)b * ce, 256, 1)), dim3(256), 0, STREAM,
+        ms, static_cast<const bf16*>(dzc), dzc_ps, tn_eps, static_cast<bf16*>(dms), dms_ps,
         np, b, z_dim, ce, kl_scale);
     return check_launch("ca_bwd");
 }

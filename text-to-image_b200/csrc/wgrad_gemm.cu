@@ -23,6 +23,9 @@ namespace t2i {
 constexpr int kWK = 64;                       // pixels per K block
 constexpr int kWAtomBytes = kWK * 128;        // 64 pixels x 64 channels bf16 = 8 KB
 constexpr int kWThreads = 192;
+constexpr int kWImgProducers = 64;            // IMG: two more warps assemble the 64 patch rows of a K block
+constexpr int kWThreadsImg = kWThreads + kWImgProducers;
+constexpr int kWImgRowBytes = 16384;          // IMG: staged fp32 image rows ((2*bp + 2) rows of w*3 floats)
 
 // CTA2: a CTA pair (cta_group::2) computes 256 output channels x BN input channels; each CTA stages its
 // own 128 output channels of dy and HALF of the x tile, and reduces its own 128 accumulator rows.
@@ -36,9 +39,13 @@ struct WgradCfg {
     static constexpr int kStages = (kStageBytes <= 32768) ? 6 : 4;
     static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kSmemBytes = kBarOffset + 256 + 1024;
+    static constexpr int kImgOffset = kBarOffset + 256;                    // IMG variants: the image-row buffer
+    static constexpr int kSmemBytesImg = kImgOffset + kWImgRowBytes + 1024;
     static constexpr int kAccCols = MT * BN;                  // 128 or 256 columns per accumulator
     static constexpr int kTmemCols = 2 * MT * BN;             // double buffered
 };
+
+__device__ __forceinline__ void named_bar(int id, int n) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(n) : "memory"); }
 
 struct alignas(64) WgradParams {
     CUtensorMap x_maps[4];
@@ -54,12 +61,19 @@ struct alignas(64) WgradParams {
     int n_pass;
     int cout, cin;
     float* dw;
+    // IMG: one operand is the 4x4 / stride-2 patch matrix of this fp32 NHWC 3-channel image (64 columns, 48 used),
+    // assembled in shared memory (see conv_gemm.cu, A_IMG)
+    const float* img;
+    int img_h, img_w;
 };
 
-template <int MT, int BN, bool CTA2>
-__global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams prm) {
+// IMG = 1: the x operand (B) is the image patch matrix -- d_net's first conv: dw[co][(kh,kw,c)] += dy[pixel][co] * patch;
+// IMG = 2: the dy operand (A) is -- g_net's last transposed conv: dw[(kh,kw,c)][ci] += patch(d image)[pixel] * x[pixel][ci].
+template <int MT, int BN, bool CTA2, int IMG = 0>
+__global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_kernel(const __grid_constant__ WgradParams prm) {
     using Cfg = WgradCfg<MT, BN, CTA2>;
     static_assert(!CTA2 || MT == 1, "the CTA-pair variant uses one accumulator per CTA");
+    static_assert(IMG == 0 || (!CTA2 && MT == 1), "image-patch operands: single CTA, one accumulator");
     constexpr int kPair = CTA2 ? 2 : 1;
     const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
     constexpr int kStages = Cfg::kStages;
@@ -77,9 +91,10 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.x_maps[i]);
-        for (int i = 0; i < (prm.tt.n_phases > 1 ? prm.tt.n_phases : 1); ++i) tma_prefetch_desc(&prm.dy_maps[i]);
+        if (IMG != 2)      // IMG = 2: dy is the image patch matrix, there is no dy tensor map
+            for (int i = 0; i < (prm.tt.n_phases > 1 ? prm.tt.n_phases : 1); ++i) tma_prefetch_desc(&prm.dy_maps[i]);
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full_bar[i], kPair);
+            mbar_init(&full_bar[i], IMG ? 1 + kWImgProducers : kPair);
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
@@ -152,7 +167,19 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                         const int q0 = tq * prm.bq, p0 = tp * prm.bp, n0 = tn * prm.bn;
                         mbar_wait(&empty_bar[stage], phase ^ 1, 100 + stage);
                         uint8_t* sa = smem + stage * Cfg::kStageBytes;
-                        if (!CTA2) {
+                        if (IMG == 1) {            // dy by TMA; the patch atom (B) comes from the producer warps
+                            mbar_arrive_expect_tx(&full_bar[stage], a_atoms * kWAtomBytes);
+#pragma unroll
+                            for (int a = 0; a < Cfg::kM / 64; ++a)
+                                if (a < a_atoms)
+                                    tma_load_5d(dy_map, &full_bar[stage], sa + a * kWAtomBytes, co_cta + a * 64, q0, p0, n0, pa);
+                        } else if (IMG == 2) {     // x by TMA; the patch atom (A, 64 of the 128 rows) from the producer warps
+                            mbar_arrive_expect_tx(&full_bar[stage], Cfg::kBBytes);
+#pragma unroll
+                            for (int b = 0; b < Cfg::kBCols / 64; ++b)
+                                tma_load_5d(x_map, &full_bar[stage], sa + Cfg::kABytes + b * kWAtomBytes, ci_cta + b * 64,
+                                            q0 + tap.dq, p0 + tap.dp, n0, pb);
+                        } else if (!CTA2) {
                             // 64-channel atoms of dy that lie entirely beyond cout are not fetched: their accumulator
                             // rows are never written out, so whatever the shared memory holds there is harmless
                             mbar_arrive_expect_tx(&full_bar[stage], a_atoms * kWAtomBytes + Cfg::kBBytes);
@@ -226,7 +253,73 @@ __global__ void __launch_bounds__(kWThreads, 1) wgrad_gemm_kernel(const __grid_c
                 ++it;
             }
         }
-    } else {
+    } else if (IMG != 0 && warp >= 6) {
+        // image-patch producers: 64 threads, one pixel row of the K block each
+        const int pt = threadIdx.x - kWThreads;
+        float* s_img = reinterpret_cast<float*>(smem + Cfg::kImgOffset);
+        const int iw3 = prm.img_w * 3, iw3q = iw3 >> 2;
+        const int n_rows = 2 * prm.bp + 2;
+        int stage = 0;
+        uint32_t phase = 0;
+        for (int w = w0; w < prm.total_work; w += w_stride) {
+            const Work wk = decode(w);
+            for (int pass = 0; pass < prm.n_pass; ++pass) {
+                const bool lo_plane = (IMG == 1) ? (pass == 2) : (pass == 1);     // x: hi, hi, lo; dy: hi, lo, hi
+                for (int kb = wk.kb_begin; kb < wk.kb_end; ++kb) {
+                    const int tq = kb % prm.tiles_q;
+                    const int tp = (kb / prm.tiles_q) % prm.tiles_p;
+                    const int tn = kb / (prm.tiles_q * prm.tiles_p);             // bn == 1: the sample
+                    const int q0 = tq * prm.bq, p0 = tp * prm.bp;
+                    named_bar(3, kWImgProducers);                                // the previous block's rows have been read
+                    const float* base = prm.img + static_cast<long long>(tn) * prm.img_h * iw3;
+                    const int ih0 = 2 * p0 - 1;
+                    for (int i = pt; i < n_rows * iw3q; i += kWImgProducers) {
+                        const int r = i / iw3q, c4 = i - r * iw3q;
+                        const int ih = ih0 + r;
+                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+                        if (ih >= 0 && ih < prm.img_h) v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(ih) * iw3) + c4);
+                        reinterpret_cast<float4*>(s_img)[i] = v;
+                    }
+                    named_bar(3, kWImgProducers);
+                    mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
+                    uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
+                    const int q = q0 + (pt & (prm.bq - 1)), pl = pt / prm.bq;
+                    uint8_t* dst = atom + (pt >> 3) * 1024 + (pt & 7) * 128;
+#pragma unroll
+                    for (int chunk = 0; chunk < 8; ++chunk) {
+                        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
+                        if (chunk < 6) {
+                            float v[8];
+#pragma unroll
+                            for (int j = 0; j < 8; ++j) {
+                                const int colj = chunk * 8 + j;
+                                const int kh = colj / 12, rem = colj - kh * 12;
+                                const int x0 = (2 * q - 1) * 3 + rem;
+                                v[j] = (x0 >= 0 && x0 < iw3) ? s_img[(2 * pl + kh) * iw3 + x0] : 0.f;
+                            }
+                            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
+                            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
+                            if (lo_plane) {
+                                uint4 lo;
+                                lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
+                                lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
+                                lo.z = pack_bf16x2(v[4] - bf16_lo(hi.z), v[5] - bf16_hi(hi.z));
+                                lo.w = pack_bf16x2(v[6] - bf16_lo(hi.w), v[7] - bf16_hi(hi.w));
+                                hi = lo;
+                            }
+                        }
+                        *reinterpret_cast<uint4*>(dst + ((chunk ^ (pt & 7)) * 16)) = hi;    // columns 48..63: zeros
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&full_bar[stage]);
+                    if (++stage == kStages) {
+                        stage = 0;
+                        phase ^= 1;
+                    }
+                }
+            }
+        }
+    } else if (IMG == 0 || warp < 6) {
         // reduction warps: accumulator -> red.global.add into dw, while the MMAs of the next item run
         const int quarter = warp & 3;
         int it = 0;
@@ -327,9 +420,82 @@ static int launch_wgrad(const WgradParams& prm, int grid, cudaStream_t stream) {
     return check_launch("wgrad_gemm_kernel");
 }
 
+template <int BN, int IMG>
+static int launch_wgrad_img(const WgradParams& prm, int grid, cudaStream_t stream) {
+    using Cfg = WgradCfg<1, BN, false>;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t e = cudaFuncSetAttribute(wgrad_gemm_kernel<1, BN, false, IMG>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             Cfg::kSmemBytesImg);
+        if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
+        attr_done = true;
+    }
+    cudaError_t le = launch_pdl(wgrad_gemm_kernel<1, BN, false, IMG>, grid, kWThreadsImg, Cfg::kSmemBytesImg, stream, prm, 1);
+    if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "wgrad_gemm_kernel (image patches) launch: %s", cudaGetErrorString(le));
+    return check_launch("wgrad_gemm_kernel");
+}
+
 }  // namespace t2i
 
 using namespace t2i;
+
+extern "C" int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_act* other, int img_side, int np, float* dw,
+                             int cout, int cin, void* stream_) {
+    if (img == nullptr || other == nullptr || other->ptr == nullptr || dw == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
+    if (np != 1 && np != 2) return fail(T2I_ERR_BAD_ARG, "np must be 1 or 2");
+    if (img_side != 1 && img_side != 2) return fail(T2I_ERR_BAD_ARG, "img_side must be 1 (x) or 2 (dy)");
+    if ((h & 1) || (w & 3)) return fail(T2I_ERR_BAD_ARG, "wgrad_img: image %d x %d (need even height, width multiple of 4)", h, w);
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    WgradParams prm;
+    memset(&prm, 0, sizeof(prm));
+    prm.tt.n_phases = 1; prm.tt.taps_per_phase = 1; prm.tt.n_maps = 0;
+    prm.N = n; prm.P = h / 2; prm.Q = w / 2;
+    if (other->n != n || other->h != prm.P || other->w != prm.Q)
+        return fail(T2I_ERR_BAD_ARG, "wgrad_img: tensor [%d,%d,%d] does not sit on the %d x %d x %d patch grid", other->n, other->h,
+                    other->w, n, prm.P, prm.Q);
+    {
+        int q = floor_pow2(prm.Q); if (q > kWK) q = kWK;
+        int p = floor_pow2(prm.P); if (p > kWK / q) p = kWK / q;
+        prm.bq = q; prm.bp = p; prm.bn = kWK / (q * p);
+    }
+    if (prm.bn != 1 || (2 * prm.bp + 2) * w * 3 * 4 > kWImgRowBytes)
+        return fail(T2I_ERR_BAD_ARG, "wgrad_img: unsupported image extent %d x %d", h, w);
+    prm.tiles_q = ceil_div(prm.Q, prm.bq);
+    prm.tiles_p = ceil_div(prm.P, prm.bp);
+    prm.k_blocks = n * prm.tiles_p * prm.tiles_q;
+    prm.cout = cout;
+    prm.cin = cin;
+    int bnn = 64;
+    if (img_side == 1) {
+        if (cin != 64 || other->c > cout) return fail(T2I_ERR_BAD_ARG, "wgrad_img: dw must be [cout >= %d][64] (got [%d][%d])", other->c, cout, cin);
+        prm.tiles_co = ceil_div(other->c, 128);
+        prm.tiles_ci = 1;
+    } else {
+        if (cout != 64 || other->c > cin || cin % 4 != 0)
+            return fail(T2I_ERR_BAD_ARG, "wgrad_img: dw must be [64][cin >= %d] (got [%d][%d])", other->c, cout, cin);
+        bnn = other->c <= 64 ? 64 : 128;
+        prm.tiles_co = 1;
+        prm.tiles_ci = ceil_div(other->c, bnn);
+    }
+    prm.jobs = 1;
+    prm.n_pass = (np == 2) ? 3 : 1;
+    const int tiles = prm.tiles_co * prm.tiles_ci;
+    const int workers = num_sms();
+    int splits = workers / tiles;
+    if (splits > prm.k_blocks / 8) splits = prm.k_blocks / 8;
+    if (splits < 1) splits = 1;
+    prm.kb_per_split = ceil_div(prm.k_blocks, splits);
+    prm.splits = ceil_div(prm.k_blocks, prm.kb_per_split);
+    prm.dw = dw;
+    prm.img = img; prm.img_h = h; prm.img_w = w;
+    int rc = make_maps(*other, false, np, prm.bq, prm.bp, prm.bn, img_side == 1 ? prm.dy_maps : prm.x_maps);
+    if (rc != T2I_OK) return rc;
+    prm.total_work = tiles * prm.splits;
+    const int grid = prm.total_work < workers ? prm.total_work : workers;
+    if (img_side == 1) return launch_wgrad_img<64, 1>(prm, grid, stream);
+    if (bnn == 64) return launch_wgrad_img<64, 2>(prm, grid, stream);
+    return launch_wgrad_img<128, 2>(prm, grid, stream);
+}
 
 extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     if (d == nullptr) return fail(T2I_ERR_BAD_ARG, "null descriptor");

@@ -134,7 +134,7 @@ class Engine:
         S1, K4 = K.CONV_S1, K.CONV_K4S2
         d, L = "d_net/", Layer
         layers = [
-            L("h0", "col_in", d + "Conv", d + "Conv", S1, 1, 1, df, 64),
+            L("h0", "col_in", d + "Conv", d + "Conv", K4, 4, 1, df, 64),
             L("h1", "conv", d + "Conv_1", d + "Conv_1", K4, 4, 16, 2 * df, df),
             L("h2", "conv", d + "Conv_2", d + "Conv_2", K4, 4, 16, 4 * df, 2 * df),
             L("h3", "conv", d + "Conv_3", d + "Conv_3", K4, 4, 16, 8 * df, 4 * df),
@@ -475,8 +475,9 @@ class Engine:
         f32 = dict(device=self.dev, dtype=self.f32_dtype)
         planes = self._planes
         d = self.d = {}
-        d["img"] = torch.zeros(S, IMG, IMG, 3, **f32)     # [fake | real | mismatch | x_hat]
-        d["col0"] = planes(S * 1024, 64)
+        # [fake | real | mismatch | x_hat]; after the penalty seeds exist, segment 3 holds the TANGENT image
+        # coef * dD/dx_hat instead (the x_hat fetch recomputes the interpolation)
+        d["img"] = torch.zeros(S, IMG, IMG, 3, **f32)
         dshapes = {"a0": (S, 32, 32, df), "a1": (S, 16, 16, 2 * df), "a2": (S, 8, 8, 4 * df), "a3": (S, 4, 4, 8 * df),
                    "r1": (S, 4, 4, 2 * df), "r2": (S, 4, 4, 4 * df), "cat": (S, 4, 4, 8 * df + ce),
                    "a5": (S, 4, 4, 8 * df), "a6": (S, 4, 4, 8 * df)}
@@ -489,7 +490,6 @@ class Engine:
         d["logit"] = torch.zeros(S, **f32)
         d["seed"] = torch.zeros(S, **f32)
         d["gseed"] = torch.full((B,), -1.0 / self.GB, **f32)    # G_loss = -mean D(G) + ...  (model.py:92)
-        d["d_col0"] = planes(B * 1024, 64)
         d["gx"] = torch.zeros(B, IMG, IMG, 3, **f32)       # dD/d image
         d["d_cond"] = planes(B, E)
         d["g2"] = torch.zeros(B, E, **f32)                  # dD/d cond
@@ -512,9 +512,11 @@ class Engine:
         for n, sh in gshapes.items():
             g[n] = planes(*sh)
             g["d_" + n] = planes(*sh)
-        for n, sh in {"cond": (B, E), "ms": (B, 2 * ce), "zc": (B, Z + ce), "colg": (B * 1024, 64)}.items():
+        for n, sh in {"cond": (B, E), "zc": (B, Z + ce)}.items():
             g[n] = planes(*sh)
             g["d_" + n] = planes(*sh)
+        g["ms"] = torch.zeros(B, 2 * ce, **f32)            # [mean | log_sigma]: fp32 (feeds exp(), model.py:121)
+        g["d_ms"] = planes(B, 2 * ce)
         g["u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
         g["d_u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
         g["tn"] = torch.zeros(B, ce, **f32)
@@ -574,8 +576,8 @@ class Engine:
         def bn(i, x, y, **kw):
             self._bn(i, x, y, train=train, update_moving=update_moving, **kw)
 
-        K.to_planes(cond, g["cond"])
-        K.conv_gemm(S1, 1, 0, V(g["cond"]), gl["ms"].Wf, V(g["ms"]), bias=gl["ms"].b, act=K.ACT_LRELU)   # :113-114
+        self._g_cond = cond          # g_backward forms the head's weight gradient from it
+        K.dense_f32(cond, gl["ms"].w.view(2 * self.ce, self.E), gl["ms"].b, g["ms"], act=K.ACT_LRELU)   # :113-114, fp32
         if not cond_noise:
             tn_eps = torch.zeros_like(tn_eps)
         K.ca_fwd(g["ms"], z, tn_eps, g["zc"], kl_sum)                                                   # :117-122,174
@@ -597,9 +599,8 @@ class Engine:
         res("h2", "c4", "t5", 5, "u5", "c5", "t6", 6, "u6", "c6", "t7", 7, "h3")                        # :200-207
         conv("t1", "h3", "d2"); conv("c7", "d2", "t8", 8); bn(8, g["t8"], g["h4"], relu=True)            # :210-212
         conv("t2", "h4", "d3"); conv("c8", "d3", "t9", 9); bn(9, g["t9"], g["h5"], relu=True)            # :214-216
-        K.conv_gemm(S1, 1, 0, V(self._rows(g["h5"])), gl["t3"].Wf, V(g["colg"]), algo_scale=0.75)      # :218 as patches
-        K.col2im_k4s2_c3(g["colg"], g["u4"], gl["t3"].b)
-        K.conv3x3_c3_tanh_fwd(g["u4"], gl["c9"].w, gl["c9"].b, img_out)                                  # :219-221
+        # :218-221 in one kernel: transposed conv 128 -> 3 (overlap-add on chip) + bias -> u4, 3x3 conv 3 -> 3 + tanh
+        K.deconv_img(V(g["h5"]), gl["t3"].Wf, g["u4"], bias3=gl["t3"].b, w9=gl["c9"].w, b9=gl["c9"].b, img=img_out)
 
     def g_backward(self, d_img):
         """Backward of g_forward given dLoss/d image (fp32 [B,64,64,3]); fills the g gradient buffer.
@@ -655,11 +656,11 @@ class Engine:
             conv_bwd(c_a, x, "d_" + t_a, g["d_" + x], add=V(ds), **last_epi)     # skip connection joins here
 
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
-        K.im2col_k4s2_c3(g["d_u4"], g["d_colg"])
+        # the 4x4/s2 patches of d_u4 are formed on chip by both kernels (no patch matrix in HBM)
         with self._side():
-            K.wgrad_gemm(S1, 1, V(rows(g["h5"])), V(g["d_colg"]), gl["t3"].gw, algo_scale=0.75)
-        K.conv_gemm(S1, 1, 0, V(g["d_colg"]), gl["t3"].Wf, V(rows(g["d_h5"])), algo_scale=0.75, w_kn=True,
-                    mask=V(rows(g["h5"])), mask_kind=RELU, **bn_red(9, rows(g["t9"])))
+            K.wgrad_img(g["d_u4"], V(g["h5"]), gl["t3"].gw, 2)
+        K.conv_gemm(K4, 4, 0, K.ImgPatches(g["d_u4"]), gl["t3"].Wf, V(g["d_h5"]), w_kn=True,
+                    mask=V(g["h5"]), mask_kind=RELU, **bn_red(9, g["t9"]))
         bn_bwd(9, g["d_h5"], g["t9"], g["d_t9"], gl["c8"].gb)
         conv_bwd("c8", "d3", "d_t9", g["d_d3"], stat_sum=gl["t2"].gb)      # gradient at t2's output: its bias gradient
         conv_bwd("t2", "h4", "d_d3", g["d_h4"], **relu_of("h4"), **bn_red(8, g["t8"]))
@@ -683,6 +684,7 @@ class Engine:
         K.ca_bwd(g["ms"], g["d_zc"], g["tn"], g["d_ms"], self.Z, self.kl_coeff / (self.GB * self.ce))
         L = gl["ms"]
         K.colsum(V(g["d_ms"]), L.gb)
+        K.to_planes(self._g_cond, g["cond"])
         K.wgrad_gemm(S1, 1, V(g["cond"]), V(g["d_ms"]), L.gw)
         self._join()
 
@@ -701,9 +703,6 @@ class Engine:
         def V(t, **kw):
             return K.View(t, s0, n, **kw)
 
-        def R(t):   # per-pixel rows of a 32x32 tensor
-            return K.View(t, s0 * 1024, n * 1024)
-
         def cg(l, x, y, act=True, add=None):
             L = dl[l]
             kw = {}
@@ -712,13 +711,12 @@ class Engine:
                     kw = dict(mask=y, mask_kind=K.MASK_LRELU)
             else:
                 kw = dict(bias=L.b, act=K.ACT_LRELU if act else K.ACT_NONE)
-            K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, algo_scale=0.75 if l == "h0" else 1.0, **kw)
+            K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, **kw)
 
         done = after if after is not None else (lambda buf: None)   # `buf` holds its final values for this pass
-        if not tangent:
-            K.im2col_k4s2_c3(d["img"][s0:s0 + n], d["col0"][:, s0 * 1024:(s0 + n) * 1024])
-        done("col0"); done("cond")
-        cg("h0", R(d["col0"]), R(rows(d["a0"]))); done("a0")                       # :135
+        # :135 straight from the fp32 image (tangent pass: from the tangent image _d_body left in segment 3)
+        done("img"); done("cond")
+        cg("h0", K.ImgPatches(d["img"][s0:s0 + n]), V(d["a0"])); done("a0")
         cg("h1", V(d["a0"]), V(d["a1"])); done("a1")                                # :136
         cg("h2", V(d["a1"]), V(d["a2"])); done("a2")                                # :137
         cg("h3", V(d["a2"]), V(d["a3"]), act=False); done("a3")                     # :138
@@ -764,15 +762,13 @@ class Engine:
         K.conv_gemm(DC, 4, 0, V(d["d_a2"]), dl["h2"].Wf, V(d["d_a1"]), mask=V(d["a1"]), mask_kind=LR, **KN, **bias_of("h1"))
         K.conv_gemm(DC, 4, 0, V(d["d_a1"]), dl["h1"].Wf, V(d["d_a0"]), mask=V(d["a0"]), mask_kind=LR, **KN, **bias_of("h0"))
         if gn > 0:
-            K.conv_gemm(S1, 1, 0, K.View(rows(d["d_a0"]), g0 * 1024, gn * 1024), dl["h0"].Wf,
-                        K.View(d["d_col0"], 0, gn * 1024), algo_scale=0.75, **KN)
-            K.col2im_k4s2_c3(d["d_col0"], d["gx"], None)
+            K.deconv_img(K.View(d["d_a0"], g0, gn), dl["h0"].Wf, d["gx"], w_kn=True)     # transposed conv, overlap-add on chip
             if want_cond_grad:
                 K.conv_gemm(S1, 1, 0, K.View(d["d_e"], g0, gn), dl["efc"].Wf, K.View(d["d_cond"], 0, gn), **KN)
                 K.from_planes(d["d_cond"], d["g2"])
 
     # weight-gradient jobs of d_net: name -> (buffer holding the layer input, buffer holding the output gradient)
-    D_WGRAD = OrderedDict([("h0", ("col0", "d_a0")), ("h1", ("a0", "d_a1")), ("h2", ("a1", "d_a2")), ("h3", ("a2", "d_a3")),
+    D_WGRAD = OrderedDict([("h0", ("img", "d_a0")), ("h1", ("a0", "d_a1")), ("h2", ("a1", "d_a2")), ("h3", ("a2", "d_a3")),
                            ("r1", ("a3", "d_r1")), ("r2", ("r1", "d_r2")), ("r3", ("r2", "d_cat")), ("efc", ("cond", "d_e")),
                            ("h5", ("cat", "d_a5")), ("h6", ("a5", "d_a6")), ("out", ("a6", None))])
 
@@ -782,8 +778,7 @@ class Engine:
         rows = self._rows
         x, dy = self.D_WGRAD[l]
         if l == "h0":
-            K.wgrad_gemm(K.CONV_S1, 1, K.View(d["col0"], 0, n * 1024), K.View(rows(d["d_a0"]), 0, n * 1024), dl["h0"].gw,
-                         algo_scale=0.75)
+            K.wgrad_img(d["img"][:n], K.View(d["d_a0"], 0, n), dl["h0"].gw, 1)
         elif l == "out":
             K.dout_bwd_weight(d["a6"][:, :n], d["seed"][:n], dl["out"].gw, dl["out"].gb, n_bias)
         else:
@@ -948,7 +943,7 @@ class Engine:
         K.gp_penalty(d["gx"], GP_WEIGHT, inv, d["slope"], d["coef"], self.sums["d"][4:5])       # :62-65
         K.gp_penalty(d["g2"], GP_WEIGHT, inv, d["slope2"], d["coef2"], self.sums["d"][5:6])     # :67-70
         # second-order term: tangent (coef * g) through d_net, in place over the x_hat segment
-        K.im2col_k4s2_c3(d["gx"], d["col0"][:, 3 * B * 1024:], d["coef"])
+        K.scale_rows(d["gx"], d["coef"], d["img"][3 * B:])
         K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])
         with self._side():
             self.d_bias_grads(3 * B)             # first-order only (the JVP does not depend on biases)

@@ -179,7 +179,8 @@ class PgganEngine(Engine):
         top = self.stage - 1
         g = self.g = {}
         g["cond"] = self._planes(B, E)
-        self._pair(g, "ms", B, 2 * ce)
+        g["ms"] = torch.zeros(B, 2 * ce, **f32)            # [mean | log_sigma]: fp32 (feeds exp())
+        g["d_ms"] = self._planes(B, 2 * ce)
         self._pair(g, "zc", B, Z + ce)
         self._pair(g, "f0", B, 16 * n0)
         for n in ("h0", "t0a", "u0a", "t0b", "x0"):
@@ -233,8 +234,8 @@ class PgganEngine(Engine):
         S1 = K.CONV_S1
         np_, B, top = self.np, self.B, self.stage - 1
         self.ln_scratch.zero_()
-        K.to_planes(cond, g["cond"])
-        K.conv_gemm(S1, 1, 0, V(g["cond"]), gl["ms"].Wf, V(g["ms"]), bias=gl["ms"].b, act=K.ACT_LRELU)    # :343-347
+        self._g_cond = cond
+        K.dense_f32(cond, gl["ms"].w.view(2 * self.ce, self.E), gl["ms"].b, g["ms"], act=K.ACT_LRELU)    # :343-347, fp32
         if not cond_noise:
             tn_eps = torch.zeros_like(tn_eps)
         K.ca_fwd(g["ms"], z, tn_eps, g["zc"], kl_sum)                                                    # :349-354,287
@@ -318,6 +319,7 @@ class PgganEngine(Engine):
         K.ca_bwd(g["ms"], g["d_zc"], g["tn"], g["d_ms"], self.Z, self.kl_coeff / (self.GB * self.ce))
         L = gl["ms"]
         K.colsum(V(g["d_ms"]), L.gb)
+        K.to_planes(self._g_cond, g["cond"])
         K.wgrad_gemm(S1, 1, V(g["cond"]), V(g["d_ms"]), L.gw)
         self._join()
 

@@ -150,7 +150,8 @@ class StageIIEngine(Engine):
         self._pair(g, "t2", B, 16, 16, C4)
         self._pair(g, "cat", B, 16, 16, C4 + ce)
         g["cond"] = self._planes(B, E)
-        self._pair(g, "ms", B, 2 * ce)
+        g["ms"] = torch.zeros(B, 2 * ce, **f32)            # [mean | log_sigma]: fp32 (feeds exp())
+        g["d_ms"] = self._planes(B, 2 * ce)
         self._pair(g, "c", B, ce)
         self._pair(g, "t3", B, 16, 16, C4); self._pair(g, "r0", B, 16, 16, C4)
         for r in range(4):
@@ -271,8 +272,7 @@ class StageIIEngine(Engine):
         else:
             self._bn("g", g, 1, "t2", "d_t2", RELU_ACT, train=False)       # contiguous scratch, then copied into the concat buffer
             g["cat"][..., :C4].copy_(g["d_t2"])
-        K.to_planes(self.feed["cond"], g["cond"])
-        K.conv_gemm(S1, 1, 0, V(g["cond"]), gl["ms"].Wf, V(g["ms"]), bias=gl["ms"].b, act=K.ACT_LRELU)   # :64-68
+        K.dense_f32(self.feed["cond"], gl["ms"].w.view(2 * self.ce, self.E), gl["ms"].b, g["ms"], act=K.ACT_LRELU)   # :64-68, fp32
         tn = g["tn"] if cond_noise else torch.zeros_like(g["tn"])
         K.ca_fwd(g["ms"], g["z0"], tn, g["c"], kl_sum)                                           # :71-76
         K.embed_tile(g["c"], g["cat"], C4)
@@ -348,6 +348,7 @@ class StageIIEngine(Engine):
         L = gl["ms"]
         with self._side():
             K.colsum(V(g["d_ms"]), L.gb)
+            K.to_planes(self.feed["cond"], g["cond"])
             K.wgrad_gemm(S1, 1, V(g["cond"]), V(g["d_ms"]), L.gw)
         bnb(1, "d_cat", "t2", "d_t2", "e2", dy_pitch=C4 + ce)
         wgrad("e2", "a1", "d_t2")

@@ -97,6 +97,22 @@ def _prof_end(ev, kernel, tag, flops, nbytes):
         PROFILE.append([kernel, tag, flops, nbytes, ev, end])
 
 
+class ImgPatches:
+    """The 4x4 / stride-2 SAME patch matrix of an fp32 NHWC 3-channel image [n, h, w, 3] as the x operand of conv_gemm
+    (rows = pixels of the [n, h/2, w/2] grid, 48 columns (kh*4 + kw)*3 + c): it exists only in shared memory."""
+
+    def __init__(self, img):
+        assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[3] == 3
+        self.img = img
+        self.np = None          # taken from the weights
+        self.n, self.H, self.W, self.c = img.shape[0], img.shape[1], img.shape[2], 48
+
+    def _act(self):
+        a = _lib.Act()
+        a.n, a.h, a.w, a.c, a.pitch = self.n, self.H, self.W, 48, 48
+        return a
+
+
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
               algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
               stat_c=0, w_n0=0):
@@ -109,6 +125,11 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     dot with stat_x (a View on the output grid), over samples [0, stat_n) / channels [0, stat_c) (0 = all)."""
     ev = _prof_begin()
     d = _lib.ConvGemmDesc()
+    img = isinstance(x, ImgPatches)
+    if img:
+        assert mode == CONV_K4S2 and k == 4
+        x.np = w.shape[0]
+        d.x_img = x.img.data_ptr()
     d.mode, d.k, d.flip, d.np = mode, k, flip, x.np
     d.x = x._act()
     assert w.dtype == torch.bfloat16 and w.dim() == 4 and w[0].is_contiguous() and w.shape[0] == x.np
@@ -129,6 +150,11 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     _lib.call("t2i_conv_gemm", C.byref(d), _stream())
     if ev is not None:
         opix = y.n * y.H * y.W
+        if img:       # 48 = 16 taps x 3 channels per output pixel; the image is read once as fp32
+            flops = 2.0 * opix * y.c * 48 * (3 if x.np == 2 else 1)
+            nbytes = 4.0 * x.n * x.H * x.W * 3 + 2.0 * x.np * (opix * y.c * (1 + (add is not None) + (mask is not None)) + y.c * 48)
+            _prof_end(ev, "conv_gemm", "img k4s2 %dx%dx%d co%d" % (x.n, x.H, x.W, y.c), flops, nbytes)
+            return
         flops = 2.0 * opix * y.c * x.c * _taps_per_output(mode, k) * algo_scale * (3 if x.np == 2 else 1)
         nbytes = 2.0 * x.np * (x.n * x.H * x.W * x.c + opix * y.c * (1 + (add is not None) + (mask is not None))
                                + w.shape[1] * y.c * x.c)
@@ -152,6 +178,51 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
         flops = 2.0 * vpix * dy.c * x.c * taps * algo_scale * (3 if x.np == 2 else 1)
         nbytes = 2.0 * x.np * (x.n * x.H * x.W * x.c + dy.n * dy.H * dy.W * dy.c) + 4.0 * taps * dy.c * x.c
         _prof_end(ev, "wgrad_gemm", "m%d k%d %dx%dx%d ci%d co%d" % (mode, k, x.n, x.H, x.W, x.c, dy.c), flops, nbytes)
+
+
+def wgrad_img(img, other, dw, img_side):
+    """Weight gradient between the on-chip patch matrix of img (fp32 NHWC [n, h, w, 3]) and `other` (a View on the
+    [n, h/2, w/2] grid): img_side 1: dw[co, 64] += other^T patch (the image is the conv input); img_side 2:
+    dw[64, ci] += patch^T other (the image is the gradient at a transposed conv's output).  dw: fp32 [1, rows, cols]."""
+    ev = _prof_begin()
+    n, h, w, _ = img.shape
+    assert dw.dtype == torch.float32 and dw.dim() == 3 and dw.shape[0] == 1 and dw.is_contiguous()
+    a = other._act()
+    _lib.call("t2i_wgrad_img", _f32(img), n, h, w, C.byref(a), img_side, other.np, _f32(dw), dw.shape[1], dw.shape[2],
+              _stream())
+    if ev is not None:
+        pix = n * (h // 2) * (w // 2)
+        flops = 2.0 * pix * other.c * 48 * (3 if other.np == 2 else 1)
+        nbytes = 4.0 * n * h * w * 3 + 2.0 * other.np * pix * other.c + 4.0 * other.c * 48
+        _prof_end(ev, "wgrad_gemm", "img side%d %dx%dx%d c%d" % (img_side, n, h, w, other.c), flops, nbytes)
+
+
+def deconv_img(a, w, out, bias3=None, w_kn=False, w9=None, b9=None, img=None):
+    """out (fp32 NHWC [n, 2h, 2w, 3]) = bias3 + transposed 4x4/s2 conv of a (View [n, h, w, c]) with w (planes
+    [np, 1, 64, K] or, w_kn, [np, 1, K, 64]); with w9 / b9 / img also img = tanh(conv3x3(out) + b9)."""
+    ev = _prof_begin()
+    assert w.dtype == torch.bfloat16 and w.dim() == 4 and w.shape[1] == 1 and w[0].is_contiguous() and w.shape[0] == a.np
+    act = a._act()
+    _lib.call("t2i_deconv_img", C.byref(act), _p(w), w.stride(0), w.shape[2], w.shape[3], int(w_kn), a.np, _p(bias3),
+              _f32(out), _p(w9), _p(b9), _p(img), _stream())
+    if ev is not None:
+        pix = a.n * a.H * a.W
+        flops = 2.0 * pix * a.c * 48 * (3 if a.np == 2 else 1)
+        nbytes = 2.0 * a.np * pix * a.c + 4.0 * pix * 4 * 3 * (2 if img is not None else 1)
+        _prof_end(ev, "deconv_img", "%dx%dx%d c%d%s" % (a.n, a.H, a.W, a.c, " +c9" if img is not None else ""), flops, nbytes)
+
+
+def dense_f32(x, w, bias, y, act=ACT_NONE):
+    """y = act(x @ w^T + bias), all fp32; w [cout, cin]."""
+    rows, cin = x.shape
+    cout = w.shape[0]
+    assert w.shape[1] == cin and y.shape == (rows, cout) and w.is_contiguous()
+    _lib.call("t2i_dense_f32", _f32(x), rows, cin, _f32(w), _p(bias), cout, act, _f32(y), _stream())
+
+
+def scale_rows(src, row_scale, dst):
+    rows = src.shape[0]
+    _lib.call("t2i_scale_rows", _f32(src), _f32(row_scale), _f32(dst), rows, src.numel() // rows, _stream())
 
 
 def to_planes(src, dst, row_scale=None):
@@ -322,15 +393,16 @@ def gp_penalty(grad, weight, inv_global_batch, slope, coef, pen_sum):
 
 
 def ca_fwd(ms, z, tn_eps, zc, kl_sum):
+    """ms: fp32 [b, 2*ce] = [mean | log_sigma] (dense_f32)"""
     b, z_dim = z.shape
     ce = tn_eps.shape[1]
-    _lib.call("t2i_ca_fwd", _p(ms), _ps(ms), _f32(z), _f32(tn_eps), _p(zc), _ps(zc), ms.shape[0], b, z_dim, ce,
+    _lib.call("t2i_ca_fwd", _f32(ms), _f32(z), _f32(tn_eps), _p(zc), _ps(zc), zc.shape[0], b, z_dim, ce,
               _p(kl_sum), _stream())
 
 
 def ca_bwd(ms, dzc, tn_eps, dms, z_dim, kl_scale):
     b, ce = tn_eps.shape
-    _lib.call("t2i_ca_bwd", _p(ms), _ps(ms), _p(dzc), _ps(dzc), _f32(tn_eps), _p(dms), _ps(dms), ms.shape[0], b, z_dim,
+    _lib.call("t2i_ca_bwd", _f32(ms), _p(dzc), _ps(dzc), _f32(tn_eps), _p(dms), _ps(dms), dms.shape[0], b, z_dim,
               ce, kl_scale, _stream())
 
 

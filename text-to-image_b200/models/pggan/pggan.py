@@ -249,8 +249,7 @@ class PGGAN(object):
         eng.g["kl_scratch"].zero_()
         eng.g_forward(z, cond, tn, out, eng.g["kl_scratch"], cond_noise=cond_noise)
         ce = self.compr_embed_dim
-        ms = torch.empty(b, 2 * ce, device=self.device, dtype=torch.float32)
-        self._K.from_planes(eng.g["ms"], ms)
+        ms = eng.g["ms"].clone()        # fp32 [b, 2*ce] = [mean | log_sigma]
         return out, ms[:, :ce], ms[:, ce:]
 
     def discriminator(self, inp, cond, stages=None, t=None, reuse=False, alpha=None):

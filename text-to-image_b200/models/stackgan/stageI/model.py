@@ -165,8 +165,7 @@ class ConditionalGan(object):
         zp[:, :self.z_dim] = z
         eng.g["kl_scratch"].zero_()
         eng.g_forward(zp, embed, tn, out, eng.g["kl_scratch"], train=is_training, cond_noise=cond_noise)
-        ms = torch.empty(b, 2 * self.compressed_embed_dim, device=self.device, dtype=torch.float32)
-        self._K.from_planes(eng.g["ms"], ms)
+        ms = eng.g["ms"].clone()        # fp32 [b, 2*ce] = [mean | log_sigma]
         ce = self.compressed_embed_dim
         return out, ms[:, :ce], ms[:, ce:]
 

@@ -188,8 +188,7 @@ class ConditionalGan(object):
         eng.g2_forward(out, eng.g["kl_scratch"], train=is_training, cond_noise=cond_noise, update_moving=False,
                        run_stage1=False)
         ce = self.compressed_embed_dim
-        ms = torch.empty(b, 2 * ce, device=self.device, dtype=torch.float32)
-        self._K.from_planes(eng.g["ms"], ms)
+        ms = eng.g["ms"].clone()        # fp32 [b, 2*ce] = [mean | log_sigma]
         return out, ms[:, :ce], ms[:, ce:]
 
     def discriminator(self, inputs, embed, is_training=True, reuse=False):

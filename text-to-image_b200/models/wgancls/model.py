@@ -236,8 +236,7 @@ class WGanCls(object):
         out = torch.empty(b, 64, 64, 3, device=self.device, dtype=torch.float32)
         eng.g["kl_scratch"].zero_()
         eng.g_forward(z, embed, tn, out, eng.g["kl_scratch"], train=is_training, cond_noise=cond_noise)
-        ms = torch.empty(b, 2 * self.compressed_embed_dim, device=self.device, dtype=torch.float32)
-        self._K.from_planes(eng.g["ms"], ms)
+        ms = eng.g["ms"].clone()        # fp32 [b, 2*ce] = [mean | log_sigma]
         ce = self.compressed_embed_dim
         return out, ms[:, :ce], ms[:, ce:]
 
@@ -302,15 +301,19 @@ class WGanCls(object):
             # the remaining tensors of build_model (model.py:48-55) live in the engine's buffers after a D run:
             # image segments [fake | real | mismatch | x_hat] and one logit per sample of the 4B batch
             elif f.name == "x_hat":
+                # segment 3 of the image buffer holds the penalty's tangent image after a D run: recompute
+                # eps * G + (1 - eps) * x (model.py:53) from the segments / feed that are still in place
                 b = self.batch_size
-                out.append(eng.d["img"][3 * b:].cpu().numpy())
+                xh = torch.empty(b, 64, 64, 3, device=self.device, dtype=torch.float32)
+                self._K.gp_interp(eng.d["img"][:b], eng.d["img"][b:2 * b], eng.feed["epsilon"], xh)
+                out.append(xh.cpu().numpy())
             elif f.name in ("Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit"):
                 b = self.batch_size
                 k = ("Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit").index(f.name)
                 out.append(eng.d["logit"][k * b:(k + 1) * b].cpu().numpy().reshape(b, 1, 1, 1))
             elif f.name in ("embed_mean", "embed_log_sigma"):
                 ce = self.compressed_embed_dim
-                ms = eng.ms_f32()
+                ms = eng.g["ms"]
                 out.append((ms[:, :ce] if f.name == "embed_mean" else ms[:, ce:]).cpu().numpy())
             else:
                 raise KeyError("fetch '%s' is not materialised by this implementation" % f.name)
