@@ -92,6 +92,9 @@ typedef struct {
     const float* x_img;
 } t2i_conv_gemm_desc;
 int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
+/* Development aid (T2I_TIMELINE=1 in the environment): %globaltimer stamps CTA 0 of the LAST t2i_conv_gemm launch left
+ * at the hand-over points of its first 64 tiles, [tile][8 events] (csrc/conv_gemm.cu); synchronises the device. */
+int t2i_debug_timeline(unsigned long long* host_dst, int count);
 
 /* Weight gradient of the same three conv forms on tcgen05 (both operands MN-major, contraction
  * over pixels, split-K with fp32 atomic accumulation into dw, which the caller zeroes):

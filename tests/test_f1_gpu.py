@@ -115,18 +115,37 @@ def test_trainer_three_iterations_and_sampler_vs_oracle(tmp_path):
         f["tn_eps"], f["tn_eps_g"] = rec.draws[2 * it].double(), rec.draws[2 * it + 1].double()
         rd, rg = O.iteration(p, st, f, ocfg)
         log = tr.log[it]
+        # iteration 0 starts from identical weights: 2e-3.  Later iterations start from weights that differ in the few
+        # elements whose near-zero gradient took the other sign in the Adam step before (|step| ~ lr whatever |g| is);
+        # on this 8-channel net single weights move the penalty terms by a few 1e-3: 2e-2.  A wrong Adam step count,
+        # kt order or moving-average update would be O(1) here and in the weight deltas checked below.
+        tol_it = 2e-3 if it == 0 else 2e-2
         for k in ("D_loss", "D_loss_real", "D_loss_fake", "D_loss_mismatch", "wdist", "wdist2", "real_gp", "real_gp2",
                   "balance_loss", "reg_loss"):
-            assert abs(log[k] - float(rd[k])) < 2e-3 * max(1.0, abs(float(rd[k]))), (it, k, log[k], float(rd[k]))
-        assert abs(log["G_loss"] - float(rg["G_loss"])) < 2e-3 * max(1.0, abs(float(rg["G_loss"]))), (it, log["G_loss"])
+            assert abs(log[k] - float(rd[k])) < tol_it * max(1.0, abs(float(rd[k]))), (it, k, log[k], float(rd[k]))
+        assert abs(log["G_loss"] - float(rg["G_loss"])) < tol_it * max(1.0, abs(float(rg["G_loss"]))), (it, log["G_loss"])
         # the summary's kt is read in the D run that also steps it: either value is a legal TF ordering, ours is the new one
         assert abs(log["kt"] - float(st["kt"])) < 1e-5
     assert abs(float(eng.kt.item()) - float(st["kt"])) < 1e-5
     got = m.get_variables()
+    p0 = O.init_params(ocfg, 3, torch.float64)
+    worst_delta = (0.0, "")
+    for n, w in p.items():
+        if "moving_" not in n and float(st["v"][n].abs().max()) > 1e-18 and w.numel() >= 64:
+            da, db = torch.as_tensor(got[n]).double() - p0[n], w.double() - p0[n]
+            worst_delta = max(worst_delta, (rel(da, db), n))
+    print("\n[f1] three Adam steps, worst relative L2 of (weights - initial) vs the oracle: %.3f (%s)" % worst_delta)
+    assert worst_delta[0] < 0.25, worst_delta     # a step-size error (Adam t, lr_t) of 25 % or a skipped step shows here
     for n, w in p.items():
         a, b = torch.as_tensor(got[n]).double(), w.double()
-        if "moving_" in n:              # three EMA steps of the batch statistics (utils/ops.py:20-29), G runs only
+        if n.endswith("moving_variance"):   # three EMA steps of the batch statistics (utils/ops.py:20-29), G runs only
             assert rel(a, b) < 1e-3, (n, rel(a, b))
+        elif n.endswith("moving_mean"):
+            # measured against the spread of the normalised tensor: behind another BatchNorm the true channel means are
+            # ~1e-6 (beta = 0), pure cancellation noise that a relative comparison would amplify
+            spread = torch.sqrt(p[n.replace("moving_mean", "moving_variance")].double())
+            err = float((a - b).norm() / spread.norm())
+            assert err < 1e-3, (n, err)
         elif float(st["v"][n].abs().max()) > 1e-18:
             # three Adam steps of ~lr each; sign(g) decides a step, isolated near-zero gradients may go the other way
             bad = (a - b).abs() > 6e-5
@@ -180,8 +199,8 @@ def test_remaining_graph_fetches():
     ff = {k: v.float() for k, v in f.items()}
     out = m.run([m.D_optim, m.kt_optim, m.D_loss, m.G, m.x_hat, m.Dg_logit, m.Dx_logit, m.Dxmi_logit, m.Dx_hat_logit,
                  m.embed_mean, m.embed_log_sigma], feed_dict(m, ff, "tn_eps"))
-    with torch.no_grad():
-        ref = O.d_forward_losses(p, torch.tensor(O.KT_INIT, dtype=torch.float64), f, ocfg, create_graph=False)
+    ref = O.d_forward_losses(p, torch.tensor(O.KT_INIT, dtype=torch.float64), f, ocfg, create_graph=False)
+    ref = {k: v.detach() for k, v in ref.items()}
     for got, k in zip(out[3:], ["G", "x_hat", "Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit", "embed_mean",
                                 "embed_log_sigma"]):
         assert got.shape == tuple(ref[k].shape), k

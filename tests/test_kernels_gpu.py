@@ -526,7 +526,8 @@ def test_gp_ca_scalar_adam_pack_kernels(K):
     assert float(co[0]) == 0.0 and float(cog[0]) == 0.0 and float(co[1]) > 0
     for np_ in (1, 2):
         ce, zd = 16, 24
-        ms, msg_ = both(np_, (B, 2 * ce), gen, 0.5)
+        ms = torch.randn(B, 2 * ce, generator=gen) * 0.5          # fp32 [mean | log_sigma] (dense_f32)
+        msg_ = ms.cuda()
         z, tn = torch.randn(B, zd, generator=gen), torch.randn(B, ce, generator=gen)
         zc, kl = torch.zeros(np_, B, zd + ce, dtype=torch.bfloat16), torch.zeros(1)
         fk.ca_fwd(ms, z, tn, zc, kl)
@@ -535,9 +536,9 @@ def test_gp_ca_scalar_adam_pack_kernels(K):
         check_close("ca_fwd", fk.val(zcg.cpu()), fk.val(zc), *tol(np_))
         check_close("kl", klg.cpu(), kl, 1e-4, 1.0)
         dzc, dzcg = both(np_, (B, zd + ce), gen)
-        dms = torch.zeros_like(ms)
+        dms = torch.zeros(np_, B, 2 * ce, dtype=torch.bfloat16)
         fk.ca_bwd(ms, dzc, tn, dms, zd, 0.01)
-        dmsg = torch.zeros_like(ms).cuda()
+        dmsg = torch.zeros_like(dms).cuda()
         K.ca_bwd(msg_, dzcg, tn.cuda(), dmsg, zd, 0.01)
         check_close("ca_bwd", fk.val(dmsg.cpu()), fk.val(dms), *tol(np_))
         w = torch.randn(9, 40, 24, generator=gen)

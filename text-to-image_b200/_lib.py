@@ -5,7 +5,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libt2i_b200.so")
+LIB_PATH = os.environ.get("T2I_B200_LIB") or os.path.join(_HERE, "libt2i_b200.so")     # the override is a development aid
 
 CONV_S1, CONV_K4S2, DECONV_K4S2 = 0, 1, 2
 ACT_NONE, ACT_LRELU, ACT_RELU = 0, 1, 2
@@ -45,6 +45,7 @@ _P, _LL, _I, _F = C.c_void_p, C.c_longlong, C.c_int, C.c_float
 SIGNATURES = {
     "t2i_conv_gemm": [C.POINTER(ConvGemmDesc), _P],
     "t2i_wgrad_gemm": [C.POINTER(WgradDesc), _P],
+    "t2i_debug_timeline": [_P, _I],
     "t2i_to_planes": [_P, _P, _LL, _I, _LL, _I, _P, _P],
     "t2i_from_planes": [_P, _LL, _I, _P, _LL, _P],
     "t2i_im2col_k4s2_c3": [_P, _I, _I, _I, _P, _P, _LL, _I, _P],
@@ -111,6 +112,8 @@ def load():
                        "There is no CPU fallback." % LIB_PATH)
     lib = C.CDLL(LIB_PATH)
     for name, argtypes in SIGNATURES.items():
+        if os.environ.get("T2I_B200_LIB") and not hasattr(lib, name):
+            continue        # development aid: an older build without the newest entry points
         fn = getattr(lib, name)
         fn.argtypes = argtypes
         fn.restype = C.c_int

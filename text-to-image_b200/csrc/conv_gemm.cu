@@ -18,6 +18,7 @@
 // Conv2DBackpropInput, MatMul + BiasAdd + activation) for every dense contraction on the
 // wgancls path, forward and input-gradient (see include/t2i_b200.h: t2i_conv_gemm).
 #include "host_util.h"
+#include "img_patch.cuh"
 #include "ptx.cuh"
 
 namespace t2i {
@@ -25,9 +26,12 @@ namespace t2i {
 constexpr int kBlockM = 128;
 constexpr int kBlockK = 64;
 constexpr int kThreads = 320;                  // 2 control warps + 8 epilogue warps
-constexpr int kImgProducers = 64;              // A_IMG: two more warps assemble the patch rows of the A tile
-constexpr int kThreadsImg = kThreads + kImgProducers;
+// A_IMG: two or four more warps assemble the patch rows of the A tile (four where the register file allows it:
+// the STATS epilogue needs 168 registers per thread, 448 threads of that do not fit)
+__host__ __device__ constexpr int img_producers(bool stats) { return stats ? 64 : 128; }
+constexpr int kImgRing = 4;                    // A_IMG: raw image-row buffers in flight (cp.async ring, tiles ahead)
 constexpr int kEpiThreads = 256;
+constexpr int kEpiGroup = 128;                 // an epilogue group: four warps, thread <-> accumulator row
 constexpr int kABytes = kBlockM * kBlockK * 2;  // 16 KB
 constexpr int kSubBytes = kBlockM * 64 * 2;     // one 128-pixel x 64-channel bf16 sub-tile = 16 KB
 constexpr int kMaxStages = 8;
@@ -52,7 +56,9 @@ struct alignas(64) ConvGemmParams {
     int np;
     int Cout;
     int n_stages;              // mainloop pipeline depth (what fits beside the epilogue buffers)
-    int epi_depth;             // 1 or 2 staging buffers per epilogue tensor
+    int epi_depth;             // 1, 2 or 4 staging buffers per epilogue tensor and group
+    int epi_groups;            // 2: two epilogue groups; 1: group 1 idles (np = 2: shared memory)
+    int epi_split;             // 1: the groups share every tile (sub-tiles g, g + 2, ..); 0: they take alternate tiles
     int has_add, has_mask, has_sx;
     const float* bias;
     int act, mask_kind;
@@ -70,7 +76,17 @@ struct alignas(64) ConvGemmParams {
     // column (kh*4 + kw)*3 + c, 48 columns), assembled in shared memory by two producer warps -- never in HBM
     const float* img;
     int img_h, img_w;
+    // debug build + T2I_TIMELINE=1 (tools/conv_timeline.py): CTA 0 records %globaltimer at the pipeline's hand-over points of its
+    // first 64 tiles: [tile][event], events 0 weights TMA issued, 1 patch rows arrived, 2 MMA sees the stage, 3 MMA
+    // committed, 4 epilogue sees the accumulator, 5 epilogue done with the tile, 6 MMA got a free accumulator
+    unsigned long long* timeline;
 };
+#ifdef T2I_TIMELINE_BUILD     // make -C csrc EXTRA=-DT2I_TIMELINE_BUILD: a DEBUG build -- the stamps in the MMA issue loop cost 10-25 %
+#define T2I_MARK(it, ev) \
+    do { if (prm.timeline != nullptr && blockIdx.x == 0 && (it) < 64) prm.timeline[(it) * 8 + (ev)] = global_timer_ns(); } while (0)
+#else
+#define T2I_MARK(it, ev) do {} while (0)
+#endif
 
 // Column totals of a 32 x 32 block held one row per lane, 32 values per lane: after the five folds lane l
 // holds the total of column l (31 shuffles instead of 32 x 5).
@@ -137,16 +153,21 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvGemmParams& prm, int 
 // STATS = true adds the per-channel statistics of the epilogue (a separate instantiation so that plain
 // launches keep the lean epilogue).
 // A_IMG = true (single CTA, BLOCK_N = 128): the 3-channel ends.  One K block of 48 (= 3 MMA steps) per tile and pass;
-// warp 0 fetches only the weights, warps 10-11 stage the 2*bp + 2 image rows of the tile in shared memory (coalesced
+// warp 0 fetches only the weights, warps 10-11 (10-13 without STATS) stage the 2*bp + 2 image rows of the tile in shared memory (coalesced
 // 16-byte loads, zero rows = SAME padding) and write each pixel's 48 patch values as bf16 into the 128B-swizzled
 // K-major A tile (fence.proxy.async, then they arrive on the stage's full barrier next to the weight TMA).
 template <int BLOCK_N, bool B_KN, bool CTA2, bool STATS, bool A_IMG = false>
-__global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
+__global__ void __launch_bounds__(A_IMG ? kThreads + img_producers(STATS) : kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
+    constexpr int kImgProducers = img_producers(STATS);
     static_assert(!A_IMG || (!CTA2 && BLOCK_N == 128), "the image-patch producer exists for single-CTA 128-wide tiles");
     constexpr int kBRows = CTA2 ? BLOCK_N / 2 : BLOCK_N;     // weight rows (output channels) staged by this CTA
     constexpr int kBBytes = kBRows * kBlockK * 2;
     constexpr int kStageBytes = kABytes + kBBytes;
     constexpr int kPair = CTA2 ? 2 : 1;
+    // accumulator buffers in TMEM (512 columns): with four, the MMAs run up to three tiles ahead of the epilogue, which
+    // hides the commit -> wait -> load -> release handshakes of short-K tiles (they cost more than the MMAs themselves)
+    constexpr int kAccBufs = (BLOCK_N <= 128) ? 4 : 2;
     const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
     const int unit0 = blockIdx.x / kPair;                     // first tile (pair) of this CTA (pair)
     const int unit_stride = gridDim.x / kPair;
@@ -155,21 +176,25 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
     const int n_stages = prm.n_stages;
     const int D = prm.epi_depth;
     const int np = prm.np;
-    // carve-up: [stages][out D*np][add D*np][mask D*np][sx D*np][bias][stat partials][barriers]
+    // carve-up: [stages][out G*D*np][add G*D*np][mask G*D*np][sx G*D*np][bias G][stat partials G][totals G][barriers]
+    // (G = epilogue groups, each with its own staging buffers)
+    const int G = prm.epi_groups;
     uint8_t* s_out = smem + n_stages * kStageBytes;
-    uint8_t* s_add = s_out + D * np * kSubBytes;
-    uint8_t* s_mask = s_add + (prm.has_add ? D * np * kSubBytes : 0);
-    uint8_t* s_sx = s_mask + (prm.has_mask ? D * np * kSubBytes : 0);
-    float* s_bias = reinterpret_cast<float*>(s_sx + (prm.has_sx ? D * np * kSubBytes : 0));
-    float* s_stat = s_bias + BLOCK_N;               // STATS: [2 statistics][2 column halves][4 lane quarters][32]
-    float* s_acc = s_stat + (STATS ? 512 : 0);      // STATS: per-CTA running totals [2][stat_acc] (0 = straight to global)
-    float* s_img = s_acc + (STATS ? 2 * prm.stat_acc : 0);   // A_IMG: [2*bp + 2][img_w * 3] staged image rows
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_img + (A_IMG ? (2 * prm.bp + 2) * prm.img_w * 3 : 0));
+    uint8_t* s_add = s_out + G * D * np * kSubBytes;
+    uint8_t* s_mask = s_add + (prm.has_add ? G * D * np * kSubBytes : 0);
+    uint8_t* s_sx = s_mask + (prm.has_mask ? G * D * np * kSubBytes : 0);
+    float* s_bias = reinterpret_cast<float*>(s_sx + (prm.has_sx ? G * D * np * kSubBytes : 0));
+    float* s_stat = s_bias + 2 * BLOCK_N;           // STATS: per group [2 statistics][2 column halves][4 lane quarters][32]
+    float* s_acc = s_stat + (STATS ? 1024 : 0);     // STATS: per group running totals [2][stat_acc] (0 = straight to global)
+    // A_IMG: kImgRing x [2*bp + 2][img_w * 3] raw fp32 image rows (cp.async ring), then np bf16 padded row buffers
+    float* s_img = s_acc + (STATS ? 4 * prm.stat_acc : 0);
+    uint32_t* s_bf = reinterpret_cast<uint32_t*>(s_img + (A_IMG ? kImgRing * (2 * prm.bp + 2) * prm.img_w * 3 : 0));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bf + (A_IMG ? np * (2 * prm.bp + 2) * img_pitch_words(prm.img_w) : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
-    uint64_t* tmem_empty = tmem_full + 2;
-    uint64_t* aux_full = tmem_empty + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 2);
+    uint64_t* tmem_empty = tmem_full + 4;
+    uint64_t* aux_full = tmem_empty + 4;
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 4);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -182,20 +207,21 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
             mbar_init(&full_bar[i], A_IMG ? 1 + kImgProducers : kPair);   // one arrival per producer (pair: in the leader)
             mbar_init(&empty_bar[i], 1);
         }
-        for (int i = 0; i < 2; ++i) {
+        for (int i = 0; i < kAccBufs; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], kPair * (kEpiThreads / 32));   // epilogue warps of both CTAs (leader's copy)
-            mbar_init(&aux_full[i], 1);
+            // the warps that read the tile (one group, or both when they share tiles), in both CTAs (leader's copy)
+            mbar_init(&tmem_empty[i], kPair * (kEpiGroup / 32) * (prm.epi_split ? prm.epi_groups : 1));
         }
+        for (int i = 0; i < 4; ++i) mbar_init(&aux_full[i], 1);
         fence_barrier_init();
     }
     if (CTA2) cluster_sync_all();               // peer barriers exist before anything can target them
     if (warp == 1) {
         if (CTA2) {
-            tmem_alloc_2sm(tmem_slot, 2 * BLOCK_N);
+            tmem_alloc_2sm(tmem_slot, kAccBufs * BLOCK_N);
             tmem_relinquish_2sm();
         } else {
-            tmem_alloc(tmem_slot, 2 * BLOCK_N);
+            tmem_alloc(tmem_slot, kAccBufs * BLOCK_N);
             tmem_relinquish();
         }
     }
@@ -226,6 +252,7 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
                             const int brow = prm.w_n0 + tc.ct * BLOCK_N + rank * kBRows;   // this CTA's slice of the weight tile
                             if (A_IMG) {       // the weights only; the A tile comes from the producer warps
                                 mbar_arrive_expect_tx(&full_bar[stage], kBBytes);
+                                T2I_MARK((tile - unit0) / unit_stride, 0);
                                 if (!B_KN) {
                                     tma_load_4d(&prm.b_map, &full_bar[stage], sa + kABytes, kc * kBlockK, brow, tap.wtap, pb);
                                 } else {
@@ -278,15 +305,17 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
             uint32_t phase = 0;
             int it = 0;
             for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride, ++it) {
-                const int acc = it & 1;
-                const uint32_t acc_phase = (it >> 1) & 1;
+                const int acc = it & (kAccBufs - 1);
+                const uint32_t acc_phase = (it / kAccBufs) & 1;
                 mbar_wait(&tmem_empty[acc], acc_phase ^ 1, 300 + acc);
                 tc_fence_after();
+                T2I_MARK(it, 6);
                 const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
                 int kc = 0;     // K chunk inside the tap: the last one may hold fewer than 64 real input channels
                 for (int kb = 0; kb < kb_per_tile; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 200 + stage);
                     tc_fence_after();
+                    if (kb == 0) T2I_MARK(it, 2);
                     const int k_steps = (kc == prm.k_chunks - 1) ? prm.last_k_steps : kBlockK / 16;
                     if (++kc == prm.k_chunks) kc = 0;
                     const uint32_t sa = smem_u32(smem + stage * kStageBytes);
@@ -308,6 +337,7 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
                         umma_commit(&empty_bar[stage]);
                         if (kb == kb_per_tile - 1) umma_commit(&tmem_full[acc]);
                     }
+                    if (kb == kb_per_tile - 1) T2I_MARK(it, 3);
                     if (++stage == n_stages) {
                         stage = 0;
                         phase ^= 1;
@@ -318,58 +348,48 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
     } else if (A_IMG && warp >= 10) {
         // ------------------------------------------------ image-patch producers (64 threads, two tile rows each)
         const int pt = threadIdx.x - kThreads;
-        const int iw3 = prm.img_w * 3, iw3q = iw3 >> 2;
+        const int iw3 = prm.img_w * 3;
         const int n_rows = 2 * prm.bp + 2;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride) {
-            const TileCoord tc = decode_tile(prm, tile, 1, 0);
-            named_bar_sync(3, kImgProducers);                  // the previous tile's patch rows have been read
-            const float* base = prm.img + static_cast<long long>(tc.n0) * prm.img_h * iw3;
-            const int ih0 = 2 * tc.p0 - 1;
-            for (int i = pt; i < n_rows * iw3q; i += kImgProducers) {
-                const int r = i / iw3q, c4 = i - r * iw3q;
-                const int ih = ih0 + r;
-                float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                if (ih >= 0 && ih < prm.img_h) v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(ih) * iw3) + c4);
-                reinterpret_cast<float4*>(s_img)[i] = v;
+        const int img_floats = n_rows * iw3;
+        // the rows of the next kImgRing - 1 tiles stream into the ring (cp.async) while this tile's patches are assembled:
+        // one tile's work is far shorter than the memory latency.  Every iteration commits exactly one group (an empty
+        // one past the end), so "all but the newest kImgRing - 2 groups are complete" always means "this tile is in".
+        auto prefetch = [&](int tile, int buf) {
+            if (tile >= prm.total_tiles) {
+                cp_async_commit();
+                return;
             }
-            named_bar_sync(3, kImgProducers);
+            const TileCoord tn = decode_tile(prm, tile, 1, 0);
+            img_rows_prefetch(prm.img + static_cast<long long>(tn.n0) * prm.img_h * iw3, 2 * tn.p0 - 1, prm.img_h, n_rows, iw3,
+                              s_img + buf * img_floats, prm.img, pt, kImgProducers);
+            cp_async_commit();
+        };
+        int stage = 0, buf = 0;
+        uint32_t phase = 0;
+        for (int a = 0; a < kImgRing - 1; ++a) prefetch(unit0 + a * unit_stride, a);
+        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride, buf = (buf + 1) & (kImgRing - 1)) {
+            const TileCoord tc = decode_tile(prm, tile, 1, 0);
+            cp_async_wait_pending<kImgRing - 2>();
+            named_bar_sync(5, kImgProducers);     // every producer's rows of this tile are in; the oldest ring slot is free
+            prefetch(tile + (kImgRing - 1) * unit_stride, (buf + kImgRing - 1) & (kImgRing - 1));
+            const int pitchw = img_pitch_words(prm.img_w);
+            uint32_t* s_lo = (np == 2) ? s_bf + n_rows * pitchw : nullptr;
+            img_rows_convert(s_img + buf * img_floats, n_rows, iw3, s_bf, s_lo, pitchw, pt, kImgProducers);
+            named_bar_sync(5, kImgProducers);     // the bf16 rows are complete
             for (int pass = 0; pass < prm.n_pass; ++pass) {
-                const bool lo_plane = (pass == 1);             // A plane: hi, lo, hi
+                const uint32_t* plane = (pass == 1) ? s_lo : s_bf;             // A plane: hi, lo, hi
                 mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
                 uint8_t* sa = smem + stage * kStageBytes;
 #pragma unroll 1
-                for (int half_r = 0; half_r < 2; ++half_r) {
+                for (int half_r = 0; half_r < kBlockM / kImgProducers; ++half_r) {
                     const int row = pt + half_r * kImgProducers;
-                    const int q = tc.q0 + (row & (prm.bq - 1)), pl = row >> prm.lg_bq;   // bn == 1: rows = (pl, q)
-                    uint8_t* dst = sa + (row >> 3) * 1024 + (row & 7) * 128;
-#pragma unroll
-                    for (int chunk = 0; chunk < 6; ++chunk) {
-                        float v[8];
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) {
-                            const int colj = chunk * 8 + j;
-                            const int kh = colj / 12, rem = colj - kh * 12;     // rem = kw*3 + c
-                            const int x0 = (2 * q - 1) * 3 + rem;               // float index inside the image row
-                            v[j] = (x0 >= 0 && x0 < iw3) ? s_img[(2 * pl + kh) * iw3 + x0] : 0.f;
-                        }
-                        uint4 hi;
-                        hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                        hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                        if (lo_plane) {
-                            uint4 lo;
-                            lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
-                            lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
-                            lo.z = pack_bf16x2(v[4] - bf16_lo(hi.z), v[5] - bf16_hi(hi.z));
-                            lo.w = pack_bf16x2(v[6] - bf16_lo(hi.w), v[7] - bf16_hi(hi.w));
-                            hi = lo;
-                        }
-                        *reinterpret_cast<uint4*>(dst + ((chunk ^ (row & 7)) * 16)) = hi;
-                    }
+                    int q = tc.q0 + (row & (prm.bq - 1));                      // bn == 1: rows = (pl, q)
+                    if (q >= prm.Q) q = prm.Q - 1;                             // ragged tile: the row is clipped by the store
+                    img_patch_row(plane, pitchw, row >> prm.lg_bq, q, sa + (row >> 3) * 1024 + (row & 7) * 128, row, false);
                 }
                 fence_proxy_async();                           // generic-proxy writes -> visible to the tensor core
                 mbar_arrive(&full_bar[stage]);
+                if (pt == 0 && pass == 0) T2I_MARK((tile - unit0) / unit_stride, 1);
                 if (++stage == n_stages) {
                     stage = 0;
                     phase ^= 1;
@@ -377,16 +397,25 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
             }
         }
     } else if (!A_IMG || warp < 10) {
-        // ------------------------------------------------ epilogue warps (256 threads: thread <-> tile row x column half)
+        // ------------------------------------------------ epilogue: two groups of four warps (thread <-> accumulator row)
+        // Group g takes this CTA's tiles g, g + 2, ...: while one group waits for a barrier, a TMA store or an accumulator,
+        // the other one works, and every named barrier spans 128 threads.  A thread walks the 64 columns of a sub-tile
+        // as two halves of 32.
         const int quarter = warp & 3;
-        const int half = (warp - 2) >> 2;             // which 32 of the 64 columns of a sub-tile
-        const int et = threadIdx.x - 64;              // epilogue thread index
+        const int grp = (warp - 2) >> 2;
+        const int et = threadIdx.x - 64 - grp * kEpiGroup;     // thread index inside the group
         const int row = quarter * 32 + lane;
-        const bool leader = (warp == 2 && lane == 0);
+        const bool leader = (((warp - 2) & 3) == 0 && lane == 0);
+        const int bar_a = 1 + 2 * grp, bar_b = 2 + 2 * grp;     // the group's named barriers
+        if (grp < G) {
+        s_out += grp * D * np * kSubBytes; s_add += grp * D * np * kSubBytes;
+        s_mask += grp * D * np * kSubBytes; s_sx += grp * D * np * kSubBytes;
+        s_bias += grp * BLOCK_N; s_stat += grp * 512; s_acc += grp * 2 * prm.stat_acc;
+        aux_full += grp * 2;
         const bool has_aux = prm.has_add || prm.has_mask || prm.has_sx;
         const uint32_t aux_bytes = static_cast<uint32_t>((prm.has_add + prm.has_mask + prm.has_sx) * np * kSubBytes);
-        if (STATS) {   // running per-CTA totals: thread et owns channels == et mod 64 of statistic et / 64
-            for (int i = et; i < 2 * prm.stat_acc; i += kEpiThreads) s_acc[i] = 0.f;
+        if (STATS) {   // running per-group totals: thread et owns channels == et mod 64 of statistic et / 64
+            for (int i = et; i < 2 * prm.stat_acc; i += kEpiGroup) s_acc[i] = 0.f;
         }
         const int sw = row & 7;                       // 128B swizzle: 16B chunk j of row r lives at chunk j ^ (r & 7)
         const uint32_t row_off = row * 128;
@@ -394,10 +423,7 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
         // shared addresses of this thread's row in the staging tiles, and its four 16-byte chunks inside the row
         const uint32_t so_u32 = smem_u32(s_out) + row_off, sa_u32 = smem_u32(s_add) + row_off;
         const uint32_t sm_u32 = smem_u32(s_mask) + row_off, sx_u32 = smem_u32(s_sx) + row_off;
-        const uint32_t sb_u32 = smem_u32(s_bias) + static_cast<uint32_t>(half * 32) * 4;
-        uint32_t coff4[4];
-#pragma unroll
-        for (int gq = 0; gq < 4; ++gq) coff4[gq] = static_cast<uint32_t>(((half * 4 + gq) ^ sw) * 16);
+        const uint32_t sb0_u32 = smem_u32(s_bias);
 
         // aux tiles are prefetched D sub-tiles ahead along the sequence (tile, sub) this CTA will process
         auto issue_aux = [&](int tile, int sub, int buf) {
@@ -422,12 +448,20 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
             if (rem > BLOCK_N) rem = BLOCK_N;
             return (rem + 63) / 64;
         };
-        // prefetch cursor (tile, sub) runs D elements ahead of the compute cursor
-        int pf_tile = unit0, pf_sub = 0;
+        // The group's sequence of (tile, sub-tile): alternate tiles with all their sub-tiles, or (epi_split) every tile
+        // with sub-tiles grp, grp + G, ...  The aux prefetch cursor runs D elements ahead of the compute cursor.
+        const bool split = prm.epi_split != 0;
+        const int tile_step = split ? unit_stride : G * unit_stride, it_step = split ? 1 : G;
+        const int tile_first = unit0 + (split ? 0 : grp * unit_stride), it_first = split ? 0 : grp;
+        const int sub_first = split ? grp : 0, sub_step = split ? G : 1;
+        int pf_tile = tile_first, pf_sub = sub_first;
+        while (pf_tile < prm.total_tiles && pf_sub >= subs_of(pf_tile)) pf_tile += tile_step;
         auto pf_advance = [&]() {
-            if (++pf_sub >= subs_of(pf_tile)) {
-                pf_sub = 0;
-                pf_tile += unit_stride;
+            pf_sub += sub_step;
+            if (pf_sub >= subs_of(pf_tile)) {
+                pf_sub = sub_first;
+                pf_tile += tile_step;
+                while (pf_tile < prm.total_tiles && pf_sub >= subs_of(pf_tile)) pf_tile += tile_step;
             }
         };
         if (has_aux && leader) {
@@ -439,11 +473,11 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
             }
         }
 
-        int g = 0;   // running index of 64-channel sub-tiles processed by this CTA
-        int it = 0;
-        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride, ++it) {
-            const int acc = it & 1;
-            const uint32_t acc_phase = (it >> 1) & 1;
+        int g = 0;   // running index of 64-channel sub-tiles processed by this group
+        int it = it_first;
+        for (int tile = tile_first; tile < prm.total_tiles; tile += tile_step, it += it_step) {
+            const int acc = it & (kAccBufs - 1);
+            const uint32_t acc_phase = (it / kAccBufs) & 1;
             const TileCoord tc = decode_tile(prm, tile, kPair, rank);
             const int co_base = tc.ct * BLOCK_N;
             const int n_sub = subs_of(tile);
@@ -456,27 +490,45 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
             if (tile_ragged)
                 row_ok = tc.n0 + (row >> prm.lg_bqp) < prm.stat_n && tc.p0 + ((row >> prm.lg_bq) & (prm.bp - 1)) < prm.P &&
                          tc.q0 + (row & (prm.bq - 1)) < prm.Q;
+            if (leader) T2I_MARK(it, 7);
             // stage this tile's bias slice (all threads passed the previous sub-tile's second barrier)
             if (prm.bias != nullptr) {
-                for (int i = et; i < BLOCK_N; i += kEpiThreads) s_bias[i] = (co_base + i < prm.Cout) ? __ldg(prm.bias + co_base + i) : 0.f;
+                for (int i = et; i < BLOCK_N; i += kEpiGroup) s_bias[i] = (co_base + i < prm.Cout) ? __ldg(prm.bias + co_base + i) : 0.f;
             }
-            for (int sub = 0; sub < n_sub; ++sub, ++g) {
-                const int buf = (D == 2) ? (g & 1) : 0;
-                const uint32_t aux_parity = (D == 2) ? ((g >> 1) & 1) : (g & 1);
+            if (sub_first >= n_sub) {       // shared tile without a sub-tile for this group: stay in step, release it
+                mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
+                __syncwarp();
+                if (lane == 0) {
+                    if (CTA2 && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+                    else mbar_arrive(&tmem_empty[acc]);
+                }
+                continue;
+            }
+            for (int sub = sub_first; sub < n_sub; sub += sub_step, ++g) {
+                const int buf = g & (D - 1);                       // D is 1, 2 or 4
+                const uint32_t aux_parity = (D == 4) ? ((g >> 2) & 1) : (D == 2) ? ((g >> 1) & 1) : (g & 1);
                 if (leader) {   // the store that last used out[buf] must have finished reading it
-                    if (D == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
+                    if (D == 4) bulk_wait_read<3>(); else if (D == 2) bulk_wait_read<1>(); else bulk_wait_read<0>();
                 }
                 if (has_aux) mbar_wait(&aux_full[buf], aux_parity, 500 + buf);
-                named_bar_sync(1, kEpiThreads);
-                if (sub == 0) {
+                named_bar_sync(bar_a, kEpiGroup);
+                if (sub == sub_first) {
                     mbar_wait(&tmem_full[acc], acc_phase, 400 + acc);
                     tc_fence_after();
+                    if (leader) T2I_MARK(it, 4);
                 }
                 uint8_t* o_hi = s_out + (buf * np) * kSubBytes + row_off;
                 const uint8_t* a_base = s_add + (buf * np) * kSubBytes + row_off;
                 const uint8_t* m_base = s_mask + (buf * np) * kSubBytes + row_off;
                 const uint8_t* x_base = s_sx + (buf * np) * kSubBytes + row_off;
-                {
+                // the two 32-column halves of the sub-tile; without the statistics' extra registers both halves are
+                // in flight together (two independent dependency chains per warp)
+#pragma unroll(STATS ? 1 : 2)
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t sb_u32 = sb0_u32 + static_cast<uint32_t>(half * 32) * 4;
+                    uint32_t coff4[4];
+#pragma unroll
+                    for (int gq = 0; gq < 4; ++gq) coff4[gq] = static_cast<uint32_t>(((half * 4 + gq) ^ sw) * 16);
                     __syncwarp();
                     uint32_t r[32];
                     float r2[32];     // second statistic's per-element terms (only live when requested)
@@ -637,7 +689,7 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
                         }
                     }
                 }
-                if (sub == n_sub - 1) {   // accumulator fully read: hand the TMEM buffer back to the MMA warp
+                if (sub + sub_step >= n_sub) {   // accumulator fully read by this group: hand the TMEM buffer back to the MMA warp
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) {
@@ -646,8 +698,10 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
                     }
                 }
                 fence_proxy_async();      // generic-proxy smem writes -> visible to the TMA store
-                named_bar_sync(2, kEpiThreads);
-                if (tile_stats && et < 128 && !(prm.dbg & 2)) {   // (statistic, channel) totals of the sub-tile
+                if (!A_IMG && leader && sub == 0) T2I_MARK(it, 0);
+                named_bar_sync(bar_b, kEpiGroup);
+                if (!A_IMG && leader && sub == 0) T2I_MARK(it, 1);
+                if (tile_stats && !(prm.dbg & 2)) {   // (statistic, channel) totals of the sub-tile: 128 threads = 2 x 64
                     const int which = et >> 6, hc = et & 63;          // hc = column inside the 64-channel sub-tile
                     float* dst = which == 0 ? prm.stat_sum : prm.stat_second;
                     const int ch = co_base + sub * 64 + hc;
@@ -667,11 +721,12 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
                         issue_aux(pf_tile, pf_sub, buf);
                         pf_advance();
                     }
+                    if (sub + sub_step >= n_sub) T2I_MARK(it, 5);
                 }
             }
         }
         if (leader) bulk_wait_all();
-        if (STATS && prm.stat_acc > 0 && et < 128 && !(prm.dbg & 4)) {   // one global atomic per channel this CTA contributed to
+        if (STATS && prm.stat_acc > 0 && !(prm.dbg & 4)) {   // one global atomic per channel this group contributed to
             const int which = et >> 6;
             float* dst = which == 0 ? prm.stat_sum : prm.stat_second;
             if (dst != nullptr) {
@@ -681,6 +736,7 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
                 }
             }
         }
+        }   // grp < G
     }
 
     tc_fence_before();
@@ -688,8 +744,8 @@ __global__ void __launch_bounds__(A_IMG ? kThreadsImg : kThreads, 1) conv_gemm_k
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
-        if (CTA2) tmem_dealloc_2sm(tmem_base, 2 * BLOCK_N);
-        else tmem_dealloc(tmem_base, 2 * BLOCK_N);
+        if (CTA2) tmem_dealloc_2sm(tmem_base, kAccBufs * BLOCK_N);
+        else tmem_dealloc(tmem_base, kAccBufs * BLOCK_N);
     }
 }
 
@@ -735,6 +791,13 @@ static void choose_box(int P, int Q, int rows, int* bn, int* bp, int* bq) {
 }  // namespace t2i
 
 using namespace t2i;
+
+static unsigned long long* g_timeline = nullptr;
+extern "C" int t2i_debug_timeline(unsigned long long* host_dst, int count) {
+    if (g_timeline == nullptr || count > 64 * 8) return fail(T2I_ERR_BAD_ARG, "no timeline recorded (T2I_TIMELINE=1)");
+    cudaError_t e = cudaMemcpy(host_dst, g_timeline, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost);
+    return e == cudaSuccess ? T2I_OK : fail(T2I_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
+}
 
 extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     if (d == nullptr) return fail(T2I_ERR_BAD_ARG, "null descriptor");
@@ -837,7 +900,18 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const int stage_bytes = kABytes + b_rows * kBlockK * 2;
     const int n_aux = prm.has_add + prm.has_mask + prm.has_sx;
     if (n_aux == 3) prm.epi_depth = 1;
-    const int epi_bytes = (1 + n_aux) * prm.epi_depth * d->np * kSubBytes;
+    // two epilogue groups (each with its own staging buffers) in the throughput mode; with aux tiles one buffer each
+    prm.epi_groups = (d->np == 1) ? 2 : 1;
+    // 256-wide tiles have two TMEM accumulators: both groups must finish a tile together (sub-tile split), or the
+    // MMAs of the tile after next wait for a whole single-group epilogue
+    prm.epi_split = (block_n == 256) ? 1 : 0;
+    {
+        static const int force = [] { const char* e = getenv("T2I_EPI_MODE"); return e ? atoi(e) : 0; }();
+        if (force == 1) prm.epi_split = 0;
+        if (force == 2) prm.epi_split = 1;
+    }
+    if (prm.epi_groups == 2) prm.epi_depth = 1;      // one staging buffer per group = the two of a single group: the mainloop keeps its stages
+    const int epi_bytes = prm.epi_groups * (1 + n_aux) * prm.epi_depth * d->np * kSubBytes;
     const bool stats = prm.stat_sum != nullptr || prm.stat_second != nullptr;
     // per-CTA running totals in shared memory (one flush per CTA instead of one atomic per tile and channel:
     // thousands of tiles hammering the same few L2 lines serialise); very wide outputs have few tiles -> direct
@@ -847,11 +921,19 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         prm.dbg = e ? atoi(e) : 0;
         if (prm.dbg & 8) prm.stat_acc = 0;
     }
+    {
+        static const bool want = [] { const char* e = getenv("T2I_TIMELINE"); return e && e[0] == '1'; }();
+        if (want && g_timeline == nullptr) {
+            cudaMalloc(&g_timeline, 64 * 8 * sizeof(unsigned long long));
+            cudaMemset(g_timeline, 0, 64 * 8 * sizeof(unsigned long long));
+        }
+        prm.timeline = want ? g_timeline : nullptr;
+    }
     prm.img = d->x_img;
     prm.img_h = x.h;
     prm.img_w = x.w;
-    const int img_bytes = a_img ? (2 * prm.bp + 2) * x.w * 3 * 4 : 0;
-    const int tail_bytes = block_n * 4 + (stats ? 2048 + 8 * prm.stat_acc : 0) + img_bytes + 256;   // bias, statistics, image rows, barriers
+    const int img_bytes = a_img ? (2 * prm.bp + 2) * (kImgRing * x.w * 3 * 4 + d->np * img_pitch_words(x.w) * 4) : 0;   // raw ring + bf16 planes
+    const int tail_bytes = 2 * block_n * 4 + (stats ? 2 * (2048 + 8 * prm.stat_acc) : 0) + img_bytes + 256;   // bias, statistics (per group), image rows, barriers
     int stages = (kSmemBudget - epi_bytes - tail_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return fail(T2I_ERR_BAD_ARG, "shared memory plan leaves %d pipeline stages", stages);
@@ -924,7 +1006,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
             if (e != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(e));
             img_attr_done[iv] = true;
         }
-        cudaError_t le = launch_pdl(img_fns[iv], grid, kThreadsImg, smem_bytes, stream, prm, 1);
+        cudaError_t le = launch_pdl(img_fns[iv], grid, kThreads + img_producers(stats), smem_bytes, stream, prm, 1);
         if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "conv_gemm_kernel (image patches) launch: %s", cudaGetErrorString(le));
         return check_launch("conv_gemm_kernel");
     }

@@ -24,7 +24,8 @@
 
 namespace t2i {
 
-constexpr int kDiThreads = 192;          // warp 0 TMA, warp 1 MMA, warps 2..5 epilogue
+constexpr int kDiThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
+constexpr int kDiEpi = 256;
 constexpr int kDiStages = 4;
 constexpr int kDiABytes = 128 * 64 * 2;  // 128 patch pixels x 64 channels
 constexpr int kDiBChunk = 64 * 64 * 2;   // 64 x 64 weight block
@@ -35,7 +36,7 @@ struct alignas(64) DeconvImgParams {
     CUtensorMap a_map;
     CUtensorMap b_map;
     int N, P, Q, bp, tiles_per_img;
-    int lg_q;
+    int lg_q, urows;
     int k_chunks, last_k_steps, n_pass, np, b_kn;
     const float* bias3;
     float* out;          // fp32 NHWC [N][2P][2Q][3]
@@ -67,8 +68,11 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int np = prm.np, kch = prm.k_chunks;
     const int H = 2 * prm.P, W = 2 * prm.Q;
-    const int slots = prm.bp + 1;                 // patch-row ring: bp rows of this tile + the carried one
-    const int urows = 2 * prm.bp + 3;             // image-row ring for the fused 3x3 conv (the last tile adds a row)
+    // rings indexed by (row & (size - 1)): patch rows -- the bp rows of this tile + the carried one fit in 2*bp slots;
+    // image rows for the fused 3x3 conv -- 2*bp + 3 live rows fit in prm.urows (a power of two)
+    const int slots = 2 * prm.bp;
+    const int urows = prm.urows;
+    const int lg_w = prm.lg_q + 1;
     // carve-up: [A stages][B: np x k_chunks blocks][S: slots x Q x 52 fp32][U: urows x W*3 fp32][w9 81 + b9 3 + bias 3][barriers]
     uint8_t* s_a = smem;
     uint8_t* s_b = s_a + kDiStages * kDiABytes;
@@ -93,7 +97,7 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
-            mbar_init(&tmem_empty[i], 4);
+            mbar_init(&tmem_empty[i], kDiEpi / 32);
         }
         mbar_init(b_bar, 1);
         fence_barrier_init();
@@ -174,8 +178,12 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
                 }
         }
     } else {
-        // ------------------------------------------------ epilogue: patch contributions -> image rows (128 threads)
+        // ------------------------------------------------ epilogue: patch contributions -> image rows (256 threads)
+        // TMEM -> shared memory: warp w reads the 32 accumulator rows of lane quarter (w & 3); the two warps of a quarter
+        // split the 48 columns (32 + 16).  Gather / conv: thread t owns image column (t & (W - 1)) and walks rows, so the
+        // column-side indices (which two patch columns, which kw) are loop invariants and nothing divides.
         const int quarter = warp & 3;
+        const int part = (warp - 2) >> 2;               // 0: columns 0..31, 1: columns 32..47
         const int row = quarter * 32 + lane;            // TMEM lane = patch pixel inside the tile
         const int et = threadIdx.x - 64;
         const int pl = row >> prm.lg_q, q = row & (prm.Q - 1);
@@ -183,6 +191,12 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
         if (et < 81) s_w[et] = fuse ? prm.w9[et] : 0.f;
         else if (et < 84) s_w[et] = fuse ? prm.b9[et - 81] : 0.f;
         else if (et < 87) s_w[et] = prm.bias3 != nullptr ? prm.bias3[et - 84] : 0.f;
+        const int ow = et & (W - 1);
+        const int row_step = kDiEpi >> lg_w;            // image rows covered per sweep of the 256 threads (>= 1: W <= 256)
+        const int row_first = et >> lg_w;
+        const int kw0 = (ow + 1) & 1;
+        const int q_a = (ow + 1 - kw0) >> 1, q_b = q_a - 1;           // patch columns reaching this pixel (kw0, kw0 + 2)
+        const bool qa_ok = q_a < prm.Q, qb_ok = q_b >= 0;
         int it = 0;
         for (int n = blockIdx.x; n < prm.N; n += gridDim.x)
             for (int t = 0; t < total_tiles; ++t, ++it) {
@@ -190,74 +204,82 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
                 const int p0 = t * prm.bp;
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1, 400 + acc);
                 tc_fence_after();
-                uint32_t r0[32], r1[16];
                 const uint32_t taddr = tmem_base + acc * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
-                tmem_ld_32x32(taddr, r0);
-                tmem_ld_32x16(taddr + 32, r1);
-                tmem_ld_wait();
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&tmem_empty[acc]);     // the MMAs of the next tile may start
-                named_bar(1, 128);                                // the previous tile's gather / conv is finished
-                {
-                    float4* dst = reinterpret_cast<float4*>(s_s + (((p0 + pl) % slots) * prm.Q + q) * kDiSPitch);
+                float4* dst = reinterpret_cast<float4*>(s_s + ((((p0 + pl) & (slots - 1)) << prm.lg_q) + q) * kDiSPitch);
+                if (part == 0) {
+                    uint32_t r0[32];
+                    tmem_ld_32x32(taddr, r0);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    named_bar(1, kDiEpi);                         // the previous tile's gather / conv is finished
 #pragma unroll
                     for (int j = 0; j < 8; ++j)
                         dst[j] = make_float4(__uint_as_float(r0[4 * j]), __uint_as_float(r0[4 * j + 1]),
                                              __uint_as_float(r0[4 * j + 2]), __uint_as_float(r0[4 * j + 3]));
+                } else {
+                    uint32_t r1[16];
+                    tmem_ld_32x16(taddr + 32, r1);
+                    tmem_ld_wait();
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&tmem_empty[acc]);
+                    named_bar(1, kDiEpi);
 #pragma unroll
                     for (int j = 0; j < 4; ++j)
                         dst[8 + j] = make_float4(__uint_as_float(r1[4 * j]), __uint_as_float(r1[4 * j + 1]),
                                                  __uint_as_float(r1[4 * j + 2]), __uint_as_float(r1[4 * j + 3]));
                 }
-                named_bar(2, 128);
+                named_bar(2, kDiEpi);
                 const bool last = (t == total_tiles - 1);
                 const int oh_lo = (p0 == 0) ? 0 : 2 * p0 - 1;
                 const int oh_hi = last ? H - 1 : 2 * p0 + 2 * prm.bp - 2;       // inclusive
                 const float bz0 = s_w[84], bz1 = s_w[85], bz2 = s_w[86];
-                float* obase = prm.out + static_cast<long long>(n) * H * W * 3;
-                for (int i = et; i < (oh_hi - oh_lo + 1) * W; i += 128) {
-                    const int oh = oh_lo + i / W, ow = i % W;
+                float* obase = prm.out + (static_cast<long long>(n) * H * W + ow) * 3;
+                for (int oh = oh_lo + row_first; oh <= oh_hi; oh += row_step) {
+                    const int kh0 = (oh + 1) & 1;
+                    const int p_a = (oh + 1 - kh0) >> 1, p_b = p_a - 1;        // patch rows reaching this pixel (kh0, kh0 + 2)
                     float a0 = bz0, a1 = bz1, a2 = bz2;
 #pragma unroll
                     for (int dh = 0; dh < 2; ++dh) {
-                        const int kh = ((oh + 1) & 1) + 2 * dh;
-                        const int p = (oh + 1 - kh) >> 1;
-                        if (p < 0 || p >= prm.P || oh + 1 - kh < 0) continue;
-#pragma unroll
-                        for (int dw = 0; dw < 2; ++dw) {
-                            const int kw = ((ow + 1) & 1) + 2 * dw;
-                            const int qq = (ow + 1 - kw) >> 1;
-                            if (qq < 0 || qq >= prm.Q || ow + 1 - kw < 0) continue;
-                            const float* src = s_s + ((p % slots) * prm.Q + qq) * kDiSPitch + (kh * 4 + kw) * 3;
+                        const int p = dh ? p_b : p_a;
+                        if (dh ? (p_b < 0) : (p_a >= prm.P)) continue;
+                        const float* srow = s_s + (((p & (slots - 1)) << prm.lg_q)) * kDiSPitch + ((kh0 + 2 * dh) * 4 + kw0) * 3;
+                        if (qa_ok) {
+                            const float* src = srow + q_a * kDiSPitch;
+                            a0 += src[0]; a1 += src[1]; a2 += src[2];
+                        }
+                        if (qb_ok) {
+                            const float* src = srow + q_b * kDiSPitch + 6;      // kw0 + 2
                             a0 += src[0]; a1 += src[1]; a2 += src[2];
                         }
                     }
-                    float* o = obase + (static_cast<long long>(oh) * W + ow) * 3;
+                    float* o = obase + (static_cast<long long>(oh) << lg_w) * 3;
                     o[0] = a0; o[1] = a1; o[2] = a2;
                     if (fuse) {
-                        float* u = s_u + ((oh % urows) * W + ow) * 3;
+                        float* u = s_u + (((oh & (urows - 1)) << lg_w) + ow) * 3;
                         u[0] = a0; u[1] = a1; u[2] = a2;
                     }
                 }
                 if (fuse) {
-                    named_bar(3, 128);
+                    named_bar(3, kDiEpi);
                     // 3x3 conv + tanh on the image rows whose three input rows are complete
                     const int c_lo = (p0 == 0) ? 0 : oh_lo - 1;
                     const int c_hi = last ? H - 1 : oh_hi - 1;
-                    float* ibase = prm.img + static_cast<long long>(n) * H * W * 3;
-                    for (int i = et; i < (c_hi - c_lo + 1) * W; i += 128) {
-                        const int oh = c_lo + i / W, ow = i % W;
+                    float* ibase = prm.img + (static_cast<long long>(n) * H * W + ow) * 3;
+                    for (int oh = c_lo + row_first; oh <= c_hi; oh += row_step) {
                         float a0 = s_w[81], a1 = s_w[82], a2 = s_w[83];
 #pragma unroll
                         for (int kh = 0; kh < 3; ++kh) {
                             const int ih = oh + kh - 1;
                             if (ih < 0 || ih >= H) continue;
+                            const float* urow = s_u + ((ih & (urows - 1)) << lg_w) * 3;
 #pragma unroll
                             for (int kw = 0; kw < 3; ++kw) {
                                 const int iw = ow + kw - 1;
                                 if (iw < 0 || iw >= W) continue;
-                                const float* u = s_u + ((ih % urows) * W + iw) * 3;
+                                const float* u = urow + iw * 3;
                                 const float* wp = s_w + (kh * 3 + kw) * 9;
 #pragma unroll
                                 for (int ci = 0; ci < 3; ++ci) {
@@ -268,7 +290,7 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
                                 }
                             }
                         }
-                        float* o = ibase + (static_cast<long long>(oh) * W + ow) * 3;
+                        float* o = ibase + (static_cast<long long>(oh) << lg_w) * 3;
                         o[0] = tanhf(a0); o[1] = tanhf(a1); o[2] = tanhf(a2);
                     }
                 }
@@ -284,49 +306,93 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// y[r][o] = act(sum_k x[r][k] * w[o][k] + b[o]), everything fp32.  Tile 16 rows x 64 outputs, K in steps of 32.
-constexpr int kDfR = 16, kDfO = 64, kDfK = 32;
-__global__ void __launch_bounds__(256) dense_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                        const float* __restrict__ bias, float* y, int rows, int cin, int cout,
-                                                        int act) {
+// y[r][o] = act(sum_k x[r][k] * w[o][k] + b[o]), everything fp32.  CTA tile 16 rows x 32 outputs; the 256 threads form
+// four groups that take every fourth 16-wide K chunk (their partial sums meet in shared memory at the end); a thread owns
+// a 2 x 4 register tile.  Operands are staged K-major-transposed ([k][row], [k][output]) so that a thread's rows /
+// outputs are one 8- / 16-byte shared load; the next chunk's global loads are in flight while the current one is used.
+constexpr int kDfR = 16, kDfO = 32, kDfK = 16, kDfG = 4, kDfXP = 20;     // kDfXP: padded row pitch of the x tile
+__global__ void __launch_bounds__(64 * kDfG) dense_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
+                                                              const float* __restrict__ bias, float* y, int rows, int cin,
+                                                              int cout, int act) {
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ float xs[kDfR][kDfK + 1];
-    __shared__ float ws[kDfO][kDfK + 1];
+    __shared__ __align__(16) float xs[kDfG][2][kDfK][kDfXP];
+    __shared__ __align__(16) float ws[kDfG][2][kDfK][kDfO];
+    __shared__ float red[kDfG - 1][64][9];
+    const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
+    const int tr = t >> 3, to = t & 7;                  // rows 2*tr .. +1, outputs 4*to .. +3 of the tile
     const int r0 = blockIdx.y * kDfR, o0 = blockIdx.x * kDfO;
-    const int tr = threadIdx.x >> 4, to = threadIdx.x & 15;
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};
-    for (int k0 = 0; k0 < cin; k0 += kDfK) {
-        if (threadIdx.x < kDfR * kDfK / 4) {
-            const int r = threadIdx.x >> 3, c4 = (threadIdx.x & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r0 + r < rows && k0 + c4 < cin) v = __ldg(reinterpret_cast<const float4*>(x + (long long)(r0 + r) * cin + k0 + c4));
-            xs[r][c4] = v.x; xs[r][c4 + 1] = v.y; xs[r][c4 + 2] = v.z; xs[r][c4 + 3] = v.w;
+    const int n_chunks = (cin + kDfK - 1) / kDfK;
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    float4 xr, wr[2];
+    auto load = [&](int c) {
+        const int k0 = c * kDfK;
+        {
+            const int r = t & 15, k4 = (t >> 4) * 4;
+            xr = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (r0 + r < rows && k0 + k4 < cin) xr = __ldg(reinterpret_cast<const float4*>(x + (long long)(r0 + r) * cin + k0 + k4));
         }
-        for (int i = threadIdx.x; i < kDfO * kDfK / 4; i += 256) {
-            const int o = i >> 3, c4 = (i & 7) * 4;
-            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o0 + o < cout && k0 + c4 < cin) v = __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + o) * cin + k0 + c4));
-            ws[o][c4] = v.x; ws[o][c4 + 1] = v.y; ws[o][c4 + 2] = v.z; ws[o][c4 + 3] = v.w;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = t + 64 * j, o = idx & 31, k4 = (idx >> 5) * 4;
+            wr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (o0 + o < cout && k0 + k4 < cin) wr[j] = __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + o) * cin + k0 + k4));
         }
-        __syncthreads();
+    };
+    auto store = [&](int buf) {
+        {
+            const int r = t & 15, k4 = (t >> 4) * 4;
+            xs[g][buf][k4 + 0][r] = xr.x; xs[g][buf][k4 + 1][r] = xr.y;
+            xs[g][buf][k4 + 2][r] = xr.z; xs[g][buf][k4 + 3][r] = xr.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int idx = t + 64 * j, o = idx & 31, k4 = (idx >> 5) * 4;
+            ws[g][buf][k4 + 0][o] = wr[j].x; ws[g][buf][k4 + 1][o] = wr[j].y;
+            ws[g][buf][k4 + 2][o] = wr[j].z; ws[g][buf][k4 + 3][o] = wr[j].w;
+        }
+    };
+    int c = g, buf = 0;
+    if (c < n_chunks) {
+        load(c);
+        store(0);
+    }
+    named_bar(1 + g, 64);
+    for (; c < n_chunks; c += kDfG) {
+        const bool more = c + kDfG < n_chunks;
+        if (more) load(c + kDfG);
 #pragma unroll
         for (int k = 0; k < kDfK; ++k) {
-            const float xv = xs[tr][k];
-#pragma unroll
-            for (int j = 0; j < 4; ++j) acc[j] += xv * ws[to + 16 * j][k];
+            const float2 xv = *reinterpret_cast<const float2*>(&xs[g][buf][k][2 * tr]);
+            const float4 wv = *reinterpret_cast<const float4*>(&ws[g][buf][k][4 * to]);
+            acc[0][0] += xv.x * wv.x; acc[0][1] += xv.x * wv.y; acc[0][2] += xv.x * wv.z; acc[0][3] += xv.x * wv.w;
+            acc[1][0] += xv.y * wv.x; acc[1][1] += xv.y * wv.y; acc[1][2] += xv.y * wv.z; acc[1][3] += xv.y * wv.w;
         }
-        __syncthreads();
+        if (more) store(buf ^ 1);
+        named_bar(1 + g, 64);
+        buf ^= 1;
     }
-    if (r0 + tr < rows) {
+    if (g > 0) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            const int o = o0 + to + 16 * j;
-            if (o < cout) {
-                float v = acc[j] + (bias != nullptr ? bias[o] : 0.f);
-                if (act == T2I_ACT_LRELU) v = fmaxf(v, 0.2f * v);
-                else if (act == T2I_ACT_RELU) v = fmaxf(v, 0.f);
-                y[(long long)(r0 + tr) * cout + o] = v;
+        for (int i = 0; i < 8; ++i) red[g - 1][t][i] = acc[i >> 2][i & 3];
+    }
+    __syncthreads();
+    if (g == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i) {
+            const int r = r0 + 2 * tr + i;
+            if (r >= rows) continue;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int o = o0 + 4 * to + j;
+                if (o < cout) {
+                    float v = acc[i][j] + (bias != nullptr ? bias[o] : 0.f);
+#pragma unroll
+                    for (int gg = 0; gg < kDfG - 1; ++gg) v += red[gg][t][i * 4 + j];
+                    if (act == T2I_ACT_LRELU) v = fmaxf(v, 0.2f * v);
+                    else if (act == T2I_ACT_RELU) v = fmaxf(v, 0.f);
+                    y[(long long)r * cout + o] = v;
+                }
             }
         }
     }
@@ -354,6 +420,7 @@ extern "C" int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane
     if (prm.P % prm.bp != 0) return fail(T2I_ERR_BAD_ARG, "deconv_img: %d rows are not a multiple of %d", prm.P, prm.bp);
     prm.tiles_per_img = prm.P / prm.bp;
     for (prm.lg_q = 0; (1 << prm.lg_q) < prm.Q; ++prm.lg_q) {}
+    for (prm.urows = 8; prm.urows < 2 * prm.bp + 3; prm.urows *= 2) {}
     const bool kn = w_layout == T2I_W_KN;
     const int w_n = kn ? w_cols : w_rows, w_k = kn ? w_rows : w_cols;
     if (w_n != 64 || a->c > w_k || a->c > 256 || a->c % 8 != 0 || a->pitch % 8 != 0 || a->coff % 8 != 0 || w_cols % 8 != 0)
@@ -384,8 +451,8 @@ extern "C" int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane
         if (rc != T2I_OK) return rc;
     }
     const bool fuse = w9 != nullptr;
-    const int smem_bytes = kDiStages * kDiABytes + np * prm.k_chunks * kDiBChunk + (prm.bp + 1) * prm.Q * kDiSPitch * 4 +
-                           (fuse ? (2 * prm.bp + 3) * 2 * prm.Q * 3 * 4 : 0) + 96 * 4 + 256 + 1024;
+    const int smem_bytes = kDiStages * kDiABytes + np * prm.k_chunks * kDiBChunk + 2 * prm.bp * prm.Q * kDiSPitch * 4 +
+                           (fuse ? prm.urows * 2 * prm.Q * 3 * 4 : 0) + 96 * 4 + 256 + 1024;
     if (smem_bytes > 232448) return fail(T2I_ERR_BAD_ARG, "deconv_img: shared memory plan of %d bytes", smem_bytes);
     static bool attr_done = false;
     if (!attr_done) {
@@ -404,7 +471,7 @@ extern "C" int t2i_dense_f32(const float* x, int rows, int cin, const float* w, 
     if (x == nullptr || w == nullptr || y == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
     if (cin % 4 != 0) return fail(T2I_ERR_BAD_ARG, "dense_f32: cin=%d must be a multiple of 4", cin);
     dim3 grid(ceil_div(cout, kDfO), ceil_div(rows, kDfR));
-    cudaError_t le = launch_ew(dense_f32_kernel, grid, dim3(256), 0, static_cast<cudaStream_t>(stream), x, w, bias, y, rows, cin,
+    cudaError_t le = launch_ew(dense_f32_kernel, grid, dim3(64 * kDfG), 0, static_cast<cudaStream_t>(stream), x, w, bias, y, rows, cin,
                                cout, act);
     if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "dense_f32_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("dense_f32_kernel");

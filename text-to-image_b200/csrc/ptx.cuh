@@ -173,6 +173,18 @@ __host__ __device__ constexpr uint32_t make_idesc_bf16(int m, int n, int a_mn_ma
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
+// ---------------------------------------------------------------- cp.async (16-byte LDGSTS, zero fill when !valid)
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, bool valid) {
+    const uint32_t sz = valid ? 16u : 0u;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(sz) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_pending() {      // at most the N most recent groups may still be in flight
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+
 // ---------------------------------------------------------------- small helpers
 __device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
     __nv_bfloat162 v = __floats2bfloat162_rn(a, b);

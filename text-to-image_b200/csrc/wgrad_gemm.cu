@@ -16,6 +16,7 @@
 // models/wgancls/model.py:94-106 of the reference; also forms the second-order term of the
 // gradient penalty (model.py:62-70,88-91) when x holds the tangent activations.
 #include "host_util.h"
+#include "img_patch.cuh"
 #include "ptx.cuh"
 
 namespace t2i {
@@ -25,7 +26,8 @@ constexpr int kWAtomBytes = kWK * 128;        // 64 pixels x 64 channels bf16 = 
 constexpr int kWThreads = 192;
 constexpr int kWImgProducers = 64;            // IMG: two more warps assemble the 64 patch rows of a K block
 constexpr int kWThreadsImg = kWThreads + kWImgProducers;
-constexpr int kWImgRowBytes = 16384;          // IMG: staged fp32 image rows ((2*bp + 2) rows of w*3 floats)
+constexpr int kWImgRing = 4;                  // IMG: raw image-row buffers in flight (cp.async ring, K blocks ahead)
+constexpr int kWImgRowBytes = kWImgRing * 12288 + 8192;   // IMG: fp32 image rows ring ((2*bp + 2) rows of w*3 floats each) + bf16 rows
 
 // CTA2: a CTA pair (cta_group::2) computes 256 output channels x BN input channels; each CTA stages its
 // own 128 output channels of dy and HALF of the x tile, and reduces its own 128 accumulator rows.
@@ -39,7 +41,10 @@ struct WgradCfg {
     static constexpr int kStages = (kStageBytes <= 32768) ? 6 : 4;
     static constexpr int kBarOffset = kStages * kStageBytes;
     static constexpr int kSmemBytes = kBarOffset + 256 + 1024;
-    static constexpr int kImgOffset = kBarOffset + 256;                    // IMG variants: the image-row buffer
+    // IMG variants: four pipeline stages, then barriers, then the image-row buffers
+    static constexpr int kStagesImg = 4;
+    static constexpr int kBarOffsetImg = kStagesImg * kStageBytes;
+    static constexpr int kImgOffset = kBarOffsetImg + 256;
     static constexpr int kSmemBytesImg = kImgOffset + kWImgRowBytes + 1024;
     static constexpr int kAccCols = MT * BN;                  // 128 or 256 columns per accumulator
     static constexpr int kTmemCols = 2 * MT * BN;             // double buffered
@@ -76,10 +81,10 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
     static_assert(IMG == 0 || (!CTA2 && MT == 1), "image-patch operands: single CTA, one accumulator");
     constexpr int kPair = CTA2 ? 2 : 1;
     const int rank = CTA2 ? static_cast<int>(cluster_ctarank()) : 0;
-    constexpr int kStages = Cfg::kStages;
+    constexpr int kStages = IMG ? Cfg::kStagesImg : Cfg::kStages;
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + Cfg::kBarOffset);
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (IMG ? Cfg::kBarOffsetImg : Cfg::kBarOffset));
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
@@ -254,70 +259,86 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
             }
         }
     } else if (IMG != 0 && warp >= 6) {
-        // image-patch producers: 64 threads, one pixel row of the K block each
+        // image-patch producers: 64 threads, one pixel row of the K block each.  The K blocks this CTA will visit form
+        // one sequence (work item, pass, block); the image rows of the NEXT block stream into the other buffer
+        // (cp.async) while the current block's patches are assembled.
         const int pt = threadIdx.x - kWThreads;
         float* s_img = reinterpret_cast<float*>(smem + Cfg::kImgOffset);
-        const int iw3 = prm.img_w * 3, iw3q = iw3 >> 2;
+        const int iw3 = prm.img_w * 3;
         const int n_rows = 2 * prm.bp + 2;
-        int stage = 0;
-        uint32_t phase = 0;
-        for (int w = w0; w < prm.total_work; w += w_stride) {
-            const Work wk = decode(w);
-            for (int pass = 0; pass < prm.n_pass; ++pass) {
-                const bool lo_plane = (IMG == 1) ? (pass == 2) : (pass == 1);     // x: hi, hi, lo; dy: hi, lo, hi
-                for (int kb = wk.kb_begin; kb < wk.kb_end; ++kb) {
-                    const int tq = kb % prm.tiles_q;
-                    const int tp = (kb / prm.tiles_q) % prm.tiles_p;
-                    const int tn = kb / (prm.tiles_q * prm.tiles_p);             // bn == 1: the sample
-                    const int q0 = tq * prm.bq, p0 = tp * prm.bp;
-                    named_bar(3, kWImgProducers);                                // the previous block's rows have been read
-                    const float* base = prm.img + static_cast<long long>(tn) * prm.img_h * iw3;
-                    const int ih0 = 2 * p0 - 1;
-                    for (int i = pt; i < n_rows * iw3q; i += kWImgProducers) {
-                        const int r = i / iw3q, c4 = i - r * iw3q;
-                        const int ih = ih0 + r;
-                        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-                        if (ih >= 0 && ih < prm.img_h) v = __ldg(reinterpret_cast<const float4*>(base + static_cast<long long>(ih) * iw3) + c4);
-                        reinterpret_cast<float4*>(s_img)[i] = v;
-                    }
-                    named_bar(3, kWImgProducers);
-                    mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
-                    uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
-                    const int q = q0 + (pt & (prm.bq - 1)), pl = pt / prm.bq;
-                    uint8_t* dst = atom + (pt >> 3) * 1024 + (pt & 7) * 128;
-#pragma unroll
-                    for (int chunk = 0; chunk < 8; ++chunk) {
-                        uint4 hi = make_uint4(0u, 0u, 0u, 0u);
-                        if (chunk < 6) {
-                            float v[8];
-#pragma unroll
-                            for (int j = 0; j < 8; ++j) {
-                                const int colj = chunk * 8 + j;
-                                const int kh = colj / 12, rem = colj - kh * 12;
-                                const int x0 = (2 * q - 1) * 3 + rem;
-                                v[j] = (x0 >= 0 && x0 < iw3) ? s_img[(2 * pl + kh) * iw3 + x0] : 0.f;
-                            }
-                            hi.x = pack_bf16x2(v[0], v[1]); hi.y = pack_bf16x2(v[2], v[3]);
-                            hi.z = pack_bf16x2(v[4], v[5]); hi.w = pack_bf16x2(v[6], v[7]);
-                            if (lo_plane) {
-                                uint4 lo;
-                                lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
-                                lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
-                                lo.z = pack_bf16x2(v[4] - bf16_lo(hi.z), v[5] - bf16_hi(hi.z));
-                                lo.w = pack_bf16x2(v[6] - bf16_lo(hi.w), v[7] - bf16_hi(hi.w));
-                                hi = lo;
-                            }
-                        }
-                        *reinterpret_cast<uint4*>(dst + ((chunk ^ (pt & 7)) * 16)) = hi;    // columns 48..63: zeros
-                    }
-                    fence_proxy_async();
-                    mbar_arrive(&full_bar[stage]);
-                    if (++stage == kStages) {
-                        stage = 0;
-                        phase ^= 1;
-                    }
+        const int img_floats = n_rows * iw3;
+        const int pitchw = img_pitch_words(prm.img_w);
+        uint32_t* s_bf = reinterpret_cast<uint32_t*>(s_img + kWImgRing * img_floats);      // one bf16 padded row buffer (the pass's plane)
+        struct Cursor {
+            int w, pass, kb, kb_begin, kb_end;
+            bool valid;
+        };
+        auto settle = [&](Cursor& c) {      // move to the first existing block at or after (w, pass = 0)
+            while (c.w < prm.total_work) {
+                const Work wk = decode(c.w);
+                if (wk.n_kb > 0) {
+                    c.kb_begin = wk.kb_begin; c.kb_end = wk.kb_end; c.kb = wk.kb_begin; c.pass = 0;
+                    c.valid = true;
+                    return;
                 }
+                c.w += w_stride;
             }
+            c.valid = false;
+        };
+        auto advance = [&](Cursor& c) {
+            if (++c.kb < c.kb_end) return;
+            if (++c.pass < prm.n_pass) {
+                c.kb = c.kb_begin;
+                return;
+            }
+            c.w += w_stride;
+            settle(c);
+        };
+        auto prefetch = [&](const Cursor& c, int buf) {      // exactly one cp.async group per call (empty past the end)
+            if (!c.valid) {
+                cp_async_commit();
+                return;
+            }
+            const int tp = (c.kb / prm.tiles_q) % prm.tiles_p;
+            const int tn = c.kb / (prm.tiles_q * prm.tiles_p);                   // bn == 1: the sample
+            img_rows_prefetch(prm.img + static_cast<long long>(tn) * prm.img_h * iw3, 2 * tp * prm.bp - 1, prm.img_h, n_rows, iw3,
+                              s_img + buf * img_floats, prm.img, pt, kWImgProducers);
+            cp_async_commit();
+        };
+        Cursor cur;
+        cur.w = w0;
+        settle(cur);
+        Cursor pf = cur;                         // runs kWImgRing - 1 blocks ahead of cur
+        for (int a = 0; a < kWImgRing - 1; ++a) {
+            prefetch(pf, a);
+            if (pf.valid) advance(pf);
+        }
+        int stage = 0, buf = 0;
+        uint32_t phase = 0;
+        while (cur.valid) {
+            Cursor nxt = cur;
+            advance(nxt);
+            cp_async_wait_pending<kWImgRing - 2>();
+            named_bar(3, kWImgProducers);       // every producer's rows of this block are in; the oldest ring slot is free
+            prefetch(pf, (buf + kWImgRing - 1) & (kWImgRing - 1));
+            if (pf.valid) advance(pf);
+            const bool lo_plane = (IMG == 1) ? (cur.pass == 2) : (cur.pass == 1);     // x: hi, hi, lo; dy: hi, lo, hi
+            img_rows_convert(s_img + buf * img_floats, n_rows, iw3, s_bf, lo_plane ? s_bf : nullptr, pitchw, pt, kWImgProducers);
+            named_bar(4, kWImgProducers);       // the bf16 rows (of the plane this pass needs) are complete
+            const int q0 = (cur.kb % prm.tiles_q) * prm.bq;
+            mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
+            uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
+            int q = q0 + (pt & (prm.bq - 1));
+            if (q >= prm.Q) q = prm.Q - 1;
+            img_patch_row(s_bf, pitchw, pt / prm.bq, q, atom + (pt >> 3) * 1024 + (pt & 7) * 128, pt, true);   // columns 48..63: zeros
+            fence_proxy_async();
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == kStages) {
+                stage = 0;
+                phase ^= 1;
+            }
+            cur = nxt;
+            buf = (buf + 1) & (kWImgRing - 1);
         }
     } else if (IMG == 0 || warp < 6) {
         // reduction warps: accumulator -> red.global.add into dw, while the MMAs of the next item run
@@ -458,7 +479,7 @@ extern "C" int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_ac
         int p = floor_pow2(prm.P); if (p > kWK / q) p = kWK / q;
         prm.bq = q; prm.bp = p; prm.bn = kWK / (q * p);
     }
-    if (prm.bn != 1 || (2 * prm.bp + 2) * w * 3 * 4 > kWImgRowBytes)
+    if (prm.bn != 1 || (2 * prm.bp + 2) * w * 3 * 4 > 12288 || (2 * prm.bp + 2) * img_pitch_words(w) * 4 > 8192)
         return fail(T2I_ERR_BAD_ARG, "wgrad_img: unsupported image extent %d x %d", h, w);
     prm.tiles_q = ceil_div(prm.Q, prm.bq);
     prm.tiles_p = ceil_div(prm.P, prm.bp);
