@@ -85,11 +85,12 @@ typedef struct {
      * add / mask / stat_x and the stat_* vectors are indexed by the WINDOW's channels. */
     int w_n0;
     /* The 3-channel ends (d_net's first conv, model.py:135; the input gradient of g_net's last transposed conv, :218):
-     * x_img != NULL makes the A operand the 4x4 / stride-2 SAME patch matrix of this fp32 NHWC image [x.n][x.h][x.w][3]
-     * (row = output pixel, column (kh*4 + kw)*3 + c, 48 columns), assembled in shared memory from the image -- no patch
-     * matrix in HBM.  mode = T2I_CONV_K4S2, k = 4, x.ptr ignored, x.c = 48; w is [np][1][w_rows][w_cols] with 64
+     * x_img != NULL makes the A operand the 4x4 / stride-2 SAME patch matrix of the 3-channel image [x.n][x.h][x.w][3]
+     * (row = output pixel, column (kh*4 + kw)*3 + c, 48 columns), assembled in shared memory -- no patch matrix in HBM.
+     * x_img points at the image's padded bf16 rows (t2i_img_to_rows: planes [np][x.n][x.h][pitch], x.plane_stride
+     * elements apart).  mode = T2I_CONV_K4S2, k = 4, x.ptr ignored, x.c = 48; w is [np][1][w_rows][w_cols] with 64
      * (48 used) along the contraction; y is [x.n][x.h/2][x.w/2][c].  Everything else (bias, act, mask, stat_*) as above. */
-    const float* x_img;
+    const void* x_img;
 } t2i_conv_gemm_desc;
 int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
 /* Development aid (T2I_TIMELINE=1 in the environment): %globaltimer stamps CTA 0 of the LAST t2i_conv_gemm launch left
@@ -131,12 +132,17 @@ int t2i_from_planes(const void* src, long long plane_stride, int np, float* dst,
  * w9 / b9 / img (all or none): additionally img = tanh(conv3x3(out, w9 HWIO [3][3][3][3]) + b9), model.py:219-221. */
 int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane_stride, int w_rows, int w_cols, int w_layout, int np,
                    const float* bias3, float* out, const float* w9, const float* b9, float* img, void* stream);
-/* Weight gradient of a 4x4 / stride-2 conv between a 3-channel fp32 NHWC image [n][h][w][3] (patches assembled on chip)
- * and a bf16-plane tensor on the [n][h/2][w/2] grid, on tcgen05, dw += (the caller zeroes):
+/* fp32 NHWC 3-channel image [n][h][w][3] (optionally scaled per sample) -> padded bf16 rows, planes [np][n][h][pitch],
+ * pitch = 4 * ceil((3w + 6) / 4) entries, entry j = x[j - 3] (zeros outside: the left / right SAME padding).  6 bytes per
+ * pixel; this is the form in which the image-patch producers stream an image (csrc/img_patch.cuh). */
+int t2i_img_to_rows(const float* img, int n, int h, int w, const float* sample_scale, void* rows, long long plane_stride,
+                    int np, void* stream);
+/* Weight gradient of a 4x4 / stride-2 conv between a 3-channel image [n][h][w][3], given as padded bf16 rows (patches
+ * assembled on chip), and a bf16-plane tensor on the [n][h/2][w/2] grid, on tcgen05, dw += (the caller zeroes):
  *   img_side 1 (the image is the conv INPUT, model.py:135):        dw[co][64] (48 used) += sum other[pixel][co] * patch[pixel][:]
  *   img_side 2 (the image is the gradient at a deconv OUTPUT, :218): dw[64][ci] (48 used) += sum patch[pixel][:] * other[pixel][ci] */
-int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_act* other, int img_side, int np, float* dw, int cout,
-                  int cin, void* stream);
+int t2i_wgrad_img(const void* img_rows, long long plane_stride, int n, int h, int w, const t2i_act* other, int img_side,
+                  int np, float* dw, int cout, int cin, void* stream);
 /* y[r][o] = act(sum_k x[r][k] * w[o][k] + bias[o]) in fp32 (the conditioning head, model.py:113-114). */
 int t2i_dense_f32(const float* x, int rows, int cin, const float* w, const float* bias, int cout, int act, float* y,
                   void* stream);

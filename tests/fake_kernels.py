@@ -67,26 +67,32 @@ class View:
             w[1].copy_((v - hi.float()).to(torch.bfloat16))
 
 
-class ImgPatches:
-    """kernels.ImgPatches: the 4x4 / s2 SAME patch matrix of an fp32 NHWC 3-channel image, as a conv_gemm operand"""
+def img_row_pitch(w):
+    return (3 * w + 6 + 3) // 4 * 4
 
-    def __init__(self, img, planes_like=None):
-        self.img, self.np = img, None
-        self.n, self.H, self.W, self.c = img.shape[0], img.shape[1], img.shape[2], 48
-        self.planes_like = planes_like      # the planes tensor (weights / other operand) that fixes np and the storage type
+
+def img_to_rows(img, rows, sample_scale=None):
+    """padded rows: entry j of a row = x[j - 3] (zeros outside), as planes [np, n, h, pitch]"""
+    n, h, w, _ = img.shape
+    x = img.double()
+    if sample_scale is not None:
+        x = x * sample_scale.double().view(-1, 1, 1, 1)
+    v = torch.zeros(n, h, img_row_pitch(w), dtype=torch.float64)
+    v[:, :, 3:3 + 3 * w] = x.reshape(n, h, 3 * w)
+    put(rows, v)
+
+
+class ImgPatches:
+    """kernels.ImgPatches: the 4x4 / s2 SAME patch matrix of a 3-channel image given as its padded rows (planes)"""
+
+    def __init__(self, rows, w):
+        self.rows, self.np = rows, rows.shape[0]
+        self.n, self.H, self.W, self.c = rows.shape[1], rows.shape[2], w, 48
 
     def values(self):
-        """[n, h/2, w/2, 48], column (kh*4 + kw)*3 + c.  The kernel forms the patches as bf16 planes on chip: the image
-        values the tensor core sees are bf16(x) (np = 1) or bf16(x) + bf16(x - bf16(x)) (np = 2)."""
-        n, h, w, _ = self.img.shape
-        x = self.img.double()
-        ref = self.planes_like
-        if ref is not None and ref.dtype == torch.bfloat16:
-            x32 = self.img.float()
-            hi = x32.to(torch.bfloat16).float()
-            x = hi.double()
-            if ref.shape[0] == 2:
-                x = x + (x32 - hi).to(torch.bfloat16).double()
+        """[n, h/2, w/2, 48], column (kh*4 + kw)*3 + c"""
+        n, h, w = self.n, self.H, self.W
+        x = val(self.rows)[:, :, 3:3 + 3 * w].reshape(n, h, w, 3)
         xp = F.pad(x, (0, 0, 1, 1, 1, 1))
         out = torch.zeros(n, h // 2, w // 2, 48, dtype=torch.float64)
         for kh in range(4):
@@ -118,8 +124,6 @@ def _conv_core(mode, k, flip, x, w):
 def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NONE, mask_kind=MASK_NONE,
               algo_scale=1.0, w_kn=False, stat_sum=None, stat_sq=None, stat_dot=None, stat_x=None, stat_n=0,
               stat_c=0, w_n0=0):
-    if isinstance(x, ImgPatches):
-        x.planes_like = w
     xv = x.values()
     wv = val(w)
     if w_kn:
@@ -164,7 +168,7 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
 
 
 def wgrad_img(img, other, dw, img_side):
-    pv = ImgPatches(img, other.t).values().reshape(-1, 48)
+    pv = img.values().reshape(-1, 48)
     ov = other.values().reshape(-1, other.c)
     if img_side == 1:
         dw[0, :other.c, :48] += ov.t() @ pv

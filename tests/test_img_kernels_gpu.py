@@ -22,6 +22,18 @@ def f32tol(np_):
     return (4e-3, 1.0) if np_ == 1 else (2e-5, 1.0)
 
 
+def rows_of(K, img, np_, scale=None):
+    """the image's padded bf16 rows, by the CPU restatement and by the CUDA kernel (bit-identical, asserted)"""
+    n, h, w, _ = img.shape
+    r = torch.zeros(np_, n, h, fk.img_row_pitch(w), dtype=torch.bfloat16)
+    fk.img_to_rows(img, r, scale)
+    rg = torch.full_like(r, 3.0).cuda()
+    K.img_to_rows(img.cuda(), rg, None if scale is None else scale.cuda())
+    torch.cuda.synchronize()
+    assert torch.equal(rg.cpu(), r)
+    return r, rg
+
+
 IMG_CASES = [
     # name, N, H, W, Cout
     ("d_h0", 3, 64, 64, 128),
@@ -44,19 +56,22 @@ def test_conv_from_image_forward_and_tangent(K, case, np_):
     w[:, :, :, 48:] = 0
     bias = torch.randn(Co, generator=gen) * 0.1
     y = torch.zeros(np_, N, H // 2, W // 2, Co, dtype=torch.bfloat16)
-    fk.conv_gemm(fk.CONV_K4S2, 4, 0, fk.ImgPatches(img), w, fk.View(y), bias=bias, act=fk.ACT_LRELU)
-    imgg, wg = img.cuda(), w.cuda()
+    rows, rows_g = rows_of(K, img, np_)
+    fk.conv_gemm(fk.CONV_K4S2, 4, 0, fk.ImgPatches(rows, W), w, fk.View(y), bias=bias, act=fk.ACT_LRELU)
+    wg = w.cuda()
     yg = torch.full_like(y, 3.0).cuda()
-    K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(imgg), wg, K.View(yg), bias=bias.cuda(), act=K.ACT_LRELU)
+    K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(rows_g, W), wg, K.View(yg), bias=bias.cuda(), act=K.ACT_LRELU)
     torch.cuda.synchronize()
     check_close(name, fk.val(yg.cpu()), fk.val(y), *tol(np_))
     # tangent pass over a sample sub-range, in place over the forward activations
     n0, n = (1, N - 1) if N > 1 else (0, 1)
     timg = torch.randn(N, H, W, 3, generator=gen)
+    coef = torch.rand(N, generator=gen) + 0.5
+    trows, trows_g = rows_of(K, timg, np_, coef)           # per-sample scaled, as the penalty's tangent seeds are
     y2 = yg.cpu().clone()
-    fk.conv_gemm(fk.CONV_K4S2, 4, 0, fk.ImgPatches(timg[n0:n0 + n]), w, fk.View(y2, n0, n), mask=fk.View(y2, n0, n),
+    fk.conv_gemm(fk.CONV_K4S2, 4, 0, fk.ImgPatches(trows[:, n0:n0 + n], W), w, fk.View(y2, n0, n), mask=fk.View(y2, n0, n),
                  mask_kind=fk.MASK_LRELU)
-    K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(timg.cuda()[n0:n0 + n]), wg, K.View(yg, n0, n), mask=K.View(yg, n0, n),
+    K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(trows_g[:, n0:n0 + n], W), wg, K.View(yg, n0, n), mask=K.View(yg, n0, n),
                 mask_kind=K.MASK_LRELU)
     torch.cuda.synchronize()
     check_close(name + "_tangent", fk.val(yg.cpu()), fk.val(y2), *tol(np_))
@@ -76,11 +91,12 @@ def test_conv_from_image_kn_with_mask_and_bn_reductions(K, np_, cin):
     xpre = rand_planes(np_, (N, 32, 32, cin), gen)
     y = torch.zeros(np_, N, 32, 32, cin, dtype=torch.bfloat16)
     s_sum, s_dot = torch.zeros(cin, dtype=torch.float64), torch.zeros(cin, dtype=torch.float64)
-    fk.conv_gemm(fk.CONV_K4S2, 4, 0, fk.ImgPatches(dimg), w, fk.View(y), w_kn=True, mask=fk.View(mask), mask_kind=fk.MASK_RELU,
+    rows, rows_g = rows_of(K, dimg, np_)
+    fk.conv_gemm(fk.CONV_K4S2, 4, 0, fk.ImgPatches(rows, W), w, fk.View(y), w_kn=True, mask=fk.View(mask), mask_kind=fk.MASK_RELU,
                  stat_sum=s_sum, stat_dot=s_dot, stat_x=fk.View(xpre))
     yg = torch.zeros_like(y).cuda()
     g_sum, g_dot = torch.zeros(cin, device="cuda"), torch.zeros(cin, device="cuda")
-    K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(dimg.cuda()), w.cuda(), K.View(yg), w_kn=True, mask=K.View(mask.cuda()),
+    K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(rows_g, W), w.cuda(), K.View(yg), w_kn=True, mask=K.View(mask.cuda()),
                 mask_kind=K.MASK_RELU, stat_sum=g_sum, stat_dot=g_dot, stat_x=K.View(xpre.cuda()))
     torch.cuda.synchronize()
     check_close("dgrad", fk.val(yg.cpu()), fk.val(y), *tol(np_))
@@ -146,13 +162,14 @@ def test_wgrad_img(K, case, np_):
     other = rand_planes(np_, (N, H // 2, W // 2, C), gen)
     shape = (1, C, 64) if side == 1 else (1, 64, C)
     dw = torch.zeros(shape, dtype=torch.float64)
-    fk.wgrad_img(img, fk.View(other), dw, side)
+    rows, rows_g = rows_of(K, img, np_)
+    fk.wgrad_img(fk.ImgPatches(rows, W), fk.View(other), dw, side)
     dg = torch.zeros(shape, device="cuda")
-    K.wgrad_img(img.cuda(), K.View(other.cuda()), dg, side)
+    K.wgrad_img(K.ImgPatches(rows_g, W), K.View(other.cuda()), dg, side)
     torch.cuda.synchronize()
     check_close(name, dg, dw, *f32tol(np_))
     # accumulates (+=) into what is there
-    K.wgrad_img(img.cuda(), K.View(other.cuda()), dg, side)
+    K.wgrad_img(K.ImgPatches(rows_g, W), K.View(other.cuda()), dg, side)
     torch.cuda.synchronize()
     check_close(name + "_acc", dg, 2 * dw, *f32tol(np_))
 

@@ -76,7 +76,8 @@ SIGNATURES = {
     "t2i_ca_fwd": [_P, _P, _P, _P, _LL, _I, _I, _I, _I, _P, _P],
     "t2i_ca_bwd": [_P, _P, _LL, _P, _P, _LL, _I, _I, _I, _I, _F, _P],
     "t2i_deconv_img": [C.POINTER(Act), _P, _LL, _I, _I, _I, _I, _P, _P, _P, _P, _P, _P],
-    "t2i_wgrad_img": [_P, _I, _I, _I, C.POINTER(Act), _I, _I, _P, _I, _I, _P],
+    "t2i_wgrad_img": [_P, _LL, _I, _I, _I, C.POINTER(Act), _I, _I, _P, _I, _I, _P],
+    "t2i_img_to_rows": [_P, _I, _I, _I, _P, _P, _LL, _I, _P],
     "t2i_dense_f32": [_P, _I, _I, _P, _P, _I, _I, _P, _P],
     "t2i_scale_rows": [_P, _P, _P, _LL, _I, _P],
     "t2i_d_seeds": [_P, _P, _I, _F, _P],

@@ -74,7 +74,8 @@ struct alignas(64) ConvGemmParams {
     int dbg;                   // T2I_STAT_DBG bit field (tools/bench_conv.py): skip parts of the statistics path
     // A_IMG: the A operand is the 4x4 / stride-2 patch matrix of this fp32 NHWC 3-channel image (row = output pixel,
     // column (kh*4 + kw)*3 + c, 48 columns), assembled in shared memory by two producer warps -- never in HBM
-    const float* img;
+    const uint32_t* img;       // padded bf16 rows [np][N][img_h][pitch] as 32-bit words (t2i_img_to_rows)
+    long long img_plane_words; // words between the planes
     int img_h, img_w;
     // debug build + T2I_TIMELINE=1 (tools/conv_timeline.py): CTA 0 records %globaltimer at the pipeline's hand-over points of its
     // first 64 tiles: [tile][event], events 0 weights TMA issued, 1 patch rows arrived, 2 MMA sees the stage, 3 MMA
@@ -186,15 +187,15 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
     float* s_bias = reinterpret_cast<float*>(s_sx + (prm.has_sx ? G * D * np * kSubBytes : 0));
     float* s_stat = s_bias + 2 * BLOCK_N;           // STATS: per group [2 statistics][2 column halves][4 lane quarters][32]
     float* s_acc = s_stat + (STATS ? 1024 : 0);     // STATS: per group running totals [2][stat_acc] (0 = straight to global)
-    // A_IMG: kImgRing x [2*bp + 2][img_w * 3] raw fp32 image rows (cp.async ring), then np bf16 padded row buffers
-    float* s_img = s_acc + (STATS ? 4 * prm.stat_acc : 0);
-    uint32_t* s_bf = reinterpret_cast<uint32_t*>(s_img + (A_IMG ? kImgRing * (2 * prm.bp + 2) * prm.img_w * 3 : 0));
-    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_bf + (A_IMG ? np * (2 * prm.bp + 2) * img_pitch_words(prm.img_w) : 0));
+    // A_IMG: ring of kImgRing slots, each np x [2*bp + 2] padded bf16 image rows (bulk copies, tiles ahead)
+    uint32_t* s_img = reinterpret_cast<uint32_t*>(s_acc + (STATS ? 4 * prm.stat_acc : 0));
+    uint64_t* full_bar = reinterpret_cast<uint64_t*>(s_img + (A_IMG ? kImgRing * np * (2 * prm.bp + 2) * img_pitch_words(prm.img_w) : 0));
     uint64_t* empty_bar = full_bar + kMaxStages;
     uint64_t* tmem_full = empty_bar + kMaxStages;
     uint64_t* tmem_empty = tmem_full + 4;
     uint64_t* aux_full = tmem_empty + 4;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(aux_full + 4);
+    uint64_t* rows_full = aux_full + 4;          // A_IMG: one per ring slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rows_full + kImgRing);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -213,6 +214,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
             mbar_init(&tmem_empty[i], kPair * (kEpiGroup / 32) * (prm.epi_split ? prm.epi_groups : 1));
         }
         for (int i = 0; i < 4; ++i) mbar_init(&aux_full[i], 1);
+        for (int i = 0; i < kImgRing; ++i) mbar_init(&rows_full[i], 1);
         fence_barrier_init();
     }
     if (CTA2) cluster_sync_all();               // peer barriers exist before anything can target them
@@ -348,34 +350,28 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
     } else if (A_IMG && warp >= 10) {
         // ------------------------------------------------ image-patch producers (64 threads, two tile rows each)
         const int pt = threadIdx.x - kThreads;
-        const int iw3 = prm.img_w * 3;
         const int n_rows = 2 * prm.bp + 2;
-        const int img_floats = n_rows * iw3;
-        // the rows of the next kImgRing - 1 tiles stream into the ring (cp.async) while this tile's patches are assembled:
-        // one tile's work is far shorter than the memory latency.  Every iteration commits exactly one group (an empty
-        // one past the end), so "all but the newest kImgRing - 2 groups are complete" always means "this tile is in".
-        auto prefetch = [&](int tile, int buf) {
-            if (tile >= prm.total_tiles) {
-                cp_async_commit();
-                return;
-            }
+        const int pitchw = img_pitch_words(prm.img_w);
+        const int slot_words = np * n_rows * pitchw;
+        const long long sample_words = static_cast<long long>(prm.img_h) * pitchw;
+        // the rows of the next kImgRing - 1 tiles are in flight (bulk copies) while this tile's patches are assembled:
+        // one tile's work is far shorter than the memory latency
+        auto fetch = [&](int tile, int slot) {
+            if (tile >= prm.total_tiles) return;
             const TileCoord tn = decode_tile(prm, tile, 1, 0);
-            img_rows_prefetch(prm.img + static_cast<long long>(tn.n0) * prm.img_h * iw3, 2 * tn.p0 - 1, prm.img_h, n_rows, iw3,
-                              s_img + buf * img_floats, prm.img, pt, kImgProducers);
-            cp_async_commit();
+            img_rows_fetch(prm.img, prm.img_plane_words, sample_words, np, tn.n0, 2 * tn.p0 - 1, prm.img_h, n_rows, pitchw,
+                           s_img + slot * slot_words, &rows_full[slot], pt, kImgProducers);
         };
-        int stage = 0, buf = 0;
+        int stage = 0, slot = 0, round = 0;
         uint32_t phase = 0;
-        for (int a = 0; a < kImgRing - 1; ++a) prefetch(unit0 + a * unit_stride, a);
-        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride, buf = (buf + 1) & (kImgRing - 1)) {
+        for (int a = 0; a < kImgRing - 1; ++a) fetch(unit0 + a * unit_stride, a);
+        for (int tile = unit0; tile < prm.total_tiles; tile += unit_stride) {
             const TileCoord tc = decode_tile(prm, tile, 1, 0);
-            cp_async_wait_pending<kImgRing - 2>();
-            named_bar_sync(5, kImgProducers);     // every producer's rows of this tile are in; the oldest ring slot is free
-            prefetch(tile + (kImgRing - 1) * unit_stride, (buf + kImgRing - 1) & (kImgRing - 1));
-            const int pitchw = img_pitch_words(prm.img_w);
-            uint32_t* s_lo = (np == 2) ? s_bf + n_rows * pitchw : nullptr;
-            img_rows_convert(s_img + buf * img_floats, n_rows, iw3, s_bf, s_lo, pitchw, pt, kImgProducers);
-            named_bar_sync(5, kImgProducers);     // the bf16 rows are complete
+            named_bar_sync(5, kImgProducers);     // everybody is done with the previous tile: its ring slot is free
+            fetch(tile + (kImgRing - 1) * unit_stride, (slot + kImgRing - 1) & (kImgRing - 1));
+            mbar_wait(&rows_full[slot], round & 1, 800 + slot);
+            const uint32_t* s_bf = s_img + slot * slot_words;
+            const uint32_t* s_lo = s_bf + n_rows * pitchw;
             for (int pass = 0; pass < prm.n_pass; ++pass) {
                 const uint32_t* plane = (pass == 1) ? s_lo : s_bf;             // A plane: hi, lo, hi
                 mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
@@ -394,6 +390,10 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
                     stage = 0;
                     phase ^= 1;
                 }
+            }
+            if (++slot == kImgRing) {
+                slot = 0;
+                ++round;
             }
         }
     } else if (!A_IMG || warp < 10) {
@@ -820,6 +820,7 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     const t2i_act& y = d->y;
     if ((x.ptr == nullptr && !a_img) || y.ptr == nullptr || d->w == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
     if (a_img && (x.c != 48 || x.w % 4 != 0)) return fail(T2I_ERR_BAD_ARG, "x_img: x.c must be 48 and the width a multiple of 4");
+    if (a_img && (reinterpret_cast<uintptr_t>(d->x_img) & 15) != 0) return fail(T2I_ERR_BAD_ARG, "x_img must be 16-byte aligned");
     // weight matrix per tap: w_rows x w_cols, cols contiguous.  NK: rows = output channels, cols = contraction;
     // KN: rows = contraction, cols = output channels.
     const bool kn = d->w_layout == T2I_W_KN;
@@ -929,11 +930,12 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
         }
         prm.timeline = want ? g_timeline : nullptr;
     }
-    prm.img = d->x_img;
+    prm.img = static_cast<const uint32_t*>(d->x_img);
+    prm.img_plane_words = x.plane_stride / 2;
     prm.img_h = x.h;
     prm.img_w = x.w;
-    const int img_bytes = a_img ? (2 * prm.bp + 2) * (kImgRing * x.w * 3 * 4 + d->np * img_pitch_words(x.w) * 4) : 0;   // raw ring + bf16 planes
-    const int tail_bytes = 2 * block_n * 4 + (stats ? 2 * (2048 + 8 * prm.stat_acc) : 0) + img_bytes + 256;   // bias, statistics (per group), image rows, barriers
+    const int img_bytes = a_img ? kImgRing * d->np * (2 * prm.bp + 2) * img_pitch_words(x.w) * 4 : 0;   // the ring of padded bf16 rows
+    const int tail_bytes = 2 * block_n * 4 + (stats ? 2 * (2048 + 8 * prm.stat_acc) : 0) + img_bytes + 512;   // bias, statistics (per group), image rows, barriers
     int stages = (kSmemBudget - epi_bytes - tail_bytes) / stage_bytes;
     if (stages > kMaxStages) stages = kMaxStages;
     if (stages < 2) return fail(T2I_ERR_BAD_ARG, "shared memory plan leaves %d pipeline stages", stages);

@@ -51,6 +51,39 @@ __global__ void scale_rows_kernel(const float* __restrict__ src, const float* __
     }
 }
 
+// fp32 NHWC 3-channel image -> padded bf16 rows (planes [np][n][h][pitch], pitch = 4 * ceil((3w + 6) / 4) entries):
+// B[j] = x[j - 3], zeros outside.  What the image-patch producers of conv_gemm / wgrad_gemm stream (img_patch.cuh).
+__global__ void img_to_rows_kernel(const float* __restrict__ img, int n, int h, int w, const float* __restrict__ sample_scale,
+                                   bf16* rows, long long ps, int np) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int iw3 = w * 3, cpr = (iw3 + 6 + 3) / 4;             // 4-entry chunks per row
+    const long long total = (long long)n * h * cpr;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i % cpr);
+        const long long r = i / cpr;                              // (sample, row)
+        const float sc = sample_scale ? sample_scale[r / h] : 1.f;
+        const float* src = img + r * iw3;
+        float v[4];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+            const int j = 4 * c - 3 + e;
+            v[e] = (j >= 0 && j < iw3) ? src[j] * sc : 0.f;
+        }
+        bf16* dst = rows + (r * cpr + c) * 4;
+        uint2 hi;
+        hi.x = pack_bf16x2(v[0], v[1]);
+        hi.y = pack_bf16x2(v[2], v[3]);
+        *reinterpret_cast<uint2*>(dst) = hi;
+        if (np == 2) {
+            uint2 lo;
+            lo.x = pack_bf16x2(v[0] - bf16_lo(hi.x), v[1] - bf16_hi(hi.x));
+            lo.y = pack_bf16x2(v[2] - bf16_lo(hi.y), v[3] - bf16_hi(hi.y));
+            *reinterpret_cast<uint2*>(dst + ps) = lo;
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------
 // 3-channel 4x4/s2 patch matrix.  Row r = (n, p, q) of the (h/2 x w/2) grid, column
 // (kh*4 + kw)*3 + c holds img[n, 2p-1+kh, 2q-1+kw, c] (zero outside); columns 48..63 are zero.
@@ -1164,6 +1197,13 @@ extern "C" int t2i_scale_rows(const float* src, const float* row_scale, float* d
     if (cols % 4 != 0) return fail(T2I_ERR_BAD_ARG, "scale_rows: cols=%d must be a multiple of 4", cols);
     launch_ew(scale_rows_kernel, dim3(grid_for(rows * cols / 4, 256)), dim3(256), 0, STREAM, src, row_scale, dst, rows, cols);
     return check_launch("scale_rows");
+}
+extern "C" int t2i_img_to_rows(const float* img, int n, int h, int w, const float* sample_scale, void* rows,
+                               long long plane_stride, int np, void* stream) {
+    const long long chunks = (long long)n * h * ((w * 3 + 6 + 3) / 4);
+    launch_ew(img_to_rows_kernel, dim3(grid_for(chunks, 256)), dim3(256), 0, STREAM, img, n, h, w, sample_scale,
+              static_cast<bf16*>(rows), plane_stride, np);
+    return check_launch("img_to_rows");
 }
 extern "C" int t2i_im2col_k4s2_c3(const float* img, int n, int h, int w, const float* sample_scale, void* col,
                                   long long ps, int np, void* stream) {

@@ -24,10 +24,11 @@ namespace t2i {
 constexpr int kWK = 64;                       // pixels per K block
 constexpr int kWAtomBytes = kWK * 128;        // 64 pixels x 64 channels bf16 = 8 KB
 constexpr int kWThreads = 192;
-constexpr int kWImgProducers = 64;            // IMG: two more warps assemble the 64 patch rows of a K block
-constexpr int kWThreadsImg = kWThreads + kWImgProducers;
-constexpr int kWImgRing = 4;                  // IMG: raw image-row buffers in flight (cp.async ring, K blocks ahead)
-constexpr int kWImgRowBytes = kWImgRing * 12288 + 8192;   // IMG: fp32 image rows ring ((2*bp + 2) rows of w*3 floats each) + bf16 rows
+// IMG: warps 2..7 (the four reduction warps, idle until a work item ends, plus two more) feed the patch rows of the K blocks
+constexpr int kWImgProducers = 192;
+constexpr int kWThreadsImg = 64 + kWImgProducers;
+constexpr int kWImgRing = 4;                  // IMG: ring slots of padded bf16 image rows in flight (bulk copies, K blocks ahead)
+constexpr int kWImgRowBytes = kWImgRing * 6400;   // a slot: (2*bp + 2) rows of one plane (the pass's), at most 6400 bytes
 
 // CTA2: a CTA pair (cta_group::2) computes 256 output channels x BN input channels; each CTA stages its
 // own 128 output channels of dy and HALF of the x tile, and reduces its own 128 accumulator rows.
@@ -68,7 +69,8 @@ struct alignas(64) WgradParams {
     float* dw;
     // IMG: one operand is the 4x4 / stride-2 patch matrix of this fp32 NHWC 3-channel image (64 columns, 48 used),
     // assembled in shared memory (see conv_gemm.cu, A_IMG)
-    const float* img;
+    const uint32_t* img;       // padded bf16 rows [np][N][img_h][pitch] as words (t2i_img_to_rows)
+    long long img_plane_words;
     int img_h, img_w;
 };
 
@@ -88,7 +90,8 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
     uint64_t* empty_bar = full_bar + kStages;
     uint64_t* tmem_full = empty_bar + kStages;
     uint64_t* tmem_empty = tmem_full + 2;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+    uint64_t* rows_full = tmem_empty + 2;       // IMG: one per ring slot
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(rows_full + kWImgRing);
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -99,13 +102,15 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
         if (IMG != 2)      // IMG = 2: dy is the image patch matrix, there is no dy tensor map
             for (int i = 0; i < (prm.tt.n_phases > 1 ? prm.tt.n_phases : 1); ++i) tma_prefetch_desc(&prm.dy_maps[i]);
         for (int i = 0; i < kStages; ++i) {
-            mbar_init(&full_bar[i], IMG ? 1 + kWImgProducers : kPair);
+            mbar_init(&full_bar[i], IMG ? 1 + kWK : kPair);      // IMG: the TMA thread + the 64 threads that write patch rows
             mbar_init(&empty_bar[i], 1);
         }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&tmem_full[i], 1);
             mbar_init(&tmem_empty[i], kPair * 4);      // the four reduction warps of both CTAs (leader's copy)
         }
+        if (IMG != 0)
+            for (int i = 0; i < kWImgRing; ++i) mbar_init(&rows_full[i], 1);
         fence_barrier_init();
     }
     if (CTA2) cluster_sync_all();
@@ -147,6 +152,49 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
         return k;
     };
     const int w0 = blockIdx.x / kPair, w_stride = gridDim.x / kPair;
+
+    // accumulator of work item wk (the it-th of this CTA) -> red.global.add into dw; executed by warps 2..5
+    auto reduce_item = [&](const Work& wk, int it) {
+        const int quarter = warp & 3;
+        const int acc = it & 1;
+        const Tap tap = prm.tt.taps[wk.job];
+        const int co_cta = (wk.cot * kPair + rank) * Cfg::kM;
+        mbar_wait(&tmem_full[acc], (it >> 1) & 1, 400 + acc);
+        tc_fence_after();
+#pragma unroll 1
+        for (int mt = 0; mt < MT; ++mt) {
+            const int co = co_cta + mt * 128 + quarter * 32 + lane;
+            const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + mt * BN + (static_cast<uint32_t>(quarter * 32) << 16);
+            float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
+#pragma unroll 1
+            for (int c0 = 0; c0 < BN; c0 += 32) {
+                const int ci0 = wk.cit * BN + c0;
+                if (ci0 >= prm.cin) break;
+                __syncwarp();
+                uint32_t r[32];
+                tmem_ld_32x32(taddr + c0, r);
+                tmem_ld_wait();
+                if (co < prm.cout) {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) {
+                        const int ci = ci0 + g * 4;
+                        if (ci < prm.cin)
+                            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci),
+                                         "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
+                                         "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
+                                         : "memory");
+                    }
+                }
+            }
+        }
+        // accumulator read: hand the TMEM buffer back to the MMA warp (of the leader CTA)
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+            if (CTA2 && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
+            else mbar_arrive(&tmem_empty[acc]);
+        }
+    };
 
     if (warp == 0) {
         if (elect_one()) {
@@ -258,17 +306,16 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
                 ++it;
             }
         }
-    } else if (IMG != 0 && warp >= 6) {
-        // image-patch producers: 64 threads, one pixel row of the K block each.  The K blocks this CTA will visit form
-        // one sequence (work item, pass, block); the image rows of the NEXT block stream into the other buffer
-        // (cp.async) while the current block's patches are assembled.
-        const int pt = threadIdx.x - kWThreads;
-        float* s_img = reinterpret_cast<float*>(smem + Cfg::kImgOffset);
-        const int iw3 = prm.img_w * 3;
+    } else if (IMG != 0) {
+        // warps 2..7: image-patch producers (one pixel row of the K block per thread for the first 64 of them); warps
+        // 2..5 reduce a work item when its last block has been produced.  The K blocks this CTA will visit form one
+        // sequence (work item, pass, block); the padded bf16 image rows of the next kWImgRing - 1 blocks are in flight.
+        const int pt = threadIdx.x - 64;
+        uint32_t* s_img = reinterpret_cast<uint32_t*>(smem + Cfg::kImgOffset);
         const int n_rows = 2 * prm.bp + 2;
-        const int img_floats = n_rows * iw3;
         const int pitchw = img_pitch_words(prm.img_w);
-        uint32_t* s_bf = reinterpret_cast<uint32_t*>(s_img + kWImgRing * img_floats);      // one bf16 padded row buffer (the pass's plane)
+        const int slot_words = n_rows * pitchw;
+        const long long sample_words = static_cast<long long>(prm.img_h) * pitchw;
         struct Cursor {
             int w, pass, kb, kb_begin, kb_end;
             bool valid;
@@ -294,97 +341,63 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
             c.w += w_stride;
             settle(c);
         };
-        auto prefetch = [&](const Cursor& c, int buf) {      // exactly one cp.async group per call (empty past the end)
-            if (!c.valid) {
-                cp_async_commit();
-                return;
-            }
+        auto fetch = [&](const Cursor& c, int slot) {
+            if (!c.valid) return;
             const int tp = (c.kb / prm.tiles_q) % prm.tiles_p;
             const int tn = c.kb / (prm.tiles_q * prm.tiles_p);                   // bn == 1: the sample
-            img_rows_prefetch(prm.img + static_cast<long long>(tn) * prm.img_h * iw3, 2 * tp * prm.bp - 1, prm.img_h, n_rows, iw3,
-                              s_img + buf * img_floats, prm.img, pt, kWImgProducers);
-            cp_async_commit();
+            const bool lo_plane = (IMG == 1) ? (c.pass == 2) : (c.pass == 1);     // x: hi, hi, lo; dy: hi, lo, hi
+            img_rows_fetch(prm.img + (lo_plane ? prm.img_plane_words : 0), 0, sample_words, 1, tn, 2 * tp * prm.bp - 1,
+                           prm.img_h, n_rows, pitchw, s_img + slot * slot_words, &rows_full[slot], pt, kWImgProducers);
         };
         Cursor cur;
         cur.w = w0;
         settle(cur);
         Cursor pf = cur;                         // runs kWImgRing - 1 blocks ahead of cur
         for (int a = 0; a < kWImgRing - 1; ++a) {
-            prefetch(pf, a);
+            fetch(pf, a);
             if (pf.valid) advance(pf);
         }
-        int stage = 0, buf = 0;
+        int stage = 0, slot = 0, round = 0, it = 0;
         uint32_t phase = 0;
         while (cur.valid) {
             Cursor nxt = cur;
             advance(nxt);
-            cp_async_wait_pending<kWImgRing - 2>();
-            named_bar(3, kWImgProducers);       // every producer's rows of this block are in; the oldest ring slot is free
-            prefetch(pf, (buf + kWImgRing - 1) & (kWImgRing - 1));
+            named_bar(3, kWImgProducers);       // everybody is done with the previous block: its ring slot is free
+            fetch(pf, (slot + kWImgRing - 1) & (kWImgRing - 1));
             if (pf.valid) advance(pf);
-            const bool lo_plane = (IMG == 1) ? (cur.pass == 2) : (cur.pass == 1);     // x: hi, hi, lo; dy: hi, lo, hi
-            img_rows_convert(s_img + buf * img_floats, n_rows, iw3, s_bf, lo_plane ? s_bf : nullptr, pitchw, pt, kWImgProducers);
-            named_bar(4, kWImgProducers);       // the bf16 rows (of the plane this pass needs) are complete
-            const int q0 = (cur.kb % prm.tiles_q) * prm.bq;
-            mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
-            uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
-            int q = q0 + (pt & (prm.bq - 1));
-            if (q >= prm.Q) q = prm.Q - 1;
-            img_patch_row(s_bf, pitchw, pt / prm.bq, q, atom + (pt >> 3) * 1024 + (pt & 7) * 128, pt, true);   // columns 48..63: zeros
-            fence_proxy_async();
-            mbar_arrive(&full_bar[stage]);
+            if (pt < kWK) {
+                mbar_wait(&rows_full[slot], round & 1, 800 + slot);
+                const int q0 = (cur.kb % prm.tiles_q) * prm.bq;
+                mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
+                uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
+                int q = q0 + (pt & (prm.bq - 1));
+                if (q >= prm.Q) q = prm.Q - 1;
+                img_patch_row(s_img + slot * slot_words, pitchw, pt / prm.bq, q, atom + (pt >> 3) * 1024 + (pt & 7) * 128, pt,
+                              true);   // columns 48..63: zeros
+                fence_proxy_async();
+                mbar_arrive(&full_bar[stage]);
+            }
             if (++stage == kStages) {
                 stage = 0;
                 phase ^= 1;
             }
+            if (++slot == kWImgRing) {
+                slot = 0;
+                ++round;
+            }
+            if (!nxt.valid || nxt.w != cur.w) {      // the work item is complete
+                if (warp < 6) reduce_item(decode(cur.w), it);
+                ++it;
+            }
             cur = nxt;
-            buf = (buf + 1) & (kWImgRing - 1);
         }
-    } else if (IMG == 0 || warp < 6) {
+    } else {
         // reduction warps: accumulator -> red.global.add into dw, while the MMAs of the next item run
-        const int quarter = warp & 3;
         int it = 0;
         for (int w = w0; w < prm.total_work; w += w_stride) {
             const Work wk = decode(w);
             if (wk.n_kb == 0) continue;
-            const int acc = it & 1;
-            const Tap tap = prm.tt.taps[wk.job];
-            const int co_cta = (wk.cot * kPair + rank) * Cfg::kM;
-            mbar_wait(&tmem_full[acc], (it >> 1) & 1, 400 + acc);
-            tc_fence_after();
-#pragma unroll 1
-            for (int mt = 0; mt < MT; ++mt) {
-                const int co = co_cta + mt * 128 + quarter * 32 + lane;
-                const uint32_t taddr = tmem_base + acc * Cfg::kAccCols + mt * BN + (static_cast<uint32_t>(quarter * 32) << 16);
-                float* row = prm.dw + (static_cast<long long>(tap.wtap) * prm.cout + co) * prm.cin;
-#pragma unroll 1
-                for (int c0 = 0; c0 < BN; c0 += 32) {
-                    const int ci0 = wk.cit * BN + c0;
-                    if (ci0 >= prm.cin) break;
-                    __syncwarp();
-                    uint32_t r[32];
-                    tmem_ld_32x32(taddr + c0, r);
-                    tmem_ld_wait();
-                    if (co < prm.cout) {
-#pragma unroll
-                        for (int g = 0; g < 8; ++g) {
-                            const int ci = ci0 + g * 4;
-                            if (ci < prm.cin)
-                                asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(row + ci),
-                                             "f"(__uint_as_float(r[g * 4 + 0])), "f"(__uint_as_float(r[g * 4 + 1])),
-                                             "f"(__uint_as_float(r[g * 4 + 2])), "f"(__uint_as_float(r[g * 4 + 3]))
-                                             : "memory");
-                        }
-                    }
-                }
-            }
-            // accumulator read: hand the TMEM buffer back to the MMA warp (of the leader CTA)
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) {
-                if (CTA2 && rank != 0) mbar_arrive_cluster(&tmem_empty[acc], 0);
-                else mbar_arrive(&tmem_empty[acc]);
-            }
+            reduce_item(wk, it);
             ++it;
         }
     }
@@ -460,8 +473,9 @@ static int launch_wgrad_img(const WgradParams& prm, int grid, cudaStream_t strea
 
 using namespace t2i;
 
-extern "C" int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_act* other, int img_side, int np, float* dw,
-                             int cout, int cin, void* stream_) {
+extern "C" int t2i_wgrad_img(const void* img, long long plane_stride, int n, int h, int w, const t2i_act* other, int img_side,
+                             int np, float* dw, int cout, int cin, void* stream_) {
+    if ((reinterpret_cast<uintptr_t>(img) & 15) != 0) return fail(T2I_ERR_BAD_ARG, "wgrad_img: rows must be 16-byte aligned");
     if (img == nullptr || other == nullptr || other->ptr == nullptr || dw == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
     if (np != 1 && np != 2) return fail(T2I_ERR_BAD_ARG, "np must be 1 or 2");
     if (img_side != 1 && img_side != 2) return fail(T2I_ERR_BAD_ARG, "img_side must be 1 (x) or 2 (dy)");
@@ -479,7 +493,7 @@ extern "C" int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_ac
         int p = floor_pow2(prm.P); if (p > kWK / q) p = kWK / q;
         prm.bq = q; prm.bp = p; prm.bn = kWK / (q * p);
     }
-    if (prm.bn != 1 || (2 * prm.bp + 2) * w * 3 * 4 > 12288 || (2 * prm.bp + 2) * img_pitch_words(w) * 4 > 8192)
+    if (prm.bn != 1 || (2 * prm.bp + 2) * img_pitch_words(w) * 4 > kWImgRowBytes / kWImgRing)
         return fail(T2I_ERR_BAD_ARG, "wgrad_img: unsupported image extent %d x %d", h, w);
     prm.tiles_q = ceil_div(prm.Q, prm.bq);
     prm.tiles_p = ceil_div(prm.P, prm.bp);
@@ -508,7 +522,7 @@ extern "C" int t2i_wgrad_img(const float* img, int n, int h, int w, const t2i_ac
     prm.kb_per_split = ceil_div(prm.k_blocks, splits);
     prm.splits = ceil_div(prm.k_blocks, prm.kb_per_split);
     prm.dw = dw;
-    prm.img = img; prm.img_h = h; prm.img_w = w;
+    prm.img = static_cast<const uint32_t*>(img); prm.img_plane_words = plane_stride / 2; prm.img_h = h; prm.img_w = w;
     int rc = make_maps(*other, false, np, prm.bq, prm.bp, prm.bn, img_side == 1 ? prm.dy_maps : prm.x_maps);
     if (rc != T2I_OK) return rc;
     prm.total_work = tiles * prm.splits;

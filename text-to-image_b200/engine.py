@@ -475,9 +475,10 @@ class Engine:
         f32 = dict(device=self.dev, dtype=self.f32_dtype)
         planes = self._planes
         d = self.d = {}
-        # [fake | real | mismatch | x_hat]; after the penalty seeds exist, segment 3 holds the TANGENT image
-        # coef * dD/dx_hat instead (the x_hat fetch recomputes the interpolation)
-        d["img"] = torch.zeros(S, IMG, IMG, 3, **f32)
+        d["img"] = torch.zeros(S, IMG, IMG, 3, **f32)     # [fake | real | mismatch | x_hat]
+        # the same images as padded bf16 rows (what the first conv's kernels stream); after the penalty seeds exist
+        # segment 3 holds the TANGENT image coef * dD/dx_hat instead
+        d["rows"] = planes(S, IMG, self.K.img_row_pitch(IMG))
         dshapes = {"a0": (S, 32, 32, df), "a1": (S, 16, 16, 2 * df), "a2": (S, 8, 8, 4 * df), "a3": (S, 4, 4, 8 * df),
                    "r1": (S, 4, 4, 2 * df), "r2": (S, 4, 4, 4 * df), "cat": (S, 4, 4, 8 * df + ce),
                    "a5": (S, 4, 4, 8 * df), "a6": (S, 4, 4, 8 * df)}
@@ -519,6 +520,7 @@ class Engine:
         g["d_ms"] = planes(B, 2 * ce)
         g["u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
         g["d_u4"] = torch.zeros(B, IMG, IMG, 3, **f32)
+        g["d_u4_rows"] = planes(B, IMG, self.K.img_row_pitch(IMG))
         g["tn"] = torch.zeros(B, ce, **f32)
         g["z"] = torch.zeros(B, Z, **f32)
         g["kl_scratch"] = torch.zeros(1, **f32)
@@ -656,10 +658,12 @@ class Engine:
             conv_bwd(c_a, x, "d_" + t_a, g["d_" + x], add=V(ds), **last_epi)     # skip connection joins here
 
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
-        # the 4x4/s2 patches of d_u4 are formed on chip by both kernels (no patch matrix in HBM)
+        # the 4x4/s2 patches of d_u4 are formed on chip by both kernels from its padded bf16 rows (no patch matrix in HBM)
+        K.img_to_rows(g["d_u4"], g["d_u4_rows"])
+        du4 = K.ImgPatches(g["d_u4_rows"], IMG)
         with self._side():
-            K.wgrad_img(g["d_u4"], V(g["h5"]), gl["t3"].gw, 2)
-        K.conv_gemm(K4, 4, 0, K.ImgPatches(g["d_u4"]), gl["t3"].Wf, V(g["d_h5"]), w_kn=True,
+            K.wgrad_img(du4, V(g["h5"]), gl["t3"].gw, 2)
+        K.conv_gemm(K4, 4, 0, du4, gl["t3"].Wf, V(g["d_h5"]), w_kn=True,
                     mask=V(g["h5"]), mask_kind=RELU, **bn_red(9, g["t9"]))
         bn_bwd(9, g["d_h5"], g["t9"], g["d_t9"], gl["c8"].gb)
         conv_bwd("c8", "d3", "d_t9", g["d_d3"], stat_sum=gl["t2"].gb)      # gradient at t2's output: its bias gradient
@@ -714,9 +718,11 @@ class Engine:
             K.conv_gemm(L.mode, L.k, 0, x, L.Wf, y, add=add, **kw)
 
         done = after if after is not None else (lambda buf: None)   # `buf` holds its final values for this pass
-        # :135 straight from the fp32 image (tangent pass: from the tangent image _d_body left in segment 3)
+        # :135 from the images' padded bf16 rows (tangent pass: _d_body left the tangent image's rows in segment 3)
+        if not tangent:
+            K.img_to_rows(d["img"][s0:s0 + n], d["rows"][:, s0:s0 + n])
         done("img"); done("cond")
-        cg("h0", K.ImgPatches(d["img"][s0:s0 + n]), V(d["a0"])); done("a0")
+        cg("h0", K.ImgPatches(d["rows"][:, s0:s0 + n], IMG), V(d["a0"])); done("a0")
         cg("h1", V(d["a0"]), V(d["a1"])); done("a1")                                # :136
         cg("h2", V(d["a1"]), V(d["a2"])); done("a2")                                # :137
         cg("h3", V(d["a2"]), V(d["a3"]), act=False); done("a3")                     # :138
@@ -778,7 +784,7 @@ class Engine:
         rows = self._rows
         x, dy = self.D_WGRAD[l]
         if l == "h0":
-            K.wgrad_img(d["img"][:n], K.View(d["d_a0"], 0, n), dl["h0"].gw, 1)
+            K.wgrad_img(K.ImgPatches(d["rows"][:, :n], IMG), K.View(d["d_a0"], 0, n), dl["h0"].gw, 1)
         elif l == "out":
             K.dout_bwd_weight(d["a6"][:, :n], d["seed"][:n], dl["out"].gw, dl["out"].gb, n_bias)
         else:
@@ -943,7 +949,7 @@ class Engine:
         K.gp_penalty(d["gx"], GP_WEIGHT, inv, d["slope"], d["coef"], self.sums["d"][4:5])       # :62-65
         K.gp_penalty(d["g2"], GP_WEIGHT, inv, d["slope2"], d["coef2"], self.sums["d"][5:6])     # :67-70
         # second-order term: tangent (coef * g) through d_net, in place over the x_hat segment
-        K.scale_rows(d["gx"], d["coef"], d["img"][3 * B:])
+        K.img_to_rows(d["gx"], d["rows"][:, 3 * B:], d["coef"])
         K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])
         with self._side():
             self.d_bias_grads(3 * B)             # first-order only (the JVP does not depend on biases)

@@ -97,19 +97,33 @@ def _prof_end(ev, kernel, tag, flops, nbytes):
         PROFILE.append([kernel, tag, flops, nbytes, ev, end])
 
 
-class ImgPatches:
-    """The 4x4 / stride-2 SAME patch matrix of an fp32 NHWC 3-channel image [n, h, w, 3] as the x operand of conv_gemm
-    (rows = pixels of the [n, h/2, w/2] grid, 48 columns (kh*4 + kw)*3 + c): it exists only in shared memory."""
+def img_row_pitch(w):
+    """entries per padded bf16 image row: 3 * w values behind 3 zeros, rounded up to a multiple of 4"""
+    return (3 * w + 6 + 3) // 4 * 4
 
-    def __init__(self, img):
-        assert img.dtype == torch.float32 and img.is_contiguous() and img.dim() == 4 and img.shape[3] == 3
-        self.img = img
-        self.np = None          # taken from the weights
-        self.n, self.H, self.W, self.c = img.shape[0], img.shape[1], img.shape[2], 48
+
+def img_to_rows(img, rows, sample_scale=None):
+    """fp32 NHWC [n, h, w, 3] (times sample_scale[n]) -> padded bf16 rows, planes [np, n, h, img_row_pitch(w)]"""
+    n, h, w, _ = img.shape
+    assert rows.dtype == torch.bfloat16 and rows.shape[1:] == (n, h, img_row_pitch(w)) and rows[0].is_contiguous()
+    _lib.call("t2i_img_to_rows", _f32(img), n, h, w, _p(sample_scale), _p(rows), _ps(rows), rows.shape[0], _stream())
+
+
+class ImgPatches:
+    """The 4x4 / stride-2 SAME patch matrix of a 3-channel image [n, h, w, 3] as the x operand of conv_gemm / wgrad_img
+    (rows = pixels of the [n, h/2, w/2] grid, 48 columns (kh*4 + kw)*3 + c): it exists only in shared memory.  The image
+    is given as its padded bf16 rows (img_to_rows), planes [np, n, h, pitch]; slices along n are fine."""
+
+    def __init__(self, rows, w):
+        assert rows.dtype == torch.bfloat16 and rows.dim() == 4 and rows.shape[3] == img_row_pitch(w) and rows[0].is_contiguous()
+        self.rows = rows
+        self.np = rows.shape[0]
+        self.n, self.H, self.W, self.c = rows.shape[1], rows.shape[2], w, 48
 
     def _act(self):
         a = _lib.Act()
         a.n, a.h, a.w, a.c, a.pitch = self.n, self.H, self.W, 48, 48
+        a.plane_stride = self.rows.stride(0)
         return a
 
 
@@ -128,8 +142,7 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     img = isinstance(x, ImgPatches)
     if img:
         assert mode == CONV_K4S2 and k == 4
-        x.np = w.shape[0]
-        d.x_img = x.img.data_ptr()
+        d.x_img = x.rows.data_ptr()
     d.mode, d.k, d.flip, d.np = mode, k, flip, x.np
     d.x = x._act()
     assert w.dtype == torch.bfloat16 and w.dim() == 4 and w[0].is_contiguous() and w.shape[0] == x.np
@@ -152,7 +165,7 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
         opix = y.n * y.H * y.W
         if img:       # 48 = 16 taps x 3 channels per output pixel; the image is read once as fp32
             flops = 2.0 * opix * y.c * 48 * (3 if x.np == 2 else 1)
-            nbytes = 4.0 * x.n * x.H * x.W * 3 + 2.0 * x.np * (opix * y.c * (1 + (add is not None) + (mask is not None)) + y.c * 48)
+            nbytes = 2.0 * x.np * (x.n * x.H * x.W * 3 + opix * y.c * (1 + (add is not None) + (mask is not None)) + y.c * 48)
             _prof_end(ev, "conv_gemm", "img k4s2 %dx%dx%d co%d" % (x.n, x.H, x.W, y.c), flops, nbytes)
             return
         flops = 2.0 * opix * y.c * x.c * _taps_per_output(mode, k) * algo_scale * (3 if x.np == 2 else 1)
@@ -181,19 +194,19 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
 
 
 def wgrad_img(img, other, dw, img_side):
-    """Weight gradient between the on-chip patch matrix of img (fp32 NHWC [n, h, w, 3]) and `other` (a View on the
+    """Weight gradient between the on-chip patch matrix of img (an ImgPatches) and `other` (a View on the
     [n, h/2, w/2] grid): img_side 1: dw[co, 64] += other^T patch (the image is the conv input); img_side 2:
     dw[64, ci] += patch^T other (the image is the gradient at a transposed conv's output).  dw: fp32 [1, rows, cols]."""
     ev = _prof_begin()
-    n, h, w, _ = img.shape
-    assert dw.dtype == torch.float32 and dw.dim() == 3 and dw.shape[0] == 1 and dw.is_contiguous()
+    n, h, w = img.n, img.H, img.W
+    assert dw.dtype == torch.float32 and dw.dim() == 3 and dw.shape[0] == 1 and dw.is_contiguous() and img.np == other.np
     a = other._act()
-    _lib.call("t2i_wgrad_img", _f32(img), n, h, w, C.byref(a), img_side, other.np, _f32(dw), dw.shape[1], dw.shape[2],
-              _stream())
+    _lib.call("t2i_wgrad_img", _p(img.rows), _ps(img.rows), n, h, w, C.byref(a), img_side, other.np, _f32(dw), dw.shape[1],
+              dw.shape[2], _stream())
     if ev is not None:
         pix = n * (h // 2) * (w // 2)
         flops = 2.0 * pix * other.c * 48 * (3 if other.np == 2 else 1)
-        nbytes = 4.0 * n * h * w * 3 + 2.0 * other.np * pix * other.c + 4.0 * other.c * 48
+        nbytes = 2.0 * other.np * (n * h * w * 3 + pix * other.c) + 4.0 * other.c * 48
         _prof_end(ev, "wgrad_gemm", "img side%d %dx%dx%d c%d" % (img_side, n, h, w, other.c), flops, nbytes)
 
 

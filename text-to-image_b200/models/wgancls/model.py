@@ -301,12 +301,8 @@ class WGanCls(object):
             # the remaining tensors of build_model (model.py:48-55) live in the engine's buffers after a D run:
             # image segments [fake | real | mismatch | x_hat] and one logit per sample of the 4B batch
             elif f.name == "x_hat":
-                # segment 3 of the image buffer holds the penalty's tangent image after a D run: recompute
-                # eps * G + (1 - eps) * x (model.py:53) from the segments / feed that are still in place
                 b = self.batch_size
-                xh = torch.empty(b, 64, 64, 3, device=self.device, dtype=torch.float32)
-                self._K.gp_interp(eng.d["img"][:b], eng.d["img"][b:2 * b], eng.feed["epsilon"], xh)
-                out.append(xh.cpu().numpy())
+                out.append(eng.d["img"][3 * b:].cpu().numpy())
             elif f.name in ("Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit"):
                 b = self.batch_size
                 k = ("Dg_logit", "Dx_logit", "Dxmi_logit", "Dx_hat_logit").index(f.name)

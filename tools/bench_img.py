@@ -47,19 +47,25 @@ def main():
     cond, wms, bms, ms = torch.randn(B, 1024, **f32), torch.randn(256, 1024, **f32) * 0.03, torch.zeros(256, **f32), torch.zeros(B, 256, **f32)
     V = K.View
     MB = 1e6
+    rows4 = torch.zeros(1, 4 * B, 64, K.img_row_pitch(64), **bf)
+    K.img_to_rows(img4, rows4)
+    gxrows = torch.zeros(1, B, 64, K.img_row_pitch(64), **bf)
+    P4, PB, PG = K.ImgPatches(rows4, 64), K.ImgPatches(rows4[:, :B], 64), K.ImgPatches(gxrows, 64)
+    RB = 64 * K.img_row_pitch(64) * 2      # bytes of one image as padded bf16 rows
     cases = [
-        ("h0_fwd_4B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(img4), w0, V(a0), bias=bias, act=K.ACT_LRELU),
-         (4 * B * 12288 * 4 + 4 * B * 1024 * 256) / MB),
-        ("h0_fwd_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(img4[:B]), w0, V(a0, 0, B), bias=bias, act=K.ACT_LRELU),
-         (B * 12288 * 4 + B * 1024 * 256) / MB),
-        ("h0_tangent_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(img4[:B]), w0, V(a0, 0, B), mask=V(a0, 0, B), mask_kind=K.MASK_LRELU),
-         (B * 12288 * 4 + 2 * B * 1024 * 256) / MB),
-        ("h0_wgrad_4B", lambda: K.wgrad_img(img4, V(d_a0), dw0, 1), (4 * B * 12288 * 4 + 4 * B * 1024 * 256) / MB),
+        ("h0_fwd_4B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, P4, w0, V(a0), bias=bias, act=K.ACT_LRELU),
+         (4 * B * RB + 4 * B * 1024 * 256) / MB),
+        ("img_to_rows_4B", lambda: K.img_to_rows(img4, rows4), (4 * B * (12288 * 4 + RB)) / MB),
+        ("h0_fwd_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, PB, w0, V(a0, 0, B), bias=bias, act=K.ACT_LRELU),
+         (B * RB + B * 1024 * 256) / MB),
+        ("h0_tangent_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, PB, w0, V(a0, 0, B), mask=V(a0, 0, B), mask_kind=K.MASK_LRELU),
+         (B * RB + 2 * B * 1024 * 256) / MB),
+        ("h0_wgrad_4B", lambda: K.wgrad_img(P4, V(d_a0), dw0, 1), (4 * B * RB + 4 * B * 1024 * 256) / MB),
         ("h0_dgrad_B", lambda: K.deconv_img(V(d_a0, 0, B), w0, gx, w_kn=True), (B * 12288 * 4 + B * 1024 * 256) / MB),
         ("up4_fwd_B", lambda: K.deconv_img(V(a0, 0, B), wt3, u4, bias3=b3, w9=w9, b9=b9, img=out), (2 * B * 12288 * 4 + B * 1024 * 256) / MB),
-        ("up4_dgrad_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, K.ImgPatches(gx), wt3, V(d_a0, 0, B), w_kn=True, mask=V(a0, 0, B), mask_kind=K.MASK_RELU,
-                                            stat_sum=stat_a, stat_dot=stat_b, stat_x=V(a0, B, B)), (B * 12288 * 4 + 3 * B * 1024 * 256) / MB),
-        ("up4_wgrad_B", lambda: K.wgrad_img(gx, V(a0, 0, B), dwt3, 2), (B * 12288 * 4 + B * 1024 * 256) / MB),
+        ("up4_dgrad_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, PG, wt3, V(d_a0, 0, B), w_kn=True, mask=V(a0, 0, B), mask_kind=K.MASK_RELU,
+                                            stat_sum=stat_a, stat_dot=stat_b, stat_x=V(a0, B, B)), (B * RB + 3 * B * 1024 * 256) / MB),
+        ("up4_wgrad_B", lambda: K.wgrad_img(PG, V(a0, 0, B), dwt3, 2), (B * RB + B * 1024 * 256) / MB),
         ("dense_f32", lambda: K.dense_f32(cond, wms, bms, ms, act=K.ACT_LRELU), (B * 1024 * 4 + 256 * 1024 * 4 + B * 256 * 4) / MB),
     ]
     res = {}
