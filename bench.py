@@ -231,18 +231,24 @@ def main():
         eng.g["tn"].copy_(tn[1])
         eng.g_step(lr)
 
-    sampler = ClockSampler(local_rank)
-    sampler.start()                      # started before the warm-up: nvidia-smi needs ~0.3 s to deliver its first row
+    # rank 0 samples its GPU's clocks (one nvidia-smi poller per rank would put N pollers on the host cores the ranks'
+    # own launch threads need)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()                  # started before the warm-up: nvidia-smi needs ~0.3 s to deliver its first row
     for _ in range(args.warmup):
         resident_step()
     barrier()
-    if sampler.mark() == 0:              # keep the GPU loaded until the sampler is live
-        for _ in range(30):
-            resident_step()
-            if sampler.mark() > 0:
-                break
-        barrier()
-    s_first = sampler.mark()
+    live = torch.tensor([1 if (sampler is None or sampler.mark() > 0) else 0], device=dev)
+    for _ in range(30):                  # keep the GPUs loaded until the sampler is live (all ranks take the same trips)
+        if world > 1:
+            dist.all_reduce(live, op=dist.ReduceOp.MIN)
+        if int(live.item()) == 1:
+            break
+        resident_step()
+        live.fill_(1 if (sampler is None or sampler.mark() > 0) else 0)
+    barrier()
+    s_first = sampler.mark() if sampler is not None else 0
     l0 = _lib.launch_count() + eng.replayed_launches - eng.captured_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -251,7 +257,7 @@ def main():
     e1.record()
     barrier()
     launches = _lib.launch_count() + eng.replayed_launches - eng.captured_launches - l0
-    clocks = sampler.finish(s_first, sampler.mark())
+    clocks = sampler.finish(s_first, sampler.mark()) if sampler is not None else None
     ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
     if world > 1:
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)

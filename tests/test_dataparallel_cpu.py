@@ -22,7 +22,11 @@ def _free_port():
         return sk.getsockname()[1]
 
 
-def _worker(rank, world, port, out):
+def _worker_buckets(rank, world, port, out):
+    _worker(rank, world, port, out, g_buckets=2)
+
+
+def _worker(rank, world, port, out, g_buckets=None):
     sys.path.insert(0, ROOT)
     sys.path.insert(0, HERE)
     os.environ["MASTER_ADDR"] = "127.0.0.1"
@@ -45,7 +49,8 @@ def _worker(rank, world, port, out):
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
 
     eng = Engine(fk, "cpu", b, 1, cfg.z_dim, cfg.embed_dim, cfg.compressed_embed_dim, cfg.gf_dim, cfg.df_dim,
-                 cfg.beta1, cfg.beta2, cfg.kl_coeff, world, allreduce, act_dtype=torch.float64, f32_dtype=torch.float64)
+                 cfg.beta1, cfg.beta2, cfg.kl_coeff, world, allreduce, act_dtype=torch.float64, f32_dtype=torch.float64,
+                 g_buckets=g_buckets)
     eng.set_params_tf(p)
     sl = slice(rank * b, (rank + 1) * b)
     eng.load_feed(**{k: feed[k][sl] for k in ("x", "x_mismatch", "cond", "z", "epsilon")}, tn_eps=feed["tn_eps"][sl])
@@ -74,9 +79,11 @@ def _worker(rank, world, port, out):
     gathered = [torch.zeros_like(flat) for _ in range(world)]
     dist.all_gather(gathered, flat)
     same = all(torch.equal(gathered[0], t) for t in gathered)
+    # the G run's gradients against the single-process engine fed the same generator statistics are covered by the
+    # sync_bn test; here: the bucketed all-reduce (g_buckets = 2) must produce the same flat gradient as one call
     if rank == 0:
-        torch.save({"worst": worst, "smax": smax, "calls": calls, "same": same,
-                    "kt": float(eng.kt), "kt_ref": float(ref.kt)}, out)
+        torch.save({"worst": worst, "smax": smax, "calls": calls, "same": same, "g_flat": flat, "g_n": eng.g_n,
+                    "g_split": eng.g_split, "kt": float(eng.kt), "kt_ref": float(ref.kt)}, out)
     dist.destroy_process_group()
 
 
@@ -213,6 +220,21 @@ def test_two_rank_d_run_equals_single_process(tmp_path):
     assert r["smax"] < 1e-9, r
     assert abs(r["kt"] - r["kt_ref"]) < 1e-12
     assert len(r["calls"]) == 2 and r["same"], r      # exactly one allreduce per optimizer step
+
+
+def test_two_rank_bucketed_g_allreduce_matches_single_call(tmp_path):
+    """g_buckets = 2 (the CUDA default at world > 1): [t0 .. c9] goes out when the backward pass reaches the 4x4 maps,
+    the rest afterwards; same reduced gradient, element for element, as the single all-reduce"""
+    outs = []
+    for worker in (_worker, _worker_buckets):
+        out = str(tmp_path / ("r%d.pt" % len(outs)))
+        mp.spawn(worker, args=(2, _free_port(), out), nprocs=2, join=True)
+        outs.append(torch.load(out))
+    one, two = outs
+    assert len(one["calls"]) == 2 and len(two["calls"]) == 3, (one["calls"], two["calls"])
+    assert two["calls"][1] == two["g_split"] and two["calls"][1] + two["calls"][2] == one["calls"][1]
+    assert 0.5 < two["g_split"] / two["g_n"] < 0.8          # the early bucket carries most of the bytes
+    assert two["same"] and torch.equal(one["g_flat"], two["g_flat"])
 
 
 def _worker_pggan(rank, world, port, out):

@@ -82,7 +82,7 @@ class Engine:
     def __init__(self, K, device, batch, np_=1, z_dim=128, embed_dim=1024, ce=128, gf=128, df=128,
                  beta1=0.0, beta2=0.9, kl_coeff=1.0, world=1, allreduce=None, act_dtype=torch.bfloat16,
                  f32_dtype=torch.float32, share_from=None, use_graphs=False, concurrent=True, sync_bn=False,
-                 beta1_g=None):
+                 beta1_g=None, g_buckets=None):
         # act_dtype / f32_dtype exist for the CPU host-logic tests only (exact fp64 storage with the
         # kernels' CPU restatement); the CUDA kernels accept bf16 planes and fp32 exclusively.
         self.K, self.dev, self.B, self.np = K, torch.device(device), batch, np_
@@ -99,6 +99,10 @@ class Engine:
         # statistics and a single all-reduce per optimizer step
         self.sync_bn = bool(sync_bn) and world > 1
         self.GB = batch * world
+        # g_buckets = 2: the G-gradient all-reduce goes out in two pieces in backward order -- the layers from the first
+        # transposed conv on (two thirds of the bytes, final when the backward pass reaches the 4x4 maps) travel on the
+        # communication stream UNDER the rest of the backward pass.  Default: whenever there are streams to overlap on.
+        self.g_buckets = g_buckets if g_buckets is not None else (2 if (world > 1 and self.dev.type == "cuda") else 1)
         for v in (z_dim, embed_dim, ce, gf, df):
             assert v % 8 == 0, "channel counts must be multiples of 8"
         self.d_t = 0
@@ -188,8 +192,16 @@ class Engine:
         def bias_len(l):
             return {"dout": 1, "dout_fc": 1, "col_out": 3, "c9": 3}.get(l.kind, l.cout)     # img_out: 8 (3 used, zero padded)
 
+        # flat order of g_net: the layers whose gradients are final FIRST in the backward pass (t0 .. c9) lead, so that
+        # each all-reduce bucket is one contiguous range: [t0 .. c9 | ms, fc0, c0, c1, c2 | BatchNorm | sums]
+        early = ("ms", "fc0", "c0", "c1", "c2")
+        bucketed = "t0" in self.gl and all(n in self.gl for n in early)
+
         def layout(layers, bn_ch):
             off, table = 0, OrderedDict()
+            if layers is self.gl and bucketed:
+                layers = OrderedDict([(n, l) for n, l in layers.items() if n not in early] +
+                                     [(n, layers[n]) for n in early])
             for l in layers.values():
                 wn = l.taps * l.cout * l.cin if l.kind not in ("dout", "dout_fc", "c9") else (81 if l.kind == "c9" else l.cin)
                 table[l.name + ".w"] = (off, wn); off = _align(off + wn)
@@ -201,6 +213,7 @@ class Engine:
 
         self.d_n, self.d_table = layout(self.dl, self.dbn_ch)
         self.g_n, self.g_table = layout(self.gl, self.bn_ch)
+        self.g_split = self.g_table["ms.w"][0] if bucketed else None      # first element of the second bucket
         f32 = dict(device=self.dev, dtype=self.f32_dtype)
         self.flat = {"d": torch.zeros(self.d_n, **f32), "g": torch.zeros(self.g_n, **f32)}
         self.grad = {"d": torch.zeros(self.d_n + SUMS, **f32), "g": torch.zeros(self.g_n + SUMS, **f32)}
@@ -604,8 +617,10 @@ class Engine:
         # :218-221 in one kernel: transposed conv 128 -> 3 (overlap-add on chip) + bias -> u4, 3x3 conv 3 -> 3 + tanh
         K.deconv_img(V(g["h5"]), gl["t3"].Wf, g["u4"], bias3=gl["t3"].b, w9=gl["c9"].w, b9=gl["c9"].b, img=img_out)
 
-    def g_backward(self, d_img):
+    def g_backward(self, d_img, part=None):
         """Backward of g_forward given dLoss/d image (fp32 [B,64,64,3]); fills the g gradient buffer.
+        part = 1: down to the first transposed conv (every gradient of the first all-reduce bucket is final, side stream
+        joined); part = 2: the rest; None: all of it.
         Every input-gradient GEMM whose output is the gradient at a BatchNorm(+ReLU) output applies the ReLU
         derivative mask and accumulates that BatchNorm's two backward reductions (sum dy -> dbeta, sum dy * x)
         in its epilogue; bn_bwd_fused then needs one pass.  Bias gradients ride along the same way."""
@@ -657,6 +672,8 @@ class Engine:
             bn_bwd(bn_a, g["d_" + u_a], g[t_a], g["d_" + t_a], gl[c_a].gb)
             conv_bwd(c_a, x, "d_" + t_a, g["d_" + x], add=V(ds), **last_epi)     # skip connection joins here
 
+        if part == 2:
+            return self._g_backward_tail(res_bwd, bn_bwd, V)
         K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
         # the 4x4/s2 patches of d_u4 are formed on chip by both kernels from its padded bf16 rows (no patch matrix in HBM)
         K.img_to_rows(g["d_u4"], g["d_u4_rows"])
@@ -675,6 +692,16 @@ class Engine:
         bn_bwd(4, g["d_h2"], g["t4"], g["d_t4"], gl["c3"].gb)
         conv_bwd("c3", "d1", "d_t4", g["d_d1"], stat_sum=gl["t0"].gb)
         conv_bwd("t0", "h1", "d_d1", g["d_h1"], **relu_of("h1"), **bn_red(3, g["t3"]))
+        if part == 1:
+            self._join()
+            return
+        self._g_backward_tail(res_bwd, bn_bwd, V)
+
+    def _g_backward_tail(self, res_bwd, bn_bwd, V):
+        """the first residual block, BatchNorm 0, the dense layer and the conditioning head (second all-reduce bucket)"""
+        K, g, gl = self.K, self.g, self.gl
+        S1 = K.CONV_S1
+        B, np_ = self.B, self.np
         res_bwd("h0", "c0", "t1", 1, "u1", "c1", "t2", 2, "u2", "c2", "t3", 3, "h1")
         # BatchNorm 0 normalises per FEATURE of the [B, 16*C8] dense output (model.py:176), not per channel of the
         # 4x4 map the conv above wrote, so its reductions stay a separate pass
@@ -968,8 +995,16 @@ class Engine:
         self._set_lr("g", lr_g, self.g_t)
         self._run("g_a1", self._g_body_fwd)
         self.join_comm()                        # d_net's weights of this iteration are final from here on
-        self._run("g_a2", self._g_body)
-        self._reduce("g")
+        if self.g_buckets == 2 and self.world > 1 and self.g_split is not None and not self.sync_bn:
+            self._run("g_a2", lambda: self._g_body(part=1))
+            with self._on_comm():                  # bucket 1 travels under the rest of the backward pass
+                self.allreduce(self.grad["g"][:self.g_split])
+            self._run("g_a3", lambda: self.g_backward(self.d["gx"], part=2))
+            self.allreduce(self.grad["g"][self.g_split:])
+            self.join_comm()
+        else:
+            self._run("g_a2", self._g_body)
+            self._reduce("g")
         self._run("g_b", self._g_tail_scalars)
         self._publish_scalars()
         self._run("g_c", self._g_tail_adam)
@@ -988,12 +1023,15 @@ class Engine:
         self.g_forward(g["z"], cond, g["tn"], d["img"][:B], self.sums["g"][1:2], update_moving=True)
         K.to_planes(cond, d["cond"][:, :B])
 
-    def _g_body(self):
+    def _g_body(self, part=None):
         K, d, g, B = self.K, self.d, self.g, self.B
         self.d_forward(0, B)
         K.g_sums(d["logit"], B, self.sums["g"])
         self.d_backward(0, B, d["gseed"], 0, B, False)
-        self.g_backward(d["gx"])
+        if part is None:          # (subclasses override g_backward without the bucket split)
+            self.g_backward(d["gx"])
+        else:
+            self.g_backward(d["gx"], part)
 
     def sample(self, z, cond, tn_eps, out, cond_noise=True):
         """generator(z, cond, is_training=False) -- the sampler of model.py:57 (batch = engine batch)."""
