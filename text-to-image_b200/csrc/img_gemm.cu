@@ -19,6 +19,7 @@
 //   log_sigma feeds exp() (model.py:121): a bf16 rounding of it is the largest single contributor to the generator's
 //   forward error (tools/bf16_error_budget.py), and the 256 x 256 x 1024 product is far too small for a tensor tile.
 #include "host_util.h"
+#include "img_patch.cuh"
 #include "planes.cuh"
 #include "ptx.cuh"
 
@@ -306,75 +307,69 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
 }
 
 // ------------------------------------------------------------------------------------------------------------
-// y[r][o] = act(sum_k x[r][k] * w[o][k] + b[o]), everything fp32.  CTA tile 16 rows x 32 outputs; the 256 threads form
-// four groups that take every fourth 16-wide K chunk (their partial sums meet in shared memory at the end); a thread owns
-// a 2 x 4 register tile.  Operands are staged K-major-transposed ([k][row], [k][output]) so that a thread's rows /
-// outputs are one 8- / 16-byte shared load; the next chunk's global loads are in flight while the current one is used.
-constexpr int kDfR = 16, kDfO = 32, kDfK = 16, kDfG = 4, kDfXP = 20;     // kDfXP: padded row pitch of the x tile
+// y[r][o] = act(sum_k x[r][k] * w[o][k] + b[o]), everything fp32.  CTA tile 16 rows x 32 outputs.  The operands of a
+// tile (16 + 32 rows of up to 1024 floats = 192 KB) are fetched into shared memory AT ONCE with one bulk copy per row and
+// K quarter -- a single exposure to the memory latency instead of one per K chunk (the 2 MB of operands are cold in a
+// training step: the weights were last touched by Adam) -- and each of the four 64-thread groups starts on its K quarter
+// as soon as that quarter has landed; the partial sums meet in shared memory.  A thread owns rows 2*tr, 2*tr + 1 and
+// outputs to, to + 8, to + 16, to + 24 (row pitch K + 4 floats: 16-byte loads along K without bank conflicts).
+constexpr int kDfR = 16, kDfO = 32, kDfG = 4, kDfKMax = 1024;
 __global__ void __launch_bounds__(64 * kDfG) dense_f32_kernel(const float* __restrict__ x, const float* __restrict__ w,
                                                               const float* __restrict__ bias, float* y, int rows, int cin,
                                                               int cout, int act) {
+    extern __shared__ __align__(16) uint8_t df_smem[];
     pdl_launch_dependents();
     pdl_wait();
-    __shared__ __align__(16) float xs[kDfG][2][kDfK][kDfXP];
-    __shared__ __align__(16) float ws[kDfG][2][kDfK][kDfO];
-    __shared__ float red[kDfG - 1][64][9];
+    const int pitch = cin + 4;                               // floats per staged row
+    float* xs = reinterpret_cast<float*>(df_smem);           // [16][pitch]
+    float* ws = xs + kDfR * pitch;                           // [32][pitch]
+    float* red = ws + kDfO * pitch;                          // [3][64][9]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + (kDfG - 1) * 64 * 9 + 1);   // 8-byte aligned: see the host's byte count
+    bars = reinterpret_cast<uint64_t*>((reinterpret_cast<uintptr_t>(bars) + 7) & ~uintptr_t(7));
     const int g = threadIdx.x >> 6, t = threadIdx.x & 63;
-    const int tr = t >> 3, to = t & 7;                  // rows 2*tr .. +1, outputs 4*to .. +3 of the tile
+    const int tr = t >> 3, to = t & 7;
     const int r0 = blockIdx.y * kDfR, o0 = blockIdx.x * kDfO;
-    const int n_chunks = (cin + kDfK - 1) / kDfK;
-    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
-    float4 xr, wr[2];
-    auto load = [&](int c) {
-        const int k0 = c * kDfK;
-        {
-            const int r = t & 15, k4 = (t >> 4) * 4;
-            xr = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (r0 + r < rows && k0 + k4 < cin) xr = __ldg(reinterpret_cast<const float4*>(x + (long long)(r0 + r) * cin + k0 + k4));
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = t + 64 * j, o = idx & 31, k4 = (idx >> 5) * 4;
-            wr[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (o0 + o < cout && k0 + k4 < cin) wr[j] = __ldg(reinterpret_cast<const float4*>(w + (long long)(o0 + o) * cin + k0 + k4));
-        }
-    };
-    auto store = [&](int buf) {
-        {
-            const int r = t & 15, k4 = (t >> 4) * 4;
-            xs[g][buf][k4 + 0][r] = xr.x; xs[g][buf][k4 + 1][r] = xr.y;
-            xs[g][buf][k4 + 2][r] = xr.z; xs[g][buf][k4 + 3][r] = xr.w;
-        }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int idx = t + 64 * j, o = idx & 31, k4 = (idx >> 5) * 4;
-            ws[g][buf][k4 + 0][o] = wr[j].x; ws[g][buf][k4 + 1][o] = wr[j].y;
-            ws[g][buf][k4 + 2][o] = wr[j].z; ws[g][buf][k4 + 3][o] = wr[j].w;
-        }
-    };
-    int c = g, buf = 0;
-    if (c < n_chunks) {
-        load(c);
-        store(0);
+    const int kq = ((cin + 4 * kDfG - 1) / (4 * kDfG)) * 4;  // K per group, a multiple of 4
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < kDfG; ++i) mbar_init(&bars[i], 1);
+        fence_barrier_init();
     }
-    named_bar(1 + g, 64);
-    for (; c < n_chunks; c += kDfG) {
-        const bool more = c + kDfG < n_chunks;
-        if (more) load(c + kDfG);
-#pragma unroll
-        for (int k = 0; k < kDfK; ++k) {
-            const float2 xv = *reinterpret_cast<const float2*>(&xs[g][buf][k][2 * tr]);
-            const float4 wv = *reinterpret_cast<const float4*>(&ws[g][buf][k][4 * to]);
-            acc[0][0] += xv.x * wv.x; acc[0][1] += xv.x * wv.y; acc[0][2] += xv.x * wv.z; acc[0][3] += xv.x * wv.w;
-            acc[1][0] += xv.y * wv.x; acc[1][1] += xv.y * wv.y; acc[1][2] += xv.y * wv.z; acc[1][3] += xv.y * wv.w;
+    __syncthreads();
+    if (threadIdx.x < kDfG) {        // one issuing thread per K quarter
+        const int q = threadIdx.x;
+        const int k0 = q * kq, kn = min(cin, k0 + kq) - k0;
+        int n_rows = 0;
+        for (int r = 0; r < kDfR + kDfO; ++r) n_rows += (r < kDfR) ? (r0 + r < rows) : (o0 + r - kDfR < cout);
+        mbar_arrive_expect_tx(&bars[q], kn > 0 ? static_cast<uint32_t>(n_rows * kn * 4) : 0u);
+        if (kn > 0) {
+            for (int r = 0; r < kDfR; ++r)
+                if (r0 + r < rows) bulk_load_1d(xs + r * pitch + k0, x + (long long)(r0 + r) * cin + k0, kn * 4, &bars[q]);
+            for (int o = 0; o < kDfO; ++o)
+                if (o0 + o < cout) bulk_load_1d(ws + o * pitch + k0, w + (long long)(o0 + o) * cin + k0, kn * 4, &bars[q]);
         }
-        if (more) store(buf ^ 1);
-        named_bar(1 + g, 64);
-        buf ^= 1;
+    }
+    float acc[2][4] = {{0.f, 0.f, 0.f, 0.f}, {0.f, 0.f, 0.f, 0.f}};
+    {
+        const int k0 = g * kq, k1 = min(cin, k0 + kq);
+        mbar_wait(&bars[g], 0, 900 + g);
+        const float* x0 = xs + (2 * tr) * pitch;
+        const float* x1 = x0 + pitch;
+        const float* wr[4] = {ws + to * pitch, ws + (to + 8) * pitch, ws + (to + 16) * pitch, ws + (to + 24) * pitch};
+#pragma unroll 4
+        for (int k = k0; k < k1; k += 4) {
+            const float4 a = *reinterpret_cast<const float4*>(x0 + k);
+            const float4 b = *reinterpret_cast<const float4*>(x1 + k);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const float4 c = *reinterpret_cast<const float4*>(wr[j] + k);
+                acc[0][j] += a.x * c.x + a.y * c.y + a.z * c.z + a.w * c.w;
+                acc[1][j] += b.x * c.x + b.y * c.y + b.z * c.z + b.w * c.w;
+            }
+        }
     }
     if (g > 0) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) red[g - 1][t][i] = acc[i >> 2][i & 3];
+        for (int i = 0; i < 8; ++i) red[((g - 1) * 64 + t) * 9 + i] = acc[i >> 2][i & 3];
     }
     __syncthreads();
     if (g == 0) {
@@ -384,11 +379,11 @@ __global__ void __launch_bounds__(64 * kDfG) dense_f32_kernel(const float* __res
             if (r >= rows) continue;
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-                const int o = o0 + 4 * to + j;
+                const int o = o0 + to + 8 * j;
                 if (o < cout) {
                     float v = acc[i][j] + (bias != nullptr ? bias[o] : 0.f);
 #pragma unroll
-                    for (int gg = 0; gg < kDfG - 1; ++gg) v += red[gg][t][i * 4 + j];
+                    for (int gg = 0; gg < kDfG - 1; ++gg) v += red[(gg * 64 + t) * 9 + i * 4 + j];
                     if (act == T2I_ACT_LRELU) v = fmaxf(v, 0.2f * v);
                     else if (act == T2I_ACT_RELU) v = fmaxf(v, 0.f);
                     y[(long long)r * cout + o] = v;
@@ -469,10 +464,20 @@ extern "C" int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane
 extern "C" int t2i_dense_f32(const float* x, int rows, int cin, const float* w, const float* bias, int cout, int act, float* y,
                              void* stream) {
     if (x == nullptr || w == nullptr || y == nullptr) return fail(T2I_ERR_BAD_ARG, "null tensor");
-    if (cin % 4 != 0) return fail(T2I_ERR_BAD_ARG, "dense_f32: cin=%d must be a multiple of 4", cin);
+    if (cin % 4 != 0 || cin > kDfKMax) return fail(T2I_ERR_BAD_ARG, "dense_f32: cin=%d must be a multiple of 4, at most %d", cin, kDfKMax);
+    if ((reinterpret_cast<uintptr_t>(x) & 15) != 0 || (reinterpret_cast<uintptr_t>(w) & 15) != 0)
+        return fail(T2I_ERR_BAD_ARG, "dense_f32: operands must be 16-byte aligned");
+    const int smem_bytes = (kDfR + kDfO) * (cin + 4) * 4 + (kDfG - 1) * 64 * 9 * 4 + 16 + kDfG * 8;
+    static bool attr_done = false;
+    if (!attr_done) {
+        cudaError_t ce = cudaFuncSetAttribute(dense_f32_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                              (kDfR + kDfO) * (kDfKMax + 4) * 4 + (kDfG - 1) * 64 * 9 * 4 + 16 + kDfG * 8);
+        if (ce != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
+        attr_done = true;
+    }
     dim3 grid(ceil_div(cout, kDfO), ceil_div(rows, kDfR));
-    cudaError_t le = launch_ew(dense_f32_kernel, grid, dim3(64 * kDfG), 0, static_cast<cudaStream_t>(stream), x, w, bias, y, rows, cin,
-                               cout, act);
+    cudaError_t le = launch_ew(dense_f32_kernel, grid, dim3(64 * kDfG), smem_bytes, static_cast<cudaStream_t>(stream), x, w, bias, y,
+                               rows, cin, cout, act);
     if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "dense_f32_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("dense_f32_kernel");
 }

@@ -7,6 +7,7 @@ Storage convention ("bf16 planes"): a tensor of logical shape S is a torch.bfloa
 [np, *S]; its value is the sum over the first axis (np = 1: plain bf16; np = 2: hi + lo).
 """
 import ctypes as C
+import os
 
 import torch
 
@@ -80,6 +81,30 @@ PROFILE = None
 
 def _taps_per_output(mode, k):
     return k * k if mode == CONV_S1 else 16 if mode == CONV_K4S2 else 4
+
+
+# T2I_NVTX=1: every GEMM-type launch sits in an NVTX range named after its layer shape, so that
+# `ncu --nvtx --print-nvtx-rename kernel` lists launches by layer (profiles/README.md)
+NVTX = os.environ.get("T2I_NVTX") == "1"
+
+
+class _Range:
+    def __init__(self, tag):
+        self.tag = tag
+
+    def __enter__(self):
+        if NVTX:
+            torch.cuda.nvtx.range_push(self.tag)
+
+    def __exit__(self, *a):
+        if NVTX:
+            torch.cuda.nvtx.range_pop()
+
+
+def _conv_tag(mode, k, x, y, img):
+    if img:
+        return "conv_gemm img k4s2 %dx%dx%d co%d" % (x.n, x.H, x.W, y.c)
+    return "conv_gemm m%d k%d %dx%dx%d ci%d co%d" % (mode, k, x.n, x.H, x.W, x.c, y.c)
 
 
 def _prof_begin():
@@ -160,7 +185,8 @@ def conv_gemm(mode, k, flip, x, w, y, bias=None, add=None, mask=None, act=ACT_NO
     d.stat_x = stat_x._act() if stat_x is not None else _null_act()
     d.stat_n, d.stat_c = stat_n, stat_c
     d.w_n0 = w_n0
-    _lib.call("t2i_conv_gemm", C.byref(d), _stream())
+    with _Range(_conv_tag(mode, k, x, y, img)):
+        _lib.call("t2i_conv_gemm", C.byref(d), _stream())
     if ev is not None:
         opix = y.n * y.H * y.W
         if img:       # 48 = 16 taps x 3 channels per output pixel; the image is read once as fp32
@@ -184,7 +210,8 @@ def wgrad_gemm(mode, k, x, dy, dw, split_k=0, algo_scale=1.0):
     d.dw = dw.data_ptr()
     d.cout, d.cin = dw.shape[1], dw.shape[2]
     d.split_k = split_k
-    _lib.call("t2i_wgrad_gemm", C.byref(d), _stream())
+    with _Range("wgrad_gemm m%d k%d %dx%dx%d ci%d co%d" % (mode, k, x.n, x.H, x.W, x.c, dy.c)):
+        _lib.call("t2i_wgrad_gemm", C.byref(d), _stream())
     if ev is not None:
         vpix = x.n * x.H * x.W if mode != CONV_K4S2 else dy.n * dy.H * dy.W
         taps = k * k if mode == CONV_S1 else 16
