@@ -50,13 +50,18 @@ GFLOP_PER_IMAGE = 28.585          # 2 * (4 G_f + 15 D_f) MACs pe
 
 
 def measured_traffic(kernel):
-    """dram bytes per launch of `kernel` from the committed ncu capture (profiles/r01_traffic.json), or None"""
-    path = os.path.join(ROOT, "profiles", "r01_traffic.json")
-    if not os.path.exists(path):
-        return None
-    with open(path) as f:
-        t = json.load(f)
-    return t.get(kernel, {}).get("dram_bytes_per_launch")
+    """dram bytes per launch of `kernel` from the committed ncu launch list of this round's build
+    (profiles/r02_traffic.json, written by tools/summarize_ncu.py layers; falls back to round 1's), or None"""
+    for name in ("r02_traffic.json", "r01_traffic.json"):
+        path = os.path.join(ROOT, "profiles", name)
+        if not os.path.exists(path):
+            continue
+        with open(path) as f:
+            t = json.load(f)
+        t = t.get("by_kernel", t)
+        if kernel in t:
+            return t[kernel].get("dram_bytes_per_launch"), name
+    return None, None
 
 
 def peaks():
@@ -329,8 +334,8 @@ def main():
         achieved = fl / (t * 1e-3) / 1e12
         roofline = {"kernel": top + "_kernel", "bound": "tensor", "achieved": achieved, "peak": pk["bf16_sustained"],
                     "unit": "TFLOP/s", "frac": achieved / pk["bf16_sustained"],
-                    "traffic": measured_traffic(top + "_kernel"), "traffic_unit": "dram bytes per launch (ncu, mean over the "
-                    "launches of one step; profiles/r01_traffic.json)", "algorithmic_bytes_per_launch": nb / n,
+                    "traffic": measured_traffic(top + "_kernel")[0], "traffic_unit": "dram bytes per launch (ncu, mean over the "
+                    "launches of one step; profiles/%s)" % measured_traffic(top + "_kernel")[1], "algorithmic_bytes_per_launch": nb / n,
                     "peak_source": pk["source"] + ", sustained (kernel timed inside a long step)",
                     "launches_per_step": n // psteps, "ms_per_step_in_kernel": t / psteps,
                     "share_of_step": (t / psteps) / ms_per_step,

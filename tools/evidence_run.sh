@@ -1,0 +1,11 @@
+#!/bin/bash
+# Evidence set of a build (run on the GPU box through gpurun): test log, bench line + per-launch table, ncu launch list by
+# layer (duration, tensor-pipe %, DRAM bytes), sanitizer logs.  Outputs under gpurun_out/ with the prefix $1.
+P=${1:-r02}
+mkdir -p gpurun_out
+(timeout 700 python -m pytest tests -m gpu -q -s 2>&1 | grep -E "^\[|passed|failed|skipped" | tail -60) > gpurun_out/${P}_pytest_gpu_full.log
+timeout 500 python bench.py --steps 50 --warmup 5 --profile-out gpurun_out/${P}_gemm_table.json > gpurun_out/${P}_bench.json 2> gpurun_out/${P}_bench.err
+T2I_NVTX=1 timeout 600 ncu --nvtx --print-nvtx-rename kernel --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum,sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active,launch__grid_size --clock-control none -s 600 -c 460 --csv --log-file gpurun_out/${P}_launches.csv python bench.py --steps 2 --warmup 3 --only-resident --no-graphs > gpurun_out/${P}_ncu_bench.log 2>&1
+timeout 300 compute-sanitizer --tool memcheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${P}_sanitizer_memcheck.log 2>&1; echo "memcheck exit $?" >> gpurun_out/${P}_sanitizer_memcheck.log
+timeout 600 compute-sanitizer --tool racecheck --error-exitcode 7 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/${P}_sanitizer_racecheck.log 2>&1; echo "racecheck exit $?" >> gpurun_out/${P}_sanitizer_racecheck.log
+tail -3 gpurun_out/${P}_pytest_gpu_full.log; head -c 600 gpurun_out/${P}_bench.json; echo; tail -2 gpurun_out/${P}_sanitizer_memcheck.log; tail -4 gpurun_out/${P}_sanitizer_racecheck.log; wc -l gpurun_out/${P}_launches.csv

@@ -31,6 +31,56 @@ def launches(path):
         print("%-58s n=%4d  us=%9.1f  %5.1f%%" % (k[:58], v[0], v[1], 100 * v[1] / tot))
 
 
+def layers(path, out_json=None):
+    """launch list taken with T2I_NVTX=1 + `ncu --nvtx --print-nvtx-rename kernel` (tools/evidence_run.sh): the GEMM-type
+    launches carry their layer shape as the kernel name.  Per layer: launches, time, share, tensor-pipe active %
+    (time-weighted mean of sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active) and DRAM bytes per launch."""
+    import json
+    lines = [l for l in open(path) if not l.startswith("==")]
+    scale_t = {"ns": 1e-3, "us": 1.0, "ms": 1e3}
+    scale_b = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = collections.OrderedDict()
+    for row in csv.DictReader(lines):
+        v = float(row["Metric Value"].replace(",", "") or 0)
+        m = row["Metric Name"]
+        d = per.setdefault(row["ID"], {"name": row["Kernel Name"], "us": 0.0, "tp": 0.0, "bytes": 0.0})
+        if m == "gpu__time_duration.sum":
+            d["us"] = v * scale_t.get(row["Metric Unit"], 1.0)
+        elif m.startswith("sm__pipe_tensor_cycles_active"):
+            d["tp"] = v
+        elif m in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            d["bytes"] += v * scale_b.get(row["Metric Unit"], 1.0)
+    agg = collections.OrderedDict()
+    for d in per.values():
+        name = d["name"].split("/")[0] if "/" in d["name"] else d["name"].split("(")[0].replace("void ", "").replace("t2i::", "")
+        a = agg.setdefault(name, {"launches": 0, "us": 0.0, "tp_us": 0.0, "bytes": 0.0})
+        a["launches"] += 1
+        a["us"] += d["us"]
+        a["tp_us"] += d["tp"] * d["us"]
+        a["bytes"] += d["bytes"]
+    tot = sum(a["us"] for a in agg.values())
+    print("%d launches, %.1f us of kernel time (ncu: serialised, cold cache -- compare shares, not absolutes)" % (len(per), tot))
+    print("%-54s %4s %9s %6s %12s %14s" % ("layer / kernel", "n", "us", "share", "tensor-pipe%", "DRAM MB/launch"))
+    res = {}
+    for k, a in sorted(agg.items(), key=lambda kv: -kv[1]["us"]):
+        tp = a["tp_us"] / a["us"] if a["us"] else 0.0
+        res[k] = {"launches": a["launches"], "us": a["us"], "tensor_pipe_active_pct": tp,
+                  "dram_bytes_per_launch": a["bytes"] / a["launches"]}
+        print("%-54s %4d %9.1f %5.1f%% %12.1f %14.1f" % (k[:54], a["launches"], a["us"], 100 * a["us"] / tot, tp,
+                                                         a["bytes"] / a["launches"] / 1e6))
+    if out_json:
+        fam = collections.defaultdict(lambda: {"launches": 0, "dram_bytes_total": 0.0, "us": 0.0})
+        for k, a in agg.items():
+            f = "conv_gemm_kernel" if k.startswith("conv_gemm") else "wgrad_gemm_kernel" if k.startswith("wgrad_gemm") else k.split("<")[0]
+            fam[f]["launches"] += a["launches"]; fam[f]["dram_bytes_total"] += a["bytes"]; fam[f]["us"] += a["us"]
+        out = {f: {"launches": v["launches"], "dram_bytes_total": v["dram_bytes_total"],
+                   "dram_bytes_per_launch": v["dram_bytes_total"] / v["launches"],
+                   "dram_gbytes_per_s_under_ncu": v["dram_bytes_total"] / (v["us"] * 1e-6) / 1e9 if v["us"] else None}
+               for f, v in sorted(fam.items(), key=lambda kv: -kv[1]["dram_bytes_total"])}
+        with open(out_json, "w") as f:
+            json.dump({"by_kernel": out, "by_layer": res}, f, indent=1)
+
+
 def traffic(path, out_json=None):
     """dram bytes (read + write) per kernel from a launch list that also collected dram__bytes_{read,write}.sum"""
     import json
@@ -71,7 +121,9 @@ def full(path):
 
 
 if __name__ == "__main__":
-    if sys.argv[1] == "traffic":
+    if sys.argv[1] == "layers":
+        layers(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
+    elif sys.argv[1] == "traffic":
         traffic(sys.argv[2], sys.argv[3] if len(sys.argv) > 3 else None)
     else:
         (launches if sys.argv[1] == "launches" else full)(sys.argv[2])
