@@ -252,3 +252,96 @@ def test_graph_replay_and_side_stream_match_eager_schedule():
         assert float(((s - s0).abs() / (1.0 + s0.abs())).max()) < 1e-3, (s, s0)
         for n in names:   # one Adam step of ~lr: identical except where a near-zero gradient flips its sign
             assert float(((w[n] - w0[n]).abs() > 5e-5).double().mean()) < 0.03, n
+
+
+def _d_masked(p, x_nhwc, cond, slopes):
+    """models/wgancls/model.py:129-161 with every LeakyReLU replaced by a FIXED per-element slope (1 or 0.2): inside the
+    linear region the CUDA path's saved activation signs select, d_net is exactly this map."""
+    import torch.nn.functional as F
+    d = "d_net/"
+
+    def conv(scope, x, k, s, pad):
+        return F.conv2d(x, p[scope + "/weights"].permute(3, 2, 0, 1), p[scope + "/biases"], stride=s, padding=pad)
+
+    x = x_nhwc.permute(0, 3, 1, 2)
+    h0 = conv(d + "Conv", x, 4, 2, 1) * slopes["a0"]
+    h1 = conv(d + "Conv_1", h0, 4, 2, 1) * slopes["a1"]
+    h2 = conv(d + "Conv_2", h1, 4, 2, 1) * slopes["a2"]
+    h3 = conv(d + "Conv_3", h2, 4, 2, 1)
+    n = conv(d + "Conv_4", h3, 1, 1, 0) * slopes["r1"]
+    n = conv(d + "Conv_5", n, 3, 1, 1) * slopes["r2"]
+    n = conv(d + "Conv_6", n, 3, 1, 1)
+    h4 = (h3 + n) * slopes["h4"]
+    e = (cond @ p[d + "dense/kernel"] + p[d + "dense/bias"]) * slopes["e"]
+    h4c = torch.cat([h4, e[:, :, None, None].expand(-1, -1, 4, 4)], 1)
+    h5 = conv(d + "Conv_7", h4c, 3, 1, 1) * slopes["a5"]
+    h6 = conv(d + "Conv_8", h5, 1, 1, 0) * slopes["a6"]
+    return conv(d + "Conv_9", h6, 4, 4, 0)
+
+
+def _slopes_from_engine(eng, s0, n, df8):
+    """slope tensors (NCHW, fp64) of samples [s0, s0 + n) from the engine's post-activation buffers"""
+    def sl(t, c0=0, c1=None):
+        v = t.float().sum(0)[s0:s0 + n]
+        v = v[..., c0:c1] if v.dim() == 4 else v[:, c0:c1]
+        s = torch.where(v > 0, 1.0, 0.2).double().cpu()
+        return s.permute(0, 3, 1, 2) if s.dim() == 4 else s
+    d = eng.d
+    return {"a0": sl(d["a0"]), "a1": sl(d["a1"]), "a2": sl(d["a2"]), "r1": sl(d["r1"]), "r2": sl(d["r2"]),
+            "h4": sl(d["cat"], 0, df8), "e": sl(d["e"]), "a5": sl(d["a5"]), "a6": sl(d["a6"])}
+
+
+def test_gradient_penalty_path_against_mask_consistent_oracle():
+    """The tolerance of the gradient-penalty quantities, made tight.  d_net is piecewise linear; units whose
+    pre-activation is below the arithmetic difference between CUDA and CPU take the other LeakyReLU branch, which moves
+    dD/dx_hat by percents although nothing is wrong.  Here the CPU side evaluates the SAME linear piece the CUDA path
+    is on (its saved activation signs, all four segments) in fp64: slopes, both penalties, D_loss and every d_net
+    gradient (first-order + the second-order penalty term) must then agree to 1e-3 (model.py:62-70,88-97)."""
+    ocfg = O.OracleCfg(batch_size=4)
+    p = O.init_params(ocfg, 0, torch.float32)
+    p["d_net/dense/kernel"] = p["d_net/dense/kernel"] * 4.0       # makes the cond penalty active (as in the b4 golden)
+    f = O.make_feed(ocfg, 1234, torch.float32)
+    m = build(ocfg, "bf16x3", p)
+    eng = m._train_engine()
+    B, df8 = 4, 8 * ocfg.df_dim
+    out = m.run([m.D_optim, m.kt_optim, m.D_loss, m.G, m.x_hat], feed_dict(m, f, "tn_eps"))
+    G_img, x_hat = torch.from_numpy(out[3]).double(), torch.from_numpy(out[4]).double()
+    sc = eng.scalars_dict()
+    gx, g2 = eng.d["gx"].double().cpu(), eng.d["g2"].double().cpu()
+    grads = eng.get_grads_tf()
+    # signs: segments 0..2 are still in the buffers; the x_hat segment was overwritten by the tangent pass, so its
+    # forward is repeated on a second model that still holds the weights of BEFORE the update (bit-identical logits:
+    # d_net is per-sample) and read back
+    slopes = [_slopes_from_engine(eng, s * B, B, df8) for s in range(3)]
+    m2 = build(ocfg, "bf16x3", p)
+    lg = m2.discriminator(x_hat.float(), f["cond"])
+    assert torch.equal(lg.reshape(-1).cpu(), eng.d["logit"][3 * B:].cpu())
+    slopes.append(_slopes_from_engine(m2._train_engine(), 0, B, df8))
+    pd = {k: v.double() for k, v in p.items()}
+    names = [n for n in pd if n.startswith("d_net/")]
+    for n in names:
+        pd[n] = pd[n].clone().requires_grad_(True)
+    cond = f["cond"].double()
+    kt = torch.tensor(O.KT_INIT, dtype=torch.float64)
+    Dg = _d_masked(pd, G_img, cond, slopes[0])
+    Dx = _d_masked(pd, f["x"].double(), cond, slopes[1])
+    Dm = _d_masked(pd, f["x_mismatch"].double(), cond, slopes[2])
+    xh = x_hat.clone().requires_grad_(True)
+    ci = cond.clone().requires_grad_(True)
+    Dh = _d_masked(pd, xh, ci, slopes[3])
+    g_x, g_c = torch.autograd.grad(Dh.sum(), [xh, ci], create_graph=True)
+    gp, s1 = O.gradient_penalty(g_x, (1, 2, 3))
+    gp2, s2 = O.gradient_penalty(g_c, (1,))
+    wdist, wdist2 = Dx.mean() - Dg.mean(), Dx.mean() - Dm.mean()
+    d_loss = -wdist - kt * wdist2 + O.GP_WEIGHT * (gp + gp2)
+    ref_grads = torch.autograd.grad(d_loss, [pd[n] for n in names])
+    assert float(gp) > 0 and float(gp2) > 0          # both penalties are active on this feed
+    e_gx, e_g2 = rel(gx, g_x.detach()), rel(g2, g_c.detach())
+    print("\n[gp] mask-consistent oracle: dD/dx_hat %.2e  dD/dcond %.2e  real_gp %.6f vs %.6f  real_gp2 %.6f vs %.6f" % (
+        e_gx, e_g2, sc["real_gp"], float(gp), sc["real_gp2"], float(gp2)))
+    assert e_gx < 1e-3 and e_g2 < 1e-3
+    for k, v in (("real_gp", gp), ("real_gp2", gp2), ("D_loss", d_loss), ("wdist", wdist), ("wdist2", wdist2)):
+        assert abs(sc[k] - float(v)) < 1e-3 * max(1.0, abs(float(v))), (k, sc[k], float(v))
+    worst = max((rel(grads[n], g), n) for n, g in zip(names, ref_grads) if float(g.abs().max()) > 0)
+    print("[gp] worst d_net gradient (first order + second-order penalty term) rel-L2 %.2e (%s)" % worst)
+    assert worst[0] < 1e-3, worst
