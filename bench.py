@@ -174,12 +174,171 @@ def run_reference(args, rank):
     emit(line)
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# BASELINE configs 4 and 5 (the rows next to the hot path): the same line for PGGAN stage 7 (256x256) and
+# StackGAN stage-II (256x256).  Device-resident value, e2e through the model's own run(fetches, feed_dict) with pinned
+# host feeds, conv_gemm roofline from per-launch CUDA events; data-parallel over N GPUs exactly like wgancls.
+WIDEN = {
+    "pggan7": {"metric": "images/sec (D run + G run) 256x256 conditional PGGAN stage 7", "batch": 16,
+               "gflop_per_image": None,
+               "workload": "pggan stage 7 (256x256, stabilised), batch=%d per GPU (the reference's 2 x 8), reference channel schedule, "
+                           "1024-d random text embeds, D run + G run per step (BASELINE config 4)"},
+    "stackgan2": {"metric": "images/sec (D run + G run) 256x256 StackGAN stage-II", "batch": 64, "gflop_per_image": None,
+                  "workload": "stackgan stage-II 256x256 on a frozen stage-I 64x64 generator, batch=%d per GPU, GF 128 / DF 64, "
+                              "1024-d random text embeds, D run + G run per step (BASELINE config 5)"},
+}
+
+
+def run_widen(args, rank, world, local_rank):
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    from t2i_b200 import _lib, kernels
+    spec = WIDEN[args.workload]
+    B = args.batch if args.batch_given else spec["batch"]
+    distributed = True if world > 1 else None
+    gen = torch.Generator().manual_seed(1234 + rank)
+    pin = lambda t: t.pin_memory()
+    if args.workload == "pggan7":
+        from t2i_b200.models.pggan.pggan import PGGAN
+        m = PGGAN(B, 1000, "/tmp/pggan_w", "/tmp/pggan_r", None, "/tmp/pggan_s", "/tmp/pggan_l", 7, False, precision="bf16",
+                  sample_num=B, use_graphs=not args.no_graphs, distributed=distributed)
+        m.initialize(0)
+        S, zd = 256, 128
+        host = {"x": pin(torch.rand(B, S, S, 3, generator=gen) * 2 - 1), "xm": pin(torch.rand(B, S, S, 3, generator=gen) * 2 - 1),
+                "cond": pin(torch.randn(B, 1024, generator=gen)), "z": pin(torch.randn(B, zd, generator=gen)),
+                "eps": pin(torch.rand(B, 1, 1, 1, generator=gen))}
+        fd = {m.x: host["x"], m.x_mismatch: host["xm"], m.cond: host["cond"], m.z: host["z"], m.epsilon: host["eps"],
+              m.learning_rate: 2e-6, m.iter: 1}
+        d_fetch, g_fetch = [m.D_optim, m.D_loss], [m.G_optim, m.G_loss]
+        eng = m._train_engine()
+        eng.load_feed(x=host["x"], x_mismatch=host["xm"], cond=host["cond"], z=host["z"], epsilon=host["eps"].reshape(-1),
+                      tn_eps=torch.randn(B, 128, generator=gen).clamp_(-2, 2))
+        step = lambda: (eng.d_step(0.5), eng.g_step())
+        feed_keys = ("x", "xm", "cond", "z", "eps")
+    else:
+        from t2i_b200.models.stackgan.stageI.model import ConditionalGan as StageI
+        from t2i_b200.models.stackgan.stageII.model import ConditionalGan as StageII
+        from t2i_b200.utils.config import config_from_yaml
+        mdir = os.path.join(ROOT, "text-to-image_b200", "models", "stackgan")
+        c1 = config_from_yaml(os.path.join(mdir, "stageI", "cfg", "flowers.yml"))
+        c2 = config_from_yaml(os.path.join(mdir, "stageII", "cfg", "flowers.yml"))
+        c1.TRAIN.BATCH_SIZE = c2.TRAIN.BATCH_SIZE = B
+        c1.TRAIN.SAMPLE_NUM = c2.TRAIN.SAMPLE_NUM = B
+        s1 = StageI(c1, precision="bf16", use_graphs=not args.no_graphs, distributed=distributed)
+        s1.initialize(0)
+        m = StageII(s1, c2, use_graphs=not args.no_graphs, distributed=distributed)
+        m.initialize(1)
+        S, zd = 256, 100
+        host = {"x": pin(torch.rand(B, S, S, 3, generator=gen) * 2 - 1), "xm": pin(torch.rand(B, S, S, 3, generator=gen) * 2 - 1),
+                "cond": pin(torch.randn(B, 1024, generator=gen)), "z": pin(torch.randn(B, zd, generator=gen))}
+        fd = {m.inputs: host["x"], m.wrong_inputs: host["xm"], m.embed_inputs: host["cond"], m.z: host["z"]}
+        from t2i_b200.models.wgancls.model import Fetch       # the stage-II train ops belong to its trainer (trainer.py:51-57)
+        d_fetch, g_fetch = [Fetch("D_optim", "op"), Fetch("D_loss", "scalar")], [Fetch("G_optim", "op"), Fetch("G_loss", "scalar")]
+        eng = m._train_engine()
+        eng.load_feed(x=host["x"], x_mismatch=host["xm"], cond=host["cond"], z=host["z"],
+                      tn_eps=torch.randn(B, 128, generator=gen).clamp_(-2, 2), tn_s1=torch.randn(B, 128, generator=gen).clamp_(-2, 2))
+        step = lambda: (eng.d_step(2e-4), eng.g_step(2e-4))
+        feed_keys = ("x", "xm", "cond", "z")
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler is not None:
+        sampler.start()
+    for _ in range(max(args.warmup, 3)):
+        step()
+    barrier()
+    if sampler is not None:
+        t_end = time.time() + 1.0
+        while sampler.mark() == 0 and time.time() < t_end:     # nvidia-smi needs ~0.3 s for its first row
+            time.sleep(0.05)
+    barrier()
+    s_first = sampler.mark() if sampler is not None else 0
+    l0 = _lib.launch_count() + eng.replayed_launches - eng.captured_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = _lib.launch_count() + eng.replayed_launches - eng.captured_launches - l0
+    clocks = sampler.finish(s_first, sampler.mark()) if sampler is not None else None
+    ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_per_step = float(ms.item()) / args.steps
+    value = B * world / (ms_per_step * 1e-3)
+
+    def e2e_step():
+        d_loss = m.run(d_fetch, fd)[1]
+        g_loss = m.run(g_fetch, fd)[1]
+        return d_loss, g_loss
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    n_e2e = max(3, min(args.steps, 10))
+    for _ in range(n_e2e):
+        losses = e2e_step()
+    barrier()
+    dt = torch.tensor([time.perf_counter() - t0], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+    e2e_value = B * world * n_e2e / float(dt.item())
+    h2d = 2 * sum(host[k].numel() * 4 for k in feed_keys)            # both runs stage the feed dict they are given
+    # conv_gemm roofline: eager, single stream, one event pair per launch
+    pk = peaks()
+    side, eng.side_stream = eng.side_stream, None
+    kernels.PROFILE = []
+    step()
+    barrier()
+    prof, kernels.PROFILE = kernels.PROFILE, None
+    eng.side_stream = side
+    roofline = None
+    if rank == 0:
+        agg = {}
+        for k, tag, fl, nb, a, b in prof:
+            v = agg.setdefault(k, [0.0, 0.0, 0.0, 0])
+            v[0] += fl; v[1] += nb; v[2] += a.elapsed_time(b); v[3] += 1
+        top = max(agg, key=lambda k: agg[k][2])
+        fl, nb, t, n = agg[top]
+        roofline = {"kernel": top + "_kernel", "bound": "tensor", "achieved": fl / (t * 1e-3) / 1e12, "peak": pk["bf16_sustained"],
+                    "unit": "TFLOP/s", "frac": fl / (t * 1e-3) / 1e12 / pk["bf16_sustained"], "traffic": None,
+                    "algorithmic_bytes_per_launch": nb / n, "launches_per_step": n, "ms_per_step_in_kernel": t,
+                    "peak_source": pk["source"] + ", sustained",
+                    "gemm_tflop_per_step": sum(v[0] for v in agg.values()) / 1e12,
+                    "other_kernels": {k: {"ms_per_step": v[2], "tflops": v[0] / (v[2] * 1e-3) / 1e12} for k, v in agg.items() if k != top}}
+        emit({"metric": spec["metric"], "value": value, "unit": "images/s", "n_gpus": world, "steps": args.steps,
+              "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+              "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+              "config": {"workload": spec["workload"] % B, "global_batch": B * world,
+                         "parallelism": "dp%d (batch shards, one NCCL allreduce per optimizer step)" % world,
+                         "l2": "per-step working set exceeds the 126 MB L2; no explicit flush"},
+              "roofline": roofline,
+              "cpu_baseline": None, "cpu_baseline_note": "the CPU arm (bench.py --impl reference) exists for the north-star workload only",
+              "e2e": {"value": e2e_value, "unit": "images/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 2 * 16 * 4},
+              "gpu_launches": int(launches), "clocks": clocks, "finite": bool(all(np.isfinite(v) for v in losses)),
+              "peak_mem_gb": torch.cuda.max_memory_allocated() / 2 ** 30})
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=5)
-    ap.add_argument("--batch", type=int, default=256, help="images per GPU per step")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU per step (default: 256; pggan7 16; stackgan2 64)")
+    ap.add_argument("--workload", default="wgancls", choices=["wgancls", "pggan7", "stackgan2"],
+                    help="wgancls = the north-star workload (BASELINE config 2 / 3); the others are the rows next to it")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--precision", default="bf16", choices=["bf16", "bf16x3"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -188,12 +347,17 @@ def main():
     ap.add_argument("--no-graphs", action="store_true", help="profiling aid: eager launches (ncu launch lists)")
     ap.add_argument("--profile-out", default=None, help="write the per-launch GEMM table (JSON) here")
     args = ap.parse_args()
+    args.batch_given = args.batch is not None
+    if args.batch is None:
+        args.batch = 256
     claim_stdout()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     if args.impl == "reference":
         return run_reference(args, rank)
+    if args.workload != "wgancls":
+        return run_widen(args, rank, world, local_rank)
     args.warmup = max(args.warmup, 3)
 
     import torch
