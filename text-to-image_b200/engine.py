@@ -102,7 +102,11 @@ class Engine:
         # g_buckets = 2: the G-gradient all-reduce goes out in two pieces in backward order -- the layers from the first
         # transposed conv on (two thirds of the bytes, final when the backward pass reaches the 4x4 maps) travel on the
         # communication stream UNDER the rest of the backward pass.  Default: whenever there are streams to overlap on.
-        self.g_buckets = g_buckets if g_buckets is not None else (2 if (world > 1 and self.dev.type == "cuda") else 1)
+        if g_buckets is None:
+            import os
+            env = os.environ.get("T2I_G_BUCKETS")          # development aid: A/B the bucketing
+            g_buckets = int(env) if env else (2 if (world > 1 and self.dev.type == "cuda") else 1)
+        self.g_buckets = g_buckets
         for v in (z_dim, embed_dim, ce, gf, df):
             assert v % 8 == 0, "channel counts must be multiples of 8"
         self.d_t = 0

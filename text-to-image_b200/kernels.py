@@ -228,8 +228,9 @@ def wgrad_img(img, other, dw, img_side):
     n, h, w = img.n, img.H, img.W
     assert dw.dtype == torch.float32 and dw.dim() == 3 and dw.shape[0] == 1 and dw.is_contiguous() and img.np == other.np
     a = other._act()
-    _lib.call("t2i_wgrad_img", _p(img.rows), _ps(img.rows), n, h, w, C.byref(a), img_side, other.np, _f32(dw), dw.shape[1],
-              dw.shape[2], _stream())
+    with _Range("wgrad_img side%d %dx%dx%d c%d" % (img_side, n, h, w, other.c)):
+        _lib.call("t2i_wgrad_img", _p(img.rows), _ps(img.rows), n, h, w, C.byref(a), img_side, other.np, _f32(dw), dw.shape[1],
+                  dw.shape[2], _stream())
     if ev is not None:
         pix = n * (h // 2) * (w // 2)
         flops = 2.0 * pix * other.c * 48 * (3 if other.np == 2 else 1)
@@ -243,8 +244,9 @@ def deconv_img(a, w, out, bias3=None, w_kn=False, w9=None, b9=None, img=None):
     ev = _prof_begin()
     assert w.dtype == torch.bfloat16 and w.dim() == 4 and w.shape[1] == 1 and w[0].is_contiguous() and w.shape[0] == a.np
     act = a._act()
-    _lib.call("t2i_deconv_img", C.byref(act), _p(w), w.stride(0), w.shape[2], w.shape[3], int(w_kn), a.np, _p(bias3),
-              _f32(out), _p(w9), _p(b9), _p(img), _stream())
+    with _Range("deconv_img %dx%dx%d c%d%s" % (a.n, a.H, a.W, a.c, " +c9" if img is not None else "")):
+        _lib.call("t2i_deconv_img", C.byref(act), _p(w), w.stride(0), w.shape[2], w.shape[3], int(w_kn), a.np, _p(bias3),
+                  _f32(out), _p(w9), _p(b9), _p(img), _stream())
     if ev is not None:
         pix = a.n * a.H * a.W
         flops = 2.0 * pix * a.c * 48 * (3 if a.np == 2 else 1)
