@@ -27,6 +27,8 @@ from oracle import wgancls_oracle as O  # noqa: E402
 class Q:
     """rounding policy: site name -> round or not"""
 
+    round_head = False
+
     def __init__(self, fmt, sites=None, weights=True):
         self.dt = {"bf16": torch.bfloat16, "fp16": torch.float16}[fmt]
         self.sites, self.weights, self.seen = sites, weights, []
@@ -70,9 +72,15 @@ def generator(p, z, embed, tn_eps, cfg, q):
             y = act(y)
         return q.a(name, y)
 
-    cond = q.a("g.cond", embed)
-    ms_w = torch.cat([q.w(p[g + "dense/kernel"]), q.w(p[g + "dense_1/kernel"])], 1)
-    ms = q.a("g.ms", O.lrelu(cond @ ms_w + torch.cat([p[g + "dense/bias"], p[g + "dense_1/bias"]])))
+    # the conditioning head runs in fp32 since round 2 (t2i_dense_f32: fp32 cond, fp32 master weights, fp32 [mean | log_sigma]);
+    # --round-head emulates round 1, where cond, the weights and the head's output were bf16
+    head = q.round_head
+    cond = q.a("g.cond", embed) if head else embed
+    wq = q.w if head else (lambda t: t)
+    ms_w = torch.cat([wq(p[g + "dense/kernel"]), wq(p[g + "dense_1/kernel"])], 1)
+    ms = O.lrelu(cond @ ms_w + torch.cat([p[g + "dense/bias"], p[g + "dense_1/bias"]]))
+    if head:
+        ms = q.a("g.ms", ms)
     ce = cfg.compressed_embed_dim
     c = ms[:, :ce] + torch.exp(ms[:, ce:]) * tn_eps
     zc = q.a("g.zc", torch.cat([z, c], 1))
@@ -129,7 +137,9 @@ def main():
     ap.add_argument("--seed", type=int, default=0)
     ap.add_argument("--fmt", default="bf16")
     ap.add_argument("--per-site", action="store_true")
+    ap.add_argument("--round-head", action="store_true", help="round the conditioning head to the storage format too (round 1)")
     a = ap.parse_args()
+    Q.round_head = a.round_head
     torch.set_grad_enabled(False)
     cfg = O.OracleCfg(batch_size=a.batch)
     p = O.init_params(cfg, a.seed)
