@@ -26,8 +26,8 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 // The padded bf16 rows of one tile (image rows ih0 .. ih0 + n_rows - 1 of every plane) -> ring slot `dst`
 // ([plane][n_rows][pitchw] words).  Rows outside the image (SAME padding; at most the first and the last row of a tile)
-// are zero-filled by all `nthreads` producers; then thread 0 arms `bar` with the byte count and issues one bulk copy per
-// valid row.  Call it after a barrier that guarantees nobody still reads the slot.
+// are zero-filled by all `nthreads` producers (nthreads >= np * n_rows); then one bulk copy per valid row is issued.
+// Call it after a barrier that guarantees nobody still reads the slot.
 __device__ __forceinline__ void img_rows_fetch(const uint32_t* rows, long long plane_words, long long sample_words, int np,
                                                int n, int ih0, int img_h, int n_rows, int pitchw, uint32_t* dst,
                                                uint64_t* bar, int pt, int nthreads) {
@@ -39,13 +39,16 @@ __device__ __forceinline__ void img_rows_fetch(const uint32_t* rows, long long p
                 if (r < lo || r >= hi)
                     for (int c = pt; c < pitchw; c += nthreads) dst[(pl * n_rows + r) * pitchw + c] = 0u;
     }
-    if (pt == 0) {
-        mbar_arrive_expect_tx(bar, static_cast<uint32_t>(np * (hi - lo) * pitchw * 4));
-        for (int pl = 0; pl < np; ++pl)
-            for (int r = lo; r < hi; ++r)
-                bulk_load_1d(dst + (pl * n_rows + r) * pitchw,
-                             rows + pl * plane_words + n * sample_words + static_cast<long long>(ih0 + r) * pitchw,
-                             static_cast<uint32_t>(pitchw * 4), bar);
+    // thread 0 arms the barrier, thread (plane, row) issues that row's copy: the issue is one SIMT instruction stream for
+    // all rows instead of a serial loop in one thread (which made that thread the straggler of every trip).  A copy may
+    // complete before the expect_tx lands: the transaction count is signed, the phase needs thread 0's arrival too.
+    if (pt == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(np * (hi - lo) * pitchw * 4));
+    if (pt < np * n_rows) {
+        const int pl = pt / n_rows, r = pt - pl * n_rows;
+        if (r >= lo && r < hi)
+            bulk_load_1d(dst + (pl * n_rows + r) * pitchw,
+                         rows + pl * plane_words + n * sample_words + static_cast<long long>(ih0 + r) * pitchw,
+                         static_cast<uint32_t>(pitchw * 4), bar);
     }
 }
 

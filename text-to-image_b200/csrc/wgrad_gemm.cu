@@ -27,7 +27,7 @@ constexpr int kWThreads = 192;
 // IMG: warps 2..7 (the four reduction warps, idle until a work item ends, plus two more) feed the patch rows of the K blocks
 constexpr int kWImgProducers = 192;
 constexpr int kWThreadsImg = 64 + kWImgProducers;
-constexpr int kWImgRing = 4;                  // IMG: ring slots of padded bf16 image rows in flight (bulk copies, K blocks ahead)
+constexpr int kWImgRing = 8;                  // IMG: ring slots of padded bf16 image rows (bulk copies, six K blocks ahead)
 constexpr int kWImgRowBytes = kWImgRing * 6400;   // a slot: (2*bp + 2) rows of one plane (the pass's), at most 6400 bytes
 
 // CTA2: a CTA pair (cta_group::2) computes 256 output channels x BN input channels; each CTA stages its
@@ -349,47 +349,56 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
             img_rows_fetch(prm.img + (lo_plane ? prm.img_plane_words : 0), 0, sample_words, 1, tn, 2 * tp * prm.bp - 1,
                            prm.img_h, n_rows, pitchw, s_img + slot * slot_words, &rows_full[slot], pt, kWImgProducers);
         };
+        // Two K blocks per trip: threads 0..63 assemble block j, threads 64..127 block j + 1 (one named barrier and one
+        // round of bulk-copy issue per 128 pixels); the ring holds kWImgRing slots, kWImgRing - 2 blocks are in flight.
         Cursor cur;
         cur.w = w0;
         settle(cur);
-        Cursor pf = cur;                         // runs kWImgRing - 1 blocks ahead of cur
-        for (int a = 0; a < kWImgRing - 1; ++a) {
+        Cursor pf = cur;                         // runs kWImgRing - 2 blocks ahead of cur
+        for (int a = 0; a < kWImgRing - 2; ++a) {
             fetch(pf, a);
             if (pf.valid) advance(pf);
         }
-        int stage = 0, slot = 0, round = 0, it = 0;
-        uint32_t phase = 0;
+        int jb0 = 0, it = 0;                     // jb0: index of `cur` in this CTA's block sequence
+        const int gi = pt >> 6, lt = pt & 63;
         while (cur.valid) {
-            Cursor nxt = cur;
-            advance(nxt);
-            named_bar(3, kWImgProducers);       // everybody is done with the previous block: its ring slot is free
-            fetch(pf, (slot + kWImgRing - 1) & (kWImgRing - 1));
+            Cursor c1 = cur;
+            advance(c1);                         // second block of the trip (may not exist)
+            Cursor c2 = c1;
+            if (c1.valid) advance(c2);           // first block of the next trip
+            named_bar(3, kWImgProducers);        // everybody is done with the previous trip: its two ring slots are free
+            fetch(pf, (jb0 + kWImgRing - 2) & (kWImgRing - 1));
             if (pf.valid) advance(pf);
-            if (pt < kWK) {
-                mbar_wait(&rows_full[slot], round & 1, 800 + slot);
-                const int q0 = (cur.kb % prm.tiles_q) * prm.bq;
-                mbar_wait(&empty_bar[stage], phase ^ 1, 700 + stage);
-                uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
-                int q = q0 + (pt & (prm.bq - 1));
-                if (q >= prm.Q) q = prm.Q - 1;
-                img_patch_row(s_img + slot * slot_words, pitchw, pt / prm.bq, q, atom + (pt >> 3) * 1024 + (pt & 7) * 128, pt,
-                              true);   // columns 48..63: zeros
-                fence_proxy_async();
-                mbar_arrive(&full_bar[stage]);
+            fetch(pf, (jb0 + kWImgRing - 1) & (kWImgRing - 1));
+            if (pf.valid) advance(pf);
+            if (gi < 2) {
+                const Cursor& cb = (gi == 0) ? cur : c1;
+                if (cb.valid) {
+                    const int jb = jb0 + gi;
+                    const int slot = jb & (kWImgRing - 1), stage = jb % kStages;
+                    mbar_wait(&rows_full[slot], (jb / kWImgRing) & 1, 800 + slot);
+                    const int q0 = (cb.kb % prm.tiles_q) * prm.bq;
+                    mbar_wait(&empty_bar[stage], ((jb / kStages) & 1) ^ 1, 700 + stage);
+                    uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
+                    int q = q0 + (lt & (prm.bq - 1));
+                    if (q >= prm.Q) q = prm.Q - 1;
+                    img_patch_row(s_img + slot * slot_words, pitchw, lt / prm.bq, q, atom + (lt >> 3) * 1024 + (lt & 7) * 128, lt,
+                                  true);   // columns 48..63: zeros
+                    fence_proxy_async();
+                    mbar_arrive(&full_bar[stage]);
+                }
             }
-            if (++stage == kStages) {
-                stage = 0;
-                phase ^= 1;
-            }
-            if (++slot == kWImgRing) {
-                slot = 0;
-                ++round;
-            }
-            if (!nxt.valid || nxt.w != cur.w) {      // the work item is complete
+            // work items completed by this trip, in order
+            if (!c1.valid || c1.w != cur.w) {
                 if (warp < 6) reduce_item(decode(cur.w), it);
                 ++it;
             }
-            cur = nxt;
+            if (c1.valid && (!c2.valid || c2.w != c1.w)) {
+                if (warp < 6) reduce_item(decode(c1.w), it);
+                ++it;
+            }
+            jb0 += 2;
+            cur = c1.valid ? c2 : c1;
         }
     } else {
         // reduction warps: accumulator -> red.global.add into dw, while the MMAs of the next item run
