@@ -36,8 +36,19 @@ class SyntheticTextDataset(object):
             emb = self._rng.normal(0, 1, (1, batch_size, self._embed_dim)).astype(np.float32)
             return img, emb, None, [["synthetic caption %d" % i] for i in range(batch_size)]
 
-    def __init__(self, embed_dim=1024, num_examples=8192, seed=0, image_size=64):
-        self.train = self._Split(num_examples, embed_dim, seed, image_size)
+    def __init__(self, embed_dim=1024, num_examples=8192, seed=0, image_size=64, rank=None):
+        """rank: data-parallel replicas must draw DIFFERENT batches (each rank is a shard of the global batch): the
+        training stream is seeded per rank (default: the torch.distributed rank when a process group exists); the test
+        split, which conditions the sample grids, is the same everywhere."""
+        if rank is None:
+            rank = 0
+            try:
+                import torch.distributed as dist
+                if dist.is_available() and dist.is_initialized():
+                    rank = dist.get_rank()
+            except Exception:
+                pass
+        self.train = self._Split(num_examples, embed_dim, seed + 1000 * rank, image_size)
         self.test = self._Split(num_examples // 8, embed_dim, seed + 1, image_size)
 
 
@@ -117,6 +128,6 @@ class WGanClsTrainer(object):
                     print(e.args)
                     print(e)
 
-            if np.mod(idx, 500) == 2:
+            if np.mod(idx, 500) == 2:       # rank 0 writes, every rank passes the barrier inside save()
                 save(m, cfg.CHECKPOINT_DIR, idx, cfg.TRAIN.CHECKPOINTS_TO_KEEP)
             sys.stdout.flush()
