@@ -37,14 +37,14 @@ __device__ __forceinline__ void img_rows_fetch(const uint32_t* rows, long long p
         for (int pl = 0; pl < np; ++pl)
             for (int r = 0; r < n_rows; ++r)
                 if (r < lo || r >= hi)
-                    for (int c = pt; c < pitchw; c += nthreads) dst[(pl * n_rows + r) * pitchw + c] = 0u;
+                    for (int c = pt; c >= 0 && c < pitchw; c += nthreads) dst[(pl * n_rows + r) * pitchw + c] = 0u;
     }
     // thread 0 arms the barrier, thread (plane, row) issues that row's copy: the issue is one SIMT instruction stream for
     // all rows instead of a serial loop in one thread (which made that thread the straggler of every trip).  A copy may
     // complete before the expect_tx lands: the transaction count is signed, the phase needs thread 0's arrival too.
     if (pt == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(np * (hi - lo) * pitchw * 4));
-    if (pt < np * n_rows) {
-        const int pl = pt / n_rows, r = pt - pl * n_rows;
+    if (pt >= 0 && pt < np * n_rows) {
+        const int pl = (np == 1) ? 0 : pt / n_rows, r = pt - pl * n_rows;
         if (r >= lo && r < hi)
             bulk_load_1d(dst + (pl * n_rows + r) * pitchw,
                          rows + pl * plane_words + n * sample_words + static_cast<long long>(ih0 + r) * pitchw,

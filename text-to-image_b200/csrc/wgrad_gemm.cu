@@ -72,7 +72,14 @@ struct alignas(64) WgradParams {
     const uint32_t* img;       // padded bf16 rows [np][N][img_h][pitch] as words (t2i_img_to_rows)
     long long img_plane_words;
     int img_h, img_w;
+    unsigned long long* timeline;      // debug build only (T2I_TIMELINE_BUILD), see conv_gemm.cu
 };
+#ifdef T2I_TIMELINE_BUILD
+#define T2I_WMARK(it, ev) \
+    do { if (prm.timeline != nullptr && blockIdx.x == 0 && (it) < 64) prm.timeline[(it) * 8 + (ev)] = global_timer_ns(); } while (0)
+#else
+#define T2I_WMARK(it, ev) do {} while (0)
+#endif
 
 // IMG = 1: the x operand (B) is the image patch matrix -- d_net's first conv: dw[co][(kh,kw,c)] += dy[pixel][co] * patch;
 // IMG = 2: the dy operand (A) is -- g_net's last transposed conv: dw[(kh,kw,c)][ci] += patch(d image)[pixel] * x[pixel][ci].
@@ -279,6 +286,7 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
                 for (int kb = 0; kb < wk.n_kb; ++kb) {
                     mbar_wait(&full_bar[stage], phase, 200 + stage);
                     tc_fence_after();
+                    if (IMG != 0 && (kb & 1) == 0) T2I_WMARK(kb >> 1, 5);
                     const uint32_t sa = smem_u32(smem + stage * Cfg::kStageBytes);
 #pragma unroll
                     for (int k = 0; k < kWK / 16; ++k) {
@@ -316,8 +324,11 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
         const int pitchw = img_pitch_words(prm.img_w);
         const int slot_words = n_rows * pitchw;
         const long long sample_words = static_cast<long long>(prm.img_h) * pitchw;
+        // (the block coordinates travel with the cursor: the producers are few and latency bound, integer divisions in
+        // this loop cost more than the patch assembly itself -- measured with the debug timeline)
         struct Cursor {
             int w, pass, kb, kb_begin, kb_end;
+            int tq, tp, tn, tq0, tp0, tn0;        // block coordinates of kb and of kb_begin (bn == 1: tn = the sample)
             bool valid;
         };
         auto settle = [&](Cursor& c) {      // move to the first existing block at or after (w, pass = 0)
@@ -325,6 +336,10 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
                 const Work wk = decode(c.w);
                 if (wk.n_kb > 0) {
                     c.kb_begin = wk.kb_begin; c.kb_end = wk.kb_end; c.kb = wk.kb_begin; c.pass = 0;
+                    c.tq0 = c.kb % prm.tiles_q;
+                    c.tp0 = (c.kb / prm.tiles_q) % prm.tiles_p;
+                    c.tn0 = c.kb / (prm.tiles_q * prm.tiles_p);
+                    c.tq = c.tq0; c.tp = c.tp0; c.tn = c.tn0;
                     c.valid = true;
                     return;
                 }
@@ -333,21 +348,34 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
             c.valid = false;
         };
         auto advance = [&](Cursor& c) {
-            if (++c.kb < c.kb_end) return;
+            if (++c.kb < c.kb_end) {
+                if (++c.tq == prm.tiles_q) {
+                    c.tq = 0;
+                    if (++c.tp == prm.tiles_p) {
+                        c.tp = 0;
+                        ++c.tn;
+                    }
+                }
+                return;
+            }
             if (++c.pass < prm.n_pass) {
                 c.kb = c.kb_begin;
+                c.tq = c.tq0; c.tp = c.tp0; c.tn = c.tn0;
                 return;
             }
             c.w += w_stride;
             settle(c);
         };
-        auto fetch = [&](const Cursor& c, int slot) {
+        const int lg_bq = __ffs(prm.bq) - 1;
+        // `who`: the 64-thread group that issues this fetch (two fetches of a trip run side by side in two warps)
+        auto fetch = [&](const Cursor& c, int slot, int who) {
             if (!c.valid) return;
-            const int tp = (c.kb / prm.tiles_q) % prm.tiles_p;
-            const int tn = c.kb / (prm.tiles_q * prm.tiles_p);                   // bn == 1: the sample
+            const int fpt = pt - 64 * who;
+            if (fpt < 0 || fpt >= 64) return;
+            const int tp = c.tp, tn = c.tn;
             const bool lo_plane = (IMG == 1) ? (c.pass == 2) : (c.pass == 1);     // x: hi, hi, lo; dy: hi, lo, hi
             img_rows_fetch(prm.img + (lo_plane ? prm.img_plane_words : 0), 0, sample_words, 1, tn, 2 * tp * prm.bp - 1,
-                           prm.img_h, n_rows, pitchw, s_img + slot * slot_words, &rows_full[slot], pt, kWImgProducers);
+                           prm.img_h, n_rows, pitchw, s_img + slot * slot_words, &rows_full[slot], fpt, 64);
         };
         // Two K blocks per trip: threads 0..63 assemble block j, threads 64..127 block j + 1 (one named barrier and one
         // round of bulk-copy issue per 128 pixels); the ring holds kWImgRing slots, kWImgRing - 2 blocks are in flight.
@@ -356,7 +384,7 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
         settle(cur);
         Cursor pf = cur;                         // runs kWImgRing - 2 blocks ahead of cur
         for (int a = 0; a < kWImgRing - 2; ++a) {
-            fetch(pf, a);
+            fetch(pf, a, a & 1);
             if (pf.valid) advance(pf);
         }
         int jb0 = 0, it = 0;                     // jb0: index of `cur` in this CTA's block sequence
@@ -367,25 +395,30 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
             Cursor c2 = c1;
             if (c1.valid) advance(c2);           // first block of the next trip
             named_bar(3, kWImgProducers);        // everybody is done with the previous trip: its two ring slots are free
-            fetch(pf, (jb0 + kWImgRing - 2) & (kWImgRing - 1));
+            if (pt == 0) T2I_WMARK(jb0 >> 1, 0);
+            fetch(pf, (jb0 + kWImgRing - 2) & (kWImgRing - 1), 0);
             if (pf.valid) advance(pf);
-            fetch(pf, (jb0 + kWImgRing - 1) & (kWImgRing - 1));
+            fetch(pf, (jb0 + kWImgRing - 1) & (kWImgRing - 1), 1);
             if (pf.valid) advance(pf);
             if (gi < 2) {
                 const Cursor& cb = (gi == 0) ? cur : c1;
                 if (cb.valid) {
                     const int jb = jb0 + gi;
                     const int slot = jb & (kWImgRing - 1), stage = jb % kStages;
+                    if (pt == 0) T2I_WMARK(jb0 >> 1, 1);
                     mbar_wait(&rows_full[slot], (jb / kWImgRing) & 1, 800 + slot);
-                    const int q0 = (cb.kb % prm.tiles_q) * prm.bq;
+                    if (pt == 0) T2I_WMARK(jb0 >> 1, 2);
+                    const int q0 = cb.tq * prm.bq;
                     mbar_wait(&empty_bar[stage], ((jb / kStages) & 1) ^ 1, 700 + stage);
+                    if (pt == 0) T2I_WMARK(jb0 >> 1, 3);
                     uint8_t* atom = smem + stage * Cfg::kStageBytes + (IMG == 1 ? Cfg::kABytes : 0);
                     int q = q0 + (lt & (prm.bq - 1));
                     if (q >= prm.Q) q = prm.Q - 1;
-                    img_patch_row(s_img + slot * slot_words, pitchw, lt / prm.bq, q, atom + (lt >> 3) * 1024 + (lt & 7) * 128, lt,
+                    img_patch_row(s_img + slot * slot_words, pitchw, lt >> lg_bq, q, atom + (lt >> 3) * 1024 + (lt & 7) * 128, lt,
                                   true);   // columns 48..63: zeros
                     fence_proxy_async();
                     mbar_arrive(&full_bar[stage]);
+                    if (pt == 0) T2I_WMARK(jb0 >> 1, 4);
                 }
             }
             // work items completed by this trip, in order
@@ -482,6 +515,13 @@ static int launch_wgrad_img(const WgradParams& prm, int grid, cudaStream_t strea
 
 using namespace t2i;
 
+#ifdef T2I_TIMELINE_BUILD
+unsigned long long* g_wgrad_timeline = nullptr;
+extern "C" int t2i_debug_wgrad_timeline(unsigned long long* host_dst, int count) {
+    if (g_wgrad_timeline == nullptr) return -1;
+    return cudaMemcpy(host_dst, g_wgrad_timeline, 8 * count, cudaMemcpyDeviceToHost) == cudaSuccess ? 0 : -2;
+}
+#endif
 extern "C" int t2i_wgrad_img(const void* img, long long plane_stride, int n, int h, int w, const t2i_act* other, int img_side,
                              int np, float* dw, int cout, int cin, void* stream_) {
     if ((reinterpret_cast<uintptr_t>(img) & 15) != 0) return fail(T2I_ERR_BAD_ARG, "wgrad_img: rows must be 16-byte aligned");
@@ -531,6 +571,15 @@ extern "C" int t2i_wgrad_img(const void* img, long long plane_stride, int n, int
     prm.kb_per_split = ceil_div(prm.k_blocks, splits);
     prm.splits = ceil_div(prm.k_blocks, prm.kb_per_split);
     prm.dw = dw;
+#ifdef T2I_TIMELINE_BUILD
+    {
+        static unsigned long long* tl = nullptr;
+        if (tl == nullptr) { cudaMalloc(&tl, 64 * 8 * 8); cudaMemset(tl, 0, 64 * 8 * 8); }
+        prm.timeline = tl;
+        extern unsigned long long* g_wgrad_timeline;
+        g_wgrad_timeline = tl;
+    }
+#endif
     prm.img = static_cast<const uint32_t*>(img); prm.img_plane_words = plane_stride / 2; prm.img_h = h; prm.img_w = w;
     int rc = make_maps(*other, false, np, prm.bq, prm.bp, prm.bn, img_side == 1 ? prm.dy_maps : prm.x_maps);
     if (rc != T2I_OK) return rc;
