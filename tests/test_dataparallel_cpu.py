@@ -219,7 +219,9 @@ def test_two_rank_d_run_equals_single_process(tmp_path):
     assert r["worst"] < 1e-9, r
     assert r["smax"] < 1e-9, r
     assert abs(r["kt"] - r["kt_ref"]) < 1e-12
-    assert len(r["calls"]) == 2 and r["same"], r      # exactly one allreduce per optimizer step
+    # one gradient all-reduce per optimizer step; the G run sends its handful of loss sums ahead of it (the losses are
+    # published before the backward pass)
+    assert len(r["calls"]) == 3 and r["calls"][1] <= 16 and r["same"], r
 
 
 def test_two_rank_bucketed_g_allreduce_matches_single_call(tmp_path):
@@ -231,8 +233,10 @@ def test_two_rank_bucketed_g_allreduce_matches_single_call(tmp_path):
         mp.spawn(worker, args=(2, _free_port(), out), nprocs=2, join=True)
         outs.append(torch.load(out))
     one, two = outs
-    assert len(one["calls"]) == 2 and len(two["calls"]) == 3, (one["calls"], two["calls"])
-    assert two["calls"][1] == two["g_split"] and two["calls"][1] + two["calls"][2] == one["calls"][1]
+    # calls: [D gradient, G loss sums (sent ahead: the losses are published before the backward pass), G gradient ...]
+    assert len(one["calls"]) == 3 and len(two["calls"]) == 4, (one["calls"], two["calls"])
+    assert one["calls"][1] == two["calls"][1] <= 16
+    assert two["calls"][2] == two["g_split"] and two["calls"][2] + two["calls"][3] == one["calls"][2]
     assert 0.5 < two["g_split"] / two["g_n"] < 0.8          # the early bucket carries most of the bytes
     assert two["same"] and torch.equal(one["g_flat"], two["g_flat"])
 
@@ -300,7 +304,9 @@ def test_two_rank_pggan_iteration_equals_single_process(tmp_path):
     assert r["gp"] > 1e-3, r                                # the penalty (and its second-order term) is active
     assert r["img"] < 1e-10 and r["d_grads"] < 1e-8 and r["g_grads"] < 1e-8, r
     assert r["scalars"] < 1e-9 and r["params"] < 1e-10, r
-    assert r["calls"] == [r["d_n"], r["g_n"]], r            # exactly one all-reduce per optimizer step
+    # one gradient all-reduce per optimizer step, the G run's loss sums ahead of its gradient
+    assert len(r["calls"]) == 3 and r["calls"][0] == r["d_n"] and r["calls"][1] <= 16, r
+    assert r["calls"][1] + r["calls"][2] == r["g_n"], r
 
 
 def _worker_stage2(rank, world, port, out):

@@ -200,6 +200,7 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     pdl_launch_dependents();   // the next kernel may run its prologue under this grid's tail
+    if (threadIdx.x == 0) T2I_MARK(63, 0);      // row 63 of the timeline: kernel-level stamps
 
     if (warp == 0 && lane == 0) {
         for (int i = 0; i < prm.tt.n_maps; ++i) tma_prefetch_desc(&prm.a_maps[i]);
@@ -231,7 +232,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
     if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) T2I_MARK(63, 1);
     pdl_wait();                // prologue done; from here on global memory of earlier kernels is read
+    if (threadIdx.x == 0) T2I_MARK(63, 2);
 
     const int tpp = prm.tt.taps_per_phase;
     const int kb_per_tile = prm.n_pass * tpp * prm.k_chunks;
@@ -725,7 +728,9 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
                 }
             }
         }
-        if (leader) bulk_wait_all();
+        // the stores must have left shared memory before the CTA exits; their global writes complete with the grid
+        if (leader) bulk_wait_read<0>();
+        if (leader && grp == 0) T2I_MARK(63, 6);
         if (STATS && prm.stat_acc > 0 && !(prm.dbg & 4)) {   // one global atomic per channel this group contributed to
             const int which = et >> 6;
             float* dst = which == 0 ? prm.stat_sum : prm.stat_second;
@@ -739,13 +744,16 @@ conv_gemm_kernel(const __grid_constant__ ConvGemmParams prm) {
         }   // grp < G
     }
 
+    if (threadIdx.x == 0) T2I_MARK(63, 3);
     tc_fence_before();
     if (CTA2) cluster_sync_all(); else __syncthreads();   // the peer may still be read by the leader's MMAs
+    if (threadIdx.x == 0) T2I_MARK(63, 4);
     if (warp == 1) {
         __syncwarp();
         tc_fence_after();
         if (CTA2) tmem_dealloc_2sm(tmem_base, kAccBufs * BLOCK_N);
         else tmem_dealloc(tmem_base, kAccBufs * BLOCK_N);
+        if (lane == 0) T2I_MARK(63, 5);
     }
 }
 
@@ -792,9 +800,11 @@ static void choose_box(int P, int Q, int rows, int* bn, int* bp, int* bq) {
 
 using namespace t2i;
 
-static unsigned long long* g_timeline = nullptr;
+static unsigned long long* g_timeline = nullptr;     // debug build: kTimelineRegions x [64 tiles][8 events], one region per launch (round robin)
+static const int kTimelineRegions = 32;
+static int g_timeline_next = 0;
 extern "C" int t2i_debug_timeline(unsigned long long* host_dst, int count) {
-    if (g_timeline == nullptr || count > 64 * 8) return fail(T2I_ERR_BAD_ARG, "no timeline recorded (T2I_TIMELINE=1)");
+    if (g_timeline == nullptr || count > kTimelineRegions * 64 * 8) return fail(T2I_ERR_BAD_ARG, "no timeline recorded (T2I_TIMELINE=1)");
     cudaError_t e = cudaMemcpy(host_dst, g_timeline, sizeof(unsigned long long) * count, cudaMemcpyDeviceToHost);
     return e == cudaSuccess ? T2I_OK : fail(T2I_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
 }
@@ -903,15 +913,29 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     if (n_aux == 3) prm.epi_depth = 1;
     // two epilogue groups (each with its own staging buffers) in the throughput mode; with aux tiles one buffer each
     prm.epi_groups = (d->np == 1) ? 2 : 1;
+    {
+        static const int force = [] { const char* e = getenv("T2I_EPI_GROUPS"); return e ? atoi(e) : 0; }();
+        if (force == 1 && n_aux >= 2) prm.epi_groups = 1;
+    }
     // 256-wide tiles have two TMEM accumulators: both groups must finish a tile together (sub-tile split), or the
     // MMAs of the tile after next wait for a whole single-group epilogue
-    prm.epi_split = (block_n == 256) ? 1 : 0;
+    // launches of at most one tile per CTA would leave the second group idle: there too both groups share the tile
+    prm.epi_split = (block_n == 256 || prm.total_tiles <= workers) ? 1 : 0;
     {
         static const int force = [] { const char* e = getenv("T2I_EPI_MODE"); return e ? atoi(e) : 0; }();
         if (force == 1) prm.epi_split = 0;
         if (force == 2) prm.epi_split = 1;
     }
-    if (prm.epi_groups == 2) prm.epi_depth = 1;      // one staging buffer per group = the two of a single group: the mainloop keeps its stages
+    // one staging buffer per group = the two of a single group, so that the mainloop keeps its stages; tiles of one or two
+    // K blocks are bound by the epilogue (the wait for the previous store to leave the buffer is on its critical path)
+    // and need few stages: two buffers per group there
+    const bool short_k = prm.n_pass * prm.tt.taps_per_phase * prm.k_chunks <= 2;
+    if (prm.epi_groups == 2) prm.epi_depth = (short_k && n_aux <= 1) ? 2 : 1;
+    {
+        static const int force = [] { const char* e = getenv("T2I_EPI_DEPTH"); return e ? atoi(e) : 0; }();
+        if (force == 3 && a_img) prm.epi_depth = 2;
+        if ((force == 1 || force == 2) && n_aux <= 1) prm.epi_depth = force;
+    }
     const int epi_bytes = prm.epi_groups * (1 + n_aux) * prm.epi_depth * d->np * kSubBytes;
     const bool stats = prm.stat_sum != nullptr || prm.stat_second != nullptr;
     // per-CTA running totals in shared memory (one flush per CTA instead of one atomic per tile and channel:
@@ -925,10 +949,10 @@ extern "C" int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream_) {
     {
         static const bool want = [] { const char* e = getenv("T2I_TIMELINE"); return e && e[0] == '1'; }();
         if (want && g_timeline == nullptr) {
-            cudaMalloc(&g_timeline, 64 * 8 * sizeof(unsigned long long));
-            cudaMemset(g_timeline, 0, 64 * 8 * sizeof(unsigned long long));
+            cudaMalloc(&g_timeline, kTimelineRegions * 64 * 8 * sizeof(unsigned long long));
+            cudaMemset(g_timeline, 0, kTimelineRegions * 64 * 8 * sizeof(unsigned long long));
         }
-        prm.timeline = want ? g_timeline : nullptr;
+        prm.timeline = want ? g_timeline + (g_timeline_next++ % kTimelineRegions) * 64 * 8 : nullptr;
     }
     prm.img = static_cast<const uint32_t*>(d->x_img);
     prm.img_plane_words = x.plane_stride / 2;

@@ -118,6 +118,7 @@ class Engine:
         self.copy_stream = torch.cuda.Stream(self.dev) if (self.dev.type == "cuda" and concurrent) else None
         self._scalars_host = self._scalars_event = None
         self._scalars_published = False
+        self._img_free = None           # recorded after the D run's last read of the fed image segments
         self.replayed_launches = 0      # kernels executed through graph replays
         self.captured_launches = 0      # kernels recorded (not executed) during captures
         if share_from is None:
@@ -852,7 +853,12 @@ class Engine:
             # forward of the D run: copy them on their own stream so that the transfer hides under it.
             cs = self.copy_stream if (self.copy_stream is not None and not torch.as_tensor(x if x is not None else x_mismatch).is_cuda) else None
             if cs is not None:
-                cs.wait_stream(torch.cuda.current_stream())
+                # img[B:3B] is free once the last D run has read it (d_step records the event): the copy need not
+                # queue behind the G run still executing, it travels under it
+                if self._img_free is not None:
+                    cs.wait_event(self._img_free)
+                else:
+                    cs.wait_stream(torch.cuda.current_stream())
             with (torch.cuda.stream(cs) if cs is not None else contextlib.nullcontext()):
                 if x is not None:
                     d["img"][B:2 * B].copy_(x, non_blocking=True)
@@ -932,6 +938,10 @@ class Engine:
         if self.copy_stream is not None:        # the real / mismatching images arrive on the copy stream
             torch.cuda.current_stream().wait_stream(self.copy_stream)
         self._run("d_a", self._d_body)
+        if self.copy_stream is not None:        # the fed image segments may be overwritten from here on (load_feed)
+            if self._img_free is None:
+                self._img_free = torch.cuda.Event()
+            self._img_free.record()
         # The collective of the D run, the kt step and Adam go to the communication stream: the G run's
         # generator forward does not depend on them and overlaps (it joins before its d_net forward).
         with self._on_comm():
@@ -999,6 +1009,8 @@ class Engine:
         self._set_lr("g", lr_g, self.g_t)
         self._run("g_a1", self._g_body_fwd)
         self.join_comm()                        # d_net's weights of this iteration are final from here on
+        if not self.sync_bn:
+            return self._g_step_early_loss()
         if self.g_buckets == 2 and self.world > 1 and self.g_split is not None and not self.sync_bn:
             self._run("g_a2", lambda: self._g_body(part=1))
             with self._on_comm():                  # bucket 1 travels under the rest of the backward pass
@@ -1012,6 +1024,44 @@ class Engine:
         self._run("g_b", self._g_tail_scalars)
         self._publish_scalars()
         self._run("g_c", self._g_tail_adam)
+
+    def _g_step_early_loss(self):
+        """The rest of the G run with the losses published as soon as they exist: G_loss needs d_net's logits of the
+        fake batch and the KL sum only, both final after the d_net forward -- two thirds of the run are still to come
+        (d_net backward, g_net backward, all-reduce, Adam).  A caller that fetches G_loss (sess.run([G_optim, G_loss]))
+        gets it then and stages the next run's feeds while the device works on; the sums travel in their own small
+        all-reduce, the gradient all-reduce leaves them out."""
+        bucketed = self.g_buckets == 2 and self.world > 1 and self.g_split is not None
+        self._run("g_a2", self._g_body_dfwd)
+        with self._on_comm():
+            if self.world > 1:
+                self.allreduce(self.sums["g"])
+            self._run("g_b", self._g_tail_scalars)
+            self._publish_scalars()
+        if bucketed:
+            self._run("g_a3", lambda: self._g_body_bwd(part=1))
+            with self._on_comm():                  # bucket 1 travels under the rest of the backward pass
+                self.allreduce(self.grad["g"][:self.g_split])
+            self._run("g_a4", lambda: self.g_backward(self.d["gx"], part=2))
+            self.allreduce(self.grad["g"][self.g_split:self.g_n])
+        else:
+            self._run("g_a3", self._g_body_bwd)
+            if self.world > 1:
+                self.allreduce(self.grad["g"][:self.g_n])
+        self.join_comm()
+        self._run("g_c", self._g_tail_adam)
+
+    def _g_body_dfwd(self):
+        self.d_forward(0, self.B)
+        self.K.g_sums(self.d["logit"], self.B, self.sums["g"])
+
+    def _g_body_bwd(self, part=None):
+        d, B = self.d, self.B
+        self.d_backward(0, B, d["gseed"], 0, B, False)
+        if part is None:          # (subclasses override g_backward without the bucket split)
+            self.g_backward(d["gx"])
+        else:
+            self.g_backward(d["gx"], part)
 
     def _g_tail_scalars(self):
         self.K.g_scalars(self.sums["g"], self.scalars, self.GB, self.ce, self.kl_coeff)   # model.py:92
