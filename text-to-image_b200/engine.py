@@ -937,17 +937,25 @@ class Engine:
         self._run("d_a1", self._d_body_gen)
         if self.copy_stream is not None:        # the real / mismatching images arrive on the copy stream
             torch.cuda.current_stream().wait_stream(self.copy_stream)
-        self._run("d_a", self._d_body)
+        self._run("d_a", self._d_body_loss)
         if self.copy_stream is not None:        # the fed image segments may be overwritten from here on (load_feed)
             if self._img_free is None:
                 self._img_free = torch.cuda.Event()
             self._img_free.record()
-        # The collective of the D run, the kt step and Adam go to the communication stream: the G run's
-        # generator forward does not depend on them and overlaps (it joins before its d_net forward).
+        # D_loss and the kt step need the four logit sums and the two penalties only: they are published here (own small
+        # all-reduce of the sums), with the tangent pass and every weight gradient still to come -- a caller that
+        # fetches D_loss stages the G run while the device works on.
         with self._on_comm():
-            self._reduce("d")                   # outside the graphs
+            if self.world > 1:
+                self.allreduce(self.sums["d"])
             self._run("d_b", self._d_tail_scalars)
-            self._publish_scalars()             # the losses are final here: a fetch need not wait for Adam
+            self._publish_scalars()
+        self._run("d_a2", self._d_body_rest)
+        # The gradient collective and Adam go to the communication stream: the G run's generator forward does not
+        # depend on them and overlaps (it joins before its d_net forward).
+        with self._on_comm():
+            if self.world > 1:
+                self.allreduce(self.grad["d"][:self.d_n])      # outside the graphs
             self._run("d_c", self._d_tail_adam)
 
     def _d_tail_scalars(self):
@@ -976,6 +984,11 @@ class Engine:
         self.g_forward(g["z"], self.feed["cond"], g["tn"], self.d["img"][:self.B], g["kl_scratch"])   # model.py:48
 
     def _d_body(self):
+        self._d_body_loss()
+        self._d_body_rest()
+
+    def _d_body_loss(self):
+        """Everything D_loss depends on: the 4B forward, the seeded backward down to the images, the two penalties."""
         K, d, g, B = self.K, self.d, self.g, self.B
         S = 4 * B
         cond = self.feed["cond"]
@@ -989,6 +1002,11 @@ class Engine:
         inv = 1.0 / self.GB
         K.gp_penalty(d["gx"], GP_WEIGHT, inv, d["slope"], d["coef"], self.sums["d"][4:5])       # :62-65
         K.gp_penalty(d["g2"], GP_WEIGHT, inv, d["slope2"], d["coef2"], self.sums["d"][5:6])     # :67-70
+
+    def _d_body_rest(self):
+        """The second-order term and every weight gradient of the D run."""
+        K, d, g, B = self.K, self.d, self.g, self.B
+        S = 4 * B
         # second-order term: tangent (coef * g) through d_net, in place over the x_hat segment
         K.img_to_rows(d["gx"], d["rows"][:, 3 * B:], d["coef"])
         K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])

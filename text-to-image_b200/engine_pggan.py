@@ -459,7 +459,7 @@ class PgganEngine(Engine):
     def _d_tail_scalars(self):
         self.K.d_scalars(self.sums["d"], self.kt, self.scalars, self.GB, GP_WEIGHT, 0.0)     # kt stays 1 (:94-108)
 
-    def _d_body(self):
+    def _d_body_loss(self):
         K, d, B = self.K, self.d, self.B
         S4 = 4 * B
         cond = self.feed["cond"]
@@ -473,6 +473,10 @@ class PgganEngine(Engine):
         inv = 1.0 / self.GB
         K.gp_penalty(d["gx"], GP_WEIGHT, inv, d["slope"], d["coef"], self.sums["d"][4:5])          # :85-88
         K.gp_penalty(d["g2"], GP_WEIGHT, inv, d["slope2"], d["coef2"], self.sums["d"][5:6])        # :90-93
+
+    def _d_body_rest(self):
+        K, d, B = self.K, self.d, self.B
+        S4 = 4 * B
         # second-order term: tangent (coef * g) through d_net, in place over the x_hat segment
         K.img_to_c8(d["gx"], d["x8"][:, 3 * B:], d["coef"])
         K.to_planes(d["g2"], d["cond"][:, 3 * B:], d["coef2"])

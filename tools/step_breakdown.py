@@ -33,10 +33,12 @@ def main():
         eng.d_step(1e-4)
         eng.g_step(1e-4)
     torch.cuda.synchronize()
-    flops = {"d_a1": 2 * G_F * B, "d_a": 2 * 13 * D_F * B, "d_b": 0.0, "d_c": 0.0, "g_a1": 2 * G_F * B,
-             "g_a2": 2 * (2 * G_F + 2 * D_F) * B, "g_b": 0.0, "g_c": 0.0}
+    flops = {"d_a1": 2 * G_F * B, "d_a": 2 * 8 * D_F * B, "d_a2": 2 * 5 * D_F * B, "d_b": 0.0, "d_c": 0.0, "g_a1": 2 * G_F * B,
+             "g_a2": 2 * D_F * B, "g_a3": 2 * (2 * G_F + D_F) * B, "g_b": 0.0, "g_c": 0.0}
     total = 0.0
-    for name in ("d_a1", "d_a", "d_b", "d_c", "g_a1", "g_a2", "g_b", "g_c"):      # d_b / g_b: loss scalars, d_c / g_c: Adam
+    # d_b / g_b: loss scalars, d_c / g_c: Adam; g_a2: d_net forward of the G run, g_a3: both backward passes
+    # d_a: the D run up to its losses (4B forward, seeded backward, penalties), d_a2: tangent pass + weight gradients
+    for name in ("d_a1", "d_a", "d_b", "d_a2", "d_c", "g_a1", "g_a2", "g_b", "g_a3", "g_c"):
         graph = eng._graphs[name]["graph"]
         ts = []
         for _ in range(args.reps):
@@ -93,6 +95,23 @@ def main():
     timed("g_backward: the rest (c9 bwd, im2col, bn0, ca)", gb)
     K.conv_gemm, K.wgrad_gemm, K.bn_bwd_fused = real_conv, real_wgrad, real_bnb
     timed("_g_body_fwd (fresh capture)", eng._g_body_fwd)
+
+    def replay_timed(label, graph):
+        ts = []
+        for _ in range(args.reps):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b))
+        ts.sort()
+        print("%-44s %7.3f ms  (min %.3f max %.3f)" % (label, ts[len(ts) // 2], ts[0], ts[-1]))
+
+    replay_timed("g_a1 (the step's graph) again", eng._graphs["g_a1"]["graph"])
+    replay_timed("d_a1 (the step's graph) again", eng._graphs["d_a1"]["graph"])
+    with torch.cuda.stream(eng.comm_stream):
+        replay_timed("g_a1 replayed on the comm stream", eng._graphs["g_a1"]["graph"])
     timed("_d_body_gen (fresh capture)", eng._d_body_gen)
     timed("zero g + g_forward(sums tail) ", lambda: (eng.grad["g"].zero_(), eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], eng.sums["g"][1:2])))
     timed("g_forward + to_planes(cond)", lambda: (eng.g_forward(g["z"], eng.feed["cond"], g["tn"], d["img"][:B], g["kl_scratch"]),
