@@ -215,6 +215,24 @@ def test_mirror_stage_to_stage_restore_and_fade_in(tmp_path):
         _model(tmp_path / "elsewhere", 2, True).train(max_updates=1)      # no stage-1 checkpoint to fade in from (:149-151)
 
 
+def test_sampler_runs_in_training_batch_chunks(tmp_path):
+    """sess.run(sampler) for sample_num images uses the training engine chunk by chunk (the generator has no batch
+    statistics): same images as the generator called on each chunk, and no engine for a second batch size appears"""
+    m = _model(tmp_path, 2, False)            # batch 3
+    m.initialize()
+    rng = np.random.RandomState(3)
+    z, c, noise = rng.normal(0, 1, (5, 16)), rng.normal(0, 1, (5, 32)), rng.normal(0, 1, (5, 8)).clip(-2, 2)
+    m.sample_num = 5
+    got = m.run(m.sampler, feed_dict={m.z_sample: z, m.cond_sample: c, m.cond_noise_sample: noise})
+    assert got.shape == (5, 8, 8, 3)
+    for lo in (0, 3):
+        idx = np.arange(lo, lo + 3) % 5
+        ref, _, _ = m.generator(z[idx], c[idx], noise=noise[idx])
+        n = min(3, 5 - lo)
+        assert np.array_equal(got[lo:lo + n], ref[:n].cpu().numpy())
+    assert list(m._engines) == [3], list(m._engines)
+
+
 def test_schedule_driver_runs_consecutive_passes(tmp_path):
     """train_pggan.py:20-69: pass 0 (stage 1) writes stage1/, pass 1 (stage 2, transition) reads stage1/ and writes stage2/"""
     import os

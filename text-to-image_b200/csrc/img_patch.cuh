@@ -26,7 +26,7 @@ __device__ __forceinline__ void bulk_load_1d(void* smem_dst, const void* gsrc, u
 
 // The padded bf16 rows of one tile (image rows ih0 .. ih0 + n_rows - 1 of every plane) -> ring slot `dst`
 // ([plane][n_rows][pitchw] words).  Rows outside the image (SAME padding; at most the first and the last row of a tile)
-// are zero-filled by all `nthreads` producers (nthreads >= np * n_rows); then one bulk copy per valid row is issued.
+// are zero-filled by all `nthreads` producers (nthreads >= np); then one bulk copy per plane brings the valid rows.
 // Call it after a barrier that guarantees nobody still reads the slot.
 __device__ __forceinline__ void img_rows_fetch(const uint32_t* rows, long long plane_words, long long sample_words, int np,
                                                int n, int ih0, int img_h, int n_rows, int pitchw, uint32_t* dst,
@@ -39,17 +39,15 @@ __device__ __forceinline__ void img_rows_fetch(const uint32_t* rows, long long p
                 if (r < lo || r >= hi)
                     for (int c = pt; c >= 0 && c < pitchw; c += nthreads) dst[(pl * n_rows + r) * pitchw + c] = 0u;
     }
-    // thread 0 arms the barrier, thread (plane, row) issues that row's copy: the issue is one SIMT instruction stream for
-    // all rows instead of a serial loop in one thread (which made that thread the straggler of every trip).  A copy may
-    // complete before the expect_tx lands: the transaction count is signed, the phase needs thread 0's arrival too.
+    // The valid rows of a plane are CONTIGUOUS in global memory and in the slot: one bulk copy per plane (issuing a copy
+    // costs the issuing thread ~0.1 us whatever its size -- one copy per row made the fetch the longest part of a trip).
+    // Thread 0 arms the barrier; a copy may complete before the expect_tx lands: the transaction count is signed, the
+    // phase needs thread 0's arrival too.
     if (pt == 0) mbar_arrive_expect_tx(bar, static_cast<uint32_t>(np * (hi - lo) * pitchw * 4));
-    if (pt >= 0 && pt < np * n_rows) {
-        const int pl = (np == 1) ? 0 : pt / n_rows, r = pt - pl * n_rows;
-        if (r >= lo && r < hi)
-            bulk_load_1d(dst + (pl * n_rows + r) * pitchw,
-                         rows + pl * plane_words + n * sample_words + static_cast<long long>(ih0 + r) * pitchw,
-                         static_cast<uint32_t>(pitchw * 4), bar);
-    }
+    if (pt >= 0 && pt < np && hi > lo)
+        bulk_load_1d(dst + (pt * n_rows + lo) * pitchw,
+                     rows + pt * plane_words + n * sample_words + static_cast<long long>(ih0 + lo) * pitchw,
+                     static_cast<uint32_t>((hi - lo) * pitchw * 4), bar);
 }
 
 // One operand-tile row (pixel (pl, q) of the tile, tile row `row`): 48 bf16 = chunks 0..5 of the 128-byte row at `dst`

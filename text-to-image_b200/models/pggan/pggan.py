@@ -314,9 +314,19 @@ class PGGAN(object):
                 sc = sc or eng.scalars_dict()
                 out.append(sc[f.name])
             elif f.name == "sampler":
-                img, _, _ = self.generator(feed_dict[self.z_sample], feed_dict[self.cond_sample],
-                                           noise=get(self.cond_noise_sample))
-                out.append(img.cpu().numpy())
+                # The generator normalises per sample (no batch statistics): the sample_num images are produced in chunks
+                # of the training batch on the TRAINING engine -- a second engine for sample_num images would allocate
+                # its own discriminator and gradient buffers (tens of GB at 256 / 512 pixels) and never use them.
+                zs = np.asarray(feed_dict[self.z_sample], dtype=np.float32)
+                cs = np.asarray(feed_dict[self.cond_sample], dtype=np.float32).reshape(zs.shape[0], -1)
+                ns = get(self.cond_noise_sample)
+                ns = None if ns is None else np.asarray(ns, dtype=np.float32)
+                n, imgs = zs.shape[0], []
+                for i in range(0, n, b):
+                    idx = np.arange(i, i + b) % n                       # the last chunk wraps around to fill the batch
+                    img, _, _ = self.generator(zs[idx], cs[idx], noise=None if ns is None else ns[idx])
+                    imgs.append(img[:min(b, n - i)].cpu().numpy())
+                out.append(np.concatenate(imgs, 0))
             elif f.name == "G":
                 out.append(eng.d["img"][:b].cpu().numpy())
             elif f.name == "x_hat":
