@@ -72,11 +72,16 @@ static __device__ __noinline__ void mbar_timeout_trap(int what, uint32_t parity)
     __trap();
 }
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, int what) {
-    if (mbar_try_wait(bar, parity)) return;
-    const uint64_t t0 = global_timer_ns();
+    // %globaltimer is slow to read (hundreds of cycles): it is consulted every 1024 failed polls only -- a wait that ends
+    // normally never touches it, so a waiter wakes up as soon as its try_wait returns
     uint32_t spins = 0;
+    uint64_t t0 = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (((++spins) & 0x3ff) == 0 && global_timer_ns() - t0 > 4000000000ull) mbar_timeout_trap(what, parity);
+        if (((++spins) & 0x3ff) == 0) {
+            const uint64_t now = global_timer_ns();
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) mbar_timeout_trap(what, parity);
+        }
     }
 }
 
