@@ -835,10 +835,15 @@ class Engine:
         """lr_t of tf.train.AdamOptimizer, staged into device memory OUTSIDE any captured graph."""
         self.lr_ring.upload([lr * math.sqrt(1.0 - self.beta2 ** t) / (1.0 - self.beta1_net[net] ** t)], self.lr_t[net])
 
-    def _adam(self, net):
+    def _adam(self, net, lo=0, hi=None):
+        """TF-form Adam over parameters [lo, hi) of the flat buffer (default: all of them) + the bf16 repack."""
         n = self.d_n if net == "d" else self.g_n
-        self.K.adam_tf(self.flat[net], self.grad[net][:n], self.adam_m[net], self.adam_v[net], self.lr_t[net],
-                       self.beta1_net[net], self.beta2, ADAM_EPS, 1.0, self.packed[net])
+        hi = n if hi is None else hi
+        assert lo % 8 == 0 and 0 <= lo <= hi <= n
+        packed = self.packed[net]
+        self.K.adam_tf(self.flat[net][lo:hi], self.grad[net][lo:hi], self.adam_m[net][lo:hi], self.adam_v[net][lo:hi],
+                       self.lr_t[net], self.beta1_net[net], self.beta2, ADAM_EPS, 1.0,
+                       None if packed is None else packed[:, lo:hi])
 
     def _reduce(self, net):
         if self.world > 1:
@@ -1058,14 +1063,17 @@ class Engine:
             self._publish_scalars()
         if bucketed:
             self._run("g_a3", lambda: self._g_body_bwd(part=1))
-            with self._on_comm():                  # bucket 1 travels under the rest of the backward pass
-                self.allreduce(self.grad["g"][:self.g_split])
+            with self._on_comm():                  # bucket 1 and its Adam step travel under the rest of the backward pass
+                self.allreduce(self.grad["g"][:self.g_split])      # (which reads none of these layers' weights any more)
+                self._run("g_c1", lambda: self._adam("g", 0, self.g_split))
             self._run("g_a4", lambda: self.g_backward(self.d["gx"], part=2))
             self.allreduce(self.grad["g"][self.g_split:self.g_n])
-        else:
-            self._run("g_a3", self._g_body_bwd)
-            if self.world > 1:
-                self.allreduce(self.grad["g"][:self.g_n])
+            self._run("g_c2", lambda: self._adam("g", self.g_split, self.g_n))
+            self.join_comm()
+            return
+        self._run("g_a3", self._g_body_bwd)
+        if self.world > 1:
+            self.allreduce(self.grad["g"][:self.g_n])
         self.join_comm()
         self._run("g_c", self._g_tail_adam)
 
