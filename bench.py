@@ -469,12 +469,21 @@ def main():
     pk = peaks()
     roofline = None
     # every rank runs these steps (they contain the allreduce); they run eagerly, outside the CUDA graphs
-    # and single-stream (side stream off), so that each kernel's event pair times that kernel alone
+    # and single-stream (side and communication streams off), so that each kernel's event pair times that kernel alone.
+    # A spin kernel ahead of each step lets the host enqueue the step's ~300 launches while the device waits: the
+    # kernels then run back to back as in the replayed step (an eager launch on an idle device has its launch latency
+    # inside the event pair).
     side, eng.side_stream = eng.side_stream, None
+    comm, eng.comm_stream = eng.comm_stream, None
+
+    def profiled_step():
+        torch.cuda._sleep(int(3e7))
+        resident_step()
+
     kernels.PROFILE = []
     psteps = 2
     for _ in range(psteps):
-        resident_step()
+        profiled_step()
     barrier()
     prof = kernels.PROFILE
     timeline = None
@@ -482,11 +491,11 @@ def main():
         kernels.PROFILE = []
         _lib.TIMELINE = []
         for _ in range(psteps):
-            resident_step()
+            profiled_step()
         barrier()
         timeline, _lib.TIMELINE = _lib.TIMELINE, None
     kernels.PROFILE = None
-    eng.side_stream = side
+    eng.side_stream, eng.comm_stream = side, comm
     if rank == 0:
         rows = [(k, tag, fl, nb, a.elapsed_time(b)) for k, tag, fl, nb, a, b in prof]
         agg = {}
