@@ -293,7 +293,8 @@ def run_widen(args, rank, world, local_rank):
     if world > 1:
         dist.all_reduce(dt, op=dist.ReduceOp.MAX)
     e2e_value = B * world * n_e2e / float(dt.item())
-    h2d = 2 * sum(host[k].numel() * 4 for k in feed_keys)            # both runs stage the feed dict they are given
+    # the D run stages every feed, the G run the conditioning and z only (it reads no real image)
+    h2d = sum(host[k].numel() * 4 for k in feed_keys) + sum(host[k].numel() * 4 for k in ("cond", "z"))
     # conv_gemm roofline: eager, single stream, one event pair per launch
     pk = peaks()
     side, eng.side_stream = eng.side_stream, None

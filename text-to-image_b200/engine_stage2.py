@@ -14,6 +14,8 @@ at 64x64 (3x3 patch matrix) and 256x256 (8 padded output channels + tanh), an ou
 splits the gradient of the generator's concat buffer into its image part (ReLU mask, BatchNorm reductions) and its
 conditioning part, and affine_scale = 2 for the doubled residual branch.
 """
+import contextlib
+
 import torch
 
 from .engine import BN_DECAY, BN_EPS, Engine, Layer
@@ -455,10 +457,21 @@ class StageIIEngine(Engine):
     # ------------------------------------------------------------------ the two runs of an iteration
     def load_feed(self, x=None, x_mismatch=None, cond=None, z=None, tn_eps=None, tn_s1=None, **_):
         B, d, g = self.B, self.d, self.g
-        if x is not None:
-            d["img"][B:2 * B].copy_(x, non_blocking=True)
-        if x_mismatch is not None:
-            d["img"][2 * B:3 * B].copy_(x_mismatch, non_blocking=True)
+        if x is not None or x_mismatch is not None:
+            # 2 x B x 256 x 256 x 3 floats (100 MB at batch 64) that the D run needs only after its generator forward:
+            # they travel on the copy stream, behind the last D run's reads of these segments (not behind the G run)
+            first = x if x is not None else x_mismatch
+            cs = self.copy_stream if (self.copy_stream is not None and not torch.as_tensor(first).is_cuda) else None
+            if cs is not None:
+                if self._img_free is not None:
+                    cs.wait_event(self._img_free)
+                else:
+                    cs.wait_stream(torch.cuda.current_stream())
+            with (torch.cuda.stream(cs) if cs is not None else contextlib.nullcontext()):
+                if x is not None:
+                    d["img"][B:2 * B].copy_(x, non_blocking=True)
+                if x_mismatch is not None:
+                    d["img"][2 * B:3 * B].copy_(x_mismatch, non_blocking=True)
         if cond is not None:
             self.feed["cond"].copy_(cond, non_blocking=True)
         if z is not None:
@@ -472,15 +485,29 @@ class StageIIEngine(Engine):
         """sess.run([D_optim, D_loss, ...]) -- models/stackgan/stageII/trainer.py:131-132."""
         self.d_t += 1
         self._set_lr("d", lr, self.d_t)
-        self._run("s2_d", self._s2_d_body)
+        self._run("s2_d_gen", self._s2_d_gen)
+        if self.copy_stream is not None:        # the real / mismatching images arrive on the copy stream
+            torch.cuda.current_stream().wait_stream(self.copy_stream)
+        self._run("s2_d", self._s2_d_rest)
+        if self.copy_stream is not None:        # the fed image segments may be overwritten from here on (load_feed)
+            if self._img_free is None:
+                self._img_free = torch.cuda.Event()
+            self._img_free.record()
         self._reduce("d")
         self._run("s2_d_tail", self._s2_d_tail)
 
     def _s2_d_body(self):
-        K, d, g, B = self.K, self.d, self.g, self.B
+        self._s2_d_gen()
+        self._s2_d_rest()
+
+    def _s2_d_gen(self):
+        g = self.g
         self.grad["d"].zero_()
         g["kl_scratch"].zero_()
-        self.g2_forward(d["img"][:B], g["kl_scratch"])                                           # model.py:50-52
+        self.g2_forward(self.d["img"][:self.B], g["kl_scratch"])                                 # model.py:50-52
+
+    def _s2_d_rest(self):
+        K, d, g, B = self.K, self.d, self.g, self.B
         K.to_planes(self.feed["cond"], d["cond"])
         inv = 1.0 / self.GB
         for k, (label, weight) in enumerate(((0.0, 1.0 - self.alpha), (REAL_LABEL, 1.0), (0.0, self.alpha))):   # :53-56

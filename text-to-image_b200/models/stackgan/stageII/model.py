@@ -233,7 +233,9 @@ class ConditionalGan(object):
         ran = False
         for op, step in (("D_optim", eng.d_step), ("G_optim", eng.g_step)):
             if op in names:     # a fresh truncated-normal draw per run and per generator (stage-I :71, stage-II :73)
-                eng.load_feed(x=t(get(self.inputs)), x_mismatch=t(get(self.wrong_inputs)), cond=t(get(self.embed_inputs)),
+                img = op == "D_optim"       # the G run reads no real image (its graph ends at D(G(z)), trainer.py:136)
+                eng.load_feed(x=t(get(self.inputs)) if img else None, x_mismatch=t(get(self.wrong_inputs)) if img else None,
+                              cond=t(get(self.embed_inputs)),
                               z=t(get(self.z)), tn_eps=t(self._noise(get(self.cond_noise), b)),
                               tn_s1=t(self._noise(get(self.cond_noise_stagei), b)))
                 step(float(lr))
