@@ -27,7 +27,7 @@ namespace t2i {
 
 constexpr int kDiThreads = 320;          // warp 0 TMA, warp 1 MMA, warps 2..9 epilogue
 constexpr int kDiEpi = 256;
-constexpr int kDiStages = 4;
+constexpr int kDiStages = 3;           // K <= 256: a tile is at most four chunks; two CTAs share an SM (see the host side)
 constexpr int kDiABytes = 128 * 64 * 2;  // 128 patch pixels x 64 channels
 constexpr int kDiBChunk = 64 * 64 * 2;   // 64 x 64 weight block
 constexpr int kDiSPitch = 52;            // floats per patch-contribution row (48 used; 16-byte stores conflict-free)
@@ -37,7 +37,7 @@ struct alignas(64) DeconvImgParams {
     CUtensorMap a_map;
     CUtensorMap b_map;
     int N, P, Q, bp, tiles_per_img;
-    int lg_q, urows;
+    int lg_q, urows, slots;
     int k_chunks, last_k_steps, n_pass, np, b_kn;
     const float* bias3;
     float* out;          // fp32 NHWC [N][2P][2Q][3]
@@ -64,14 +64,14 @@ __device__ __forceinline__ void tma_load_3d(const void* tmap, uint64_t* bar, voi
         : "memory");
 }
 
-__global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_constant__ DeconvImgParams prm) {
+__global__ void __launch_bounds__(kDiThreads, 2) deconv_img_kernel(const __grid_constant__ DeconvImgParams prm) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     const int np = prm.np, kch = prm.k_chunks;
     const int H = 2 * prm.P, W = 2 * prm.Q;
-    // rings indexed by (row & (size - 1)): patch rows -- the bp rows of this tile + the carried one fit in 2*bp slots;
-    // image rows for the fused 3x3 conv -- 2*bp + 3 live rows fit in prm.urows (a power of two)
-    const int slots = 2 * prm.bp;
+    // rings: patch rows -- the bp rows of this tile + the carried one = bp + 1 slots, indexed by (row % slots);
+    // image rows for the fused 3x3 conv -- 2*bp + 3 live rows fit in prm.urows (a power of two), (row & (urows - 1))
+    const int slots = prm.slots;
     const int urows = prm.urows;
     const int lg_w = prm.lg_q + 1;
     // carve-up: [A stages][B: np x k_chunks blocks][S: slots x Q x 52 fp32][U: urows x W*3 fp32][w9 81 + b9 3 + bias 3][barriers]
@@ -206,7 +206,7 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
                 mbar_wait(&tmem_full[acc], (it >> 1) & 1, 400 + acc);
                 tc_fence_after();
                 const uint32_t taddr = tmem_base + acc * 64 + (static_cast<uint32_t>(quarter * 32) << 16);
-                float4* dst = reinterpret_cast<float4*>(s_s + ((((p0 + pl) & (slots - 1)) << prm.lg_q) + q) * kDiSPitch);
+                float4* dst = reinterpret_cast<float4*>(s_s + ((((p0 + pl) % slots) << prm.lg_q) + q) * kDiSPitch);
                 if (part == 0) {
                     uint32_t r0[32];
                     tmem_ld_32x32(taddr, r0);
@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(kDiThreads, 1) deconv_img_kernel(const __grid_
                     for (int dh = 0; dh < 2; ++dh) {
                         const int p = dh ? p_b : p_a;
                         if (dh ? (p_b < 0) : (p_a >= prm.P)) continue;
-                        const float* srow = s_s + (((p & (slots - 1)) << prm.lg_q)) * kDiSPitch + ((kh0 + 2 * dh) * 4 + kw0) * 3;
+                        const float* srow = s_s + (((p % slots) << prm.lg_q)) * kDiSPitch + ((kh0 + 2 * dh) * 4 + kw0) * 3;
                         if (qa_ok) {
                             const float* src = srow + q_a * kDiSPitch;
                             a0 += src[0]; a1 += src[1]; a2 += src[2];
@@ -416,6 +416,7 @@ extern "C" int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane
     prm.tiles_per_img = prm.P / prm.bp;
     for (prm.lg_q = 0; (1 << prm.lg_q) < prm.Q; ++prm.lg_q) {}
     for (prm.urows = 8; prm.urows < 2 * prm.bp + 3; prm.urows *= 2) {}
+    prm.slots = prm.bp + 1;
     const bool kn = w_layout == T2I_W_KN;
     const int w_n = kn ? w_cols : w_rows, w_k = kn ? w_rows : w_cols;
     if (w_n != 64 || a->c > w_k || a->c > 256 || a->c % 8 != 0 || a->pitch % 8 != 0 || a->coff % 8 != 0 || w_cols % 8 != 0)
@@ -446,16 +447,31 @@ extern "C" int t2i_deconv_img(const t2i_act* a, const void* w, long long w_plane
         if (rc != T2I_OK) return rc;
     }
     const bool fuse = w9 != nullptr;
-    const int smem_bytes = kDiStages * kDiABytes + np * prm.k_chunks * kDiBChunk + 2 * prm.bp * prm.Q * kDiSPitch * 4 +
+    const int smem_bytes = kDiStages * kDiABytes + np * prm.k_chunks * kDiBChunk + prm.slots * prm.Q * kDiSPitch * 4 +
                            (fuse ? prm.urows * 2 * prm.Q * 3 * 4 : 0) + 96 * 4 + 256 + 1024;
     if (smem_bytes > 232448) return fail(T2I_ERR_BAD_ARG, "deconv_img: shared memory plan of %d bytes", smem_bytes);
-    static bool attr_done = false;
-    if (!attr_done) {
-        cudaError_t ce = cudaFuncSetAttribute(deconv_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 232448);
+    static int attr_bytes = 0;      // the opt-in size is kept at what the plan needs: the occupancy the driver grants follows it
+    if (attr_bytes != smem_bytes) {
+        cudaError_t ce = cudaFuncSetAttribute(deconv_img_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
         if (ce != cudaSuccess) return fail(T2I_ERR_CUDA, "cudaFuncSetAttribute: %s", cudaGetErrorString(ce));
-        attr_done = true;
+        // two CTAs of ~110 KB per SM need the whole unified L1 / shared array as shared memory
+        cudaFuncSetAttribute(deconv_img_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        attr_bytes = smem_bytes;
     }
-    const int grid = prm.N < num_sms() ? prm.N : num_sms();
+    // The gather / 3x3 epilogue runs one phase at a time on eight warps (IPC < 1): at the step's sizes the plan is ~110 KB
+    // and TWO CTAs share an SM, each sweeping its own images -- one CTA's epilogue overlaps the other's loads and MMAs.
+    // Decided from the shared-memory plan (320 threads x 84 registers and 128 TMEM columns per CTA fit twice); the
+    // occupancy query answers 1 for this kernel, yet two CTAs per SM measured 64 -> 47 us (g.up4 forward) and 35 -> 27 us
+    // (d.h0 input-gradient) against one per SM, i.e. they do run side by side.
+    int per_sm = 1;
+    {
+        int dev = 0, sm_bytes = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sm_bytes, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+        if (2 * (smem_bytes + 1024) <= sm_bytes) per_sm = 2;
+    }
+    const int slots_total = per_sm * num_sms();
+    const int grid = prm.N < slots_total ? prm.N : slots_total;
     cudaError_t le = launch_pdl(deconv_img_kernel, grid, kDiThreads, smem_bytes, stream, prm);
     if (le != cudaSuccess) return fail(T2I_ERR_CUDA, "deconv_img_kernel launch: %s", cudaGetErrorString(le));
     return check_launch("deconv_img_kernel");
