@@ -168,7 +168,9 @@ int t2i_tanh_c3_bwd(const float* img, const float* dimg, void* dlogits8, long lo
 
 /* g_net's last conv 3->3 k3 s1 + tanh (model.py:219-221), direct; and its backward
  * (dw, db, dx_sum are accumulated: dx_sum[c] += sum of dx over pixels = bias gradient of the
- * preceding transposed conv; may be NULL). */
+ * preceding transposed conv; may be NULL).  The backward entry launches one kernel per requested result:
+ * dx != NULL -> the input gradient (+ dx_sum); dw != NULL (with db, x) -> the weight / bias gradients; a
+ * caller may ask for the two separately (the input gradient is on the critical path, the other is not). */
 int t2i_conv3x3_c3_tanh_fwd(const float* x, const float* w, const float* b, float* y, int n, int h, int wd,
                             void* stream);
 int t2i_conv3x3_c3_tanh_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,

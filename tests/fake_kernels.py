@@ -282,11 +282,13 @@ def conv3x3_c3_tanh_bwd(x, w, y, dy, dx, dw, db, dx_sum=None):
     v = F.conv2d(xd.permute(0, 3, 1, 2), wd.permute(3, 2, 0, 1), bd, padding=1).permute(0, 2, 3, 1)
     dl = dy.double() * (1 - y.double() ** 2)
     gx, gw, gb = torch.autograd.grad((v * dl).sum(), [xd, wd, bd])
-    dx.copy_(gx)
-    dw += gw.reshape(dw.shape)
-    db += gb
-    if dx_sum is not None:
-        dx_sum += gx.sum((0, 1, 2))
+    if dx is not None:
+        dx.copy_(gx)
+        if dx_sum is not None:
+            dx_sum += gx.sum((0, 1, 2))
+    if dw is not None:
+        dw += gw.reshape(dw.shape)
+        db += gb
 
 
 def colsum(src, out):

@@ -282,36 +282,46 @@ __global__ void conv3x3_c3_tanh_fwd_kernel(const float* __restrict__ x, const fl
     }
 }
 // backward: dl = dy * (1 - y^2); dx = conv^T(dl); dw[kh,kw,ci,co] += sum x[.+k-1, ci] dl[., co]; db += sum dl.
-// A block walks tiles of kC9R image rows: x and dl (with a one-pixel halo) are staged in shared memory once, each
-// thread then forms dx and its 81 weight-gradient products for its pixels from shared memory; the weight / bias
-// sums stay in registers across all tiles of the block and are reduced once at the end.
+// Two instantiations share the staging code: WANT_DX (the input gradient, on the critical path of the backward pass:
+// the 81 weights live in registers, nothing else does, several blocks per SM) and WANT_DW (the 81 weight-gradient sums
+// live in registers across all tiles of the block and are reduced once at the end; runs beside the chain).  One kernel
+// doing both kept 162 values per thread, ran one block per SM and read every weight from shared memory per use (60 us).
+// A block walks tiles of kC9R image rows: x / dl (with a one-pixel halo) are staged in shared memory once.
 constexpr int kC9R = 8;
-__global__ void __launch_bounds__(256) conv3x3_c3_tanh_bwd_kernel(const float* __restrict__ x, const float* __restrict__ w,
-                                                                  const float* __restrict__ y, const float* __restrict__ dy,
-                                                                  float* dx, float* dw, float* db, float* dx_sum, int n, int h,
-                                                                  int wd) {
+template <bool WANT_DX, bool WANT_DW>
+__global__ void __launch_bounds__(WANT_DW ? 128 : 256) conv3x3_c3_tanh_bwd_kernel(
+    const float* __restrict__ x, const float* __restrict__ w, const float* __restrict__ y, const float* __restrict__ dy, float* dx,
+    float* dw, float* db, float* dx_sum, int n, int h, int wd) {
     pdl_launch_dependents();
     pdl_wait();
-    extern __shared__ float s_c9[];               // x tile [(R+2)][(wd+2)*3], dl tile the same, then w[81], red[87]
+    extern __shared__ float s_c9[];               // x tile [(R+2)][(wd+2)*3] (WANT_DW), dl tile the same, then w[81], red[87]
     const int tw = (wd + 2) * 3;
     float* s_x = s_c9;
-    float* s_dl = s_x + (kC9R + 2) * tw;
+    float* s_dl = s_x + (WANT_DW ? (kC9R + 2) * tw : 0);
     float* sw = s_dl + (kC9R + 2) * tw;
     float* sred = sw + 81;
     if (threadIdx.x < 81) sw[threadIdx.x] = w[threadIdx.x];
     if (threadIdx.x < 87) sred[threadIdx.x] = 0.f;
-    float gw[81];
+    float gw[WANT_DW ? 81 : 1];
+    float wr[WANT_DX ? 81 : 1];
     float gb[3] = {0.f, 0.f, 0.f};
     float gs[3] = {0.f, 0.f, 0.f};
+    if (WANT_DW) {
 #pragma unroll
-    for (int j = 0; j < 81; ++j) gw[j] = 0.f;
+        for (int j = 0; j < 81; ++j) gw[j] = 0.f;
+    }
+    if (WANT_DX) {
+        __syncthreads();
+#pragma unroll
+        for (int j = 0; j < 81; ++j) wr[j] = sw[j];
+    }
     const int groups = (h + kC9R - 1) / kC9R;
     for (int blk = blockIdx.x; blk < n * groups; blk += gridDim.x) {
         const int b = blk / groups, r0 = (blk - b * groups) * kC9R;
         const long long ibase = (long long)b * h * wd * 3;
         __syncthreads();
-        // staging: 8 elements x 3 tensors per thread with all loads issued before the first use (one memory latency
-        // per tile; a one-load-at-a-time loop left the block, 8 warps on the SM, waiting 8 latencies)
+        // staging: 8 elements per tensor and thread with all loads issued before the first use (one memory latency per
+        // trip; a one-load-at-a-time loop left the block waiting 8 latencies)
         const int total = (kC9R + 2) * tw;
         for (int base = 0; base < total; base += blockDim.x * 8) {
             float xv[8], yv[8], dv[8];
@@ -322,7 +332,7 @@ __global__ void __launch_bounds__(256) conv3x3_c3_tanh_bwd_kernel(const float* _
                 const int ih = r0 - 1 + r, iw3 = cc - 3;          // float index inside the image row
                 const bool ok = i < total && ih >= 0 && ih < h && iw3 >= 0 && iw3 < wd * 3;
                 const long long e = ok ? ibase + (long long)ih * wd * 3 + iw3 : 0;
-                xv[u] = ok ? __ldg(x + e) : 0.f;
+                xv[u] = (WANT_DW && ok) ? __ldg(x + e) : 0.f;
                 yv[u] = ok ? __ldg(y + e) : 0.f;
                 dv[u] = ok ? __ldg(dy + e) : 0.f;
             }
@@ -330,7 +340,7 @@ __global__ void __launch_bounds__(256) conv3x3_c3_tanh_bwd_kernel(const float* _
             for (int u = 0; u < 8; ++u) {
                 const int i = base + u * blockDim.x + threadIdx.x;
                 if (i < total) {
-                    s_x[i] = xv[u];
+                    if (WANT_DW) s_x[i] = xv[u];
                     s_dl[i] = dv[u] * (1.f - yv[u] * yv[u]);
                 }
             }
@@ -341,50 +351,65 @@ __global__ void __launch_bounds__(256) conv3x3_c3_tanh_bwd_kernel(const float* _
             const int ow = i % wd, lr = i / wd;                   // pixel (r0 + lr, ow); halo offset +1 in both directions
             const float* cx = s_x + (lr + 1) * tw + (ow + 1) * 3;
             const float* cd = s_dl + (lr + 1) * tw + (ow + 1) * 3;
-            const float d0 = cd[0], d1 = cd[1], d2 = cd[2];       // dl of this pixel as an OUTPUT position
-            gb[0] += d0; gb[1] += d1; gb[2] += d2;
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+            if (WANT_DW) {
+                d0 = cd[0]; d1 = cd[1]; d2 = cd[2];               // dl of this pixel as an OUTPUT position
+                gb[0] += d0; gb[1] += d1; gb[2] += d2;
+            }
             float g0 = 0.f, g1 = 0.f, g2 = 0.f;
 #pragma unroll
             for (int kh = 0; kh < 3; ++kh) {
 #pragma unroll
                 for (int kw = 0; kw < 3; ++kw) {
                     const int off = (kh - 1) * tw + (kw - 1) * 3;
-                    const float* wp = sw + (kh * 3 + kw) * 9;
-                    // input read by this output through tap (kh, kw): weight gradient (zero halo = padding)
-                    const float x0 = cx[off], x1 = cx[off + 1], x2 = cx[off + 2];
-                    float* gp = gw + (kh * 3 + kw) * 9;
-                    gp[0] += x0 * d0; gp[1] += x0 * d1; gp[2] += x0 * d2;
-                    gp[3] += x1 * d0; gp[4] += x1 * d1; gp[5] += x1 * d2;
-                    gp[6] += x2 * d0; gp[7] += x2 * d1; gp[8] += x2 * d2;
-                    // output that reads this pixel as input through tap (kh, kw): input gradient
-                    const float e0 = cd[-off], e1 = cd[-off + 1], e2 = cd[-off + 2];
-                    g0 += e0 * wp[0] + e1 * wp[1] + e2 * wp[2];
-                    g1 += e0 * wp[3] + e1 * wp[4] + e2 * wp[5];
-                    g2 += e0 * wp[6] + e1 * wp[7] + e2 * wp[8];
+                    if (WANT_DW) {
+                        // input read by this output through tap (kh, kw): weight gradient (zero halo = padding)
+                        const float x0 = cx[off], x1 = cx[off + 1], x2 = cx[off + 2];
+                        float* gp = gw + (kh * 3 + kw) * 9;
+                        gp[0] += x0 * d0; gp[1] += x0 * d1; gp[2] += x0 * d2;
+                        gp[3] += x1 * d0; gp[4] += x1 * d1; gp[5] += x1 * d2;
+                        gp[6] += x2 * d0; gp[7] += x2 * d1; gp[8] += x2 * d2;
+                    }
+                    if (WANT_DX) {
+                        // output that reads this pixel as input through tap (kh, kw): input gradient
+                        const float* wp = wr + (kh * 3 + kw) * 9;
+                        const float e0 = cd[-off], e1 = cd[-off + 1], e2 = cd[-off + 2];
+                        g0 += e0 * wp[0] + e1 * wp[1] + e2 * wp[2];
+                        g1 += e0 * wp[3] + e1 * wp[4] + e2 * wp[5];
+                        g2 += e0 * wp[6] + e1 * wp[7] + e2 * wp[8];
+                    }
                 }
             }
-            float* dst = dx + ibase + ((long long)(r0 + lr) * wd + ow) * 3;
-            dst[0] = g0; dst[1] = g1; dst[2] = g2;
-            gs[0] += g0; gs[1] += g1; gs[2] += g2;
+            if (WANT_DX) {
+                float* dst = dx + ibase + ((long long)(r0 + lr) * wd + ow) * 3;
+                dst[0] = g0; dst[1] = g1; dst[2] = g2;
+                gs[0] += g0; gs[1] += g1; gs[2] += g2;
+            }
         }
     }
     const int lane = threadIdx.x & 31;
+    if (WANT_DW) {
 #pragma unroll
-    for (int j = 0; j < 81; ++j) {
-        const float t = warp_sum(gw[j]);
-        if (lane == 0) atomicAdd(&sred[j], t);
+        for (int j = 0; j < 81; ++j) {
+            const float t = warp_sum(gw[j]);
+            if (lane == 0) atomicAdd(&sred[j], t);
+        }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-        const float t = warp_sum(gb[c]);
-        if (lane == 0) atomicAdd(&sred[81 + c], t);
-        const float t2 = warp_sum(gs[c]);
-        if (lane == 0) atomicAdd(&sred[84 + c], t2);
+        if (WANT_DW) {
+            const float t = warp_sum(gb[c]);
+            if (lane == 0) atomicAdd(&sred[81 + c], t);
+        }
+        if (WANT_DX) {
+            const float t2 = warp_sum(gs[c]);
+            if (lane == 0) atomicAdd(&sred[84 + c], t2);
+        }
     }
     __syncthreads();
-    if (threadIdx.x < 81) atomicAdd(&dw[threadIdx.x], sred[threadIdx.x]);
-    else if (threadIdx.x < 84) atomicAdd(&db[threadIdx.x - 81], sred[threadIdx.x]);
-    else if (threadIdx.x < 87 && dx_sum != nullptr) atomicAdd(&dx_sum[threadIdx.x - 84], sred[threadIdx.x]);
+    if (WANT_DW && threadIdx.x < 81) atomicAdd(&dw[threadIdx.x], sred[threadIdx.x]);
+    else if (WANT_DW && threadIdx.x < 84) atomicAdd(&db[threadIdx.x - 81], sred[threadIdx.x]);
+    else if (WANT_DX && threadIdx.x >= 84 && threadIdx.x < 87 && dx_sum != nullptr) atomicAdd(&dx_sum[threadIdx.x - 84], sred[threadIdx.x]);
 }
 
 // ------------------------------------------------------------------------------------------
@@ -1259,13 +1284,26 @@ extern "C" int t2i_conv3x3_c3_tanh_fwd(const float* x, const float* w, const flo
 }
 extern "C" int t2i_conv3x3_c3_tanh_bwd(const float* x, const float* w, const float* y, const float* dy, float* dx,
                                        float* dw, float* db, float* dx_sum, int n, int h, int wd, void* stream) {
-    const size_t shm = ((size_t)2 * (kC9R + 2) * (wd + 2) * 3 + 81 + 87) * sizeof(float);
-    if (shm > 48 * 1024) return fail(T2I_ERR_BAD_ARG, "conv3x3_c3_tanh_bwd: image rows too wide (%d)", wd);
+    // dx != NULL: the input gradient (+ dx_sum); dw != NULL (with db): the weight / bias gradients; both: two launches
+    if (dx == nullptr && dw == nullptr) return fail(T2I_ERR_BAD_ARG, "conv3x3_c3_tanh_bwd: neither dx nor dw requested");
+    if (dw != nullptr && (db == nullptr || x == nullptr)) return fail(T2I_ERR_BAD_ARG, "conv3x3_c3_tanh_bwd: dw needs db and x");
+    const size_t tile = (size_t)(kC9R + 2) * (wd + 2) * 3;
+    if ((2 * tile + 81 + 87) * sizeof(float) > 48 * 1024) return fail(T2I_ERR_BAD_ARG, "conv3x3_c3_tanh_bwd: image rows too wide (%d)", wd);
     const long long groups = (long long)n * ceil_div(h, kC9R);
-    const long long cap = (long long)num_sms();      // 214 registers x 256 threads: one block per SM, ~14 tiles each
-    launch_ew(conv3x3_c3_tanh_bwd_kernel, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256), shm, STREAM, x, w, y, dy, dx, dw, db, dx_sum,
-                                                                                           n, h, wd);
-    return check_launch("conv3x3_c3_tanh_bwd");
+    if (dx != nullptr) {
+        const long long cap = 4LL * num_sms();
+        launch_ew(conv3x3_c3_tanh_bwd_kernel<true, false>, dim3((unsigned)(groups < cap ? groups : cap)), dim3(256),
+                  (tile + 81 + 87) * sizeof(float), STREAM, x, w, y, dy, dx, dw, db, dx_sum, n, h, wd);
+        int rc = check_launch("conv3x3_c3_tanh_bwd (dx)");
+        if (rc != T2I_OK) return rc;
+    }
+    if (dw != nullptr) {
+        const long long cap = 4LL * num_sms();      // 127 registers x 128 threads: four blocks per SM
+        launch_ew(conv3x3_c3_tanh_bwd_kernel<false, true>, dim3((unsigned)(groups < cap ? groups : cap)), dim3(128),
+                  (2 * tile + 81 + 87) * sizeof(float), STREAM, x, w, y, dy, dx, dw, db, dx_sum, n, h, wd);
+        return check_launch("conv3x3_c3_tanh_bwd (dw)");
+    }
+    return T2I_OK;
 }
 extern "C" int t2i_colsum(const void* src, long long ps, int np, long long rows, int c, int pitch, int coff, float* out,
                           void* stream) {

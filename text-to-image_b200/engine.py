@@ -679,7 +679,9 @@ class Engine:
 
         if part == 2:
             return self._g_backward_tail(res_bwd, bn_bwd, V)
-        K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], gl["c9"].gw, gl["c9"].gb, gl["t3"].gb)
+        K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, g["d_u4"], None, None, gl["t3"].gb)     # the chain needs d_u4
+        with self._side():
+            K.conv3x3_c3_tanh_bwd(g["u4"], gl["c9"].w, img, d_img, None, gl["c9"].gw, gl["c9"].gb)
         # the 4x4/s2 patches of d_u4 are formed on chip by both kernels from its padded bf16 rows (no patch matrix in HBM)
         K.img_to_rows(g["d_u4"], g["d_u4_rows"])
         du4 = K.ImgPatches(g["d_u4_rows"], IMG)

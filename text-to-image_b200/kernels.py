@@ -309,8 +309,12 @@ def conv3x3_c3_tanh_fwd(x, w, b, y):
 
 
 def conv3x3_c3_tanh_bwd(x, w, y, dy, dx, dw, db, dx_sum=None):
+    """dx (+ dx_sum) and / or dw, db of tanh(conv3x3(x) + b): pass dx=None or dw=db=None to get one of the two kernels
+    alone (the input gradient is on the backward pass's critical path, the weight gradient is not)."""
     n, h, wd, _ = x.shape
-    _lib.call("t2i_conv3x3_c3_tanh_bwd", _f32(x), _f32(w), _f32(y), _f32(dy), _f32(dx), _f32(dw), _f32(db),
+    for t in (x, w, y, dy, dx, dw, db, dx_sum):
+        assert t is None or (t.dtype == torch.float32 and t.is_contiguous())
+    _lib.call("t2i_conv3x3_c3_tanh_bwd", _f32(x), _f32(w), _f32(y), _f32(dy), _p(dx), _p(dw), _p(db),
               _p(dx_sum), n, h, wd, _stream())
 
 

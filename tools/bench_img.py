@@ -45,6 +45,7 @@ def main():
     dw0, dwt3 = torch.zeros(1, 128, 64, **f32), torch.zeros(1, 64, 128, **f32)
     stat_a, stat_b = torch.zeros(128, **f32), torch.zeros(128, **f32)
     cond, wms, bms, ms = torch.randn(B, 1024, **f32), torch.randn(256, 1024, **f32) * 0.03, torch.zeros(256, **f32), torch.zeros(B, 256, **f32)
+    c9_dx, c9_dw, c9_db, c9_sum = torch.zeros(B, 64, 64, 3, **f32), torch.zeros(81, **f32), torch.zeros(3, **f32), torch.zeros(3, **f32)
     V = K.View
     MB = 1e6
     rows4 = torch.zeros(1, 4 * B, 64, K.img_row_pitch(64), **bf)
@@ -66,6 +67,8 @@ def main():
         ("up4_dgrad_B", lambda: K.conv_gemm(K.CONV_K4S2, 4, 0, PG, wt3, V(d_a0, 0, B), w_kn=True, mask=V(a0, 0, B), mask_kind=K.MASK_RELU,
                                             stat_sum=stat_a, stat_dot=stat_b, stat_x=V(a0, B, B)), (B * RB + 3 * B * 1024 * 256) / MB),
         ("up4_wgrad_B", lambda: K.wgrad_img(PG, V(a0, 0, B), dwt3, 2), (B * RB + B * 1024 * 256) / MB),
+        ("c9_bwd_dx_B", lambda: K.conv3x3_c3_tanh_bwd(u4, w9.view(3, 3, 3, 3), out, gx, c9_dx, None, None, c9_sum), (3 * B * 12288 * 4) / MB),
+        ("c9_bwd_dw_B", lambda: K.conv3x3_c3_tanh_bwd(u4, w9.view(3, 3, 3, 3), out, gx, None, c9_dw, c9_db), (3 * B * 12288 * 4) / MB),
         ("floor_tiny_kernel", lambda: K.scale_rows(cond[:4], bms[:4], ms[:4, :1024 // 4 * 0 + 256][:, :256].contiguous() if False else cond[4:8]), 0.03),
         ("dense_f32", lambda: K.dense_f32(cond, wms, bms, ms, act=K.ACT_LRELU), (B * 1024 * 4 + 256 * 1024 * 4 + B * 256 * 4) / MB),
     ]
