@@ -473,14 +473,20 @@ def main():
     roofline = None
     # every rank runs these steps (they contain the allreduce); they run eagerly, outside the CUDA graphs
     # and single-stream (side and communication streams off), so that each kernel's event pair times that kernel alone.
-    # A spin kernel ahead of each step lets the host enqueue the step's ~300 launches while the device waits: the
-    # kernels then run back to back as in the replayed step (an eager launch on an idle device has its launch latency
-    # inside the event pair).
+    # Ahead of each profiled step the device gets a spin kernel and three replayed (graph) steps: while they run, the
+    # host enqueues the eager step's ~300 launches, which then execute back to back (an eager launch on an idle device
+    # has its launch latency inside the event pair) and at the SUSTAINED power state of the replayed steps (after an
+    # idle spin alone the first launches would run at boost clocks and flatter the fraction of the sustained peak).
     side, eng.side_stream = eng.side_stream, None
     comm, eng.comm_stream = eng.comm_stream, None
 
     def profiled_step():
-        torch.cuda._sleep(int(3e7))
+        prof_list, tl_list = kernels.PROFILE, _lib.TIMELINE
+        kernels.PROFILE, _lib.TIMELINE = None, None
+        torch.cuda._sleep(int(2e7))
+        for _ in range(3):
+            resident_step()
+        kernels.PROFILE, _lib.TIMELINE = prof_list, tl_list
         resident_step()
 
     kernels.PROFILE = []
