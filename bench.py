@@ -299,8 +299,10 @@ def run_widen(args, rank, world, local_rank):
     pk = peaks()
     side, eng.side_stream = eng.side_stream, None
     comm, eng.comm_stream = getattr(eng, "comm_stream", None), None
+    torch.cuda._sleep(int(2e7))          # the host enqueues the eager step while the device runs the spin kernel and two
+    for _ in range(2):                   # replayed steps: its launches then run back to back at the sustained power state
+        step()
     kernels.PROFILE = []
-    torch.cuda._sleep(int(3e7))          # the host enqueues the step while the device waits: launches run back to back
     step()
     barrier()
     prof, kernels.PROFILE = kernels.PROFILE, None
