@@ -93,8 +93,10 @@ typedef struct {
     const void* x_img;
 } t2i_conv_gemm_desc;
 int t2i_conv_gemm(const t2i_conv_gemm_desc* d, void* stream);
-/* Development aid (T2I_TIMELINE=1 in the environment): %globaltimer stamps CTA 0 of the LAST t2i_conv_gemm launch left
- * at the hand-over points of its first 64 tiles, [tile][8 events] (csrc/conv_gemm.cu); synchronises the device. */
+/* Development aid (a library built with -DT2I_TIMELINE_BUILD, T2I_TIMELINE=1 in the environment; the default build
+ * records nothing): %globaltimer stamps CTA 0 of the last 32 t2i_conv_gemm launches left at the hand-over points of its
+ * first 64 tiles -- 32 regions (one per launch, round robin) of [64 tiles][8 events], row 63 holding kernel-level
+ * stamps (csrc/conv_gemm.cu, tools/conv_timeline.py); count <= 32 * 512 values from region 0 on; synchronises. */
 int t2i_debug_timeline(unsigned long long* host_dst, int count);
 
 /* Weight gradient of the same three conv forms on tcgen05 (both operands MN-major, contraction
