@@ -83,7 +83,8 @@ def _worker(rank, world, port, out, g_buckets=None):
     # sync_bn test; here: the bucketed all-reduce (g_buckets = 2) must produce the same flat gradient as one call
     if rank == 0:
         torch.save({"worst": worst, "smax": smax, "calls": calls, "same": same, "g_flat": flat, "g_n": eng.g_n,
-                    "g_split": eng.g_split, "kt": float(eng.kt), "kt_ref": float(ref.kt)}, out)
+                    "g_split": eng.g_split, "kt": float(eng.kt), "kt_ref": float(ref.kt),
+                    "p_flat": eng.flat["g"].clone(), "m_flat": eng.adam_m["g"].clone(), "v_flat": eng.adam_v["g"].clone()}, out)
     dist.destroy_process_group()
 
 
@@ -240,6 +241,9 @@ def test_two_rank_bucketed_g_allreduce_matches_single_call(tmp_path):
     assert two["calls"][3] == two["g_split"] and two["calls"][3] + two["calls"][4] == one["calls"][3]
     assert 0.5 < two["g_split"] / two["g_n"] < 0.8          # the early bucket carries most of the bytes
     assert two["same"] and torch.equal(one["g_flat"], two["g_flat"])
+    # ... and the per-bucket Adam steps (the first one right behind its all-reduce) leave the same parameters and slots
+    for k in ("p_flat", "m_flat", "v_flat"):
+        assert torch.equal(one[k], two[k]), k
 
 
 def _worker_pggan(rank, world, port, out):

@@ -119,3 +119,34 @@ def test_iteration_matches_oracle(np_):
         newp = eng.get_params_tf()
         for n in ("g_net/BatchNorm_9/moving_mean", "g_net/BatchNorm/moving_variance", "g_net/BatchNorm_4/moving_mean"):
             assert rel(newp[n], p[n]) < (1e-9 if np_ == 0 else 1e-4), n
+
+
+def test_losses_are_final_when_published():
+    """d_step / g_step compute the loss scalars BEFORE the rest of the run (tangent pass + weight gradients; both backward
+    passes) so that a D_loss / G_loss fetch can return early: the values at that point must be the run's final ones, and
+    the order of the phases must be the documented one"""
+    cfg = O.OracleCfg(**TINY)
+    eng = make_engine(cfg, np_=0)
+    eng.set_params_tf(boosted_params(cfg))
+    feed = O.make_feed(cfg, 11, torch.float64)
+    eng.load_feed(**{k: feed[k] for k in ("x", "x_mismatch", "cond", "z", "epsilon")}, tn_eps=feed["tn_eps"])
+    order, snap = [], {}
+    real_run = eng._run
+
+    def run(name, body):
+        real_run(name, body)
+        order.append(name)
+        if name in ("d_b", "g_b"):
+            snap[name] = eng.scalars.clone()
+
+    eng._run = run
+    eng.d_step(cfg.d_lr)
+    assert order == ["d_a1", "d_a", "d_b", "d_a2", "d_c"], order
+    assert torch.equal(snap["d_b"], eng.scalars)            # nothing after d_b touches the scalars of the D run
+    del order[:]
+    eng.load_feed(tn_eps=feed["tn_eps_g"] if "tn_eps_g" in feed else feed["tn_eps"])
+    eng.g_step(cfg.g_lr)
+    assert order == ["g_a1", "g_a2", "g_b", "g_a3", "g_c"], order
+    assert torch.equal(snap["g_b"], eng.scalars)
+    sc = eng.scalars_dict()
+    assert all(v == v for v in sc.values())
