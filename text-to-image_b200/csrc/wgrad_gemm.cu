@@ -142,10 +142,11 @@ __global__ void __launch_bounds__(IMG ? kWThreadsImg : kWThreads, 1) wgrad_gemm_
     };
     auto decode = [&](int w) {
         Work k;
-        if (prm.tap_fast) {   // single channel tile, operands far larger than L2: every tap of a pixel range at once
+        if (prm.tap_fast) {   // operands larger than L2: every (tap, channel tile) item of a pixel range before the next range
             k.job = w % prm.jobs; w /= prm.jobs;
+            k.cit = w % prm.tiles_ci; w /= prm.tiles_ci;
+            k.cot = w % prm.tiles_co; w /= prm.tiles_co;
             k.split = w;
-            k.cit = k.cot = 0;
         } else {
             k.split = w % prm.splits; w /= prm.splits;
             k.cit = w % prm.tiles_ci; w /= prm.tiles_ci;
@@ -638,10 +639,14 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
     prm.jobs = prm.tt.n_phases * prm.tt.taps_per_phase;
     prm.n_pass = (d->np == 2) ? 3 : 1;
     const int tiles = prm.jobs * prm.tiles_co * prm.tiles_ci;
-    // one channel tile, several taps, and operands that cannot stay in L2 between taps (each tap is a full pass over
-    // x and dy): order the work taps-fastest so that a pixel range is fetched from HBM once
+    // Several taps and operands that cannot stay in L2 between them (each (tap, channel tile) item is a pass over its x /
+    // dy slices): order the work PIXEL-RANGE-MAJOR -- all items of a range before the next range -- so that a range is
+    // fetched from HBM once and shared through L2.  (Split-fastest order re-read the 4B-batch operands of d_net's 4x4 /
+    // stride-2 layers 2.5-2.7 times: 570 MB of DRAM traffic for 210 MB of tensors, profiles/r02_traffic.json.)
     const long long operand_bytes = (long long)prm.k_blocks * kWK * (x.c + dy.c) * 2 * d->np;
-    prm.tap_fast = (prm.tiles_co * prm.tiles_ci == 1 && prm.jobs > 1 && operand_bytes > (64ll << 20)) ? 1 : 0;
+    const int chan_tiles = prm.tiles_co * prm.tiles_ci;
+    static const bool allow_range_major = [] { const char* e = getenv("T2I_WGRAD_RANGE_MAJOR"); return !(e && e[0] == '0'); }();
+    prm.tap_fast = (prm.jobs > 1 && operand_bytes > (64ll << 20) && (chan_tiles == 1 || allow_range_major)) ? 1 : 0;
     int splits = d->split_k;
     if (splits <= 0) {
         // Cost model: the launch runs in ceil(tiles * s / workers) waves; one wave costs the K blocks of a split
@@ -659,7 +664,7 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
             }
         }
     }
-    if (prm.tap_fast && d->split_k <= 0) {
+    if (prm.tap_fast && d->split_k <= 0 && chan_tiles == 1) {
         // short pixel ranges (~96 K blocks = 6144 pixels) so that the taps of a range, launched side by side, stay
         // within L2 reach of each other; round the item count up to whole waves
         const int workers = num_sms();
@@ -669,6 +674,13 @@ extern "C" int t2i_wgrad_gemm(const t2i_wgrad_desc* d, void* stream_) {
         const long long waves = ceil_div((int)(sct * prm.jobs), workers);
         sct = waves * workers / prm.jobs;
         if (sct >= 1) splits = (int)sct;
+    } else if (prm.tap_fast && d->split_k <= 0) {
+        // several channel tiles: the cost model's split count stands (it has counted the waves); only if a range's
+        // operands would not stay in L2 while its items run (a few waves) are the ranges made shorter (<= ~48 MB each)
+        long long sct = ceil_div((int)(operand_bytes >> 20), 48);
+        const long long cap = prm.k_blocks / 16 > 0 ? prm.k_blocks / 16 : 1;
+        if (sct > cap) sct = cap;
+        if (sct > splits) splits = (int)sct;
     }
     if (splits > prm.k_blocks) splits = prm.k_blocks;
     prm.kb_per_split = ceil_div(prm.k_blocks, splits);
