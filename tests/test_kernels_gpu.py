@@ -733,3 +733,31 @@ def test_resample_blend_and_image_padding_kernels(K, np_):
     bg = torch.zeros(3, 8, 8, 3, device="cuda")
     K.c8_to_img(c8g, bg)
     check_close("c8_to_img", bg.cpu(), back, 1e-6, 1.0)
+
+
+def test_wgrad_range_major_order_large_operands(K):
+    """Operands beyond L2 (100 MB) with two channel tiles: wgrad_gemm runs its work pixel-range-major (all (tap, channel
+    tile) items of a range before the next range).  Too large for the fp64 CPU restatement: the checker is torch's fp32
+    conv weight gradient on the device (TF32 off) on the same bf16 values."""
+    import torch.nn.functional as F
+    N, H, W, ci, co = 512, 16, 16, 256, 512
+    gen = torch.Generator(device="cuda").manual_seed(7)
+    x = torch.randn(1, N, H, W, ci, device="cuda", generator=gen).bfloat16()
+    dy = (torch.randn(1, N, H // 2, W // 2, co, device="cuda", generator=gen) * 0.1).bfloat16()
+    dw = torch.zeros(16, co, ci, device="cuda")
+    K.wgrad_gemm(K.CONV_K4S2, 4, K.View(x), K.View(dy), dw)
+    torch.cuda.synchronize()
+    tf32 = torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cudnn.allow_tf32 = torch.backends.cuda.matmul.allow_tf32 = False
+    try:
+        xc = x[0].float().permute(0, 3, 1, 2).contiguous()
+        gc = dy[0].float().permute(0, 3, 1, 2).contiguous()
+        ref = torch.zeros(co, ci, 4, 4, device="cuda")
+        for lo in range(0, N, 64):          # chunks keep cuDNN's workspace small; fp32 accumulation across them
+            ref += torch.nn.grad.conv2d_weight(xc[lo:lo + 64], (co, ci, 4, 4), gc[lo:lo + 64], stride=2, padding=1)
+    finally:
+        torch.backends.cudnn.allow_tf32, torch.backends.cuda.matmul.allow_tf32 = tf32
+    ref = ref.permute(2, 3, 0, 1).reshape(16, co, ci)          # [tap = kh*4 + kw][co][ci]
+    err = float((dw - ref).abs().max() / ref.abs().max())
+    print("[wgrad range-major, 100 MB operands] max abs err / max |dw| = %.2e" % err)
+    assert err < 1e-4, "range-major wgrad: max abs err / max |dw| = %.3e" % err      # measured 2.05e-5 (fp32 accumulation order)
